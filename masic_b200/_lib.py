@@ -1,0 +1,93 @@
+"""ctypes binding of libmasic_b200.so (the C ABI declared in include/masic_b200.h).
+
+There is deliberately no fallback: if the shared object is missing or a call returns a
+non-zero status the caller gets an exception.  Nothing in this module computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libmasic_b200.so"
+
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+GDN_NONE, GDN_FWD, GDN_INV = 0, 1, 2
+CONV, DECONV_S2, DECONV_S2_SUBPIX = 0, 1, 2
+
+_ERRORS = {-1: "MASIC_EINVAL (bad argument)", -2: "MASIC_ENOSUP (not implemented)",
+           -3: "MASIC_EDRIVER (cuTensorMapEncodeTiled unavailable or failed)"}
+
+
+class MasicError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int), ("ksize", C.c_int), ("stride", C.c_int), ("tap_mask", C.c_uint32),
+        ("n", C.c_int), ("h_in", C.c_int), ("w_in", C.c_int),
+        ("c_in", C.c_int), ("c_out", C.c_int), ("c_out_pad", C.c_int), ("n_tile", C.c_int),
+        ("in_", C.c_void_p), ("in_cpitch", C.c_int), ("in_coff", C.c_int),
+        ("w_packed", C.c_void_p),
+        ("bias", C.c_void_p),
+        ("out", C.c_void_p), ("out_cpitch", C.c_int), ("out_coff", C.c_int), ("out_fp32", C.c_int),
+        ("act", C.c_uint8 * 32),
+        ("gdn", C.c_int), ("gamma_packed", C.c_void_p), ("beta", C.c_void_p),
+        ("rowscale", C.c_void_p), ("rs_stride", C.c_int), ("rs_off", C.c_int),
+    ]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared object, failing loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = Path(os.environ.get("MASIC_B200_LIB", LIB_PATH))
+    if not path.exists():
+        raise MasicError(
+            f"{path} not found: build it with `python -m masic_b200.build` (nvcc, sm_100a). "
+            "masic_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(str(path))
+    _declare(lib)
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status == 0:
+        return
+    if status < 0:
+        raise MasicError(f"{what}: {_ERRORS.get(status, status)}")
+    raise MasicError(f"{what}: CUDA error {status}")
+
+
+def _declare(lib: C.CDLL) -> None:
+    vp, i, u32, f = C.c_void_p, C.c_int, C.c_uint32, C.c_float
+    i64 = C.c_int64
+    sig = {
+        "masic_abi_version": (i, []),
+        "masic_build_info": (C.c_char_p, []),
+        "masic_conv_plan_create": (i, [C.POINTER(ConvDesc), C.POINTER(vp)]),
+        "masic_conv_plan_launch": (i, [vp, vp]),
+        "masic_conv_plan_destroy": (None, [vp]),
+        "masic_conv_plan_info": (i, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                     C.POINTER(i), C.POINTER(i)]),
+        "masic_packed_weight_bytes": (i64, [i, i, i, i]),
+        "masic_pack_conv_weights": (i, [vp, i, i, i, i, i, i, vp, vp]),
+        "masic_gdn_prepare": (i, [vp, vp, i, f, vp, vp, vp, vp]),
+        "masic_conv_direct_nhwc": (i, [vp, i, i, i, i, i, i, vp, i, i, i, u32, vp, i, vp, i, i, i, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)      # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    lib._masic_declared = tuple(sig)
+
+
+def declared_symbols() -> tuple:
+    return load()._masic_declared

@@ -1,0 +1,148 @@
+"""Python handle on one tensor-core conv layer (a MasicConvPlan of the C ABI).
+
+A plan binds its input/output activation buffers (NHWC, bf16 in, bf16 or fp32 out), the
+packed weights and the epilogue (bias, activation, fused GDN/IGDN, per-pixel scale) once;
+`launch()` is then a single kernel launch that can be captured into a CUDA graph.
+
+Reference call sites replaced: compressai/models/utils.py:128-146 (conv/deconv),
+compressai/layers/gdn.py:77-92, compressai/layers/layers.py:75-78 (MaskedConv2d).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, CONV, DECONV_S2, DECONV_S2_SUBPIX, GDN_FWD,
+                   GDN_INV, GDN_NONE, ConvDesc, check)
+
+# MaskedConv2d mask 'A' for a 5x5 kernel (layers.py:68-73): rows 0-1 and (2,0),(2,1)
+MASK_A_5x5 = sum(1 << (ky * 5 + kx) for ky in range(5) for kx in range(5)
+                 if ky < 2 or (ky == 2 and kx < 2))
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def pack_weights(w: torch.Tensor, kind: int, transposed: bool, ksize: int, c_in: int, c_out: int,
+                 c_out_pad: int) -> torch.Tensor:
+    """fp32 torch-layout weights -> bf16 [k-block][c_out_pad][64] (device)."""
+    lib = _lib.load()
+    w = w.detach().to(torch.float32).contiguous()
+    nbytes = lib.masic_packed_weight_bytes(kind, ksize, c_in, c_out_pad)
+    dst = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
+    check(lib.masic_pack_conv_weights(w.data_ptr(), kind, int(transposed), ksize, c_in, c_out,
+                                      c_out_pad, dst.data_ptr(), _stream()), "masic_pack_conv_weights")
+    return dst
+
+
+def gdn_prepare(beta: torch.Tensor, gamma: torch.Tensor, beta_min: float = 1e-6):
+    """Stored (re-parametrised) beta/gamma -> effective beta' (fp32), gamma' (fp32, bf16)."""
+    lib = _lib.load()
+    c = beta.numel()
+    beta = beta.detach().float().contiguous()
+    gamma = gamma.detach().float().contiguous()
+    b = torch.empty(c, dtype=torch.float32, device=beta.device)
+    g32 = torch.empty(c, c, dtype=torch.float32, device=beta.device)
+    g16 = torch.empty(c, c, dtype=torch.bfloat16, device=beta.device)
+    check(lib.masic_gdn_prepare(beta.data_ptr(), gamma.data_ptr(), c, float(beta_min), b.data_ptr(),
+                                g32.data_ptr(), g16.data_ptr(), _stream()), "masic_gdn_prepare")
+    return b, g32, g16
+
+
+class ConvPlan:
+    def __init__(self, *, kind: int = CONV, ksize: int, stride: int = 1, tap_mask: int = 0,
+                 x: torch.Tensor, in_coff: int = 0, c_in: int,
+                 weight: torch.Tensor, transposed: bool = False, bias: Optional[torch.Tensor] = None,
+                 c_out: int, n_tile: int, c_out_pad: Optional[int] = None,
+                 out: torch.Tensor, out_coff: int = 0,
+                 act: int | Sequence[int] = ACT_NONE,
+                 gdn: int = GDN_NONE, gdn_beta: Optional[torch.Tensor] = None,
+                 gdn_gamma: Optional[torch.Tensor] = None,
+                 rowscale: Optional[torch.Tensor] = None, rs_off: int = 0):
+        lib = _lib.load()
+        assert x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous()
+        assert out.is_cuda and out.dim() == 4 and out.is_contiguous()
+        assert out.dtype in (torch.bfloat16, torch.float32)
+        n, h_in, w_in, in_cp = x.shape
+        eff_out = 4 * c_out if kind == DECONV_S2_SUBPIX else c_out
+        if c_out_pad is None:
+            c_out_pad = -(-eff_out // n_tile) * n_tile
+        self.c_out_pad = c_out_pad
+        self.w_packed = pack_weights(weight, kind, transposed, ksize, c_in, c_out, c_out_pad)
+        self.bias = None
+        if bias is not None:
+            b = torch.zeros(c_out_pad, dtype=torch.float32, device=x.device)
+            if kind == DECONV_S2_SUBPIX:
+                b[:4 * c_out] = bias.detach().float().repeat(4)
+            else:
+                b[:c_out] = bias.detach().float()
+            self.bias = b
+        self.beta = self.gamma16 = None
+        if gdn != GDN_NONE:
+            self.beta, _, self.gamma16 = gdn_prepare(gdn_beta, gdn_gamma)
+        self.rowscale = rowscale
+        self.x, self.out = x, out       # keep the bound buffers alive
+
+        d = ConvDesc()
+        d.kind, d.ksize, d.stride, d.tap_mask = kind, ksize, stride, tap_mask
+        d.n, d.h_in, d.w_in = n, h_in, w_in
+        d.c_in, d.c_out, d.c_out_pad, d.n_tile = c_in, eff_out, c_out_pad, n_tile
+        d.in_, d.in_cpitch, d.in_coff = x.data_ptr(), in_cp, in_coff
+        d.w_packed = self.w_packed.data_ptr()
+        d.bias = _ptr(self.bias)
+        d.out, d.out_cpitch, d.out_coff = out.data_ptr(), out.shape[3], out_coff
+        d.out_fp32 = int(out.dtype == torch.float32)
+        n_nt = c_out_pad // n_tile
+        acts = [act] * n_nt if isinstance(act, int) else list(act)
+        assert len(acts) == n_nt, (len(acts), n_nt)
+        for i, a in enumerate(acts):
+            d.act[i] = a
+        d.gdn = gdn
+        d.gamma_packed, d.beta = _ptr(self.gamma16), _ptr(self.beta)
+        if rowscale is not None:
+            assert rowscale.dtype == torch.float32 and rowscale.is_contiguous() and rowscale.dim() == 4
+            d.rowscale, d.rs_stride, d.rs_off = rowscale.data_ptr(), rowscale.shape[3], rs_off
+        self._desc = d
+        handle = C.c_void_p()
+        check(lib.masic_conv_plan_create(C.byref(d), C.byref(handle)), "masic_conv_plan_create")
+        self._h = handle
+        self._lib = lib
+        fl, by, nw, sm = C.c_double(), C.c_double(), C.c_int(), C.c_int()
+        lib.masic_conv_plan_info(handle, C.byref(fl), C.byref(by), C.byref(nw), C.byref(sm))
+        self.flops, self.hbm_bytes, self.work_items, self.smem_bytes = fl.value, by.value, nw.value, sm.value
+
+    def launch(self, stream: Optional[int] = None) -> None:
+        check(self._lib.masic_conv_plan_launch(self._h, _stream() if stream is None else stream),
+              "masic_conv_plan_launch")
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.masic_conv_plan_destroy(h)
+            self._h = None
+
+
+def conv_direct(x: torch.Tensor, c_in: int, weight: torch.Tensor, *, transposed: bool, ksize: int,
+                stride: int, tap_mask: int = 0, bias: Optional[torch.Tensor] = None,
+                in_coff: int = 0, round_w_bf16: bool = True) -> torch.Tensor:
+    """CUDA-core direct conv over NHWC bf16 input -> NHWC fp32 (on-device cross-check)."""
+    lib = _lib.load()
+    n, h, w, cp = x.shape
+    c_out = weight.shape[1] if transposed else weight.shape[0]
+    ho, wo = (h * stride, w * stride) if transposed else (-(-h // stride), -(-w // stride))
+    out = torch.empty(n, ho, wo, c_out, dtype=torch.float32, device=x.device)
+    wt = weight.detach().float().contiguous()
+    bt = None if bias is None else bias.detach().float().contiguous()
+    check(lib.masic_conv_direct_nhwc(x.data_ptr(), n, h, w, cp, in_coff, c_in, wt.data_ptr(),
+                                     int(transposed), ksize, stride, tap_mask, _ptr(bt), c_out,
+                                     out.data_ptr(), c_out, 0, int(round_w_bf16), _stream()),
+          "masic_conv_direct_nhwc")
+    return out
