@@ -115,6 +115,105 @@ int masic_conv_direct_nhwc(const void* in, int n, int h_in, int w_in, int in_cpi
                            float* out_f32, int out_cpitch, int out_coff, int round_w_bf16,
                            void* stream);
 
+
+/* --------------------------------------------------------- entropy models */
+/* Tensor layouts: `*_nhwc` flags select [N][P][C] (the engine's buffers) instead of the
+ * reference's [N][C][P]; P = H*W.  Every output pointer may be NULL (not produced). */
+
+/* GaussianMixtureConditional_gf.forward (compressai/entropy_models/entropy_models.py:808-858;
+ * instantiated as HSIC.gaussian1/2, MASIC.py:658-659; called :767,:829):
+ *   y_hat = round(y);  lik = max(sum_k w_k [Phi((.5-|y_hat-mu_k|)/s_k) - Phi((-.5-|y_hat-mu_k|)/s_k)], 1e-9)
+ *   s_k = max(sigma_k, scale_bound);  parameters are k-major along channels (ch = k*M + m).
+ * weights_are_logits=1 fuses the softmax over K of MASIC.py:389-393 / :459-464.
+ * yq_bf16 (optional): NHWC bf16 copy of y_hat at channel offset bf_coff of a bf_pitch-wide
+ * buffer, times rowscale[(n*P+p)*rs_stride+rs_off] when rowscale != NULL (MASIC.py:827). */
+int masic_gmm_likelihood_fwd(const float* y, const float* sigma, const float* mu, const float* weights,
+                             int weights_are_logits, int in_nhwc, int n, int m, int k, int hw,
+                             float scale_bound, float* y_hat, float* lik, int32_t* symbols, int out_nhwc,
+                             void* yq_bf16, int bf_pitch, int bf_coff, const float* rowscale,
+                             int rs_stride, int rs_off, void* stream);
+
+/* GaussianConditional.forward + _quantize('symbols') (entropy_models.py:528-554, :112-125),
+ * elementwise over `numel` contiguous values; means may be NULL. */
+int masic_gc_likelihood_fwd(const float* y, const float* scales, const float* means, int64_t numel,
+                            float scale_bound, float* y_hat, float* lik, int32_t* symbols, void* stream);
+
+/* GaussianConditional.build_indexes (entropy_models.py:556-562): bit-exact int32 indexes. */
+int masic_gc_build_indexes(const float* scales, int64_t numel, const float* scale_table, int table_len,
+                           float scale_bound, int32_t* indexes, void* stream);
+
+/* EntropyBottleneck.forward (eval) + symbols (entropy_models.py:350-411, :420-423).
+ * matrices/biases: HOST arrays of 5 DEVICE pointers, factors: 4 — the ParameterLists
+ * _matrices/_biases/_factors with filters (3,3,3,3); quantiles: device (C,1,3).
+ * zq_bf16 (optional): NHWC bf16 copy of z_hat, pitch bf_pitch (input of h_s). */
+int masic_eb_fwd(const float* z, int in_nhwc, int n, int c, int hw, const float* const* matrices,
+                 const float* const* biases, const float* const* factors, const float* quantiles,
+                 float* z_hat, float* lik, int32_t* symbols, int out_nhwc, void* zq_bf16, int bf_pitch,
+                 void* stream);
+
+/* EntropyModel._quantize (entropy_models.py:98-125): dequantized = round(x-means)+means,
+ * symbols = int32(round(x-means)); round half to even. */
+int masic_quantize(const float* x, const float* means, int64_t numel, float* dequantized,
+                   int32_t* symbols, void* stream);
+
+/* |y| and round(y) as bf16 NHWC copies of an fp32 NHWC latent (inputs of encode_hyper
+ * MASIC.py:184-187, context_prediction :757, the mask-weighted y1_hat_warp term :827). */
+int masic_latent_prep(const float* y_nhwc, int64_t n_pixels, int c, void* y_abs_bf16, int abs_pitch,
+                      void* y_round_bf16, int rnd_pitch, int rnd_coff, const float* rowscale,
+                      int rs_stride, int rs_off, void* stream);
+
+/* compressai._CXX.pmf_to_quantized_cdf (compressai/cpp_exts/ops/ops.cpp:40-109), HOST buffers.
+ * Returns 1 / 2 for the reference's two std::domain_error cases. cdf_host holds n+1 values. */
+int masic_pmf_to_quantized_cdf(const float* pmf_host, int n, int precision, uint32_t* cdf_host);
+/* EntropyModel._pmf_to_cdf (entropy_models.py:136-142), HOST buffers; cdf is (rows, max_length+2). */
+int masic_pmf_table_to_cdf(const float* pmf_host, int rows, int row_stride, const float* tail_mass_host,
+                           const int32_t* pmf_length_host, int max_length, int precision,
+                           int32_t* cdf_host);
+
+/* ------------------------------------------------------------ image domain */
+/* kornia.warp_perspective(src, M, (h_out, w_out)) — kornia 0.5.0, call sites MASIC.py:781,821,833.
+ * Step 1: T = inv(N_dst M inv(N_src)) per batch element (invert_m=1 first replaces M by
+ * inv(M): the second warp of mask(), MASIC.py:644).  t_out is (batch,3,3) fp32 on device. */
+int masic_warp_prepare(const float* m_3x3, int batch, int h, int w, int h_out, int w_out, int invert_m,
+                       float* t_out, void* stream);
+/* Step 2: bilinear, zero padding, align_corners=True.  src NCHW fp32 with c <= 8 channels;
+ * src == NULL warps an all-ones image (mask(), MASIC.py:636-638).  Outputs: NCHW fp32 and/or
+ * NHWC bf16 zero-padded to bf_pitch channels. */
+int masic_warp_perspective_fwd(const float* src, int n, int c, int h, int w, int h_out, int w_out,
+                               const float* t_prepared, float* dst_nchw, void* dst_nhwc_bf16,
+                               int bf_pitch, void* stream);
+
+/* Direct conv for the tiny-channel layers (c_in <= 8, c_out <= 8) on NCHW fp32:
+ *   Encoder2.pre_conv+pre_gdn (MASIC.py:573-574): in0=x1_warp, in1=x2, k=5, s=1, gdn=FWD
+ *   Decoder2.after_conv       (MASIC.py:616):     transposed_s1=1 (ConvTranspose2d weight layout)
+ *   mask2weights.maskconv     (MASIC.py:475-488): k=3, s=2, ReLU
+ * weight is torch layout (c_out, c0+c1, k, k), or (c0+c1, c_out, k, k) when transposed_s1. */
+int masic_conv_small_nchw(const float* in0, int c0, const float* in1, int c1, int n, int h, int w,
+                          const float* weight, int transposed_s1, const float* bias, int c_out,
+                          int ksize, int stride, int act, int gdn, const float* beta,
+                          const float* gamma, float beta_min, float* out_nchw, void* out_nhwc_bf16,
+                          int bf_pitch, void* stream);
+
+/* Output of a MASIC_DECONV_S2_SUBPIX plan ([N][H/2][W/2][pitch] fp32, channel = phase*3+co)
+ * -> NCHW fp32 image (N,3,H,W), optionally through GDN/IGDN over the 3 channels
+ * (Decoder2.after_gdn, MASIC.py:599,615), optionally also NHWC bf16. */
+int masic_subpix_to_nchw(const float* in_nhwc, int n, int h2, int w2, int pitch, int gdn,
+                         const float* beta, const float* gamma, float beta_min, float* out_nchw,
+                         void* out_nhwc_bf16, int bf_pitch, void* stream);
+
+/* Stand-alone GDN.forward (compressai/layers/gdn.py:77-92) on NCHW fp32, c <= 256; beta/gamma are
+ * the STORED (re-parametrised) parameters, the kernel applies parametrizers.py:61-64 itself. */
+int masic_gdn_nchw(const float* x, int n, int c, int hw, const float* beta, const float* gamma,
+                   float beta_min, int inverse, float* out, void* stream);
+
+/* softmax over the c (<= 8) channels of an NCHW tensor (mask2weights, MASIC.py:497-502). */
+int masic_softmax_channels(const float* in_nchw, int n, int c, int hw, float* out_nchw, float* out_nhwc,
+                           void* stream);
+/* layout packs */
+int masic_nchw_to_nhwc_bf16(const float* in_nchw, int n, int c, int hw, void* out, int pitch, void* stream);
+int masic_nhwc_to_nchw_f32(const float* in_nhwc, int n, int c, int hw, int in_pitch, float* out_nchw,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,24 @@ def _declare(lib: C.CDLL) -> None:
         "masic_pack_conv_weights": (i, [vp, i, i, i, i, i, i, vp, vp]),
         "masic_gdn_prepare": (i, [vp, vp, i, f, vp, vp, vp, vp]),
         "masic_conv_direct_nhwc": (i, [vp, i, i, i, i, i, i, vp, i, i, i, u32, vp, i, vp, i, i, i, vp]),
+        "masic_gmm_likelihood_fwd": (i, [vp, vp, vp, vp, i, i, i, i, i, i, f, vp, vp, vp, i, vp, i, i,
+                                         vp, i, i, vp]),
+        "masic_gc_likelihood_fwd": (i, [vp, vp, vp, i64, f, vp, vp, vp, vp]),
+        "masic_gc_build_indexes": (i, [vp, i64, vp, i, f, vp, vp]),
+        "masic_eb_fwd": (i, [vp, i, i, i, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp,
+                             i, vp, i, vp]),
+        "masic_quantize": (i, [vp, vp, i64, vp, vp, vp]),
+        "masic_latent_prep": (i, [vp, i64, i, vp, i, vp, i, i, vp, i, i, vp]),
+        "masic_pmf_to_quantized_cdf": (i, [vp, i, i, vp]),
+        "masic_pmf_table_to_cdf": (i, [vp, i, i, vp, vp, i, i, vp]),
+        "masic_warp_prepare": (i, [vp, i, i, i, i, i, i, vp, vp]),
+        "masic_warp_perspective_fwd": (i, [vp, i, i, i, i, i, i, vp, vp, vp, i, vp]),
+        "masic_conv_small_nchw": (i, [vp, i, vp, i, i, i, i, vp, i, vp, i, i, i, i, i, vp, vp, f, vp, vp, i, vp]),
+        "masic_subpix_to_nchw": (i, [vp, i, i, i, i, i, vp, vp, f, vp, vp, i, vp]),
+        "masic_gdn_nchw": (i, [vp, i, i, i, vp, vp, f, i, vp, vp]),
+        "masic_softmax_channels": (i, [vp, i, i, i, vp, vp, vp]),
+        "masic_nchw_to_nhwc_bf16": (i, [vp, i, i, i, vp, i, vp]),
+        "masic_nhwc_to_nchw_f32": (i, [vp, i, i, i, i, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)      # AttributeError here = header/library mismatch

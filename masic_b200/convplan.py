@@ -57,11 +57,41 @@ def gdn_prepare(beta: torch.Tensor, gamma: torch.Tensor, beta_min: float = 1e-6)
     return b, g32, g16
 
 
-class ConvPlan:
-    def __init__(self, *, kind: int = CONV, ksize: int, stride: int = 1, tap_mask: int = 0,
-                 x: torch.Tensor, in_coff: int = 0, c_in: int,
+class PackedConv:
+    """Weights of one conv layer in the form the tensor-core kernel reads: bf16 k-blocks,
+    zero-padded fp32 bias, re-parametrised GDN beta' / bf16 gamma'.  Shared by every plan
+    that runs the layer (encoder1 runs twice per stereo pair, MASIC.py:746,822)."""
+
+    def __init__(self, *, kind: int = CONV, ksize: int, c_in: int, c_out: int, n_tile: int,
                  weight: torch.Tensor, transposed: bool = False, bias: Optional[torch.Tensor] = None,
-                 c_out: int, n_tile: int, c_out_pad: Optional[int] = None,
+                 c_out_pad: Optional[int] = None, gdn: int = GDN_NONE,
+                 gdn_beta: Optional[torch.Tensor] = None, gdn_gamma: Optional[torch.Tensor] = None):
+        self.kind, self.ksize, self.c_in, self.c_out, self.n_tile = kind, ksize, c_in, c_out, n_tile
+        self.transposed, self.gdn = transposed, gdn
+        self.eff_out = 4 * c_out if kind == DECONV_S2_SUBPIX else c_out
+        self.c_out_pad = c_out_pad if c_out_pad is not None else -(-self.eff_out // n_tile) * n_tile
+        dev = weight.device
+        self.w_packed = pack_weights(weight, kind, transposed, ksize, c_in, c_out, self.c_out_pad)
+        self.bias = None
+        if bias is not None:
+            b = torch.zeros(self.c_out_pad, dtype=torch.float32, device=dev)
+            if kind == DECONV_S2_SUBPIX:
+                b[:4 * c_out] = bias.detach().float().repeat(4)
+            else:
+                b[:c_out] = bias.detach().float()
+            self.bias = b
+        self.beta = self.gamma16 = None
+        if gdn != GDN_NONE:
+            self.beta, _, self.gamma16 = gdn_prepare(gdn_beta, gdn_gamma)
+
+
+class ConvPlan:
+    def __init__(self, *, packed: Optional[PackedConv] = None, kind: int = CONV, ksize: int = 0,
+                 stride: int = 1, tap_mask: int = 0,
+                 x: torch.Tensor, in_coff: int = 0, c_in: int = 0,
+                 weight: Optional[torch.Tensor] = None, transposed: bool = False,
+                 bias: Optional[torch.Tensor] = None,
+                 c_out: int = 0, n_tile: int = 0, c_out_pad: Optional[int] = None,
                  out: torch.Tensor, out_coff: int = 0,
                  act: int | Sequence[int] = ACT_NONE,
                  gdn: int = GDN_NONE, gdn_beta: Optional[torch.Tensor] = None,
@@ -71,42 +101,31 @@ class ConvPlan:
         assert x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous()
         assert out.is_cuda and out.dim() == 4 and out.is_contiguous()
         assert out.dtype in (torch.bfloat16, torch.float32)
+        if packed is None:
+            packed = PackedConv(kind=kind, ksize=ksize, c_in=c_in, c_out=c_out, n_tile=n_tile, weight=weight,
+                                transposed=transposed, bias=bias, c_out_pad=c_out_pad, gdn=gdn,
+                                gdn_beta=gdn_beta, gdn_gamma=gdn_gamma)
+        self.packed = packed
         n, h_in, w_in, in_cp = x.shape
-        eff_out = 4 * c_out if kind == DECONV_S2_SUBPIX else c_out
-        if c_out_pad is None:
-            c_out_pad = -(-eff_out // n_tile) * n_tile
-        self.c_out_pad = c_out_pad
-        self.w_packed = pack_weights(weight, kind, transposed, ksize, c_in, c_out, c_out_pad)
-        self.bias = None
-        if bias is not None:
-            b = torch.zeros(c_out_pad, dtype=torch.float32, device=x.device)
-            if kind == DECONV_S2_SUBPIX:
-                b[:4 * c_out] = bias.detach().float().repeat(4)
-            else:
-                b[:c_out] = bias.detach().float()
-            self.bias = b
-        self.beta = self.gamma16 = None
-        if gdn != GDN_NONE:
-            self.beta, _, self.gamma16 = gdn_prepare(gdn_beta, gdn_gamma)
         self.rowscale = rowscale
         self.x, self.out = x, out       # keep the bound buffers alive
 
         d = ConvDesc()
-        d.kind, d.ksize, d.stride, d.tap_mask = kind, ksize, stride, tap_mask
+        d.kind, d.ksize, d.stride, d.tap_mask = packed.kind, packed.ksize, stride, tap_mask
         d.n, d.h_in, d.w_in = n, h_in, w_in
-        d.c_in, d.c_out, d.c_out_pad, d.n_tile = c_in, eff_out, c_out_pad, n_tile
+        d.c_in, d.c_out, d.c_out_pad, d.n_tile = packed.c_in, packed.eff_out, packed.c_out_pad, packed.n_tile
         d.in_, d.in_cpitch, d.in_coff = x.data_ptr(), in_cp, in_coff
-        d.w_packed = self.w_packed.data_ptr()
-        d.bias = _ptr(self.bias)
+        d.w_packed = packed.w_packed.data_ptr()
+        d.bias = _ptr(packed.bias)
         d.out, d.out_cpitch, d.out_coff = out.data_ptr(), out.shape[3], out_coff
         d.out_fp32 = int(out.dtype == torch.float32)
-        n_nt = c_out_pad // n_tile
+        n_nt = packed.c_out_pad // packed.n_tile
         acts = [act] * n_nt if isinstance(act, int) else list(act)
         assert len(acts) == n_nt, (len(acts), n_nt)
         for i, a in enumerate(acts):
             d.act[i] = a
-        d.gdn = gdn
-        d.gamma_packed, d.beta = _ptr(self.gamma16), _ptr(self.beta)
+        d.gdn = packed.gdn
+        d.gamma_packed, d.beta = _ptr(packed.gamma16), _ptr(packed.beta)
         if rowscale is not None:
             assert rowscale.dtype == torch.float32 and rowscale.is_contiguous() and rowscale.dim() == 4
             d.rowscale, d.rs_stride, d.rs_off = rowscale.data_ptr(), rowscale.shape[3], rs_off
@@ -118,6 +137,10 @@ class ConvPlan:
         fl, by, nw, sm = C.c_double(), C.c_double(), C.c_int(), C.c_int()
         lib.masic_conv_plan_info(handle, C.byref(fl), C.byref(by), C.byref(nw), C.byref(sm))
         self.flops, self.hbm_bytes, self.work_items, self.smem_bytes = fl.value, by.value, nw.value, sm.value
+
+    @property
+    def c_out_pad(self) -> int:
+        return self.packed.c_out_pad
 
     def launch(self, stream: Optional[int] = None) -> None:
         check(self._lib.masic_conv_plan_launch(self._h, _stream() if stream is None else stream),

@@ -1,0 +1,347 @@
+// entropy.cu — fused, memory-bound entropy-model kernels (sm_100a).
+//
+// Replaces (reference, file:line):
+//   GaussianMixtureConditional_gf.forward/_likelihood  compressai/entropy_models/entropy_models.py:808-858
+//   (+ the softmax over K of MASIC.py:389-393 / :459-464 when the weights arrive as logits)
+//   EntropyBottleneck.forward/_likelihood/_logits_cumulative        entropy_models.py:350-411
+//   GaussianConditional._likelihood/forward/build_indexes           entropy_models.py:528-562
+//   EntropyModel._quantize('symbols'|'dequantize')                  entropy_models.py:98-125
+//
+// Layout: every tensor argument is described by (stride_n, stride_c, stride_p) in elements,
+// p = y*W + x, so the same kernel serves the reference's NCHW tensors (stride_c = H*W,
+// stride_p = 1) and the engine's NHWC buffers (stride_c = 1, stride_p = C).  Blocks walk
+// 32 channels x 32 positions through a shared-memory transpose so that both sides of a
+// layout change stay coalesced.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/masic_b200.h"
+
+namespace {
+
+constexpr float kLikBound = 1e-9f;
+constexpr float kInvSqrt2Neg = -0.70710678118654752440f;   // float(-(2**-0.5))
+
+__device__ __forceinline__ float phi(float x) { return 0.5f * erfcf(kInvSqrt2Neg * x); }
+
+__device__ __forceinline__ float gauss_mass(float v_abs, float s) {
+  return phi((0.5f - v_abs) / s) - phi((-0.5f - v_abs) / s);
+}
+
+struct View { long sn, sc, sp; };
+__device__ __forceinline__ long at(const View& v, int n, int c, int p) {
+  return n * v.sn + c * v.sc + (long)p * v.sp;
+}
+
+// ------------------------------------------------------------------ K-component mixture
+// grid: (ceil(P/32), ceil(M/32), N); block (32, 8).
+// `fast_c` != 0: parameters are channel-fastest (NHWC): threadIdx.x walks channels while loading.
+template <int K>
+__global__ void __launch_bounds__(256)
+gmm_fwd_kernel(const float* __restrict__ y, View vy, const float* __restrict__ sigma,
+               const float* __restrict__ mu, const float* __restrict__ wgt, View vp, int w_is_logits,
+               int fast_c, int M, int P, float scale_bound, float* __restrict__ y_hat,
+               float* __restrict__ lik, View vo, int32_t* __restrict__ sym,
+               __nv_bfloat16* __restrict__ yq_bf16, int bf_pitch, int bf_coff,
+               const float* __restrict__ rowscale, int rs_stride, int rs_off) {
+  __shared__ float s_lik[32][33];
+  __shared__ float s_yh[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  // ---- compute phase: pick the mapping that makes the 3K parameter loads coalesced
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int pl = fast_c ? j : threadIdx.x;
+    const int ml = fast_c ? threadIdx.x : j;
+    const int p = p0 + pl, m = m0 + ml;
+    float l = 0.0f, yh = 0.0f;
+    if (p < P && m < M) {
+      yh = rintf(y[at(vy, n, m, p)]);
+      float wk[K];
+      if (w_is_logits) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { wk[k] = wgt[at(vp, n, k * M + m, p)]; mx = fmaxf(mx, wk[k]); }
+        float sum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { wk[k] = expf(wk[k] - mx); sum += wk[k]; }
+#pragma unroll
+        for (int k = 0; k < K; ++k) wk[k] = wk[k] / sum;
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) wk[k] = wgt[at(vp, n, k * M + m, p)];
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const long o = at(vp, n, k * M + m, p);
+        const float s = fmaxf(sigma[o], scale_bound);
+        const float v = fabsf(yh - mu[o]);
+        l += gauss_mass(v, s) * wk[k];
+      }
+      l = fmaxf(l, kLikBound);
+    }
+    s_lik[pl][ml] = l;
+    s_yh[pl][ml] = yh;
+  }
+  __syncthreads();
+  // ---- store phase: fastest output dimension on threadIdx.x
+  const bool out_fast_c = vo.sc == 1;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int pl = out_fast_c ? j : threadIdx.x;
+    const int ml = out_fast_c ? threadIdx.x : j;
+    const int p = p0 + pl, m = m0 + ml;
+    if (p < P && m < M) {
+      const long o = at(vo, n, m, p);
+      if (lik) lik[o] = s_lik[pl][ml];
+      if (y_hat) y_hat[o] = s_yh[pl][ml];
+      if (sym) sym[o] = (int32_t)s_yh[pl][ml];
+    }
+  }
+  if (yq_bf16) {   // NHWC bf16 copy of round(y) for the next conv (optionally mask-weighted)
+    for (int j = threadIdx.y; j < 32; j += 8) {
+      const int p = p0 + j, m = m0 + threadIdx.x;
+      if (p < P && m < M) {
+        float v = s_yh[j][threadIdx.x];
+        if (rowscale) v *= rowscale[((long)n * P + p) * rs_stride + rs_off];
+        yq_bf16[((long)n * P + p) * bf_pitch + bf_coff + m] = __float2bfloat16_rn(v);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ single Gaussian
+__global__ void __launch_bounds__(256)
+gc_fwd_kernel(const float* __restrict__ y, const float* __restrict__ scales,
+              const float* __restrict__ means, long total, float scale_bound,
+              float* __restrict__ y_hat, float* __restrict__ lik, int32_t* __restrict__ sym) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float mu = means ? means[i] : 0.0f;
+  float r = y[i];
+  if (means) r = r - mu;
+  r = rintf(r);
+  if (sym) sym[i] = (int32_t)r;
+  const float deq = means ? r + mu : r;
+  if (y_hat) y_hat[i] = deq;
+  if (lik) {
+    const float v = means ? fabsf(deq - mu) : fabsf(deq);
+    const float s = fmaxf(scales[i], scale_bound);
+    lik[i] = fmaxf(gauss_mass(v, s), kLikBound);
+  }
+}
+
+// idx = (L-1) - #{ j < L-1 : max(scale, bound) <= table[j] }   (table ascending)
+__global__ void __launch_bounds__(256)
+gc_indexes_kernel(const float* __restrict__ scales, long total, const float* __restrict__ table, int L,
+                  float scale_bound, int32_t* __restrict__ idx) {
+  extern __shared__ float s_tab[];
+  for (int j = threadIdx.x; j < L; j += blockDim.x) s_tab[j] = table[j];
+  __syncthreads();
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float s = fmaxf(scales[i], scale_bound);
+  // first j in [0, L-1) with table[j] >= s ; count of (s <= table[j]) = (L-1) - j
+  int lo = 0, hi = L - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (s_tab[mid] >= s) hi = mid; else lo = mid + 1;
+  }
+  idx[i] = lo;      // (L-1) - ((L-1) - lo)
+}
+
+// ------------------------------------------------------------------ EntropyBottleneck
+// per-channel parameter block prepared once per launch: softplus(matrices), biases, tanh(factors)
+struct EBChan {
+  float m0[3], m1[9], m2[9], m3[9], m4[3];
+  float b0[3], b1[3], b2[3], b3[3], b4[1];
+  float f0[3], f1[3], f2[3], f3[3];
+  float median;
+};
+
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ float eb_logits(const EBChan& c, float v) {
+  float a[3], t[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    a[i] = c.m0[i] * v + c.b0[i];
+    a[i] += c.f0[i] * tanhf(a[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    t[i] = c.m1[i * 3] * a[0] + c.m1[i * 3 + 1] * a[1] + c.m1[i * 3 + 2] * a[2] + c.b1[i];
+    t[i] += c.f1[i] * tanhf(t[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    a[i] = c.m2[i * 3] * t[0] + c.m2[i * 3 + 1] * t[1] + c.m2[i * 3 + 2] * t[2] + c.b2[i];
+    a[i] += c.f2[i] * tanhf(a[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    t[i] = c.m3[i * 3] * a[0] + c.m3[i * 3 + 1] * a[1] + c.m3[i * 3 + 2] * a[2] + c.b3[i];
+    t[i] += c.f3[i] * tanhf(t[i]);
+  }
+  return c.m4[0] * t[0] + c.m4[1] * t[1] + c.m4[2] * t[2] + c.b4[0];
+}
+
+// grid (ceil(P/256), C, N)
+__global__ void __launch_bounds__(256)
+eb_fwd_kernel(const float* __restrict__ z, View vz, int P,
+              const float* __restrict__ mat0, const float* __restrict__ mat1,
+              const float* __restrict__ mat2, const float* __restrict__ mat3,
+              const float* __restrict__ mat4, const float* __restrict__ b0,
+              const float* __restrict__ b1, const float* __restrict__ b2,
+              const float* __restrict__ b3, const float* __restrict__ b4,
+              const float* __restrict__ f0, const float* __restrict__ f1,
+              const float* __restrict__ f2, const float* __restrict__ f3,
+              const float* __restrict__ quantiles, float* __restrict__ z_hat,
+              float* __restrict__ lik, View vo, int32_t* __restrict__ sym,
+              __nv_bfloat16* __restrict__ zq_bf16, int bf_pitch) {
+  __shared__ EBChan sc;
+  const int c = blockIdx.y, n = blockIdx.z;
+  if (threadIdx.x < 3) {
+    const int i = threadIdx.x;
+    sc.m0[i] = softplus_f(mat0[c * 3 + i]);  sc.m4[i] = softplus_f(mat4[c * 3 + i]);
+    sc.b0[i] = b0[c * 3 + i]; sc.b1[i] = b1[c * 3 + i]; sc.b2[i] = b2[c * 3 + i]; sc.b3[i] = b3[c * 3 + i];
+    sc.f0[i] = tanhf(f0[c * 3 + i]); sc.f1[i] = tanhf(f1[c * 3 + i]);
+    sc.f2[i] = tanhf(f2[c * 3 + i]); sc.f3[i] = tanhf(f3[c * 3 + i]);
+  }
+  if (threadIdx.x < 9) {
+    const int i = threadIdx.x;
+    sc.m1[i] = softplus_f(mat1[c * 9 + i]); sc.m2[i] = softplus_f(mat2[c * 9 + i]);
+    sc.m3[i] = softplus_f(mat3[c * 9 + i]);
+  }
+  if (threadIdx.x == 0) { sc.b4[0] = b4[c]; sc.median = quantiles[c * 3 + 1]; }
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const float med = sc.median;
+  const float r = rintf(z[at(vz, n, c, p)] - med);
+  const float q = r + med;
+  const long o = at(vo, n, c, p);
+  if (sym) sym[o] = (int32_t)r;
+  if (z_hat) z_hat[o] = q;
+  if (zq_bf16) zq_bf16[((long)n * P + p) * bf_pitch + c] = __float2bfloat16_rn(q);
+  if (lik) {
+    const float lower = eb_logits(sc, q - 0.5f);
+    const float upper = eb_logits(sc, q + 0.5f);
+    const float su = lower + upper;
+    const float sign = su > 0.0f ? -1.0f : (su < 0.0f ? 1.0f : 0.0f);
+    lik[o] = fmaxf(fabsf(sigmoid_f(sign * upper) - sigmoid_f(sign * lower)), kLikBound);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+quantize_kernel(const float* __restrict__ x, const float* __restrict__ means, long total,
+                float* __restrict__ deq, int32_t* __restrict__ sym) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float r = x[i];
+  const float mu = means ? means[i] : 0.0f;
+  if (means) r = r - mu;
+  r = rintf(r);
+  if (sym) sym[i] = (int32_t)r;
+  if (deq) deq[i] = means ? r + mu : r;
+}
+
+// |y| and round(y) as bf16 NHWC copies of an fp32 NHWC latent (inputs of h_a, context conv, decoder)
+__global__ void __launch_bounds__(256)
+latent_prep_kernel(const float* __restrict__ y, long total, int C, __nv_bfloat16* __restrict__ y_abs,
+                   int abs_pitch, __nv_bfloat16* __restrict__ y_round, int rnd_pitch, int rnd_coff,
+                   const float* __restrict__ rowscale, int rs_stride, int rs_off) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long pix = i / C;
+  const int c = (int)(i - pix * C);
+  const float v = y[i];
+  if (y_abs) y_abs[pix * abs_pitch + c] = __float2bfloat16_rn(fabsf(v));
+  if (y_round) {
+    float r = rintf(v);
+    if (rowscale) r *= rowscale[pix * rs_stride + rs_off];
+    y_round[pix * rnd_pitch + rnd_coff + c] = __float2bfloat16_rn(r);
+  }
+}
+
+inline View mkview(int layout_nhwc, int C, int P) {
+  View v;
+  if (layout_nhwc) { v.sn = (long)C * P; v.sc = 1; v.sp = C; }
+  else { v.sn = (long)C * P; v.sc = P; v.sp = 1; }
+  return v;
+}
+
+}  // namespace
+
+extern "C" int masic_gmm_likelihood_fwd(const float* y, const float* sigma, const float* mu,
+                                        const float* weights, int weights_are_logits, int in_nhwc,
+                                        int n, int m, int k, int hw, float scale_bound,
+                                        float* y_hat, float* lik, int32_t* symbols, int out_nhwc,
+                                        void* yq_bf16, int bf_pitch, int bf_coff,
+                                        const float* rowscale, int rs_stride, int rs_off, void* stream) {
+  if (!y || !sigma || !mu || !weights || n <= 0 || m <= 0 || hw <= 0) return MASIC_EINVAL;
+  if (k != 5) return MASIC_ENOSUP;    // HSIC hard-codes K = 5 (MASIC.py:653, test2_real.py:395)
+  const View vy = mkview(in_nhwc, m, hw), vp = mkview(in_nhwc, m * k, hw), vo = mkview(out_nhwc, m, hw);
+  dim3 grid((hw + 31) / 32, (m + 31) / 32, n), block(32, 8);
+  gmm_fwd_kernel<5><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      y, vy, sigma, mu, weights, vp, weights_are_logits, in_nhwc, m, hw, scale_bound, y_hat, lik, vo,
+      symbols, static_cast<__nv_bfloat16*>(yq_bf16), bf_pitch, bf_coff, rowscale, rs_stride, rs_off);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int masic_gc_likelihood_fwd(const float* y, const float* scales, const float* means,
+                                       int64_t numel, float scale_bound, float* y_hat, float* lik,
+                                       int32_t* symbols, void* stream) {
+  if (!y || numel < 0 || (lik && !scales)) return MASIC_EINVAL;
+  if (numel == 0) return MASIC_OK;
+  gc_fwd_kernel<<<(unsigned)((numel + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      y, scales, means, numel, scale_bound, y_hat, lik, symbols);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int masic_gc_build_indexes(const float* scales, int64_t numel, const float* scale_table,
+                                      int table_len, float scale_bound, int32_t* indexes, void* stream) {
+  if (!scales || !scale_table || !indexes || table_len <= 0 || table_len > 4096 || numel < 0)
+    return MASIC_EINVAL;
+  if (numel == 0) return MASIC_OK;
+  gc_indexes_kernel<<<(unsigned)((numel + 255) / 256), 256, table_len * sizeof(float),
+                      static_cast<cudaStream_t>(stream)>>>(scales, numel, scale_table, table_len,
+                                                           scale_bound, indexes);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int masic_eb_fwd(const float* z, int in_nhwc, int n, int c, int hw,
+                            const float* const* matrices, const float* const* biases,
+                            const float* const* factors, const float* quantiles, float* z_hat,
+                            float* lik, int32_t* symbols, int out_nhwc, void* zq_bf16, int bf_pitch,
+                            void* stream) {
+  if (!z || !matrices || !biases || !factors || !quantiles || n <= 0 || c <= 0 || hw <= 0)
+    return MASIC_EINVAL;
+  const View vz = mkview(in_nhwc, c, hw), vo = mkview(out_nhwc, c, hw);
+  dim3 grid((hw + 255) / 256, c, n);
+  eb_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      z, vz, hw, matrices[0], matrices[1], matrices[2], matrices[3], matrices[4], biases[0], biases[1],
+      biases[2], biases[3], biases[4], factors[0], factors[1], factors[2], factors[3], quantiles, z_hat,
+      lik, vo, symbols, static_cast<__nv_bfloat16*>(zq_bf16), bf_pitch);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int masic_quantize(const float* x, const float* means, int64_t numel, float* dequantized,
+                              int32_t* symbols, void* stream) {
+  if (!x || numel < 0) return MASIC_EINVAL;
+  if (numel == 0) return MASIC_OK;
+  quantize_kernel<<<(unsigned)((numel + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, means, numel, dequantized, symbols);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int masic_latent_prep(const float* y_nhwc, int64_t n_pixels, int c, void* y_abs_bf16,
+                                 int abs_pitch, void* y_round_bf16, int rnd_pitch, int rnd_coff,
+                                 const float* rowscale, int rs_stride, int rs_off, void* stream) {
+  if (!y_nhwc || n_pixels <= 0 || c <= 0) return MASIC_EINVAL;
+  const long total = n_pixels * c;
+  latent_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      y_nhwc, total, c, static_cast<__nv_bfloat16*>(y_abs_bf16), abs_pitch,
+      static_cast<__nv_bfloat16*>(y_round_bf16), rnd_pitch, rnd_coff, rowscale, rs_stride, rs_off);
+  return (int)cudaGetLastError();
+}

@@ -1,0 +1,364 @@
+// image.cu — memory-bound image-resolution kernels (sm_100a): homography warp, validity
+// masks, the small-channel convolutions around the codec, layout packs.
+//
+// Replaces (reference, file:line):
+//   kornia.warp_perspective call sites       coremasic/mywork/MASIC.py:781,821,833
+//   mask()                                   MASIC.py:627-649
+//   mask2weights (4x conv3 s2 + softmax)     MASIC.py:472-506
+//   Encoder2.pre_conv + pre_gdn              MASIC.py:559-560,573-574
+//   Decoder2.after_gdn + after_conv          MASIC.py:599-600,615-616
+//   the pixel interleave of ConvTranspose2d(128->3) when it runs as a sub-pixel GEMM
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/masic_b200.h"
+
+namespace {
+
+// ------------------------------------------------------------------ homography warp
+// T = inv(N_dst * M * inv(N_src)) with N(h,w) = [[2/(w-1),0,-1],[0,2/(h-1),-1],[0,0,1]]
+// (kornia 0.5.0 normalize_homography); evaluated in fp64, stored fp32.  With invert_m != 0
+// the function first replaces M by inv(M) (the second warp of mask(), MASIC.py:644).
+__global__ void warp_prepare_kernel(const float* __restrict__ M, int batch, int h, int w, int ho, int wo,
+                                    int invert_m, float* __restrict__ T) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  double m[9], a[9], r[9];
+  for (int i = 0; i < 9; ++i) m[i] = (double)M[b * 9 + i];
+  auto inv3 = [](const double* s, double* d) {
+    const double c0 = s[4] * s[8] - s[5] * s[7], c1 = s[5] * s[6] - s[3] * s[8], c2 = s[3] * s[7] - s[4] * s[6];
+    const double det = s[0] * c0 + s[1] * c1 + s[2] * c2;
+    const double id = 1.0 / det;
+    d[0] = c0 * id; d[1] = (s[2] * s[7] - s[1] * s[8]) * id; d[2] = (s[1] * s[5] - s[2] * s[4]) * id;
+    d[3] = c1 * id; d[4] = (s[0] * s[8] - s[2] * s[6]) * id; d[5] = (s[2] * s[3] - s[0] * s[5]) * id;
+    d[6] = c2 * id; d[7] = (s[1] * s[6] - s[0] * s[7]) * id; d[8] = (s[0] * s[4] - s[1] * s[3]) * id;
+  };
+  if (invert_m) { inv3(m, a); for (int i = 0; i < 9; ++i) m[i] = a[i]; }
+  const double sw = (w == 1) ? 1e-14 : (double)(w - 1), sh = (h == 1) ? 1e-14 : (double)(h - 1);
+  const double dw = (wo == 1) ? 1e-14 : (double)(wo - 1), dh = (ho == 1) ? 1e-14 : (double)(ho - 1);
+  // inv(N_src) = [[sw/2,0,sw/2],[0,sh/2,sh/2],[0,0,1]];  a = M * inv(N_src)
+  for (int i = 0; i < 3; ++i) {
+    a[i * 3 + 0] = m[i * 3 + 0] * (sw / 2);
+    a[i * 3 + 1] = m[i * 3 + 1] * (sh / 2);
+    a[i * 3 + 2] = m[i * 3 + 0] * (sw / 2) + m[i * 3 + 1] * (sh / 2) + m[i * 3 + 2];
+  }
+  // r = N_dst * a
+  for (int j = 0; j < 3; ++j) {
+    r[0 + j] = (2.0 / dw) * a[0 + j] - a[6 + j];
+    r[3 + j] = (2.0 / dh) * a[3 + j] - a[6 + j];
+    r[6 + j] = a[6 + j];
+  }
+  inv3(r, a);
+  for (int i = 0; i < 9; ++i) T[b * 9 + i] = (float)a[i];
+}
+
+// One thread per destination pixel, all channels.  src == nullptr: source is all ones
+// (mask(), MASIC.py:636-638) so the kernel is write-only.
+// Outputs (either may be null): NCHW fp32, and NHWC bf16 with `bf_pitch` channels (zero padded).
+__global__ void __launch_bounds__(256)
+warp_kernel(const float* __restrict__ src, int n, int c, int h, int w, int ho, int wo,
+            const float* __restrict__ T, float* __restrict__ dst, __nv_bfloat16* __restrict__ dst_bf,
+            int bf_pitch) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int b = blockIdx.z;
+  if (x >= wo) return;
+  const float* t = T + b * 9;
+  // create_meshgrid(normalized): (i / (n-1) - 0.5) * 2
+  const float xn = ((float)x / (float)(wo - 1) - 0.5f) * 2.0f;
+  const float yn = ((float)y / (float)(ho - 1) - 0.5f) * 2.0f;
+  const float q0 = xn * t[0] + yn * t[1] + t[2];
+  const float q1 = xn * t[3] + yn * t[4] + t[5];
+  const float q2 = xn * t[6] + yn * t[7] + t[8];
+  const float sc = fabsf(q2) > 1e-8f ? 1.0f / (q2 + 1e-8f) : 1.0f;
+  const float gx = q0 * sc, gy = q1 * sc;
+  // F.grid_sample(bilinear, zeros, align_corners=True)
+  const float ix = ((gx + 1.0f) / 2.0f) * (float)(w - 1);
+  const float iy = ((gy + 1.0f) / 2.0f) * (float)(h - 1);
+  const float fx = floorf(ix), fy = floorf(iy);
+  const float wx1 = ix - fx, wx0 = (fx + 1.0f) - ix;
+  const float wy1 = iy - fy, wy0 = (fy + 1.0f) - iy;
+  const float w_nw = wx0 * wy0, w_ne = wx1 * wy0, w_sw = wx0 * wy1, w_se = wx1 * wy1;
+  // guard the int conversion against far-away coordinates
+  const bool finite = fabsf(ix) < 1e9f && fabsf(iy) < 1e9f;
+  const int x0 = finite ? (int)fx : -10, y0 = finite ? (int)fy : -10;
+  const bool in_x0 = x0 >= 0 && x0 < w, in_x1 = x0 + 1 >= 0 && x0 + 1 < w;
+  const bool in_y0 = y0 >= 0 && y0 < h, in_y1 = y0 + 1 >= 0 && y0 + 1 < h;
+  float vals[8];
+  for (int ch = 0; ch < c && ch < 8; ++ch) {
+    float v = 0.0f;
+    if (src) {
+      const float* s = src + ((long)(b * c + ch) * h) * w;
+      if (in_y0 && in_x0) v += s[(long)y0 * w + x0] * w_nw;
+      if (in_y0 && in_x1) v += s[(long)y0 * w + x0 + 1] * w_ne;
+      if (in_y1 && in_x0) v += s[(long)(y0 + 1) * w + x0] * w_sw;
+      if (in_y1 && in_x1) v += s[(long)(y0 + 1) * w + x0 + 1] * w_se;
+    } else {
+      if (in_y0 && in_x0) v += w_nw;
+      if (in_y0 && in_x1) v += w_ne;
+      if (in_y1 && in_x0) v += w_sw;
+      if (in_y1 && in_x1) v += w_se;
+    }
+    vals[ch] = v;
+    if (dst) dst[((long)(b * c + ch) * ho + y) * wo + x] = v;
+  }
+  if (dst_bf) {
+    __nv_bfloat16* o = dst_bf + ((long)(b * ho + y) * wo + x) * bf_pitch;
+    for (int ch = 0; ch < bf_pitch; ++ch) o[ch] = __float2bfloat16_rn(ch < c ? vals[ch] : 0.0f);
+  }
+}
+
+// ------------------------------------------------------------------ small-channel direct conv (NCHW fp32)
+constexpr int SC_MAX_CO = 8, SC_MAX_CI = 8;
+
+// out = act(conv_k(cat(in0, in1))) [-> GDN over the c_out channels]; one thread per output pixel.
+__global__ void __launch_bounds__(128)
+conv_small_kernel(const float* __restrict__ in0, int c0, const float* __restrict__ in1, int c1,
+                  int n, int h, int w, const float* __restrict__ wt, int transposed_s1,
+                  const float* __restrict__ bias, int c_out, int k, int stride, int act,
+                  int gdn, const float* __restrict__ beta, const float* __restrict__ gamma, float beta_bound,
+                  int ho, int wo, float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf, int bf_pitch) {
+  __shared__ float s_w[SC_MAX_CO * SC_MAX_CI * 25];
+  __shared__ float s_b[SC_MAX_CO], s_beta[SC_MAX_CO], s_gamma[SC_MAX_CO * SC_MAX_CO];
+  const int cin = c0 + c1, kk = k * k;
+  for (int i = threadIdx.x; i < c_out * cin * kk; i += blockDim.x) {
+    const int tap = i % kk, ci = (i / kk) % cin, co = i / (kk * cin);
+    float v;
+    if (transposed_s1) {   // ConvTranspose2d(stride 1) weight (cin, cout, k, k) == flipped conv
+      const int ky = k - 1 - tap / k, kx = k - 1 - tap % k;
+      v = wt[((ci * c_out + co) * k + ky) * k + kx];
+    } else {
+      v = wt[i];
+    }
+    s_w[i] = v;
+  }
+  if (threadIdx.x < c_out) s_b[threadIdx.x] = bias ? bias[threadIdx.x] : 0.0f;
+  if (gdn) {
+    const float ped = 1.4551915228366852e-11f;   // 2^-36
+    if (threadIdx.x < c_out) { const float b = fmaxf(beta[threadIdx.x], beta_bound); s_beta[threadIdx.x] = b * b - ped; }
+    for (int i = threadIdx.x; i < c_out * c_out; i += blockDim.x) {
+      const float g = fmaxf(gamma[i], 3.814697265625e-06f);
+      s_gamma[i] = g * g - ped;
+    }
+  }
+  __syncthreads();
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+  if (x >= wo) return;
+  float acc[SC_MAX_CO];
+#pragma unroll
+  for (int co = 0; co < SC_MAX_CO; ++co) acc[co] = co < c_out ? s_b[co] : 0.0f;
+  const int pad = k / 2;
+  for (int ci = 0; ci < cin; ++ci) {
+    const float* src = ci < c0 ? in0 + ((long)(b * c0 + ci) * h) * w : in1 + ((long)(b * c1 + (ci - c0)) * h) * w;
+    for (int ky = 0; ky < k; ++ky) {
+      const int iy = y * stride - pad + ky;
+      if (iy < 0 || iy >= h) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int ix = x * stride - pad + kx;
+        if (ix < 0 || ix >= w) continue;
+        const float v = __ldg(src + (long)iy * w + ix);
+#pragma unroll
+        for (int co = 0; co < SC_MAX_CO; ++co)
+          if (co < c_out) acc[co] = fmaf(v, s_w[(co * cin + ci) * kk + ky * k + kx], acc[co]);
+      }
+    }
+  }
+  if (act == MASIC_ACT_RELU) {
+#pragma unroll
+    for (int co = 0; co < SC_MAX_CO; ++co) acc[co] = fmaxf(acc[co], 0.0f);
+  } else if (act == MASIC_ACT_LEAKY) {
+#pragma unroll
+    for (int co = 0; co < SC_MAX_CO; ++co) acc[co] = acc[co] > 0.0f ? acc[co] : 0.01f * acc[co];
+  }
+  if (gdn) {
+    float o[SC_MAX_CO];
+#pragma unroll
+    for (int i = 0; i < SC_MAX_CO; ++i) {
+      if (i >= c_out) { o[i] = 0.0f; continue; }
+      float nrm = s_beta[i];
+      for (int j = 0; j < c_out; ++j) nrm = fmaf(s_gamma[i * c_out + j], acc[j] * acc[j], nrm);
+      o[i] = acc[i] * (gdn == MASIC_GDN_FWD ? rsqrtf(nrm) : sqrtf(nrm));
+    }
+#pragma unroll
+    for (int i = 0; i < SC_MAX_CO; ++i) acc[i] = o[i];
+  }
+  if (out)
+    for (int co = 0; co < c_out; ++co) out[((long)(b * c_out + co) * ho + y) * wo + x] = acc[co];
+  if (out_bf) {
+    __nv_bfloat16* o = out_bf + ((long)(b * ho + y) * wo + x) * bf_pitch;
+    for (int ch = 0; ch < bf_pitch; ++ch) o[ch] = __float2bfloat16_rn(ch < c_out && ch < SC_MAX_CO ? acc[ch] : 0.0f);
+  }
+}
+
+// ------------------------------------------------------------------ sub-pixel output -> NCHW (+ IGDN over 3 ch)
+// in: [N][H2][W2][pitch] fp32, channel (py*2+px)*3 + co ; out: (N,3,2*H2,2*W2)
+__global__ void __launch_bounds__(256)
+subpix_to_nchw_kernel(const float* __restrict__ in, int n, int h2, int w2, int pitch, int gdn,
+                      const float* __restrict__ beta, const float* __restrict__ gamma, float beta_bound,
+                      float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf, int bf_pitch) {
+  __shared__ float s_beta[3], s_gamma[9];
+  if (gdn && threadIdx.x < 9) {
+    const float ped = 1.4551915228366852e-11f;
+    const float g = fmaxf(gamma[threadIdx.x], 3.814697265625e-06f);
+    s_gamma[threadIdx.x] = g * g - ped;
+    if (threadIdx.x < 3) { const float b = fmaxf(beta[threadIdx.x], beta_bound); s_beta[threadIdx.x] = b * b - ped; }
+  }
+  __syncthreads();
+  const int r = blockIdx.x * blockDim.x + threadIdx.x, q = blockIdx.y, b = blockIdx.z;
+  if (r >= w2) return;
+  const float4* ip = reinterpret_cast<const float4*>(in + ((long)(b * h2 + q) * w2 + r) * pitch);
+  float v[12];
+  const float4 a0 = ip[0], a1 = ip[1], a2 = ip[2];
+  v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+  v[8] = a2.x; v[9] = a2.y; v[10] = a2.z; v[11] = a2.w;
+  const int H = 2 * h2, W = 2 * w2;
+#pragma unroll
+  for (int ph = 0; ph < 4; ++ph) {
+    float x0 = v[ph * 3], x1 = v[ph * 3 + 1], x2 = v[ph * 3 + 2];
+    if (gdn) {
+      const float s0 = x0 * x0, s1 = x1 * x1, s2 = x2 * x2;
+      const float n0 = fmaf(s_gamma[2], s2, fmaf(s_gamma[1], s1, fmaf(s_gamma[0], s0, s_beta[0])));
+      const float n1 = fmaf(s_gamma[5], s2, fmaf(s_gamma[4], s1, fmaf(s_gamma[3], s0, s_beta[1])));
+      const float n2 = fmaf(s_gamma[8], s2, fmaf(s_gamma[7], s1, fmaf(s_gamma[6], s0, s_beta[2])));
+      if (gdn == MASIC_GDN_FWD) { x0 *= rsqrtf(n0); x1 *= rsqrtf(n1); x2 *= rsqrtf(n2); }
+      else { x0 *= sqrtf(n0); x1 *= sqrtf(n1); x2 *= sqrtf(n2); }
+    }
+    const int oy = 2 * q + (ph >> 1), ox = 2 * r + (ph & 1);
+    if (out) {
+      out[((long)(b * 3 + 0) * H + oy) * W + ox] = x0;
+      out[((long)(b * 3 + 1) * H + oy) * W + ox] = x1;
+      out[((long)(b * 3 + 2) * H + oy) * W + ox] = x2;
+    }
+    if (out_bf) {
+      __nv_bfloat16* o = out_bf + ((long)(b * H + oy) * W + ox) * bf_pitch;
+      o[0] = __float2bfloat16_rn(x0); o[1] = __float2bfloat16_rn(x1); o[2] = __float2bfloat16_rn(x2);
+      for (int ch = 3; ch < bf_pitch; ++ch) o[ch] = __float2bfloat16_rn(0.0f);
+    }
+  }
+}
+
+// softmax over c (<= 8) channels of an NCHW tensor -> NCHW and/or NHWC ([pix][c]) fp32
+__global__ void __launch_bounds__(256)
+softmax_channels_kernel(const float* __restrict__ in, int n, int c, int hw, float* __restrict__ out_nchw,
+                        float* __restrict__ out_nhwc) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= (long)n * hw) return;
+  const int b = (int)(i / hw), p = (int)(i % hw);
+  float v[8], mx = -INFINITY, sum = 0.0f;
+  for (int ch = 0; ch < c; ++ch) { v[ch] = in[((long)(b * c + ch)) * hw + p]; mx = fmaxf(mx, v[ch]); }
+  for (int ch = 0; ch < c; ++ch) { v[ch] = expf(v[ch] - mx); sum += v[ch]; }
+  for (int ch = 0; ch < c; ++ch) {
+    const float o = v[ch] / sum;
+    if (out_nchw) out_nchw[((long)(b * c + ch)) * hw + p] = o;
+    if (out_nhwc) out_nhwc[i * c + ch] = o;
+  }
+}
+
+// NCHW fp32 (c <= 8 real channels) -> NHWC bf16 with `pitch` channels, zero padded
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, int n, int c, int hw, __nv_bfloat16* __restrict__ out,
+                         int pitch) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= (long)n * hw) return;
+  const int b = (int)(i / hw), p = (int)(i % hw);
+  __nv_bfloat16* o = out + i * pitch;
+  for (int ch = 0; ch < pitch; ++ch)
+    o[ch] = __float2bfloat16_rn(ch < c ? in[((long)(b * c + ch)) * hw + p] : 0.0f);
+}
+
+// generic tiled transpose between NHWC and NCHW fp32 (c arbitrary)
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_f32_kernel(const float* __restrict__ in, int c, int hw, int in_pitch, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int p = p0 + j, ch = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (p < hw && ch < c) ? in[((long)b * hw + p) * in_pitch + ch] : 0.0f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int ch = c0 + j, p = p0 + threadIdx.x;
+    if (p < hw && ch < c) out[((long)(b * c + ch)) * hw + p] = tile[threadIdx.x][j];
+  }
+}
+
+}  // namespace
+
+extern "C" int masic_warp_prepare(const float* m_3x3, int batch, int h, int w, int h_out, int w_out,
+                                  int invert_m, float* t_out, void* stream) {
+  if (!m_3x3 || !t_out || batch <= 0) return MASIC_EINVAL;
+  warp_prepare_kernel<<<(batch + 31) / 32, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      m_3x3, batch, h, w, h_out, w_out, invert_m, t_out);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int masic_warp_perspective_fwd(const float* src, int n, int c, int h, int w, int h_out,
+                                          int w_out, const float* t_prepared, float* dst_nchw,
+                                          void* dst_nhwc_bf16, int bf_pitch, void* stream) {
+  if (!t_prepared || n <= 0 || c <= 0 || c > 8 || (!dst_nchw && !dst_nhwc_bf16)) return MASIC_EINVAL;
+  if (h_out < 2 || w_out < 2) return MASIC_ENOSUP;
+  dim3 grid((w_out + 255) / 256, h_out, n);
+  warp_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, n, c, h, w, h_out, w_out, t_prepared, dst_nchw, static_cast<__nv_bfloat16*>(dst_nhwc_bf16),
+      bf_pitch);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int masic_conv_small_nchw(const float* in0, int c0, const float* in1, int c1, int n, int h,
+                                     int w, const float* weight, int transposed_s1, const float* bias,
+                                     int c_out, int ksize, int stride, int act, int gdn, const float* beta,
+                                     const float* gamma, float beta_min, float* out_nchw,
+                                     void* out_nhwc_bf16, int bf_pitch, void* stream) {
+  if (!in0 || !weight || c_out <= 0 || c_out > SC_MAX_CO || c0 + c1 > SC_MAX_CI || c0 <= 0) return MASIC_EINVAL;
+  if ((ksize != 3 && ksize != 5 && ksize != 1) || (stride != 1 && stride != 2)) return MASIC_EINVAL;
+  if (c1 > 0 && !in1) return MASIC_EINVAL;
+  if (gdn && (!beta || !gamma)) return MASIC_EINVAL;
+  if (transposed_s1 && stride != 1) return MASIC_EINVAL;
+  const int ho = (h + stride - 1) / stride, wo = (w + stride - 1) / stride;
+  dim3 grid((wo + 127) / 128, ho, n);
+  conv_small_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      in0, c0, in1, c1, n, h, w, weight, transposed_s1, bias, c_out, ksize, stride, act, gdn, beta, gamma,
+      sqrtf(beta_min + 1.4551915228366852e-11f), ho, wo, out_nchw,
+      static_cast<__nv_bfloat16*>(out_nhwc_bf16), bf_pitch);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int masic_subpix_to_nchw(const float* in_nhwc, int n, int h2, int w2, int pitch, int gdn,
+                                    const float* beta, const float* gamma, float beta_min, float* out_nchw,
+                                    void* out_nhwc_bf16, int bf_pitch, void* stream) {
+  if (!in_nhwc || pitch < 12 || pitch % 4 || n <= 0) return MASIC_EINVAL;
+  if (gdn && (!beta || !gamma)) return MASIC_EINVAL;
+  dim3 grid((w2 + 255) / 256, h2, n);
+  subpix_to_nchw_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in_nhwc, n, h2, w2, pitch, gdn, beta, gamma, sqrtf(beta_min + 1.4551915228366852e-11f), out_nchw,
+      static_cast<__nv_bfloat16*>(out_nhwc_bf16), bf_pitch);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int masic_softmax_channels(const float* in_nchw, int n, int c, int hw, float* out_nchw,
+                                      float* out_nhwc, void* stream) {
+  if (!in_nchw || c <= 0 || c > 8 || n <= 0 || hw <= 0) return MASIC_EINVAL;
+  const long total = (long)n * hw;
+  softmax_channels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in_nchw, n, c, hw, out_nchw, out_nhwc);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int masic_nchw_to_nhwc_bf16(const float* in_nchw, int n, int c, int hw, void* out, int pitch,
+                                       void* stream) {
+  if (!in_nchw || !out || c <= 0 || c > pitch || pitch > 64) return MASIC_EINVAL;
+  const long total = (long)n * hw;
+  nchw_to_nhwc_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in_nchw, n, c, hw, static_cast<__nv_bfloat16*>(out), pitch);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int masic_nhwc_to_nchw_f32(const float* in_nhwc, int n, int c, int hw, int in_pitch,
+                                      float* out_nchw, void* stream) {
+  if (!in_nhwc || !out_nchw || n <= 0 || c <= 0 || hw <= 0 || in_pitch < c) return MASIC_EINVAL;
+  dim3 grid((hw + 31) / 32, (c + 31) / 32, n), block(32, 8);
+  nhwc_to_nchw_f32_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(in_nhwc, c, hw, in_pitch,
+                                                                               out_nchw);
+  return (int)cudaGetLastError();
+}

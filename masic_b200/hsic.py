@@ -1,0 +1,215 @@
+"""HSIC — MASIC's stereo codec model on the B200-native engine.
+
+Same public surface as the reference's `HSIC(CompressionModel)`
+(coremasic/mywork/MASIC.py:40-110, 652-851): constructor `HSIC(N=128, M=192, K=5)`,
+`forward(x1, x2, h_matrix) -> dict`, `update(force)`, `aux_loss()`, `parameters()` /
+`aux_parameters()` split, and a `state_dict()` with the reference's 248 entries (names,
+shapes, dtypes), so checkpoints move both ways.  Parameters are created in the reference's
+order with the same initialisers, hence `torch.manual_seed(s); HSIC()` draws the same
+weights as the reference.
+
+`forward` does not execute the module tree: it hands the state_dict to an `HSICEngine`
+(masic_b200/engine.py) compiled for the input's (batch, H, W) and replays its CUDA graph.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from ._lib import MasicError
+from .engine import HSICEngine
+from .entropy_models import EntropyBottleneck, GaussianMixtureConditional_gf
+from .layers import GDN, MaskedConv2d, conv, deconv
+
+
+class _Block(nn.Module):
+    """Parameter container (the engine, not the module tree, executes the forward pass)."""
+
+
+def _encoder(N: int, M: int, second_view: bool) -> nn.Module:
+    b = _Block()
+    if second_view:                       # MASIC.py:559-560
+        b.pre_conv = conv(6, 3, stride=1)
+        b.pre_gdn = GDN(3)
+    b.g_a_conv1 = conv(3, N)              # MASIC.py:513-519 / :562-568
+    b.g_a_gdn1 = GDN(N)
+    b.g_a_conv2 = conv(N, N)
+    b.g_a_gdn2 = GDN(N)
+    b.g_a_conv3 = conv(N, N)
+    b.g_a_gdn3 = GDN(N)
+    b.g_a_conv4 = conv(N, M)
+    return b
+
+
+def _decoder(N: int, M: int, second_view: bool) -> nn.Module:
+    b = _Block()
+    b.g_s_conv1 = deconv(M, N)            # MASIC.py:536-542 / :590-596
+    b.g_s_gdn1 = GDN(N, inverse=True)
+    b.g_s_conv2 = deconv(N, N)
+    b.g_s_gdn2 = GDN(N, inverse=True)
+    b.g_s_conv3 = deconv(N, N)
+    b.g_s_gdn3 = GDN(N, inverse=True)
+    b.g_s_conv4 = deconv(N, 3)
+    if second_view:                       # MASIC.py:599-600
+        b.after_gdn = GDN(3, inverse=True)
+        b.after_conv = deconv(6, 3, stride=1)
+    return b
+
+
+def _hyper_analysis(N: int, M: int) -> nn.Module:
+    b = _Block()                          # MASIC.py:170-183
+    b.encode_hyper = nn.Sequential(conv(M, N, kernel_size=5, stride=1), nn.ReLU(inplace=True),
+                                   conv(N, N, kernel_size=5), nn.ReLU(inplace=True), conv(N, N, kernel_size=5))
+    return b
+
+
+def _hyper_synthesis_up(N: int, M: int) -> nn.Sequential:
+    return nn.Sequential(deconv(N, M, stride=2, kernel_size=5), nn.LeakyReLU(inplace=True),   # MASIC.py:678-691
+                         deconv(M, M * 3 // 2, stride=2, kernel_size=5), nn.LeakyReLU(inplace=True),
+                         conv(M * 3 // 2, M * 2, stride=1, kernel_size=3))
+
+
+def _gmm_param_net(N: int, M: int, K: int, c_in: int, transposed_head: bool) -> nn.Module:
+    """MASIC.py:330-376 (y1: ConvTranspose2d k=1 for the first two layers) / :399-444 (y2)."""
+    head = deconv if transposed_head else conv
+    b = _Block()
+    b.N, b.M, b.K = N, M, K
+    b.gmm_sigma = nn.Sequential(head(c_in, 6 * M, kernel_size=1, stride=1), nn.ReLU(inplace=True),
+                                head(6 * M, 4 * M, kernel_size=1, stride=1), nn.ReLU(inplace=True),
+                                conv(4 * M, M * K, kernel_size=1, stride=1), nn.ReLU(inplace=True))
+    b.gmm_means = nn.Sequential(head(c_in, 6 * M, kernel_size=1, stride=1), nn.LeakyReLU(inplace=True),
+                                head(6 * M, 4 * M, kernel_size=1, stride=1), nn.LeakyReLU(inplace=True),
+                                conv(4 * M, M * K, kernel_size=1, stride=1))
+    b.gmm_weights = nn.Sequential(head(c_in, 6 * M, kernel_size=1, stride=1), nn.LeakyReLU(inplace=True),
+                                  head(6 * M, M * K, kernel_size=1, stride=1), nn.LeakyReLU(inplace=True),
+                                  conv(M * K, M * K, kernel_size=1, stride=1))
+    return b
+
+
+def _mask2weights(Kw: int = 3) -> nn.Module:
+    b = _Block()                          # MASIC.py:472-491
+    b.maskconv = nn.Sequential(conv(1, 3, kernel_size=3, stride=2), nn.ReLU(inplace=True),
+                               conv(3, 6, kernel_size=3), nn.ReLU(inplace=True),
+                               conv(6, 6, kernel_size=3), nn.ReLU(inplace=True), conv(6, 3, kernel_size=3))
+    b.Kw = Kw
+    return b
+
+
+class HSIC(nn.Module):
+    def __init__(self, N: int = 128, M: int = 192, K: int = 5, use_cuda_graph: bool = True, **kwargs):
+        super().__init__()
+        self.entropy_bottleneck1 = EntropyBottleneck(N)          # MASIC.py:50-54
+        self.entropy_bottleneck2 = EntropyBottleneck(N)
+        self.gaussian1 = GaussianMixtureConditional_gf(K=K)      # :658-659
+        self.gaussian2 = GaussianMixtureConditional_gf(K=K)
+        self.N, self.M, self.K = int(N), int(M), int(K)
+        self.encoder1 = _encoder(N, M, False)                    # :664-667
+        self.encoder2 = _encoder(N, M, True)
+        self.decoder1 = _decoder(N, M, False)
+        self.decoder2 = _decoder(N, M, True)
+        self._h_a1 = _hyper_analysis(N, M)                       # :672-673
+        self._h_a2 = _hyper_analysis(N, M)
+        self.h_s1_up = _hyper_synthesis_up(N, M)                 # :678-691
+        self.h_s2_up = _hyper_synthesis_up(N, M)
+        self.context_prediction1 = MaskedConv2d(M, 2 * M, kernel_size=5, padding=2, stride=1)   # :693-703
+        self.context_prediction2 = MaskedConv2d(M, 2 * M, kernel_size=5, padding=2, stride=1)
+        self._h_s1_same_resolution = _gmm_param_net(N, M, K, 4 * M, True)                         # :704-705
+        self._h_s2_same_resolution = _gmm_param_net(N, M, K, 5 * M, False)
+        self.mask2weights_unit = _mask2weights(3)                # :706
+        self._use_graph = use_cuda_graph
+        self._engines: Dict[Tuple, HSICEngine] = {}
+        self._engine_version = 0
+
+    # ---- CompressionModel surface (MASIC.py:59-109)
+    def aux_loss(self):
+        return sum(m.loss() for m in self.modules() if isinstance(m, EntropyBottleneck))
+
+    def parameters(self, recurse: bool = True):
+        for m in self.children():
+            if isinstance(m, EntropyBottleneck):
+                continue
+            for p in m.parameters():
+                yield p
+
+    def aux_parameters(self):
+        for m in self.children():
+            if not isinstance(m, EntropyBottleneck):
+                continue
+            for p in m.parameters():
+                yield p
+
+    def update(self, force: bool = False):
+        for m in self.children():
+            if isinstance(m, EntropyBottleneck):
+                m.update(force=force)
+
+    # ---- engine management
+    def _weights_fingerprint(self):
+        return tuple(p._version for p in nn.Module.parameters(self))
+
+    def invalidate_engines(self):
+        """Call after mutating weights in place (load_state_dict does it automatically)."""
+        self._engines.clear()
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        # CDF buffers are empty (0,) tensors in checkpoints until update(): resize to fit
+        for name in ("entropy_bottleneck1", "entropy_bottleneck2", "gaussian1", "gaussian2"):
+            mod = getattr(self, name)
+            for buf in ("_offset", "_quantized_cdf", "_cdf_length", "scale_table"):
+                key = f"{name}.{buf}"
+                if key in state_dict and hasattr(mod, buf):
+                    cur = getattr(mod, buf)
+                    if cur.shape != state_dict[key].shape:
+                        setattr(mod, buf, torch.empty(state_dict[key].shape, dtype=cur.dtype, device=cur.device))
+        res = super().load_state_dict(state_dict, strict=strict, **kw)
+        self.invalidate_engines()
+        return res
+
+    def engine_for(self, batch: int, height: int, width: int, device) -> HSICEngine:
+        key = (batch, height, width, str(device), self._weights_fingerprint())
+        eng = self._engines.get(key)
+        if eng is None:
+            self._engines.clear()
+            # MaskedConv2d side effect of the reference's forward (layers.py:77): weight.data *= mask
+            with torch.no_grad():
+                for cp in (self.context_prediction1, self.context_prediction2):
+                    cp.weight.data *= cp.mask
+            key = (batch, height, width, str(device), self._weights_fingerprint())
+            eng = HSICEngine(self.state_dict(), batch, height, width, device, self.N, self.M, self.K,
+                             use_graph=self._use_graph)
+            self._engines[key] = eng
+        return eng
+
+    # ---- forward (MASIC.py:744-851)
+    def forward(self, x1: torch.Tensor, x2: torch.Tensor, h_matrix: torch.Tensor, clone: bool = True):
+        if self.training:
+            raise MasicError("HSIC.forward: masic_b200 implements the inference path (model.eval()); "
+                             "the training step (noise quantisation + backward kernels) is not built yet")
+        if not x1.is_cuda:
+            raise MasicError("HSIC.forward needs CUDA tensors: masic_b200 has no CPU fallback")
+        b, _, h, w = x1.shape
+        eng = self.engine_for(b, h, w, x1.device)
+        o = eng.run(x1, x2, h_matrix)
+        c = (lambda t: t.clone()) if clone else (lambda t: t)
+        return {
+            "x1_hat": c(o["x1_hat"]), "x2_hat": c(o["x2_hat"]),
+            "y1_hat": c(o["y1_hat"]), "z1_hat": c(o["z1_hat"]),
+            "x1_mask_R": c(o["x1_mask_R"]), "x1_mask_L": c(o["x1_mask_L"]),
+            "likelihoods": {"y1": c(o["lik_y1"]), "y2": c(o["lik_y2"]), "z1": c(o["lik_z1"]), "z2": c(o["lik_z2"])},
+        }
+
+
+def bpp_and_psnr(out: Dict, x1: torch.Tensor, x2: torch.Tensor):
+    """The criterion the reference's eval script applies to forward()'s output
+    (coremasic/mywork/test2_real.py:88-114): bpp from the likelihoods, PSNR per view."""
+    n, _, h, w = x1.shape
+    num_pixels = n * h * w
+    bpp = sum(torch.log(l).sum() / (-math.log(2) * num_pixels) for l in out["likelihoods"].values())
+    mse1 = torch.mean((out["x1_hat"] - x1) ** 2)
+    mse2 = torch.mean((out["x2_hat"] - x2) ** 2)
+    psnr1 = 10.0 * torch.log10(1.0 / mse1)
+    psnr2 = 10.0 * torch.log10(1.0 / mse2)
+    return bpp, psnr1, psnr2
