@@ -1,0 +1,112 @@
+"""GPU parity of the image-domain kernels (warp, masks, small convs, GDN, packs) against oracle/
+and torch fp32 on the same inputs.  Warp is a tolerance item (kornia is un-vendored: the
+restatement in oracle/shims is the specification) — WARP_ATOL on [0,1] images."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+WARP_ATOL = 1e-4
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    from masic_b200 import _lib
+    _lib.load()
+    return torch.device("cuda:0")
+
+
+def test_warp_and_masks_match_fixture(dev, golden_dir):
+    from masic_b200 import ops
+    fx = np.load(golden_dir / "warp.npz")
+    img, Hm = _t(fx["img"]).to(dev), _t(fx["H"]).to(dev)
+    out, out_bf = ops.warp_perspective(img, Hm, (40, 56), bf16_pitch=16)
+    assert (out.cpu() - _t(fx["warped"])).abs().max() <= WARP_ATOL
+    assert (out_bf[..., :3].float().permute(0, 3, 1, 2).cpu() - _t(fx["warped"])).abs().max() <= 5e-3
+    assert float(out_bf[..., 3:].abs().max()) == 0.0
+    m_r = ops.warp_perspective(None, Hm, (40, 56), ones_shape=(2, 1, 40, 56))
+    m_l = ops.warp_perspective(m_r, Hm, (40, 56), invert=True)
+    assert (m_r.cpu() - _t(fx["mask_R"])).abs().max() <= WARP_ATOL
+    assert (m_l.cpu() - _t(fx["mask_L"])).abs().max() <= WARP_ATOL
+
+
+@pytest.mark.parametrize("h,w", [(128, 192), (1216, 2176)])
+def test_warp_against_oracle(dev, h, w):
+    from masic_b200 import ops
+    from oracle import hsic as OH
+    g = torch.Generator().manual_seed(2)
+    img = torch.rand(1, 3, h, w, generator=g)
+    img = F.avg_pool2d(img, 3, 1, 1)                      # mild low-pass so the warp is non-trivial but smooth
+    Hm = OH.synthetic_homography(1, seed=1)
+    ref = OH.warp(img, Hm)
+    out = ops.warp_perspective(img.to(dev), Hm.to(dev), (h, w))
+    assert (out.cpu() - ref).abs().max() <= WARP_ATOL
+    # identity homography reproduces the image (to interpolation rounding)
+    ident = ops.warp_perspective(img.to(dev), torch.eye(3, device=dev)[None], (h, w))
+    assert (ident.cpu() - img).abs().max() <= 2e-4
+
+
+def test_small_convs_against_torch(dev):
+    from masic_b200 import ops
+    from masic_b200.ops import ACT_RELU, GDN_FWD
+    from oracle import hsic as OH
+    torch.manual_seed(4)
+    a, b = torch.rand(2, 3, 40, 56), torch.rand(2, 3, 40, 56)
+    pre = torch.nn.Conv2d(6, 3, 5, 1, 2)
+    beta = OH.nonneg_init(torch.ones(3) + torch.rand(3))
+    gamma = OH.nonneg_init(0.1 * torch.eye(3) + torch.rand(3, 3) * 0.02)
+    with torch.no_grad():
+        ref = OH.gdn(pre(torch.cat((a, b), 1)), beta, gamma, False)
+    out_bf = torch.empty(2, 40, 56, 16, dtype=torch.bfloat16, device=dev)
+    out = torch.empty(2, 3, 40, 56, device=dev)
+    ops.conv_small(a.to(dev), b.to(dev), pre.weight.to(dev), pre.bias.to(dev), ksize=5, stride=1, gdn=GDN_FWD,
+                   beta=beta.to(dev), gamma=gamma.to(dev), out=out, out_bf16=out_bf)
+    assert (out.cpu() - ref).abs().max() <= 2e-5
+    assert (out_bf[..., :3].float().permute(0, 3, 1, 2).cpu() - ref).abs().max() <= 8e-3
+    # ConvTranspose2d(6, 3, 5, stride=1) == after_conv (MASIC.py:600)
+    post = torch.nn.ConvTranspose2d(6, 3, 5, 1, 2)
+    with torch.no_grad():
+        ref2 = post(torch.cat((a, b), 1))
+    out2 = ops.conv_small(a.to(dev), b.to(dev), post.weight.to(dev), post.bias.to(dev), ksize=5, stride=1,
+                          transposed_s1=True)
+    assert (out2.cpu() - ref2).abs().max() <= 2e-5
+    # mask2weights layer: conv3 s2 + ReLU on an odd-sized map
+    m = torch.rand(1, 1, 37, 51)
+    c = torch.nn.Conv2d(1, 3, 3, 2, 1)
+    with torch.no_grad():
+        ref3 = F.relu(c(m))
+    out3 = ops.conv_small(m.to(dev), None, c.weight.to(dev), c.bias.to(dev), ksize=3, stride=2, act=ACT_RELU)
+    assert out3.shape == ref3.shape and (out3.cpu() - ref3).abs().max() <= 1e-5
+    sm, sm_nhwc = ops.softmax_channels(out3, nhwc_out=True)
+    assert torch.allclose(sm.cpu(), torch.softmax(ref3, 1), atol=1e-6)
+    assert torch.equal(sm_nhwc.permute(0, 3, 1, 2), sm)
+
+
+def test_standalone_gdn_matches_reference_fixture(dev, golden_dir):
+    from masic_b200.layers import GDN
+    fx = np.load(golden_dir / "gdn.npz")
+    for tag, inv in (("gdn", False), ("igdn", True)):
+        layer = GDN(12, inverse=inv).eval()
+        with torch.no_grad():
+            layer.beta.copy_(_t(fx[f"{tag}/beta"]))
+            layer.gamma.copy_(_t(fx[f"{tag}/gamma"]))
+        layer = layer.to(dev)
+        with torch.no_grad():
+            y = layer(_t(fx[f"{tag}/x"]).to(dev))
+        assert torch.allclose(y.cpu(), _t(fx[f"{tag}/y"]), rtol=2e-5, atol=1e-6)
+
+
+def test_layout_packs_round_trip(dev):
+    from masic_b200 import ops
+    x = torch.rand(2, 3, 17, 23, device=dev)
+    p = ops.nchw_to_nhwc_bf16(x, 16)
+    assert torch.equal(p[..., :3].permute(0, 3, 1, 2).float(), x.to(torch.bfloat16).float())
+    assert float(p[..., 3:].abs().max()) == 0
+    y = torch.rand(2, 9, 11, 200, device=dev)
+    assert torch.equal(ops.nhwc_to_nchw_f32(y, 192), y[..., :192].permute(0, 3, 1, 2))
