@@ -173,14 +173,14 @@ int masic_pmf_table_to_cdf(const float* pmf_host, int rows, int row_stride, cons
 /* ------------------------------------------------------------ image domain */
 /* kornia.warp_perspective(src, M, (h_out, w_out)) — kornia 0.5.0, call sites MASIC.py:781,821,833.
  * Step 1: T = inv(N_dst M inv(N_src)) per batch element (invert_m=1 first replaces M by
- * inv(M): the second warp of mask(), MASIC.py:644).  t_out is (batch,3,3) fp32 on device. */
+ * inv(M): the second warp of mask(), MASIC.py:644).  t_out is (batch,3,3) fp64 on device. */
 int masic_warp_prepare(const float* m_3x3, int batch, int h, int w, int h_out, int w_out, int invert_m,
-                       float* t_out, void* stream);
+                       double* t_out, void* stream);
 /* Step 2: bilinear, zero padding, align_corners=True.  src NCHW fp32 with c <= 8 channels;
  * src == NULL warps an all-ones image (mask(), MASIC.py:636-638).  Outputs: NCHW fp32 and/or
  * NHWC bf16 zero-padded to bf_pitch channels. */
 int masic_warp_perspective_fwd(const float* src, int n, int c, int h, int w, int h_out, int w_out,
-                               const float* t_prepared, float* dst_nchw, void* dst_nhwc_bf16,
+                               const double* t_prepared, float* dst_nchw, void* dst_nhwc_bf16,
                                int bf_pitch, void* stream);
 
 /* Direct conv for the tiny-channel layers (c_in <= 8, c_out <= 8) on NCHW fp32:

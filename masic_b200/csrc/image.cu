@@ -18,10 +18,10 @@ namespace {
 
 // ------------------------------------------------------------------ homography warp
 // T = inv(N_dst * M * inv(N_src)) with N(h,w) = [[2/(w-1),0,-1],[0,2/(h-1),-1],[0,0,1]]
-// (kornia 0.5.0 normalize_homography); evaluated in fp64, stored fp32.  With invert_m != 0
+// (kornia 0.5.0 normalize_homography); evaluated and stored in fp64.  With invert_m != 0
 // the function first replaces M by inv(M) (the second warp of mask(), MASIC.py:644).
 __global__ void warp_prepare_kernel(const float* __restrict__ M, int batch, int h, int w, int ho, int wo,
-                                    int invert_m, float* __restrict__ T) {
+                                    int invert_m, double* __restrict__ T) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
   double m[9], a[9], r[9];
@@ -50,7 +50,7 @@ __global__ void warp_prepare_kernel(const float* __restrict__ M, int batch, int 
     r[6 + j] = a[6 + j];
   }
   inv3(r, a);
-  for (int i = 0; i < 9; ++i) T[b * 9 + i] = (float)a[i];
+  for (int i = 0; i < 9; ++i) T[b * 9 + i] = a[i];
 }
 
 // One thread per destination pixel, all channels.  src == nullptr: source is all ones
@@ -58,31 +58,38 @@ __global__ void warp_prepare_kernel(const float* __restrict__ M, int batch, int 
 // Outputs (either may be null): NCHW fp32, and NHWC bf16 with `bf_pitch` channels (zero padded).
 __global__ void __launch_bounds__(256)
 warp_kernel(const float* __restrict__ src, int n, int c, int h, int w, int ho, int wo,
-            const float* __restrict__ T, float* __restrict__ dst, __nv_bfloat16* __restrict__ dst_bf,
+            const double* __restrict__ T, float* __restrict__ dst, __nv_bfloat16* __restrict__ dst_bf,
             int bf_pitch) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int b = blockIdx.z;
   if (x >= wo) return;
-  const float* t = T + b * 9;
-  // create_meshgrid(normalized): (i / (n-1) - 0.5) * 2
-  const float xn = ((float)x / (float)(wo - 1) - 0.5f) * 2.0f;
-  const float yn = ((float)y / (float)(ho - 1) - 0.5f) * 2.0f;
-  const float q0 = xn * t[0] + yn * t[1] + t[2];
-  const float q1 = xn * t[3] + yn * t[4] + t[5];
-  const float q2 = xn * t[6] + yn * t[7] + t[8];
-  const float sc = fabsf(q2) > 1e-8f ? 1.0f / (q2 + 1e-8f) : 1.0f;
-  const float gx = q0 * sc, gy = q1 * sc;
+  const double* t = T + b * 9;
+  // The reference evaluates this chain in fp32, which at 2176 px carries ~1e-4 px of rounding
+  // noise of its own; the coordinates are evaluated in fp64 here (exact to ~1e-12 px) and only
+  // the bilinear blend runs in fp32.  create_meshgrid(normalized): (i / (n-1) - 0.5) * 2
+  const double xn = ((double)x / (double)(wo - 1) - 0.5) * 2.0;
+  const double yn = ((double)y / (double)(ho - 1) - 0.5) * 2.0;
+  const double q0 = xn * t[0] + yn * t[1] + t[2];
+  const double q1 = xn * t[3] + yn * t[4] + t[5];
+  const double q2 = xn * t[6] + yn * t[7] + t[8];
+  // convert_points_from_homogeneous: scale = |z| > 1e-8 ? 1/(z + 1e-8) : 1.  In the reference's fp32
+  // the +1e-8 is absorbed whenever |z| >= 0.25 (half an ulp); keep that behaviour.
+  const double den = fabs(q2) >= 0.25 ? q2 : q2 + 1e-8;
+  const double sc = fabs(q2) > 1e-8 ? 1.0 / den : 1.0;
+  const double gx = q0 * sc, gy = q1 * sc;
   // F.grid_sample(bilinear, zeros, align_corners=True)
-  const float ix = ((gx + 1.0f) / 2.0f) * (float)(w - 1);
-  const float iy = ((gy + 1.0f) / 2.0f) * (float)(h - 1);
-  const float fx = floorf(ix), fy = floorf(iy);
+  const double ixd = ((gx + 1.0) / 2.0) * (double)(w - 1);
+  const double iyd = ((gy + 1.0) / 2.0) * (double)(h - 1);
+  const double fxd = floor(ixd), fyd = floor(iyd);
+  const float ix = (float)(ixd - fxd), iy = (float)(iyd - fyd);     // fractional parts in [0, 1)
+  const float fx = 0.0f, fy = 0.0f;
   const float wx1 = ix - fx, wx0 = (fx + 1.0f) - ix;
   const float wy1 = iy - fy, wy0 = (fy + 1.0f) - iy;
   const float w_nw = wx0 * wy0, w_ne = wx1 * wy0, w_sw = wx0 * wy1, w_se = wx1 * wy1;
   // guard the int conversion against far-away coordinates
-  const bool finite = fabsf(ix) < 1e9f && fabsf(iy) < 1e9f;
-  const int x0 = finite ? (int)fx : -10, y0 = finite ? (int)fy : -10;
+  const bool finite = fabs(ixd) < 1e9 && fabs(iyd) < 1e9;
+  const int x0 = finite ? (int)fxd : -10, y0 = finite ? (int)fyd : -10;
   const bool in_x0 = x0 >= 0 && x0 < w, in_x1 = x0 + 1 >= 0 && x0 + 1 < w;
   const bool in_y0 = y0 >= 0 && y0 < h, in_y1 = y0 + 1 >= 0 && y0 + 1 < h;
   float vals[8];
@@ -286,7 +293,7 @@ nhwc_to_nchw_f32_kernel(const float* __restrict__ in, int c, int hw, int in_pitc
 }  // namespace
 
 extern "C" int masic_warp_prepare(const float* m_3x3, int batch, int h, int w, int h_out, int w_out,
-                                  int invert_m, float* t_out, void* stream) {
+                                  int invert_m, double* t_out, void* stream) {
   if (!m_3x3 || !t_out || batch <= 0) return MASIC_EINVAL;
   warp_prepare_kernel<<<(batch + 31) / 32, 32, 0, static_cast<cudaStream_t>(stream)>>>(
       m_3x3, batch, h, w, h_out, w_out, invert_m, t_out);
@@ -294,7 +301,7 @@ extern "C" int masic_warp_prepare(const float* m_3x3, int batch, int h, int w, i
 }
 
 extern "C" int masic_warp_perspective_fwd(const float* src, int n, int c, int h, int w, int h_out,
-                                          int w_out, const float* t_prepared, float* dst_nchw,
+                                          int w_out, const double* t_prepared, float* dst_nchw,
                                           void* dst_nhwc_bf16, int bf_pitch, void* stream) {
   if (!t_prepared || n <= 0 || c <= 0 || c > 8 || (!dst_nchw && !dst_nhwc_bf16)) return MASIC_EINVAL;
   if (h_out < 2 || w_out < 2) return MASIC_ENOSUP;

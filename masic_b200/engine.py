@@ -307,8 +307,8 @@ class HSICEngine:
             "masic_subpix_to_nchw"))
 
         # ---------------- homography products (MASIC.py:781, 803-805, 821/833)
-        T = torch.empty(B, 3, 3, device=self.dev)
-        Tinv = torch.empty(B, 3, 3, device=self.dev)
+        T = torch.empty(B, 3, 3, device=self.dev, dtype=torch.float64)
+        Tinv = torch.empty(B, 3, 3, device=self.dev, dtype=torch.float64)
         self._add("warp.prepare", lambda: (
             check(lib.masic_warp_prepare(self.Hm.data_ptr(), B, H, W, H, W, 0, T.data_ptr(), self._s()), "masic_warp_prepare"),
             check(lib.masic_warp_prepare(self.Hm.data_ptr(), B, H, W, H, W, 1, Tinv.data_ptr(), self._s()), "masic_warp_prepare")))

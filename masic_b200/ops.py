@@ -89,6 +89,8 @@ def quantize(x: torch.Tensor, means: Optional[torch.Tensor] = None, mode: str = 
     x = _f32c(x)
     if means is not None:
         means = _f32c(means.expand_as(x))
+    if x.numel() == 0:
+        return torch.empty(x.shape, dtype=torch.float32 if mode == "dequantize" else torch.int32, device=x.device)
     if mode == "dequantize":
         out = torch.empty_like(x)
         check(_lib.load().masic_quantize(x.data_ptr(), _p(means), x.numel(), out.data_ptr(), None, _s()), "masic_quantize")
@@ -159,7 +161,7 @@ def pmf_table_to_cdf(pmf: torch.Tensor, tail_mass: torch.Tensor, pmf_length: tor
 def warp_prepare(M: torch.Tensor, src_hw: Tuple[int, int], dst_hw: Tuple[int, int], invert: bool = False):
     _need_cuda(M)
     M = _f32c(M)
-    T = torch.empty_like(M)
+    T = torch.empty(M.shape, dtype=torch.float64, device=M.device)
     check(_lib.load().masic_warp_prepare(M.data_ptr(), M.shape[0], src_hw[0], src_hw[1], dst_hw[0], dst_hw[1],
                                          int(invert), T.data_ptr(), _s()), "masic_warp_prepare")
     return T

@@ -36,8 +36,32 @@ def test_warp_and_masks_match_fixture(dev, golden_dir):
     assert (m_l.cpu() - _t(fx["mask_L"])).abs().max() <= WARP_ATOL
 
 
+def _warp_exact_f64(img, Hm):
+    """Ground truth: src = M^-1 dst in pixel space, bilinear, zeros outside — all in float64."""
+    b, c, h, w = img.shape
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float64), torch.arange(w, dtype=torch.float64), indexing="ij")
+    pts = torch.stack((xs, ys, torch.ones_like(xs)), -1).reshape(-1, 3)
+    out = torch.zeros(b, c, h * w, dtype=torch.float64)
+    for i in range(b):
+        q = pts @ torch.inverse(Hm[i].double()).T
+        sx, sy = q[:, 0] / q[:, 2], q[:, 1] / q[:, 2]
+        x0, y0 = torch.floor(sx), torch.floor(sy)
+        for dy in (0, 1):
+            for dx in (0, 1):
+                xi, yi = x0 + dx, y0 + dy
+                wgt = (1 - (sx - xi).abs()) * (1 - (sy - yi).abs())
+                ok = (xi >= 0) & (xi < w) & (yi >= 0) & (yi < h)
+                v = img[i].double()[:, yi.clamp(0, h - 1).long(), xi.clamp(0, w - 1).long()]
+                out[i] += v * (wgt * ok)
+    return out.view(b, c, h, w)
+
+
 @pytest.mark.parametrize("h,w", [(128, 192), (1216, 2176)])
 def test_warp_against_oracle(dev, h, w):
+    """The fp32 kornia chain (the oracle) carries rounding noise of its own that grows with the image
+    size (~2e-4 at 2176 px); the kernel evaluates coordinates in fp64.  So: the kernel must match the
+    float64 ground truth to blend rounding, and differ from the oracle by no more than the oracle
+    itself differs from the ground truth (and by <= WARP_ATOL where the oracle is that accurate)."""
     from masic_b200 import ops
     from oracle import hsic as OH
     g = torch.Generator().manual_seed(2)
@@ -45,11 +69,18 @@ def test_warp_against_oracle(dev, h, w):
     img = F.avg_pool2d(img, 3, 1, 1)                      # mild low-pass so the warp is non-trivial but smooth
     Hm = OH.synthetic_homography(1, seed=1)
     ref = OH.warp(img, Hm)
-    out = ops.warp_perspective(img.to(dev), Hm.to(dev), (h, w))
-    assert (out.cpu() - ref).abs().max() <= WARP_ATOL
+    exact = _warp_exact_f64(img, Hm)
+    out = ops.warp_perspective(img.to(dev), Hm.to(dev), (h, w)).cpu()
+    e_oracle = float((ref.double() - exact).abs().max())
+    e_cuda = float((out.double() - exact).abs().max())
+    d = float((out - ref).abs().max())
+    print(f"warp {h}x{w}: |oracle-exact|={e_oracle:.3g} |cuda-exact|={e_cuda:.3g} |cuda-oracle|={d:.3g}")
+    assert e_cuda <= 5e-6
+    assert d <= max(WARP_ATOL, 1.5 * e_oracle)
+    assert d <= 1e-3
     # identity homography reproduces the image (to interpolation rounding)
     ident = ops.warp_perspective(img.to(dev), torch.eye(3, device=dev)[None], (h, w))
-    assert (ident.cpu() - img).abs().max() <= 2e-4
+    assert (ident.cpu() - img).abs().max() <= 1e-5
 
 
 def test_small_convs_against_torch(dev):
