@@ -40,6 +40,13 @@ METRIC = "stereo pairs/s at 1216x2176 (HSIC.forward: codec + warp/mask fusion, b
 FLOP_PER_PAIR = 1626.3e9          # BASELINE.md §2, counted on the reference with forward hooks
 
 
+CROPS = [(1216, 2176), (1216, 1088), (576, 1088), (320, 576)]   # multiples of 64 (MASIC.py:1191-1192)
+
+
+def _frac(h, w):
+    return h * w / float(H * W)
+
+
 def _peaks():
     f = ROOT / "MEASURED_PEAKS.json"
     if f.exists():
@@ -129,18 +136,20 @@ def run_reference(args, rank, world):
     model = _oracle_model()
     # calibrate the sample: a crop with area fraction f of the 1216x2176 pair (the net is fully
     # convolutional and its cost exactly linear in H*W — BASELINE.md §2), so that W+K steps fit ~2 min
-    t_probe = _cpu_forward_seconds(model, 304, 544, reps=1, warm=1)[0]      # 1/16 of the area
+    hh, ww = CROPS[-1]                                                      # H, W must stay multiples of 64
+    t_probe = _cpu_forward_seconds(model, hh, ww, reps=1, warm=1)[0]
+    per_pair = t_probe / _frac(hh, ww)
     budget = 120.0 / max(1, args.steps + args.warmup)
-    frac, hh, ww = 1.0 / 16, 304, 544
-    for f, (a, b) in ((1.0, (1216, 2176)), (0.5, (608, 2176)), (0.25, (608, 1088)), (0.125, (304, 1088))):
-        if t_probe * 16 * f <= budget:
-            frac, hh, ww = f, a, b
+    for a, b in CROPS:
+        if per_pair * _frac(a, b) <= budget:
+            hh, ww = a, b
             break
+    frac = _frac(hh, ww)
     ts = _cpu_forward_seconds(model, hh, ww, reps=args.steps, warm=args.warmup)
     total = sum(ts)
     pairs_per_s = (args.steps * frac) / total
     sample = (f"{args.steps} timed forward passes of the oracle port (torch-CPU fp32, oneDNN) on a {hh}x{ww} crop "
-              f"= {frac:g} of a 1216x2176 pair (cost is linear in H*W), {cores} threads")
+              f"= {frac:.4f} of a 1216x2176 pair (cost is linear in H*W), {cores} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": pairs_per_s, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps / frac,
@@ -280,16 +289,19 @@ def run_ours(args, rank, world, local_rank):
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         oracle = _oracle_model()
-        t_probe = _cpu_forward_seconds(oracle, 304, 544, reps=1, warm=1)[0]
-        if t_probe * 16 * 3 <= 40:
-            hh, ww, frac, reps = H, W, 1.0, 2
-        else:
-            hh, ww, frac, reps = 608, 1088, 0.25, 2
+        hh, ww = CROPS[-1]
+        per_pair = _cpu_forward_seconds(oracle, hh, ww, reps=1, warm=1)[0] / _frac(hh, ww)
+        reps = 2
+        for a, b in CROPS:
+            if per_pair * _frac(a, b) * (reps + 1) <= 40:
+                hh, ww = a, b
+                break
+        frac = _frac(hh, ww)
         ts = _cpu_forward_seconds(oracle, hh, ww, reps=reps, warm=1)
         v = reps * frac / sum(ts)
         line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
                                 "sample": f"{reps} timed forward passes of oracle/ (torch-CPU fp32) on a {hh}x{ww} "
-                                          f"crop = {frac:g} of a pair, {cores} threads"}
+                                          f"crop = {frac:.4f} of a pair (cost linear in H*W), {cores} threads"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
