@@ -77,6 +77,7 @@ def _declare(lib: C.CDLL) -> None:
         "masic_conv_plan_destroy": (None, [vp]),
         "masic_conv_plan_info": (i, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                      C.POINTER(i), C.POINTER(i)]),
+        "masic_conv_plan_trace": (i, [vp, vp]),
         "masic_packed_weight_bytes": (i64, [i, i, i, i]),
         "masic_pack_conv_weights": (i, [vp, i, i, i, i, i, i, vp, vp]),
         "masic_gdn_prepare": (i, [vp, vp, i, f, vp, vp, vp, vp]),

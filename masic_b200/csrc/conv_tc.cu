@@ -40,9 +40,12 @@ namespace masic {
 constexpr int TILE_W = 8;
 constexpr int TILE_H = 16;
 constexpr int KBLK = 64;            // channels per k-block: 128 B of bf16 = one swizzle row
-constexpr int NUM_THREADS = 256;    // warp 0: A producer, 1: B producer, 2: MMA, 3: TMEM, 4-7: epilogue
+constexpr int NUM_THREADS = 384;    // stream 0: warps 0 (A producer), 1 (B producer), 2 (MMA); warp 3: TMEM alloc;
+                                    // warps 4-7: epilogue; stream 1: warps 8 (A), 9 (B), 10 (MMA); warp 11 idle
+constexpr int NUM_STREAMS = 2;      // two independent load->MMA pipelines per CTA, one accumulator buffer each
 constexpr int MAX_VARIANTS = 4;
 constexpr int MAX_STAGES = 8;
+constexpr int MAX_AOPS = 64, MAX_BOPS = 96, MAX_MOPS = 96;
 constexpr int STAGE_BLK_BYTES = 16384;  // one 128-row x 128-B staging block
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -60,9 +63,11 @@ struct Variant {
 
 struct KParams {
   CUtensorMap tmA, tmB, tmO, tmG;
-  const AOp* aops;
-  const BOp* bops;
-  const MOp* mops;
+  // per-layer programs live in the kernel-parameter constant bank: the role loops read them with
+  // warp-uniform indices, so ptxas keeps ops / descriptors in uniform registers (no R2UR, no L1 trip)
+  AOp aops[MAX_AOPS];
+  BOp bops[MAX_BOPS];
+  MOp mops[MAX_MOPS];
   Variant var[MAX_VARIANTS];
   int n_var;
   int tiles_x, tiles_y, n_img, n_ntiles;
@@ -79,21 +84,24 @@ struct KParams {
   const float* rowscale;
   int rs_stride, rs_off, rs_H, rs_W;
   uint32_t idesc;
+  long long* trace; // optional [64 tiles][16] clock64() stamps of CTA 0 (MASIC_CONV_TRACE=1)
+  int debug;       // bit0: skip A loads, bit1: skip B loads (timing experiments only; results are garbage)
 };
 
 // misc smem region layout (byte offsets from smem_misc_off)
-constexpr int MISC_A_FULL = 0;                       // 8 x u64
-constexpr int MISC_A_EMPTY = 64;
-constexpr int MISC_B_FULL = 128;
-constexpr int MISC_B_EMPTY = 192;
-constexpr int MISC_ACC_FULL = 256;                   // 2 x u64
-constexpr int MISC_ACC_EMPTY = 272;                  // 2 x u64
-constexpr int MISC_GDN_BAR = 288;
-constexpr int MISC_G_FULL = 296;
-constexpr int MISC_TMEM_PTR = 304;
-constexpr int MISC_BIAS = 320;                       // 256 floats
-constexpr int MISC_BETA = 320 + 1024;                // 128 floats
-static_assert(320 + 1024 + 512 <= 2048, "misc region");
+constexpr int MISC_A_FULL = 0;                       // [2 streams][8] x u64
+constexpr int MISC_A_EMPTY = 128;
+constexpr int MISC_B_FULL = 256;
+constexpr int MISC_B_EMPTY = 384;
+constexpr int MISC_ACC_FULL = 512;                   // 2 x u64
+constexpr int MISC_ACC_EMPTY = 528;                  // 2 x u64
+constexpr int MISC_GDN_BAR = 544;
+constexpr int MISC_G_FULL = 552;
+constexpr int MISC_TMEM_PTR = 560;
+constexpr int MISC_BIAS = 576;                       // 256 floats
+constexpr int MISC_BETA = 576 + 1024;                // 128 floats
+static_assert(576 + 1024 + 512 <= 2560, "misc region");
+constexpr int MISC_BYTES = 2560;
 
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == MASIC_ACT_RELU) return fmaxf(x, 0.0f);
@@ -110,6 +118,8 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
                "r"(d)
                : "memory");
 }
+
+#define TRACE(it, slot) do { if (p.trace && blockIdx.x == 0 && (it) < 64) p.trace[(it) * 16 + (slot)] = clock64(); } while (0)
 
 struct Work { int n, ty, tx, var, nt; };
 __device__ __forceinline__ Work decode_work(const KParams& p, int w) {
@@ -146,7 +156,7 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     tma_prefetch_desc(&p.tmO);
-    for (int i = 0; i < MAX_STAGES; ++i) {
+    for (int i = 0; i < NUM_STREAMS * MAX_STAGES; ++i) {
       mbar_init(sMisc + MISC_A_FULL + 8 * i, 1);
       mbar_init(sMisc + MISC_A_EMPTY + 8 * i, 1);
       mbar_init(sMisc + MISC_B_FULL + 8 * i, 1);
@@ -164,90 +174,129 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     tmem_alloc(sMisc + MISC_TMEM_PTR, TMEM_COLS);
     tmem_relinquish();
   }
-  if (threadIdx.x >= 128 && p.gdn) beta_s[threadIdx.x - 128] = p.beta[threadIdx.x - 128];
+  if (threadIdx.x >= 128 && threadIdx.x < 256 && p.gdn) beta_s[threadIdx.x - 128] = p.beta[threadIdx.x - 128];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  if (warp == 0) {
+  // Role loops are WARP-UNIFORM (all 32 lanes walk them, barrier waits included) and only the
+  // issue instructions sit under elect_one(): tcgen05.mma / TMA are uniform-datapath instructions,
+  // and inside a divergent `if (lane == 0)` region ptxas wraps each of them in an ELECT/BRA.U.ANY
+  // waterfall loop (measured: ~320 cycles per 128x128x16 MMA instead of 64).
+  // stream s owns tiles it = s, s+2, ... of this CTA's sequence, accumulator buffer s, and its own rings
+  const int sid = warp >= 8 ? 1 : 0;
+  const int role = warp - 8 * sid;            // 0: A producer, 1: B producer, 2: MMA (warps 3..7 handled below)
+  const uint32_t sAs = sA + sid * p.a_stages * p.a_stage_bytes;
+  const uint32_t sBs = sB + sid * p.b_stages * p.b_stage_bytes;
+  const uint32_t bar_off = sid * MAX_STAGES * 8;
+  const int w_first = blockIdx.x + sid * gridDim.x, w_step = NUM_STREAMS * gridDim.x;
+  if (warp != 3 && (warp < 4 || warp >= 8) && role == 0) {
     // ===================== A producer: activation strips =====================
-    if (lane == 0) {
-      uint32_t cnt = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
-        const Work wk = decode_work(p, w);
-        const Variant& v = p.var[wk.var];
-        for (int i = 0; i < v.n_aops; ++i, ++cnt) {
-          const AOp op = p.aops[v.aops_off + i];
-          const uint32_t st = cnt % p.a_stages, ph = (cnt / p.a_stages) & 1;
-          mbar_wait(sMisc + MISC_A_EMPTY + 8 * st, ph ^ 1);
-          mbar_expect_tx(sMisc + MISC_A_FULL + 8 * st, p.a_stage_bytes);
-          tma_load_5d(sA + st * p.a_stage_bytes, &p.tmA, sMisc + MISC_A_FULL + 8 * st, op.c0,
-                      wk.tx * TILE_W + op.dx, op.p2, wk.ty * TILE_H + op.dy, wk.n);
+    uint32_t st = 0, ph = 0;
+    const uint32_t n_st = p.a_stages, st_bytes = p.a_stage_bytes;
+    for (int w = w_first; w < total; w += w_step) {
+      const Work wk = decode_work(p, w);
+      const int x0 = wk.tx * TILE_W, y0 = wk.ty * TILE_H;
+      const int i0 = p.var[wk.var].aops_off, i1 = i0 + p.var[wk.var].n_aops;
+      for (int i = i0; i < i1; ++i) {
+        const AOp op = p.aops[i];
+        const uint32_t full = sMisc + MISC_A_FULL + bar_off + 8 * st;
+        mbar_wait(sMisc + MISC_A_EMPTY + bar_off + 8 * st, ph ^ 1);
+        if (elect_one()) {
+          if (p.debug & 1) {
+            mbar_arrive(full);
+          } else {
+            mbar_expect_tx(full, st_bytes);
+            tma_load_5d(sAs + st * st_bytes, &p.tmA, full, op.c0, x0 + op.dx, op.p2, y0 + op.dy, wk.n);
+          }
         }
+        __syncwarp();
+        if (++st == n_st) { st = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp != 3 && (warp < 4 || warp >= 8) && role == 1) {
     // ===================== B producer: weight k-blocks (+ gamma once) =====================
-    if (lane == 0) {
-      if (p.gdn) {
-        tma_prefetch_desc(&p.tmG);
-        mbar_expect_tx(sMisc + MISC_G_FULL, 2 * STAGE_BLK_BYTES);
-        tma_load_2d(sG, &p.tmG, sMisc + MISC_G_FULL, 0, 0);
-        tma_load_2d(sG + STAGE_BLK_BYTES, &p.tmG, sMisc + MISC_G_FULL, KBLK, 0);
-      }
-      uint32_t cnt = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
-        const Work wk = decode_work(p, w);
-        const Variant& v = p.var[wk.var];
-        for (int i = 0; i < v.n_bops; ++i, ++cnt) {
-          const BOp op = p.bops[v.bops_off + i];
-          const uint32_t st = cnt % p.b_stages, ph = (cnt / p.b_stages) & 1;
-          mbar_wait(sMisc + MISC_B_EMPTY + 8 * st, ph ^ 1);
-          mbar_expect_tx(sMisc + MISC_B_FULL + 8 * st, p.b_stage_bytes);
-          tma_load_2d(sB + st * p.b_stage_bytes, &p.tmB, sMisc + MISC_B_FULL + 8 * st, 0,
-                      op.row0 + wk.nt * p.n_tile);
+    if (p.gdn && sid == 0 && elect_one()) {
+      tma_prefetch_desc(&p.tmG);
+      mbar_expect_tx(sMisc + MISC_G_FULL, 2 * STAGE_BLK_BYTES);
+      tma_load_2d(sG, &p.tmG, sMisc + MISC_G_FULL, 0, 0);
+      tma_load_2d(sG + STAGE_BLK_BYTES, &p.tmG, sMisc + MISC_G_FULL, KBLK, 0);
+    }
+    __syncwarp();
+    uint32_t st = 0, ph = 0;
+    const uint32_t n_st = p.b_stages, st_bytes = p.b_stage_bytes;
+    for (int w = w_first; w < total; w += w_step) {
+      const Work wk = decode_work(p, w);
+      const int nrow = wk.nt * p.n_tile;
+      const int i0 = p.var[wk.var].bops_off, i1 = i0 + p.var[wk.var].n_bops;
+      for (int i = i0; i < i1; ++i) {
+        const BOp op = p.bops[i];
+        const uint32_t full = sMisc + MISC_B_FULL + bar_off + 8 * st;
+        mbar_wait(sMisc + MISC_B_EMPTY + bar_off + 8 * st, ph ^ 1);
+        if (elect_one()) {
+          if (p.debug & 2) {
+            mbar_arrive(full);
+          } else {
+            mbar_expect_tx(full, st_bytes);
+            tma_load_2d(sBs + st * st_bytes, &p.tmB, full, 0, op.row0 + nrow);
+          }
         }
+        __syncwarp();
+        if (++st == n_st) { st = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 2) {
+  } else if (warp != 3 && (warp < 4 || warp >= 8) && role == 2) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      uint32_t a_cnt = 0, b_cnt = 0, sa = 0, sb = 0;
-      int it = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-        const Work wk = decode_work(p, w);
-        const Variant& v = p.var[wk.var];
-        const int buf = it & 1;
-        mbar_wait(sMisc + MISC_ACC_EMPTY + 8 * buf, ((it >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * acc_stride;
-        for (int i = 0; i < v.n_mops; ++i) {
-          const MOp op = p.mops[v.mops_off + i];
-          if (op.flags & M_NEW_A) {
-            sa = a_cnt % p.a_stages;
-            mbar_wait(sMisc + MISC_A_FULL + 8 * sa, (a_cnt / p.a_stages) & 1);
-            ++a_cnt;
-          }
-          if (op.flags & M_NEW_B) {
-            sb = b_cnt % p.b_stages;
-            mbar_wait(sMisc + MISC_B_FULL + 8 * sb, (b_cnt / p.b_stages) & 1);
-            ++b_cnt;
-          }
-          tc_fence_after();
-          const uint32_t a_addr = sA + sa * p.a_stage_bytes + op.a_row * 1024u;
-          const uint32_t b_addr = sB + sb * p.b_stage_bytes;
-          for (int k = 0; k < op.nk; ++k) {
-            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32),
-                      p.idesc, ((op.flags & M_FIRST) && k == 0) ? 0u : 1u);
-          }
-          if (op.flags & M_REL_A) umma_commit(sMisc + MISC_A_EMPTY + 8 * sa);
-          if (op.flags & M_REL_B) umma_commit(sMisc + MISC_B_EMPTY + 8 * sb);
+    const uint32_t n_sa = p.a_stages, n_sb = p.b_stages;
+    uint32_t sa = n_sa - 1, pa = 1, sb = n_sb - 1, pb = 1;    // first advance lands on stage 0, phase 0
+    int it = sid;
+    // descriptor = constant high part | (smem address >> 4); +2 per K=16 step, +64 per strip row
+    const uint64_t descA0 = umma_desc_sw128(sAs), descB0 = umma_desc_sw128(sBs);
+    const uint32_t a_step = p.a_stage_bytes >> 4, b_step = p.b_stage_bytes >> 4;
+    const uint32_t idesc = p.idesc;
+    for (int w = w_first; w < total; w += w_step, it += NUM_STREAMS) {
+      const Work wk = decode_work(p, w);
+      const int buf = sid;                      // == it & 1
+      if (lane == 0) TRACE(it, 0);
+      mbar_wait(sMisc + MISC_ACC_EMPTY + 8 * buf, ((it >> 1) & 1) ^ 1);
+      if (lane == 0) TRACE(it, 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * acc_stride;
+      const int i0 = p.var[wk.var].mops_off, i1 = i0 + p.var[wk.var].n_mops;
+      for (int i = i0; i < i1; ++i) {
+        const MOp op = p.mops[i];
+#define TRACE_OP(slot) do { if (p.trace && blockIdx.x == 0 && it == 4 && (i - i0) < 32 && lane == 0) p.trace[(32 + i - i0) * 16 + (slot)] = clock64(); } while (0)
+        TRACE_OP(0);
+        if (op.flags & M_NEW_A) {
+          if (++sa == n_sa) { sa = 0; pa ^= 1; }
+          mbar_wait(sMisc + MISC_A_FULL + bar_off + 8 * sa, pa);
         }
-        umma_commit(sMisc + MISC_ACC_FULL + 8 * buf);
+        if (op.flags & M_NEW_B) {
+          if (++sb == n_sb) { sb = 0; pb ^= 1; }
+          mbar_wait(sMisc + MISC_B_FULL + bar_off + 8 * sb, pb);
+        }
+        TRACE_OP(1);
+        tc_fence_after();
+        TRACE_OP(2);
+        if (elect_one()) {
+          const uint64_t adesc = descA0 + (sa * a_step + op.a_row * 64u);
+          const uint64_t bdesc = descB0 + sb * b_step;
+          umma_bf16(d_tmem, adesc, bdesc, idesc, (op.flags & M_FIRST) ? 0u : 1u);
+          if (op.nk > 1) umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);     // +32 B per K=16 step
+          if (op.nk > 2) umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+          if (op.nk > 3) umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+          if (op.flags & M_REL_A) umma_commit(sMisc + MISC_A_EMPTY + bar_off + 8 * sa);
+          if (op.flags & M_REL_B) umma_commit(sMisc + MISC_B_EMPTY + bar_off + 8 * sb);
+          if (i + 1 == i1) umma_commit(sMisc + MISC_ACC_FULL + 8 * buf);
+        }
+        TRACE_OP(3);
+        __syncwarp();
+        TRACE_OP(4);
       }
+      if (lane == 0) TRACE(it, 2);
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // ===================== epilogue: TMEM -> regs -> smem -> TMA store =====================
     const int ew = warp - 4;            // == warp % 4: the TMEM lane quarter this warp may read
     const int t = ew * 32 + lane;       // accumulator row = tile position
@@ -255,7 +304,7 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     const int nblk = p.n_tile / p.blk_ch;
     const int chunks_per_blk = p.blk_ch / 16;
     int it = 0;
-    if (p.gdn && t == 0) mbar_wait(sMisc + MISC_G_FULL, 0);
+    if (p.gdn && ew == 0) mbar_wait(sMisc + MISC_G_FULL, 0);
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
       const Work wk = decode_work(p, w);
       const Variant& v = p.var[wk.var];
@@ -263,6 +312,7 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
       const int act = p.act[wk.nt];
       const uint32_t acc_addr = tmem_base + lane_sel + buf * acc_stride;
 
+      if (t == 0) TRACE(it, 4);
       // stage this n-tile's bias; the barrier also fences the previous tile's readers
       named_bar_sync(1, 128);
       for (int c = t; c < p.n_tile; c += 128) bias_s[c] = p.bias ? p.bias[wk.nt * p.n_tile + c] : 0.0f;
@@ -275,8 +325,10 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
       if (t == 0) tma_store_wait_read<0>();     // staging (and A2) free again
       named_bar_sync(1, 128);
 
+      if (t == 0) TRACE(it, 5);
       mbar_wait(sMisc + MISC_ACC_FULL + 8 * buf, (it >> 1) & 1);
       tc_fence_after();
+      if (t == 0) TRACE(it, 6);
 
       if (p.gdn) {
         // ---- pass 1: A2 = bf16((acc + bias)^2), K-major SWIZZLE_128B, two 64-channel blocks
@@ -299,18 +351,26 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
         fence_proxy_async_smem();
         tc_fence_before();
         named_bar_sync(1, 128);
-        if (t == 0) {
+        if (t == 0) TRACE(it, 7);
+        if (ew == 0) {                      // warp-uniform; one elected lane issues the 8 MMAs
           tc_fence_after();
-          const uint32_t d2 = tmem_base + 2 * acc_stride;
-          for (int kb = 0; kb < 2; ++kb)
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(d2, umma_desc_sw128(sStage + kb * STAGE_BLK_BYTES + k * 32),
-                        umma_desc_sw128(sG + kb * STAGE_BLK_BYTES + k * 32), p.idesc,
-                        (kb | k) ? 1u : 0u);
-          umma_commit(sMisc + MISC_GDN_BAR);
+          if (elect_one()) {
+            const uint32_t d2 = tmem_base + 2 * acc_stride;
+            const uint64_t dh = umma_desc_sw128(0);
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb) {
+              const uint64_t a2 = dh | (((sStage + kb * STAGE_BLK_BYTES) & 0x3FFFFu) >> 4);
+              const uint64_t g2 = dh | (((sG + kb * STAGE_BLK_BYTES) & 0x3FFFFu) >> 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16(d2, a2 + 2 * k, g2 + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
+            }
+            umma_commit(sMisc + MISC_GDN_BAR);
+          }
+          __syncwarp();
         }
         mbar_wait(sMisc + MISC_GDN_BAR, it & 1);
         tc_fence_after();
+        if (t == 0) TRACE(it, 8);
       }
 
       // ---- pass 2: finalise and store, one staging block (<= 16 KB) at a time
@@ -378,6 +438,7 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
           tma_store_commit();
         }
       }
+      if (t == 0) TRACE(it, 9);
     }
     if (t == 0) tma_store_wait_all<0>();
   }
@@ -465,6 +526,7 @@ using namespace masic;
 struct MasicConvPlan {
   KParams kp;
   void* d_tables = nullptr;
+  void* d_trace = nullptr;
   int smem_bytes = 0;
   int grid = 0;
   int total_work = 0;
@@ -645,22 +707,22 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   // shared memory carve-up
   kp.a_stage_bytes = rows * 1024;
   kp.b_stage_bytes = d.n_tile * 128;
-  const int fixed = (d.gdn ? 2 * STAGE_BLK_BYTES : 0) + 2 * STAGE_BLK_BYTES + 2048 /*misc*/ + 1024 /*align*/;
-  const int budget = 227 * 1024 - fixed;
-  int sa = 4, sb = 4;
-  while (sa * kp.a_stage_bytes + sb * kp.b_stage_bytes > budget && (sa > 2 || sb > 2)) {
-    if (sb >= sa && sb > 2) --sb; else if (sa > 2) --sa; else --sb;
-  }
-  // use what is left for deeper rings (B first: it is consumed fastest)
-  while (sb < MAX_STAGES && sa * kp.a_stage_bytes + (sb + 1) * kp.b_stage_bytes <= budget && sb < 6) ++sb;
-  while (sa < MAX_STAGES && (sa + 1) * kp.a_stage_bytes + sb * kp.b_stage_bytes <= budget && sa < 5) ++sa;
+  const int fixed = (d.gdn ? 2 * STAGE_BLK_BYTES : 0) + 2 * STAGE_BLK_BYTES + MISC_BYTES + 1024 /*align*/;
+  const int budget = (227 * 1024 - fixed) / NUM_STREAMS;      // ring bytes per stream
+  int sa = 2, sb = 2;
   if (sa * kp.a_stage_bytes + sb * kp.b_stage_bytes > budget) { delete pl; return MASIC_EINVAL; }
+  // deepen the rings with what is left (B first: a B stage is consumed by a single op)
+  for (bool grew = true; grew;) {
+    grew = false;
+    if (sb < 4 && sa * kp.a_stage_bytes + (sb + 1) * kp.b_stage_bytes <= budget) { ++sb; grew = true; }
+    if (sa < 3 && (sa + 1) * kp.a_stage_bytes + sb * kp.b_stage_bytes <= budget) { ++sa; grew = true; }
+  }
   kp.a_stages = sa; kp.b_stages = sb;
-  kp.smem_b_off = sa * kp.a_stage_bytes;
-  kp.smem_g_off = kp.smem_b_off + sb * kp.b_stage_bytes;
+  kp.smem_b_off = NUM_STREAMS * sa * kp.a_stage_bytes;
+  kp.smem_g_off = kp.smem_b_off + NUM_STREAMS * sb * kp.b_stage_bytes;
   kp.smem_stage_off = kp.smem_g_off + (d.gdn ? 2 * STAGE_BLK_BYTES : 0);
   kp.smem_misc_off = kp.smem_stage_off + 2 * STAGE_BLK_BYTES;
-  pl->smem_bytes = kp.smem_misc_off + 2048 + 1024;
+  pl->smem_bytes = kp.smem_misc_off + MISC_BYTES + 1024;
   if (pl->smem_bytes < 120 * 1024) pl->smem_bytes = 120 * 1024;   // keep 1 CTA/SM: 512 TMEM cols each
 
   // tensor maps
@@ -674,26 +736,25 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   if (!rc && d.gdn) rc = encode_gamma(&kp.tmG, d.gamma_packed);
   if (rc) { delete pl; return rc; }
 
-  // upload the programs
-  const size_t abytes = aops.size() * sizeof(AOp), bbytes = bops.size() * sizeof(BOp),
-               mbytes = mops.size() * sizeof(MOp);
-  const size_t aoff = 0, boff = (abytes + 15) & ~size_t(15), moff = (boff + bbytes + 15) & ~size_t(15);
-  std::vector<uint8_t> host(moff + mbytes);
-  memcpy(host.data() + aoff, aops.data(), abytes);
-  memcpy(host.data() + boff, bops.data(), bbytes);
-  memcpy(host.data() + moff, mops.data(), mbytes);
-  cudaError_t ce = cudaMalloc(&pl->d_tables, host.size());
-  if (ce == cudaSuccess) ce = cudaMemcpy(pl->d_tables, host.data(), host.size(), cudaMemcpyHostToDevice);
-  if (ce != cudaSuccess) { if (pl->d_tables) cudaFree(pl->d_tables); delete pl; return (int)ce; }
-  kp.aops = reinterpret_cast<const AOp*>(static_cast<uint8_t*>(pl->d_tables) + aoff);
-  kp.bops = reinterpret_cast<const BOp*>(static_cast<uint8_t*>(pl->d_tables) + boff);
-  kp.mops = reinterpret_cast<const MOp*>(static_cast<uint8_t*>(pl->d_tables) + moff);
+  // the programs travel in the kernel parameters (constant bank)
+  if (aops.size() > MAX_AOPS || bops.size() > MAX_BOPS || mops.size() > MAX_MOPS) { delete pl; return MASIC_ENOSUP; }
+  memcpy(kp.aops, aops.data(), aops.size() * sizeof(AOp));
+  memcpy(kp.bops, bops.data(), bops.size() * sizeof(BOp));
+  memcpy(kp.mops, mops.data(), mops.size() * sizeof(MOp));
+  cudaError_t ce = cudaSuccess;
 
   kp.bias = d.bias; kp.beta = d.beta; kp.gdn = d.gdn; kp.out_fp32 = d.out_fp32;
   memcpy(kp.act, d.act, sizeof(kp.act));
   kp.out_coff = d.out_coff;
   kp.rowscale = d.rowscale; kp.rs_stride = d.rs_stride; kp.rs_off = d.rs_off;
   kp.rs_H = gh; kp.rs_W = gw;
+  { const char* e = getenv("MASIC_CONV_DEBUG"); kp.debug = e ? atoi(e) : 0; }
+  if (getenv("MASIC_CONV_TRACE")) {
+    if (cudaMalloc(&pl->d_trace, 64 * 16 * sizeof(long long)) == cudaSuccess) {
+      cudaMemset(pl->d_trace, 0, 64 * 16 * sizeof(long long));
+      kp.trace = static_cast<long long*>(pl->d_trace);
+    }
+  }
 
   pl->total_work = kp.n_img * kp.tiles_y * kp.tiles_x * kp.n_var * kp.n_ntiles;
   int dev = 0, sms = 148;
@@ -720,7 +781,7 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   static bool attr_set = false;
   if (!attr_set) {
     ce = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (ce != cudaSuccess) { cudaFree(pl->d_tables); delete pl; return (int)ce; }
+    if (ce != cudaSuccess) { delete pl; return (int)ce; }
     attr_set = true;
   }
   *plan_out = pl;
@@ -736,7 +797,15 @@ extern "C" int masic_conv_plan_launch(const MasicConvPlan* pl, void* stream) {
 extern "C" void masic_conv_plan_destroy(MasicConvPlan* pl) {
   if (!pl) return;
   if (pl->d_tables) cudaFree(pl->d_tables);
+  if (pl->d_trace) cudaFree(pl->d_trace);
   delete pl;
+}
+
+// Debug: copy out the clock64() stamps of CTA 0 (64 tiles x 16 slots); needs MASIC_CONV_TRACE=1 at plan creation.
+extern "C" int masic_conv_plan_trace(const MasicConvPlan* pl, long long* out_host) {
+  if (!pl || !out_host) return MASIC_EINVAL;
+  if (!pl->d_trace) return MASIC_ENOSUP;
+  return (int)cudaMemcpy(out_host, pl->d_trace, 64 * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
 }
 
 extern "C" int masic_conv_plan_info(const MasicConvPlan* pl, double* flops, double* hbm_bytes,

@@ -198,6 +198,115 @@ conv_small_kernel(const float* __restrict__ in0, int c0, const float* __restrict
   }
 }
 
+// ------------------------------------------------------------------ 6 -> 3, 5x5, stride 1 (pre_conv / after_conv)
+// Shared-memory tiled: a block produces 128 x 8 output pixels from a (128+4) x (8+4) x 6 input
+// patch staged once; each thread owns 4 horizontally adjacent pixels so every staged value and
+// every (broadcast) weight feeds 12 / 4 FMAs.  HBM-bound: 24 B in + 12 B out per pixel.
+constexpr int F_TW = 128, F_TH = 8, F_PW = F_TW + 8, F_PH = F_TH + 4;   // pitch padded to 136 floats
+
+__global__ void __launch_bounds__(256)
+conv5x5_6to3_kernel(const float* __restrict__ in0, const float* __restrict__ in1, int n, int h, int w,
+                    const float* __restrict__ wt, int transposed_s1, const float* __restrict__ bias,
+                    int gdn, const float* __restrict__ beta, const float* __restrict__ gamma, float beta_bound,
+                    float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf, int bf_pitch) {
+  __shared__ __align__(16) float s_in[6][F_PH][F_PW];
+  __shared__ float s_w[3 * 6 * 25];
+  __shared__ float s_b[3], s_beta[3], s_gamma[9];
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  for (int i = tid; i < 450; i += 256) {
+    const int tap = i % 25, ci = (i / 25) % 6, co = i / 150;
+    float v;
+    if (transposed_s1) {
+      const int ky = 4 - tap / 5, kx = 4 - tap % 5;
+      v = wt[((ci * 3 + co) * 5 + ky) * 5 + kx];
+    } else {
+      v = wt[i];
+    }
+    s_w[i] = v;
+  }
+  if (tid < 3) s_b[tid] = bias ? bias[tid] : 0.0f;
+  if (gdn) {
+    const float ped = 1.4551915228366852e-11f;
+    if (tid < 3) { const float b = fmaxf(beta[tid], beta_bound); s_beta[tid] = b * b - ped; }
+    if (tid < 9) { const float g = fmaxf(gamma[tid], 3.814697265625e-06f); s_gamma[tid] = g * g - ped; }
+  }
+  const int b = blockIdx.z, y0 = blockIdx.y * F_TH, x0 = blockIdx.x * F_TW;
+  for (int i = tid; i < 6 * F_PH * (F_TW + 4); i += 256) {
+    const int px = i % (F_TW + 4), py = (i / (F_TW + 4)) % F_PH, ci = i / ((F_TW + 4) * F_PH);
+    const int gy = y0 + py - 2, gx = x0 + px - 2;
+    float v = 0.0f;
+    if (gy >= 0 && gy < h && gx >= 0 && gx < w) {
+      const float* src = ci < 3 ? in0 + ((long)(b * 3 + ci) * h) * w : in1 + ((long)(b * 3 + ci - 3) * h) * w;
+      v = __ldg(src + (long)gy * w + gx);
+    }
+    s_in[ci][py][px] = v;
+  }
+  __syncthreads();
+  float acc[4][3];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int co = 0; co < 3; ++co) acc[p][co] = s_b[co];
+  const int lx = threadIdx.x * 4, ly = threadIdx.y;
+#pragma unroll 1
+  for (int ci = 0; ci < 6; ++ci) {
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) {
+      const float4 a = *reinterpret_cast<const float4*>(&s_in[ci][ly + ky][lx]);
+      const float4 c = *reinterpret_cast<const float4*>(&s_in[ci][ly + ky][lx + 4]);
+      const float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx) {
+        const float w0 = s_w[(0 * 6 + ci) * 25 + ky * 5 + kx];
+        const float w1 = s_w[(1 * 6 + ci) * 25 + ky * 5 + kx];
+        const float w2 = s_w[(2 * 6 + ci) * 25 + ky * 5 + kx];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          acc[p][0] = fmaf(v[p + kx], w0, acc[p][0]);
+          acc[p][1] = fmaf(v[p + kx], w1, acc[p][1]);
+          acc[p][2] = fmaf(v[p + kx], w2, acc[p][2]);
+        }
+      }
+    }
+  }
+  const int oy = y0 + ly;
+  if (oy >= h) return;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    if (gdn) {
+      const float s0 = acc[p][0] * acc[p][0], s1 = acc[p][1] * acc[p][1], s2 = acc[p][2] * acc[p][2];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const float nrm = fmaf(s_gamma[i * 3 + 2], s2, fmaf(s_gamma[i * 3 + 1], s1, fmaf(s_gamma[i * 3], s0, s_beta[i])));
+        acc[p][i] *= (gdn == MASIC_GDN_FWD) ? rsqrtf(nrm) : sqrtf(nrm);
+      }
+    }
+  }
+  const int ox = x0 + lx;
+  if (out) {
+#pragma unroll
+    for (int co = 0; co < 3; ++co) {
+      float* o = out + ((long)(b * 3 + co) * h + oy) * w + ox;
+      if (ox + 3 < w && (w & 3) == 0) {
+        *reinterpret_cast<float4*>(o) = make_float4(acc[0][co], acc[1][co], acc[2][co], acc[3][co]);
+      } else {
+        for (int p = 0; p < 4; ++p) if (ox + p < w) o[p] = acc[p][co];
+      }
+    }
+  }
+  if (out_bf) {
+    for (int p = 0; p < 4; ++p) {
+      if (ox + p >= w) break;
+      uint32_t* o = reinterpret_cast<uint32_t*>(out_bf + ((long)(b * h + oy) * w + ox + p) * bf_pitch);
+      __nv_bfloat162 q0 = __floats2bfloat162_rn(acc[p][0], acc[p][1]);
+      __nv_bfloat162 q1 = __floats2bfloat162_rn(acc[p][2], 0.0f);
+      o[0] = *reinterpret_cast<uint32_t*>(&q0);
+      o[1] = *reinterpret_cast<uint32_t*>(&q1);
+      for (int j = 2; j < bf_pitch / 2; ++j) o[j] = 0u;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ sub-pixel output -> NCHW (+ IGDN over 3 ch)
 // in: [N][H2][W2][pitch] fp32, channel (py*2+px)*3 + co ; out: (N,3,2*H2,2*W2)
 __global__ void __launch_bounds__(256)
@@ -323,6 +432,15 @@ extern "C" int masic_conv_small_nchw(const float* in0, int c0, const float* in1,
   if (gdn && (!beta || !gamma)) return MASIC_EINVAL;
   if (transposed_s1 && stride != 1) return MASIC_EINVAL;
   const int ho = (h + stride - 1) / stride, wo = (w + stride - 1) / stride;
+  if (ksize == 5 && stride == 1 && c0 == 3 && c1 == 3 && c_out == 3 && act == MASIC_ACT_NONE &&
+      (bf_pitch % 2 == 0)) {
+    dim3 fgrid((w + F_TW - 1) / F_TW, (h + F_TH - 1) / F_TH, n), fblock(32, 8);
+    conv5x5_6to3_kernel<<<fgrid, fblock, 0, static_cast<cudaStream_t>(stream)>>>(
+        in0, in1, n, h, w, weight, transposed_s1, bias, gdn, beta, gamma,
+        sqrtf(beta_min + 1.4551915228366852e-11f), out_nchw, static_cast<__nv_bfloat16*>(out_nhwc_bf16),
+        bf_pitch);
+    return (int)cudaGetLastError();
+  }
   dim3 grid((wo + 127) / 128, ho, n);
   conv_small_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       in0, c0, in1, c1, n, h, w, weight, transposed_s1, bias, c_out, ksize, stride, act, gdn, beta, gamma,

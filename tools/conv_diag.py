@@ -146,7 +146,7 @@ CASES = {
     "subpix_deconv4": dict(kind=DECONV_S2_SUBPIX, k=5, h=24, w=16, c_in=128, c_out=3, n_tile=16, out_fp32=True),
     "1x1_gmm_l0": dict(k=1, h=19, w=34, c_in=768, c_out=1152, n_tile=192,
                        act=[ACT_RELU, ACT_RELU, ACT_LEAKY, ACT_LEAKY, ACT_NONE, ACT_RELU]),
-    "1x1_deconvk1": dict(k=1, h=16, w=8, c_in=128, c_out=256, n_tile=256, transposed=True),
+    "1x1_deconvk1": dict(k=1, h=16, w=8, c_in=128, c_out=256, n_tile=128, transposed=True),
     "1x1_ntile240": dict(k=1, h=16, w=24, c_in=192, c_out=960, n_tile=192, out_fp32=True, in_coff=64, in_cp=320),
     "batch2_s2": dict(k=5, stride=2, n=2, h=32, w=16, c_in=64, c_out=128, n_tile=128),
 }
