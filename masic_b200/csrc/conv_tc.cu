@@ -394,7 +394,10 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
             for (int i = 0; i < 16; ++i) {
               const float x = __uint_as_float(r[i]) + bias_s[c + i];
               const float nrm = __uint_as_float(g[i]) + beta_s[c + i];
-              o[i] = (p.gdn == MASIC_GDN_FWD) ? x * rsqrtf(nrm) : x * sqrtf(nrm);
+              // IGDN: sqrt(n) = n * rsqrt(n) on the MUFU fast path (sqrtf's IEEE path doubled the epilogue time;
+              // 2-ulp rsqrt is far below the bf16 output rounding)
+              const float rs_n = rsqrtf(nrm);
+              o[i] = (p.gdn == MASIC_GDN_FWD) ? x * rs_n : x * (nrm * rs_n);
             }
           } else {
             tmem_ld_wait();

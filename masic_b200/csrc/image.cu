@@ -16,6 +16,23 @@
 
 namespace {
 
+// write c (<= 8) fp32 values as one zero-padded NHWC bf16 pixel of `pitch` channels with 16-byte stores
+__device__ __forceinline__ void store_pixel_bf16(__nv_bfloat16* o, const float* v, int c, int pitch) {
+  if ((pitch & 7) == 0) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 q = __floats2bfloat162_rn(2 * i < c ? v[2 * i] : 0.0f, 2 * i + 1 < c ? v[2 * i + 1] : 0.0f);
+      w[i] = *reinterpret_cast<uint32_t*>(&q);
+    }
+    uint4* o4 = reinterpret_cast<uint4*>(o);
+    o4[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    for (int j = 1; j < pitch / 8; ++j) o4[j] = make_uint4(0u, 0u, 0u, 0u);
+  } else {
+    for (int ch = 0; ch < pitch; ++ch) o[ch] = __float2bfloat16_rn(ch < c ? v[ch] : 0.0f);
+  }
+}
+
 // ------------------------------------------------------------------ homography warp
 // T = inv(N_dst * M * inv(N_src)) with N(h,w) = [[2/(w-1),0,-1],[0,2/(h-1),-1],[0,0,1]]
 // (kornia 0.5.0 normalize_homography); evaluated and stored in fp64.  With invert_m != 0
@@ -111,8 +128,8 @@ warp_kernel(const float* __restrict__ src, int n, int c, int h, int w, int ho, i
     if (dst) dst[((long)(b * c + ch) * ho + y) * wo + x] = v;
   }
   if (dst_bf) {
-    __nv_bfloat16* o = dst_bf + ((long)(b * ho + y) * wo + x) * bf_pitch;
-    for (int ch = 0; ch < bf_pitch; ++ch) o[ch] = __float2bfloat16_rn(ch < c ? vals[ch] : 0.0f);
+    for (int ch = c; ch < 8; ++ch) vals[ch] = 0.0f;
+    store_pixel_bf16(dst_bf + ((long)(b * ho + y) * wo + x) * bf_pitch, vals, c, bf_pitch);
   }
 }
 
@@ -297,12 +314,8 @@ conv5x5_6to3_kernel(const float* __restrict__ in0, const float* __restrict__ in1
   if (out_bf) {
     for (int p = 0; p < 4; ++p) {
       if (ox + p >= w) break;
-      uint32_t* o = reinterpret_cast<uint32_t*>(out_bf + ((long)(b * h + oy) * w + ox + p) * bf_pitch);
-      __nv_bfloat162 q0 = __floats2bfloat162_rn(acc[p][0], acc[p][1]);
-      __nv_bfloat162 q1 = __floats2bfloat162_rn(acc[p][2], 0.0f);
-      o[0] = *reinterpret_cast<uint32_t*>(&q0);
-      o[1] = *reinterpret_cast<uint32_t*>(&q1);
-      for (int j = 2; j < bf_pitch / 2; ++j) o[j] = 0u;
+      const float v3[8] = {acc[p][0], acc[p][1], acc[p][2], 0.f, 0.f, 0.f, 0.f, 0.f};
+      store_pixel_bf16(out_bf + ((long)(b * h + oy) * w + ox + p) * bf_pitch, v3, 3, bf_pitch);
     }
   }
 }
@@ -347,9 +360,8 @@ subpix_to_nchw_kernel(const float* __restrict__ in, int n, int h2, int w2, int p
       out[((long)(b * 3 + 2) * H + oy) * W + ox] = x2;
     }
     if (out_bf) {
-      __nv_bfloat16* o = out_bf + ((long)(b * H + oy) * W + ox) * bf_pitch;
-      o[0] = __float2bfloat16_rn(x0); o[1] = __float2bfloat16_rn(x1); o[2] = __float2bfloat16_rn(x2);
-      for (int ch = 3; ch < bf_pitch; ++ch) o[ch] = __float2bfloat16_rn(0.0f);
+      const float v3[8] = {x0, x1, x2, 0.f, 0.f, 0.f, 0.f, 0.f};
+      store_pixel_bf16(out_bf + ((long)(b * H + oy) * W + ox) * bf_pitch, v3, 3, bf_pitch);
     }
   }
 }
@@ -378,9 +390,9 @@ nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, int n, int c, int hw, __n
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= (long)n * hw) return;
   const int b = (int)(i / hw), p = (int)(i % hw);
-  __nv_bfloat16* o = out + i * pitch;
-  for (int ch = 0; ch < pitch; ++ch)
-    o[ch] = __float2bfloat16_rn(ch < c ? in[((long)(b * c + ch)) * hw + p] : 0.0f);
+  float v[8];
+  for (int ch = 0; ch < 8; ++ch) v[ch] = ch < c ? __ldg(in + ((long)(b * c + ch)) * hw + p) : 0.0f;
+  store_pixel_bf16(out + i * pitch, v, c, pitch);
 }
 
 // generic tiled transpose between NHWC and NCHW fp32 (c arbitrary)
@@ -472,7 +484,7 @@ extern "C" int masic_softmax_channels(const float* in_nchw, int n, int c, int hw
 
 extern "C" int masic_nchw_to_nhwc_bf16(const float* in_nchw, int n, int c, int hw, void* out, int pitch,
                                        void* stream) {
-  if (!in_nchw || !out || c <= 0 || c > pitch || pitch > 64) return MASIC_EINVAL;
+  if (!in_nchw || !out || c <= 0 || c > 8 || c > pitch || pitch > 64) return MASIC_EINVAL;
   const long total = (long)n * hw;
   nchw_to_nhwc_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       in_nchw, n, c, hw, static_cast<__nv_bfloat16*>(out), pitch);
