@@ -48,7 +48,9 @@ class HSICEngine:
             raise MasicError("HSICEngine runs on a CUDA device only (no CPU fallback)")
         self.B, self.H, self.W, self.N, self.M, self.K = batch, height, width, N, M, K
         self.sd = {k: v.detach().to(self.dev) for k, v in sd.items()}
-        self.steps: List[Tuple[str, Callable[[], None]]] = []
+        self.steps: List[Tuple[str, Callable[[], None]]] = []      # kernel launches, issue order
+        self.sched: List[Tuple] = []     # ("run", idx, lane) | ("record", key, lane) | ("wait", key, lane)
+        self._lane = 0
         self.plans: Dict[str, ConvPlan] = {}
         self._keep = []
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -65,6 +67,20 @@ class HSICEngine:
 
     def _add(self, name: str, fn: Callable[[], None]):
         self.steps.append((name, fn))
+        self.sched.append(("run", len(self.steps) - 1, self._lane))
+
+    # Three lanes (CUDA streams) inside the captured graph: lane 0 carries the critical path
+    # (encoder1 -> decoder1 -> warp -> encoder1 again -> gmm2 -> decoder2), lane 1 the left view's
+    # hyper/context/GMM chain, lane 2 the right view's encoder + hyper chain and the mask chain.
+    # Most of lanes 1/2 are small launches (<= 148 work items) that would otherwise leave SMs idle.
+    def _on(self, lane: int):
+        self._lane = lane
+
+    def _record(self, key: str):
+        self.sched.append(("record", key, self._lane))
+
+    def _wait(self, key: str):
+        self.sched.append(("wait", key, self._lane))
 
     def _s(self):
         return torch.cuda.current_stream().cuda_stream
@@ -286,7 +302,8 @@ class HSICEngine:
             "lik_y1": self._buf(B, M, h16, w16, dtype=f32), "lik_y2": self._buf(B, M, h16, w16, dtype=f32),
         }
 
-        # ---------------- left view (MASIC.py:746-777)
+        # ---------------- lane 0: left encoder (MASIC.py:746, :755)
+        self._on(0)
         x1_bf = self._buf(B, H, W, IMG_CP)
         self._add("x1.pack_nhwc", lambda: check(lib.masic_nchw_to_nhwc_bf16(
             self.x1.data_ptr(), B, 3, H * W, x1_bf.data_ptr(), IMG_CP, self._s()), "masic_nchw_to_nhwc_bf16"))
@@ -295,25 +312,17 @@ class HSICEngine:
         y1_abs = self._buf(B, h16, w16, M)
         y1_rnd = self._buf(B, h16, w16, M)
         self._latent_prep("L", y1, y1_abs, y1_rnd)
-        gmm1_in = self._buf(B, h16, w16, 4 * M)
-        o["z1_hat"], o["lik_z1"] = self._hyper("L", 1, y1_abs, gmm1_in)
-        ctx1 = self._pack("context_prediction1", c_in=M, c_out=2 * M, n_tile=192)
-        self._conv("L.context(masked5x5)", ctx1, y1_rnd, gmm1_in, stride=1, tap_mask=MASK_A_5x5, out_coff=2 * M)
-        s1, m1, w1 = self._gmm_net("L", "_h_s1_same_resolution", 4 * M, True, gmm1_in)
-        self._gmm_likelihood("L", y1, s1, m1, w1, o["y1_hat"], o["lik_y1"])
-        sp1 = self._decoder("L.g_s", "decoder1", y1_rnd)
-        self._add("L.x1_hat(unshuffle)", lambda: check(lib.masic_subpix_to_nchw(
-            sp1.data_ptr(), B, H // 2, W // 2, 16, 0, None, None, 1e-6, o["x1_hat"].data_ptr(), None, 0, self._s()),
-            "masic_subpix_to_nchw"))
+        self._record("y1")
 
-        # ---------------- homography products (MASIC.py:781, 803-805, 821/833)
+        # ---------------- lane 2: homography products, mask weights, right encoder + hyper chain
+        # (MASIC.py:781-805; none of it depends on the left view's latents)
+        self._on(2)
         T = torch.empty(B, 3, 3, device=self.dev, dtype=torch.float64)
         Tinv = torch.empty(B, 3, 3, device=self.dev, dtype=torch.float64)
         self._add("warp.prepare", lambda: (
             check(lib.masic_warp_prepare(self.Hm.data_ptr(), B, H, W, H, W, 0, T.data_ptr(), self._s()), "masic_warp_prepare"),
             check(lib.masic_warp_prepare(self.Hm.data_ptr(), B, H, W, H, W, 1, Tinv.data_ptr(), self._s()), "masic_warp_prepare")))
-        x1_warp = self._buf(B, 3, H, W, dtype=f32)
-        self._warp("R.warp(x1)", self.x1, T, x1_warp)
+        self._record("T")
         self._warp("mask_R=warp(ones)", None, T, o["x1_mask_R"], channels=1)
         self._warp("mask_L=warp(mask_R,Hinv)", o["x1_mask_R"], Tinv, o["x1_mask_L"], channels=1)
         # mask2weights: 4x (conv3 s2 [+ReLU]) + softmax over 3 (MASIC.py:472-506)
@@ -330,8 +339,9 @@ class HSICEngine:
         self.mask_weights = mw
         self._add("mask2weights.softmax", lambda: check(lib.masic_softmax_channels(
             k4.data_ptr(), B, 3, h16 * w16, None, mw.data_ptr(), self._s()), "masic_softmax_channels"))
-
-        # ---------------- right view (MASIC.py:782-834)
+        self._record("mw")
+        x1_warp = self._buf(B, 3, H, W, dtype=f32)
+        self._warp("R.warp(x1)", self.x1, T, x1_warp)
         x2in_bf = self._buf(B, H, W, IMG_CP)
         self._conv_small("R.pre_conv+pre_gdn", x1_warp, self.x2, "encoder2.pre_conv", ksize=5, stride=1, gdn=GDN_FWD,
                          gdn_prefix="encoder2.pre_gdn", out_bf=x2in_bf)
@@ -344,15 +354,37 @@ class HSICEngine:
         ctx2 = self._pack("context_prediction2", c_in=M, c_out=2 * M, n_tile=192)
         self._conv("R.context(masked5x5)", ctx2, y2_rnd, gmm2_in, stride=1, tap_mask=MASK_A_5x5, out_coff=2 * M,
                    rowscale=mw, rs_off=1)                                                          # ctx2 * w1
+        self._record("right")
+
+        # ---------------- lane 1: left hyperprior, context, GMM parameters, likelihood (MASIC.py:747-767)
+        self._on(1)
+        self._wait("y1")
+        gmm1_in = self._buf(B, h16, w16, 4 * M)
+        o["z1_hat"], o["lik_z1"] = self._hyper("L", 1, y1_abs, gmm1_in)
+        ctx1 = self._pack("context_prediction1", c_in=M, c_out=2 * M, n_tile=192)
+        self._conv("L.context(masked5x5)", ctx1, y1_rnd, gmm1_in, stride=1, tap_mask=MASK_A_5x5, out_coff=2 * M)
+        s1, m1, w1 = self._gmm_net("L", "_h_s1_same_resolution", 4 * M, True, gmm1_in)
+        self._gmm_likelihood("L", y1, s1, m1, w1, o["y1_hat"], o["lik_y1"])
+        self._record("left_entropy")
+
+        # ---------------- lane 0: left decoder, warp of x1_hat, encoder1 on it, right GMM + decoder
+        self._on(0)
+        sp1 = self._decoder("L.g_s", "decoder1", y1_rnd)                                           # :777
+        self._add("L.x1_hat(unshuffle)", lambda: check(lib.masic_subpix_to_nchw(
+            sp1.data_ptr(), B, H // 2, W // 2, 16, 0, None, None, 1e-6, o["x1_hat"].data_ptr(), None, 0, self._s()),
+            "masic_subpix_to_nchw"))
         # x1_hat warped once (the reference computes it twice, :821 and :833)
         x1hw = self._buf(B, 3, H, W, dtype=f32)
         x1hw_bf = self._buf(B, H, W, IMG_CP)
+        self._wait("T")
         self._warp("R.warp(x1_hat)", o["x1_hat"], T, x1hw, x1hw_bf)
-        y1w = self._encoder("R.g_a(enc1 on warped x1_hat)", enc1, x1hw_bf)
+        y1w = self._encoder("R.g_a(enc1 on warped x1_hat)", enc1, x1hw_bf)                         # :822
+        self._wait("mw")
+        self._wait("right")
         self._latent_prep("R.y1warp", y1w, None, gmm2_in, rnd_coff=4 * M, rowscale=mw, rs_off=2)   # round(.) * w2
-        s2, m2, w2 = self._gmm_net("R", "_h_s2_same_resolution", 5 * M, False, gmm2_in)
-        self._gmm_likelihood("R", y2, s2, m2, w2, o["y2_hat"], o["lik_y2"])
-        sp2 = self._decoder("R.g_s", "decoder2", y2_rnd)
+        s2, m2, w2 = self._gmm_net("R", "_h_s2_same_resolution", 5 * M, False, gmm2_in)            # :827
+        self._gmm_likelihood("R", y2, s2, m2, w2, o["y2_hat"], o["lik_y2"])                        # :829
+        sp2 = self._decoder("R.g_s", "decoder2", y2_rnd)                                           # :834
         after1 = self._buf(B, 3, H, W, dtype=f32)
         ab = self._w("decoder2.after_gdn.beta")
         ag = self._w("decoder2.after_gdn.gamma")
@@ -362,12 +394,36 @@ class HSICEngine:
             self._s()), "masic_subpix_to_nchw"))
         self._conv_small("R.after_conv", after1, x1hw, "decoder2.after_conv", ksize=5, stride=1, transposed_s1=True,
                          out=o["x2_hat"])
+        self._wait("left_entropy")
         self.flops = sum(p.flops for p in self.plans.values())
 
     # ------------------------------------------------------------------ running
-    def _launch_all(self):
-        for _, fn in self.steps:
-            fn()
+    def _launch_all(self, concurrent: bool = True):
+        """Issue every step.  concurrent=True spreads the three lanes over CUDA streams (fork from the
+        current stream, join back into it); False issues everything in order on the current stream."""
+        if not concurrent:
+            for _, fn in self.steps:
+                fn()
+            return
+        main = torch.cuda.current_stream()
+        if getattr(self, "_side", None) is None:
+            self._side = [torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev)]
+        lanes = [main] + self._side
+        for sd in self._side:
+            sd.wait_stream(main)                       # fork
+        events: Dict[str, torch.cuda.Event] = {}
+        for kind, a, lane in self.sched:
+            if kind == "run":
+                with torch.cuda.stream(lanes[lane]):
+                    self.steps[a][1]()
+            elif kind == "record":
+                ev = torch.cuda.Event()
+                ev.record(lanes[lane])
+                events[a] = ev
+            else:
+                lanes[lane].wait_event(events[a])
+        for sd in self._side:
+            main.wait_stream(sd)                       # join
 
     def run(self, x1: Optional[torch.Tensor] = None, x2: Optional[torch.Tensor] = None,
             h_matrix: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
@@ -399,7 +455,7 @@ class HSICEngine:
     def profile_steps(self, iters: int = 3) -> List[Tuple[str, float]]:
         """Eager run with a CUDA-event pair around every step; median ms per step."""
         with torch.cuda.device(self.dev):
-            self._launch_all()
+            self._launch_all(concurrent=False)
             torch.cuda.synchronize()
             acc = [[] for _ in self.steps]
             for _ in range(iters):
