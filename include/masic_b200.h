@@ -30,6 +30,8 @@
 extern "C" {
 #endif
 
+#define MASIC_IMG_XOFF 2    /* first real pixel column of a padded image row (MASIC_CONV_XFOLD4 input) */
+#define MASIC_IMG_XPAD 8    /* extra columns per padded image row                                         */
 #define MASIC_OK 0
 #define MASIC_EINVAL (-1)   /* bad argument (shape, alignment, enum)        */
 #define MASIC_ENOSUP (-2)   /* valid request this build does not implement  */
@@ -49,8 +51,15 @@ enum { MASIC_GDN_NONE = 0, MASIC_GDN_FWD = 1, MASIC_GDN_INV = 2 };
 enum {
   MASIC_CONV = 0,          /* nn.Conv2d(k, stride s, pad k/2)  — models/utils.py:128-135  */
   MASIC_DECONV_S2 = 1,     /* nn.ConvTranspose2d(5, s=2, p=2, op=1) — models/utils.py:138-146 */
-  MASIC_DECONV_S2_SUBPIX = 2 /* same op, all 4 output phases stacked on N (for tiny Cout):
+  MASIC_DECONV_S2_SUBPIX = 2,/* same op, all 4 output phases stacked on N (for tiny Cout):
                                 out buffer is [N][H][W][4*Cout padded], phase-major   */
+  MASIC_CONV_XFOLD4 = 3      /* nn.Conv2d(c<=16 -> Cout, k=5, s=2, p=2) with four horizontal taps folded into
+                                one K=64 block (g_a_conv1, MASIC.py:513: 10 MMA groups per tile instead
+                                of 25).  The input is a plain 16-channel-pitch image stored with a padded
+                                row: [N][H][W+8][16] bf16, pixel x at column x+2, pad columns zero
+                                (MASIC_IMG_XOFF / MASIC_IMG_XPAD); the TMA tensor map reads OVERLAPPING
+                                4-pixel windows (stride 2 pixels) from it, so nothing is replicated in HBM.
+                                Pass in_cpitch = 16, c_in = 64, w_in = the real width W.               */
 };
 
 typedef struct MasicConvDesc {
@@ -185,7 +194,7 @@ int masic_warp_prepare(const float* m_3x3, int batch, int h, int w, int h_out, i
  * NHWC bf16 zero-padded to bf_pitch channels. */
 int masic_warp_perspective_fwd(const float* src, int n, int c, int h, int w, int h_out, int w_out,
                                const double* t_prepared, float* dst_nchw, void* dst_nhwc_bf16,
-                               int bf_pitch, void* stream);
+                               int bf_pitch, int bf_row_pixels, int bf_xoff, void* stream);
 
 /* Direct conv for the tiny-channel layers (c_in <= 8, c_out <= 8) on NCHW fp32:
  *   Encoder2.pre_conv+pre_gdn (MASIC.py:573-574): in0=x1_warp, in1=x2, k=5, s=1, gdn=FWD
@@ -196,7 +205,7 @@ int masic_conv_small_nchw(const float* in0, int c0, const float* in1, int c1, in
                           const float* weight, int transposed_s1, const float* bias, int c_out,
                           int ksize, int stride, int act, int gdn, const float* beta,
                           const float* gamma, float beta_min, float* out_nchw, void* out_nhwc_bf16,
-                          int bf_pitch, void* stream);
+                          int bf_pitch, int bf_row_pixels, int bf_xoff, void* stream);
 
 /* Output of a MASIC_DECONV_S2_SUBPIX plan ([N][H/2][W/2][pitch] fp32, channel = phase*3+co)
  * -> NCHW fp32 image (N,3,H,W), optionally through GDN/IGDN over the 3 channels
@@ -213,8 +222,11 @@ int masic_gdn_nchw(const float* x, int n, int c, int hw, const float* beta, cons
 /* softmax over the c (<= 8) channels of an NCHW tensor (mask2weights, MASIC.py:497-502). */
 int masic_softmax_channels(const float* in_nchw, int n, int c, int hw, float* out_nchw, float* out_nhwc,
                            void* stream);
-/* layout packs */
-int masic_nchw_to_nhwc_bf16(const float* in_nchw, int n, int c, int hw, void* out, int pitch, void* stream);
+/* layout packs.  The NHWC bf16 outputs of this function, of masic_warp_perspective_fwd and of
+ * masic_conv_small_nchw may have a padded row: pixel (y,x) goes to out[(y*row_pixels + x + xoff)*pitch];
+ * row_pixels = 0 means a dense image (row_pixels = w, xoff = 0). */
+int masic_nchw_to_nhwc_bf16(const float* in_nchw, int n, int c, int h, int w, void* out, int pitch,
+                            int row_pixels, int xoff, void* stream);
 int masic_nhwc_to_nchw_f32(const float* in_nhwc, int n, int c, int hw, int in_pitch, float* out_nchw,
                            void* stream);
 

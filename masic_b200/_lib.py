@@ -14,7 +14,8 @@ LIB_PATH = _PKG / "libmasic_b200.so"
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 GDN_NONE, GDN_FWD, GDN_INV = 0, 1, 2
-CONV, DECONV_S2, DECONV_S2_SUBPIX = 0, 1, 2
+IMG_XOFF, IMG_XPAD = 2, 8       # MASIC_IMG_XOFF / MASIC_IMG_XPAD
+CONV, DECONV_S2, DECONV_S2_SUBPIX, CONV_XFOLD4 = 0, 1, 2, 3
 
 _ERRORS = {-1: "MASIC_EINVAL (bad argument)", -2: "MASIC_ENOSUP (not implemented)",
            -3: "MASIC_EDRIVER (cuTensorMapEncodeTiled unavailable or failed)"}
@@ -93,12 +94,12 @@ def _declare(lib: C.CDLL) -> None:
         "masic_pmf_to_quantized_cdf": (i, [vp, i, i, vp]),
         "masic_pmf_table_to_cdf": (i, [vp, i, i, vp, vp, i, i, vp]),
         "masic_warp_prepare": (i, [vp, i, i, i, i, i, i, vp, vp]),
-        "masic_warp_perspective_fwd": (i, [vp, i, i, i, i, i, i, vp, vp, vp, i, vp]),
-        "masic_conv_small_nchw": (i, [vp, i, vp, i, i, i, i, vp, i, vp, i, i, i, i, i, vp, vp, f, vp, vp, i, vp]),
+        "masic_warp_perspective_fwd": (i, [vp, i, i, i, i, i, i, vp, vp, vp, i, i, i, vp]),
+        "masic_conv_small_nchw": (i, [vp, i, vp, i, i, i, i, vp, i, vp, i, i, i, i, i, vp, vp, f, vp, vp, i, i, i, vp]),
         "masic_subpix_to_nchw": (i, [vp, i, i, i, i, i, vp, vp, f, vp, vp, i, vp]),
         "masic_gdn_nchw": (i, [vp, i, i, i, vp, vp, f, i, vp, vp]),
         "masic_softmax_channels": (i, [vp, i, i, i, vp, vp, vp]),
-        "masic_nchw_to_nhwc_bf16": (i, [vp, i, i, i, vp, i, vp]),
+        "masic_nchw_to_nhwc_bf16": (i, [vp, i, i, i, i, vp, i, i, i, vp]),
         "masic_nhwc_to_nchw_f32": (i, [vp, i, i, i, i, vp, vp]),
     }
     for name, (res, args) in sig.items():

@@ -15,7 +15,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, CONV, DECONV_S2, DECONV_S2_SUBPIX, GDN_FWD,
+from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, CONV, CONV_XFOLD4, DECONV_S2, DECONV_S2_SUBPIX, GDN_FWD,
                    GDN_INV, GDN_NONE, ConvDesc, check)
 
 # MaskedConv2d mask 'A' for a 5x5 kernel (layers.py:68-73): rows 0-1 and (2,0),(2,1)
@@ -71,7 +71,8 @@ class PackedConv:
         self.eff_out = 4 * c_out if kind == DECONV_S2_SUBPIX else c_out
         self.c_out_pad = c_out_pad if c_out_pad is not None else -(-self.eff_out // n_tile) * n_tile
         dev = weight.device
-        self.w_packed = pack_weights(weight, kind, transposed, ksize, c_in, c_out, self.c_out_pad)
+        pack_cin = weight.shape[1] if kind == CONV_XFOLD4 else c_in     # XFOLD4: real channels of w (<= 16)
+        self.w_packed = pack_weights(weight, kind, transposed, ksize, pack_cin, c_out, self.c_out_pad)
         self.bias = None
         if bias is not None:
             b = torch.zeros(self.c_out_pad, dtype=torch.float32, device=dev)
@@ -107,6 +108,8 @@ class ConvPlan:
                                 gdn_beta=gdn_beta, gdn_gamma=gdn_gamma)
         self.packed = packed
         n, h_in, w_in, in_cp = x.shape
+        if packed.kind == CONV_XFOLD4:          # padded image rows: [N][H][W + IMG_XPAD][16]
+            w_in -= _lib.IMG_XPAD
         self.rowscale = rowscale
         self.x, self.out = x, out       # keep the bound buffers alive
 

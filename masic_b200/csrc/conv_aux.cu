@@ -23,7 +23,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int kind, int t
   const int tap = kb / ncb, cb = kb % ncb;
   const int ci = cb * KBLK + c;
   float v = 0.0f;
-  if (ci < c_in) {
+  if (ci < c_in || kind == MASIC_CONV_XFOLD4) {
     if (kind == MASIC_DECONV_S2_SUBPIX) {
       // 3x3 stride-1 taps over the INPUT grid, N = (py, px, co): ky = py + 2*(1 - dy)
       const int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -34,6 +34,15 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int kind, int t
         if (ky >= 0 && ky < 5 && kx >= 0 && kx < 5)
           v = w[((static_cast<long>(ci) * c_out + cc) * 5 + ky) * 5 + kx];
       }
+    } else if (kind == MASIC_CONV_XFOLD4) {
+      // k-block = (ky, group): group 0 holds taps kx = 0..3 as column j*16 + ch (window at pixel 2*ox),
+      // group 1 holds kx = 4 in columns 32..47 (j = 2 of the window at pixel 2*ox+2);
+      // `c_in` here is the REAL channel count of w (<= 16)
+      const int ky = kb >> 1, grp = kb & 1;
+      const int j = c >> 4, ch = c & 15;
+      const int kx = grp ? (j == 2 ? 4 : 99) : j;
+      if (co < c_out && ch < c_in && kx < 5)
+        v = w[((static_cast<long>(co) * c_in + ch) * 5 + ky) * 5 + kx];
     } else if (co < c_out) {
       int ky = tap / k, kx = tap % k;
       if (transposed) {
@@ -107,6 +116,7 @@ __global__ void conv_direct_kernel(const __nv_bfloat16* __restrict__ in, int n, 
 }  // namespace
 
 extern "C" int64_t masic_packed_weight_bytes(int kind, int ksize, int c_in, int c_out_pad) {
+  if (kind == MASIC_CONV_XFOLD4) return static_cast<int64_t>(10) * c_out_pad * KBLK * 2;   // (ky, group) blocks
   const int taps = (kind == MASIC_DECONV_S2_SUBPIX) ? 9 : ksize * ksize;
   const int ncb = (c_in + KBLK - 1) / KBLK;
   return static_cast<int64_t>(taps) * ncb * c_out_pad * KBLK * 2;
@@ -120,7 +130,8 @@ extern "C" int masic_pack_conv_weights(const float* w, int kind, int transposed,
   } else if (c_out > c_out_pad) {
     return MASIC_EINVAL;
   }
-  const int ncb = (c_in + KBLK - 1) / KBLK;
+  if (kind == MASIC_CONV_XFOLD4 && (ksize != 5 || c_in > 16 || transposed)) return MASIC_EINVAL;
+  const int ncb = (kind == MASIC_CONV_XFOLD4) ? 1 : (c_in + KBLK - 1) / KBLK;
   const long total = masic_packed_weight_bytes(kind, ksize, c_in, c_out_pad) / 2;
   const int bs = 256;
   pack_weights_kernel<<<(unsigned)((total + bs - 1) / bs), bs, 0, static_cast<cudaStream_t>(stream)>>>(

@@ -51,7 +51,7 @@ constexpr uint32_t TMEM_COLS = 512;
 
 struct AOp { int16_t c0, dx, p2, dy; };          // TMA coordinates relative to the tile origin
 struct BOp { int32_t row0; };                    // first row of the k-block in the packed weights
-struct MOp { uint16_t a_row; uint8_t nk; uint8_t flags; };
+struct MOp { uint16_t a_row; uint8_t nk; uint8_t flags; };   // nk: low nibble = #K16 steps, high nibble = first step
 enum { M_NEW_A = 1, M_NEW_B = 2, M_FIRST = 4, M_REL_A = 8, M_REL_B = 16 };
 
 struct Variant {
@@ -280,12 +280,13 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
         tc_fence_after();
         TRACE_OP(2);
         if (elect_one()) {
-          const uint64_t adesc = descA0 + (sa * a_step + op.a_row * 64u);
-          const uint64_t bdesc = descB0 + sb * b_step;
+          const uint32_t nk = op.nk & 15u, k0 = op.nk >> 4;                      // +32 B (= 2) per K=16 step
+          const uint64_t adesc = descA0 + (sa * a_step + op.a_row * 64u + 2u * k0);
+          const uint64_t bdesc = descB0 + (sb * b_step + 2u * k0);
           umma_bf16(d_tmem, adesc, bdesc, idesc, (op.flags & M_FIRST) ? 0u : 1u);
-          if (op.nk > 1) umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);     // +32 B per K=16 step
-          if (op.nk > 2) umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-          if (op.nk > 3) umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+          if (nk > 1) umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+          if (nk > 2) umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+          if (nk > 3) umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
           if (op.flags & M_REL_A) umma_commit(sMisc + MISC_A_EMPTY + bar_off + 8 * sa);
           if (op.flags & M_REL_B) umma_commit(sMisc + MISC_B_EMPTY + bar_off + 8 * sb);
           if (i + 1 == i1) umma_commit(sMisc + MISC_ACC_FULL + 8 * buf);
@@ -508,6 +509,24 @@ static int encode_rows64(CUtensorMap* tm, const void* base, long rows, int box_r
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MASIC_OK : MASIC_EDRIVER;
 }
+// MASIC_CONV_XFOLD4 input: a [N][H][W + MASIC_IMG_XPAD][16] bf16 image (pixel x at column x + MASIC_IMG_XOFF, pad
+// columns zero) seen as OVERLAPPING 4-pixel windows: dims (64 elements, (W+XPAD)/2 windows 64 B apart, 2 row phases,
+// H/2, N).  Window hx starts at column 2*hx, i.e. pixel 2*hx - 2.
+static int encode_xfold4_view(CUtensorMap* tm, const void* base, int n, int h, int w, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return MASIC_EDRIVER;
+  const cuuint64_t row_bytes = (cuuint64_t)(w + MASIC_IMG_XPAD) * 32;
+  cuuint64_t dims[5] = {64, (cuuint64_t)(w + MASIC_IMG_XPAD) / 2 - 1, 2, (cuuint64_t)h / 2, (cuuint64_t)n};
+  cuuint64_t strides[4] = {64, row_bytes, 2 * row_bytes, (cuuint64_t)h * row_bytes};
+  cuuint32_t box[5] = {64, (cuuint32_t)TILE_W, 1, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (reinterpret_cast<uintptr_t>(base) % 16 || (w % 2) || (h % 2)) return MASIC_EINVAL;
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MASIC_OK : MASIC_EDRIVER;
+}
+
 // gamma [128][128] bf16 row-major, loaded as two (64 x 128-row) K-blocks
 static int encode_gamma(CUtensorMap* tm, const void* base) {
   EncodeTiledFn enc = get_encode_fn();
@@ -630,6 +649,42 @@ int build_programs(const MasicConvDesc& d, std::vector<AOp>& aops, std::vector<B
     }
     int rc = emit_variant(strips, 0, 0);
     if (rc) return rc;
+  } else if (d.kind == MASIC_CONV_XFOLD4) {
+    // Overlapping-window view of a padded 16-channel image (encode_xfold4_view): window hx holds pixels
+    // 2*hx-2 .. 2*hx+1 as 64 consecutive bf16.  Taps kx = 0..3 are one K=64 block read at window ox;
+    // tap kx = 4 is K sub-block j=2 of window ox+1.
+    if (k != 5 || d.c_in != 64 || d.in_cpitch != 16 || d.in_coff != 0 || d.stride != 2 || d.tap_mask) return MASIC_EINVAL;
+    rows = TILE_H + 2;
+    std::vector<std::pair<AOp, TapList>> strips;
+    for (int grp = 0; grp < 2; ++grp)
+      for (int py = 0; py < 2; ++py) {
+        AOp a; a.c0 = 0; a.dx = (int16_t)(grp ? 1 : 0); a.p2 = (int16_t)py; a.dy = -1;
+        TapList tl;
+        for (int ky = py; ky < 5; ky += 2) tl.taps.push_back({(ky >> 1), ky * 2 + grp});
+        strips.push_back({a, tl});
+      }
+    // emit by hand: group 1 ops use a single K=16 MMA
+    Variant& v = var[*n_var];
+    v.aops_off = (int)aops.size(); v.bops_off = (int)bops.size(); v.mops_off = (int)mops.size();
+    v.out_p2 = 0; v.out_c0 = 0;
+    bool first = true;
+    for (size_t si = 0; si < strips.size(); ++si) {
+      aops.push_back(strips[si].first);
+      const auto& taps = strips[si].second.taps;
+      for (size_t i = 0; i < taps.size(); ++i) {
+        BOp b; b.row0 = taps[i].second * d.c_out_pad; bops.push_back(b);
+        MOp m; m.a_row = (uint16_t)taps[i].first; m.nk = (uint8_t)(si >= 2 ? (1 | (2 << 4)) : 4);
+        m.flags = M_NEW_B | M_REL_B;
+        if (i == 0) m.flags |= M_NEW_A;
+        if (i + 1 == taps.size()) m.flags |= M_REL_A;
+        if (first) m.flags |= M_FIRST;
+        first = false;
+        mops.push_back(m);
+      }
+    }
+    v.n_aops = (int)aops.size() - v.aops_off; v.n_bops = (int)bops.size() - v.bops_off;
+    v.n_mops = (int)mops.size() - v.mops_off;
+    ++*n_var;
   } else if (d.kind == MASIC_DECONV_S2) {
     if (k != 5) return MASIC_ENOSUP;
     // out[2q+py] gets taps ky = py, py+2, .. from input row q + dy, dy = 1 - (ky-py)/2
@@ -668,10 +723,12 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   if (d.c_out_pad % d.n_tile || d.c_out > d.c_out_pad) return MASIC_EINVAL;
   if (d.c_out_pad / d.n_tile > 32) return MASIC_EINVAL;
   if (d.in_cpitch % 8 || d.in_coff % 8 || d.out_coff % 8) return MASIC_EINVAL;
+  if (d.kind == MASIC_CONV_XFOLD4 && d.c_in != 64) return MASIC_EINVAL;
   if (d.out_cpitch % (d.out_fp32 ? 4 : 8)) return MASIC_EINVAL;
   if (d.ksize != 1 && d.ksize != 3 && d.ksize != 5) return MASIC_EINVAL;
   if (d.gdn && (d.n_tile != 128 || d.c_out != 128 || !d.gamma_packed || !d.beta)) return MASIC_EINVAL;
-  if (d.kind == MASIC_CONV && d.stride == 2 && (d.h_in % 2 || d.w_in % 2)) return MASIC_EINVAL;
+  if ((d.kind == MASIC_CONV || d.kind == MASIC_CONV_XFOLD4) && d.stride == 2 && (d.h_in % 2 || d.w_in % 2))
+    return MASIC_EINVAL;
 
   MasicConvPlan* pl = new MasicConvPlan();
   KParams& kp = pl->kp;
@@ -684,7 +741,7 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
 
   // geometry of the tile grid (output positions for conv, input positions for deconv)
   int gh, gw, out_h, out_w, out_split = 0;
-  if (d.kind == MASIC_CONV) {
+  if (d.kind == MASIC_CONV || d.kind == MASIC_CONV_XFOLD4) {
     gh = d.stride == 2 ? d.h_in / 2 : d.h_in;
     gw = d.stride == 2 ? d.w_in / 2 : d.w_in;
     out_h = gh; out_w = gw;
@@ -729,10 +786,11 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   if (pl->smem_bytes < 120 * 1024) pl->smem_bytes = 120 * 1024;   // keep 1 CTA/SM: 512 TMEM cols each
 
   // tensor maps
-  const int split_in = (d.kind == MASIC_CONV && d.stride == 2) ? 1 : 0;
-  rc = encode_nhwc_view(&kp.tmA, d.in, 2, d.n, d.h_in, d.w_in, d.in_cpitch, split_in, KBLK, rows, true);
-  const int ktaps = (d.kind == MASIC_DECONV_S2_SUBPIX) ? 9 : d.ksize * d.ksize;
-  const int ncb = (d.c_in + KBLK - 1) / KBLK;
+  const int split_in = ((d.kind == MASIC_CONV || d.kind == MASIC_CONV_XFOLD4) && d.stride == 2) ? 1 : 0;
+  if (d.kind == MASIC_CONV_XFOLD4) rc = encode_xfold4_view(&kp.tmA, d.in, d.n, d.h_in, d.w_in, rows);
+  else rc = encode_nhwc_view(&kp.tmA, d.in, 2, d.n, d.h_in, d.w_in, d.in_cpitch, split_in, KBLK, rows, true);
+  const int ktaps = (d.kind == MASIC_DECONV_S2_SUBPIX) ? 9 : (d.kind == MASIC_CONV_XFOLD4 ? 10 : d.ksize * d.ksize);
+  const int ncb = (d.kind == MASIC_CONV_XFOLD4) ? 1 : (d.c_in + KBLK - 1) / KBLK;
   if (!rc) rc = encode_rows64(&kp.tmB, d.w_packed, (long)ktaps * ncb * d.c_out_pad, d.n_tile);
   if (!rc) rc = encode_nhwc_view(&kp.tmO, d.out, esz, d.n, out_h, out_w, d.out_cpitch, out_split,
                                  kp.blk_ch, TILE_H, kp.blk_pitch == 128);
@@ -773,11 +831,12 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
     const double out_pos = (double)d.n * out_h * out_w;
     double macs;
     const double co_real = (d.kind == MASIC_DECONV_S2_SUBPIX) ? d.c_out / 4 : d.c_out;
-    if (d.kind == MASIC_CONV) macs = out_pos * live * d.c_in * d.c_out;
+    if (d.kind == MASIC_CONV_XFOLD4) macs = out_pos * 25.0 * 3.0 * d.c_out;       // the real 3-channel 5x5
+    else if (d.kind == MASIC_CONV) macs = out_pos * live * d.c_in * d.c_out;
     else macs = (double)d.n * d.h_in * d.w_in * 25.0 * d.c_in * co_real;   // each input feeds 25 taps
     pl->flops = 2.0 * macs + (d.gdn ? 2.0 * out_pos * 128.0 * 128.0 : 0.0);
     const double out_ch = (d.kind == MASIC_DECONV_S2_SUBPIX) ? d.c_out_pad : d.c_out;
-    pl->hbm_bytes = (double)d.n * d.h_in * d.w_in * d.c_in * 2.0 + out_pos * out_ch * esz +
+    pl->hbm_bytes = (double)d.n * d.h_in * d.w_in * (d.kind == MASIC_CONV_XFOLD4 ? 16 : d.c_in) * 2.0 + out_pos * out_ch * esz +
                     (double)ktaps * ncb * d.c_out_pad * 128.0;
   }
 

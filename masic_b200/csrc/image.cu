@@ -76,7 +76,7 @@ __global__ void warp_prepare_kernel(const float* __restrict__ M, int batch, int 
 __global__ void __launch_bounds__(256)
 warp_kernel(const float* __restrict__ src, int n, int c, int h, int w, int ho, int wo,
             const double* __restrict__ T, float* __restrict__ dst, __nv_bfloat16* __restrict__ dst_bf,
-            int bf_pitch) {
+            int bf_pitch, int bf_row, int bf_xoff) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int b = blockIdx.z;
@@ -129,7 +129,7 @@ warp_kernel(const float* __restrict__ src, int n, int c, int h, int w, int ho, i
   }
   if (dst_bf) {
     for (int ch = c; ch < 8; ++ch) vals[ch] = 0.0f;
-    store_pixel_bf16(dst_bf + ((long)(b * ho + y) * wo + x) * bf_pitch, vals, c, bf_pitch);
+    store_pixel_bf16(dst_bf + ((long)(b * ho + y) * bf_row + x + bf_xoff) * bf_pitch, vals, c, bf_pitch);
   }
 }
 
@@ -142,7 +142,8 @@ conv_small_kernel(const float* __restrict__ in0, int c0, const float* __restrict
                   int n, int h, int w, const float* __restrict__ wt, int transposed_s1,
                   const float* __restrict__ bias, int c_out, int k, int stride, int act,
                   int gdn, const float* __restrict__ beta, const float* __restrict__ gamma, float beta_bound,
-                  int ho, int wo, float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf, int bf_pitch) {
+                  int ho, int wo, float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf, int bf_pitch,
+                  int bf_row, int bf_xoff) {
   __shared__ float s_w[SC_MAX_CO * SC_MAX_CI * 25];
   __shared__ float s_b[SC_MAX_CO], s_beta[SC_MAX_CO], s_gamma[SC_MAX_CO * SC_MAX_CO];
   const int cin = c0 + c1, kk = k * k;
@@ -210,8 +211,7 @@ conv_small_kernel(const float* __restrict__ in0, int c0, const float* __restrict
   if (out)
     for (int co = 0; co < c_out; ++co) out[((long)(b * c_out + co) * ho + y) * wo + x] = acc[co];
   if (out_bf) {
-    __nv_bfloat16* o = out_bf + ((long)(b * ho + y) * wo + x) * bf_pitch;
-    for (int ch = 0; ch < bf_pitch; ++ch) o[ch] = __float2bfloat16_rn(ch < c_out && ch < SC_MAX_CO ? acc[ch] : 0.0f);
+    store_pixel_bf16(out_bf + ((long)(b * ho + y) * bf_row + x + bf_xoff) * bf_pitch, acc, c_out, bf_pitch);
   }
 }
 
@@ -225,7 +225,8 @@ __global__ void __launch_bounds__(256)
 conv5x5_6to3_kernel(const float* __restrict__ in0, const float* __restrict__ in1, int n, int h, int w,
                     const float* __restrict__ wt, int transposed_s1, const float* __restrict__ bias,
                     int gdn, const float* __restrict__ beta, const float* __restrict__ gamma, float beta_bound,
-                    float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf, int bf_pitch) {
+                    float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf, int bf_pitch, int bf_row,
+                    int bf_xoff) {
   __shared__ __align__(16) float s_in[6][F_PH][F_PW];
   __shared__ float s_w[3 * 6 * 25];
   __shared__ float s_b[3], s_beta[3], s_gamma[9];
@@ -315,7 +316,7 @@ conv5x5_6to3_kernel(const float* __restrict__ in0, const float* __restrict__ in1
     for (int p = 0; p < 4; ++p) {
       if (ox + p >= w) break;
       const float v3[8] = {acc[p][0], acc[p][1], acc[p][2], 0.f, 0.f, 0.f, 0.f, 0.f};
-      store_pixel_bf16(out_bf + ((long)(b * h + oy) * w + ox + p) * bf_pitch, v3, 3, bf_pitch);
+      store_pixel_bf16(out_bf + ((long)(b * h + oy) * bf_row + ox + p + bf_xoff) * bf_pitch, v3, 3, bf_pitch);
     }
   }
 }
@@ -386,13 +387,14 @@ softmax_channels_kernel(const float* __restrict__ in, int n, int c, int hw, floa
 // NCHW fp32 (c <= 8 real channels) -> NHWC bf16 with `pitch` channels, zero padded
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, int n, int c, int hw, __nv_bfloat16* __restrict__ out,
-                         int pitch) {
+                         int pitch, int w, int row, int xoff) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= (long)n * hw) return;
   const int b = (int)(i / hw), p = (int)(i % hw);
   float v[8];
   for (int ch = 0; ch < 8; ++ch) v[ch] = ch < c ? __ldg(in + ((long)(b * c + ch)) * hw + p) : 0.0f;
-  store_pixel_bf16(out + i * pitch, v, c, pitch);
+  const int y = p / w, x = p - y * w;
+  store_pixel_bf16(out + (((long)b * (hw / w) + y) * row + x + xoff) * pitch, v, c, pitch);
 }
 
 // generic tiled transpose between NHWC and NCHW fp32 (c arbitrary)
@@ -423,13 +425,16 @@ extern "C" int masic_warp_prepare(const float* m_3x3, int batch, int h, int w, i
 
 extern "C" int masic_warp_perspective_fwd(const float* src, int n, int c, int h, int w, int h_out,
                                           int w_out, const double* t_prepared, float* dst_nchw,
-                                          void* dst_nhwc_bf16, int bf_pitch, void* stream) {
+                                          void* dst_nhwc_bf16, int bf_pitch, int bf_row_pixels, int bf_xoff,
+                                          void* stream) {
   if (!t_prepared || n <= 0 || c <= 0 || c > 8 || (!dst_nchw && !dst_nhwc_bf16)) return MASIC_EINVAL;
+  if (bf_row_pixels == 0) { bf_row_pixels = w_out; bf_xoff = 0; }
+  if (bf_row_pixels < w_out + bf_xoff || bf_xoff < 0) return MASIC_EINVAL;
   if (h_out < 2 || w_out < 2) return MASIC_ENOSUP;
   dim3 grid((w_out + 255) / 256, h_out, n);
   warp_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, n, c, h, w, h_out, w_out, t_prepared, dst_nchw, static_cast<__nv_bfloat16*>(dst_nhwc_bf16),
-      bf_pitch);
+      bf_pitch, bf_row_pixels, bf_xoff);
   return (int)cudaGetLastError();
 }
 
@@ -437,27 +442,30 @@ extern "C" int masic_conv_small_nchw(const float* in0, int c0, const float* in1,
                                      int w, const float* weight, int transposed_s1, const float* bias,
                                      int c_out, int ksize, int stride, int act, int gdn, const float* beta,
                                      const float* gamma, float beta_min, float* out_nchw,
-                                     void* out_nhwc_bf16, int bf_pitch, void* stream) {
+                                     void* out_nhwc_bf16, int bf_pitch, int bf_row_pixels, int bf_xoff,
+                                     void* stream) {
   if (!in0 || !weight || c_out <= 0 || c_out > SC_MAX_CO || c0 + c1 > SC_MAX_CI || c0 <= 0) return MASIC_EINVAL;
   if ((ksize != 3 && ksize != 5 && ksize != 1) || (stride != 1 && stride != 2)) return MASIC_EINVAL;
   if (c1 > 0 && !in1) return MASIC_EINVAL;
   if (gdn && (!beta || !gamma)) return MASIC_EINVAL;
   if (transposed_s1 && stride != 1) return MASIC_EINVAL;
   const int ho = (h + stride - 1) / stride, wo = (w + stride - 1) / stride;
+  if (bf_row_pixels == 0) { bf_row_pixels = wo; bf_xoff = 0; }
+  if (bf_row_pixels < wo + bf_xoff || bf_xoff < 0) return MASIC_EINVAL;
   if (ksize == 5 && stride == 1 && c0 == 3 && c1 == 3 && c_out == 3 && act == MASIC_ACT_NONE &&
       (bf_pitch % 2 == 0)) {
     dim3 fgrid((w + F_TW - 1) / F_TW, (h + F_TH - 1) / F_TH, n), fblock(32, 8);
     conv5x5_6to3_kernel<<<fgrid, fblock, 0, static_cast<cudaStream_t>(stream)>>>(
         in0, in1, n, h, w, weight, transposed_s1, bias, gdn, beta, gamma,
         sqrtf(beta_min + 1.4551915228366852e-11f), out_nchw, static_cast<__nv_bfloat16*>(out_nhwc_bf16),
-        bf_pitch);
+        bf_pitch, bf_row_pixels, bf_xoff);
     return (int)cudaGetLastError();
   }
   dim3 grid((wo + 127) / 128, ho, n);
   conv_small_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       in0, c0, in1, c1, n, h, w, weight, transposed_s1, bias, c_out, ksize, stride, act, gdn, beta, gamma,
       sqrtf(beta_min + 1.4551915228366852e-11f), ho, wo, out_nchw,
-      static_cast<__nv_bfloat16*>(out_nhwc_bf16), bf_pitch);
+      static_cast<__nv_bfloat16*>(out_nhwc_bf16), bf_pitch, bf_row_pixels, bf_xoff);
   return (int)cudaGetLastError();
 }
 
@@ -482,12 +490,15 @@ extern "C" int masic_softmax_channels(const float* in_nchw, int n, int c, int hw
   return (int)cudaGetLastError();
 }
 
-extern "C" int masic_nchw_to_nhwc_bf16(const float* in_nchw, int n, int c, int hw, void* out, int pitch,
-                                       void* stream) {
-  if (!in_nchw || !out || c <= 0 || c > 8 || c > pitch || pitch > 64) return MASIC_EINVAL;
+extern "C" int masic_nchw_to_nhwc_bf16(const float* in_nchw, int n, int c, int h, int w, void* out, int pitch,
+                                       int row_pixels, int xoff, void* stream) {
+  if (!in_nchw || !out || c <= 0 || c > 8 || c > pitch || pitch > 64 || h <= 0 || w <= 0) return MASIC_EINVAL;
+  if (row_pixels == 0) { row_pixels = w; xoff = 0; }
+  if (row_pixels < w + xoff || xoff < 0) return MASIC_EINVAL;
+  const int hw = h * w;
   const long total = (long)n * hw;
   nchw_to_nhwc_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      in_nchw, n, c, hw, static_cast<__nv_bfloat16*>(out), pitch);
+      in_nchw, n, c, hw, static_cast<__nv_bfloat16*>(out), pitch, w, row_pixels, xoff);
   return (int)cudaGetLastError();
 }
 

@@ -26,11 +26,12 @@ import torch
 
 from . import _lib
 from ._lib import MasicError, check
-from .convplan import (ACT_LEAKY, ACT_NONE, ACT_RELU, CONV, DECONV_S2, DECONV_S2_SUBPIX, GDN_FWD, GDN_INV,
+from .convplan import (ACT_LEAKY, ACT_NONE, ACT_RELU, CONV, CONV_XFOLD4, DECONV_S2, DECONV_S2_SUBPIX, GDN_FWD, GDN_INV,
                        GDN_NONE, MASK_A_5x5, ConvPlan, PackedConv)
 
 SCALE_BOUND = 0.11
-IMG_CP = 16          # channel pitch of the NHWC bf16 image buffers feeding g_a_conv1 (3 real channels)
+IMG_CP = 16          # channel pitch of the bf16 images feeding g_a_conv1 (3 real channels); rows are padded:
+XOFF, XPAD = _lib.IMG_XOFF, _lib.IMG_XPAD   # [N][H][W+XPAD][16], pixel x at column x+XOFF (MASIC_CONV_XFOLD4 input)
 
 
 class HSICEngine:
@@ -109,8 +110,8 @@ class HSICEngine:
     def _encoder_weights(self, enc: str):
         N, M = self.N, self.M
         return [
-            self._pack(f"{enc}.g_a_conv1", c_in=IMG_CP, c_out=N, n_tile=128, gdn=GDN_FWD, gdn_prefix=f"{enc}.g_a_gdn1",
-                       pad_cin_from=3),
+            self._pack(f"{enc}.g_a_conv1", kind=CONV_XFOLD4, c_in=64, c_out=N, n_tile=128, gdn=GDN_FWD,
+                       gdn_prefix=f"{enc}.g_a_gdn1"),
             self._pack(f"{enc}.g_a_conv2", c_in=N, c_out=N, n_tile=128, gdn=GDN_FWD, gdn_prefix=f"{enc}.g_a_gdn2"),
             self._pack(f"{enc}.g_a_conv3", c_in=N, c_out=N, n_tile=128, gdn=GDN_FWD, gdn_prefix=f"{enc}.g_a_gdn3"),
             self._pack(f"{enc}.g_a_conv4", c_in=N, c_out=M, n_tile=192),
@@ -259,7 +260,9 @@ class HSICEngine:
             check(self.lib.masic_warp_perspective_fwd(None if src is None else src.data_ptr(), B, channels, H, W, H, W,
                                                       T.data_ptr(), None if dst is None else dst.data_ptr(),
                                                       None if dst_bf is None else dst_bf.data_ptr(),
-                                                      0 if dst_bf is None else dst_bf.shape[3], self._s()),
+                                                      0 if dst_bf is None else dst_bf.shape[3],
+                                                      0 if dst_bf is None else dst_bf.shape[2],
+                                                      0 if dst_bf is None else XOFF, self._s()),
                   "masic_warp_perspective_fwd")
         self._add(tag, step)
 
@@ -281,7 +284,9 @@ class HSICEngine:
                                                  None if gamma is None else gamma.data_ptr(), 1e-6,
                                                  None if out is None else out.data_ptr(),
                                                  None if out_bf is None else out_bf.data_ptr(),
-                                                 0 if out_bf is None else out_bf.shape[3], self._s()),
+                                                 0 if out_bf is None else out_bf.shape[3],
+                                                 0 if out_bf is None else out_bf.shape[2],
+                                                 0 if out_bf is None else XOFF, self._s()),
                   "masic_conv_small_nchw")
         self._add(tag, step)
 
@@ -304,9 +309,9 @@ class HSICEngine:
 
         # ---------------- lane 0: left encoder (MASIC.py:746, :755)
         self._on(0)
-        x1_bf = self._buf(B, H, W, IMG_CP)
+        x1_bf = self._buf(B, H, W + XPAD, IMG_CP)
         self._add("x1.pack_nhwc", lambda: check(lib.masic_nchw_to_nhwc_bf16(
-            self.x1.data_ptr(), B, 3, H * W, x1_bf.data_ptr(), IMG_CP, self._s()), "masic_nchw_to_nhwc_bf16"))
+            self.x1.data_ptr(), B, 3, H, W, x1_bf.data_ptr(), IMG_CP, W + XPAD, XOFF, self._s()), "masic_nchw_to_nhwc_bf16"))
         enc1 = self._encoder_weights("encoder1")
         y1 = self._encoder("L.g_a", enc1, x1_bf)
         y1_abs = self._buf(B, h16, w16, M)
@@ -342,7 +347,7 @@ class HSICEngine:
         self._record("mw")
         x1_warp = self._buf(B, 3, H, W, dtype=f32)
         self._warp("R.warp(x1)", self.x1, T, x1_warp)
-        x2in_bf = self._buf(B, H, W, IMG_CP)
+        x2in_bf = self._buf(B, H, W + XPAD, IMG_CP)
         self._conv_small("R.pre_conv+pre_gdn", x1_warp, self.x2, "encoder2.pre_conv", ksize=5, stride=1, gdn=GDN_FWD,
                          gdn_prefix="encoder2.pre_gdn", out_bf=x2in_bf)
         y2 = self._encoder("R.g_a", self._encoder_weights("encoder2"), x2in_bf)
@@ -375,7 +380,7 @@ class HSICEngine:
             "masic_subpix_to_nchw"))
         # x1_hat warped once (the reference computes it twice, :821 and :833)
         x1hw = self._buf(B, 3, H, W, dtype=f32)
-        x1hw_bf = self._buf(B, H, W, IMG_CP)
+        x1hw_bf = self._buf(B, H, W + XPAD, IMG_CP)
         self._wait("T")
         self._warp("R.warp(x1_hat)", o["x1_hat"], T, x1hw, x1hw_bf)
         y1w = self._encoder("R.g_a(enc1 on warped x1_hat)", enc1, x1hw_bf)                         # :822

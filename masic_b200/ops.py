@@ -183,7 +183,7 @@ def warp_perspective(src: Optional[torch.Tensor], M: torch.Tensor, dsize: Tuple[
     dst = torch.empty(n, c, ho, wo, dtype=torch.float32, device=M.device)
     dst_bf = torch.empty(n, ho, wo, bf16_pitch, dtype=torch.bfloat16, device=M.device) if bf16_pitch else None
     check(_lib.load().masic_warp_perspective_fwd(_p(src), n, c, h, w, ho, wo, T.data_ptr(), dst.data_ptr(),
-                                                 _p(dst_bf), bf16_pitch, _s()), "masic_warp_perspective_fwd")
+                                                 _p(dst_bf), bf16_pitch, 0, 0, _s()), "masic_warp_perspective_fwd")
     return (dst, dst_bf) if bf16_pitch else dst
 
 
@@ -207,7 +207,7 @@ def conv_small(in0: torch.Tensor, in1: Optional[torch.Tensor], weight: torch.Ten
     check(_lib.load().masic_conv_small_nchw(in0.data_ptr(), c0, _p(in1), c1, n, h, w, weight.data_ptr(),
                                             int(transposed_s1), _p(bias), c_out, ksize, stride, act, gdn, _p(beta),
                                             _p(gamma), float(beta_min), _p(out), _p(out_bf16),
-                                            0 if out_bf16 is None else out_bf16.shape[3], _s()),
+                                            0 if out_bf16 is None else out_bf16.shape[3], 0, 0, _s()),
           "masic_conv_small_nchw")
     return out if out is not None else out_bf16
 
@@ -229,7 +229,7 @@ def nchw_to_nhwc_bf16(x: torch.Tensor, pitch: int, out: Optional[torch.Tensor] =
     n, c, h, w = x.shape
     if out is None:
         out = torch.empty(n, h, w, pitch, dtype=torch.bfloat16, device=x.device)
-    check(_lib.load().masic_nchw_to_nhwc_bf16(x.data_ptr(), n, c, h * w, out.data_ptr(), pitch, _s()),
+    check(_lib.load().masic_nchw_to_nhwc_bf16(x.data_ptr(), n, c, h, w, out.data_ptr(), pitch, 0, 0, _s()),
           "masic_nchw_to_nhwc_bf16")
     return out
 

@@ -48,6 +48,8 @@ def run_case(name, *, kind=CONV, k, stride=1, tap_mask=0, n=1, h, w, c_in, c_out
              in_coff=0, out_cp=None, out_coff=0, out_fp32=False, act=ACT_NONE, gdn=GDN_NONE, bias=True,
              rowscale=False, transposed=None, seed=0):
     torch.manual_seed(seed)
+    if kind == 3:
+        return run_xfold4(name, n=n, h=h, w=w, c_out=c_out, n_tile=n_tile, gdn=gdn)
     transposed = (kind != CONV) if transposed is None else transposed
     in_cp = in_cp or max(c_in + in_coff, 8)
     x = (torch.randn(n, h, w, in_cp, device=dev) * 1.0).to(torch.bfloat16)
@@ -127,6 +129,39 @@ def run_case(name, *, kind=CONV, k, stride=1, tap_mask=0, n=1, h, w, c_in, c_out
     return ok
 
 
+def run_xfold4(name, *, n, h, w, c_out, n_tile, gdn):
+    """g_a_conv1 path: NCHW fp32 image -> window-4 pack kernel -> XFOLD4 plan (+GDN) vs torch conv2d."""
+    from masic_b200 import _lib as L
+    img = torch.rand(n, 3, h, w, device=dev)
+    wt = torch.randn(c_out, 3, 5, 5, device=dev) / 75 ** 0.5
+    b = torch.randn(c_out, device=dev) * 0.1
+    xw = torch.zeros(n, h, w + L.IMG_XPAD, 16, device=dev, dtype=torch.bfloat16)
+    L.check(L.load().masic_nchw_to_nhwc_bf16(img.data_ptr(), n, 3, h, w, xw.data_ptr(), 16, w + L.IMG_XPAD, L.IMG_XOFF,
+                                             torch.cuda.current_stream().cuda_stream), "pack")
+    out = torch.zeros(n, h // 2, w // 2, c_out, device=dev, dtype=torch.bfloat16)
+    gb = torch.sqrt(torch.rand(c_out, device=dev) * 0.5 + 0.75)
+    gg = torch.sqrt(torch.rand(c_out, c_out, device=dev) * 0.02 + 0.1 * torch.eye(c_out, device=dev))
+    plan = ConvPlan(kind=3, ksize=5, stride=2, x=xw, c_in=64, weight=wt, bias=b, c_out=c_out, n_tile=n_tile, out=out,
+                    gdn=gdn, gdn_beta=gb, gdn_gamma=gg)
+    plan.launch()
+    torch.cuda.synchronize()
+    y = F.conv2d(img.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float(), b, stride=2, padding=2).permute(0, 2, 3, 1)
+    if gdn:
+        beta_p, g32, _ = gdn_prepare(gb, gg)
+        norm = torch.einsum("nhwj,ij->nhwi", y * y, g32) + beta_p
+        y = y * torch.rsqrt(norm)
+    err = (out.float() - y).abs()
+    scale = y.abs().max().item()
+    ok = bool(torch.isfinite(out.float()).all()) and err.max().item() <= 3e-2 * scale
+    print(f"[{name}] {'OK ' if ok else 'BAD'} maxerr={err.max().item():.4g} scale={scale:.4g} work={plan.work_items}", flush=True)
+    if not ok:
+        bad = (err > 3e-2 * scale).nonzero()
+        print("    first bad", bad[:6].tolist(), "count", bad.shape[0], "of", err.numel())
+        xs = sorted(set(bad[:, 2].tolist()))
+        print("    bad x columns:", xs[:20], " bad y rows:", sorted(set(bad[:, 1].tolist()))[:20])
+    return ok
+
+
 CASES = {
     "1x1_min": dict(k=1, h=16, w=8, c_in=64, c_out=128, n_tile=128, bias=False),
     "1x1_k128_bias_relu_partial": dict(k=1, h=20, w=12, c_in=128, c_out=128, n_tile=128, act=ACT_RELU),
@@ -148,6 +183,7 @@ CASES = {
                        act=[ACT_RELU, ACT_RELU, ACT_LEAKY, ACT_LEAKY, ACT_NONE, ACT_RELU]),
     "1x1_deconvk1": dict(k=1, h=16, w=8, c_in=128, c_out=256, n_tile=128, transposed=True),
     "1x1_ntile240": dict(k=1, h=16, w=24, c_in=192, c_out=960, n_tile=192, out_fp32=True, in_coff=64, in_cp=320),
+    "xfold4_conv1_gdn": dict(kind=3, k=5, stride=2, n=2, h=48, w=40, c_in=3, c_out=128, n_tile=128, gdn=GDN_FWD),
     "batch2_s2": dict(k=5, stride=2, n=2, h=32, w=16, c_in=64, c_out=128, n_tile=128),
 }
 
