@@ -40,8 +40,10 @@ namespace masic {
 constexpr int TILE_W = 8;
 constexpr int TILE_H = 16;
 constexpr int KBLK = 64;            // channels per k-block: 128 B of bf16 = one swizzle row
-constexpr int NUM_THREADS = 384;    // stream 0: warps 0 (A producer), 1 (B producer), 2 (MMA); warp 3: TMEM alloc;
-                                    // warps 4-7: epilogue; stream 1: warps 8 (A), 9 (B), 10 (MMA); warp 11 idle
+constexpr int NUM_THREADS = 512;    // stream 0: warps 0 (A producer), 1 (B producer), 2 (MMA); warp 3: TMEM alloc;
+                                    // warps 4-7: epilogue group 0; stream 1: warps 8 (A), 9 (B), 10 (MMA);
+                                    // warp 11 idle; warps 12-15: epilogue group 1 (warp%4 = TMEM lane quarter)
+constexpr int EPI_THREADS = 256;    // both epilogue groups
 constexpr int NUM_STREAMS = 2;      // two independent load->MMA pipelines per CTA, one accumulator buffer each
 constexpr int MAX_VARIANTS = 4;
 constexpr int MAX_STAGES = 8;
@@ -79,6 +81,7 @@ struct KParams {
   int gdn, out_fp32;
   int blk_ch;      // channels per staging block / TMA store
   int blk_pitch;   // bytes per row of a staging block (128 = swizzled)
+  int stage_per_group;   // staging buffers per epilogue group (1 or 2)
   uint8_t act[32];
   int out_coff;
   const float* rowscale;
@@ -98,10 +101,7 @@ constexpr int MISC_ACC_EMPTY = 528;                  // 2 x u64
 constexpr int MISC_GDN_BAR = 544;
 constexpr int MISC_G_FULL = 552;
 constexpr int MISC_TMEM_PTR = 560;
-constexpr int MISC_BIAS = 576;                       // 256 floats
-constexpr int MISC_BETA = 576 + 1024;                // 128 floats
-static_assert(576 + 1024 + 512 <= 2560, "misc region");
-constexpr int MISC_BYTES = 2560;
+constexpr int MISC_BYTES = 1024;
 
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == MASIC_ACT_RELU) return fmaxf(x, 0.0f);
@@ -142,8 +142,6 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
   const uint32_t sG = smem_base + p.smem_g_off;
   const uint32_t sStage = smem_base + p.smem_stage_off;
   const uint32_t sMisc = smem_base + p.smem_misc_off;
-  float* bias_s = reinterpret_cast<float*>(smem_gen + p.smem_misc_off + MISC_BIAS);
-  float* beta_s = reinterpret_cast<float*>(smem_gen + p.smem_misc_off + MISC_BETA);
   volatile uint32_t* tmem_ptr_s =
       reinterpret_cast<volatile uint32_t*>(smem_gen + p.smem_misc_off + MISC_TMEM_PTR);
 
@@ -164,7 +162,7 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(sMisc + MISC_ACC_FULL + 8 * i, 1);
-      mbar_init(sMisc + MISC_ACC_EMPTY + 8 * i, 128);
+      mbar_init(sMisc + MISC_ACC_EMPTY + 8 * i, EPI_THREADS);
     }
     mbar_init(sMisc + MISC_GDN_BAR, 1);
     mbar_init(sMisc + MISC_G_FULL, 1);
@@ -174,7 +172,6 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     tmem_alloc(sMisc + MISC_TMEM_PTR, TMEM_COLS);
     tmem_relinquish();
   }
-  if (threadIdx.x >= 128 && threadIdx.x < 256 && p.gdn) beta_s[threadIdx.x - 128] = p.beta[threadIdx.x - 128];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -185,13 +182,13 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
   // and inside a divergent `if (lane == 0)` region ptxas wraps each of them in an ELECT/BRA.U.ANY
   // waterfall loop (measured: ~320 cycles per 128x128x16 MMA instead of 64).
   // stream s owns tiles it = s, s+2, ... of this CTA's sequence, accumulator buffer s, and its own rings
-  const int sid = warp >= 8 ? 1 : 0;
+  const int sid = (warp >= 8 && warp < 12) ? 1 : 0;
   const int role = warp - 8 * sid;            // 0: A producer, 1: B producer, 2: MMA (warps 3..7 handled below)
   const uint32_t sAs = sA + sid * p.a_stages * p.a_stage_bytes;
   const uint32_t sBs = sB + sid * p.b_stages * p.b_stage_bytes;
   const uint32_t bar_off = sid * MAX_STAGES * 8;
   const int w_first = blockIdx.x + sid * gridDim.x, w_step = NUM_STREAMS * gridDim.x;
-  if (warp != 3 && (warp < 4 || warp >= 8) && role == 0) {
+  if ((warp < 3 || (warp >= 8 && warp < 11)) && role == 0) {
     // ===================== A producer: activation strips =====================
     uint32_t st = 0, ph = 0;
     const uint32_t n_st = p.a_stages, st_bytes = p.a_stage_bytes;
@@ -215,7 +212,7 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
         if (++st == n_st) { st = 0; ph ^= 1; }
       }
     }
-  } else if (warp != 3 && (warp < 4 || warp >= 8) && role == 1) {
+  } else if ((warp < 3 || (warp >= 8 && warp < 11)) && role == 1) {
     // ===================== B producer: weight k-blocks (+ gamma once) =====================
     if (p.gdn && sid == 0 && elect_one()) {
       tma_prefetch_desc(&p.tmG);
@@ -246,7 +243,7 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
         if (++st == n_st) { st = 0; ph ^= 1; }
       }
     }
-  } else if (warp != 3 && (warp < 4 || warp >= 8) && role == 2) {
+  } else if ((warp < 3 || (warp >= 8 && warp < 11)) && role == 2) {
     // ===================== MMA issuer =====================
     const uint32_t n_sa = p.a_stages, n_sb = p.b_stages;
     uint32_t sa = n_sa - 1, pa = 1, sb = n_sb - 1, pb = 1;    // first advance lands on stage 0, phase 0
@@ -297,63 +294,70 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
       }
       if (lane == 0) TRACE(it, 2);
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if ((warp >= 4 && warp < 8) || warp >= 12) {
     // ===================== epilogue: TMEM -> regs -> smem -> TMA store =====================
-    const int ew = warp - 4;            // == warp % 4: the TMEM lane quarter this warp may read
+    // Two groups of 4 warps; group g owns staging buffer g and the channel blocks j = g, g+2, ...
+    // (with GDN: the 64 channels [64g, 64g+64)).  Bias/beta are read through L1 (uniform addresses).
+    const int grp = warp >= 12 ? 1 : 0;
+    const int ew = warp & 3;            // the TMEM lane quarter this warp may read
     const int t = ew * 32 + lane;       // accumulator row = tile position
     const uint32_t lane_sel = static_cast<uint32_t>(ew * 32) << 16;
+    const uint32_t gbar = 1 + grp;      // named barrier of this group (128 threads); barrier 3 = both groups
+    const bool leader = (t == 0);       // issues this group's TMA stores (bulk groups are per thread)
     const int nblk = p.n_tile / p.blk_ch;
     const int chunks_per_blk = p.blk_ch / 16;
+    // staging: with GDN one 16 KB buffer per group (together they are the 32 KB A2 operand of the norm MMA);
+    // without GDN (no gamma resident) two buffers per group, so a block's TMA store drains behind the next block
+    const uint32_t sbuf = sStage + grp * p.stage_per_group * STAGE_BLK_BYTES;
+    uint32_t flip = 0;
+    const float* __restrict__ bias_g = p.bias;
     int it = 0;
-    if (p.gdn && ew == 0) mbar_wait(sMisc + MISC_G_FULL, 0);
+    if (p.gdn && grp == 0 && ew == 0) mbar_wait(sMisc + MISC_G_FULL, 0);
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
       const Work wk = decode_work(p, w);
       const Variant& v = p.var[wk.var];
       const int buf = it & 1;
       const int act = p.act[wk.nt];
       const uint32_t acc_addr = tmem_base + lane_sel + buf * acc_stride;
-
-      if (t == 0) TRACE(it, 4);
-      // stage this n-tile's bias; the barrier also fences the previous tile's readers
-      named_bar_sync(1, 128);
-      for (int c = t; c < p.n_tile; c += 128) bias_s[c] = p.bias ? p.bias[wk.nt * p.n_tile + c] : 0.0f;
+      const float* __restrict__ bias_t = bias_g ? bias_g + wk.nt * p.n_tile : nullptr;
+      if (t == 0 && grp == 0) TRACE(it, 4);
       float rs = 1.0f;
       if (p.rowscale) {
         const int y = wk.ty * TILE_H + (t >> 3), x = wk.tx * TILE_W + (t & 7);
         if (y < p.rs_H && x < p.rs_W)
           rs = p.rowscale[(static_cast<size_t>(wk.n * p.rs_H + y) * p.rs_W + x) * p.rs_stride + p.rs_off];
       }
-      if (t == 0) tma_store_wait_read<0>();     // staging (and A2) free again
-      named_bar_sync(1, 128);
-
-      if (t == 0) TRACE(it, 5);
+      if (t == 0 && grp == 0) TRACE(it, 5);
       mbar_wait(sMisc + MISC_ACC_FULL + 8 * buf, (it >> 1) & 1);
       tc_fence_after();
-      if (t == 0) TRACE(it, 6);
+      if (t == 0 && grp == 0) TRACE(it, 6);
 
       if (p.gdn) {
-        // ---- pass 1: A2 = bf16((acc + bias)^2), K-major SWIZZLE_128B, two 64-channel blocks
-        for (int c = 0; c < 128; c += 16) {
+        // ---- pass 1: A2[:, 64g .. 64g+64) = bf16((acc + bias)^2), K-major SWIZZLE_128B block g
+        if (leader) tma_store_wait_read<0>();          // staging buffer g (== A2 block g) free again
+        named_bar_sync(gbar, 128);
+        const uint32_t arow = sbuf + t * 128;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c = grp * 64 + cc * 16;
           uint32_t r[16];
           tmem_ld16(acc_addr + c, r);
           tmem_ld_wait();
           uint32_t q[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float x0 = __uint_as_float(r[2 * i]) + bias_s[c + 2 * i];
-            const float x1 = __uint_as_float(r[2 * i + 1]) + bias_s[c + 2 * i + 1];
+            const float x0 = __uint_as_float(r[2 * i]) + __ldg(bias_t + c + 2 * i);
+            const float x1 = __uint_as_float(r[2 * i + 1]) + __ldg(bias_t + c + 2 * i + 1);
             q[i] = pack_bf16x2(x0 * x0, x1 * x1);
           }
-          const uint32_t blk = sStage + (c >> 6) * STAGE_BLK_BYTES + t * 128;
-          const int ch0 = (c & 63) >> 3;
-          st_shared_v4(blk + (((ch0) ^ (t & 7)) << 4), q[0], q[1], q[2], q[3]);
-          st_shared_v4(blk + (((ch0 + 1) ^ (t & 7)) << 4), q[4], q[5], q[6], q[7]);
+          st_shared_v4(arow + (((2 * cc) ^ (t & 7)) << 4), q[0], q[1], q[2], q[3]);
+          st_shared_v4(arow + (((2 * cc + 1) ^ (t & 7)) << 4), q[4], q[5], q[6], q[7]);
         }
         fence_proxy_async_smem();
         tc_fence_before();
-        named_bar_sync(1, 128);
-        if (t == 0) TRACE(it, 7);
-        if (ew == 0) {                      // warp-uniform; one elected lane issues the 8 MMAs
+        named_bar_sync(3, EPI_THREADS);
+        if (t == 0 && grp == 0) TRACE(it, 7);
+        if (grp == 0 && ew == 0) {                      // warp-uniform; one elected lane issues the 8 MMAs
           tc_fence_after();
           if (elect_one()) {
             const uint32_t d2 = tmem_base + 2 * acc_stride;
@@ -371,80 +375,97 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
         }
         mbar_wait(sMisc + MISC_GDN_BAR, it & 1);
         tc_fence_after();
-        if (t == 0) TRACE(it, 8);
-      }
-
-      // ---- pass 2: finalise and store, one staging block (<= 16 KB) at a time
-      const uint32_t norm_addr = tmem_base + lane_sel + 2 * acc_stride;
-      for (int j = 0; j < nblk; ++j) {
-        const uint32_t sbuf = sStage + (j & 1) * STAGE_BLK_BYTES;
-        if (j >= 2) {
-          if (t == 0) tma_store_wait_read<1>();
-          named_bar_sync(1, 128);
-        }
-        for (int cc = 0; cc < chunks_per_blk; ++cc) {
-          const int c = j * p.blk_ch + cc * 16;
-          uint32_t r[16];
-          float o[16];
-          tmem_ld16(acc_addr + c, r);
-          if (p.gdn) {
-            uint32_t g[16];
-            tmem_ld16(norm_addr + c, g);
-            tmem_ld_wait();
+        if (t == 0 && grp == 0) TRACE(it, 8);
+        // ---- pass 2: out[:, 64g .. 64g+64) = x * rsqrt(beta + norm)  (IGDN: x * sqrt(.))
+        const uint32_t norm_addr = tmem_base + lane_sel + 2 * acc_stride;
+        const float* __restrict__ beta_g = p.beta;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float x = __uint_as_float(r[i]) + bias_s[c + i];
-              const float nrm = __uint_as_float(g[i]) + beta_s[c + i];
-              // IGDN: sqrt(n) = n * rsqrt(n) on the MUFU fast path (sqrtf's IEEE path doubled the epilogue time;
-              // 2-ulp rsqrt is far below the bf16 output rounding)
-              const float rs_n = rsqrtf(nrm);
-              o[i] = (p.gdn == MASIC_GDN_FWD) ? x * rs_n : x * (nrm * rs_n);
-            }
-          } else {
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c = grp * 64 + cc * 16;
+          uint32_t r[16], g[16];
+          tmem_ld16(acc_addr + c, r);
+          tmem_ld16(norm_addr + c, g);
+          tmem_ld_wait();
+          float o[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float x = __uint_as_float(r[i]) + __ldg(bias_t + c + i);
+            const float nrm = __uint_as_float(g[i]) + __ldg(beta_g + c + i);
+            // IGDN: sqrt(n) = n * rsqrt(n) on the MUFU fast path (2-ulp rsqrt is far below bf16 rounding)
+            const float rs_n = rsqrtf(nrm);
+            o[i] = ((p.gdn == MASIC_GDN_FWD) ? x * rs_n : x * (nrm * rs_n)) * rs;
+          }
+          st_shared_v4(arow + (((2 * cc) ^ (t & 7)) << 4), pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                       pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+          st_shared_v4(arow + (((2 * cc + 1) ^ (t & 7)) << 4), pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]),
+                       pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
+        }
+        tc_fence_before();
+        mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * buf);
+        fence_proxy_async_smem();
+        named_bar_sync(gbar, 128);
+        if (leader && !(p.debug & 4)) {
+          tma_store_5d(&p.tmO, sbuf, p.out_coff + v.out_c0 + wk.nt * p.n_tile + grp * 64, wk.tx * TILE_W, v.out_p2,
+                       wk.ty * TILE_H, wk.n);
+          tma_store_commit();
+        }
+      } else {
+        // ---- plain epilogue: bias, activation, per-pixel scale; this group's blocks j = grp, grp+2, ...
+        for (int j = grp; j < nblk; j += 2) {
+          const uint32_t sb2 = sbuf + flip * STAGE_BLK_BYTES;
+          if (p.stage_per_group == 2) {
+            flip ^= 1;
+            if (leader) tma_store_wait_read<1>();      // the store issued two blocks ago has left this buffer
+          } else if (leader) {
+            tma_store_wait_read<0>();
+          }
+          named_bar_sync(gbar, 128);
+          const uint32_t row = sb2 + t * p.blk_pitch;
+          const int sw = (p.blk_pitch == 128) ? (t & 7) : 0;
+          for (int cc = 0; cc < chunks_per_blk; ++cc) {
+            const int c = j * p.blk_ch + cc * 16;
+            uint32_t r[16];
+            float o[16];
+            tmem_ld16(acc_addr + c, r);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              o[i] = apply_act(__uint_as_float(r[i]) + bias_s[c + i], act);
+              o[i] = apply_act(__uint_as_float(r[i]) + (bias_t ? __ldg(bias_t + c + i) : 0.0f), act) * rs;
+            if (p.out_fp32) {
+              const int ch0 = cc * 4;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                st_shared_v4(row + (((ch0 + i) ^ sw) << 4), __float_as_uint(o[4 * i]), __float_as_uint(o[4 * i + 1]),
+                             __float_as_uint(o[4 * i + 2]), __float_as_uint(o[4 * i + 3]));
+            } else {
+              const int ch0 = cc * 2;
+#pragma unroll
+              for (int i = 0; i < 2; ++i)
+                st_shared_v4(row + (((ch0 + i) ^ sw) << 4), pack_bf16x2(o[8 * i], o[8 * i + 1]),
+                             pack_bf16x2(o[8 * i + 2], o[8 * i + 3]), pack_bf16x2(o[8 * i + 4], o[8 * i + 5]),
+                             pack_bf16x2(o[8 * i + 6], o[8 * i + 7]));
+            }
           }
-          if (p.rowscale) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] *= rs;
+          if (j + 2 >= nblk) {      // this group's last TMEM read of the accumulator
+            tc_fence_before();
+            mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * buf);
           }
-          const uint32_t row = sbuf + t * p.blk_pitch;
-          const int sw = (p.blk_pitch == 128) ? (t & 7) : 0;
-          if (p.out_fp32) {
-            const int ch0 = cc * 4;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              st_shared_v4(row + (((ch0 + i) ^ sw) << 4), __float_as_uint(o[4 * i]),
-                           __float_as_uint(o[4 * i + 1]), __float_as_uint(o[4 * i + 2]),
-                           __float_as_uint(o[4 * i + 3]));
-          } else {
-            const int ch0 = cc * 2;
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-              st_shared_v4(row + (((ch0 + i) ^ sw) << 4), pack_bf16x2(o[8 * i], o[8 * i + 1]),
-                           pack_bf16x2(o[8 * i + 2], o[8 * i + 3]),
-                           pack_bf16x2(o[8 * i + 4], o[8 * i + 5]),
-                           pack_bf16x2(o[8 * i + 6], o[8 * i + 7]));
+          fence_proxy_async_smem();
+          named_bar_sync(gbar, 128);
+          if (leader && !(p.debug & 4)) {
+            tma_store_5d(&p.tmO, sb2, p.out_coff + v.out_c0 + wk.nt * p.n_tile + j * p.blk_ch, wk.tx * TILE_W,
+                         v.out_p2, wk.ty * TILE_H, wk.n);
+            tma_store_commit();
           }
         }
-        if (j == nblk - 1) {
-          // every TMEM read of this accumulator has retired: hand it back to the MMA warp
+        if (grp >= nblk) {          // nothing to do for this group (single-block tile): just release the accumulator
           tc_fence_before();
           mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * buf);
         }
-        fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (t == 0) {
-          tma_store_5d(&p.tmO, sbuf, p.out_coff + v.out_c0 + wk.nt * p.n_tile + j * p.blk_ch,
-                       wk.tx * TILE_W, v.out_p2, wk.ty * TILE_H, wk.n);
-          tma_store_commit();
-        }
       }
-      if (t == 0) TRACE(it, 9);
+      if (t == 0 && grp == 0) TRACE(it, 9);
     }
-    if (t == 0) tma_store_wait_all<0>();
+    if (leader) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -726,7 +747,7 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   if (d.kind == MASIC_CONV_XFOLD4 && d.c_in != 64) return MASIC_EINVAL;
   if (d.out_cpitch % (d.out_fp32 ? 4 : 8)) return MASIC_EINVAL;
   if (d.ksize != 1 && d.ksize != 3 && d.ksize != 5) return MASIC_EINVAL;
-  if (d.gdn && (d.n_tile != 128 || d.c_out != 128 || !d.gamma_packed || !d.beta)) return MASIC_EINVAL;
+  if (d.gdn && (d.n_tile != 128 || d.c_out != 128 || !d.gamma_packed || !d.beta || !d.bias)) return MASIC_EINVAL;
   if ((d.kind == MASIC_CONV || d.kind == MASIC_CONV_XFOLD4) && d.stride == 2 && (d.h_in % 2 || d.w_in % 2))
     return MASIC_EINVAL;
 
@@ -767,9 +788,18 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   // shared memory carve-up
   kp.a_stage_bytes = rows * 1024;
   kp.b_stage_bytes = d.n_tile * 128;
-  const int fixed = (d.gdn ? 2 * STAGE_BLK_BYTES : 0) + 2 * STAGE_BLK_BYTES + MISC_BYTES + 1024 /*align*/;
-  const int budget = (227 * 1024 - fixed) / NUM_STREAMS;      // ring bytes per stream
+  // staging: with GDN one block per epilogue group (the pair is the A2 operand); otherwise two per group when
+  // the minimum rings (2 A + 2 B stages per stream) still fit, else one
+  int n_stage_blk = d.gdn ? 2 : 4;
+  int fixed = (d.gdn ? 2 * STAGE_BLK_BYTES : 0) + n_stage_blk * STAGE_BLK_BYTES + MISC_BYTES + 1024 /*align*/;
+  int budget = (227 * 1024 - fixed) / NUM_STREAMS;            // ring bytes per stream
   int sa = 2, sb = 2;
+  if (n_stage_blk == 4 && sa * kp.a_stage_bytes + sb * kp.b_stage_bytes > budget) {
+    n_stage_blk = 2;
+    fixed -= 2 * STAGE_BLK_BYTES;
+    budget = (227 * 1024 - fixed) / NUM_STREAMS;
+  }
+  kp.stage_per_group = n_stage_blk / 2;
   if (sa * kp.a_stage_bytes + sb * kp.b_stage_bytes > budget) { delete pl; return MASIC_EINVAL; }
   // deepen the rings with what is left (B first: a B stage is consumed by a single op)
   for (bool grew = true; grew;) {
@@ -781,7 +811,7 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   kp.smem_b_off = NUM_STREAMS * sa * kp.a_stage_bytes;
   kp.smem_g_off = kp.smem_b_off + NUM_STREAMS * sb * kp.b_stage_bytes;
   kp.smem_stage_off = kp.smem_g_off + (d.gdn ? 2 * STAGE_BLK_BYTES : 0);
-  kp.smem_misc_off = kp.smem_stage_off + 2 * STAGE_BLK_BYTES;
+  kp.smem_misc_off = kp.smem_stage_off + n_stage_blk * STAGE_BLK_BYTES;
   pl->smem_bytes = kp.smem_misc_off + MISC_BYTES + 1024;
   if (pl->smem_bytes < 120 * 1024) pl->smem_bytes = 120 * 1024;   // keep 1 CTA/SM: 512 TMEM cols each
 
