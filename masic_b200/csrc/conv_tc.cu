@@ -8,8 +8,8 @@
 //   MaskedConv2d.forward               compressai/layers/layers.py:75-78
 //   the nn.ReLU / nn.LeakyReLU that follow them in MASIC.py:173-183,338-444,678-691
 //
-// Design (see DESIGN.md §3):
-//   * activations NHWC bf16; one CTA tile = 16 rows x 8 cols of output positions (M = 128);
+// Design (see DESIGN.md §4.1):
+//   * activations NHWC bf16; one tile = 16 rows x 8 cols of output positions (M = 128);
 //   * the A operand of every filter tap is a *row-shifted window* of a "strip" —
 //     (16 + taps-1) rows x 8 cols x 64 channels — that TMA drops into shared memory once,
 //     so vertical taps re-use the same bytes (rows are 1024 B = one SWIZZLE_128B atom, so
@@ -17,11 +17,17 @@
 //   * stride-2 convs read the input through a 5-D "phase split" view
 //     (2C, W/2, 2, H/2, N) of the same NHWC buffer, stride-2 transposed convs write their
 //     output through the same view — no im2col, no scatter kernels;
-//   * a per-layer *program* (A loads, B loads, MMA ops) built on the host drives three
-//     single-thread roles (A producer, B producer, MMA issuer); 4 epilogue warps drain the
-//     double-buffered TMEM accumulator: +bias, activation, optional GDN (a second
-//     128x128x128 tcgen05.mma on the squared tile against gamma), optional per-pixel scale,
-//     then swizzled smem staging and a TMA store.
+//   * a work item is a PAIR of tiles of the same (variant, n-tile) when the accumulator is
+//     <= 128 columns wide: every weight k-block that TMA brings in feeds two M=128 MMAs
+//     (M = 256 per CTA per B stage), and the TMEM holds two such pairs (4 x 128 columns) so the
+//     epilogue of one item overlaps the MMAs of the next; wider accumulators (<= 256
+//     columns) run as single tiles, double-buffered the same way;
+//   * a per-layer *program* (strips -> taps) built on the host drives three warp-uniform roles
+//     (A producer, B producer, MMA issuer); 8 epilogue warps (two groups splitting the
+//     channels) drain the accumulators: +bias, activation, optional GDN — the squared tile goes
+//     to smem as a bf16 A operand, a second tcgen05.mma against gamma' writes the norm IN PLACE
+//     over the accumulator while x stays in registers — optional per-pixel scale, then
+//     swizzled smem staging and a TMA store.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -40,25 +46,26 @@ namespace masic {
 constexpr int TILE_W = 8;
 constexpr int TILE_H = 16;
 constexpr int KBLK = 64;            // channels per k-block: 128 B of bf16 = one swizzle row
-constexpr int NUM_THREADS = 512;    // stream 0: warps 0 (A producer), 1 (B producer), 2 (MMA); warp 3: TMEM alloc;
-                                    // warps 4-7: epilogue group 0; stream 1: warps 8 (A), 9 (B), 10 (MMA);
-                                    // warp 11 idle; warps 12-15: epilogue group 1 (warp%4 = TMEM lane quarter)
-constexpr int EPI_THREADS = 256;    // both epilogue groups
-constexpr int NUM_STREAMS = 2;      // two independent load->MMA pipelines per CTA, one accumulator buffer each
+constexpr int NUM_THREADS = 384;    // warp 0: A producer, 1: B producer, 2: MMA issuer, 3: TMEM alloc;
+                                    // warps 4-7: epilogue group 0, warps 8-11: epilogue group 1
+                                    // (warp % 4 = the TMEM lane quarter a warp may read)
+constexpr int EPI_THREADS = 256;
 constexpr int MAX_VARIANTS = 4;
 constexpr int MAX_STAGES = 8;
-constexpr int MAX_AOPS = 64, MAX_BOPS = 96, MAX_MOPS = 96;
+constexpr int MAX_STRIPS = 64, MAX_BOPS = 96;
 constexpr int STAGE_BLK_BYTES = 16384;  // one 128-row x 128-B staging block
 constexpr uint32_t TMEM_COLS = 512;
 
-struct AOp { int16_t c0, dx, p2, dy; };          // TMA coordinates relative to the tile origin
-struct BOp { int32_t row0; };                    // first row of the k-block in the packed weights
-struct MOp { uint16_t a_row; uint8_t nk; uint8_t flags; };   // nk: low nibble = #K16 steps, high nibble = first step
-enum { M_NEW_A = 1, M_NEW_B = 2, M_FIRST = 4, M_REL_A = 8, M_REL_B = 16 };
+// One A strip of the per-tile program and the taps (MMA groups) that read it.
+struct Strip {
+  int16_t c0, dx, p2, dy;   // TMA coordinates relative to the tile origin
+  uint8_t n_taps;           // MMA groups fed by this strip (one B k-block each)
+  int8_t a_row0, a_step;    // strip row of tap j = a_row0 + j * a_step
+  uint8_t nk;               // low nibble: K=16 steps per tap, high nibble: first step
+};
 
 struct Variant {
-  int n_aops, n_bops, n_mops;
-  int aops_off, bops_off, mops_off;
+  int strip_off, n_strips, bop_off, n_bops;
   int out_p2;   // phase-row coordinate in the 5-D output view
   int out_c0;   // channel offset inside the output view (px * Cpitch)
 };
@@ -66,48 +73,45 @@ struct Variant {
 struct KParams {
   CUtensorMap tmA, tmB, tmO, tmG;
   // per-layer programs live in the kernel-parameter constant bank: the role loops read them with
-  // warp-uniform indices, so ptxas keeps ops / descriptors in uniform registers (no R2UR, no L1 trip)
-  AOp aops[MAX_AOPS];
-  BOp bops[MAX_BOPS];
-  MOp mops[MAX_MOPS];
+  // warp-uniform indices
+  Strip strips[MAX_STRIPS];
+  int32_t bops[MAX_BOPS];          // first row of the tap's k-block in the packed weights
   Variant var[MAX_VARIANTS];
   int n_var;
   int tiles_x, tiles_y, n_img, n_ntiles;
+  int n_spatial;                   // tiles_x * tiles_y * n_img
+  int n_tiles_total;               // n_spatial * n_var * n_ntiles; tile id u = group * n_spatial + s
   int n_tile;
-  int a_stage_bytes, b_stage_bytes, a_stages, b_stages;
+  int pair;                        // tiles per work item: 2 (n_tile <= 128) or 1
+  int strip_bytes, b_stage_bytes, a_stages, b_stages;
   int smem_b_off, smem_g_off, smem_stage_off, smem_misc_off;
   const float* bias;
   const float* beta;
   int gdn, out_fp32;
   int blk_ch;      // channels per staging block / TMA store
   int blk_pitch;   // bytes per row of a staging block (128 = swizzled)
-  int stage_per_group;   // staging buffers per epilogue group (1 or 2)
-  uint8_t act[32];
+  float slope[32]; // per n-tile activation: out = max(x,0) + slope * min(x,0)
   int out_coff;
   const float* rowscale;
   int rs_stride, rs_off, rs_H, rs_W;
   uint32_t idesc;
-  long long* trace; // optional [64 tiles][16] clock64() stamps of CTA 0 (MASIC_CONV_TRACE=1)
-  int debug;       // bit0: skip A loads, bit1: skip B loads (timing experiments only; results are garbage)
+  int debug;       // bit0: skip A loads, bit1: skip B loads, bit2: skip stores (timing experiments only)
 };
 
 // misc smem region layout (byte offsets from smem_misc_off)
-constexpr int MISC_A_FULL = 0;                       // [2 streams][8] x u64
-constexpr int MISC_A_EMPTY = 128;
-constexpr int MISC_B_FULL = 256;
-constexpr int MISC_B_EMPTY = 384;
-constexpr int MISC_ACC_FULL = 512;                   // 2 x u64
-constexpr int MISC_ACC_EMPTY = 528;                  // 2 x u64
-constexpr int MISC_GDN_BAR = 544;
-constexpr int MISC_G_FULL = 552;
-constexpr int MISC_TMEM_PTR = 560;
-constexpr int MISC_BYTES = 1024;
+constexpr int MISC_A_FULL = 0;                       // [8] x u64
+constexpr int MISC_A_EMPTY = 64;
+constexpr int MISC_B_FULL = 128;
+constexpr int MISC_B_EMPTY = 192;
+constexpr int MISC_ACC_FULL = 256;                   // 2 x u64
+constexpr int MISC_ACC_EMPTY = 272;                  // 2 x u64
+constexpr int MISC_GDN_BAR = 288;
+constexpr int MISC_G_FULL = 296;
+constexpr int MISC_TMEM_PTR = 304;
+constexpr int MISC_BIAS = 512;                       // 128 floats (GDN layers: bias of the single n-tile)
+constexpr int MISC_BETA = 1024;                      // 128 floats
+constexpr int MISC_BYTES = 1536;
 
-__device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == MASIC_ACT_RELU) return fmaxf(x, 0.0f);
-  if (act == MASIC_ACT_LEAKY) return x > 0.0f ? x : 0.01f * x;
-  return x;
-}
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -118,17 +122,33 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
                "r"(d)
                : "memory");
 }
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 
-#define TRACE(it, slot) do { if (p.trace && blockIdx.x == 0 && (it) < 64) p.trace[(it) * 16 + (slot)] = clock64(); } while (0)
-
-struct Work { int n, ty, tx, var, nt; };
-__device__ __forceinline__ Work decode_work(const KParams& p, int w) {
-  Work r;
-  r.nt = w % p.n_ntiles; w /= p.n_ntiles;
-  r.var = w % p.n_var;   w /= p.n_var;
-  r.tx = w % p.tiles_x;  w /= p.tiles_x;
-  r.ty = w % p.tiles_y;  r.n = w / p.tiles_y;
-  return r;
+// A work item: `cnt` (1 or 2) tiles u, u+1 of the same group (variant, n-tile).
+struct Item {
+  int cnt, var, nt;
+  int n[2], y0[2], x0[2];
+};
+__device__ __forceinline__ void decode_tile(const KParams& p, int s, int& n, int& y0, int& x0) {
+  const int tx = s % p.tiles_x;
+  const int r = s / p.tiles_x;
+  x0 = tx * TILE_W;
+  y0 = (r % p.tiles_y) * TILE_H;
+  n = r / p.tiles_y;
+}
+__device__ __forceinline__ Item decode_item(const KParams& p, int u, int u_end) {
+  Item it;
+  const int g = u / p.n_spatial, s = u - g * p.n_spatial;
+  it.nt = g % p.n_ntiles;
+  it.var = g / p.n_ntiles;
+  it.cnt = (p.pair == 2 && u + 1 < u_end && s + 1 < p.n_spatial) ? 2 : 1;
+  decode_tile(p, s, it.n[0], it.y0[0], it.x0[0]);
+  decode_tile(p, it.cnt == 2 ? s + 1 : s, it.n[1], it.y0[1], it.x0[1]);
+  return it;
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -145,16 +165,19 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
   volatile uint32_t* tmem_ptr_s =
       reinterpret_cast<volatile uint32_t*>(smem_gen + p.smem_misc_off + MISC_TMEM_PTR);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: provably warp-uniform, so ptxas keeps the role loops (which only
+  // depend on blockIdx and kernel parameters) on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int total = p.n_img * p.tiles_y * p.tiles_x * p.n_var * p.n_ntiles;
-  const int acc_stride = p.n_tile <= 128 ? 128 : 256;   // TMEM columns between the two buffers
+  // this CTA's contiguous, balanced range of tiles
+  const int u_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * p.n_tiles_total / gridDim.x);
+  const int u_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * p.n_tiles_total / gridDim.x);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     tma_prefetch_desc(&p.tmO);
-    for (int i = 0; i < NUM_STREAMS * MAX_STAGES; ++i) {
+    for (int i = 0; i < MAX_STAGES; ++i) {
       mbar_init(sMisc + MISC_A_FULL + 8 * i, 1);
       mbar_init(sMisc + MISC_A_EMPTY + 8 * i, 1);
       mbar_init(sMisc + MISC_B_FULL + 8 * i, 1);
@@ -172,49 +195,50 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     tmem_alloc(sMisc + MISC_TMEM_PTR, TMEM_COLS);
     tmem_relinquish();
   }
+  if (p.gdn && threadIdx.x >= 128) {       // the single n-tile's bias / beta' stay in smem for the whole kernel
+    float* bs = reinterpret_cast<float*>(smem_gen + p.smem_misc_off + MISC_BIAS);
+    float* be = reinterpret_cast<float*>(smem_gen + p.smem_misc_off + MISC_BETA);
+    const int i = threadIdx.x - 128;
+    if (i < 128) bs[i] = p.bias[i];
+    else be[i - 128] = p.beta[i - 128];
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
   // Role loops are WARP-UNIFORM (all 32 lanes walk them, barrier waits included) and only the
-  // issue instructions sit under elect_one(): tcgen05.mma / TMA are uniform-datapath instructions,
-  // and inside a divergent `if (lane == 0)` region ptxas wraps each of them in an ELECT/BRA.U.ANY
-  // waterfall loop (measured: ~320 cycles per 128x128x16 MMA instead of 64).
-  // stream s owns tiles it = s, s+2, ... of this CTA's sequence, accumulator buffer s, and its own rings
-  const int sid = (warp >= 8 && warp < 12) ? 1 : 0;
-  const int role = warp - 8 * sid;            // 0: A producer, 1: B producer, 2: MMA (warps 3..7 handled below)
-  const uint32_t sAs = sA + sid * p.a_stages * p.a_stage_bytes;
-  const uint32_t sBs = sB + sid * p.b_stages * p.b_stage_bytes;
-  const uint32_t bar_off = sid * MAX_STAGES * 8;
-  const int w_first = blockIdx.x + sid * gridDim.x, w_step = NUM_STREAMS * gridDim.x;
-  if ((warp < 3 || (warp >= 8 && warp < 11)) && role == 0) {
+  // issue instructions sit under elect_one(): tcgen05.mma / TMA are uniform-datapath instructions.
+  if (warp == 0) {
     // ===================== A producer: activation strips =====================
     uint32_t st = 0, ph = 0;
-    const uint32_t n_st = p.a_stages, st_bytes = p.a_stage_bytes;
-    for (int w = w_first; w < total; w += w_step) {
-      const Work wk = decode_work(p, w);
-      const int x0 = wk.tx * TILE_W, y0 = wk.ty * TILE_H;
-      const int i0 = p.var[wk.var].aops_off, i1 = i0 + p.var[wk.var].n_aops;
+    const uint32_t n_st = p.a_stages, strip_bytes = p.strip_bytes, st_bytes = p.pair * p.strip_bytes;
+    for (int u = u_begin; u < u_end;) {
+      const Item it = decode_item(p, u, u_end);
+      u += it.cnt;
+      const int i0 = p.var[it.var].strip_off, i1 = i0 + p.var[it.var].n_strips;
       for (int i = i0; i < i1; ++i) {
-        const AOp op = p.aops[i];
-        const uint32_t full = sMisc + MISC_A_FULL + bar_off + 8 * st;
-        mbar_wait(sMisc + MISC_A_EMPTY + bar_off + 8 * st, ph ^ 1);
+        const Strip sp = p.strips[i];
+        const uint32_t full = sMisc + MISC_A_FULL + 8 * st;
+        mbar_wait(sMisc + MISC_A_EMPTY + 8 * st, ph ^ 1);
         if (elect_one()) {
           if (p.debug & 1) {
             mbar_arrive(full);
           } else {
-            mbar_expect_tx(full, st_bytes);
-            tma_load_5d(sAs + st * st_bytes, &p.tmA, full, op.c0, x0 + op.dx, op.p2, y0 + op.dy, wk.n);
+            mbar_expect_tx(full, it.cnt * strip_bytes);
+            tma_load_5d(sA + st * st_bytes, &p.tmA, full, sp.c0, it.x0[0] + sp.dx, sp.p2, it.y0[0] + sp.dy, it.n[0]);
+            if (it.cnt == 2)
+              tma_load_5d(sA + st * st_bytes + strip_bytes, &p.tmA, full, sp.c0, it.x0[1] + sp.dx, sp.p2,
+                          it.y0[1] + sp.dy, it.n[1]);
           }
         }
         __syncwarp();
         if (++st == n_st) { st = 0; ph ^= 1; }
       }
     }
-  } else if ((warp < 3 || (warp >= 8 && warp < 11)) && role == 1) {
+  } else if (warp == 1) {
     // ===================== B producer: weight k-blocks (+ gamma once) =====================
-    if (p.gdn && sid == 0 && elect_one()) {
+    if (p.gdn && elect_one()) {
       tma_prefetch_desc(&p.tmG);
       mbar_expect_tx(sMisc + MISC_G_FULL, 2 * STAGE_BLK_BYTES);
       tma_load_2d(sG, &p.tmG, sMisc + MISC_G_FULL, 0, 0);
@@ -223,247 +247,301 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     __syncwarp();
     uint32_t st = 0, ph = 0;
     const uint32_t n_st = p.b_stages, st_bytes = p.b_stage_bytes;
-    for (int w = w_first; w < total; w += w_step) {
-      const Work wk = decode_work(p, w);
-      const int nrow = wk.nt * p.n_tile;
-      const int i0 = p.var[wk.var].bops_off, i1 = i0 + p.var[wk.var].n_bops;
+    for (int u = u_begin; u < u_end;) {
+      const Item it = decode_item(p, u, u_end);
+      u += it.cnt;
+      const int nrow = it.nt * p.n_tile;
+      const int i0 = p.var[it.var].bop_off, i1 = i0 + p.var[it.var].n_bops;
       for (int i = i0; i < i1; ++i) {
-        const BOp op = p.bops[i];
-        const uint32_t full = sMisc + MISC_B_FULL + bar_off + 8 * st;
-        mbar_wait(sMisc + MISC_B_EMPTY + bar_off + 8 * st, ph ^ 1);
+        const int row0 = p.bops[i];
+        const uint32_t full = sMisc + MISC_B_FULL + 8 * st;
+        mbar_wait(sMisc + MISC_B_EMPTY + 8 * st, ph ^ 1);
         if (elect_one()) {
           if (p.debug & 2) {
             mbar_arrive(full);
           } else {
             mbar_expect_tx(full, st_bytes);
-            tma_load_2d(sBs + st * st_bytes, &p.tmB, full, 0, op.row0 + nrow);
+            tma_load_2d(sB + st * st_bytes, &p.tmB, full, 0, row0 + nrow);
           }
         }
         __syncwarp();
         if (++st == n_st) { st = 0; ph ^= 1; }
       }
     }
-  } else if ((warp < 3 || (warp >= 8 && warp < 11)) && role == 2) {
+  } else if (warp == 2) {
     // ===================== MMA issuer =====================
     const uint32_t n_sa = p.a_stages, n_sb = p.b_stages;
-    uint32_t sa = n_sa - 1, pa = 1, sb = n_sb - 1, pb = 1;    // first advance lands on stage 0, phase 0
-    int it = sid;
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
     // descriptor = constant high part | (smem address >> 4); +2 per K=16 step, +64 per strip row
-    const uint64_t descA0 = umma_desc_sw128(sAs), descB0 = umma_desc_sw128(sBs);
-    const uint32_t a_step = p.a_stage_bytes >> 4, b_step = p.b_stage_bytes >> 4;
+    const uint64_t descA0 = umma_desc_sw128(sA), descB0 = umma_desc_sw128(sB);
+    const uint32_t a_step = (p.pair * p.strip_bytes) >> 4, b_step = p.b_stage_bytes >> 4;
+    const uint32_t t1_off = p.strip_bytes >> 4;           // second tile of a pair inside an A stage
     const uint32_t idesc = p.idesc;
-    for (int w = w_first; w < total; w += w_step, it += NUM_STREAMS) {
-      const Work wk = decode_work(p, w);
-      const int buf = sid;                      // == it & 1
-      if (lane == 0) TRACE(it, 0);
-      mbar_wait(sMisc + MISC_ACC_EMPTY + 8 * buf, ((it >> 1) & 1) ^ 1);
-      if (lane == 0) TRACE(it, 1);
+    const uint32_t slot_cols = 128;                        // pair mode: tile t of buffer b at column b*256 + t*128
+    int n_item = 0;
+    for (int u = u_begin; u < u_end; ++n_item) {
+      const Item it = decode_item(p, u, u_end);
+      u += it.cnt;
+      const int buf = n_item & 1;
+      mbar_wait(sMisc + MISC_ACC_EMPTY + 8 * buf, ((n_item >> 1) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + buf * acc_stride;
-      const int i0 = p.var[wk.var].mops_off, i1 = i0 + p.var[wk.var].n_mops;
+      const uint32_t d0 = tmem_base + buf * 256;
+      const uint32_t d1 = d0 + slot_cols;
+      const bool two = it.cnt == 2;
+      uint32_t acc = 0;                                    // 0 for the first MMA group of the item
+      const int i0 = p.var[it.var].strip_off, i1 = i0 + p.var[it.var].n_strips;
       for (int i = i0; i < i1; ++i) {
-        const MOp op = p.mops[i];
-#define TRACE_OP(slot) do { if (p.trace && blockIdx.x == 0 && it == 4 && (i - i0) < 32 && lane == 0) p.trace[(32 + i - i0) * 16 + (slot)] = clock64(); } while (0)
-        TRACE_OP(0);
-        if (op.flags & M_NEW_A) {
-          if (++sa == n_sa) { sa = 0; pa ^= 1; }
-          mbar_wait(sMisc + MISC_A_FULL + bar_off + 8 * sa, pa);
-        }
-        if (op.flags & M_NEW_B) {
+        const Strip sp = p.strips[i];
+        const uint32_t nk = sp.nk & 15u, k0 = sp.nk >> 4;
+        mbar_wait(sMisc + MISC_A_FULL + 8 * sa, pa);
+        uint64_t adesc = descA0 + (sa * a_step + static_cast<uint32_t>(sp.a_row0) * 64u + 2u * k0);
+        const int64_t a_inc = static_cast<int64_t>(sp.a_step) * 64;
+        const int n_taps = sp.n_taps;
+        for (int j = 0; j < n_taps; ++j) {
+          mbar_wait(sMisc + MISC_B_FULL + 8 * sb, pb);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t bdesc = descB0 + (sb * b_step + 2u * k0);
+            if (nk == 4) {
+              umma_bf16(d0, adesc, bdesc, idesc, acc);
+              umma_bf16(d0, adesc + 2, bdesc + 2, idesc, 1u);
+              umma_bf16(d0, adesc + 4, bdesc + 4, idesc, 1u);
+              umma_bf16(d0, adesc + 6, bdesc + 6, idesc, 1u);
+              if (two) {
+                const uint64_t a1 = adesc + t1_off;
+                umma_bf16(d1, a1, bdesc, idesc, acc);
+                umma_bf16(d1, a1 + 2, bdesc + 2, idesc, 1u);
+                umma_bf16(d1, a1 + 4, bdesc + 4, idesc, 1u);
+                umma_bf16(d1, a1 + 6, bdesc + 6, idesc, 1u);
+              }
+            } else {
+              for (uint32_t k = 0; k < nk; ++k) umma_bf16(d0, adesc + 2 * k, bdesc + 2 * k, idesc, k ? 1u : acc);
+              if (two)
+                for (uint32_t k = 0; k < nk; ++k)
+                  umma_bf16(d1, adesc + t1_off + 2 * k, bdesc + 2 * k, idesc, k ? 1u : acc);
+            }
+            umma_commit(sMisc + MISC_B_EMPTY + 8 * sb);
+            if (j + 1 == n_taps) {
+              umma_commit(sMisc + MISC_A_EMPTY + 8 * sa);
+              if (i + 1 == i1) umma_commit(sMisc + MISC_ACC_FULL + 8 * buf);
+            }
+          }
+          __syncwarp();
+          acc = 1u;
+          adesc += a_inc;
           if (++sb == n_sb) { sb = 0; pb ^= 1; }
-          mbar_wait(sMisc + MISC_B_FULL + bar_off + 8 * sb, pb);
         }
-        TRACE_OP(1);
-        tc_fence_after();
-        TRACE_OP(2);
-        if (elect_one()) {
-          const uint32_t nk = op.nk & 15u, k0 = op.nk >> 4;                      // +32 B (= 2) per K=16 step
-          const uint64_t adesc = descA0 + (sa * a_step + op.a_row * 64u + 2u * k0);
-          const uint64_t bdesc = descB0 + (sb * b_step + 2u * k0);
-          umma_bf16(d_tmem, adesc, bdesc, idesc, (op.flags & M_FIRST) ? 0u : 1u);
-          if (nk > 1) umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-          if (nk > 2) umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-          if (nk > 3) umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
-          if (op.flags & M_REL_A) umma_commit(sMisc + MISC_A_EMPTY + bar_off + 8 * sa);
-          if (op.flags & M_REL_B) umma_commit(sMisc + MISC_B_EMPTY + bar_off + 8 * sb);
-          if (i + 1 == i1) umma_commit(sMisc + MISC_ACC_FULL + 8 * buf);
-        }
-        TRACE_OP(3);
-        __syncwarp();
-        TRACE_OP(4);
+        if (++sa == n_sa) { sa = 0; pa ^= 1; }
       }
-      if (lane == 0) TRACE(it, 2);
     }
-  } else if ((warp >= 4 && warp < 8) || warp >= 12) {
+  } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> regs -> smem -> TMA store =====================
-    // Two groups of 4 warps; group g owns staging buffer g and the channel blocks j = g, g+2, ...
-    // (with GDN: the 64 channels [64g, 64g+64)).  Bias/beta are read through L1 (uniform addresses).
-    const int grp = warp >= 12 ? 1 : 0;
+    // Two groups of 4 warps.  GDN: group g owns channels [64g, 64g+64) and staging block g (the pair of
+    // blocks is the A2 operand of the norm MMA).  Otherwise group g owns the channel blocks j = g, g+2, ...
+    // and two staging blocks, so a block's TMA store drains behind the next block.
+    const int grp = warp >= 8 ? 1 : 0;
     const int ew = warp & 3;            // the TMEM lane quarter this warp may read
     const int t = ew * 32 + lane;       // accumulator row = tile position
     const uint32_t lane_sel = static_cast<uint32_t>(ew * 32) << 16;
     const uint32_t gbar = 1 + grp;      // named barrier of this group (128 threads); barrier 3 = both groups
     const bool leader = (t == 0);       // issues this group's TMA stores (bulk groups are per thread)
     const int nblk = p.n_tile / p.blk_ch;
-    const int chunks_per_blk = p.blk_ch / 16;
-    // staging: with GDN one 16 KB buffer per group (together they are the 32 KB A2 operand of the norm MMA);
-    // without GDN (no gamma resident) two buffers per group, so a block's TMA store drains behind the next block
-    const uint32_t sbuf = sStage + grp * p.stage_per_group * STAGE_BLK_BYTES;
-    uint32_t flip = 0;
+    const uint32_t sbuf = sStage + grp * (p.gdn ? 1 : 2) * STAGE_BLK_BYTES;
+    const uint32_t bias_s = sMisc + MISC_BIAS, beta_s = sMisc + MISC_BETA;
+    uint32_t flip = 0, gdn_par = 0;
     const float* __restrict__ bias_g = p.bias;
-    int it = 0;
+    const bool fwd = (p.gdn == MASIC_GDN_FWD);
+    const bool nostore = (p.debug & 4) != 0;
+    int n_item = 0;
     if (p.gdn && grp == 0 && ew == 0) mbar_wait(sMisc + MISC_G_FULL, 0);
-    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-      const Work wk = decode_work(p, w);
-      const Variant& v = p.var[wk.var];
-      const int buf = it & 1;
-      const int act = p.act[wk.nt];
-      const uint32_t acc_addr = tmem_base + lane_sel + buf * acc_stride;
-      const float* __restrict__ bias_t = bias_g ? bias_g + wk.nt * p.n_tile : nullptr;
-      if (t == 0 && grp == 0) TRACE(it, 4);
-      float rs = 1.0f;
-      if (p.rowscale) {
-        const int y = wk.ty * TILE_H + (t >> 3), x = wk.tx * TILE_W + (t & 7);
-        if (y < p.rs_H && x < p.rs_W)
-          rs = p.rowscale[(static_cast<size_t>(wk.n * p.rs_H + y) * p.rs_W + x) * p.rs_stride + p.rs_off];
-      }
-      if (t == 0 && grp == 0) TRACE(it, 5);
-      mbar_wait(sMisc + MISC_ACC_FULL + 8 * buf, (it >> 1) & 1);
+    for (int u = u_begin; u < u_end; ++n_item) {
+      const Item it = decode_item(p, u, u_end);
+      u += it.cnt;
+      const Variant& v = p.var[it.var];
+      const int buf = n_item & 1;
+      const float slope = p.slope[it.nt];
+      const float* __restrict__ bias_t = bias_g ? bias_g + it.nt * p.n_tile : nullptr;
+      mbar_wait(sMisc + MISC_ACC_FULL + 8 * buf, (n_item >> 1) & 1);
       tc_fence_after();
-      if (t == 0 && grp == 0) TRACE(it, 6);
-
-      if (p.gdn) {
-        // ---- pass 1: A2[:, 64g .. 64g+64) = bf16((acc + bias)^2), K-major SWIZZLE_128B block g
-        if (leader) tma_store_wait_read<0>();          // staging buffer g (== A2 block g) free again
-        named_bar_sync(gbar, 128);
-        const uint32_t arow = sbuf + t * 128;
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const int c = grp * 64 + cc * 16;
-          uint32_t r[16];
-          tmem_ld16(acc_addr + c, r);
+      for (int tt = 0; tt < it.cnt; ++tt) {
+        const uint32_t acc_addr = tmem_base + lane_sel + buf * 256 + tt * 128;
+        const bool last_tile = (tt + 1 == it.cnt);
+        float rs = 1.0f;
+        if (p.rowscale) {
+          const int y = it.y0[tt] + (t >> 3), x = it.x0[tt] + (t & 7);
+          if (y < p.rs_H && x < p.rs_W)
+            rs = __ldg(p.rowscale + (static_cast<size_t>(it.n[tt] * p.rs_H + y) * p.rs_W + x) * p.rs_stride + p.rs_off);
+        }
+        if (p.gdn) {
+          // ---- pass 1: x = acc + bias stays in registers; A2[:, 64g .. 64g+64) = bf16(x^2), SWIZZLE_128B block g
+          const int cb = grp * 64;
+          uint32_t r[64];
+          tmem_ld16(acc_addr + cb, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+          tmem_ld16(acc_addr + cb + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+          tmem_ld16(acc_addr + cb + 32, *reinterpret_cast<uint32_t(*)[16]>(&r[32]));
+          tmem_ld16(acc_addr + cb + 48, *reinterpret_cast<uint32_t(*)[16]>(&r[48]));
+          if (leader) tma_store_wait_read<0>();          // staging block g (== A2 block g) free again
           tmem_ld_wait();
-          uint32_t q[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float x0 = __uint_as_float(r[2 * i]) + __ldg(bias_t + c + 2 * i);
-            const float x1 = __uint_as_float(r[2 * i + 1]) + __ldg(bias_t + c + 2 * i + 1);
-            q[i] = pack_bf16x2(x0 * x0, x1 * x1);
-          }
-          st_shared_v4(arow + (((2 * cc) ^ (t & 7)) << 4), q[0], q[1], q[2], q[3]);
-          st_shared_v4(arow + (((2 * cc + 1) ^ (t & 7)) << 4), q[4], q[5], q[6], q[7]);
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        named_bar_sync(3, EPI_THREADS);
-        if (t == 0 && grp == 0) TRACE(it, 7);
-        if (grp == 0 && ew == 0) {                      // warp-uniform; one elected lane issues the 8 MMAs
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t d2 = tmem_base + 2 * acc_stride;
-            const uint64_t dh = umma_desc_sw128(0);
-#pragma unroll
-            for (int kb = 0; kb < 2; ++kb) {
-              const uint64_t a2 = dh | (((sStage + kb * STAGE_BLK_BYTES) & 0x3FFFFu) >> 4);
-              const uint64_t g2 = dh | (((sG + kb * STAGE_BLK_BYTES) & 0x3FFFFu) >> 4);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(d2, a2 + 2 * k, g2 + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
-            }
-            umma_commit(sMisc + MISC_GDN_BAR);
-          }
-          __syncwarp();
-        }
-        mbar_wait(sMisc + MISC_GDN_BAR, it & 1);
-        tc_fence_after();
-        if (t == 0 && grp == 0) TRACE(it, 8);
-        // ---- pass 2: out[:, 64g .. 64g+64) = x * rsqrt(beta + norm)  (IGDN: x * sqrt(.))
-        const uint32_t norm_addr = tmem_base + lane_sel + 2 * acc_stride;
-        const float* __restrict__ beta_g = p.beta;
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const int c = grp * 64 + cc * 16;
-          uint32_t r[16], g[16];
-          tmem_ld16(acc_addr + c, r);
-          tmem_ld16(norm_addr + c, g);
-          tmem_ld_wait();
-          float o[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float x = __uint_as_float(r[i]) + __ldg(bias_t + c + i);
-            const float nrm = __uint_as_float(g[i]) + __ldg(beta_g + c + i);
-            // IGDN: sqrt(n) = n * rsqrt(n) on the MUFU fast path (2-ulp rsqrt is far below bf16 rounding)
-            const float rs_n = rsqrtf(nrm);
-            o[i] = ((p.gdn == MASIC_GDN_FWD) ? x * rs_n : x * (nrm * rs_n)) * rs;
-          }
-          st_shared_v4(arow + (((2 * cc) ^ (t & 7)) << 4), pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                       pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-          st_shared_v4(arow + (((2 * cc + 1) ^ (t & 7)) << 4), pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]),
-                       pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
-        }
-        tc_fence_before();
-        mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * buf);
-        fence_proxy_async_smem();
-        named_bar_sync(gbar, 128);
-        if (leader && !(p.debug & 4)) {
-          tma_store_5d(&p.tmO, sbuf, p.out_coff + v.out_c0 + wk.nt * p.n_tile + grp * 64, wk.tx * TILE_W, v.out_p2,
-                       wk.ty * TILE_H, wk.n);
-          tma_store_commit();
-        }
-      } else {
-        // ---- plain epilogue: bias, activation, per-pixel scale; this group's blocks j = grp, grp+2, ...
-        for (int j = grp; j < nblk; j += 2) {
-          const uint32_t sb2 = sbuf + flip * STAGE_BLK_BYTES;
-          if (p.stage_per_group == 2) {
-            flip ^= 1;
-            if (leader) tma_store_wait_read<1>();      // the store issued two blocks ago has left this buffer
-          } else if (leader) {
-            tma_store_wait_read<0>();
-          }
           named_bar_sync(gbar, 128);
-          const uint32_t row = sb2 + t * p.blk_pitch;
-          const int sw = (p.blk_pitch == 128) ? (t & 7) : 0;
-          for (int cc = 0; cc < chunks_per_blk; ++cc) {
-            const int c = j * p.blk_ch + cc * 16;
-            uint32_t r[16];
-            float o[16];
-            tmem_ld16(acc_addr + c, r);
-            tmem_ld_wait();
+          const uint32_t arow = sbuf + t * 128;
+          float x[64];
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              o[i] = apply_act(__uint_as_float(r[i]) + (bias_t ? __ldg(bias_t + c + i) : 0.0f), act) * rs;
-            if (p.out_fp32) {
-              const int ch0 = cc * 4;
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                st_shared_v4(row + (((ch0 + i) ^ sw) << 4), __float_as_uint(o[4 * i]), __float_as_uint(o[4 * i + 1]),
-                             __float_as_uint(o[4 * i + 2]), __float_as_uint(o[4 * i + 3]));
-            } else {
-              const int ch0 = cc * 2;
-#pragma unroll
-              for (int i = 0; i < 2; ++i)
-                st_shared_v4(row + (((ch0 + i) ^ sw) << 4), pack_bf16x2(o[8 * i], o[8 * i + 1]),
-                             pack_bf16x2(o[8 * i + 2], o[8 * i + 3]), pack_bf16x2(o[8 * i + 4], o[8 * i + 5]),
-                             pack_bf16x2(o[8 * i + 6], o[8 * i + 7]));
-            }
+          for (int q = 0; q < 16; ++q) {
+            const float4 b4 = ld_shared_f4(bias_s + (cb + 4 * q) * 4);
+            x[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b4.x;
+            x[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
+            x[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z;
+            x[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
           }
-          if (j + 2 >= nblk) {      // this group's last TMEM read of the accumulator
-            tc_fence_before();
-            mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * buf);
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            const float* xx = &x[8 * c8];
+            st_shared_v4(arow + ((c8 ^ (t & 7)) << 4), pack_bf16x2(xx[0] * xx[0], xx[1] * xx[1]),
+                         pack_bf16x2(xx[2] * xx[2], xx[3] * xx[3]), pack_bf16x2(xx[4] * xx[4], xx[5] * xx[5]),
+                         pack_bf16x2(xx[6] * xx[6], xx[7] * xx[7]));
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          named_bar_sync(3, EPI_THREADS);
+          if (grp == 0 && ew == 0) {                      // warp-uniform; one elected lane issues the 8 MMAs
+            tc_fence_after();
+            if (elect_one()) {
+              // norm = x^2 * gamma'^T written IN PLACE over the accumulator (every thread holds its x in registers)
+              const uint32_t d2 = tmem_base + buf * 256 + tt * 128;
+              const uint64_t dh = umma_desc_sw128(0);
+#pragma unroll
+              for (int kb = 0; kb < 2; ++kb) {
+                const uint64_t a2 = dh | (((sStage + kb * STAGE_BLK_BYTES) & 0x3FFFFu) >> 4);
+                const uint64_t g2 = dh | (((sG + kb * STAGE_BLK_BYTES) & 0x3FFFFu) >> 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(d2, a2 + 2 * k, g2 + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
+              }
+              umma_commit(sMisc + MISC_GDN_BAR);
+            }
+            __syncwarp();
+          }
+          mbar_wait(sMisc + MISC_GDN_BAR, gdn_par);
+          gdn_par ^= 1;
+          tc_fence_after();
+          // ---- pass 2: out[:, 64g .. 64g+64) = x * rsqrt(beta + norm)  (IGDN: x * sqrt(.))
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {                 // two halves of 32 channels: bounds the live registers
+            tmem_ld16(acc_addr + cb + 32 * h, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+            tmem_ld16(acc_addr + cb + 32 * h + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+            tmem_ld_wait();
+            if (h == 1 && last_tile) {                  // last TMEM read of this item's accumulators
+              tc_fence_before();
+              mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * buf);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 e4 = ld_shared_f4(beta_s + (cb + 32 * h + 4 * q) * 4);
+              const float ee[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float nrm = __uint_as_float(r[4 * q + e]) + ee[e];
+                // IGDN: sqrt(n) = n * rsqrt(n) on the MUFU fast path (2-ulp rsqrt is far below bf16 rounding)
+                const float rn = rsqrtf(nrm);
+                const float xv = x[32 * h + 4 * q + e];
+                x[32 * h + 4 * q + e] = (fwd ? xv * rn : xv * (nrm * rn)) * rs;
+              }
+            }
+#pragma unroll
+            for (int c8 = 4 * h; c8 < 4 * h + 4; ++c8) {
+              const float* xx = &x[8 * c8];
+              st_shared_v4(arow + ((c8 ^ (t & 7)) << 4), pack_bf16x2(xx[0], xx[1]), pack_bf16x2(xx[2], xx[3]),
+                           pack_bf16x2(xx[4], xx[5]), pack_bf16x2(xx[6], xx[7]));
+            }
           }
           fence_proxy_async_smem();
           named_bar_sync(gbar, 128);
-          if (leader && !(p.debug & 4)) {
-            tma_store_5d(&p.tmO, sb2, p.out_coff + v.out_c0 + wk.nt * p.n_tile + j * p.blk_ch, wk.tx * TILE_W,
-                         v.out_p2, wk.ty * TILE_H, wk.n);
+          if (leader && !nostore) {
+            tma_store_5d(&p.tmO, sbuf, p.out_coff + v.out_c0 + it.nt * p.n_tile + cb, it.x0[tt], v.out_p2, it.y0[tt],
+                         it.n[tt]);
             tma_store_commit();
           }
-        }
-        if (grp >= nblk) {          // nothing to do for this group (single-block tile): just release the accumulator
-          tc_fence_before();
-          mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * buf);
+        } else {
+          // ---- plain epilogue: bias, activation, per-pixel scale; this group's blocks j = grp, grp+2, ...
+          const int sw = (p.blk_pitch == 128) ? (t & 7) : 0;
+          for (int j = grp; j < nblk; j += 2) {
+            const uint32_t sb2 = sbuf + flip * STAGE_BLK_BYTES;
+            flip ^= 1;
+            const int c = j * p.blk_ch;
+            const uint32_t row = sb2 + t * p.blk_pitch;
+            const bool last_read = last_tile && (j + 2 >= nblk);
+            if (p.out_fp32) {
+              // 32 fp32 channels per 128-B row (16 when the whole tile is narrower)
+              uint32_t r[32];
+              tmem_ld16(acc_addr + c, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+              if (p.blk_ch == 32) tmem_ld16(acc_addr + c + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+              if (leader) tma_store_wait_read<1>();      // the store issued two blocks ago has left this buffer
+              tmem_ld_wait();
+              if (last_read) { tc_fence_before(); mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * buf); }
+              named_bar_sync(gbar, 128);
+              const int nq = p.blk_ch / 4;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                if (q < nq) {
+                  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (bias_t) b4 = __ldg(reinterpret_cast<const float4*>(bias_t + c) + q);
+                  const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                  float o[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float xv = __uint_as_float(r[4 * q + e]) + bb[e];
+                    o[e] = fmaf(slope, fminf(xv, 0.0f), fmaxf(xv, 0.0f)) * rs;
+                  }
+                  st_shared_v4(row + ((q ^ sw) << 4), __float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]),
+                               __float_as_uint(o[3]));
+                }
+              }
+            } else {
+              // 64 bf16 channels per 128-B row (fewer when the whole tile is narrower)
+              uint32_t r[64];
+              const int nch = p.blk_ch / 16;
+              tmem_ld16(acc_addr + c, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+              if (nch > 1) tmem_ld16(acc_addr + c + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+              if (nch > 2) tmem_ld16(acc_addr + c + 32, *reinterpret_cast<uint32_t(*)[16]>(&r[32]));
+              if (nch > 3) tmem_ld16(acc_addr + c + 48, *reinterpret_cast<uint32_t(*)[16]>(&r[48]));
+              if (leader) tma_store_wait_read<1>();
+              tmem_ld_wait();
+              if (last_read) { tc_fence_before(); mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * buf); }
+              named_bar_sync(gbar, 128);
+              const int n8 = p.blk_ch / 8;
+#pragma unroll
+              for (int c8 = 0; c8 < 8; ++c8) {
+                if (c8 < n8) {
+                  float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                  if (bias_t) {
+                    b0 = __ldg(reinterpret_cast<const float4*>(bias_t + c) + 2 * c8);
+                    b1 = __ldg(reinterpret_cast<const float4*>(bias_t + c) + 2 * c8 + 1);
+                  }
+                  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                  float o[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const float xv = __uint_as_float(r[8 * c8 + e]) + bb[e];
+                    o[e] = fmaf(slope, fminf(xv, 0.0f), fmaxf(xv, 0.0f)) * rs;
+                  }
+                  st_shared_v4(row + ((c8 ^ sw) << 4), pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                               pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+                }
+              }
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(gbar, 128);
+            if (leader && !nostore) {
+              tma_store_5d(&p.tmO, sb2, p.out_coff + v.out_c0 + it.nt * p.n_tile + c, it.x0[tt], v.out_p2, it.y0[tt],
+                           it.n[tt]);
+              tma_store_commit();
+            }
+          }
+          if (last_tile && grp >= nblk) {   // nothing to do for this group (single-block tile): just release
+            tc_fence_before();
+            mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * buf);
+          }
         }
       }
-      if (t == 0 && grp == 0) TRACE(it, 9);
     }
     if (leader) tma_store_wait_all<0>();
   }
@@ -569,7 +647,6 @@ using namespace masic;
 struct MasicConvPlan {
   KParams kp;
   void* d_tables = nullptr;
-  void* d_trace = nullptr;
   int smem_bytes = 0;
   int grid = 0;
   int total_work = 0;
@@ -581,54 +658,48 @@ namespace {
 struct TapList {   // live taps of one strip: (a_row, kb_tap_index)
   std::vector<std::pair<int, int>> taps;
 };
+struct StripSpec { int c0, dx, p2, dy; TapList tl; int nk; };   // nk: packed (first step << 4 | steps), 0 = per k-block default
 
 inline int floordiv2(int t) { return t >= 0 ? t / 2 : -((-t + 1) / 2); }
 
 // Build the per-variant programs.  Returns the strip height (rows) via *rows_out.
-int build_programs(const MasicConvDesc& d, std::vector<AOp>& aops, std::vector<BOp>& bops,
-                   std::vector<MOp>& mops, Variant* var, int* n_var, int* rows_out) {
+int build_programs(const MasicConvDesc& d, std::vector<Strip>& strips_out, std::vector<int32_t>& bops,
+                   Variant* var, int* n_var, int* rows_out) {
   const int k = d.ksize, ncb = (d.c_in + KBLK - 1) / KBLK;
   const uint32_t mask = d.tap_mask ? d.tap_mask : 0xFFFFFFFFu;
   const int nk_last = (d.c_in - (ncb - 1) * KBLK) / 16;
   int rows = TILE_H;
   *n_var = 0;
 
-  auto emit_variant = [&](const std::vector<std::pair<AOp, TapList>>& strips_cb0, int out_p2,
-                          int out_c0) -> int {
+  // one variant = for every 64-channel block, every strip with its taps (a_row must be an arithmetic sequence)
+  auto emit_variant = [&](const std::vector<StripSpec>& specs, int n_cblocks, int out_p2, int out_c0) -> int {
+    if (*n_var >= MAX_VARIANTS) return MASIC_ENOSUP;
     Variant& v = var[*n_var];
-    v.aops_off = (int)aops.size();
-    v.bops_off = (int)bops.size();
-    v.mops_off = (int)mops.size();
+    v.strip_off = (int)strips_out.size();
+    v.bop_off = (int)bops.size();
     v.out_p2 = out_p2;
     v.out_c0 = out_c0;
-    bool first = true;
-    for (int cb = 0; cb < ncb; ++cb) {
-      const int nk = (cb == ncb - 1) ? nk_last : 4;
-      for (const auto& st : strips_cb0) {
-        if (st.second.taps.empty()) continue;
-        AOp a = st.first;
-        a.c0 = (int16_t)(a.c0 + cb * KBLK);
-        aops.push_back(a);
-        for (size_t i = 0; i < st.second.taps.size(); ++i) {
-          BOp b;
-          b.row0 = (st.second.taps[i].second * ncb + cb) * d.c_out_pad;
-          bops.push_back(b);
-          MOp m;
-          m.a_row = (uint16_t)st.second.taps[i].first;
-          m.nk = (uint8_t)nk;
-          m.flags = M_NEW_B | M_REL_B;
-          if (i == 0) m.flags |= M_NEW_A;
-          if (i + 1 == st.second.taps.size()) m.flags |= M_REL_A;
-          if (first) m.flags |= M_FIRST;
-          first = false;
-          mops.push_back(m);
+    for (int cb = 0; cb < n_cblocks; ++cb) {
+      const int nk_def = (cb == n_cblocks - 1) ? nk_last : 4;
+      for (const auto& st : specs) {
+        const auto& taps = st.tl.taps;
+        if (taps.empty()) continue;
+        Strip s;
+        s.c0 = (int16_t)(st.c0 + cb * KBLK); s.dx = (int16_t)st.dx; s.p2 = (int16_t)st.p2; s.dy = (int16_t)st.dy;
+        s.n_taps = (uint8_t)taps.size();
+        s.a_row0 = (int8_t)taps[0].first;
+        s.a_step = (int8_t)(taps.size() > 1 ? taps[1].first - taps[0].first : 0);
+        for (size_t i = 0; i < taps.size(); ++i) {
+          if (taps[i].first != s.a_row0 + (int)i * s.a_step) return MASIC_ENOSUP;
+          bops.push_back((taps[i].second * n_cblocks + cb) * d.c_out_pad);
         }
+        s.nk = (uint8_t)(st.nk ? st.nk : nk_def);
+        strips_out.push_back(s);
       }
     }
-    v.n_aops = (int)aops.size() - v.aops_off;
-    v.n_bops = (int)bops.size() - v.bops_off;
-    v.n_mops = (int)mops.size() - v.mops_off;
-    if (v.n_mops == 0) return MASIC_EINVAL;
+    v.n_strips = (int)strips_out.size() - v.strip_off;
+    v.n_bops = (int)bops.size() - v.bop_off;
+    if (v.n_bops == 0) return MASIC_EINVAL;
     ++*n_var;
     return MASIC_OK;
   };
@@ -637,15 +708,14 @@ int build_programs(const MasicConvDesc& d, std::vector<AOp>& aops, std::vector<B
     const int kk = (d.kind == MASIC_DECONV_S2_SUBPIX) ? 3 : k;
     const int stride = (d.kind == MASIC_DECONV_S2_SUBPIX) ? 1 : d.stride;
     const int pad = kk / 2;
-    std::vector<std::pair<AOp, TapList>> strips;
+    std::vector<StripSpec> specs;
     if (stride == 1) {
       rows = TILE_H + kk - 1;
       for (int kx = 0; kx < kk; ++kx) {
-        AOp a; a.c0 = (int16_t)d.in_coff; a.dx = (int16_t)(kx - pad); a.p2 = 0; a.dy = (int16_t)(-pad);
-        TapList tl;
+        StripSpec s{d.in_coff, kx - pad, 0, -pad, {}, 0};
         for (int ky = 0; ky < kk; ++ky)
-          if (mask & (1u << (ky * kk + kx))) tl.taps.push_back({ky, ky * kk + kx});
-        strips.push_back({a, tl});
+          if (mask & (1u << (ky * kk + kx))) s.tl.taps.push_back({ky, ky * kk + kx});
+        specs.push_back(s);
       }
     } else if (stride == 2) {
       // input row = 2*(oy + half) + py with t = ky - pad, half = floor(t/2), py = t - 2*half
@@ -654,76 +724,52 @@ int build_programs(const MasicConvDesc& d, std::vector<AOp>& aops, std::vector<B
       for (int kx = 0; kx < kk; ++kx) {
         const int tx = kx - pad, hx = floordiv2(tx), px = tx - 2 * hx;
         for (int py = 0; py < 2; ++py) {
-          AOp a; a.c0 = (int16_t)(d.in_coff + px * d.in_cpitch); a.dx = (int16_t)hx; a.p2 = (int16_t)py;
-          a.dy = (int16_t)half_min;
-          TapList tl;
+          StripSpec s{d.in_coff + px * d.in_cpitch, hx, py, half_min, {}, 0};
           for (int ky = 0; ky < kk; ++ky) {
             const int ty = ky - pad, hy = floordiv2(ty);
             if (ty - 2 * hy != py) continue;
-            if (mask & (1u << (ky * kk + kx))) tl.taps.push_back({hy - half_min, ky * kk + kx});
+            if (mask & (1u << (ky * kk + kx))) s.tl.taps.push_back({hy - half_min, ky * kk + kx});
           }
-          strips.push_back({a, tl});
+          specs.push_back(s);
         }
       }
     } else {
       return MASIC_EINVAL;
     }
-    int rc = emit_variant(strips, 0, 0);
+    int rc = emit_variant(specs, ncb, 0, 0);
     if (rc) return rc;
   } else if (d.kind == MASIC_CONV_XFOLD4) {
     // Overlapping-window view of a padded 16-channel image (encode_xfold4_view): window hx holds pixels
     // 2*hx-2 .. 2*hx+1 as 64 consecutive bf16.  Taps kx = 0..3 are one K=64 block read at window ox;
-    // tap kx = 4 is K sub-block j=2 of window ox+1.
+    // tap kx = 4 is K sub-block j=2 of window ox+1 (a single K=16 MMA).
     if (k != 5 || d.c_in != 64 || d.in_cpitch != 16 || d.in_coff != 0 || d.stride != 2 || d.tap_mask) return MASIC_EINVAL;
     rows = TILE_H + 2;
-    std::vector<std::pair<AOp, TapList>> strips;
+    std::vector<StripSpec> specs;
     for (int grp = 0; grp < 2; ++grp)
       for (int py = 0; py < 2; ++py) {
-        AOp a; a.c0 = 0; a.dx = (int16_t)(grp ? 1 : 0); a.p2 = (int16_t)py; a.dy = -1;
-        TapList tl;
-        for (int ky = py; ky < 5; ky += 2) tl.taps.push_back({(ky >> 1), ky * 2 + grp});
-        strips.push_back({a, tl});
+        StripSpec s{0, grp ? 1 : 0, py, -1, {}, grp ? (1 | (2 << 4)) : 4};
+        for (int ky = py; ky < 5; ky += 2) s.tl.taps.push_back({(ky >> 1), ky * 2 + grp});
+        specs.push_back(s);
       }
-    // emit by hand: group 1 ops use a single K=16 MMA
-    Variant& v = var[*n_var];
-    v.aops_off = (int)aops.size(); v.bops_off = (int)bops.size(); v.mops_off = (int)mops.size();
-    v.out_p2 = 0; v.out_c0 = 0;
-    bool first = true;
-    for (size_t si = 0; si < strips.size(); ++si) {
-      aops.push_back(strips[si].first);
-      const auto& taps = strips[si].second.taps;
-      for (size_t i = 0; i < taps.size(); ++i) {
-        BOp b; b.row0 = taps[i].second * d.c_out_pad; bops.push_back(b);
-        MOp m; m.a_row = (uint16_t)taps[i].first; m.nk = (uint8_t)(si >= 2 ? (1 | (2 << 4)) : 4);
-        m.flags = M_NEW_B | M_REL_B;
-        if (i == 0) m.flags |= M_NEW_A;
-        if (i + 1 == taps.size()) m.flags |= M_REL_A;
-        if (first) m.flags |= M_FIRST;
-        first = false;
-        mops.push_back(m);
-      }
-    }
-    v.n_aops = (int)aops.size() - v.aops_off; v.n_bops = (int)bops.size() - v.bops_off;
-    v.n_mops = (int)mops.size() - v.mops_off;
-    ++*n_var;
+    int rc = emit_variant(specs, 1, 0, 0);
+    if (rc) return rc;
   } else if (d.kind == MASIC_DECONV_S2) {
     if (k != 5) return MASIC_ENOSUP;
     // out[2q+py] gets taps ky = py, py+2, .. from input row q + dy, dy = 1 - (ky-py)/2
     rows = TILE_H + 2;
     for (int py = 0; py < 2; ++py)
       for (int px = 0; px < 2; ++px) {
-        std::vector<std::pair<AOp, TapList>> strips;
+        std::vector<StripSpec> specs;
         for (int kx = px; kx < 5; kx += 2) {
           const int dx = 1 - (kx - px) / 2;
-          AOp a; a.c0 = (int16_t)d.in_coff; a.dx = (int16_t)dx; a.p2 = 0; a.dy = -1;
-          TapList tl;
+          StripSpec s{d.in_coff, dx, 0, -1, {}, 0};
           for (int ky = py; ky < 5; ky += 2) {
             const int dy = 1 - (ky - py) / 2;
-            if (mask & (1u << (ky * 5 + kx))) tl.taps.push_back({dy + 1, ky * 5 + kx});
+            if (mask & (1u << (ky * 5 + kx))) s.tl.taps.push_back({dy + 1, ky * 5 + kx});
           }
-          strips.push_back({a, tl});
+          specs.push_back(s);
         }
-        int rc = emit_variant(strips, py, px * d.out_cpitch);
+        int rc = emit_variant(specs, ncb, py, px * d.out_cpitch);
         if (rc) return rc;
       }
   } else {
@@ -755,9 +801,9 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   KParams& kp = pl->kp;
   memset(&kp, 0, sizeof(kp));
 
-  std::vector<AOp> aops; std::vector<BOp> bops; std::vector<MOp> mops;
+  std::vector<Strip> strips; std::vector<int32_t> bops;
   int rows = 0;
-  int rc = build_programs(d, aops, bops, mops, kp.var, &kp.n_var, &rows);
+  int rc = build_programs(d, strips, bops, kp.var, &kp.n_var, &rows);
   if (rc) { delete pl; return rc; }
 
   // geometry of the tile grid (output positions for conv, input positions for deconv)
@@ -785,31 +831,31 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   else if (d.n_tile * esz < 128) { kp.blk_ch = d.n_tile; kp.blk_pitch = d.n_tile * esz; }
   else { delete pl; return MASIC_EINVAL; }
 
+  // work items: pairs of tiles sharing every weight k-block when two accumulators fit 256 TMEM columns
+  kp.pair = (d.n_tile <= 128) ? 2 : 1;
+  kp.n_spatial = kp.tiles_x * kp.tiles_y * kp.n_img;
+  kp.n_tiles_total = kp.n_spatial * kp.n_var * kp.n_ntiles;
+
   // shared memory carve-up
-  kp.a_stage_bytes = rows * 1024;
+  kp.strip_bytes = rows * 1024;
   kp.b_stage_bytes = d.n_tile * 128;
-  // staging: with GDN one block per epilogue group (the pair is the A2 operand); otherwise two per group when
-  // the minimum rings (2 A + 2 B stages per stream) still fit, else one
-  int n_stage_blk = d.gdn ? 2 : 4;
-  int fixed = (d.gdn ? 2 * STAGE_BLK_BYTES : 0) + n_stage_blk * STAGE_BLK_BYTES + MISC_BYTES + 1024 /*align*/;
-  int budget = (227 * 1024 - fixed) / NUM_STREAMS;            // ring bytes per stream
+  const int a_stage_bytes = kp.pair * kp.strip_bytes;
+  // staging: with GDN two blocks (together the A2 operand of the norm MMA, then the output tile);
+  // otherwise two per epilogue group so a block's TMA store drains behind the next block
+  const int n_stage_blk = d.gdn ? 2 : 4;
+  const int fixed = (d.gdn ? 2 * STAGE_BLK_BYTES : 0) + n_stage_blk * STAGE_BLK_BYTES + MISC_BYTES + 1024 /*align*/;
+  const int budget = 227 * 1024 - fixed;                      // ring bytes
   int sa = 2, sb = 2;
-  if (n_stage_blk == 4 && sa * kp.a_stage_bytes + sb * kp.b_stage_bytes > budget) {
-    n_stage_blk = 2;
-    fixed -= 2 * STAGE_BLK_BYTES;
-    budget = (227 * 1024 - fixed) / NUM_STREAMS;
-  }
-  kp.stage_per_group = n_stage_blk / 2;
-  if (sa * kp.a_stage_bytes + sb * kp.b_stage_bytes > budget) { delete pl; return MASIC_EINVAL; }
-  // deepen the rings with what is left (B first: a B stage is consumed by a single op)
+  if (sa * a_stage_bytes + sb * kp.b_stage_bytes > budget) { delete pl; return MASIC_EINVAL; }
+  // deepen the rings with what is left (B first: a B stage is consumed by a single tap)
   for (bool grew = true; grew;) {
     grew = false;
-    if (sb < 4 && sa * kp.a_stage_bytes + (sb + 1) * kp.b_stage_bytes <= budget) { ++sb; grew = true; }
-    if (sa < 3 && (sa + 1) * kp.a_stage_bytes + sb * kp.b_stage_bytes <= budget) { ++sa; grew = true; }
+    if (sb < MAX_STAGES && sb < 6 && sa * a_stage_bytes + (sb + 1) * kp.b_stage_bytes <= budget) { ++sb; grew = true; }
+    if (sa < 4 && (sa + 1) * a_stage_bytes + sb * kp.b_stage_bytes <= budget) { ++sa; grew = true; }
   }
   kp.a_stages = sa; kp.b_stages = sb;
-  kp.smem_b_off = NUM_STREAMS * sa * kp.a_stage_bytes;
-  kp.smem_g_off = kp.smem_b_off + NUM_STREAMS * sb * kp.b_stage_bytes;
+  kp.smem_b_off = sa * a_stage_bytes;
+  kp.smem_g_off = kp.smem_b_off + sb * kp.b_stage_bytes;
   kp.smem_stage_off = kp.smem_g_off + (d.gdn ? 2 * STAGE_BLK_BYTES : 0);
   kp.smem_misc_off = kp.smem_stage_off + n_stage_blk * STAGE_BLK_BYTES;
   pl->smem_bytes = kp.smem_misc_off + MISC_BYTES + 1024;
@@ -828,30 +874,24 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   if (rc) { delete pl; return rc; }
 
   // the programs travel in the kernel parameters (constant bank)
-  if (aops.size() > MAX_AOPS || bops.size() > MAX_BOPS || mops.size() > MAX_MOPS) { delete pl; return MASIC_ENOSUP; }
-  memcpy(kp.aops, aops.data(), aops.size() * sizeof(AOp));
-  memcpy(kp.bops, bops.data(), bops.size() * sizeof(BOp));
-  memcpy(kp.mops, mops.data(), mops.size() * sizeof(MOp));
+  if (strips.size() > MAX_STRIPS || bops.size() > MAX_BOPS) { delete pl; return MASIC_ENOSUP; }
+  memcpy(kp.strips, strips.data(), strips.size() * sizeof(Strip));
+  memcpy(kp.bops, bops.data(), bops.size() * sizeof(int32_t));
   cudaError_t ce = cudaSuccess;
 
   kp.bias = d.bias; kp.beta = d.beta; kp.gdn = d.gdn; kp.out_fp32 = d.out_fp32;
-  memcpy(kp.act, d.act, sizeof(kp.act));
+  for (int i = 0; i < 32; ++i)
+    kp.slope[i] = d.act[i] == MASIC_ACT_RELU ? 0.0f : (d.act[i] == MASIC_ACT_LEAKY ? 0.01f : 1.0f);
   kp.out_coff = d.out_coff;
   kp.rowscale = d.rowscale; kp.rs_stride = d.rs_stride; kp.rs_off = d.rs_off;
   kp.rs_H = gh; kp.rs_W = gw;
   { const char* e = getenv("MASIC_CONV_DEBUG"); kp.debug = e ? atoi(e) : 0; }
-  if (getenv("MASIC_CONV_TRACE")) {
-    if (cudaMalloc(&pl->d_trace, 64 * 16 * sizeof(long long)) == cudaSuccess) {
-      cudaMemset(pl->d_trace, 0, 64 * 16 * sizeof(long long));
-      kp.trace = static_cast<long long*>(pl->d_trace);
-    }
-  }
-
-  pl->total_work = kp.n_img * kp.tiles_y * kp.tiles_x * kp.n_var * kp.n_ntiles;
+  pl->total_work = kp.n_tiles_total;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   pl->grid = pl->total_work < sms ? pl->total_work : sms;
+  { const char* e = getenv("MASIC_CONV_GRID"); if (e && atoi(e) > 0 && atoi(e) < pl->grid) pl->grid = atoi(e); }
 
   // useful work: live taps only, real channels only
   {
@@ -889,15 +929,13 @@ extern "C" int masic_conv_plan_launch(const MasicConvPlan* pl, void* stream) {
 extern "C" void masic_conv_plan_destroy(MasicConvPlan* pl) {
   if (!pl) return;
   if (pl->d_tables) cudaFree(pl->d_tables);
-  if (pl->d_trace) cudaFree(pl->d_trace);
   delete pl;
 }
 
-// Debug: copy out the clock64() stamps of CTA 0 (64 tiles x 16 slots); needs MASIC_CONV_TRACE=1 at plan creation.
+// The clock64() tracing hooks of the first kernel generation were removed from the hot loops.
 extern "C" int masic_conv_plan_trace(const MasicConvPlan* pl, long long* out_host) {
-  if (!pl || !out_host) return MASIC_EINVAL;
-  if (!pl->d_trace) return MASIC_ENOSUP;
-  return (int)cudaMemcpy(out_host, pl->d_trace, 64 * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+  (void)pl; (void)out_host;
+  return MASIC_ENOSUP;
 }
 
 extern "C" int masic_conv_plan_info(const MasicConvPlan* pl, double* flops, double* hbm_bytes,
