@@ -23,7 +23,7 @@
 //     epilogue of one item overlaps the MMAs of the next; wider accumulators (<= 256
 //     columns) run as single tiles, double-buffered the same way;
 //   * a per-layer *program* (strips -> taps) built on the host drives three warp-uniform roles
-//     (A producer, B producer, MMA issuer); 8 epilogue warps (two groups splitting the
+//     (A producer, B producer, MMA issuer); 16 epilogue warps (four groups splitting the
 //     channels) drain the accumulators: +bias, activation, optional GDN — the squared tile goes
 //     to smem as a bf16 A operand, a second tcgen05.mma against gamma' writes the norm IN PLACE
 //     over the accumulator while x stays in registers — optional per-pixel scale, then
@@ -46,10 +46,10 @@ namespace masic {
 constexpr int TILE_W = 8;
 constexpr int TILE_H = 16;
 constexpr int KBLK = 64;            // channels per k-block: 128 B of bf16 = one swizzle row
-constexpr int NUM_THREADS = 384;    // warp 0: A producer, 1: B producer, 2: MMA issuer, 3: TMEM alloc;
-                                    // warps 4-7: epilogue group 0, warps 8-11: epilogue group 1
+constexpr int NUM_THREADS = 640;    // warp 0: A producer, 1: B producer, 2: MMA issuer, 3: TMEM alloc;
+                                    // warps 4-19: four epilogue groups of 4 warps
                                     // (warp % 4 = the TMEM lane quarter a warp may read)
-constexpr int EPI_THREADS = 256;
+constexpr int EPI_THREADS = 512;
 constexpr int MAX_VARIANTS = 4;
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_STRIPS = 64, MAX_BOPS = 96;
@@ -95,7 +95,8 @@ struct KParams {
   const float* rowscale;
   int rs_stride, rs_off, rs_H, rs_W;
   uint32_t idesc;
-  int debug;       // bit0: skip A loads, bit1: skip B loads, bit2: skip stores (timing experiments only)
+  int debug;       // timing experiments only (results are garbage): bit0 skip A loads, bit1 skip B loads, bit2 skip stores,
+                   // bit3 skip the GDN norm MMA, bit4 skip the whole epilogue
 };
 
 // misc smem region layout (byte offsets from smem_misc_off)
@@ -200,7 +201,7 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     float* be = reinterpret_cast<float*>(smem_gen + p.smem_misc_off + MISC_BETA);
     const int i = threadIdx.x - 128;
     if (i < 128) bs[i] = p.bias[i];
-    else be[i - 128] = p.beta[i - 128];
+    else if (i < 256) be[i - 128] = p.beta[i - 128];
   }
   tc_fence_before();
   __syncthreads();
@@ -336,22 +337,29 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> regs -> smem -> TMA store =====================
-    // Two groups of 4 warps.  GDN: group g owns channels [64g, 64g+64) and staging block g (the pair of
-    // blocks is the A2 operand of the norm MMA).  Otherwise group g owns the channel blocks j = g, g+2, ...
-    // and two staging blocks, so a block's TMA store drains behind the next block.
-    const int grp = warp >= 8 ? 1 : 0;
+    // Four groups of 4 warps (16 warps keep the 4 schedulers busy while tcgen05.ld / MUFU / st.shared latencies
+    // overlap).  Groups 2P and 2P+1 form a pair sharing 128-B staging rows: group g writes the 16-B chunks
+    // [4*(g&1), 4*(g&1)+4) of every row.  GDN: pair P owns channels [64P, 64P+64) = staging block P (the two
+    // blocks are the A2 operand of the norm MMA).  Otherwise pair P owns the channel blocks j = P, P+2, ... and
+    // two staging blocks, so a block's TMA store drains behind the next block.
+    const int grp = (warp - 4) >> 2;
+    const int half = grp & 1, pr = grp >> 1;
     const int ew = warp & 3;            // the TMEM lane quarter this warp may read
     const int t = ew * 32 + lane;       // accumulator row = tile position
     const uint32_t lane_sel = static_cast<uint32_t>(ew * 32) << 16;
-    const uint32_t gbar = 1 + grp;      // named barrier of this group (128 threads); barrier 3 = both groups
-    const bool leader = (t == 0);       // issues this group's TMA stores (bulk groups are per thread)
+    const uint32_t pbar = 1 + pr;       // named barrier of this pair (256 threads); barrier 3 = all epilogue threads
+    const bool leader = (t == 0 && half == 0);   // issues this pair's TMA stores (bulk groups are per thread)
     const int nblk = p.n_tile / p.blk_ch;
-    const uint32_t sbuf = sStage + grp * (p.gdn ? 1 : 2) * STAGE_BLK_BYTES;
+    const uint32_t sbuf = sStage + pr * (p.gdn ? 1 : 2) * STAGE_BLK_BYTES;
     const uint32_t bias_s = sMisc + MISC_BIAS, beta_s = sMisc + MISC_BETA;
     uint32_t flip = 0, gdn_par = 0;
     const float* __restrict__ bias_g = p.bias;
     const bool fwd = (p.gdn == MASIC_GDN_FWD);
     const bool nostore = (p.debug & 4) != 0;
+    const int sw = (p.blk_pitch == 128) ? (t & 7) : 0;
+    // plain path: this group's 16-channel chunks inside a block: bf16 rows hold 4 (2 per group), fp32 rows 2 (1 per group)
+    const int cpg = p.out_fp32 ? 1 : 2;
+    const int nchunk_blk = p.blk_ch / 16;
     int n_item = 0;
     if (p.gdn && grp == 0 && ew == 0) mbar_wait(sMisc + MISC_G_FULL, 0);
     for (int u = u_begin; u < u_end; ++n_item) {
@@ -363,6 +371,11 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
       const float* __restrict__ bias_t = bias_g ? bias_g + it.nt * p.n_tile : nullptr;
       mbar_wait(sMisc + MISC_ACC_FULL + 8 * buf, (n_item >> 1) & 1);
       tc_fence_after();
+      if (p.debug & 16) {                         // timing experiment: release the accumulators untouched
+        tc_fence_before();
+        mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * buf);
+        continue;
+      }
       for (int tt = 0; tt < it.cnt; ++tt) {
         const uint32_t acc_addr = tmem_base + lane_sel + buf * 256 + tt * 128;
         const bool last_tile = (tt + 1 == it.cnt);
@@ -373,20 +386,18 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
             rs = __ldg(p.rowscale + (static_cast<size_t>(it.n[tt] * p.rs_H + y) * p.rs_W + x) * p.rs_stride + p.rs_off);
         }
         if (p.gdn) {
-          // ---- pass 1: x = acc + bias stays in registers; A2[:, 64g .. 64g+64) = bf16(x^2), SWIZZLE_128B block g
-          const int cb = grp * 64;
-          uint32_t r[64];
+          // ---- pass 1: x = acc + bias stays in registers; A2[:, 32g .. 32g+32) = bf16(x^2) (SWIZZLE_128B block pr)
+          const int cb = grp * 32;
+          uint32_t r[32];
           tmem_ld16(acc_addr + cb, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
           tmem_ld16(acc_addr + cb + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
-          tmem_ld16(acc_addr + cb + 32, *reinterpret_cast<uint32_t(*)[16]>(&r[32]));
-          tmem_ld16(acc_addr + cb + 48, *reinterpret_cast<uint32_t(*)[16]>(&r[48]));
-          if (leader) tma_store_wait_read<0>();          // staging block g (== A2 block g) free again
+          if (leader) tma_store_wait_read<0>();          // staging block pr (== A2 block pr) free again
           tmem_ld_wait();
-          named_bar_sync(gbar, 128);
+          named_bar_sync(pbar, 256);
           const uint32_t arow = sbuf + t * 128;
-          float x[64];
+          float x[32];
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
+          for (int q = 0; q < 8; ++q) {
             const float4 b4 = ld_shared_f4(bias_s + (cb + 4 * q) * 4);
             x[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b4.x;
             x[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
@@ -394,15 +405,16 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
             x[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
           }
 #pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8) {
+          for (int c8 = 0; c8 < 4; ++c8) {
             const float* xx = &x[8 * c8];
-            st_shared_v4(arow + ((c8 ^ (t & 7)) << 4), pack_bf16x2(xx[0] * xx[0], xx[1] * xx[1]),
+            st_shared_v4(arow + (((4 * half + c8) ^ (t & 7)) << 4), pack_bf16x2(xx[0] * xx[0], xx[1] * xx[1]),
                          pack_bf16x2(xx[2] * xx[2], xx[3] * xx[3]), pack_bf16x2(xx[4] * xx[4], xx[5] * xx[5]),
                          pack_bf16x2(xx[6] * xx[6], xx[7] * xx[7]));
           }
           fence_proxy_async_smem();
           tc_fence_before();
           named_bar_sync(3, EPI_THREADS);
+          if (!(p.debug & 8)) {
           if (grp == 0 && ew == 0) {                      // warp-uniform; one elected lane issues the 8 MMAs
             tc_fence_after();
             if (elect_one()) {
@@ -422,121 +434,100 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
           }
           mbar_wait(sMisc + MISC_GDN_BAR, gdn_par);
           gdn_par ^= 1;
+          }
           tc_fence_after();
-          // ---- pass 2: out[:, 64g .. 64g+64) = x * rsqrt(beta + norm)  (IGDN: x * sqrt(.))
+          // ---- pass 2: out[:, 32g .. 32g+32) = x * rsqrt(beta + norm)  (IGDN: x * sqrt(.))
+          tmem_ld16(acc_addr + cb, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+          tmem_ld16(acc_addr + cb + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+          tmem_ld_wait();
+          if (last_tile) {                              // last TMEM read of this item's accumulators
+            tc_fence_before();
+            mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * buf);
+          }
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {                 // two halves of 32 channels: bounds the live registers
-            tmem_ld16(acc_addr + cb + 32 * h, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-            tmem_ld16(acc_addr + cb + 32 * h + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
-            tmem_ld_wait();
-            if (h == 1 && last_tile) {                  // last TMEM read of this item's accumulators
-              tc_fence_before();
-              mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * buf);
-            }
+          for (int q = 0; q < 8; ++q) {
+            const float4 e4 = ld_shared_f4(beta_s + (cb + 4 * q) * 4);
+            const float ee[4] = {e4.x, e4.y, e4.z, e4.w};
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 e4 = ld_shared_f4(beta_s + (cb + 32 * h + 4 * q) * 4);
-              const float ee[4] = {e4.x, e4.y, e4.z, e4.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float nrm = __uint_as_float(r[4 * q + e]) + ee[e];
-                // IGDN: sqrt(n) = n * rsqrt(n) on the MUFU fast path (2-ulp rsqrt is far below bf16 rounding)
-                const float rn = rsqrtf(nrm);
-                const float xv = x[32 * h + 4 * q + e];
-                x[32 * h + 4 * q + e] = (fwd ? xv * rn : xv * (nrm * rn)) * rs;
-              }
-            }
-#pragma unroll
-            for (int c8 = 4 * h; c8 < 4 * h + 4; ++c8) {
-              const float* xx = &x[8 * c8];
-              st_shared_v4(arow + ((c8 ^ (t & 7)) << 4), pack_bf16x2(xx[0], xx[1]), pack_bf16x2(xx[2], xx[3]),
-                           pack_bf16x2(xx[4], xx[5]), pack_bf16x2(xx[6], xx[7]));
+            for (int e = 0; e < 4; ++e) {
+              const float nrm = __uint_as_float(r[4 * q + e]) + ee[e];
+              // IGDN: sqrt(n) = n * rsqrt(n) on the MUFU fast path (2-ulp rsqrt is far below bf16 rounding)
+              const float rn = rsqrtf(nrm);
+              const float xv = x[4 * q + e];
+              x[4 * q + e] = (fwd ? xv * rn : xv * (nrm * rn)) * rs;
             }
           }
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            const float* xx = &x[8 * c8];
+            st_shared_v4(arow + (((4 * half + c8) ^ (t & 7)) << 4), pack_bf16x2(xx[0], xx[1]), pack_bf16x2(xx[2], xx[3]),
+                         pack_bf16x2(xx[4], xx[5]), pack_bf16x2(xx[6], xx[7]));
+          }
           fence_proxy_async_smem();
-          named_bar_sync(gbar, 128);
+          named_bar_sync(pbar, 256);
           if (leader && !nostore) {
-            tma_store_5d(&p.tmO, sbuf, p.out_coff + v.out_c0 + it.nt * p.n_tile + cb, it.x0[tt], v.out_p2, it.y0[tt],
+            tma_store_5d(&p.tmO, sbuf, p.out_coff + v.out_c0 + it.nt * p.n_tile + 64 * pr, it.x0[tt], v.out_p2, it.y0[tt],
                          it.n[tt]);
             tma_store_commit();
           }
         } else {
-          // ---- plain epilogue: bias, activation, per-pixel scale; this group's blocks j = grp, grp+2, ...
-          const int sw = (p.blk_pitch == 128) ? (t & 7) : 0;
-          for (int j = grp; j < nblk; j += 2) {
+          // ---- plain epilogue: bias, activation, per-pixel scale
+          for (int j = pr; j < nblk; j += 2) {
             const uint32_t sb2 = sbuf + flip * STAGE_BLK_BYTES;
             flip ^= 1;
-            const int c = j * p.blk_ch;
+            const int c = j * p.blk_ch;                 // first channel of the block inside the n-tile
             const uint32_t row = sb2 + t * p.blk_pitch;
             const bool last_read = last_tile && (j + 2 >= nblk);
-            if (p.out_fp32) {
-              // 32 fp32 channels per 128-B row (16 when the whole tile is narrower)
-              uint32_t r[32];
-              tmem_ld16(acc_addr + c, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-              if (p.blk_ch == 32) tmem_ld16(acc_addr + c + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
-              if (leader) tma_store_wait_read<1>();      // the store issued two blocks ago has left this buffer
-              tmem_ld_wait();
-              if (last_read) { tc_fence_before(); mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * buf); }
-              named_bar_sync(gbar, 128);
-              const int nq = p.blk_ch / 4;
+            const int k0 = half * cpg;                  // this group's first 16-channel chunk of the block
+            const bool has0 = k0 < nchunk_blk, has1 = cpg == 2 && k0 + 1 < nchunk_blk;
+            uint32_t r[32];
+            if (has0) tmem_ld16(acc_addr + c + 16 * k0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+            if (has1) tmem_ld16(acc_addr + c + 16 * k0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+            if (leader) tma_store_wait_read<1>();        // the store issued two blocks ago has left this buffer
+            tmem_ld_wait();
+            if (last_read) { tc_fence_before(); mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * buf); }
+            named_bar_sync(pbar, 256);
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                if (q < nq) {
+            for (int kk = 0; kk < 2; ++kk) {
+              if (kk == 0 ? has0 : has1) {
+                const int ch = c + 16 * (k0 + kk);       // channel inside the n-tile
+                float o[16];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
                   float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (bias_t) b4 = __ldg(reinterpret_cast<const float4*>(bias_t + c) + q);
+                  if (bias_t) b4 = __ldg(reinterpret_cast<const float4*>(bias_t + ch) + q);
                   const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-                  float o[4];
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
-                    const float xv = __uint_as_float(r[4 * q + e]) + bb[e];
-                    o[e] = fmaf(slope, fminf(xv, 0.0f), fmaxf(xv, 0.0f)) * rs;
+                    const float xv = __uint_as_float(r[16 * kk + 4 * q + e]) + bb[e];
+                    o[4 * q + e] = fmaf(slope, fminf(xv, 0.0f), fmaxf(xv, 0.0f)) * rs;
                   }
-                  st_shared_v4(row + ((q ^ sw) << 4), __float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]),
-                               __float_as_uint(o[3]));
                 }
-              }
-            } else {
-              // 64 bf16 channels per 128-B row (fewer when the whole tile is narrower)
-              uint32_t r[64];
-              const int nch = p.blk_ch / 16;
-              tmem_ld16(acc_addr + c, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-              if (nch > 1) tmem_ld16(acc_addr + c + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
-              if (nch > 2) tmem_ld16(acc_addr + c + 32, *reinterpret_cast<uint32_t(*)[16]>(&r[32]));
-              if (nch > 3) tmem_ld16(acc_addr + c + 48, *reinterpret_cast<uint32_t(*)[16]>(&r[48]));
-              if (leader) tma_store_wait_read<1>();
-              tmem_ld_wait();
-              if (last_read) { tc_fence_before(); mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * buf); }
-              named_bar_sync(gbar, 128);
-              const int n8 = p.blk_ch / 8;
+                if (p.out_fp32) {
+                  const int ch16 = 4 * (k0 + kk);        // 16 fp32 = four 16-B chunks
 #pragma unroll
-              for (int c8 = 0; c8 < 8; ++c8) {
-                if (c8 < n8) {
-                  float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-                  if (bias_t) {
-                    b0 = __ldg(reinterpret_cast<const float4*>(bias_t + c) + 2 * c8);
-                    b1 = __ldg(reinterpret_cast<const float4*>(bias_t + c) + 2 * c8 + 1);
-                  }
-                  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                  float o[8];
+                  for (int q = 0; q < 4; ++q)
+                    st_shared_v4(row + (((ch16 + q) ^ sw) << 4), __float_as_uint(o[4 * q]), __float_as_uint(o[4 * q + 1]),
+                                 __float_as_uint(o[4 * q + 2]), __float_as_uint(o[4 * q + 3]));
+                } else {
+                  const int ch16 = 2 * (k0 + kk);        // 16 bf16 = two 16-B chunks
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    const float xv = __uint_as_float(r[8 * c8 + e]) + bb[e];
-                    o[e] = fmaf(slope, fminf(xv, 0.0f), fmaxf(xv, 0.0f)) * rs;
-                  }
-                  st_shared_v4(row + ((c8 ^ sw) << 4), pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                               pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+                  for (int q = 0; q < 2; ++q)
+                    st_shared_v4(row + (((ch16 + q) ^ sw) << 4), pack_bf16x2(o[8 * q], o[8 * q + 1]),
+                                 pack_bf16x2(o[8 * q + 2], o[8 * q + 3]), pack_bf16x2(o[8 * q + 4], o[8 * q + 5]),
+                                 pack_bf16x2(o[8 * q + 6], o[8 * q + 7]));
                 }
               }
             }
             fence_proxy_async_smem();
-            named_bar_sync(gbar, 128);
+            named_bar_sync(pbar, 256);
             if (leader && !nostore) {
               tma_store_5d(&p.tmO, sb2, p.out_coff + v.out_c0 + it.nt * p.n_tile + c, it.x0[tt], v.out_p2, it.y0[tt],
                            it.n[tt]);
               tma_store_commit();
             }
           }
-          if (last_tile && grp >= nblk) {   // nothing to do for this group (single-block tile): just release
+          if (last_tile && pr >= nblk) {   // nothing to do for this pair (single-block tile): just release
             tc_fence_before();
             mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * buf);
           }
@@ -852,6 +843,12 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
     grew = false;
     if (sb < MAX_STAGES && sb < 6 && sa * a_stage_bytes + (sb + 1) * kp.b_stage_bytes <= budget) { ++sb; grew = true; }
     if (sa < 4 && (sa + 1) * a_stage_bytes + sb * kp.b_stage_bytes <= budget) { ++sa; grew = true; }
+  }
+  {   // experiments: MASIC_CONV_STAGES="sa,sb" caps the ring depths
+    const char* e = getenv("MASIC_CONV_STAGES");
+    int ea = 0, eb = 0;
+    if (e && sscanf(e, "%d,%d", &ea, &eb) == 2 && ea >= 2 && eb >= 2 && ea <= MAX_STAGES && eb <= MAX_STAGES &&
+        ea * a_stage_bytes + eb * kp.b_stage_bytes <= budget) { sa = ea; sb = eb; }
   }
   kp.a_stages = sa; kp.b_stages = sb;
   kp.smem_b_off = sa * a_stage_bytes;

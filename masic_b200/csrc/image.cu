@@ -137,6 +137,7 @@ warp_kernel(const float* __restrict__ src, int n, int c, int h, int w, int ho, i
 constexpr int SC_MAX_CO = 8, SC_MAX_CI = 8;
 
 // out = act(conv_k(cat(in0, in1))) [-> GDN over the c_out channels]; one thread per output pixel.
+template <int KT>     // KT = 3: fully unrolled 3x3 taps (all 9 loads of a channel in flight); KT = 0: generic loops
 __global__ void __launch_bounds__(128)
 conv_small_kernel(const float* __restrict__ in0, int c0, const float* __restrict__ in1, int c1,
                   int n, int h, int w, const float* __restrict__ wt, int transposed_s1,
@@ -174,6 +175,24 @@ conv_small_kernel(const float* __restrict__ in0, int c0, const float* __restrict
 #pragma unroll
   for (int co = 0; co < SC_MAX_CO; ++co) acc[co] = co < c_out ? s_b[co] : 0.0f;
   const int pad = k / 2;
+  if (KT == 3) {
+    for (int ci = 0; ci < cin; ++ci) {
+      const float* src = ci < c0 ? in0 + ((long)(b * c0 + ci) * h) * w : in1 + ((long)(b * c1 + (ci - c0)) * h) * w;
+      float v[9];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int iy = y * stride - 1 + ky, ix = x * stride - 1 + kx;
+          v[ky * 3 + kx] = (iy >= 0 && iy < h && ix >= 0 && ix < w) ? __ldg(src + (long)iy * w + ix) : 0.0f;
+        }
+#pragma unroll
+      for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+        for (int co = 0; co < SC_MAX_CO; ++co)
+          if (co < c_out) acc[co] = fmaf(v[tp], s_w[(co * cin + ci) * 9 + tp], acc[co]);
+    }
+  } else {
   for (int ci = 0; ci < cin; ++ci) {
     const float* src = ci < c0 ? in0 + ((long)(b * c0 + ci) * h) * w : in1 + ((long)(b * c1 + (ci - c0)) * h) * w;
     for (int ky = 0; ky < k; ++ky) {
@@ -188,6 +207,7 @@ conv_small_kernel(const float* __restrict__ in0, int c0, const float* __restrict
           if (co < c_out) acc[co] = fmaf(v, s_w[(co * cin + ci) * kk + ky * k + kx], acc[co]);
       }
     }
+  }
   }
   if (act == MASIC_ACT_RELU) {
 #pragma unroll
@@ -216,29 +236,29 @@ conv_small_kernel(const float* __restrict__ in0, int c0, const float* __restrict
 }
 
 // ------------------------------------------------------------------ 6 -> 3, 5x5, stride 1 (pre_conv / after_conv)
-// Shared-memory tiled: a block produces 128 x 8 output pixels from a (128+4) x (8+4) x 6 input
-// patch staged once; each thread owns 4 horizontally adjacent pixels so every staged value and
-// every (broadcast) weight feeds 12 / 4 FMAs.  HBM-bound: 24 B in + 12 B out per pixel.
+// Shared-memory tiled: a block of 16 x 8 threads produces 128 x 8 output pixels from a (128+4) x (8+4) x 6
+// input patch staged once; each thread owns 2 x 4 horizontally adjacent pixels x 3 output channels (24
+// accumulators), so per (ci, ky) it issues 4 conflict-free LDS.128 of pixels + 4 LDS.128 of (broadcast) weights
+// for 120 FMAs: FMA-bound, not LDS-bound.  HBM traffic: 24 B in + 12 B out per pixel.
 constexpr int F_TW = 128, F_TH = 8, F_PW = F_TW + 8, F_PH = F_TH + 4;   // pitch padded to 136 floats
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 conv5x5_6to3_kernel(const float* __restrict__ in0, const float* __restrict__ in1, int n, int h, int w,
                     const float* __restrict__ wt, int transposed_s1, const float* __restrict__ bias,
                     int gdn, const float* __restrict__ beta, const float* __restrict__ gamma, float beta_bound,
                     float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf, int bf_pitch, int bf_row,
                     int bf_xoff) {
   __shared__ __align__(16) float s_in[6][F_PH][F_PW];
-  __shared__ float s_w[3 * 6 * 25];
+  __shared__ __align__(16) float s_w[6 * 5 * 16];      // [ci][ky][kx*3 + co], 15 used of 16
   __shared__ float s_b[3], s_beta[3], s_gamma[9];
-  const int tid = threadIdx.y * 32 + threadIdx.x;
-  for (int i = tid; i < 450; i += 256) {
-    const int tap = i % 25, ci = (i / 25) % 6, co = i / 150;
-    float v;
-    if (transposed_s1) {
-      const int ky = 4 - tap / 5, kx = 4 - tap % 5;
-      v = wt[((ci * 3 + co) * 5 + ky) * 5 + kx];
-    } else {
-      v = wt[i];
+  const int tid = threadIdx.y * 16 + threadIdx.x;
+  for (int i = tid; i < 6 * 5 * 16; i += 128) {
+    const int j = i & 15, ky = (i >> 4) % 5, ci = i / 80;
+    float v = 0.0f;
+    if (j < 15) {
+      const int kx = j / 3, co = j % 3;
+      if (transposed_s1) v = wt[((ci * 3 + co) * 5 + (4 - ky)) * 5 + (4 - kx)];   // flipped conv
+      else v = wt[((co * 6 + ci) * 5 + ky) * 5 + kx];
     }
     s_w[i] = v;
   }
@@ -249,40 +269,60 @@ conv5x5_6to3_kernel(const float* __restrict__ in0, const float* __restrict__ in1
     if (tid < 9) { const float g = fmaxf(gamma[tid], 3.814697265625e-06f); s_gamma[tid] = g * g - ped; }
   }
   const int b = blockIdx.z, y0 = blockIdx.y * F_TH, x0 = blockIdx.x * F_TW;
-  for (int i = tid; i < 6 * F_PH * (F_TW + 4); i += 256) {
-    const int px = i % (F_TW + 4), py = (i / (F_TW + 4)) % F_PH, ci = i / ((F_TW + 4) * F_PH);
-    const int gy = y0 + py - 2, gx = x0 + px - 2;
-    float v = 0.0f;
-    if (gy >= 0 && gy < h && gx >= 0 && gx < w) {
-      const float* src = ci < 3 ? in0 + ((long)(b * 3 + ci) * h) * w : in1 + ((long)(b * 3 + ci - 3) * h) * w;
-      v = __ldg(src + (long)gy * w + gx);
+  // stage the patch with aligned float4 global loads; s_in column c holds image column x0 - 2 + c
+  const bool vec_ok = (w & 3) == 0;
+  for (int i = tid; i < 6 * F_PH * (F_PW / 4); i += 128) {
+    const int q = i % (F_PW / 4), py = (i / (F_PW / 4)) % F_PH, ci = i / ((F_PW / 4) * F_PH);
+    const int gy = y0 + py - 2, gx = x0 + 4 * q - 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gy >= 0 && gy < h) {
+      const float* src = (ci < 3 ? in0 + ((long)(b * 3 + ci) * h) * w : in1 + ((long)(b * 3 + ci - 3) * h) * w) + (long)gy * w;
+      if (vec_ok && gx >= 0 && gx + 3 < w) {
+        v = __ldg(reinterpret_cast<const float4*>(src + gx));
+      } else {
+        if (gx >= 0 && gx < w) v.x = __ldg(src + gx);
+        if (gx + 1 >= 0 && gx + 1 < w) v.y = __ldg(src + gx + 1);
+        if (gx + 2 >= 0 && gx + 2 < w) v.z = __ldg(src + gx + 2);
+        if (gx + 3 >= 0 && gx + 3 < w) v.w = __ldg(src + gx + 3);
+      }
     }
-    s_in[ci][py][px] = v;
+    const int c = 4 * q - 2;
+    if (c >= 0) *reinterpret_cast<float2*>(&s_in[ci][py][c]) = make_float2(v.x, v.y);
+    if (c + 2 < F_PW) *reinterpret_cast<float2*>(&s_in[ci][py][c + 2]) = make_float2(v.z, v.w);
   }
   __syncthreads();
-  float acc[4][3];
+  // thread (tx, ty): pixels 4tx..4tx+3 (group 0) and 64+4tx..64+4tx+3 (group 1) of row ty: every LDS.128 of a
+  // quarter-warp covers 128 contiguous bytes (no bank conflicts)
+  float acc[2][4][3];
 #pragma unroll
-  for (int p = 0; p < 4; ++p)
+  for (int g = 0; g < 2; ++g)
 #pragma unroll
-    for (int co = 0; co < 3; ++co) acc[p][co] = s_b[co];
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int co = 0; co < 3; ++co) acc[g][p][co] = s_b[co];
   const int lx = threadIdx.x * 4, ly = threadIdx.y;
 #pragma unroll 1
   for (int ci = 0; ci < 6; ++ci) {
 #pragma unroll
     for (int ky = 0; ky < 5; ++ky) {
-      const float4 a = *reinterpret_cast<const float4*>(&s_in[ci][ly + ky][lx]);
-      const float4 c = *reinterpret_cast<const float4*>(&s_in[ci][ly + ky][lx + 4]);
-      const float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+      const float4* wq = reinterpret_cast<const float4*>(&s_w[(ci * 5 + ky) * 16]);
+      const float4 w0 = wq[0], w1 = wq[1], w2 = wq[2], w3 = wq[3];
+      const float ww[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
 #pragma unroll
-      for (int kx = 0; kx < 5; ++kx) {
-        const float w0 = s_w[(0 * 6 + ci) * 25 + ky * 5 + kx];
-        const float w1 = s_w[(1 * 6 + ci) * 25 + ky * 5 + kx];
-        const float w2 = s_w[(2 * 6 + ci) * 25 + ky * 5 + kx];
+      for (int g = 0; g < 2; ++g) {
+        // output pixel lx+64g+p, tap kx reads image column x0 + lx + 64g + p + kx - 2 = s_in column lx + 64g + p + kx
+        const float4 a0 = *reinterpret_cast<const float4*>(&s_in[ci][ly + ky][lx + 64 * g]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&s_in[ci][ly + ky][lx + 64 * g + 4]);
+        const float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          acc[p][0] = fmaf(v[p + kx], w0, acc[p][0]);
-          acc[p][1] = fmaf(v[p + kx], w1, acc[p][1]);
-          acc[p][2] = fmaf(v[p + kx], w2, acc[p][2]);
+        for (int kx = 0; kx < 5; ++kx) {
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float x = v[p + kx];
+            acc[g][p][0] = fmaf(x, ww[kx * 3 + 0], acc[g][p][0]);
+            acc[g][p][1] = fmaf(x, ww[kx * 3 + 1], acc[g][p][1]);
+            acc[g][p][2] = fmaf(x, ww[kx * 3 + 2], acc[g][p][2]);
+          }
         }
       }
     }
@@ -290,33 +330,36 @@ conv5x5_6to3_kernel(const float* __restrict__ in0, const float* __restrict__ in1
   const int oy = y0 + ly;
   if (oy >= h) return;
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
+  for (int g = 0; g < 2; ++g) {
     if (gdn) {
-      const float s0 = acc[p][0] * acc[p][0], s1 = acc[p][1] * acc[p][1], s2 = acc[p][2] * acc[p][2];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const float nrm = fmaf(s_gamma[i * 3 + 2], s2, fmaf(s_gamma[i * 3 + 1], s1, fmaf(s_gamma[i * 3], s0, s_beta[i])));
-        acc[p][i] *= (gdn == MASIC_GDN_FWD) ? rsqrtf(nrm) : sqrtf(nrm);
+      for (int p = 0; p < 4; ++p) {
+        const float s0 = acc[g][p][0] * acc[g][p][0], s1 = acc[g][p][1] * acc[g][p][1], s2 = acc[g][p][2] * acc[g][p][2];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float nrm = fmaf(s_gamma[i * 3 + 2], s2, fmaf(s_gamma[i * 3 + 1], s1, fmaf(s_gamma[i * 3], s0, s_beta[i])));
+          acc[g][p][i] *= (gdn == MASIC_GDN_FWD) ? rsqrtf(nrm) : sqrtf(nrm);
+        }
       }
     }
-  }
-  const int ox = x0 + lx;
-  if (out) {
+    const int ox = x0 + lx + 64 * g;
+    if (out) {
 #pragma unroll
-    for (int co = 0; co < 3; ++co) {
-      float* o = out + ((long)(b * 3 + co) * h + oy) * w + ox;
-      if (ox + 3 < w && (w & 3) == 0) {
-        *reinterpret_cast<float4*>(o) = make_float4(acc[0][co], acc[1][co], acc[2][co], acc[3][co]);
-      } else {
-        for (int p = 0; p < 4; ++p) if (ox + p < w) o[p] = acc[p][co];
+      for (int co = 0; co < 3; ++co) {
+        float* o = out + ((long)(b * 3 + co) * h + oy) * w + ox;
+        if (ox + 3 < w && (w & 3) == 0) {
+          *reinterpret_cast<float4*>(o) = make_float4(acc[g][0][co], acc[g][1][co], acc[g][2][co], acc[g][3][co]);
+        } else {
+          for (int p = 0; p < 4; ++p) if (ox + p < w) o[p] = acc[g][p][co];
+        }
       }
     }
-  }
-  if (out_bf) {
-    for (int p = 0; p < 4; ++p) {
-      if (ox + p >= w) break;
-      const float v3[8] = {acc[p][0], acc[p][1], acc[p][2], 0.f, 0.f, 0.f, 0.f, 0.f};
-      store_pixel_bf16(out_bf + ((long)(b * h + oy) * bf_row + ox + p + bf_xoff) * bf_pitch, v3, 3, bf_pitch);
+    if (out_bf) {
+      for (int p = 0; p < 4; ++p) {
+        if (ox + p >= w) break;
+        const float v3[8] = {acc[g][p][0], acc[g][p][1], acc[g][p][2], 0.f, 0.f, 0.f, 0.f, 0.f};
+        store_pixel_bf16(out_bf + ((long)(b * h + oy) * bf_row + ox + p + bf_xoff) * bf_pitch, v3, 3, bf_pitch);
+      }
     }
   }
 }
@@ -454,7 +497,7 @@ extern "C" int masic_conv_small_nchw(const float* in0, int c0, const float* in1,
   if (bf_row_pixels < wo + bf_xoff || bf_xoff < 0) return MASIC_EINVAL;
   if (ksize == 5 && stride == 1 && c0 == 3 && c1 == 3 && c_out == 3 && act == MASIC_ACT_NONE &&
       (bf_pitch % 2 == 0)) {
-    dim3 fgrid((w + F_TW - 1) / F_TW, (h + F_TH - 1) / F_TH, n), fblock(32, 8);
+    dim3 fgrid((w + F_TW - 1) / F_TW, (h + F_TH - 1) / F_TH, n), fblock(16, 8);
     conv5x5_6to3_kernel<<<fgrid, fblock, 0, static_cast<cudaStream_t>(stream)>>>(
         in0, in1, n, h, w, weight, transposed_s1, bias, gdn, beta, gamma,
         sqrtf(beta_min + 1.4551915228366852e-11f), out_nchw, static_cast<__nv_bfloat16*>(out_nhwc_bf16),
@@ -462,7 +505,8 @@ extern "C" int masic_conv_small_nchw(const float* in0, int c0, const float* in1,
     return (int)cudaGetLastError();
   }
   dim3 grid((wo + 127) / 128, ho, n);
-  conv_small_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  auto kern = (ksize == 3) ? conv_small_kernel<3> : conv_small_kernel<0>;
+  kern<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       in0, c0, in1, c1, n, h, w, weight, transposed_s1, bias, c_out, ksize, stride, act, gdn, beta, gamma,
       sqrtf(beta_min + 1.4551915228366852e-11f), ho, wo, out_nchw,
       static_cast<__nv_bfloat16*>(out_nhwc_bf16), bf_pitch, bf_row_pixels, bf_xoff);
