@@ -46,7 +46,7 @@ namespace masic {
 constexpr int TILE_W = 8;
 constexpr int TILE_H = 16;
 constexpr int KBLK = 64;            // channels per k-block: 128 B of bf16 = one swizzle row
-constexpr int NUM_THREADS = 640;    // warp 0: A producer, 1: B producer, 2: MMA issuer, 3: TMEM alloc;
+constexpr int NUM_THREADS = 640;    // warp 0: A producer, 1: B producer, 2: MMA issuer of slot 0, 3: TMEM alloc + issuer of slot 1;
                                     // warps 4-19: four epilogue groups of 4 warps
                                     // (warp % 4 = the TMEM lane quarter a warp may read)
 constexpr int EPI_THREADS = 512;
@@ -82,7 +82,8 @@ struct KParams {
   int n_spatial;                   // tiles_x * tiles_y * n_img
   int n_tiles_total;               // n_spatial * n_var * n_ntiles; tile id u = group * n_spatial + s
   int n_tile;
-  int pair;                        // tiles per work item: 2 (n_tile <= 128) or 1
+  int pair;                        // accumulator slots per CTA and work item: 2 (n_tile <= 128) or 1
+  int cg2;                         // 1: launched as CTA pairs (clusters of 2) issuing tcgen05.mma.cta_group::2
   int strip_bytes, b_stage_bytes, a_stages, b_stages;
   int smem_b_off, smem_g_off, smem_stage_off, smem_misc_off;
   const float* bias;
@@ -109,6 +110,7 @@ constexpr int MISC_ACC_EMPTY = 272;                  // 2 x u64
 constexpr int MISC_GDN_BAR = 288;
 constexpr int MISC_G_FULL = 296;
 constexpr int MISC_TMEM_PTR = 304;
+constexpr int MISC_A2_READY = 312;                   // CTA pairs: both CTAs have written their A2 operand
 constexpr int MISC_BIAS = 512;                       // 128 floats (GDN layers: bias of the single n-tile)
 constexpr int MISC_BETA = 1024;                      // 128 floats
 constexpr int MISC_BYTES = 1536;
@@ -129,9 +131,13 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
   return v;
 }
 
-// A work item: `cnt` (1 or 2) tiles u, u+1 of the same group (variant, n-tile).
+// A work item: `cnt` consecutive tiles of the same group (variant, n-tile): up to `pair` per CTA, i.e. up to
+// 2*pair for a CTA pair, where tile k of the item lives in CTA (k & 1), accumulator slot (k >> 1).
 struct Item {
-  int cnt, var, nt;
+  int cnt;        // tiles in the item (whole CTA pair)
+  int nslots;     // accumulator slots in use per CTA
+  int var, nt;
+  bool valid[2];  // does this CTA own a tile in slot t
   int n[2], y0[2], x0[2];
 };
 __device__ __forceinline__ void decode_tile(const KParams& p, int s, int& n, int& y0, int& x0) {
@@ -141,17 +147,25 @@ __device__ __forceinline__ void decode_tile(const KParams& p, int s, int& n, int
   y0 = (r % p.tiles_y) * TILE_H;
   n = r / p.tiles_y;
 }
-__device__ __forceinline__ Item decode_item(const KParams& p, int u, int u_end) {
+template <bool CG2>
+__device__ __forceinline__ Item decode_item(const KParams& p, int u, int u_end, int rank) {
   Item it;
   const int g = u / p.n_spatial, s = u - g * p.n_spatial;
   it.nt = g % p.n_ntiles;
   it.var = g / p.n_ntiles;
-  it.cnt = (p.pair == 2 && u + 1 < u_end && s + 1 < p.n_spatial) ? 2 : 1;
-  decode_tile(p, s, it.n[0], it.y0[0], it.x0[0]);
-  decode_tile(p, it.cnt == 2 ? s + 1 : s, it.n[1], it.y0[1], it.x0[1]);
+  const int cap = CG2 ? 2 * p.pair : p.pair;
+  it.cnt = min(cap, min(u_end - u, p.n_spatial - s));
+  it.nslots = CG2 ? (it.cnt + 1) >> 1 : it.cnt;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int k = CG2 ? 2 * t + rank : t;
+    it.valid[t] = k < it.cnt;
+    decode_tile(p, it.valid[t] ? s + k : s, it.n[t], it.y0[t], it.x0[t]);
+  }
   return it;
 }
 
+template <bool CG2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -170,9 +184,13 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
   // depend on blockIdx and kernel parameters) on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  // this CTA's contiguous, balanced range of tiles
-  const int u_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * p.n_tiles_total / gridDim.x);
-  const int u_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * p.n_tiles_total / gridDim.x);
+  // this CTA's (CTA pair's) contiguous, balanced range of tiles
+  const int rank = CG2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int unit = CG2 ? blockIdx.x >> 1 : blockIdx.x, n_units = CG2 ? gridDim.x >> 1 : gridDim.x;
+  const int u_begin = static_cast<int>(static_cast<long long>(unit) * p.n_tiles_total / n_units);
+  const int u_end = static_cast<int>(static_cast<long long>(unit + 1) * p.n_tiles_total / n_units);
+  // mbarriers the producers credit / the epilogue releases live in the leader CTA (rank 0) of a pair
+  auto leader_bar = [&](uint32_t local) -> uint32_t { return CG2 ? mapa_shared(local, 0) : local; };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -180,21 +198,22 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     tma_prefetch_desc(&p.tmO);
     for (int i = 0; i < MAX_STAGES; ++i) {
       mbar_init(sMisc + MISC_A_FULL + 8 * i, 1);
-      mbar_init(sMisc + MISC_A_EMPTY + 8 * i, 1);
+      mbar_init(sMisc + MISC_A_EMPTY + 8 * i, p.pair);     // one commit per MMA-issuing warp
       mbar_init(sMisc + MISC_B_FULL + 8 * i, 1);
-      mbar_init(sMisc + MISC_B_EMPTY + 8 * i, 1);
+      mbar_init(sMisc + MISC_B_EMPTY + 8 * i, p.pair);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(sMisc + MISC_ACC_FULL + 8 * i, 1);
-      mbar_init(sMisc + MISC_ACC_EMPTY + 8 * i, EPI_THREADS);
+      mbar_init(sMisc + MISC_ACC_FULL + 8 * i, p.pair);
+      mbar_init(sMisc + MISC_ACC_EMPTY + 8 * i, CG2 ? 2 * EPI_THREADS : EPI_THREADS);
     }
     mbar_init(sMisc + MISC_GDN_BAR, 1);
     mbar_init(sMisc + MISC_G_FULL, 1);
+    mbar_init(sMisc + MISC_A2_READY, 2);
     fence_mbar_init();
   }
   if (warp == 3) {
-    tmem_alloc(sMisc + MISC_TMEM_PTR, TMEM_COLS);
-    tmem_relinquish();
+    if (CG2) { tmem_alloc_cg2(sMisc + MISC_TMEM_PTR, TMEM_COLS); tmem_relinquish_cg2(); }
+    else { tmem_alloc(sMisc + MISC_TMEM_PTR, TMEM_COLS); tmem_relinquish(); }
   }
   if (p.gdn && threadIdx.x >= 128) {       // the single n-tile's bias / beta' stay in smem for the whole kernel
     float* bs = reinterpret_cast<float*>(smem_gen + p.smem_misc_off + MISC_BIAS);
@@ -204,18 +223,19 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     else if (i < 256) be[i - 128] = p.beta[i - 128];
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG2) cluster_sync_all(); else __syncthreads();     // barrier inits visible to the peer before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
   // Role loops are WARP-UNIFORM (all 32 lanes walk them, barrier waits included) and only the
   // issue instructions sit under elect_one(): tcgen05.mma / TMA are uniform-datapath instructions.
-  if (warp == 0) {
+  const bool free_run = (p.debug & 32) != 0;     // timing experiment: MMA issuers ignore the A/B rings entirely
+  if (warp == 0 && !free_run) {
     // ===================== A producer: activation strips =====================
     uint32_t st = 0, ph = 0;
     const uint32_t n_st = p.a_stages, strip_bytes = p.strip_bytes, st_bytes = p.pair * p.strip_bytes;
     for (int u = u_begin; u < u_end;) {
-      const Item it = decode_item(p, u, u_end);
+      const Item it = decode_item<CG2>(p, u, u_end, rank);
       u += it.cnt;
       const int i0 = p.var[it.var].strip_off, i1 = i0 + p.var[it.var].n_strips;
       for (int i = i0; i < i1; ++i) {
@@ -224,34 +244,51 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
         mbar_wait(sMisc + MISC_A_EMPTY + 8 * st, ph ^ 1);
         if (elect_one()) {
           if (p.debug & 1) {
-            mbar_arrive(full);
+            if (rank == 0) mbar_arrive(full);
           } else {
-            mbar_expect_tx(full, it.cnt * strip_bytes);
-            tma_load_5d(sA + st * st_bytes, &p.tmA, full, sp.c0, it.x0[0] + sp.dx, sp.p2, it.y0[0] + sp.dy, it.n[0]);
-            if (it.cnt == 2)
-              tma_load_5d(sA + st * st_bytes + strip_bytes, &p.tmA, full, sp.c0, it.x0[1] + sp.dx, sp.p2,
-                          it.y0[1] + sp.dy, it.n[1]);
+            // the leader's barrier collects the strips of every tile of the item, whichever CTA stages them
+            if (rank == 0) mbar_expect_tx(full, it.cnt * strip_bytes);
+            const uint32_t fl = leader_bar(full);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              if (it.valid[t]) {
+                if (CG2)
+                  tma_load_5d_cg2(sA + st * st_bytes + t * strip_bytes, &p.tmA, fl, sp.c0, it.x0[t] + sp.dx, sp.p2,
+                                  it.y0[t] + sp.dy, it.n[t]);
+                else
+                  tma_load_5d(sA + st * st_bytes + t * strip_bytes, &p.tmA, fl, sp.c0, it.x0[t] + sp.dx, sp.p2,
+                              it.y0[t] + sp.dy, it.n[t]);
+              }
+            }
           }
         }
         __syncwarp();
         if (++st == n_st) { st = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && !free_run) {
     // ===================== B producer: weight k-blocks (+ gamma once) =====================
     if (p.gdn && elect_one()) {
       tma_prefetch_desc(&p.tmG);
-      mbar_expect_tx(sMisc + MISC_G_FULL, 2 * STAGE_BLK_BYTES);
-      tma_load_2d(sG, &p.tmG, sMisc + MISC_G_FULL, 0, 0);
-      tma_load_2d(sG + STAGE_BLK_BYTES, &p.tmG, sMisc + MISC_G_FULL, KBLK, 0);
+      if (CG2) {          // each CTA holds the 64 N-rows of gamma' it feeds to the pair's norm MMA
+        if (rank == 0) mbar_expect_tx(sMisc + MISC_G_FULL, 2 * STAGE_BLK_BYTES);
+        const uint32_t gf = leader_bar(sMisc + MISC_G_FULL);
+        tma_load_2d_cg2(sG, &p.tmG, gf, 0, 64 * rank);
+        tma_load_2d_cg2(sG + STAGE_BLK_BYTES / 2, &p.tmG, gf, KBLK, 64 * rank);
+      } else {
+        mbar_expect_tx(sMisc + MISC_G_FULL, 2 * STAGE_BLK_BYTES);
+        tma_load_2d(sG, &p.tmG, sMisc + MISC_G_FULL, 0, 0);
+        tma_load_2d(sG + STAGE_BLK_BYTES, &p.tmG, sMisc + MISC_G_FULL, KBLK, 0);
+      }
     }
     __syncwarp();
     uint32_t st = 0, ph = 0;
     const uint32_t n_st = p.b_stages, st_bytes = p.b_stage_bytes;
     for (int u = u_begin; u < u_end;) {
-      const Item it = decode_item(p, u, u_end);
+      const Item it = decode_item<CG2>(p, u, u_end, rank);
       u += it.cnt;
-      const int nrow = it.nt * p.n_tile;
+      // a CTA of a pair stages its half of the n-tile's rows (st_bytes = that half)
+      const int nrow = it.nt * p.n_tile + (CG2 ? rank * (p.n_tile >> 1) : 0);
       const int i0 = p.var[it.var].bop_off, i1 = i0 + p.var[it.var].n_bops;
       for (int i = i0; i < i1; ++i) {
         const int row0 = p.bops[i];
@@ -259,72 +296,70 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
         mbar_wait(sMisc + MISC_B_EMPTY + 8 * st, ph ^ 1);
         if (elect_one()) {
           if (p.debug & 2) {
-            mbar_arrive(full);
+            if (rank == 0) mbar_arrive(full);
           } else {
-            mbar_expect_tx(full, st_bytes);
-            tma_load_2d(sB + st * st_bytes, &p.tmB, full, 0, row0 + nrow);
+            if (rank == 0) mbar_expect_tx(full, CG2 ? 2 * st_bytes : st_bytes);
+            if (CG2) tma_load_2d_cg2(sB + st * st_bytes, &p.tmB, leader_bar(full), 0, row0 + nrow);
+            else tma_load_2d(sB + st * st_bytes, &p.tmB, full, 0, row0 + nrow);
           }
         }
         __syncwarp();
         if (++st == n_st) { st = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 2) {
-    // ===================== MMA issuer =====================
+  } else if ((warp == 2 || (warp == 3 && p.pair == 2)) && rank == 0) {
+    // ===================== MMA issuers (CTA pairs: the leader issues for both CTAs) =====================
+    // One issuing warp per accumulator slot: with two tiles per item, warp 2 feeds slot 0 and warp 3 slot 1 from
+    // the SAME A/B stages, so each warp's loop (mbarrier waits, descriptor arithmetic, 4 MMAs, commits) only
+    // has to keep up with half of the tensor-pipe work.  Every stage is released by one commit per issuer.
+    const int slot = warp - 2;
     const uint32_t n_sa = p.a_stages, n_sb = p.b_stages;
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
     // descriptor = constant high part | (smem address >> 4); +2 per K=16 step, +64 per strip row
-    const uint64_t descA0 = umma_desc_sw128(sA), descB0 = umma_desc_sw128(sB);
+    const uint64_t descA0 = umma_desc_sw128(sA) + slot * (p.strip_bytes >> 4), descB0 = umma_desc_sw128(sB);
     const uint32_t a_step = (p.pair * p.strip_bytes) >> 4, b_step = p.b_stage_bytes >> 4;
-    const uint32_t t1_off = p.strip_bytes >> 4;           // second tile of a pair inside an A stage
     const uint32_t idesc = p.idesc;
-    const uint32_t slot_cols = 128;                        // pair mode: tile t of buffer b at column b*256 + t*128
     int n_item = 0;
     for (int u = u_begin; u < u_end; ++n_item) {
-      const Item it = decode_item(p, u, u_end);
+      const Item it = decode_item<CG2>(p, u, u_end, rank);
       u += it.cnt;
       const int buf = n_item & 1;
       mbar_wait(sMisc + MISC_ACC_EMPTY + 8 * buf, ((n_item >> 1) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t d0 = tmem_base + buf * 256;
-      const uint32_t d1 = d0 + slot_cols;
-      const bool two = it.cnt == 2;
+      const uint32_t d0 = tmem_base + buf * 256 + slot * 128;
+      const bool active = slot < it.nslots;                // an item may fill only slot 0
       uint32_t acc = 0;                                    // 0 for the first MMA group of the item
       const int i0 = p.var[it.var].strip_off, i1 = i0 + p.var[it.var].n_strips;
       for (int i = i0; i < i1; ++i) {
         const Strip sp = p.strips[i];
         const uint32_t nk = sp.nk & 15u, k0 = sp.nk >> 4;
-        mbar_wait(sMisc + MISC_A_FULL + 8 * sa, pa);
+        if (!free_run) mbar_wait(sMisc + MISC_A_FULL + 8 * sa, pa);
         uint64_t adesc = descA0 + (sa * a_step + static_cast<uint32_t>(sp.a_row0) * 64u + 2u * k0);
         const int64_t a_inc = static_cast<int64_t>(sp.a_step) * 64;
         const int n_taps = sp.n_taps;
         for (int j = 0; j < n_taps; ++j) {
-          mbar_wait(sMisc + MISC_B_FULL + 8 * sb, pb);
+          if (!free_run) mbar_wait(sMisc + MISC_B_FULL + 8 * sb, pb);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t bdesc = descB0 + (sb * b_step + 2u * k0);
-            if (nk == 4) {
-              umma_bf16(d0, adesc, bdesc, idesc, acc);
-              umma_bf16(d0, adesc + 2, bdesc + 2, idesc, 1u);
-              umma_bf16(d0, adesc + 4, bdesc + 4, idesc, 1u);
-              umma_bf16(d0, adesc + 6, bdesc + 6, idesc, 1u);
-              if (two) {
-                const uint64_t a1 = adesc + t1_off;
-                umma_bf16(d1, a1, bdesc, idesc, acc);
-                umma_bf16(d1, a1 + 2, bdesc + 2, idesc, 1u);
-                umma_bf16(d1, a1 + 4, bdesc + 4, idesc, 1u);
-                umma_bf16(d1, a1 + 6, bdesc + 6, idesc, 1u);
+            auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t ac) {
+              if (CG2) umma_bf16_cg2(d, a, b, idesc, ac); else umma_bf16(d, a, b, idesc, ac);
+            };
+            auto commit = [&](uint32_t bar) { if (CG2) umma_commit_cg2(bar); else umma_commit(bar); };
+            if (active) {
+              if (nk == 4) {
+                mma(d0, adesc, bdesc, acc);
+                mma(d0, adesc + 2, bdesc + 2, 1u);
+                mma(d0, adesc + 4, bdesc + 4, 1u);
+                mma(d0, adesc + 6, bdesc + 6, 1u);
+              } else {
+                for (uint32_t k = 0; k < nk; ++k) mma(d0, adesc + 2 * k, bdesc + 2 * k, k ? 1u : acc);
               }
-            } else {
-              for (uint32_t k = 0; k < nk; ++k) umma_bf16(d0, adesc + 2 * k, bdesc + 2 * k, idesc, k ? 1u : acc);
-              if (two)
-                for (uint32_t k = 0; k < nk; ++k)
-                  umma_bf16(d1, adesc + t1_off + 2 * k, bdesc + 2 * k, idesc, k ? 1u : acc);
             }
-            umma_commit(sMisc + MISC_B_EMPTY + 8 * sb);
+            if (!free_run) commit(sMisc + MISC_B_EMPTY + 8 * sb);
             if (j + 1 == n_taps) {
-              umma_commit(sMisc + MISC_A_EMPTY + 8 * sa);
-              if (i + 1 == i1) umma_commit(sMisc + MISC_ACC_FULL + 8 * buf);
+              if (!free_run) commit(sMisc + MISC_A_EMPTY + 8 * sa);
+              if (i + 1 == i1) commit(sMisc + MISC_ACC_FULL + 8 * buf);
             }
           }
           __syncwarp();
@@ -361,9 +396,14 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     const int cpg = p.out_fp32 ? 1 : 2;
     const int nchunk_blk = p.blk_ch / 16;
     int n_item = 0;
-    if (p.gdn && grp == 0 && ew == 0) mbar_wait(sMisc + MISC_G_FULL, 0);
+    if (p.gdn && rank == 0 && grp == 0 && ew == 0) mbar_wait_cluster(sMisc + MISC_G_FULL, 0);
+    const uint32_t acc_empty0 = leader_bar(sMisc + MISC_ACC_EMPTY);
+    auto release_acc = [&](int buf) {              // this thread has finished reading the item's accumulators
+      tc_fence_before();
+      if (CG2) mbar_arrive_cluster(acc_empty0 + 8 * buf); else mbar_arrive(acc_empty0 + 8 * buf);
+    };
     for (int u = u_begin; u < u_end; ++n_item) {
-      const Item it = decode_item(p, u, u_end);
+      const Item it = decode_item<CG2>(p, u, u_end, rank);
       u += it.cnt;
       const Variant& v = p.var[it.var];
       const int buf = n_item & 1;
@@ -372,15 +412,15 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
       mbar_wait(sMisc + MISC_ACC_FULL + 8 * buf, (n_item >> 1) & 1);
       tc_fence_after();
       if (p.debug & 16) {                         // timing experiment: release the accumulators untouched
-        tc_fence_before();
-        mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * buf);
+        release_acc(buf);
         continue;
       }
-      for (int tt = 0; tt < it.cnt; ++tt) {
+      for (int tt = 0; tt < it.nslots; ++tt) {
         const uint32_t acc_addr = tmem_base + lane_sel + buf * 256 + tt * 128;
-        const bool last_tile = (tt + 1 == it.cnt);
+        const bool last_tile = (tt + 1 == it.nslots);
+        const bool valid = it.valid[tt];          // CTA pairs: an odd item leaves the peer's last slot without a tile
         float rs = 1.0f;
-        if (p.rowscale) {
+        if (p.rowscale && valid) {
           const int y = it.y0[tt] + (t >> 3), x = it.x0[tt] + (t & 7);
           if (y < p.rs_H && x < p.rs_W)
             rs = __ldg(p.rowscale + (static_cast<size_t>(it.n[tt] * p.rs_H + y) * p.rs_W + x) * p.rs_stride + p.rs_off);
@@ -416,19 +456,27 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
           named_bar_sync(3, EPI_THREADS);
           if (!(p.debug & 8)) {
           if (grp == 0 && ew == 0) {                      // warp-uniform; one elected lane issues the 8 MMAs
+            if (CG2) {        // the pair's norm MMA reads both CTAs' A2: tell the leader this CTA's half is in place
+              if (elect_one()) mbar_arrive_cluster(leader_bar(sMisc + MISC_A2_READY));
+              __syncwarp();
+              if (rank == 0) mbar_wait_cluster(sMisc + MISC_A2_READY, gdn_par);
+            }
             tc_fence_after();
-            if (elect_one()) {
+            if (rank == 0 && elect_one()) {
               // norm = x^2 * gamma'^T written IN PLACE over the accumulator (every thread holds its x in registers)
               const uint32_t d2 = tmem_base + buf * 256 + tt * 128;
               const uint64_t dh = umma_desc_sw128(0);
 #pragma unroll
               for (int kb = 0; kb < 2; ++kb) {
                 const uint64_t a2 = dh | (((sStage + kb * STAGE_BLK_BYTES) & 0x3FFFFu) >> 4);
-                const uint64_t g2 = dh | (((sG + kb * STAGE_BLK_BYTES) & 0x3FFFFu) >> 4);
+                const uint64_t g2 = dh | (((sG + kb * (CG2 ? STAGE_BLK_BYTES / 2 : STAGE_BLK_BYTES)) & 0x3FFFFu) >> 4);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(d2, a2 + 2 * k, g2 + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) {
+                  if (CG2) umma_bf16_cg2(d2, a2 + 2 * k, g2 + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
+                  else umma_bf16(d2, a2 + 2 * k, g2 + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
+                }
               }
-              umma_commit(sMisc + MISC_GDN_BAR);
+              if (CG2) umma_commit_cg2(sMisc + MISC_GDN_BAR); else umma_commit(sMisc + MISC_GDN_BAR);
             }
             __syncwarp();
           }
@@ -440,10 +488,7 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
           tmem_ld16(acc_addr + cb, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
           tmem_ld16(acc_addr + cb + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
           tmem_ld_wait();
-          if (last_tile) {                              // last TMEM read of this item's accumulators
-            tc_fence_before();
-            mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * buf);
-          }
+          if (last_tile) release_acc(buf);              // last TMEM read of this item's accumulators
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 e4 = ld_shared_f4(beta_s + (cb + 4 * q) * 4);
@@ -465,7 +510,7 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
           }
           fence_proxy_async_smem();
           named_bar_sync(pbar, 256);
-          if (leader && !nostore) {
+          if (leader && !nostore && valid) {
             tma_store_5d(&p.tmO, sbuf, p.out_coff + v.out_c0 + it.nt * p.n_tile + 64 * pr, it.x0[tt], v.out_p2, it.y0[tt],
                          it.n[tt]);
             tma_store_commit();
@@ -485,7 +530,7 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
             if (has1) tmem_ld16(acc_addr + c + 16 * k0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
             if (leader) tma_store_wait_read<1>();        // the store issued two blocks ago has left this buffer
             tmem_ld_wait();
-            if (last_read) { tc_fence_before(); mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * buf); }
+            if (last_read) release_acc(buf);
             named_bar_sync(pbar, 256);
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
@@ -521,16 +566,13 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
             }
             fence_proxy_async_smem();
             named_bar_sync(pbar, 256);
-            if (leader && !nostore) {
+            if (leader && !nostore && valid) {
               tma_store_5d(&p.tmO, sb2, p.out_coff + v.out_c0 + it.nt * p.n_tile + c, it.x0[tt], v.out_p2, it.y0[tt],
                            it.n[tt]);
               tma_store_commit();
             }
           }
-          if (last_tile && pr >= nblk) {   // nothing to do for this pair (single-block tile): just release
-            tc_fence_before();
-            mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * buf);
-          }
+          if (last_tile && pr >= nblk) release_acc(buf);   // nothing to do for this group pair (single-block tile)
         }
       }
     }
@@ -538,10 +580,10 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG2) cluster_sync_all(); else __syncthreads();     // no CTA leaves while its peer may still signal it
   if (warp == 3) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CG2) tmem_dealloc_cg2(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -618,12 +660,12 @@ static int encode_xfold4_view(CUtensorMap* tm, const void* base, int n, int h, i
 }
 
 // gamma [128][128] bf16 row-major, loaded as two (64 x 128-row) K-blocks
-static int encode_gamma(CUtensorMap* tm, const void* base) {
+static int encode_gamma(CUtensorMap* tm, const void* base, int box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return MASIC_EDRIVER;
   cuuint64_t dims[2] = {128, 128};
   cuuint64_t strides[1] = {256};
-  cuuint32_t box[2] = {64, 128};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -813,7 +855,9 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   kp.n_img = d.n;
   kp.n_tile = d.n_tile;
   kp.n_ntiles = d.c_out_pad / d.n_tile;
-  kp.idesc = umma_idesc_bf16(d.n_tile);
+  // CTA pairs (tcgen05 cta_group::2): each CTA stages half of every weight k-block and the pair issues M = 256 MMAs
+  { const char* e = getenv("MASIC_CONV_CG2"); kp.cg2 = e ? (atoi(e) != 0) : 0; }
+  kp.idesc = kp.cg2 ? umma_idesc_bf16_m256(d.n_tile) : umma_idesc_bf16(d.n_tile);
 
   // staging block: 128-B swizzled rows when the n-tile is wide enough, else one narrow block
   const int esz = d.out_fp32 ? 4 : 2;
@@ -829,12 +873,13 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
 
   // shared memory carve-up
   kp.strip_bytes = rows * 1024;
-  kp.b_stage_bytes = d.n_tile * 128;
+  kp.b_stage_bytes = (kp.cg2 ? d.n_tile / 2 : d.n_tile) * 128;      // per CTA
   const int a_stage_bytes = kp.pair * kp.strip_bytes;
   // staging: with GDN two blocks (together the A2 operand of the norm MMA, then the output tile);
   // otherwise two per epilogue group so a block's TMA store drains behind the next block
   const int n_stage_blk = d.gdn ? 2 : 4;
-  const int fixed = (d.gdn ? 2 * STAGE_BLK_BYTES : 0) + n_stage_blk * STAGE_BLK_BYTES + MISC_BYTES + 1024 /*align*/;
+  const int gamma_bytes = d.gdn ? (kp.cg2 ? STAGE_BLK_BYTES : 2 * STAGE_BLK_BYTES) : 0;
+  const int fixed = gamma_bytes + n_stage_blk * STAGE_BLK_BYTES + MISC_BYTES + 1024 /*align*/;
   const int budget = 227 * 1024 - fixed;                      // ring bytes
   int sa = 2, sb = 2;
   if (sa * a_stage_bytes + sb * kp.b_stage_bytes > budget) { delete pl; return MASIC_EINVAL; }
@@ -853,7 +898,7 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   kp.a_stages = sa; kp.b_stages = sb;
   kp.smem_b_off = sa * a_stage_bytes;
   kp.smem_g_off = kp.smem_b_off + sb * kp.b_stage_bytes;
-  kp.smem_stage_off = kp.smem_g_off + (d.gdn ? 2 * STAGE_BLK_BYTES : 0);
+  kp.smem_stage_off = kp.smem_g_off + gamma_bytes;
   kp.smem_misc_off = kp.smem_stage_off + n_stage_blk * STAGE_BLK_BYTES;
   pl->smem_bytes = kp.smem_misc_off + MISC_BYTES + 1024;
   if (pl->smem_bytes < 120 * 1024) pl->smem_bytes = 120 * 1024;   // keep 1 CTA/SM: 512 TMEM cols each
@@ -864,10 +909,10 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   else rc = encode_nhwc_view(&kp.tmA, d.in, 2, d.n, d.h_in, d.w_in, d.in_cpitch, split_in, KBLK, rows, true);
   const int ktaps = (d.kind == MASIC_DECONV_S2_SUBPIX) ? 9 : (d.kind == MASIC_CONV_XFOLD4 ? 10 : d.ksize * d.ksize);
   const int ncb = (d.kind == MASIC_CONV_XFOLD4) ? 1 : (d.c_in + KBLK - 1) / KBLK;
-  if (!rc) rc = encode_rows64(&kp.tmB, d.w_packed, (long)ktaps * ncb * d.c_out_pad, d.n_tile);
+  if (!rc) rc = encode_rows64(&kp.tmB, d.w_packed, (long)ktaps * ncb * d.c_out_pad, kp.cg2 ? d.n_tile / 2 : d.n_tile);
   if (!rc) rc = encode_nhwc_view(&kp.tmO, d.out, esz, d.n, out_h, out_w, d.out_cpitch, out_split,
                                  kp.blk_ch, TILE_H, kp.blk_pitch == 128);
-  if (!rc && d.gdn) rc = encode_gamma(&kp.tmG, d.gamma_packed);
+  if (!rc && d.gdn) rc = encode_gamma(&kp.tmG, d.gamma_packed, kp.cg2 ? 64 : 128);
   if (rc) { delete pl; return rc; }
 
   // the programs travel in the kernel parameters (constant bank)
@@ -889,6 +934,12 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   pl->grid = pl->total_work < sms ? pl->total_work : sms;
   { const char* e = getenv("MASIC_CONV_GRID"); if (e && atoi(e) > 0 && atoi(e) < pl->grid) pl->grid = atoi(e); }
+  if (kp.cg2) {          // one work range per CTA pair; a pair handles at least two tiles at a time
+    int pairs = (pl->total_work + 1) / 2;
+    if (pairs > pl->grid / 2) pairs = pl->grid / 2;
+    if (pairs < 1) pairs = 1;
+    pl->grid = 2 * pairs;
+  }
 
   // useful work: live taps only, real channels only
   {
@@ -909,7 +960,9 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
 
   static bool attr_set = false;
   if (!attr_set) {
-    ce = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    ce = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (ce == cudaSuccess)
+      ce = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (ce != cudaSuccess) { delete pl; return (int)ce; }
     attr_set = true;
   }
@@ -919,8 +972,21 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
 
 extern "C" int masic_conv_plan_launch(const MasicConvPlan* pl, void* stream) {
   if (!pl) return MASIC_EINVAL;
-  conv_tc_kernel<<<pl->grid, NUM_THREADS, pl->smem_bytes, static_cast<cudaStream_t>(stream)>>>(pl->kp);
-  return (int)cudaGetLastError();
+  if (!pl->kp.cg2) {
+    conv_tc_kernel<false><<<pl->grid, NUM_THREADS, pl->smem_bytes, static_cast<cudaStream_t>(stream)>>>(pl->kp);
+    return (int)cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(pl->grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = pl->smem_bytes;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, pl->kp);
 }
 
 extern "C" void masic_conv_plan_destroy(MasicConvPlan* pl) {

@@ -40,6 +40,14 @@ LAYERS = {
     "gmm_l1": dict(k=1, h=H // 16, w=W // 16, c_in=1152, c_out=768, n_tile=192, act=ACT_RELU),
     "gmm_l2": dict(k=1, h=H // 16, w=W // 16, c_in=768, c_out=960, n_tile=192, out_fp32=True),
 }
+# MMA-shape microbenchmarks (python tools/conv_perf.py --only mb_): same GEMM, different accumulator widths
+MICRO = {
+    "mb_n64": dict(k=1, h=304, w=272, c_in=512, c_out=512, n_tile=64),
+    "mb_n128": dict(k=1, h=304, w=272, c_in=512, c_out=512, n_tile=128),
+    "mb_n256": dict(k=1, h=304, w=272, c_in=512, c_out=512, n_tile=256),
+    "mb_n16": dict(k=1, h=304, w=272, c_in=512, c_out=16, n_tile=16),
+    "mb_n32": dict(k=1, h=304, w=272, c_in=512, c_out=32, n_tile=32),
+}
 
 
 def build(name, kind=CONV, k=1, stride=1, tap_mask=0, h=0, w=0, c_in=0, c_out=0, n_tile=128, gdn=GDN_NONE,
@@ -81,7 +89,10 @@ def main():
     bw_peak = peaks.get("hbm_gbs", 6650.0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     tot_ms = 0.0
-    for name, kw in LAYERS.items():
+    layers = dict(LAYERS)
+    if a.only and a.only.startswith("mb_"):
+        layers = MICRO
+    for name, kw in layers.items():
         if a.only and a.only not in name:
             continue
         plan = build(name, **kw)
