@@ -183,6 +183,29 @@ int masic_pmf_table_to_cdf(const float* pmf_host, int rows, int row_stride, cons
                            const int32_t* pmf_length_host, int max_length, int precision,
                            int32_t* cdf_host);
 
+/* Per-symbol coder model of the y bitstream (HSIC.compress / decompress, MASIC.py:1006-1043 and :1263-1300):
+ * for every position p < n_pos and listed channel ch_list[j] the K-mixture pmf on the support
+ * s = 0 .. 2*minmax (means shifted by +minmax), clipped to [1/65536, 1], normalised to 65536, rounded and
+ * prefix-summed in float32 like the reference's numpy code.  sigma/mu/weights: NHWC fp32 (n_pos, K*m),
+ * k-major channels.  rows (optional): (n_pos, n_ch, 2*minmax+2) int32, row[0] = 0.  intervals (optional,
+ * needs y_hat_nhwc (n_pos, m)): (n_pos, n_ch, 3) int32 = cdf[sym], cdf[sym+1]-cdf[sym], cdf[-1] for
+ * sym = y_hat + minmax.  All device pointers. */
+int masic_gmm_symbol_cdfs(const float* sigma_nhwc, const float* mu_nhwc, const float* weights_nhwc,
+                          int weights_are_logits, int m, int k, int64_t n_pos, const int32_t* ch_list,
+                          int n_ch, int minmax, float scale_bound, const float* y_hat_nhwc, int32_t* rows,
+                          int32_t* intervals, void* stream);
+
+/* Range coder standing in for the PyPI `range_coder` package the reference calls at MASIC.py:958,1043,1221
+ * (RangeEncoder.encode([symbol], cdf) / RangeDecoder.decode(1, cdf)); HOST buffers.  intervals_host is
+ * (n, 3) int32 as produced by masic_gmm_symbol_cdfs.  The byte format is this library's own. */
+typedef struct MasicRangeDecoder MasicRangeDecoder;
+int masic_range_encode(const int32_t* intervals_host, int64_t n, uint8_t* out_host, int64_t out_cap,
+                       int64_t* out_len);
+int masic_range_decoder_create(const uint8_t* data_host, int64_t len, MasicRangeDecoder** dec_out);
+int masic_range_decode_rows(MasicRangeDecoder* dec, const int32_t* rows_host, int n_rows, int row_len,
+                            int32_t* symbols_host);
+void masic_range_decoder_destroy(MasicRangeDecoder* dec);
+
 /* ------------------------------------------------------------ image domain */
 /* kornia.warp_perspective(src, M, (h_out, w_out)) — kornia 0.5.0, call sites MASIC.py:781,821,833.
  * Step 1: T = inv(N_dst M inv(N_src)) per batch element (invert_m=1 first replaces M by

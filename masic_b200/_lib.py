@@ -93,6 +93,11 @@ def _declare(lib: C.CDLL) -> None:
         "masic_latent_prep": (i, [vp, i64, i, vp, i, vp, i, i, vp, i, i, vp]),
         "masic_pmf_to_quantized_cdf": (i, [vp, i, i, vp]),
         "masic_pmf_table_to_cdf": (i, [vp, i, i, vp, vp, i, i, vp]),
+        "masic_gmm_symbol_cdfs": (i, [vp, vp, vp, i, i, i, i64, vp, i, i, f, vp, vp, vp, vp]),
+        "masic_range_encode": (i, [vp, i64, vp, i64, C.POINTER(i64)]),
+        "masic_range_decoder_create": (i, [vp, i64, C.POINTER(vp)]),
+        "masic_range_decode_rows": (i, [vp, vp, i, i, vp]),
+        "masic_range_decoder_destroy": (None, [vp]),
         "masic_warp_prepare": (i, [vp, i, i, i, i, i, i, vp, vp]),
         "masic_warp_perspective_fwd": (i, [vp, i, i, i, i, i, i, vp, vp, vp, i, i, i, vp]),
         "masic_conv_small_nchw": (i, [vp, i, vp, i, i, i, i, vp, i, vp, i, i, i, i, i, vp, vp, f, vp, vp, i, i, i, vp]),

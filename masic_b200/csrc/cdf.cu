@@ -69,3 +69,92 @@ extern "C" int masic_pmf_table_to_cdf(const float* pmf_host, int rows, int row_s
   }
   return MASIC_OK;
 }
+
+// ------------------------------------------------------------------ range coder of the y bitstream (host)
+// HSIC.compress / decompress drive the PyPI package `range_coder` (RangeEncoder.encode(symbols, cumFreq),
+// MASIC.py:958,1043,1221), which the reference neither vendors nor pins and which is not installable here.
+// This is a plain 32-bit carry-propagating range coder over arbitrary integer cumulative frequencies
+// (total <= 2^16 + alphabet size): same interface, own byte format (the y byte string is NOT
+// comparable with the package's; lengths agree with the ideal code length to a fraction of a percent).
+namespace {
+struct RangeEnc {
+  uint64_t low = 0;
+  uint32_t range = 0xFFFFFFFFu;
+  uint8_t cache = 0;
+  int64_t cache_size = 1;
+  uint8_t* out; int64_t cap; int64_t len = 0; bool overflow = false;
+  void put(uint8_t b) { if (len < cap) out[len] = b; else overflow = true; ++len; }
+  void shift_low() {
+    if (static_cast<uint32_t>(low) < 0xFF000000u || (low >> 32) != 0) {
+      uint8_t c = cache;
+      do { put(static_cast<uint8_t>(c + static_cast<uint8_t>(low >> 32))); c = 0xFF; } while (--cache_size != 0);
+      cache = static_cast<uint8_t>(low >> 24);
+    }
+    ++cache_size;
+    low = (low & 0x00FFFFFFu) << 8;
+  }
+  void encode(uint32_t cum, uint32_t freq, uint32_t total) {
+    const uint32_t r = range / total;
+    low += static_cast<uint64_t>(r) * cum;
+    range = r * freq;
+    while (range < (1u << 24)) { range <<= 8; shift_low(); }
+  }
+  void finish() { for (int i = 0; i < 5; ++i) shift_low(); }
+};
+}  // namespace
+
+struct MasicRangeDecoder {
+  const uint8_t* data; int64_t len; int64_t pos = 0;
+  uint32_t range = 0xFFFFFFFFu, code = 0;
+  uint8_t next() { return pos < len ? data[pos++] : 0; }
+};
+
+extern "C" int masic_range_encode(const int32_t* intervals_host, int64_t n, uint8_t* out_host, int64_t out_cap,
+                                  int64_t* out_len) {
+  if ((!intervals_host && n > 0) || !out_host || !out_len || n < 0) return MASIC_EINVAL;
+  RangeEnc e;
+  e.out = out_host; e.cap = out_cap;
+  for (int64_t i = 0; i < n; ++i) {
+    const int32_t lo = intervals_host[3 * i], fr = intervals_host[3 * i + 1], tot = intervals_host[3 * i + 2];
+    if (lo < 0 || fr <= 0 || tot <= 0 || lo + fr > tot || tot > (1 << 22)) return MASIC_EINVAL;
+    e.encode(static_cast<uint32_t>(lo), static_cast<uint32_t>(fr), static_cast<uint32_t>(tot));
+  }
+  e.finish();
+  *out_len = e.len;
+  return e.overflow ? MASIC_EINVAL : MASIC_OK;
+}
+
+extern "C" int masic_range_decoder_create(const uint8_t* data_host, int64_t len, MasicRangeDecoder** dec_out) {
+  if (!data_host || len < 0 || !dec_out) return MASIC_EINVAL;
+  MasicRangeDecoder* d = new MasicRangeDecoder();
+  d->data = data_host; d->len = len;
+  d->next();                                   // the encoder's first byte is always 0 (initial cache)
+  for (int i = 0; i < 4; ++i) d->code = (d->code << 8) | d->next();
+  *dec_out = d;
+  return MASIC_OK;
+}
+
+// Decode one symbol per CDF row: rows_host is (n_rows, row_len) int32 with row[0] = 0 and row[row_len-1] = total.
+extern "C" int masic_range_decode_rows(MasicRangeDecoder* d, const int32_t* rows_host, int n_rows, int row_len,
+                                       int32_t* symbols_host) {
+  if (!d || !rows_host || !symbols_host || n_rows < 0 || row_len < 2) return MASIC_EINVAL;
+  for (int i = 0; i < n_rows; ++i) {
+    const int32_t* row = rows_host + static_cast<size_t>(i) * row_len;
+    const uint32_t total = static_cast<uint32_t>(row[row_len - 1]);
+    if (total == 0 || total > (1u << 22)) return MASIC_EINVAL;
+    const uint32_t r = d->range / total;
+    uint32_t v = d->code / r;
+    if (v >= total) v = total - 1;
+    int lo = 0, hi = row_len - 1;              // largest s with row[s] <= v
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (static_cast<uint32_t>(row[mid]) <= v) lo = mid; else hi = mid; }
+    const uint32_t cum = static_cast<uint32_t>(row[lo]), freq = static_cast<uint32_t>(row[lo + 1]) - cum;
+    if (freq == 0) return MASIC_EINVAL;
+    d->code -= r * cum;
+    d->range = r * freq;
+    while (d->range < (1u << 24)) { d->code = (d->code << 8) | d->next(); d->range <<= 8; }
+    symbols_host[i] = lo;
+  }
+  return MASIC_OK;
+}
+
+extern "C" void masic_range_decoder_destroy(MasicRangeDecoder* d) { delete d; }

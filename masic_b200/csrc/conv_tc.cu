@@ -83,6 +83,7 @@ struct KParams {
   int n_tiles_total;               // n_spatial * n_var * n_ntiles; tile id u = group * n_spatial + s
   int n_tile;
   int pair;                        // accumulator slots per CTA and work item: 2 (n_tile <= 128) or 1
+  int pdl;                         // 1: launched with programmatic stream serialization
   int cg2;                         // 1: launched as CTA pairs (clusters of 2) issuing tcgen05.mma.cta_group::2
   int strip_bytes, b_stage_bytes, a_stages, b_stages;
   int smem_b_off, smem_g_off, smem_stage_off, smem_misc_off;
@@ -226,6 +227,13 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
   if (CG2) cluster_sync_all(); else __syncthreads();     // barrier inits visible to the peer before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may
+  // overlap the tail of the previous kernel in the stream; from here on we read its output.  The trigger lets
+  // the NEXT kernel's CTAs be scheduled as soon as SMs free up (they block in their own griddepcontrol.wait).
+  if (p.pdl) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
 
   // Role loops are WARP-UNIFORM (all 32 lanes walk them, barrier waits included) and only the
   // issue instructions sit under elect_one(): tcgen05.mma / TMA are uniform-datapath instructions.
@@ -857,6 +865,7 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   kp.n_ntiles = d.c_out_pad / d.n_tile;
   // CTA pairs (tcgen05 cta_group::2): each CTA stages half of every weight k-block and the pair issues M = 256 MMAs
   { const char* e = getenv("MASIC_CONV_CG2"); kp.cg2 = e ? (atoi(e) != 0) : 0; }
+  { const char* e = getenv("MASIC_CONV_PDL"); kp.pdl = e ? (atoi(e) != 0) : 0; }
   kp.idesc = kp.cg2 ? umma_idesc_bf16_m256(d.n_tile) : umma_idesc_bf16(d.n_tile);
 
   // staging block: 128-B swizzled rows when the n-tile is wide enough, else one narrow block
@@ -972,21 +981,27 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
 
 extern "C" int masic_conv_plan_launch(const MasicConvPlan* pl, void* stream) {
   if (!pl) return MASIC_EINVAL;
-  if (!pl->kp.cg2) {
-    conv_tc_kernel<false><<<pl->grid, NUM_THREADS, pl->smem_bytes, static_cast<cudaStream_t>(stream)>>>(pl->kp);
-    return (int)cudaGetLastError();
-  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(pl->grid);
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = pl->smem_bytes;
   cfg.stream = static_cast<cudaStream_t>(stream);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, pl->kp);
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pl->kp.pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (pl->kp.cg2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  if (pl->kp.cg2) return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, pl->kp);
+  return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, pl->kp);
 }
 
 extern "C" void masic_conv_plan_destroy(MasicConvPlan* pl) {

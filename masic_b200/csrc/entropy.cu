@@ -264,6 +264,94 @@ latent_prep_kernel(const float* __restrict__ y, long total, int C, __nv_bfloat16
   }
 }
 
+
+// ------------------------------------------------------------------ per-symbol CDFs of the y bitstream
+// HSIC.compress / decompress (MASIC.py:1006-1043, :1263-1300): for latent element (p, ch) the coder model is
+//   pmf[s]  = sum_k w_k [Phi((.5 - |s - (mu_k + minmax)|)/max(sigma_k, bound)) - Phi((-.5 - |..|)/..)],  s = 0..2*minmax
+//   pmf     = round(clip(pmf, 1/65536, 1) / sum(clip) * 65536)          (float32 throughout)
+//   cdf     = [0] + cumsum(pmf)                                         (its total need not be 65536)
+// One warp per (position, listed channel).  mode 0 writes the whole row (L+1 int32, L = 2*minmax+1), which the
+// decoder searches; mode 1 writes only (cdf[sym], cdf[sym+1]-cdf[sym], cdf[L]) for the known symbol
+// sym = y_hat + minmax — all an encoder needs.
+template <int K>
+__global__ void __launch_bounds__(256)
+gmm_cdf_kernel(const float* __restrict__ sigma, const float* __restrict__ mu, const float* __restrict__ wgt,
+               int w_is_logits, int M, long n_pos, const int32_t* __restrict__ ch_list, int n_ch, int minmax,
+               float scale_bound, const float* __restrict__ y_hat_nhwc, int32_t* __restrict__ rows,
+               int32_t* __restrict__ intervals) {
+  const long wid = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= n_pos * n_ch) return;
+  const long pos = wid / n_ch;
+  const int ch = ch_list[wid - pos * n_ch];
+  const int L = 2 * minmax + 1;
+  float s_k[K], m_k[K], w_k[K];
+  const long base = pos * (long)(M * K) + ch;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    s_k[k] = fmaxf(sigma[base + (long)k * M], scale_bound);
+    m_k[k] = mu[base + (long)k * M] + (float)minmax;
+    w_k[k] = wgt[base + (long)k * M];
+  }
+  if (w_is_logits) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < K; ++k) mx = fmaxf(mx, w_k[k]);
+    float sum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { w_k[k] = expf(w_k[k] - mx); sum += w_k[k]; }
+#pragma unroll
+    for (int k = 0; k < K; ++k) w_k[k] = w_k[k] / sum;
+  }
+  auto pmf_at = [&](int s) -> float {
+    float acc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float v = fabsf((float)s - m_k[k]);
+      const float d = phi((0.5f - v) / s_k[k]) - phi((-0.5f - v) / s_k[k]);
+      acc = (k == 0) ? d * w_k[0] : acc + d * w_k[k];
+    }
+    return fminf(fmaxf(acc, 1.0f / 65536.0f), 1.0f);
+  };
+  // pass 1: sum of the clipped pmf (lane-strided partial sums, then a shuffle tree; fp32 like np.sum)
+  float part = 0.0f;
+  for (int s = lane; s < L; s += 32) part += pmf_at(s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  const float total = part;
+  // pass 2: rounded counts and their running sum, 32 samples at a time
+  const int sym = y_hat_nhwc ? (int)y_hat_nhwc[pos * (long)M + ch] + minmax : -1;
+  int run = 0, lo = 0, fr = 0;
+  int32_t* row = rows ? rows + wid * (long)(L + 1) : nullptr;
+  if (row && lane == 0) row[0] = 0;
+  for (int s0 = 0; s0 < L; s0 += 32) {
+    const int s = s0 + lane;
+    int c = 0;
+    if (s < L) c = (int)rintf(pmf_at(s) / total * 65536.0f);
+    int inc = c;                                  // inclusive scan inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (s < L) {
+      if (row) row[s + 1] = run + inc;
+      if (s == sym) { lo = run + inc - c; fr = c; }
+    }
+    run += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  if (intervals) {
+    // the lane that saw the symbol holds (lo, fr); everyone else holds zeros
+    lo = __reduce_add_sync(0xffffffffu, lo);
+    fr = __reduce_add_sync(0xffffffffu, fr);
+    if (lane == 0) {
+      intervals[wid * 3 + 0] = lo;
+      intervals[wid * 3 + 1] = fr;
+      intervals[wid * 3 + 2] = run;
+    }
+  }
+}
+
 inline View mkview(int layout_nhwc, int C, int P) {
   View v;
   if (layout_nhwc) { v.sn = (long)C * P; v.sc = 1; v.sp = C; }
@@ -343,5 +431,22 @@ extern "C" int masic_latent_prep(const float* y_nhwc, int64_t n_pixels, int c, v
   latent_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       y_nhwc, total, c, static_cast<__nv_bfloat16*>(y_abs_bf16), abs_pitch,
       static_cast<__nv_bfloat16*>(y_round_bf16), rnd_pitch, rnd_coff, rowscale, rs_stride, rs_off);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int masic_gmm_symbol_cdfs(const float* sigma_nhwc, const float* mu_nhwc, const float* weights_nhwc,
+                                     int weights_are_logits, int m, int k, int64_t n_pos,
+                                     const int32_t* ch_list, int n_ch, int minmax, float scale_bound,
+                                     const float* y_hat_nhwc, int32_t* rows, int32_t* intervals, void* stream) {
+  if (!sigma_nhwc || !mu_nhwc || !weights_nhwc || !ch_list || m <= 0 || n_pos < 0 || n_ch < 0 || minmax < 1 ||
+      minmax > 32767 || (!rows && !intervals) || (intervals && !y_hat_nhwc))
+    return MASIC_EINVAL;
+  if (k != 5) return MASIC_ENOSUP;
+  const long warps = n_pos * n_ch;
+  if (warps == 0) return MASIC_OK;
+  const long blocks = (warps * 32 + 255) / 256;
+  gmm_cdf_kernel<5><<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      sigma_nhwc, mu_nhwc, weights_nhwc, weights_are_logits, m, n_pos, ch_list, n_ch, minmax, scale_bound,
+      y_hat_nhwc, rows, intervals);
   return (int)cudaGetLastError();
 }

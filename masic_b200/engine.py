@@ -53,6 +53,8 @@ class HSICEngine:
         self.sched: List[Tuple] = []     # ("run", idx, lane) | ("record", key, lane) | ("wait", key, lane)
         self._lane = 0
         self.plans: Dict[str, ConvPlan] = {}
+        self.buf: Dict[str, torch.Tensor] = {}     # named internal buffers (bitstream.py drives partial runs)
+        self.packs: Dict[str, PackedConv] = {}     # packed weights the per-pixel decoder re-uses
         self._keep = []
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.use_graph = use_graph
@@ -178,6 +180,7 @@ class HSICEngine:
         z_hat = self._buf(B, N, h16 // 4, w16 // 4, dtype=torch.float32)
         z_lik = self._buf(B, N, h16 // 4, w16 // 4, dtype=torch.float32)
         zq = self._buf(B, h16 // 4, w16 // 4, N)
+        self.buf[f"{tag}.z"], self.buf[f"{tag}.zq"] = z, zq
 
         def eb_step():
             check(self.lib.masic_eb_fwd(z.data_ptr(), 1, B, N, hw64, pm, pb, pf, quant.data_ptr(), z_hat.data_ptr(),
@@ -207,6 +210,7 @@ class HSICEngine:
         w0 = torch.cat([self._w(f"{net}.{b}.0.weight") for b in br], dim=cat_dim)
         b0 = torch.cat([self._w(f"{net}.{b}.0.bias") for b in br])
         p0 = PackedConv(ksize=1, c_in=cin, c_out=18 * M, n_tile=192, weight=w0, transposed=t, bias=b0)
+        self.packs[f"{tag}.gmm.l0"] = p0
         l0 = self._buf(B, h16, w16, 18 * M)
         self._conv(f"{tag}.gmm.l0(3 branches)", p0, gmm_in, l0,
                    act=[ACT_RELU] * 6 + [ACT_LEAKY] * 12)
@@ -214,8 +218,10 @@ class HSICEngine:
         l1w = self._buf(B, h16, w16, MK)
 
         def pk(b, i, ci, co):
-            return PackedConv(ksize=1, c_in=ci, c_out=co, n_tile=192, weight=self._w(f"{net}.{b}.{i}.weight"),
-                              transposed=t if i == 2 else False, bias=self._w(f"{net}.{b}.{i}.bias"))
+            pc = PackedConv(ksize=1, c_in=ci, c_out=co, n_tile=192, weight=self._w(f"{net}.{b}.{i}.weight"),
+                            transposed=t if i == 2 else False, bias=self._w(f"{net}.{b}.{i}.bias"))
+            self.packs[f"{tag}.gmm.{b[4:]}.l{i // 2}"] = pc
+            return pc
         self._conv(f"{tag}.gmm.sigma.l1", pk("gmm_sigma", 2, 6 * M, 4 * M), l0, l1, in_coff=0, out_coff=0, act=ACT_RELU)
         self._conv(f"{tag}.gmm.means.l1", pk("gmm_means", 2, 6 * M, 4 * M), l0, l1, in_coff=6 * M, out_coff=4 * M,
                    act=ACT_LEAKY)
@@ -226,6 +232,7 @@ class HSICEngine:
         self._conv(f"{tag}.gmm.sigma.l2", pk("gmm_sigma", 4, 4 * M, MK), l1, sig, in_coff=0, act=ACT_RELU)
         self._conv(f"{tag}.gmm.means.l2", pk("gmm_means", 4, 4 * M, MK), l1, mu, in_coff=4 * M)
         self._conv(f"{tag}.gmm.weights.l2", pk("gmm_weights", 4, MK, MK), l1w, wl)
+        self.buf[f"{tag}.sigma"], self.buf[f"{tag}.mu"], self.buf[f"{tag}.wlogit"] = sig, mu, wl
         return sig, mu, wl
 
     def _gmm_likelihood(self, tag, y, sig, mu, wl, y_hat_nchw, lik_nchw):
@@ -317,6 +324,7 @@ class HSICEngine:
         y1_abs = self._buf(B, h16, w16, M)
         y1_rnd = self._buf(B, h16, w16, M)
         self._latent_prep("L", y1, y1_abs, y1_rnd)
+        self.buf["L.y"], self.buf["L.y_rnd"] = y1, y1_rnd
         self._record("y1")
 
         # ---------------- lane 2: homography products, mask weights, right encoder + hyper chain
@@ -354,9 +362,12 @@ class HSICEngine:
         y2_abs = self._buf(B, h16, w16, M)
         y2_rnd = self._buf(B, h16, w16, M)
         self._latent_prep("R", y2, y2_abs, y2_rnd)
+        self.buf["R.y"], self.buf["R.y_rnd"] = y2, y2_rnd
         gmm2_in = self._buf(B, h16, w16, 5 * M)
+        self.buf["R.gmm_in"] = gmm2_in
         o["z2_hat"], o["lik_z2"] = self._hyper("R", 2, y2_abs, gmm2_in, rowscale=mw)           # params2 * w0
         ctx2 = self._pack("context_prediction2", c_in=M, c_out=2 * M, n_tile=192)
+        self.packs["R.context"] = ctx2
         self._conv("R.context(masked5x5)", ctx2, y2_rnd, gmm2_in, stride=1, tap_mask=MASK_A_5x5, out_coff=2 * M,
                    rowscale=mw, rs_off=1)                                                          # ctx2 * w1
         self._record("right")
@@ -365,8 +376,10 @@ class HSICEngine:
         self._on(1)
         self._wait("y1")
         gmm1_in = self._buf(B, h16, w16, 4 * M)
+        self.buf["L.gmm_in"] = gmm1_in
         o["z1_hat"], o["lik_z1"] = self._hyper("L", 1, y1_abs, gmm1_in)
         ctx1 = self._pack("context_prediction1", c_in=M, c_out=2 * M, n_tile=192)
+        self.packs["L.context"] = ctx1
         self._conv("L.context(masked5x5)", ctx1, y1_rnd, gmm1_in, stride=1, tap_mask=MASK_A_5x5, out_coff=2 * M)
         s1, m1, w1 = self._gmm_net("L", "_h_s1_same_resolution", 4 * M, True, gmm1_in)
         self._gmm_likelihood("L", y1, s1, m1, w1, o["y1_hat"], o["lik_y1"])
@@ -456,6 +469,17 @@ class HSICEngine:
         with torch.cuda.graph(g):
             self._launch_all()
         self.graph = g
+
+    def run_steps(self, select: Callable[[str], bool]) -> List[str]:
+        """Eagerly issue, in plan order on the current stream, the steps whose name `select` accepts
+        (the decoder runs the plan piecewise around its sequential latent decode)."""
+        done = []
+        with torch.cuda.device(self.dev):
+            for name, fn in self.steps:
+                if select(name):
+                    fn()
+                    done.append(name)
+        return done
 
     def profile_steps(self, iters: int = 3) -> List[Tuple[str, float]]:
         """Eager run with a CUDA-event pair around every step; median ms per step."""

@@ -201,6 +201,16 @@ class HSIC(nn.Module):
             "likelihoods": {"y1": c(o["lik_y1"]), "y2": c(o["lik_y2"]), "z1": c(o["lik_z1"]), "z2": c(o["lik_z2"])},
         }
 
+    # ---- bitstreams (MASIC.py:855-1158, :1161-1408)
+    def compress(self, x1, x2, h_matrix, output_name, output_path="", device="cpu"):
+        from .bitstream import compress
+        return compress(self, x1, x2, h_matrix, output_name, output_path, device)
+
+    def decompress(self, x1, x2, h_matrix, output_name, output_path="", device="cpu"):
+        from .bitstream import decompress
+        return decompress(self, x1, x2, h_matrix, output_name, output_path,
+                          None if device == "cpu" else device)
+
 
 def bpp_and_psnr(out: Dict, x1: torch.Tensor, x2: torch.Tensor):
     """The criterion the reference's eval script applies to forward()'s output
