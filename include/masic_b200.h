@@ -253,6 +253,18 @@ int masic_nchw_to_nhwc_bf16(const float* in_nchw, int n, int c, int h, int w, vo
 int masic_nhwc_to_nchw_f32(const float* in_nhwc, int n, int c, int hw, int in_pitch, float* out_nchw,
                            void* stream);
 
+/* ------------------------------------------------------------- criterion */
+/* RateDistortionLoss.forward (coremasic/mywork/test2_real.py:88-114, newtrain_codec_real.py:66-87) on the
+ * output of HSIC.forward: out8 (device, 8 floats) = { bpp of the 4 likelihood tensors (y1,y2,z1,z2 or any order),
+ * mse view 1, mse view 2, bpp total, lambda*255^2*(mse1+mse2)+bpp }.  bpp_t = sum(log lik_t) / (-ln2 * n*h*w);
+ * mse_v = mean over n*c*h*w.  lik4_host / lik_numel4_host are HOST arrays of 4 device pointers / element
+ * counts (a NULL pointer skips the tensor); scratch is masic_rd_metrics_scratch_bytes() of device memory.
+ * Two launches, deterministic (fixed-order fp64 reduction). */
+int64_t masic_rd_metrics_scratch_bytes(void);
+int masic_rd_metrics(const float* const* lik4_host, const int64_t* lik_numel4_host, const float* x1_hat,
+                     const float* x1, const float* x2_hat, const float* x2, int n, int c, int h, int w,
+                     float lmbda, void* scratch, float* out8, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -106,6 +106,8 @@ def _declare(lib: C.CDLL) -> None:
         "masic_softmax_channels": (i, [vp, i, i, i, vp, vp, vp]),
         "masic_nchw_to_nhwc_bf16": (i, [vp, i, i, i, i, vp, i, i, i, vp]),
         "masic_nhwc_to_nchw_f32": (i, [vp, i, i, i, i, vp, vp]),
+        "masic_rd_metrics_scratch_bytes": (i64, []),
+        "masic_rd_metrics": (i, [C.POINTER(vp), C.POINTER(i64), vp, vp, vp, vp, i, i, i, i, f, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)      # AttributeError here = header/library mismatch

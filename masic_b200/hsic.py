@@ -201,6 +201,10 @@ class HSIC(nn.Module):
             "likelihoods": {"y1": c(o["lik_y1"]), "y2": c(o["lik_y2"]), "z1": c(o["lik_z1"]), "z2": c(o["lik_z2"])},
         }
 
+    def pair_stream(self, height: int, width: int, device, depth: int = 2, lmbda: float = 0.0) -> "PairStream":
+        """Pipelined host-to-host evaluation of batch-1 stereo pairs (see PairStream)."""
+        return PairStream(self, height, width, device, depth=depth, lmbda=lmbda)
+
     # ---- bitstreams (MASIC.py:855-1158, :1161-1408)
     def compress(self, x1, x2, h_matrix, output_name, output_path="", device="cpu"):
         from .bitstream import compress
@@ -210,6 +214,85 @@ class HSIC(nn.Module):
         from .bitstream import decompress
         return decompress(self, x1, x2, h_matrix, output_name, output_path,
                           None if device == "cpu" else device)
+
+
+class PairStream:
+    """Pipelined evaluation of stereo pairs that live in HOST memory (the reference's eval loop,
+    coremasic/mywork/test2_real.py:172-252: `d.to(device)` -> `model(d1, d2, h)` -> criterion -> `.item()`).
+
+        ps = model.pair_stream(H, W, device)
+        t0 = ps.submit(x1_host, x2_host, h_host)     # pinned (1,3,H,W) fp32 x2, (1,3,3) fp32
+        t1 = ps.submit(...)                          # its H2D copy overlaps pair 0's kernels
+        bpp, psnr1, psnr2 = ps.result(t0)            # the criterion, read back from the device (32 bytes)
+
+    Two input slots: the H2D copy of pair i+1 runs on a copy stream while pair i runs the engine's CUDA graph
+    on the compute stream; the criterion is one fused reduction pass (masic_rd_metrics) whose 8 floats come
+    back through pinned memory.  `outputs()` exposes the engine's output tensors of the LAST submitted pair.
+    """
+
+    def __init__(self, model: "HSIC", height: int, width: int, device, depth: int = 2, lmbda: float = 0.0):
+        import ctypes as C
+        from . import _lib
+        self.lib = _lib.load()
+        self.dev = torch.device(device)
+        if self.dev.type != "cuda":
+            raise MasicError("PairStream needs a CUDA device: masic_b200 has no CPU fallback")
+        self.model, self.H, self.W, self.lmbda = model, height, width, float(lmbda)
+        self.eng = model.engine_for(1, height, width, self.dev)
+        self.depth = depth
+        with torch.cuda.device(self.dev):
+            self.copy_stream = torch.cuda.Stream(device=self.dev)
+            self.slots = [dict(x1=torch.empty(1, 3, height, width, device=self.dev),
+                               x2=torch.empty(1, 3, height, width, device=self.dev),
+                               h=torch.empty(1, 3, 3, device=self.dev),
+                               res_d=torch.zeros(8, device=self.dev),
+                               res_h=torch.zeros(8).pin_memory(),
+                               copied=torch.cuda.Event(), done=torch.cuda.Event(), busy=False)
+                          for _ in range(depth)]
+            self.scratch = torch.empty(self.lib.masic_rd_metrics_scratch_bytes() // 8, dtype=torch.float64,
+                                       device=self.dev)
+        o = self.eng.out
+        liks = [o["lik_y1"], o["lik_y2"], o["lik_z1"], o["lik_z2"]]
+        self._lik_p = (C.c_void_p * 4)(*[t.data_ptr() for t in liks])
+        self._lik_n = (C.c_int64 * 4)(*[t.numel() for t in liks])
+        self._n = 0
+
+    def submit(self, x1_host: torch.Tensor, x2_host: torch.Tensor, h_host: torch.Tensor) -> int:
+        from ._lib import check
+        s = self.slots[self._n % self.depth]
+        if s["busy"]:
+            s["done"].synchronize()                 # the slot's previous pair has left the engine
+        main = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.copy_stream):
+            s["x1"].copy_(x1_host.reshape(1, 3, self.H, self.W), non_blocking=True)
+            s["x2"].copy_(x2_host.reshape(1, 3, self.H, self.W), non_blocking=True)
+            s["h"].copy_(h_host.reshape(1, 3, 3), non_blocking=True)
+            s["copied"].record(self.copy_stream)
+        main.wait_event(s["copied"])
+        o = self.eng.run(s["x1"], s["x2"], s["h"])
+        check(self.lib.masic_rd_metrics(self._lik_p, self._lik_n, o["x1_hat"].data_ptr(), s["x1"].data_ptr(),
+                                        o["x2_hat"].data_ptr(), s["x2"].data_ptr(), 1, 3, self.H, self.W, self.lmbda,
+                                        self.scratch.data_ptr(), s["res_d"].data_ptr(), main.cuda_stream),
+              "masic_rd_metrics")
+        s["res_h"].copy_(s["res_d"], non_blocking=True)
+        s["done"].record(main)
+        s["busy"] = True
+        self._n += 1
+        return self._n - 1
+
+    def result(self, ticket: int):
+        """(bpp, psnr1_db, psnr2_db, detail) of a submitted pair; blocks until its D2H copy has landed."""
+        if not (self._n - self.depth <= ticket < self._n):
+            raise ValueError(f"ticket {ticket} is no longer (or not yet) in flight")
+        s = self.slots[ticket % self.depth]
+        s["done"].synchronize()
+        r = s["res_h"].tolist()
+        psnr = [10.0 * math.log10(1.0 / m) if m > 0 else float("inf") for m in r[4:6]]
+        return r[6], psnr[0], psnr[1], {"bpp_y1": r[0], "bpp_y2": r[1], "bpp_z1": r[2], "bpp_z2": r[3],
+                                        "mse1": r[4], "mse2": r[5], "loss": r[7]}
+
+    def outputs(self) -> Dict[str, torch.Tensor]:
+        return self.eng.out
 
 
 def bpp_and_psnr(out: Dict, x1: torch.Tensor, x2: torch.Tensor):

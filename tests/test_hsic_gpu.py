@@ -134,3 +134,37 @@ def test_full_size_pair_properties(dev):
     assert bool(torch.isfinite(out["x1_hat"]).all()) and bool(torch.isfinite(out["x2_hat"]).all())
     m = out["x1_mask_R"]
     assert float(m.min()) >= 0.0 and float(m.max()) <= 1.0 + 1e-5
+
+
+def test_pair_stream_matches_forward_and_criterion(dev):
+    """HSIC.pair_stream (pipelined host->host evaluation, fused criterion kernel) returns, for every pair,
+    the numbers the reference's criterion (test2_real.py:88-114) gives on forward()'s output — regardless
+    of how many pairs are in flight."""
+    from masic_b200.hsic import HSIC, bpp_and_psnr
+    torch.manual_seed(0)
+    net = HSIC().eval().to(dev)
+    h, w = 192, 256
+    x1, x2, Hm = _inputs(h, w, seed=11, batch=5)
+    x1p, x2p, Hp = x1.pin_memory(), x2.pin_memory(), Hm.pin_memory()
+    want = []
+    with torch.no_grad():
+        for i in range(5):
+            a, b = x1[i:i + 1].to(dev), x2[i:i + 1].to(dev)
+            out = net(a, b, Hm[i:i + 1].to(dev))
+            want.append([float(v.double()) for v in bpp_and_psnr(out, a, b)] + [out["x2_hat"].clone()])
+    ps = net.pair_stream(h, w, dev, lmbda=0.001)
+    tickets = []
+    got = {}
+    for i in range(5):
+        tickets.append(ps.submit(x1p[i:i + 1], x2p[i:i + 1], Hp[i:i + 1]))
+        if i >= 1:
+            got[i - 1] = ps.result(tickets[i - 1])
+    got[4] = ps.result(tickets[4])
+    assert torch.equal(ps.outputs()["x2_hat"], want[4][3])          # same engine, bit-identical reconstruction
+    for i in range(5):
+        bpp, p1, p2, d = got[i]
+        assert bpp == pytest.approx(want[i][0], rel=2e-6)
+        assert p1 == pytest.approx(want[i][1], abs=1e-4) and p2 == pytest.approx(want[i][2], abs=1e-4)
+        assert d["loss"] == pytest.approx(0.001 * 255 ** 2 * (d["mse1"] + d["mse2"]) + bpp, rel=1e-6)
+    with pytest.raises(ValueError):
+        ps.result(tickets[0])                                        # left the two-slot window

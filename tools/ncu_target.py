@@ -16,6 +16,8 @@ DEFAULT = ["L.g_a.conv1+gdn", "L.g_a.conv2+gdn", "L.g_a.conv4", "L.g_s.deconv3+i
            "L.x1_hat(unshuffle)", "L.entropy_bottleneck", "x1.pack_nhwc", "L.latent_prep"]
 
 want = sys.argv[1:] or DEFAULT
+if want == ["ALL"]:          # every launch of one step (e.g. `--metrics dram__bytes_read.sum,dram__bytes_write.sum`)
+    want = [""]
 torch.manual_seed(0)
 net = HSIC().eval().cuda()
 eng = net.engine_for(1, 1216, 2176, torch.device("cuda:0"))
