@@ -77,7 +77,18 @@ def run_decoder(h, y):
     return h.g_s_conv4(y)
 
 
-def eb_forward_train(p: E.EBParams, z: torch.Tensor, noise: torch.Tensor):
+class _EBLive:
+    """E.EBParams without the detach: the live parameters of an oracle bottleneck (autograd flows)."""
+
+    def __init__(self, eb, detach_net: bool = False):
+        d = (lambda t: t.detach()) if detach_net else (lambda t: t)
+        self.matrices = [d(m) for m in eb._matrices]
+        self.biases = [d(b) for b in eb._biases]
+        self.factors = [d(f) for f in eb._factors]
+        self.quantiles = eb.quantiles
+
+
+def eb_forward_train(p, z: torch.Tensor, noise: torch.Tensor):
     """entropy_models.py:384-411, training: outputs = z + noise; likelihood floored with LowerBound(1e-9)."""
     zc = z.permute(1, 2, 3, 0).contiguous()
     shape = zc.shape
@@ -107,7 +118,7 @@ def forward_train(net: "OH.OracleHSIC", x1, x2, Hm, noise: Dict[str, torch.Tenso
     K = net.K
     y1 = run_encoder(net.encoder1, x1)                                             # :746
     z1 = net._h_a1.encode_hyper(torch.abs(y1))                                     # :747
-    z1_hat, z1_lik = eb_forward_train(net.entropy_bottleneck1.params(), z1, noise["z1"])   # :749
+    z1_hat, z1_lik = eb_forward_train(_EBLive(net.entropy_bottleneck1), z1, noise["z1"])   # :749
     params1 = net.h_s1_up(z1_hat)                                                  # :754
     ctx1 = net.context_prediction1(y1 + noise["y1_ctx"])                           # :755-757
     s1, m1, w1 = OH._run_gmm_net(net._h_s1_same_resolution, torch.cat((params1, ctx1), dim=1))   # :765
@@ -118,7 +129,7 @@ def forward_train(net: "OH.OracleHSIC", x1, x2, Hm, noise: Dict[str, torch.Tenso
     pre = gdn(e2.pre_conv(torch.cat((x1_warp, x2), dim=-3)), e2.pre_gdn)           # :573-574
     y2 = run_encoder(e2, pre)                                                      # :782
     z2 = net._h_a2.encode_hyper(torch.abs(y2))                                     # :786
-    z2_hat, z2_lik = eb_forward_train(net.entropy_bottleneck2.params(), z2, noise["z2"])   # :787
+    z2_hat, z2_lik = eb_forward_train(_EBLive(net.entropy_bottleneck2), z2, noise["z2"])   # :787
     params2 = net.h_s2_up(z2_hat)                                                  # :793
     ctx2 = net.context_prediction2(y2 + noise["y2_ctx"])                           # :794-796
     mask_r, mask_l = OH.warp_masks(x1, Hm)                                         # :803
@@ -150,10 +161,8 @@ def aux_loss(net: "OH.OracleHSIC"):
     matrices/biases/factors detached."""
     total = 0.0
     for eb in (net.entropy_bottleneck1, net.entropy_bottleneck2):
-        p = eb.params()
-        det = E.EBParams([m.detach() for m in p.matrices], [b.detach() for b in p.biases],
-                         [f.detach() for f in p.factors], p.quantiles)
-        total = total + torch.abs(E.eb_logits_cumulative(det, p.quantiles) - eb.target).sum()
+        det = _EBLive(eb, detach_net=True)
+        total = total + torch.abs(E.eb_logits_cumulative(det, eb.quantiles) - eb.target).sum()
     return total
 
 
