@@ -265,6 +265,32 @@ int masic_rd_metrics(const float* const* lik4_host, const int64_t* lik_numel4_ho
                      const float* x1, const float* x2_hat, const float* x2, int n, int c, int h, int w,
                      float lmbda, void* scratch, float* out8, void* stream);
 
+/* ------------------------------------------------------- training: weight gradients */
+/* dW[cl][ch][ky][kx] = sum_{n,p} LO[n,p,cl] * HI[n, stride*p + k - ksize/2, ch]  on the tensor cores
+ * (reference: loss.backward() of newtrain_codec_real.py:134 -> ATen convolution_backward for every
+ * conv()/deconv() of compressai/models/utils.py:128-146).
+ *   nn.Conv2d          (W = (Cout,Cin,k,k)):  LO = dL/d(output), HI = layer input
+ *   nn.ConvTranspose2d (W = (Cin,Cout,k,k)):  LO = layer input,  HI = dL/d(output)
+ * LO is [n][h_lo][w_lo][lo_cpitch], HI is [n][stride*h_lo][stride*w_lo][hi_cpitch], both NHWC bf16; c_lo and c_hi
+ * must be multiples of 64 (channels beyond the real count must hold zeros or are ignored: only dW[c_lo][c_hi] is
+ * written).  dw is fp32 in the torch layout of the layer's weight; accumulate=1 adds to it (a layer that runs
+ * twice per step, encoder1: MASIC.py:746,822).  Deterministic (fixed-order partial sums in `workspace`). */
+typedef struct MasicWgradDesc {
+  int ksize, stride;          /* 1/3/5, 1/2 */
+  uint32_t tap_mask;          /* as MasicConvDesc.tap_mask; masked taps are left untouched in dw */
+  int n, h_lo, w_lo;
+  const void* lo; int lo_cpitch, lo_coff, c_lo;
+  const void* hi; int hi_cpitch, hi_coff, c_hi;
+  float* dw;
+  int accumulate;
+} MasicWgradDesc;
+typedef struct MasicWgradPlan MasicWgradPlan;
+int masic_wgrad_plan_create(const MasicWgradDesc* desc, MasicWgradPlan** plan_out);
+int64_t masic_wgrad_plan_workspace_bytes(const MasicWgradPlan* plan);
+int masic_wgrad_plan_launch(const MasicWgradPlan* plan, void* workspace, void* stream);
+int masic_wgrad_plan_info(const MasicWgradPlan* plan, double* flops, int* n_ctas);
+void masic_wgrad_plan_destroy(MasicWgradPlan* plan);
+
 #ifdef __cplusplus
 }
 #endif

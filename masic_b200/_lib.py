@@ -40,6 +40,16 @@ class ConvDesc(C.Structure):
     ]
 
 
+class WgradDesc(C.Structure):
+    _fields_ = [
+        ("ksize", C.c_int), ("stride", C.c_int), ("tap_mask", C.c_uint32),
+        ("n", C.c_int), ("h_lo", C.c_int), ("w_lo", C.c_int),
+        ("lo", C.c_void_p), ("lo_cpitch", C.c_int), ("lo_coff", C.c_int), ("c_lo", C.c_int),
+        ("hi", C.c_void_p), ("hi_cpitch", C.c_int), ("hi_coff", C.c_int), ("c_hi", C.c_int),
+        ("dw", C.c_void_p), ("accumulate", C.c_int),
+    ]
+
+
 _lib = None
 
 
@@ -106,6 +116,11 @@ def _declare(lib: C.CDLL) -> None:
         "masic_softmax_channels": (i, [vp, i, i, i, vp, vp, vp]),
         "masic_nchw_to_nhwc_bf16": (i, [vp, i, i, i, i, vp, i, i, i, vp]),
         "masic_nhwc_to_nchw_f32": (i, [vp, i, i, i, i, vp, vp]),
+        "masic_wgrad_plan_create": (i, [C.POINTER(WgradDesc), C.POINTER(vp)]),
+        "masic_wgrad_plan_workspace_bytes": (i64, [vp]),
+        "masic_wgrad_plan_launch": (i, [vp, vp, vp]),
+        "masic_wgrad_plan_info": (i, [vp, C.POINTER(C.c_double), C.POINTER(i)]),
+        "masic_wgrad_plan_destroy": (None, [vp]),
         "masic_rd_metrics_scratch_bytes": (i64, []),
         "masic_rd_metrics": (i, [C.POINTER(vp), C.POINTER(i64), vp, vp, vp, vp, i, i, i, i, f, vp, vp, vp]),
     }

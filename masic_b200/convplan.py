@@ -156,6 +156,52 @@ class ConvPlan:
             self._h = None
 
 
+class WgradPlan:
+    """Tensor-core weight gradient of one conv / transposed-conv layer (MasicWgradPlan of the C ABI).
+    `lo` / `hi` are the bound NHWC bf16 buffers (see include/masic_b200.h), `dw` the fp32 torch-layout gradient."""
+
+    _ws: dict = {}          # one shared workspace per device, grown to the largest plan
+
+    def __init__(self, *, ksize: int, stride: int, lo: torch.Tensor, c_lo: int, hi: torch.Tensor, c_hi: int,
+                 dw: torch.Tensor, lo_coff: int = 0, hi_coff: int = 0, tap_mask: int = 0, accumulate: bool = False):
+        lib = _lib.load()
+        for t in (lo, hi):
+            assert t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 4 and t.is_contiguous()
+        assert dw.is_cuda and dw.dtype == torch.float32 and dw.is_contiguous()
+        n, h_lo, w_lo, lo_cp = lo.shape
+        assert hi.shape[0] == n and hi.shape[1] == h_lo * stride and hi.shape[2] == w_lo * stride, (lo.shape, hi.shape)
+        d = _lib.WgradDesc()
+        d.ksize, d.stride, d.tap_mask = ksize, stride, tap_mask
+        d.n, d.h_lo, d.w_lo = n, h_lo, w_lo
+        d.lo, d.lo_cpitch, d.lo_coff, d.c_lo = lo.data_ptr(), lo_cp, lo_coff, c_lo
+        d.hi, d.hi_cpitch, d.hi_coff, d.c_hi = hi.data_ptr(), hi.shape[3], hi_coff, c_hi
+        d.dw, d.accumulate = dw.data_ptr(), int(accumulate)
+        self._desc, self.lo, self.hi, self.dw = d, lo, hi, dw
+        h = C.c_void_p()
+        check(lib.masic_wgrad_plan_create(C.byref(d), C.byref(h)), "masic_wgrad_plan_create")
+        self._h, self._lib = h, lib
+        fl, nc = C.c_double(), C.c_int()
+        lib.masic_wgrad_plan_info(h, C.byref(fl), C.byref(nc))
+        self.flops, self.n_ctas = fl.value, nc.value
+        need = lib.masic_wgrad_plan_workspace_bytes(h)
+        key = lo.device.index
+        cur = WgradPlan._ws.get(key)
+        if cur is None or cur.numel() * 4 < need:
+            WgradPlan._ws[key] = torch.empty(need // 4 + 1024, dtype=torch.float32, device=lo.device)
+        self._key = key
+
+    def launch(self, stream: Optional[int] = None) -> None:
+        ws = WgradPlan._ws[self._key]
+        check(self._lib.masic_wgrad_plan_launch(self._h, ws.data_ptr(), _stream() if stream is None else stream),
+              "masic_wgrad_plan_launch")
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.masic_wgrad_plan_destroy(h)
+            self._h = None
+
+
 def conv_direct(x: torch.Tensor, c_in: int, weight: torch.Tensor, *, transposed: bool, ksize: int,
                 stride: int, tap_mask: int = 0, bias: Optional[torch.Tensor] = None,
                 in_coff: int = 0, round_w_bf16: bool = True) -> torch.Tensor:
