@@ -291,6 +291,87 @@ int masic_wgrad_plan_launch(const MasicWgradPlan* plan, void* workspace, void* s
 int masic_wgrad_plan_info(const MasicWgradPlan* plan, double* flops, int* n_ctas);
 void masic_wgrad_plan_destroy(MasicWgradPlan* plan);
 
+/* 3-channel side of g_a_conv1 (Conv2d 3->128) / g_s_conv4 (ConvTranspose2d 128->3), k = 5, stride 2 (CUDA cores):
+ * dw[cl][ci][ky][kx] += sum LO[n,p,cl] * HI[n][ci][2p + k - 2];  LO NHWC bf16 [n][h_lo][w_lo][lo_pitch],
+ * HI NCHW fp32 [n][c_hi<=4][2 h_lo][2 w_lo].  Accumulates (atomics) into dw. */
+int masic_wgrad_small(const void* lo_bf16, int lo_pitch, int c_lo, const float* hi_nchw, int c_hi, int n,
+                      int h_lo, int w_lo, float* dw_accum, void* stream);
+
+/* --------------------------------------------- training: entropy models (forward + local backward) */
+/* GaussianMixtureConditional_gf.forward in train() mode (entropy_models.py:808-858, 'noise' quantisation :103-110)
+ * fused with the backward of the rate term  lik_grad_scale * sum(log lik),  lik_grad_scale = -1/(ln2 * N*H*W)
+ * (newtrain_codec_real.py:73-76).  All tensors NHWC: y/noise/lik/y_hat/dy [n_pixels][m]; sigma (post-ReLU), mu,
+ * wlogits and the bf16 gradients [n_pixels][k*m], k-major.  dsigma already includes the final ReLU of the sigma
+ * branch and the LowerBound(0.11) gradient rule (bound_ops.py:40-42); dwl is w.r.t. the logits (softmax fused). */
+int masic_gmm_likelihood_train(const float* y, const float* noise, const float* sigma, const float* mu,
+                               const float* wlogits, int64_t n_pixels, int m, int k, float scale_bound,
+                               float lik_grad_scale, float* lik, void* y_hat_bf16, int bf_pitch, float* y_hat,
+                               float* dy, void* dsigma_bf16, void* dmu_bf16, void* dwl_bf16, void* stream);
+/* EntropyBottleneck.forward in train() mode (entropy_models.py:384-411) + backward of its rate term.
+ * z/noise/dz NHWC fp32 [n*hw][c]; z_hat/lik NCHW fp32; zq NHWC bf16.  dparams [c][58] = gradients w.r.t. the RAW
+ * parameters, per channel: matrices 0..4 (3,9,9,9,3 values, row-major (out,in)), biases 0..4 (3,3,3,3,1),
+ * factors 0..3 (3 each). */
+int masic_eb_train(const float* z_nhwc, const float* noise_nhwc, int n, int c, int hw,
+                   const float* const* matrices, const float* const* biases, const float* const* factors,
+                   float lik_grad_scale, float* z_hat_nchw, float* lik_nchw, void* zq_bf16, int bf_pitch,
+                   float* dz_nhwc, float* dparams, void* stream);
+/* EntropyBottleneck.loss (entropy_models.py:345-348): *loss += sum |logits(quantiles) - target|, dquantiles (c,1,3). */
+int masic_eb_aux_loss(const float* quantiles, int c, const float* const* matrices, const float* const* biases,
+                      const float* const* factors, const float* target3_host, float* loss, float* dquantiles,
+                      void* stream);
+
+/* ------------------------------------- training: element-wise backward over NHWC bf16 [pixels][pitch] */
+/* g *= act'(y) in place (ReLU / LeakyReLU(0.01) after conv()/deconv()); bias_grad[c] += sum_p g (may be NULL). */
+int masic_act_bwd_bias(void* g_bf16, int g_pitch, int g_coff, const void* y_bf16, int y_pitch, int y_coff,
+                       int act, int64_t n_pixels, int c, float* bias_grad, void* stream);
+/* GDN.forward as separate steps (gdn.py:77-92) keeping x and norm for the backward: sq = x^2; (norm = 1x1 conv on
+ * the tensor cores); y = x * rsqrt(norm) (inverse: x * sqrt(norm)). */
+int masic_gdn_square(const void* x_bf16, void* sq_bf16, int64_t numel, void* stream);
+int masic_gdn_apply(const void* x_bf16, const float* norm, int inverse, void* y_bf16, int64_t numel, void* stream);
+/* GDN backward: (a) t = dL/dnorm, written to t_bf16; g := g * norm^(-+1/2) in place; dbeta'[c] += sum_p t.
+ * (b) after v = gamma'^T t (1x1 conv): u := u + 2 x v in place (= dL/dx); dbias[c] += sum_p (may be NULL). */
+int masic_gdn_bwd_a(void* g_bf16, const void* x_bf16, const float* norm, int inverse, void* t_bf16,
+                    int64_t n_pixels, int c, float* dbeta_prime, void* stream);
+int masic_gdn_bwd_b(void* u_bf16, const void* x_bf16, const float* v, int64_t n_pixels, int c, float* dbias,
+                    void* stream);
+/* NonNegativeParametrizer backward with LowerBound's rule (parametrizers.py:61-64, bound_ops.py:40-42). */
+int masic_reparam_bwd(const float* dprime, const float* stored, int n, float minimum, int accumulate,
+                      float* dstored, void* stream);
+int masic_latent_prep_train(const float* y_nhwc, const float* noise_nhwc, int64_t n_pixels, int c,
+                            void* y_abs_bf16, int abs_pitch, void* y_noisy_bf16, int noisy_pitch, void* stream);
+/* dy = dy_lik + d_dec + d_ctx + sign(y) * d_abs (NULL sources are skipped) -> bf16 */
+int masic_latent_merge_bwd(const float* y_nhwc, const float* dy_lik, const void* d_dec_bf16, const void* d_ctx_bf16,
+                           const void* d_abs_bf16, int64_t numel, void* dy_bf16, void* stream);
+int masic_add_f32_bf16(const float* a, const void* b_bf16, int64_t numel, void* out_bf16, void* stream);
+/* cat(params2*w0, ctx2*w1, (y1w+noise)*w2) (MASIC.py:827) and its backward; mask weights NHWC [pixels][3]. */
+int masic_mask_fuse_fwd(const void* p2_bf16, const void* c2_bf16, int c2, const float* y1w_nhwc,
+                        const float* noise_nhwc, int m, const float* mask_weights_nhwc, int64_t n_pixels,
+                        void* fused_bf16, void* stream);
+int masic_mask_fuse_bwd(const void* g_bf16, const void* p2_bf16, const void* c2_bf16, int c2, const float* y1w_nhwc,
+                        const float* noise_nhwc, int m, const float* mask_weights_nhwc, int64_t n_pixels,
+                        void* dp2_bf16, void* dc2_bf16, void* dy1w_bf16, float* dmask_weights_nhwc, void* stream);
+
+/* --------------------------------------------------- training: image domain (NCHW fp32, <= 8 channels) */
+/* g = scale * (x_hat - x) [+ addend]: nn.MSELoss backward (newtrain_codec_real.py:78-79). */
+int masic_mse_grad(const float* x_hat, const float* x, const float* addend, float scale, int64_t numel, float* g,
+                   void* stream);
+/* kornia.warp_perspective backward w.r.t. src (g = g0 [+ g1]); dsrc must be zeroed by the caller (atomics). */
+int masic_warp_perspective_bwd(const float* g0, const float* g1, int n, int c, int h, int w, int h_out, int w_out,
+                               const double* t_prepared, float* dsrc_zeroed, void* stream);
+/* backward of masic_conv_small_nchw: g_out is dL/d(output); act_out != NULL masks it with (act_out > 0) (ReLU);
+ * din0/din1 (optional) receive dL/d(inputs); dweight/dbias (optional, zeroed by the caller) accumulate. */
+int masic_conv_small_bwd(const float* in0, int c0, const float* in1, int c1, int n, int h, int w,
+                         const float* weight, int transposed_s1, int c_out, int ksize, int stride,
+                         const float* g_out, const float* act_out, float* din0, float* din1,
+                         float* dweight_zeroed, float* dbias_zeroed, void* stream);
+/* backward of masic_gdn_nchw: dx, and the gradients of beta' / gamma' (accumulated; chain with masic_reparam_bwd). */
+int masic_gdn_small_bwd(const float* x, const float* g, int n, int c, int hw, const float* beta,
+                        const float* gamma, float beta_min, int inverse, float* dx, float* dbeta_prime_zeroed,
+                        float* dgamma_prime_zeroed, void* stream);
+int masic_softmax_channels_bwd(const float* w_nhwc, const float* dw_nhwc, int n, int c, int hw,
+                               float* dlogits_nchw, void* stream);
+int masic_colsum_nchw(const float* g, int n, int c, int64_t hw, float* out_accum, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

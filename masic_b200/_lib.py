@@ -121,6 +121,28 @@ def _declare(lib: C.CDLL) -> None:
         "masic_wgrad_plan_launch": (i, [vp, vp, vp]),
         "masic_wgrad_plan_info": (i, [vp, C.POINTER(C.c_double), C.POINTER(i)]),
         "masic_wgrad_plan_destroy": (None, [vp]),
+        "masic_wgrad_small": (i, [vp, i, i, vp, i, i, i, i, vp, vp]),
+        "masic_gmm_likelihood_train": (i, [vp, vp, vp, vp, vp, i64, i, i, f, f, vp, vp, i, vp, vp, vp, vp, vp, vp]),
+        "masic_eb_train": (i, [vp, vp, i, i, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), f, vp, vp, vp, i,
+                               vp, vp, vp]),
+        "masic_eb_aux_loss": (i, [vp, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(f), vp, vp, vp]),
+        "masic_act_bwd_bias": (i, [vp, i, i, vp, i, i, i, i64, i, vp, vp]),
+        "masic_gdn_square": (i, [vp, vp, i64, vp]),
+        "masic_gdn_apply": (i, [vp, vp, i, vp, i64, vp]),
+        "masic_gdn_bwd_a": (i, [vp, vp, vp, i, vp, i64, i, vp, vp]),
+        "masic_gdn_bwd_b": (i, [vp, vp, vp, i64, i, vp, vp]),
+        "masic_reparam_bwd": (i, [vp, vp, i, f, i, vp, vp]),
+        "masic_latent_prep_train": (i, [vp, vp, i64, i, vp, i, vp, i, vp]),
+        "masic_latent_merge_bwd": (i, [vp, vp, vp, vp, vp, i64, vp, vp]),
+        "masic_add_f32_bf16": (i, [vp, vp, i64, vp, vp]),
+        "masic_mask_fuse_fwd": (i, [vp, vp, i, vp, vp, i, vp, i64, vp, vp]),
+        "masic_mask_fuse_bwd": (i, [vp, vp, vp, i, vp, vp, i, vp, i64, vp, vp, vp, vp, vp]),
+        "masic_mse_grad": (i, [vp, vp, vp, f, i64, vp, vp]),
+        "masic_warp_perspective_bwd": (i, [vp, vp, i, i, i, i, i, i, vp, vp, vp]),
+        "masic_conv_small_bwd": (i, [vp, i, vp, i, i, i, i, vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]),
+        "masic_gdn_small_bwd": (i, [vp, vp, i, i, i, vp, vp, f, i, vp, vp, vp, vp]),
+        "masic_softmax_channels_bwd": (i, [vp, vp, i, i, i, vp, vp]),
+        "masic_colsum_nchw": (i, [vp, i, i, i64, vp, vp]),
         "masic_rd_metrics_scratch_bytes": (i64, []),
         "masic_rd_metrics": (i, [C.POINTER(vp), C.POINTER(i64), vp, vp, vp, vp, i, i, i, i, f, vp, vp, vp]),
     }

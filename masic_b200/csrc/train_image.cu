@@ -1,0 +1,395 @@
+// train_image.cu — image-domain backward kernels of the training step (NCHW fp32, <= 8 channels), sm_100a.
+//
+// Replaces the autograd backward (coremasic/mywork/newtrain_codec_real.py:134) of:
+//   nn.MSELoss in RateDistortionLoss                     newtrain_codec_real.py:78-79
+//   kornia.warp_perspective (F.grid_sample, bilinear, zeros, align_corners=True) w.r.t. its source   MASIC.py:821,833
+//   Encoder2.pre_conv / Decoder2.after_conv / mask2weights.maskconv  MASIC.py:559,600,475-488 (conv_small_kernel's layers)
+//   GDN(3) / GDN(3, inverse)  (pre_gdn, after_gdn)       MASIC.py:560,599; compressai/layers/gdn.py:77-92
+//   the softmax over the 3 mask weights                  MASIC.py:497-502
+//   g_a_conv1 (3 -> 128) and g_s_conv4 (128 -> 3) weight gradients (3-channel side: too thin for the tensor cores)
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/masic_b200.h"
+
+namespace {
+
+constexpr int MAXC = 8;
+
+// g = scale * (xh - x) [+ addend]
+__global__ void __launch_bounds__(256)
+mse_grad_kernel(const float* __restrict__ xh, const float* __restrict__ x, const float* __restrict__ addend, float scale,
+                long n, float* __restrict__ g) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = scale * (xh[i] - x[i]);
+  if (addend) v += addend[i];
+  g[i] = v;
+}
+
+// ---------------------------------------------------------------- warp backward (scatter into the source grid)
+__global__ void __launch_bounds__(256)
+warp_bwd_kernel(const float* __restrict__ g0, const float* __restrict__ g1, int n, int c, int h, int w, int ho, int wo,
+                const double* __restrict__ T, float* __restrict__ dsrc) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int b = blockIdx.z;
+  if (x >= wo) return;
+  const double* t = T + b * 9;
+  // same coordinate chain as warp_kernel (image.cu)
+  const double xn = ((double)x / (double)(wo - 1) - 0.5) * 2.0;
+  const double yn = ((double)y / (double)(ho - 1) - 0.5) * 2.0;
+  const double q0 = xn * t[0] + yn * t[1] + t[2];
+  const double q1 = xn * t[3] + yn * t[4] + t[5];
+  const double q2 = xn * t[6] + yn * t[7] + t[8];
+  const double den = fabs(q2) >= 0.25 ? q2 : q2 + 1e-8;
+  const double sc = fabs(q2) > 1e-8 ? 1.0 / den : 1.0;
+  const double gx = q0 * sc, gy = q1 * sc;
+  const double ixd = ((gx + 1.0) / 2.0) * (double)(w - 1);
+  const double iyd = ((gy + 1.0) / 2.0) * (double)(h - 1);
+  const double fxd = floor(ixd), fyd = floor(iyd);
+  const float ix = (float)(ixd - fxd), iy = (float)(iyd - fyd);
+  const float wx1 = ix, wx0 = 1.0f - ix, wy1 = iy, wy0 = 1.0f - iy;
+  const bool finite = fabs(ixd) < 1e9 && fabs(iyd) < 1e9;
+  const int x0 = finite ? (int)fxd : -10, y0 = finite ? (int)fyd : -10;
+  const bool in_x0 = x0 >= 0 && x0 < w, in_x1 = x0 + 1 >= 0 && x0 + 1 < w;
+  const bool in_y0 = y0 >= 0 && y0 < h, in_y1 = y0 + 1 >= 0 && y0 + 1 < h;
+  for (int ch = 0; ch < c; ++ch) {
+    const long o = ((long)(b * c + ch) * ho + y) * wo + x;
+    float gv = g0[o];
+    if (g1) gv += g1[o];
+    float* s = dsrc + ((long)(b * c + ch) * h) * w;
+    if (in_y0 && in_x0) atomicAdd(s + (long)y0 * w + x0, gv * wx0 * wy0);
+    if (in_y0 && in_x1) atomicAdd(s + (long)y0 * w + x0 + 1, gv * wx1 * wy0);
+    if (in_y1 && in_x0) atomicAdd(s + (long)(y0 + 1) * w + x0, gv * wx0 * wy1);
+    if (in_y1 && in_x1) atomicAdd(s + (long)(y0 + 1) * w + x0 + 1, gv * wx1 * wy1);
+  }
+}
+
+// ---------------------------------------------------------------- small conv backward
+// Forward (conv_small_kernel): conv:   out[co][oy][ox] = b + sum in[ci][oy*s+ky-pad][ox*s+kx-pad] W[co][ci][ky][kx]
+//                              transposed (s = 1): out[co][y][x] = b + sum in[ci][y+pad-ky][x+pad-kx] W[ci][co][ky][kx]
+// g is dL/d(out) BEFORE the activation mask; act_out (forward output, post-ReLU) masks it: g' = g * (act_out > 0).
+struct SCArgs {
+  const float* in0; const float* in1; int c0, c1;
+  int n, h, w, ho, wo, c_out, k, stride, transposed;
+  const float* g; const float* act_out;
+  const float* wt;
+};
+__device__ __forceinline__ float sc_in(const SCArgs& a, int b, int ci, int y, int x) {
+  if (y < 0 || y >= a.h || x < 0 || x >= a.w) return 0.0f;
+  return ci < a.c0 ? a.in0[((long)(b * a.c0 + ci) * a.h + y) * a.w + x]
+                   : a.in1[((long)(b * a.c1 + ci - a.c0) * a.h + y) * a.w + x];
+}
+__device__ __forceinline__ float sc_g(const SCArgs& a, int b, int co, int y, int x) {
+  if (y < 0 || y >= a.ho || x < 0 || x >= a.wo) return 0.0f;
+  const long o = ((long)(b * a.c_out + co) * a.ho + y) * a.wo + x;
+  const float v = a.g[o];
+  return (a.act_out && !(a.act_out[o] > 0.0f)) ? 0.0f : v;
+}
+
+// grid (n_weights + c_out, SPLIT): block b handles weight element (or bias) `blockIdx.x` over a slab of output pixels
+__global__ void __launch_bounds__(256)
+small_conv_wgrad_kernel(const SCArgs a, float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float red[8];
+  const int cin = a.c0 + a.c1, kk = a.k * a.k, pad = a.k / 2;
+  const int nw = a.c_out * cin * kk;
+  const int e = blockIdx.x;
+  const long npix = (long)a.n * a.ho * a.wo;
+  const long per = (npix + gridDim.y - 1) / gridDim.y;
+  const long p0 = per * blockIdx.y, p1 = min(npix, p0 + per);
+  float s = 0.0f;
+  if (e < nw) {
+    const int tap = e % kk;
+    int co, ci;
+    if (a.transposed) { co = (e / kk) % a.c_out; ci = e / (kk * a.c_out); }
+    else { ci = (e / kk) % cin; co = e / (kk * cin); }
+    const int ky = tap / a.k, kx = tap % a.k;
+    for (long p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+      const int ox = (int)(p % a.wo);
+      const long r = p / a.wo;
+      const int oy = (int)(r % a.ho), b = (int)(r / a.ho);
+      const float gv = sc_g(a, b, co, oy, ox);
+      if (gv != 0.0f) {
+        const int iy = a.transposed ? oy + pad - ky : oy * a.stride + ky - pad;
+        const int ix = a.transposed ? ox + pad - kx : ox * a.stride + kx - pad;
+        s += gv * sc_in(a, b, ci, iy, ix);
+      }
+    }
+  } else {
+    const int co = e - nw;
+    for (long p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+      const int ox = (int)(p % a.wo);
+      const long r = p / a.wo;
+      s += sc_g(a, (int)(r / a.ho), co, (int)(r % a.ho), ox);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    if (e < nw) atomicAdd(dw + e, t);
+    else if (db) atomicAdd(db + (e - nw), t);
+  }
+}
+
+// one thread per input pixel: d_in[ci] for every input channel (written to din0 / din1; either may be NULL)
+__global__ void __launch_bounds__(128)
+small_conv_dgrad_kernel(const SCArgs a, float* __restrict__ din0, float* __restrict__ din1) {
+  __shared__ float s_w[MAXC * MAXC * 25];
+  const int cin = a.c0 + a.c1, kk = a.k * a.k, pad = a.k / 2;
+  for (int i = threadIdx.x; i < a.c_out * cin * kk; i += blockDim.x) s_w[i] = a.wt[i];
+  __syncthreads();
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, b = blockIdx.z;
+  if (x >= a.w) return;
+  float acc[MAXC];
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) acc[i] = 0.0f;
+  for (int ky = 0; ky < a.k; ++ky)
+    for (int kx = 0; kx < a.k; ++kx) {
+      int oy, ox;
+      if (a.transposed) { oy = y - pad + ky; ox = x - pad + kx; }
+      else {
+        const int ty = y + pad - ky, tx = x + pad - kx;
+        if (ty < 0 || tx < 0 || (ty % a.stride) || (tx % a.stride)) continue;
+        oy = ty / a.stride; ox = tx / a.stride;
+      }
+      for (int co = 0; co < a.c_out; ++co) {
+        const float gv = sc_g(a, b, co, oy, ox);
+        if (gv == 0.0f) continue;
+        for (int ci = 0; ci < cin; ++ci) {
+          const float wv = a.transposed ? s_w[((ci * a.c_out + co) * a.k + ky) * a.k + kx]
+                                        : s_w[((co * cin + ci) * a.k + ky) * a.k + kx];
+          acc[ci] += gv * wv;
+        }
+      }
+    }
+  for (int ci = 0; ci < cin; ++ci) {
+    if (ci < a.c0) { if (din0) din0[((long)(b * a.c0 + ci) * a.h + y) * a.w + x] = acc[ci]; }
+    else if (din1) din1[((long)(b * a.c1 + ci - a.c0) * a.h + y) * a.w + x] = acc[ci];
+  }
+}
+
+// ---------------------------------------------------------------- GDN over <= 8 channels, backward (NCHW fp32)
+// dx written; dbeta' [c] and dgamma' [c][c] accumulated (atomics) — chain to the stored parameters with masic_reparam_bwd
+__global__ void __launch_bounds__(256)
+gdn_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, int n, int c, long hw,
+                     const float* __restrict__ beta, const float* __restrict__ gamma, float beta_bound, float gamma_bound,
+                     float pedestal, int inverse, float* __restrict__ dx, float* __restrict__ dbeta, float* __restrict__ dgamma) {
+  __shared__ float s_b[MAXC], s_g[MAXC * MAXC];
+  __shared__ float red[8][MAXC + MAXC * MAXC];
+  if (threadIdx.x < c) { const float v = fmaxf(beta[threadIdx.x], beta_bound); s_b[threadIdx.x] = v * v - pedestal; }
+  if (threadIdx.x < c * c) { const float v = fmaxf(gamma[threadIdx.x], gamma_bound); s_g[threadIdx.x] = v * v - pedestal; }
+  __syncthreads();
+  const long total = (long)n * hw;
+  float ab[MAXC], ag[MAXC * MAXC];
+  for (int i = 0; i < MAXC; ++i) ab[i] = 0.0f;
+  for (int i = 0; i < MAXC * MAXC; ++i) ag[i] = 0.0f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / hw);
+    const long p = i - b * hw;
+    float xv[MAXC], x2[MAXC], t[MAXC], gv[MAXC], nr[MAXC];
+    for (int j = 0; j < c; ++j) {
+      xv[j] = x[((long)b * c + j) * hw + p]; x2[j] = xv[j] * xv[j];
+      gv[j] = g[((long)b * c + j) * hw + p];
+    }
+    for (int k = 0; k < c; ++k) {
+      float nn = s_b[k];
+      for (int j = 0; j < c; ++j) nn += s_g[k * c + j] * x2[j];
+      nr[k] = nn;
+      const float r = rsqrtf(nn);
+      t[k] = inverse ? 0.5f * gv[k] * xv[k] * r : -0.5f * gv[k] * xv[k] * r * r * r;
+      ab[k] += t[k];
+      for (int j = 0; j < c; ++j) ag[k * c + j] += t[k] * x2[j];
+    }
+    for (int j = 0; j < c; ++j) {
+      float v = 0.0f;
+      for (int k = 0; k < c; ++k) v += s_g[k * c + j] * t[k];
+      const float u = inverse ? gv[j] * sqrtf(nr[j]) : gv[j] * rsqrtf(nr[j]);
+      dx[((long)b * c + j) * hw + p] = u + 2.0f * xv[j] * v;
+    }
+  }
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  for (int i = 0; i < c + c * c; ++i) {
+    float a = i < c ? ab[i] : ag[i - c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) red[wp][i] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < c + c * c) {
+    float s = 0.0f;
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    if (threadIdx.x < c) atomicAdd(dbeta + threadIdx.x, s);
+    else atomicAdd(dgamma + threadIdx.x - c, s);
+  }
+}
+
+// softmax over c channels, backward: w NHWC [P][c], dw NHWC [P][c] -> dlogits NCHW [n][c][hw]
+__global__ void __launch_bounds__(256)
+softmax_bwd_kernel(const float* __restrict__ w, const float* __restrict__ dw, int n, int c, long hw,
+                   float* __restrict__ dl) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= (long)n * hw) return;
+  const int b = (int)(i / hw);
+  const long p = i - b * hw;
+  float dot = 0.0f;
+  for (int j = 0; j < c; ++j) dot += w[i * c + j] * dw[i * c + j];
+  for (int j = 0; j < c; ++j) dl[((long)b * c + j) * hw + p] = w[i * c + j] * (dw[i * c + j] - dot);
+}
+
+// dW[cl][ci][ky][kx] += sum_{n,p} LO[n,p,cl] * HI[n][ci][2p + k - 2]   (k = 5, stride 2, c_hi <= 4)
+// LO NHWC bf16 [n][h][w][lo_pitch] (cl < c_lo <= 128 * gridDim.y), HI NCHW fp32.  block (128): one thread per cl,
+// the 5x5xc_hi patch of a pixel is broadcast from shared memory.
+__global__ void __launch_bounds__(128)
+wgrad_small_kernel(const __nv_bfloat16* __restrict__ lo, int lo_pitch, int c_lo, const float* __restrict__ hi, int c_hi,
+                   int n, int h, int w, int transposed_layout, float* __restrict__ dw) {
+  __shared__ float patch[2][4 * 25];
+  const int cl = blockIdx.y * 128 + threadIdx.x;
+  const long npix = (long)n * h * w;
+  const long per = (npix + gridDim.x - 1) / gridDim.x;
+  const long p0 = per * blockIdx.x, p1 = min(npix, p0 + per);
+  float acc[4 * 25];
+#pragma unroll
+  for (int i = 0; i < 100; ++i) acc[i] = 0.0f;
+  const int np = c_hi * 25;
+  const int hh = 2 * h, ww = 2 * w;
+  int buf = 0;
+  for (long p = p0; p < p1; ++p, buf ^= 1) {
+    const int ox = (int)(p % w);
+    const long r = p / w;
+    const int oy = (int)(r % h), b = (int)(r / h);
+    if (threadIdx.x < np) {
+      const int ci = threadIdx.x / 25, tap = threadIdx.x % 25;
+      const int iy = 2 * oy + tap / 5 - 2, ix = 2 * ox + tap % 5 - 2;
+      patch[buf][threadIdx.x] = (iy >= 0 && iy < hh && ix >= 0 && ix < ww)
+                                    ? hi[((long)(b * c_hi + ci) * hh + iy) * ww + ix] : 0.0f;
+    }
+    __syncthreads();
+    if (cl < c_lo) {
+      const float lv = __bfloat162float(lo[p * lo_pitch + cl]);
+#pragma unroll
+      for (int i = 0; i < 100; ++i)
+        if (i < np) acc[i] += lv * patch[buf][i];
+    }
+  }
+  if (cl < c_lo)
+    for (int i = 0; i < np; ++i) {
+      const int ci = i / 25, tap = i % 25;
+      // Conv2d weight (c_lo, c_hi, 5, 5) or ConvTranspose2d weight (c_lo, c_hi, 5, 5): both index [cl][ci][tap]
+      (void)transposed_layout;
+      atomicAdd(dw + ((long)cl * c_hi + ci) * 25 + tap, acc[i]);
+    }
+}
+
+// out[c] += sum over n, hw of g[n][c][hw]
+__global__ void __launch_bounds__(256)
+colsum_nchw_kernel(const float* __restrict__ g, int n, int c, long hw, float* __restrict__ out) {
+  __shared__ float red[8];
+  const int ch = blockIdx.x;
+  float s = 0.0f;
+  for (int b = 0; b < n; ++b)
+    for (long p = blockIdx.y * (long)blockDim.x + threadIdx.x; p < hw; p += (long)gridDim.y * blockDim.x)
+      s += g[((long)b * c + ch) * hw + p];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    atomicAdd(out + ch, t);
+  }
+}
+
+}  // namespace
+
+#define S(stream) static_cast<cudaStream_t>(stream)
+
+extern "C" int masic_mse_grad(const float* x_hat, const float* x, const float* addend, float scale, int64_t numel,
+                              float* g, void* stream) {
+  if (!x_hat || !x || !g || numel <= 0) return MASIC_EINVAL;
+  mse_grad_kernel<<<(unsigned)((numel + 255) / 256), 256, 0, S(stream)>>>(x_hat, x, addend, scale, numel, g);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int masic_warp_perspective_bwd(const float* g0, const float* g1, int n, int c, int h, int w, int h_out,
+                                          int w_out, const double* t_prepared, float* dsrc_zeroed, void* stream) {
+  if (!g0 || !t_prepared || !dsrc_zeroed || n <= 0 || c <= 0 || c > 8 || h_out < 2 || w_out < 2) return MASIC_EINVAL;
+  dim3 grid((w_out + 255) / 256, h_out, n);
+  warp_bwd_kernel<<<grid, 256, 0, S(stream)>>>(g0, g1, n, c, h, w, h_out, w_out, t_prepared, dsrc_zeroed);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int masic_conv_small_bwd(const float* in0, int c0, const float* in1, int c1, int n, int h, int w,
+                                    const float* weight, int transposed_s1, int c_out, int ksize, int stride,
+                                    const float* g_out, const float* act_out, float* din0, float* din1,
+                                    float* dweight_zeroed, float* dbias_zeroed, void* stream) {
+  if (!in0 || !weight || !g_out || c_out <= 0 || c_out > MAXC || c0 <= 0 || c0 + c1 > MAXC) return MASIC_EINVAL;
+  if ((ksize != 3 && ksize != 5) || (stride != 1 && stride != 2) || (transposed_s1 && stride != 1)) return MASIC_EINVAL;
+  SCArgs a;
+  a.in0 = in0; a.in1 = in1; a.c0 = c0; a.c1 = c1; a.n = n; a.h = h; a.w = w;
+  a.ho = (h + stride - 1) / stride; a.wo = (w + stride - 1) / stride;
+  a.c_out = c_out; a.k = ksize; a.stride = stride; a.transposed = transposed_s1;
+  a.g = g_out; a.act_out = act_out; a.wt = weight;
+  if (dweight_zeroed) {
+    const int nw = c_out * (c0 + c1) * ksize * ksize;
+    const long npix = (long)n * a.ho * a.wo;
+    int split = (int)((npix + 16383) / 16384);
+    if (split < 1) split = 1;
+    if (split > 64) split = 64;
+    small_conv_wgrad_kernel<<<dim3(nw + (dbias_zeroed ? c_out : 0), split), 256, 0, S(stream)>>>(a, dweight_zeroed,
+                                                                                                 dbias_zeroed);
+  }
+  if (din0 || din1) {
+    dim3 grid((w + 127) / 128, h, n);
+    small_conv_dgrad_kernel<<<grid, 128, 0, S(stream)>>>(a, din0, din1);
+  }
+  return (int)cudaGetLastError();
+}
+
+extern "C" int masic_gdn_small_bwd(const float* x, const float* g, int n, int c, int hw, const float* beta,
+                                   const float* gamma, float beta_min, int inverse, float* dx,
+                                   float* dbeta_prime_zeroed, float* dgamma_prime_zeroed, void* stream) {
+  if (!x || !g || !beta || !gamma || !dx || !dbeta_prime_zeroed || !dgamma_prime_zeroed || c <= 0 || c > MAXC)
+    return MASIC_EINVAL;
+  const long total = (long)n * hw;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 1184) blocks = 1184;
+  gdn_small_bwd_kernel<<<blocks, 256, 0, S(stream)>>>(x, g, n, c, hw, beta, gamma, sqrtf(beta_min + 1.4551915228366852e-11f),
+                                                      3.814697265625e-06f, 1.4551915228366852e-11f, inverse, dx,
+                                                      dbeta_prime_zeroed, dgamma_prime_zeroed);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int masic_softmax_channels_bwd(const float* w_nhwc, const float* dw_nhwc, int n, int c, int hw,
+                                          float* dlogits_nchw, void* stream) {
+  if (!w_nhwc || !dw_nhwc || !dlogits_nchw || c <= 0 || c > MAXC) return MASIC_EINVAL;
+  const long total = (long)n * hw;
+  softmax_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(w_nhwc, dw_nhwc, n, c, hw, dlogits_nchw);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int masic_wgrad_small(const void* lo_bf16, int lo_pitch, int c_lo, const float* hi_nchw, int c_hi, int n,
+                                 int h_lo, int w_lo, float* dw_accum, void* stream) {
+  if (!lo_bf16 || !hi_nchw || !dw_accum || c_hi <= 0 || c_hi > 4 || c_lo <= 0 || n <= 0) return MASIC_EINVAL;
+  const long npix = (long)n * h_lo * w_lo;
+  int gx = (int)((npix + 255) / 256);
+  if (gx > 592) gx = 592;
+  wgrad_small_kernel<<<dim3(gx, (c_lo + 127) / 128), 128, 0, S(stream)>>>(
+      static_cast<const __nv_bfloat16*>(lo_bf16), lo_pitch, c_lo, hi_nchw, c_hi, n, h_lo, w_lo, 0, dw_accum);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int masic_colsum_nchw(const float* g, int n, int c, int64_t hw, float* out_accum, void* stream) {
+  if (!g || !out_accum || n <= 0 || c <= 0 || hw <= 0) return MASIC_EINVAL;
+  int gy = (int)((hw + 4095) / 4096);
+  if (gy > 128) gy = 128;
+  colsum_nchw_kernel<<<dim3(c, gy), 256, 0, S(stream)>>>(g, n, c, hw, out_accum);
+  return (int)cudaGetLastError();
+}
