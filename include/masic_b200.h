@@ -271,9 +271,9 @@ int masic_rd_metrics(const float* const* lik4_host, const int64_t* lik_numel4_ho
  * conv()/deconv() of compressai/models/utils.py:128-146).
  *   nn.Conv2d          (W = (Cout,Cin,k,k)):  LO = dL/d(output), HI = layer input
  *   nn.ConvTranspose2d (W = (Cin,Cout,k,k)):  LO = layer input,  HI = dL/d(output)
- * LO is [n][h_lo][w_lo][lo_cpitch], HI is [n][stride*h_lo][stride*w_lo][hi_cpitch], both NHWC bf16; c_lo and c_hi
- * must be multiples of 64 (channels beyond the real count must hold zeros or are ignored: only dW[c_lo][c_hi] is
- * written).  dw is fp32 in the torch layout of the layer's weight; accumulate=1 adds to it (a layer that runs
+ * LO is [n][h_lo][w_lo][lo_cpitch], HI is [n][stride*h_lo][stride*w_lo][hi_cpitch], both NHWC bf16; c_lo, c_hi
+ * >= 16 are the real channel counts (the kernel reads whole 64/128-channel tiles: what lies beyond the real
+ * count, in the buffer or zero-filled outside it, only reaches rows/columns that are never written to dW).  dw is fp32 in the torch layout of the layer's weight; accumulate=1 adds to it (a layer that runs
  * twice per step, encoder1: MASIC.py:746,822).  Deterministic (fixed-order partial sums in `workspace`). */
 typedef struct MasicWgradDesc {
   int ksize, stride;          /* 1/3/5, 1/2 */

@@ -85,6 +85,24 @@ class PackedConv:
         if gdn != GDN_NONE:
             self.beta, _, self.gamma16 = gdn_prepare(gdn_beta, gdn_gamma)
 
+    def repack(self, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> None:
+        """Re-pack changed weights IN PLACE (same device buffers, so bound plans stay valid): the training step
+        calls this after every optimizer step."""
+        lib = _lib.load()
+        w = weight.detach()
+        if w.dtype != torch.float32 or not w.is_contiguous():
+            w = w.float().contiguous()
+        pack_cin = w.shape[1] if self.kind == CONV_XFOLD4 else self.c_in
+        check(lib.masic_pack_conv_weights(w.data_ptr(), self.kind, int(self.transposed), self.ksize, pack_cin,
+                                          self.c_out, self.c_out_pad, self.w_packed.data_ptr(), _stream()),
+              "masic_pack_conv_weights")
+        self._keep = w
+        if bias is not None and self.bias is not None:
+            if self.kind == DECONV_S2_SUBPIX:
+                self.bias[:4 * self.c_out].copy_(bias.detach().float().repeat(4))
+            else:
+                self.bias[:self.c_out].copy_(bias.detach().float())
+
 
 class ConvPlan:
     def __init__(self, *, packed: Optional[PackedConv] = None, kind: int = CONV, ksize: int = 0,

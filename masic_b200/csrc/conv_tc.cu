@@ -52,7 +52,7 @@ constexpr int NUM_THREADS = 640;    // warp 0: A producer, 1: B producer, 2: MMA
 constexpr int EPI_THREADS = 512;
 constexpr int MAX_VARIANTS = 4;
 constexpr int MAX_STAGES = 8;
-constexpr int MAX_STRIPS = 64, MAX_BOPS = 96;
+constexpr int MAX_STRIPS = 64, MAX_BOPS = 128;
 constexpr int STAGE_BLK_BYTES = 16384;  // one 128-row x 128-B staging block
 constexpr uint32_t TMEM_COLS = 512;
 

@@ -261,12 +261,13 @@ extern "C" int masic_wgrad_plan_create(const MasicWgradDesc* dp, MasicWgradPlan*
   *out = nullptr;
   if (d.ksize != 1 && d.ksize != 3 && d.ksize != 5) return MASIC_EINVAL;
   if (d.stride != 1 && d.stride != 2) return MASIC_EINVAL;
-  if (d.c_lo <= 0 || d.c_hi <= 0 || d.c_lo % 64 || d.c_hi % 64) return MASIC_ENOSUP;   // small-channel layers: masic_wgrad_small
+  if (d.c_lo < 16 || d.c_hi < 16) return MASIC_ENOSUP;      // small-channel layers: masic_wgrad_small
+  const int c_hi_pad = (d.c_hi + 63) / 64 * 64;               // channels read beyond the real count are ignored
   if (d.lo_cpitch % 8 || d.hi_cpitch % 8 || d.lo_coff % 8 || d.hi_coff % 8) return MASIC_EINVAL;
   if (!d.lo || !d.hi || !d.dw || d.n <= 0 || d.h_lo <= 0 || d.w_lo <= 0) return MASIC_EINVAL;
   const int k = d.ksize, pad = k / 2, s = d.stride;
   const uint32_t mask = d.tap_mask ? d.tap_mask : 0xFFFFFFFFu;
-  const int n_cols = d.c_hi >= 128 ? 128 : 64;
+  const int n_cols = c_hi_pad >= 128 ? 128 : 64;
   const int max_acc = WG_MAX_ACC;
 
   // HI strips: (c0 relative to hi_coff incl. the column phase, dx, p2, dy) and their live taps (row, tap id)
@@ -301,7 +302,7 @@ extern "C" int masic_wgrad_plan_create(const MasicWgradDesc* dp, MasicWgradPlan*
 
   const int l_blk = WG_TILE_H * 1024, h_blk = rows * 1024;
   const int n_hblk = n_cols / 64;
-  const int cl_tiles = (d.c_lo + 127) / 128, ch_tiles = (d.c_hi + n_cols - 1) / n_cols;
+  const int cl_tiles = (d.c_lo + 127) / 128, ch_tiles = (c_hi_pad + n_cols - 1) / n_cols;
   const bool one_by_one = (k == 1);
   const int max_b = one_by_one ? 2 : 1;
   const int stage_bytes = 2 * l_blk + max_b * n_hblk * h_blk;

@@ -1,0 +1,89 @@
+"""Gradient parity of the CUDA training step (masic_b200/trainer.py) against oracle/train.py — the CPU restatement of
+the reference's training step, pinned to the unmodified reference in tests/test_oracle_train_pinned.py — on the same
+seeded weights, inputs and quantisation noise.
+
+Tolerances: the CUDA path feeds the tensor cores bf16 activations / gradients with fp32 accumulation, the oracle is
+fp32 throughout; per parameter tensor the gradient must agree in direction (cosine >= COS_MIN) and magnitude
+(|norm ratio - 1| <= NORM_RTOL); loss / bpp / mse to 0.1 % (the north-star's bpp tolerance)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+COS_MIN = 0.99
+NORM_RTOL = 0.05
+LOSS_RTOL = 5e-3      # train mode has no rounding to absorb bf16 activation noise: y + U(-.5,.5) enters the likelihood directly
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    from masic_b200 import _lib
+    _lib.load()
+    return torch.device("cuda:0")
+
+
+def _setup(batch, h, w, scale, dev):
+    from masic_b200.hsic import HSIC
+    from oracle import train as OT
+    from oracle.hsic import OracleHSIC, synthetic_homography
+    torch.manual_seed(0)
+    oracle = OracleHSIC(128, 192, 5)
+    with torch.no_grad():
+        oracle.encoder1.g_a_conv4.weight.mul_(scale)
+        oracle.encoder2.g_a_conv4.weight.mul_(scale)
+    g = torch.Generator().manual_seed(100)
+    x1, x2 = torch.rand(batch, 3, h, w, generator=g), torch.rand(batch, 3, h, w, generator=g)
+    Hm = synthetic_homography(batch, seed=1)
+    noise = OT.make_noise(oracle, batch, h, w, 77)
+    net = HSIC()
+    net.load_state_dict(oracle.state_dict())
+    net = net.to(dev).train()
+    return oracle, net, x1, x2, Hm, noise
+
+
+@pytest.mark.parametrize("batch,h,w,scale", [(2, 64, 128, 8.0), (1, 128, 192, 1.0)])
+def test_training_step_gradients_match_oracle(dev, batch, h, w, scale):
+    from masic_b200.trainer import HSICTrainer
+    from oracle import train as OT
+    oracle, net, x1, x2, Hm, noise = _setup(batch, h, w, scale, dev)
+    lmbda = 0.001
+    loss, bpp, mse, aux, grads, out = OT.train_step_grads(oracle, x1, x2, Hm, noise, lmbda)
+    tr = HSICTrainer(net, batch, h, w, dev, lmbda=lmbda)
+    res = tr.step_grads(x1.to(dev), x2.to(dev), Hm.to(dev), noise={k: v.to(dev) for k, v in noise.items()})
+    torch.cuda.synchronize()
+    print("loss", res, "oracle", loss, bpp, mse, aux)
+    assert res["bpp"] == pytest.approx(bpp, rel=LOSS_RTOL)
+    assert res["mse"] == pytest.approx(mse, rel=LOSS_RTOL)
+    assert res["loss"] == pytest.approx(loss, rel=LOSS_RTOL)
+    assert res["aux"] == pytest.approx(aux, rel=1e-5)
+    bad = []
+    for name, p in torch.nn.Module.named_parameters(net):
+        want = grads[name].double()
+        got = p.grad.detach().cpu().double()
+        assert got.shape == want.shape, name
+        if name.startswith("context_prediction") and name.endswith("weight"):
+            pass                                    # full 5x5 gradient, like autograd (the mask acts on .data only)
+        nw, ng = float(want.norm()), float(got.norm())
+        if nw < 1e-12:
+            assert ng < 1e-9, name
+            continue
+        cos = float((want * got).sum() / (nw * ng + 1e-300))
+        if cos < COS_MIN or abs(ng / nw - 1.0) > NORM_RTOL:
+            bad.append((name, round(cos, 5), round(ng / nw, 4), nw))
+    print("\n".join(str(b) for b in bad))
+    assert not bad, f"{len(bad)} of {len(grads)} parameter gradients out of tolerance"
+    # second step with unchanged weights and inputs reproduces the first (buffers are re-zeroed, weights re-packed)
+    g1 = tr.flat_grad.clone()
+    res2 = tr.step_grads(x1.to(dev), x2.to(dev), Hm.to(dev), noise={k: v.to(dev) for k, v in noise.items()})
+    assert res2["loss"] == pytest.approx(res["loss"], rel=1e-6)
+    rel = float((tr.flat_grad - g1).norm() / g1.norm())
+    assert rel < 1e-3, rel                          # only atomics' summation order differs
+
+
+def test_training_mode_forward_raises_without_trainer(dev):
+    from masic_b200._lib import MasicError
+    from masic_b200.hsic import HSIC
+    net = HSIC().to(dev).train()
+    with pytest.raises(MasicError):
+        net(torch.rand(1, 3, 64, 64, device=dev), torch.rand(1, 3, 64, 64, device=dev), torch.eye(3, device=dev)[None])
