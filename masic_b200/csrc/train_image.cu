@@ -89,51 +89,82 @@ __device__ __forceinline__ float sc_g(const SCArgs& a, int b, int co, int y, int
   return (a.act_out && !(a.act_out[o] > 0.0f)) ? 0.0f : v;
 }
 
-// grid (n_weights + c_out, SPLIT): block b handles weight element (or bias) `blockIdx.x` over a slab of output pixels
+// Persistent blocks walk 16x16 tiles of OUTPUT pixels: the masked gradient tile (c_out x 256) and the input halo tile
+// (cin x (16 s + k - 1)^2 for a conv, cin x (16 + k - 1)^2 for the transposed layer) are staged in shared memory;
+// thread t owns weight elements t, t + 256, ... (and the bias), accumulates over all its tiles in registers and issues
+// one atomicAdd per owned element at the end.
+constexpr int SW_T = 16;
+constexpr int SW_MAXW = 2;                       // owned weight elements per thread: 450 + 3 <= 2 * 256
 __global__ void __launch_bounds__(256)
 small_conv_wgrad_kernel(const SCArgs a, float* __restrict__ dw, float* __restrict__ db) {
-  __shared__ float red[8];
+  extern __shared__ float sm[];
   const int cin = a.c0 + a.c1, kk = a.k * a.k, pad = a.k / 2;
   const int nw = a.c_out * cin * kk;
-  const int e = blockIdx.x;
-  const long npix = (long)a.n * a.ho * a.wo;
-  const long per = (npix + gridDim.y - 1) / gridDim.y;
-  const long p0 = per * blockIdx.y, p1 = min(npix, p0 + per);
-  float s = 0.0f;
-  if (e < nw) {
-    const int tap = e % kk;
-    int co, ci;
-    if (a.transposed) { co = (e / kk) % a.c_out; ci = e / (kk * a.c_out); }
-    else { ci = (e / kk) % cin; co = e / (kk * cin); }
-    const int ky = tap / a.k, kx = tap % a.k;
-    for (long p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
-      const int ox = (int)(p % a.wo);
-      const long r = p / a.wo;
-      const int oy = (int)(r % a.ho), b = (int)(r / a.ho);
-      const float gv = sc_g(a, b, co, oy, ox);
-      if (gv != 0.0f) {
-        const int iy = a.transposed ? oy + pad - ky : oy * a.stride + ky - pad;
-        const int ix = a.transposed ? ox + pad - kx : ox * a.stride + kx - pad;
-        s += gv * sc_in(a, b, ci, iy, ix);
-      }
+  const int ntot = nw + (db ? a.c_out : 0);
+  const int span = a.transposed ? SW_T + a.k - 1 : (SW_T - 1) * a.stride + a.k;      // input tile edge
+  float* s_g = sm;                                // [c_out][256]
+  float* s_in = sm + a.c_out * SW_T * SW_T;       // [cin][span][span]
+  const int tiles_x = (a.wo + SW_T - 1) / SW_T, tiles_y = (a.ho + SW_T - 1) / SW_T;
+  const int n_tiles = tiles_x * tiles_y * a.n;
+  // decode owned elements once
+  int e_co[SW_MAXW], e_ci[SW_MAXW], e_ky[SW_MAXW], e_kx[SW_MAXW];
+  float acc[SW_MAXW];
+#pragma unroll
+  for (int j = 0; j < SW_MAXW; ++j) {
+    const int e = threadIdx.x + j * 256;
+    acc[j] = 0.0f;
+    e_co[j] = -1; e_ci[j] = 0; e_ky[j] = 0; e_kx[j] = 0;
+    if (e < nw) {
+      const int tap = e % kk;
+      if (a.transposed) { e_co[j] = (e / kk) % a.c_out; e_ci[j] = e / (kk * a.c_out); }
+      else { e_ci[j] = (e / kk) % cin; e_co[j] = e / (kk * cin); }
+      e_ky[j] = tap / a.k; e_kx[j] = tap % a.k;
+    } else if (e < ntot) {
+      e_co[j] = e - nw; e_ci[j] = -1;
     }
-  } else {
-    const int co = e - nw;
-    for (long p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
-      const int ox = (int)(p % a.wo);
-      const long r = p / a.wo;
-      s += sc_g(a, (int)(r / a.ho), co, (int)(r % a.ho), ox);
+  }
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int tx = t % tiles_x, r = t / tiles_x;
+    const int ty = r % tiles_y, b = r / tiles_y;
+    const int oy0 = ty * SW_T, ox0 = tx * SW_T;
+    // input tile origin: conv reads in[o*s + k - pad]; transposed reads in[o + pad - k]
+    const int iy0 = a.transposed ? oy0 + pad - (a.k - 1) : oy0 * a.stride - pad;
+    const int ix0 = a.transposed ? ox0 + pad - (a.k - 1) : ox0 * a.stride - pad;
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.c_out * SW_T * SW_T; i += 256) {
+      const int co = i / (SW_T * SW_T), q = i % (SW_T * SW_T);
+      s_g[i] = sc_g(a, b, co, oy0 + q / SW_T, ox0 + q % SW_T);
+    }
+    for (int i = threadIdx.x; i < cin * span * span; i += 256) {
+      const int ci = i / (span * span), q = i % (span * span);
+      s_in[i] = sc_in(a, b, ci, iy0 + q / span, ix0 + q % span);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SW_MAXW; ++j) {
+      if (e_co[j] < 0) continue;
+      const float* g = s_g + e_co[j] * SW_T * SW_T;
+      float s = 0.0f;
+      if (e_ci[j] < 0) {
+        for (int q = 0; q < SW_T * SW_T; ++q) s += g[q];
+      } else {
+        const float* in = s_in + e_ci[j] * span * span;
+        // conv: in index = (oy*s + ky, ox*s + kx) relative to the tile; transposed: (oy + k-1-ky, ox + k-1-kx)
+        const int by = a.transposed ? a.k - 1 - e_ky[j] : e_ky[j], bx = a.transposed ? a.k - 1 - e_kx[j] : e_kx[j];
+        const int st = a.transposed ? 1 : a.stride;
+        for (int oy = 0; oy < SW_T; ++oy)
+#pragma unroll 4
+          for (int ox = 0; ox < SW_T; ++ox)
+            s += g[oy * SW_T + ox] * in[(oy * st + by) * span + ox * st + bx];
+      }
+      acc[j] += s;
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.0f;
-    for (int i = 0; i < 8; ++i) t += red[i];
-    if (e < nw) atomicAdd(dw + e, t);
-    else if (db) atomicAdd(db + (e - nw), t);
+  for (int j = 0; j < SW_MAXW; ++j) {
+    const int e = threadIdx.x + j * 256;
+    if (e < nw) atomicAdd(dw + e, acc[j]);
+    else if (e < ntot) atomicAdd(db + (e - nw), acc[j]);
   }
 }
 
@@ -243,48 +274,58 @@ softmax_bwd_kernel(const float* __restrict__ w, const float* __restrict__ dw, in
   for (int j = 0; j < c; ++j) dl[((long)b * c + j) * hw + p] = w[i * c + j] * (dw[i * c + j] - dot);
 }
 
-// dW[cl][ci][ky][kx] += sum_{n,p} LO[n,p,cl] * HI[n][ci][2p + k - 2]   (k = 5, stride 2, c_hi <= 4)
-// LO NHWC bf16 [n][h][w][lo_pitch] (cl < c_lo <= 128 * gridDim.y), HI NCHW fp32.  block (128): one thread per cl,
-// the 5x5xc_hi patch of a pixel is broadcast from shared memory.
+// dW[cl][ci][ky][kx] += sum_{n,p} LO[n,p,cl] * HI[n][ci][2p + k - 2]   (k = 5, stride 2, c_hi <= 3)
+// LO NHWC bf16 [n][h][w][lo_pitch] (cl < c_lo <= 128 * gridDim.y), HI NCHW fp32.  block (128): one thread per cl with
+// 75 accumulators; 32 pixels per step: their 5x5xc_hi patches are staged in shared memory (one barrier per 32
+// pixels) and read back as broadcast float4.
+constexpr int WS_PIX = 32, WS_NP = 76;          // 75 patch values padded to a multiple of 4
 __global__ void __launch_bounds__(128)
 wgrad_small_kernel(const __nv_bfloat16* __restrict__ lo, int lo_pitch, int c_lo, const float* __restrict__ hi, int c_hi,
-                   int n, int h, int w, int transposed_layout, float* __restrict__ dw) {
-  __shared__ float patch[2][4 * 25];
+                   int n, int h, int w, float* __restrict__ dw) {
+  __shared__ __align__(16) float patch[WS_PIX][WS_NP];
   const int cl = blockIdx.y * 128 + threadIdx.x;
   const long npix = (long)n * h * w;
-  const long per = (npix + gridDim.x - 1) / gridDim.x;
+  const long per = ((npix + gridDim.x - 1) / gridDim.x + WS_PIX - 1) / WS_PIX * WS_PIX;
   const long p0 = per * blockIdx.x, p1 = min(npix, p0 + per);
-  float acc[4 * 25];
+  float acc[WS_NP];
 #pragma unroll
-  for (int i = 0; i < 100; ++i) acc[i] = 0.0f;
+  for (int i = 0; i < WS_NP; ++i) acc[i] = 0.0f;
   const int np = c_hi * 25;
   const int hh = 2 * h, ww = 2 * w;
-  int buf = 0;
-  for (long p = p0; p < p1; ++p, buf ^= 1) {
-    const int ox = (int)(p % w);
-    const long r = p / w;
-    const int oy = (int)(r % h), b = (int)(r / h);
-    if (threadIdx.x < np) {
-      const int ci = threadIdx.x / 25, tap = threadIdx.x % 25;
-      const int iy = 2 * oy + tap / 5 - 2, ix = 2 * ox + tap % 5 - 2;
-      patch[buf][threadIdx.x] = (iy >= 0 && iy < hh && ix >= 0 && ix < ww)
-                                    ? hi[((long)(b * c_hi + ci) * hh + iy) * ww + ix] : 0.0f;
+  for (long pb = p0; pb < p1; pb += WS_PIX) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < WS_PIX * WS_NP; e += 128) {
+      const int pl = e / WS_NP, i = e - pl * WS_NP;
+      const long p = pb + pl;
+      float v = 0.0f;
+      if (p < p1 && i < np) {
+        const int ox = (int)(p % w);
+        const long r = p / w;
+        const int oy = (int)(r % h), b = (int)(r / h);
+        const int ci = i / 25, tap = i - ci * 25;
+        const int iy = 2 * oy + tap / 5 - 2, ix = 2 * ox + tap % 5 - 2;
+        if (iy >= 0 && iy < hh && ix >= 0 && ix < ww) v = hi[((long)(b * c_hi + ci) * hh + iy) * ww + ix];
+      }
+      patch[pl][i] = v;
     }
     __syncthreads();
     if (cl < c_lo) {
-      const float lv = __bfloat162float(lo[p * lo_pitch + cl]);
+      const int cnt = (int)min((long)WS_PIX, p1 - pb);
+      for (int pl = 0; pl < cnt; ++pl) {
+        const float lv = __bfloat162float(lo[(pb + pl) * lo_pitch + cl]);
+        const float4* pp = reinterpret_cast<const float4*>(patch[pl]);
 #pragma unroll
-      for (int i = 0; i < 100; ++i)
-        if (i < np) acc[i] += lv * patch[buf][i];
+        for (int q = 0; q < WS_NP / 4; ++q) {
+          const float4 v = pp[q];
+          acc[4 * q] += lv * v.x; acc[4 * q + 1] += lv * v.y; acc[4 * q + 2] += lv * v.z; acc[4 * q + 3] += lv * v.w;
+        }
+      }
     }
   }
   if (cl < c_lo)
-    for (int i = 0; i < np; ++i) {
-      const int ci = i / 25, tap = i % 25;
-      // Conv2d weight (c_lo, c_hi, 5, 5) or ConvTranspose2d weight (c_lo, c_hi, 5, 5): both index [cl][ci][tap]
-      (void)transposed_layout;
-      atomicAdd(dw + ((long)cl * c_hi + ci) * 25 + tap, acc[i]);
-    }
+#pragma unroll
+    for (int i = 0; i < WS_NP; ++i)
+      if (i < np) atomicAdd(dw + (long)cl * np + i, acc[i]);     // [cl][ci][tap], Conv2d and ConvTranspose2d alike
 }
 
 // out[c] += sum over n, hw of g[n][c][hw]
@@ -339,12 +380,12 @@ extern "C" int masic_conv_small_bwd(const float* in0, int c0, const float* in1, 
   a.g = g_out; a.act_out = act_out; a.wt = weight;
   if (dweight_zeroed) {
     const int nw = c_out * (c0 + c1) * ksize * ksize;
-    const long npix = (long)n * a.ho * a.wo;
-    int split = (int)((npix + 16383) / 16384);
-    if (split < 1) split = 1;
-    if (split > 64) split = 64;
-    small_conv_wgrad_kernel<<<dim3(nw + (dbias_zeroed ? c_out : 0), split), 256, 0, S(stream)>>>(a, dweight_zeroed,
-                                                                                                 dbias_zeroed);
+    if (nw + c_out > SW_MAXW * 256) return MASIC_ENOSUP;
+    const int span = transposed_s1 ? SW_T + ksize - 1 : (SW_T - 1) * stride + ksize;
+    const int smem = (c_out * SW_T * SW_T + (c0 + c1) * span * span) * (int)sizeof(float);
+    const int n_tiles = ((a.wo + SW_T - 1) / SW_T) * ((a.ho + SW_T - 1) / SW_T) * n;
+    int blocks = n_tiles < 592 ? n_tiles : 592;
+    small_conv_wgrad_kernel<<<blocks, 256, smem, S(stream)>>>(a, dweight_zeroed, dbias_zeroed);
   }
   if (din0 || din1) {
     dim3 grid((w + 127) / 128, h, n);
@@ -377,12 +418,12 @@ extern "C" int masic_softmax_channels_bwd(const float* w_nhwc, const float* dw_n
 
 extern "C" int masic_wgrad_small(const void* lo_bf16, int lo_pitch, int c_lo, const float* hi_nchw, int c_hi, int n,
                                  int h_lo, int w_lo, float* dw_accum, void* stream) {
-  if (!lo_bf16 || !hi_nchw || !dw_accum || c_hi <= 0 || c_hi > 4 || c_lo <= 0 || n <= 0) return MASIC_EINVAL;
+  if (!lo_bf16 || !hi_nchw || !dw_accum || c_hi <= 0 || c_hi > 3 || c_lo <= 0 || n <= 0) return MASIC_EINVAL;
   const long npix = (long)n * h_lo * w_lo;
-  int gx = (int)((npix + 255) / 256);
-  if (gx > 592) gx = 592;
+  int gx = (int)((npix + 127) / 128);
+  if (gx > 1184) gx = 1184;                      // 8 resident blocks x 148 SMs
   wgrad_small_kernel<<<dim3(gx, (c_lo + 127) / 128), 128, 0, S(stream)>>>(
-      static_cast<const __nv_bfloat16*>(lo_bf16), lo_pitch, c_lo, hi_nchw, c_hi, n, h_lo, w_lo, 0, dw_accum);
+      static_cast<const __nv_bfloat16*>(lo_bf16), lo_pitch, c_lo, hi_nchw, c_hi, n, h_lo, w_lo, dw_accum);
   return (int)cudaGetLastError();
 }
 

@@ -440,7 +440,7 @@ extern "C" int masic_wgrad_plan_launch(const MasicWgradPlan* pl, void* workspace
   wgrad_tc_kernel<<<pl->n_ctas, WG_THREADS, smem, s>>>(kp);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return (int)ce;
-  dim3 grid(pl->n_items, 4);
+  dim3 grid(pl->n_items, 16);
   wgrad_reduce_kernel<<<grid, 256, 0, s>>>(kp.partial, pl->d_items, kp.n_cols, pl->c_lo, pl->c_hi, pl->ktaps,
                                            pl->accumulate, pl->dw);
   return (int)cudaGetLastError();

@@ -186,8 +186,9 @@ class HSIC(nn.Module):
     # ---- forward (MASIC.py:744-851)
     def forward(self, x1: torch.Tensor, x2: torch.Tensor, h_matrix: torch.Tensor, clone: bool = True):
         if self.training:
-            raise MasicError("HSIC.forward: masic_b200 implements the inference path (model.eval()); "
-                             "the training step (noise quantisation + backward kernels) is not built yet")
+            raise MasicError("HSIC.forward in train() mode does not build an autograd graph: the training step "
+                             "(noise quantisation, loss, backward, aux loss) runs as fused CUDA kernels through "
+                             "model.trainer(batch, H, W, device, lmbda).train_step(x1, x2, h, optimizer, aux_optimizer)")
         if not x1.is_cuda:
             raise MasicError("HSIC.forward needs CUDA tensors: masic_b200 has no CPU fallback")
         b, _, h, w = x1.shape
@@ -204,6 +205,13 @@ class HSIC(nn.Module):
     def pair_stream(self, height: int, width: int, device, depth: int = 2, lmbda: float = 0.0) -> "PairStream":
         """Pipelined host-to-host evaluation of batch-1 stereo pairs (see PairStream)."""
         return PairStream(self, height, width, device, depth=depth, lmbda=lmbda)
+
+    def trainer(self, batch: int, height: int, width: int, device, lmbda: float = 0.01):
+        """The CUDA training step for this model (forward in train() mode + loss + backward + aux loss):
+        `HSICTrainer.step_grads` fills `.grad` of every parameter, `train_step` also all-reduces and steps the
+        two optimisers (coremasic/mywork/newtrain_codec_real.py:105-146)."""
+        from .trainer import HSICTrainer
+        return HSICTrainer(self, batch, height, width, device, lmbda=lmbda)
 
     # ---- bitstreams (MASIC.py:855-1158, :1161-1408)
     def compress(self, x1, x2, h_matrix, output_name, output_path="", device="cpu"):
