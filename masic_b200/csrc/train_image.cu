@@ -279,10 +279,11 @@ softmax_bwd_kernel(const float* __restrict__ w, const float* __restrict__ dw, in
 // 75 accumulators; 32 pixels per step: their 5x5xc_hi patches are staged in shared memory (one barrier per 32
 // pixels) and read back as broadcast float4.
 constexpr int WS_PIX = 32, WS_NP = 76;          // 75 patch values padded to a multiple of 4
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 wgrad_small_kernel(const __nv_bfloat16* __restrict__ lo, int lo_pitch, int c_lo, const float* __restrict__ hi, int c_hi,
                    int n, int h, int w, float* __restrict__ dw) {
   __shared__ __align__(16) float patch[WS_PIX][WS_NP];
+  __shared__ float lo_s[WS_PIX][128];
   const int cl = blockIdx.y * 128 + threadIdx.x;
   const long npix = (long)n * h * w;
   const long per = ((npix + gridDim.x - 1) / gridDim.x + WS_PIX - 1) / WS_PIX * WS_PIX;
@@ -294,25 +295,41 @@ wgrad_small_kernel(const __nv_bfloat16* __restrict__ lo, int lo_pitch, int c_lo,
   const int hh = 2 * h, ww = 2 * w;
   for (long pb = p0; pb < p1; pb += WS_PIX) {
     __syncthreads();
-    for (int e = threadIdx.x; e < WS_PIX * WS_NP; e += 128) {
-      const int pl = e / WS_NP, i = e - pl * WS_NP;
-      const long p = pb + pl;
-      float v = 0.0f;
-      if (p < p1 && i < np) {
-        const int ox = (int)(p % w);
-        const long r = p / w;
-        const int oy = (int)(r % h), b = (int)(r / h);
-        const int ci = i / 25, tap = i - ci * 25;
-        const int iy = 2 * oy + tap / 5 - 2, ix = 2 * ox + tap % 5 - 2;
-        if (iy >= 0 && iy < hh && ix >= 0 && ix < ww) v = hi[((long)(b * c_hi + ci) * hh + iy) * ww + ix];
+    {   // patch staging: thread -> (pixel tid/4, values tid%4, +4, ...): pixel coordinates computed once, 32-bit math
+      const int pl = threadIdx.x >> 2, sub = threadIdx.x & 3;
+      const int p = (int)(pb - p0) + pl;                   // pixel index relative to this block's slab
+      const long pg = p0 + p;
+      const bool live = pg < p1;
+      const int pgi = (int)pg;                             // n*h*w < 2^31 (checked on the host)
+      const int ox = pgi % w, r = pgi / w;
+      const int oy = r % h, b = r / h;
+      const float* hb = hi + (long)b * c_hi * hh * ww;
+#pragma unroll
+      for (int i = sub; i < WS_NP; i += 4) {
+        float v = 0.0f;
+        if (live && i < np) {
+          const int ci = i / 25, tap = i - ci * 25;
+          const int iy = 2 * oy + tap / 5 - 2, ix = 2 * ox + tap % 5 - 2;
+          if (iy >= 0 && iy < hh && ix >= 0 && ix < ww) v = hb[((long)ci * hh + iy) * ww + ix];
+        }
+        patch[pl][i] = v;
       }
-      patch[pl][i] = v;
+    }
+    // LO tile: groups of 8 independent coalesced loads per thread (one dependent load per pixel would expose latency)
+#pragma unroll
+    for (int g8 = 0; g8 < WS_PIX; g8 += 8) {
+      float t[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        t[q] = (cl < c_lo && pb + g8 + q < p1) ? __bfloat162float(lo[(pb + g8 + q) * lo_pitch + cl]) : 0.0f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) lo_s[g8 + q][threadIdx.x] = t[q];
     }
     __syncthreads();
     if (cl < c_lo) {
       const int cnt = (int)min((long)WS_PIX, p1 - pb);
       for (int pl = 0; pl < cnt; ++pl) {
-        const float lv = __bfloat162float(lo[(pb + pl) * lo_pitch + cl]);
+        const float lv = lo_s[pl][threadIdx.x];
         const float4* pp = reinterpret_cast<const float4*>(patch[pl]);
 #pragma unroll
         for (int q = 0; q < WS_NP / 4; ++q) {
@@ -420,6 +437,7 @@ extern "C" int masic_wgrad_small(const void* lo_bf16, int lo_pitch, int c_lo, co
                                  int h_lo, int w_lo, float* dw_accum, void* stream) {
   if (!lo_bf16 || !hi_nchw || !dw_accum || c_hi <= 0 || c_hi > 3 || c_lo <= 0 || n <= 0) return MASIC_EINVAL;
   const long npix = (long)n * h_lo * w_lo;
+  if (npix >= (1L << 31)) return MASIC_EINVAL;
   int gx = (int)((npix + 127) / 128);
   if (gx > 1184) gx = 1184;                      // 8 resident blocks x 148 SMs
   wgrad_small_kernel<<<dim3(gx, (c_lo + 127) / 128), 128, 0, S(stream)>>>(

@@ -62,7 +62,6 @@ struct WgParams {
   int l_blk_bytes, h_blk_bytes;       // one 64-channel block of the LO tile / of a HI strip
   int stage_bytes, n_stages;
   uint32_t idesc;
-  int swap_lbo_sbo;                   // bring-up switch (MASIC_WGRAD_SWAP=1)
 };
 
 // MN-major, SWIZZLE_128B operand: 64 MN elements (128 B) contiguous per K index, 8 K indices per 1024-B atom,
@@ -141,12 +140,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       tc_fence_after();
       if (elect_one()) {
         const uint32_t base = smem_base + st * p.stage_bytes;
-        const uint32_t lbo_a = p.swap_lbo_sbo ? 1024u : (uint32_t)p.l_blk_bytes, sbo_a = p.swap_lbo_sbo ? (uint32_t)p.l_blk_bytes : 1024u;
-        const uint32_t lbo_b = p.swap_lbo_sbo ? 1024u : (uint32_t)p.h_blk_bytes, sbo_b = p.swap_lbo_sbo ? (uint32_t)p.h_blk_bytes : 1024u;
-        const uint64_t adesc0 = umma_desc_mn_sw128(base, lbo_a, sbo_a);
+        // LBO = distance between the two 64-channel blocks, SBO = 1024 B between 8-pixel rows
+        const uint64_t adesc0 = umma_desc_mn_sw128(base, (uint32_t)p.l_blk_bytes, 1024u);
         for (int j = 0; j < ty.n_acc; ++j) {
           const uint32_t baddr = base + l_bytes + ty.acc_b[j] * h_bytes + ty.acc_row[j] * 1024u;
-          const uint64_t bdesc0 = umma_desc_mn_sw128(baddr, lbo_b, sbo_b);
+          const uint64_t bdesc0 = umma_desc_mn_sw128(baddr, (uint32_t)p.h_blk_bytes, 1024u);
           const uint32_t d = tmem_base + j * 128;
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)              // K = 16 pixels = two 8-pixel rows = 2048 B
@@ -190,19 +188,28 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 }
 
 // dW[cl][ch][tap] (+)= sum over the CTAs of the item's type
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, const WgItem* __restrict__ items, int n_cols,
-                                    int c_lo, int c_hi, int ktaps, int accumulate, float* __restrict__ dw) {
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, const WgItem* __restrict__ items, int n_cols, int c_lo, int c_hi,
+                    int ktaps, int accumulate, float* __restrict__ dw) {
   const WgItem it = items[blockIdx.x];
-  for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < 128 * n_cols; e += gridDim.y * blockDim.x) {
-    const int r = e / n_cols, c = e - r * n_cols;
-    const int cl = it.cl0 + r, ch = it.ch0 + c;
-    if (cl >= c_lo || ch >= c_hi) continue;
-    float s = 0.0f;
-    for (int b = it.cta_begin; b < it.cta_end; ++b)
-      s += partial[(((size_t)b * WG_MAX_ACC + it.acc) * 128 + r) * n_cols + c];
-    float* o = dw + ((size_t)cl * c_hi + ch) * ktaps + it.tap;
-    *o = accumulate ? *o + s : s;
+  const int e = blockIdx.y * blockDim.x + threadIdx.x;           // one (row, column) of the 128 x n_cols tile per thread
+  if (e >= 128 * n_cols) return;
+  const int r = e / n_cols, c = e - r * n_cols;
+  const int cl = it.cl0 + r, ch = it.ch0 + c;
+  if (cl >= c_lo || ch >= c_hi) return;
+  const size_t stride = (size_t)WG_MAX_ACC * 128 * n_cols;
+  const float* p = partial + ((size_t)it.cta_begin * WG_MAX_ACC + it.acc) * 128 * n_cols + e;
+  const int n = it.cta_end - it.cta_begin;
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;              // fixed association -> deterministic
+  int b = 0;
+  for (; b + 4 <= n; b += 4) {
+    s0 += p[(size_t)b * stride]; s1 += p[(size_t)(b + 1) * stride];
+    s2 += p[(size_t)(b + 2) * stride]; s3 += p[(size_t)(b + 3) * stride];
   }
+  for (; b < n; ++b) s0 += p[(size_t)b * stride];
+  const float s = (s0 + s1) + (s2 + s3);
+  float* o = dw + ((size_t)cl * c_hi + ch) * ktaps + it.tap;
+  *o = accumulate ? *o + s : s;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -404,7 +411,6 @@ extern "C" int masic_wgrad_plan_create(const MasicWgradDesc* dp, MasicWgradPlan*
   kp.stage_bytes = stage_bytes; kp.n_stages = n_stages;
   // kind::f16, bf16 x bf16 -> fp32, A and B both MN-major (bits 15, 16), M = 128, N = n_cols
   kp.idesc = umma_idesc_bf16(n_cols) | (1u << 15) | (1u << 16);
-  { const char* e = getenv("MASIC_WGRAD_SWAP"); kp.swap_lbo_sbo = e ? atoi(e) : 0; }
   pl->n_ctas = (int)ctas.size(); pl->n_items = (int)items.size();
   pl->smem_bytes = n_stages * stage_bytes + 2048;
   pl->c_lo = d.c_lo; pl->c_hi = d.c_hi; pl->ktaps = k * k; pl->accumulate = d.accumulate; pl->dw = d.dw;
@@ -440,7 +446,7 @@ extern "C" int masic_wgrad_plan_launch(const MasicWgradPlan* pl, void* workspace
   wgrad_tc_kernel<<<pl->n_ctas, WG_THREADS, smem, s>>>(kp);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return (int)ce;
-  dim3 grid(pl->n_items, 16);
+  dim3 grid(pl->n_items, (128 * kp.n_cols + 255) / 256);
   wgrad_reduce_kernel<<<grid, 256, 0, s>>>(kp.partial, pl->d_items, kp.n_cols, pl->c_lo, pl->c_hi, pl->ktaps,
                                            pl->accumulate, pl->dw);
   return (int)cudaGetLastError();
