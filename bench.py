@@ -259,6 +259,13 @@ def run_ours(args, rank, world, local_rank):
     gmm_bytes = 72.0 * 192 * (H // 16) * (W // 16)
     top = sorted(prof, key=lambda t: -t[1])[:8]
 
+    traffic, traffic_src = None, None
+    tf = ROOT / "profiles" / "r1_conv_traffic.json"
+    if tf.exists():                                    # ncu dram__bytes_read.sum + dram__bytes_write.sum, per launch
+        tj = json.loads(tf.read_text())
+        traffic, traffic_src = tj["conv_tc_dram_bytes_per_launch"], "profiles/r1_conv_traffic.json: " + tj["source"]
+    conv_alg_bytes = sum(p.hbm_bytes for p in eng.plans.values())
+
     line = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -274,7 +281,9 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": (len(eng.steps) + 1) * args.steps,   # engine kernels per step (+ the D2D input copy)
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops_sustained"],
-                     "unit": "TFLOP/s", "frac": achieved_tf / peaks["bf16_tflops_sustained"], "traffic": None,
+                     "unit": "TFLOP/s", "frac": achieved_tf / peaks["bf16_tflops_sustained"], "traffic": traffic,
+                     "traffic_unit": "DRAM bytes per launch (average over the step's conv_tc launches)",
+                     "traffic_src": traffic_src, "algorithmic_bytes_per_launch": conv_alg_bytes / max(1, n_conv),
                      "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv/deconv + fused GDN)",
                      "launches_per_step": n_conv, "flops_per_step": conv_flops, "ms_per_step": conv_ms,
                      "peak_src": peaks["src"] + ", sustained bf16 (kernel timed inside a long step)",
