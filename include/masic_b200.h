@@ -38,7 +38,7 @@ extern "C" {
 #define MASIC_EDRIVER (-3)  /* cuTensorMapEncodeTiled unavailable / failed  */
 
 /* ---------------------------------------------------------------- version */
-int masic_abi_version(void);                 /* bumps on any signature change */
+int masic_abi_version(void);                 /* bumps on any signature change (2: residual inputs of MasicConvDesc) */
 const char* masic_build_info(void);          /* "sm_100a nvcc 12.9 ..." */
 
 /* ------------------------------------------------------------------ convs */
@@ -88,6 +88,11 @@ typedef struct MasicConvDesc {
   /* optional per-pixel multiplier applied last (mask-weighted fusion, MASIC.py:827):
    * out *= rowscale[((n*H+y)*W+x)*rs_stride + rs_off]                                   */
   const float* rowscale; int rs_stride; int rs_off;
+  /* optional residual inputs added after the activation (MASIC_CONV, stride 1 only): NHWC bf16 with the output's
+   * spatial size; out = act(conv + bias) * rowscale + residual0 [+ residual1]   (ResidualBlock, layers.py:160-190;
+   * Enhancement_Block, MASIC.py:149-164).  Channel c of the output reads residual[... * cpitch + coff + c]. */
+  const void* residual0; int res0_cpitch; int res0_coff;
+  const void* residual1; int res1_cpitch; int res1_coff;
 } MasicConvDesc;
 
 typedef struct MasicConvPlan MasicConvPlan;   /* opaque: tensor maps + tile program */

@@ -37,6 +37,8 @@ class ConvDesc(C.Structure):
         ("act", C.c_uint8 * 32),
         ("gdn", C.c_int), ("gamma_packed", C.c_void_p), ("beta", C.c_void_p),
         ("rowscale", C.c_void_p), ("rs_stride", C.c_int), ("rs_off", C.c_int),
+        ("residual0", C.c_void_p), ("res0_cpitch", C.c_int), ("res0_coff", C.c_int),
+        ("residual1", C.c_void_p), ("res1_cpitch", C.c_int), ("res1_coff", C.c_int),
     ]
 
 

@@ -115,7 +115,9 @@ class ConvPlan:
                  act: int | Sequence[int] = ACT_NONE,
                  gdn: int = GDN_NONE, gdn_beta: Optional[torch.Tensor] = None,
                  gdn_gamma: Optional[torch.Tensor] = None,
-                 rowscale: Optional[torch.Tensor] = None, rs_off: int = 0):
+                 rowscale: Optional[torch.Tensor] = None, rs_off: int = 0,
+                 residual0: Optional[torch.Tensor] = None, res0_coff: int = 0,
+                 residual1: Optional[torch.Tensor] = None, res1_coff: int = 0):
         lib = _lib.load()
         assert x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous()
         assert out.is_cuda and out.dim() == 4 and out.is_contiguous()
@@ -150,6 +152,14 @@ class ConvPlan:
         if rowscale is not None:
             assert rowscale.dtype == torch.float32 and rowscale.is_contiguous() and rowscale.dim() == 4
             d.rowscale, d.rs_stride, d.rs_off = rowscale.data_ptr(), rowscale.shape[3], rs_off
+        for i, (r, off) in enumerate(((residual0, res0_coff), (residual1, res1_coff))):
+            if r is not None:
+                assert r.is_cuda and r.dtype == torch.bfloat16 and r.dim() == 4 and r.is_contiguous()
+                assert r.shape[:3] == out.shape[:3], (r.shape, out.shape)
+                setattr(d, f"residual{i}", r.data_ptr())
+                setattr(d, f"res{i}_cpitch", r.shape[3])
+                setattr(d, f"res{i}_coff", off)
+        self.residuals = (residual0, residual1)
         self._desc = d
         handle = C.c_void_p()
         check(lib.masic_conv_plan_create(C.byref(d), C.byref(handle)), "masic_conv_plan_create")

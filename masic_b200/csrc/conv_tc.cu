@@ -96,6 +96,9 @@ struct KParams {
   int out_coff;
   const float* rowscale;
   int rs_stride, rs_off, rs_H, rs_W;
+  const __nv_bfloat16* res0;       // optional residuals added after the activation (ResidualBlock / Enhancement_Block):
+  const __nv_bfloat16* res1;       // NHWC bf16, same spatial size as the output
+  int res0_pitch, res0_coff, res1_pitch, res1_coff;
   uint32_t idesc;
   int debug;       // timing experiments only (results are garbage): bit0 skip A loads, bit1 skip B loads, bit2 skip stores,
                    // bit3 skip the GDN norm MMA, bit4 skip the whole epilogue
@@ -428,10 +431,13 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
         const bool last_tile = (tt + 1 == it.nslots);
         const bool valid = it.valid[tt];          // CTA pairs: an odd item leaves the peer's last slot without a tile
         float rs = 1.0f;
-        if (p.rowscale && valid) {
+        size_t pix = 0;                           // linear output pixel of this thread's row (residual / rowscale)
+        bool pix_ok = false;
+        if ((p.rowscale || p.res0) && valid) {
           const int y = it.y0[tt] + (t >> 3), x = it.x0[tt] + (t & 7);
-          if (y < p.rs_H && x < p.rs_W)
-            rs = __ldg(p.rowscale + (static_cast<size_t>(it.n[tt] * p.rs_H + y) * p.rs_W + x) * p.rs_stride + p.rs_off);
+          pix_ok = y < p.rs_H && x < p.rs_W;
+          pix = static_cast<size_t>(it.n[tt] * p.rs_H + y) * p.rs_W + x;
+          if (p.rowscale && pix_ok) rs = __ldg(p.rowscale + pix * p.rs_stride + p.rs_off);
         }
         if (p.gdn) {
           // ---- pass 1: x = acc + bias stays in registers; A2[:, 32g .. 32g+32) = bf16(x^2) (SWIZZLE_128B block pr)
@@ -554,6 +560,23 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
                   for (int e = 0; e < 4; ++e) {
                     const float xv = __uint_as_float(r[16 * kk + 4 * q + e]) + bb[e];
                     o[4 * q + e] = fmaf(slope, fminf(xv, 0.0f), fmaxf(xv, 0.0f)) * rs;
+                  }
+                }
+                if (p.res0 && pix_ok) {            // out += residual(s): 16 bf16 = two 16-byte loads each
+                  const int gch = it.nt * p.n_tile + ch;
+#pragma unroll
+                  for (int rr = 0; rr < 2; ++rr) {
+                    const __nv_bfloat16* rp = rr == 0 ? p.res0 + pix * p.res0_pitch + p.res0_coff + gch
+                                                      : (p.res1 ? p.res1 + pix * p.res1_pitch + p.res1_coff + gch : nullptr);
+                    if (!rp) continue;
+                    const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(rp));
+                    const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+                    const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+                      o[2 * e] += f.x; o[2 * e + 1] += f.y;
+                    }
                   }
                 }
                 if (p.out_fp32) {
@@ -873,6 +896,7 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   const int full_blk_ch = 128 / esz;
   if (d.n_tile % full_blk_ch == 0) { kp.blk_ch = full_blk_ch; kp.blk_pitch = 128; }
   else if (d.n_tile * esz < 128) { kp.blk_ch = d.n_tile; kp.blk_pitch = d.n_tile * esz; }
+  else if (!d.out_fp32 && d.n_tile % 32 == 0) { kp.blk_ch = 32; kp.blk_pitch = 64; }    // e.g. 96 channels: 3 narrow blocks
   else { delete pl; return MASIC_EINVAL; }
 
   // work items: pairs of tiles sharing every weight k-block when two accumulators fit 256 TMEM columns
@@ -936,6 +960,12 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   kp.out_coff = d.out_coff;
   kp.rowscale = d.rowscale; kp.rs_stride = d.rs_stride; kp.rs_off = d.rs_off;
   kp.rs_H = gh; kp.rs_W = gw;
+  if (d.residual0) {
+    if (d.kind != MASIC_CONV || d.stride != 1 || d.gdn || d.res0_cpitch % 8 || d.res0_coff % 8 ||
+        (d.residual1 && (d.res1_cpitch % 8 || d.res1_coff % 8))) { delete pl; return MASIC_EINVAL; }
+    kp.res0 = static_cast<const __nv_bfloat16*>(d.residual0); kp.res0_pitch = d.res0_cpitch; kp.res0_coff = d.res0_coff;
+    kp.res1 = static_cast<const __nv_bfloat16*>(d.residual1); kp.res1_pitch = d.res1_cpitch; kp.res1_coff = d.res1_coff;
+  } else if (d.residual1) { delete pl; return MASIC_EINVAL; }
   { const char* e = getenv("MASIC_CONV_DEBUG"); kp.debug = e ? atoi(e) : 0; }
   pl->total_work = kp.n_tiles_total;
   int dev = 0, sms = 148;
