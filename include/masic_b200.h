@@ -258,6 +258,24 @@ int masic_nchw_to_nhwc_bf16(const float* in_nchw, int n, int c, int h, int w, vo
 int masic_nhwc_to_nchw_f32(const float* in_nhwc, int n, int c, int hw, int in_pitch, float* out_nchw,
                            void* stream);
 
+/* ------------------------------------------------- cross quality enhancement (CQE) glue */
+/* Independent_EN (coremasic/mywork/MASIC.py:1436-1501).  Its 3x3 convs run as MASIC_CONV plans with LeakyReLU and
+ * the ResidualBlock / Enhancement_Block adds fused (MasicConvDesc.residual0/1); these are the blends around them.
+ * weights_nchw2 = softmax output of mask2weights_EN, (N,2,H,W) fp32: channel 0 weighs the OTHER view's warped map,
+ * channel 1 this view's own map.
+ * MASIC.py:1470-1471: out[p][0:3] = a[:,p]*w0[p], out[p][3:6] = b[:,p]*w1[p], out[p][6:16] = 0 (NHWC bf16, pitch 16);
+ * a = the other view warped (NCHW fp32), b = this view's image. */
+int masic_cqe_blend_images(const float* a_nchw, const float* b_nchw, const float* weights_nchw2, int n, int h,
+                           int w, void* out_nhwc16_bf16, void* stream);
+/* MASIC.py:1479-1482: out[p][0:c] = self[p]*w1[p]; out[p][c:2c] = warp_perspective(other, M)[p]*w0[p] (bilinear,
+ * zeros, align_corners=True; t_prepared from masic_warp_prepare with src = dst = (h, w)).  NHWC bf16, c % 8 == 0. */
+int masic_cqe_feature_fuse(const void* self_bf16, int self_pitch, const void* other_bf16, int other_pitch,
+                           int c, const float* weights_nchw2, const double* t_prepared, int n, int h, int w,
+                           void* out_bf16, int out_pitch, void* stream);
+/* MASIC.py:1495-1496: out_nchw[b][c][p] = conv_out_nhwc[b][p][c] + identity_nchw[b][c][p], c < 3 (fp32). */
+int masic_cqe_residual_image(const float* conv_out_nhwc, int pitch, const float* identity_nchw, int n, int h,
+                             int w, float* out_nchw, void* stream);
+
 /* ------------------------------------------------------------- criterion */
 /* RateDistortionLoss.forward (coremasic/mywork/test2_real.py:88-114, newtrain_codec_real.py:66-87) on the
  * output of HSIC.forward: out8 (device, 8 floats) = { bpp of the 4 likelihood tensors (y1,y2,z1,z2 or any order),

@@ -145,6 +145,9 @@ def _declare(lib: C.CDLL) -> None:
         "masic_gdn_small_bwd": (i, [vp, vp, i, i, i, vp, vp, f, i, vp, vp, vp, vp]),
         "masic_softmax_channels_bwd": (i, [vp, vp, i, i, i, vp, vp]),
         "masic_colsum_nchw": (i, [vp, i, i, i64, vp, vp]),
+        "masic_cqe_blend_images": (i, [vp, vp, vp, i, i, i, vp, vp]),
+        "masic_cqe_feature_fuse": (i, [vp, i, vp, i, i, vp, vp, i, i, i, vp, i, vp]),
+        "masic_cqe_residual_image": (i, [vp, i, vp, i, i, i, vp, vp]),
         "masic_rd_metrics_scratch_bytes": (i64, []),
         "masic_rd_metrics": (i, [C.POINTER(vp), C.POINTER(i64), vp, vp, vp, vp, i, i, i, i, f, vp, vp, vp]),
     }

@@ -135,6 +135,50 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
   return v;
 }
 
+// packed fp32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100a): the epilogue is instruction-issue bound, so every
+// bias add / square / scale works on two channels per instruction
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void upk2u(uint64_t v, uint32_t& lo, uint32_t& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_p(uint64_t v) {   // bf16x2 {lo, hi} of a packed fp32 pair
+  float lo, hi;
+  upk2(v, lo, hi);
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {           // one MUFU.RSQ (rsqrtf() adds a denormal fix-up path)
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void ld_shared_p2(uint32_t addr, uint64_t& a, uint64_t& b) {   // four floats as two pairs
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+
 // A work item: `cnt` consecutive tiles of the same group (variant, n-tile): up to `pair` per CTA, i.e. up to
 // 2*pair for a CTA pair, where tile k of the item lives in CTA (k & 1), accumulator slot (k >> 1).
 struct Item {
@@ -144,27 +188,49 @@ struct Item {
   bool valid[2];  // does this CTA own a tile in slot t
   int n[2], y0[2], x0[2];
 };
-__device__ __forceinline__ void decode_tile(const KParams& p, int s, int& n, int& y0, int& x0) {
-  const int tx = s % p.tiles_x;
-  const int r = s / p.tiles_x;
-  x0 = tx * TILE_W;
-  y0 = (r % p.tiles_y) * TILE_H;
-  n = r / p.tiles_y;
+// Position in the tile sequence u = (variant, n-tile, image, tile row, tile column): every role walks its CTA's range
+// with one division at the start and increments afterwards (the walk used to cost ~10 % of all issued instructions).
+struct Cursor { int u, s, nt, var, tx, ty, n; };
+__device__ __forceinline__ Cursor cursor_init(const KParams& p, int u) {
+  Cursor c;
+  c.u = u;
+  const int g = u / p.n_spatial;
+  c.s = u - g * p.n_spatial;
+  c.nt = g % p.n_ntiles;
+  c.var = g / p.n_ntiles;
+  c.tx = c.s % p.tiles_x;
+  const int r = c.s / p.tiles_x;
+  c.ty = r % p.tiles_y;
+  c.n = r / p.tiles_y;
+  return c;
 }
 template <bool CG2>
-__device__ __forceinline__ Item decode_item(const KParams& p, int u, int u_end, int rank) {
+__device__ __forceinline__ Item next_item(const KParams& p, Cursor& c, int u_end, int rank) {
   Item it;
-  const int g = u / p.n_spatial, s = u - g * p.n_spatial;
-  it.nt = g % p.n_ntiles;
-  it.var = g / p.n_ntiles;
+  it.nt = c.nt;
+  it.var = c.var;
   const int cap = CG2 ? 2 * p.pair : p.pair;
-  it.cnt = min(cap, min(u_end - u, p.n_spatial - s));
+  it.cnt = min(cap, min(u_end - c.u, p.n_spatial - c.s));
   it.nslots = CG2 ? (it.cnt + 1) >> 1 : it.cnt;
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
-    const int k = CG2 ? 2 * t + rank : t;
-    it.valid[t] = k < it.cnt;
-    decode_tile(p, it.valid[t] ? s + k : s, it.n[t], it.y0[t], it.x0[t]);
+    it.valid[t] = false; it.n[t] = c.n; it.y0[t] = c.ty * TILE_H; it.x0[t] = c.tx * TILE_W;
+  }
+#pragma unroll
+  for (int k = 0; k < (CG2 ? 4 : 2); ++k) {
+    if (k < it.cnt) {
+      const int t = CG2 ? (k >> 1) : k;
+      if (!CG2 || (k & 1) == rank) {
+        it.valid[t] = true; it.n[t] = c.n; it.y0[t] = c.ty * TILE_H; it.x0[t] = c.tx * TILE_W;
+      }
+      if (++c.tx == p.tiles_x) { c.tx = 0; if (++c.ty == p.tiles_y) { c.ty = 0; ++c.n; } }
+    }
+  }
+  c.u += it.cnt;
+  c.s += it.cnt;
+  if (c.s == p.n_spatial) {
+    c.s = 0; c.tx = 0; c.ty = 0; c.n = 0;
+    if (++c.nt == p.n_ntiles) { c.nt = 0; ++c.var; }
   }
   return it;
 }
@@ -245,9 +311,8 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     // ===================== A producer: activation strips =====================
     uint32_t st = 0, ph = 0;
     const uint32_t n_st = p.a_stages, strip_bytes = p.strip_bytes, st_bytes = p.pair * p.strip_bytes;
-    for (int u = u_begin; u < u_end;) {
-      const Item it = decode_item<CG2>(p, u, u_end, rank);
-      u += it.cnt;
+    for (Cursor cur = cursor_init(p, u_begin); cur.u < u_end;) {
+      const Item it = next_item<CG2>(p, cur, u_end, rank);
       const int i0 = p.var[it.var].strip_off, i1 = i0 + p.var[it.var].n_strips;
       for (int i = i0; i < i1; ++i) {
         const Strip sp = p.strips[i];
@@ -295,9 +360,8 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     __syncwarp();
     uint32_t st = 0, ph = 0;
     const uint32_t n_st = p.b_stages, st_bytes = p.b_stage_bytes;
-    for (int u = u_begin; u < u_end;) {
-      const Item it = decode_item<CG2>(p, u, u_end, rank);
-      u += it.cnt;
+    for (Cursor cur = cursor_init(p, u_begin); cur.u < u_end;) {
+      const Item it = next_item<CG2>(p, cur, u_end, rank);
       // a CTA of a pair stages its half of the n-tile's rows (st_bytes = that half)
       const int nrow = it.nt * p.n_tile + (CG2 ? rank * (p.n_tile >> 1) : 0);
       const int i0 = p.var[it.var].bop_off, i1 = i0 + p.var[it.var].n_bops;
@@ -331,9 +395,8 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     const uint32_t a_step = (p.pair * p.strip_bytes) >> 4, b_step = p.b_stage_bytes >> 4;
     const uint32_t idesc = p.idesc;
     int n_item = 0;
-    for (int u = u_begin; u < u_end; ++n_item) {
-      const Item it = decode_item<CG2>(p, u, u_end, rank);
-      u += it.cnt;
+    for (Cursor cur = cursor_init(p, u_begin); cur.u < u_end; ++n_item) {
+      const Item it = next_item<CG2>(p, cur, u_end, rank);
       const int buf = n_item & 1;
       mbar_wait(sMisc + MISC_ACC_EMPTY + 8 * buf, ((n_item >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -413,9 +476,8 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
       tc_fence_before();
       if (CG2) mbar_arrive_cluster(acc_empty0 + 8 * buf); else mbar_arrive(acc_empty0 + 8 * buf);
     };
-    for (int u = u_begin; u < u_end; ++n_item) {
-      const Item it = decode_item<CG2>(p, u, u_end, rank);
-      u += it.cnt;
+    for (Cursor cur = cursor_init(p, u_begin); cur.u < u_end; ++n_item) {
+      const Item it = next_item<CG2>(p, cur, u_end, rank);
       const Variant& v = p.var[it.var];
       const int buf = n_item & 1;
       const float slope = p.slope[it.nt];
@@ -429,14 +491,16 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
       for (int tt = 0; tt < it.nslots; ++tt) {
         const uint32_t acc_addr = tmem_base + lane_sel + buf * 256 + tt * 128;
         const bool last_tile = (tt + 1 == it.nslots);
-        const bool valid = it.valid[tt];          // CTA pairs: an odd item leaves the peer's last slot without a tile
+        // selects instead of dynamically indexed arrays (those would live in local memory)
+        const bool valid = tt ? it.valid[1] : it.valid[0];
+        const int tn = tt ? it.n[1] : it.n[0], ty0 = tt ? it.y0[1] : it.y0[0], tx0 = tt ? it.x0[1] : it.x0[0];          // CTA pairs: an odd item leaves the peer's last slot without a tile
         float rs = 1.0f;
         size_t pix = 0;                           // linear output pixel of this thread's row (residual / rowscale)
         bool pix_ok = false;
         if ((p.rowscale || p.res0) && valid) {
-          const int y = it.y0[tt] + (t >> 3), x = it.x0[tt] + (t & 7);
+          const int y = ty0 + (t >> 3), x = tx0 + (t & 7);
           pix_ok = y < p.rs_H && x < p.rs_W;
-          pix = static_cast<size_t>(it.n[tt] * p.rs_H + y) * p.rs_W + x;
+          pix = static_cast<size_t>(tn * p.rs_H + y) * p.rs_W + x;
           if (p.rowscale && pix_ok) rs = __ldg(p.rowscale + pix * p.rs_stride + p.rs_off);
         }
         if (p.gdn) {
@@ -449,21 +513,20 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
           tmem_ld_wait();
           named_bar_sync(pbar, 256);
           const uint32_t arow = sbuf + t * 128;
-          float x[32];
+          uint64_t x2[16];                                // x = acc + bias, two channels per register pair
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 b4 = ld_shared_f4(bias_s + (cb + 4 * q) * 4);
-            x[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b4.x;
-            x[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
-            x[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z;
-            x[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
+            uint64_t b0, b1;
+            ld_shared_p2(bias_s + (cb + 4 * q) * 4, b0, b1);
+            x2[2 * q] = add2(pk2u(r[4 * q], r[4 * q + 1]), b0);
+            x2[2 * q + 1] = add2(pk2u(r[4 * q + 2], r[4 * q + 3]), b1);
           }
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {
-            const float* xx = &x[8 * c8];
-            st_shared_v4(arow + (((4 * half + c8) ^ (t & 7)) << 4), pack_bf16x2(xx[0] * xx[0], xx[1] * xx[1]),
-                         pack_bf16x2(xx[2] * xx[2], xx[3] * xx[3]), pack_bf16x2(xx[4] * xx[4], xx[5] * xx[5]),
-                         pack_bf16x2(xx[6] * xx[6], xx[7] * xx[7]));
+            const uint64_t* xx = &x2[4 * c8];
+            st_shared_v4(arow + (((4 * half + c8) ^ (t & 7)) << 4), pack_bf16x2_p(mul2(xx[0], xx[0])),
+                         pack_bf16x2_p(mul2(xx[1], xx[1])), pack_bf16x2_p(mul2(xx[2], xx[2])),
+                         pack_bf16x2_p(mul2(xx[3], xx[3])));
           }
           fence_proxy_async_smem();
           tc_fence_before();
@@ -503,30 +566,37 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
           tmem_ld16(acc_addr + cb + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
           tmem_ld_wait();
           if (last_tile) release_acc(buf);              // last TMEM read of this item's accumulators
+          // IGDN: sqrt(n) = n * rsqrt(n) on the MUFU fast path (2-ulp rsqrt is far below bf16 rounding)
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 e4 = ld_shared_f4(beta_s + (cb + 4 * q) * 4);
-            const float ee[4] = {e4.x, e4.y, e4.z, e4.w};
+            uint64_t e0, e1;
+            ld_shared_p2(beta_s + (cb + 4 * q) * 4, e0, e1);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float nrm = __uint_as_float(r[4 * q + e]) + ee[e];
-              // IGDN: sqrt(n) = n * rsqrt(n) on the MUFU fast path (2-ulp rsqrt is far below bf16 rounding)
-              const float rn = rsqrtf(nrm);
-              const float xv = x[4 * q + e];
-              x[4 * q + e] = (fwd ? xv * rn : xv * (nrm * rn)) * rs;
+            for (int e = 0; e < 2; ++e) {
+              const uint64_t nrm = add2(pk2u(r[4 * q + 2 * e], r[4 * q + 2 * e + 1]), e ? e1 : e0);
+              float n0, n1;
+              upk2(nrm, n0, n1);
+              uint64_t f = pk2(rsqrt_approx(n0), rsqrt_approx(n1));
+              if (!fwd) f = mul2(f, nrm);
+              x2[2 * q + e] = mul2(x2[2 * q + e], f);
             }
+          }
+          if (p.rowscale) {
+            const uint64_t rs2 = pk2(rs, rs);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x2[i] = mul2(x2[i], rs2);
           }
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {
-            const float* xx = &x[8 * c8];
-            st_shared_v4(arow + (((4 * half + c8) ^ (t & 7)) << 4), pack_bf16x2(xx[0], xx[1]), pack_bf16x2(xx[2], xx[3]),
-                         pack_bf16x2(xx[4], xx[5]), pack_bf16x2(xx[6], xx[7]));
+            const uint64_t* xx = &x2[4 * c8];
+            st_shared_v4(arow + (((4 * half + c8) ^ (t & 7)) << 4), pack_bf16x2_p(xx[0]), pack_bf16x2_p(xx[1]),
+                         pack_bf16x2_p(xx[2]), pack_bf16x2_p(xx[3]));
           }
           fence_proxy_async_smem();
           named_bar_sync(pbar, 256);
           if (leader && !nostore && valid) {
-            tma_store_5d(&p.tmO, sbuf, p.out_coff + v.out_c0 + it.nt * p.n_tile + 64 * pr, it.x0[tt], v.out_p2, it.y0[tt],
-                         it.n[tt]);
+            tma_store_5d(&p.tmO, sbuf, p.out_coff + v.out_c0 + it.nt * p.n_tile + 64 * pr, tx0, v.out_p2, ty0,
+                         tn);
             tma_store_commit();
           }
         } else {
@@ -550,17 +620,34 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
             for (int kk = 0; kk < 2; ++kk) {
               if (kk == 0 ? has0 : has1) {
                 const int ch = c + 16 * (k0 + kk);       // channel inside the n-tile
-                float o[16];
+                uint64_t o2[8];                          // 16 channels as packed pairs
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (bias_t) b4 = __ldg(reinterpret_cast<const float4*>(bias_t + ch) + q);
-                  const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                  o2[2 * q] = pk2u(r[16 * kk + 4 * q], r[16 * kk + 4 * q + 1]);
+                  o2[2 * q + 1] = pk2u(r[16 * kk + 4 * q + 2], r[16 * kk + 4 * q + 3]);
+                }
+                if (bias_t) {
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float xv = __uint_as_float(r[16 * kk + 4 * q + e]) + bb[e];
-                    o[4 * q + e] = fmaf(slope, fminf(xv, 0.0f), fmaxf(xv, 0.0f)) * rs;
+                  for (int q = 0; q < 4; ++q) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_t + ch) + q);
+                    o2[2 * q] = add2(o2[2 * q], pk2(b4.x, b4.y));
+                    o2[2 * q + 1] = add2(o2[2 * q + 1], pk2(b4.z, b4.w));
                   }
+                }
+                if (slope != 1.0f) {                     // ReLU / LeakyReLU: max(x, slope * x) for slope in [0, 1)
+                  const uint64_t sl2 = pk2(slope, slope);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    float a0, a1, s0, s1;
+                    upk2(o2[i], a0, a1);
+                    upk2(mul2(o2[i], sl2), s0, s1);
+                    o2[i] = pk2(fmaxf(a0, s0), fmaxf(a1, s1));
+                  }
+                }
+                if (p.rowscale) {
+                  const uint64_t rs2 = pk2(rs, rs);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) o2[i] = mul2(o2[i], rs2);
                 }
                 if (p.res0 && pix_ok) {            // out += residual(s): 16 bf16 = two 16-byte loads each
                   const int gch = it.nt * p.n_tile + ch;
@@ -575,31 +662,33 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                       const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
-                      o[2 * e] += f.x; o[2 * e + 1] += f.y;
+                      o2[e] = add2(o2[e], pk2(f.x, f.y));
                     }
                   }
                 }
                 if (p.out_fp32) {
                   const int ch16 = 4 * (k0 + kk);        // 16 fp32 = four 16-B chunks
 #pragma unroll
-                  for (int q = 0; q < 4; ++q)
-                    st_shared_v4(row + (((ch16 + q) ^ sw) << 4), __float_as_uint(o[4 * q]), __float_as_uint(o[4 * q + 1]),
-                                 __float_as_uint(o[4 * q + 2]), __float_as_uint(o[4 * q + 3]));
+                  for (int q = 0; q < 4; ++q) {
+                    uint32_t w0, w1, w2, w3;
+                    upk2u(o2[2 * q], w0, w1);
+                    upk2u(o2[2 * q + 1], w2, w3);
+                    st_shared_v4(row + (((ch16 + q) ^ sw) << 4), w0, w1, w2, w3);
+                  }
                 } else {
                   const int ch16 = 2 * (k0 + kk);        // 16 bf16 = two 16-B chunks
 #pragma unroll
                   for (int q = 0; q < 2; ++q)
-                    st_shared_v4(row + (((ch16 + q) ^ sw) << 4), pack_bf16x2(o[8 * q], o[8 * q + 1]),
-                                 pack_bf16x2(o[8 * q + 2], o[8 * q + 3]), pack_bf16x2(o[8 * q + 4], o[8 * q + 5]),
-                                 pack_bf16x2(o[8 * q + 6], o[8 * q + 7]));
+                    st_shared_v4(row + (((ch16 + q) ^ sw) << 4), pack_bf16x2_p(o2[4 * q]), pack_bf16x2_p(o2[4 * q + 1]),
+                                 pack_bf16x2_p(o2[4 * q + 2]), pack_bf16x2_p(o2[4 * q + 3]));
                 }
               }
             }
             fence_proxy_async_smem();
             named_bar_sync(pbar, 256);
             if (leader && !nostore && valid) {
-              tma_store_5d(&p.tmO, sb2, p.out_coff + v.out_c0 + it.nt * p.n_tile + c, it.x0[tt], v.out_p2, it.y0[tt],
-                           it.n[tt]);
+              tma_store_5d(&p.tmO, sb2, p.out_coff + v.out_c0 + it.nt * p.n_tile + c, tx0, v.out_p2, ty0,
+                           tn);
               tma_store_commit();
             }
           }
