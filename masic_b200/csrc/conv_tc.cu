@@ -235,7 +235,11 @@ __device__ __forceinline__ Item next_item(const KParams& p, Cursor& c, int u_end
   return it;
 }
 
-template <bool CG2>
+// EPI selects the epilogue at compile time so that each variant gets its own register allocation (the GDN epilogue
+// is issue- and latency-bound: a spill there costs ~40 % on the 608x1088 layers)
+constexpr int EPI_PLAIN = 0, EPI_GDN = 1, EPI_RES = 2;
+
+template <bool CG2, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -285,7 +289,7 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     if (CG2) { tmem_alloc_cg2(sMisc + MISC_TMEM_PTR, TMEM_COLS); tmem_relinquish_cg2(); }
     else { tmem_alloc(sMisc + MISC_TMEM_PTR, TMEM_COLS); tmem_relinquish(); }
   }
-  if (p.gdn && threadIdx.x >= 128) {       // the single n-tile's bias / beta' stay in smem for the whole kernel
+  if (EPI == EPI_GDN && threadIdx.x >= 128) {       // the single n-tile's bias / beta' stay in smem for the whole kernel
     float* bs = reinterpret_cast<float*>(smem_gen + p.smem_misc_off + MISC_BIAS);
     float* be = reinterpret_cast<float*>(smem_gen + p.smem_misc_off + MISC_BETA);
     const int i = threadIdx.x - 128;
@@ -344,7 +348,7 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     }
   } else if (warp == 1 && !free_run) {
     // ===================== B producer: weight k-blocks (+ gamma once) =====================
-    if (p.gdn && elect_one()) {
+    if (EPI == EPI_GDN && elect_one()) {
       tma_prefetch_desc(&p.tmG);
       if (CG2) {          // each CTA holds the 64 N-rows of gamma' it feeds to the pair's norm MMA
         if (rank == 0) mbar_expect_tx(sMisc + MISC_G_FULL, 2 * STAGE_BLK_BYTES);
@@ -459,18 +463,19 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     const uint32_t pbar = 1 + pr;       // named barrier of this pair (256 threads); barrier 3 = all epilogue threads
     const bool leader = (t == 0 && half == 0);   // issues this pair's TMA stores (bulk groups are per thread)
     const int nblk = p.n_tile / p.blk_ch;
-    const uint32_t sbuf = sStage + pr * (p.gdn ? 1 : 2) * STAGE_BLK_BYTES;
+    const uint32_t sbuf = sStage + pr * (EPI == EPI_GDN ? 1 : 2) * STAGE_BLK_BYTES;
     const uint32_t bias_s = sMisc + MISC_BIAS, beta_s = sMisc + MISC_BETA;
     uint32_t flip = 0, gdn_par = 0;
     const float* __restrict__ bias_g = p.bias;
     const bool fwd = (p.gdn == MASIC_GDN_FWD);
     const bool nostore = (p.debug & 4) != 0;
     const int sw = (p.blk_pitch == 128) ? (t & 7) : 0;
-    // plain path: this group's 16-channel chunks inside a block: bf16 rows hold 4 (2 per group), fp32 rows 2 (1 per group)
-    const int cpg = p.out_fp32 ? 1 : 2;
+    // plain path: a block's 16-channel chunks are split between the pair's two groups (bf16 rows hold up to 4 chunks,
+    // fp32 rows 2); a group handles at most two
     const int nchunk_blk = p.blk_ch / 16;
+    const int cpg = (nchunk_blk + 1) >> 1;
     int n_item = 0;
-    if (p.gdn && rank == 0 && grp == 0 && ew == 0) mbar_wait_cluster(sMisc + MISC_G_FULL, 0);
+    if (EPI == EPI_GDN && rank == 0 && grp == 0 && ew == 0) mbar_wait_cluster(sMisc + MISC_G_FULL, 0);
     const uint32_t acc_empty0 = leader_bar(sMisc + MISC_ACC_EMPTY);
     auto release_acc = [&](int buf) {              // this thread has finished reading the item's accumulators
       tc_fence_before();
@@ -488,22 +493,20 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
         release_acc(buf);
         continue;
       }
+      if (EPI == EPI_GDN) {
       for (int tt = 0; tt < it.nslots; ++tt) {
         const uint32_t acc_addr = tmem_base + lane_sel + buf * 256 + tt * 128;
         const bool last_tile = (tt + 1 == it.nslots);
         // selects instead of dynamically indexed arrays (those would live in local memory)
-        const bool valid = tt ? it.valid[1] : it.valid[0];
-        const int tn = tt ? it.n[1] : it.n[0], ty0 = tt ? it.y0[1] : it.y0[0], tx0 = tt ? it.x0[1] : it.x0[0];          // CTA pairs: an odd item leaves the peer's last slot without a tile
+        const bool valid = tt ? it.valid[1] : it.valid[0];   // CTA pairs: an odd item leaves the peer's last slot without a tile
+        const int tn = tt ? it.n[1] : it.n[0], ty0 = tt ? it.y0[1] : it.y0[0], tx0 = tt ? it.x0[1] : it.x0[0];
         float rs = 1.0f;
-        size_t pix = 0;                           // linear output pixel of this thread's row (residual / rowscale)
-        bool pix_ok = false;
-        if ((p.rowscale || p.res0) && valid) {
+        if (p.rowscale && valid) {
           const int y = ty0 + (t >> 3), x = tx0 + (t & 7);
-          pix_ok = y < p.rs_H && x < p.rs_W;
-          pix = static_cast<size_t>(tn * p.rs_H + y) * p.rs_W + x;
-          if (p.rowscale && pix_ok) rs = __ldg(p.rowscale + pix * p.rs_stride + p.rs_off);
+          if (y < p.rs_H && x < p.rs_W)
+            rs = __ldg(p.rowscale + (static_cast<size_t>(tn * p.rs_H + y) * p.rs_W + x) * p.rs_stride + p.rs_off);
         }
-        if (p.gdn) {
+        {
           // ---- pass 1: x = acc + bias stays in registers; A2[:, 32g .. 32g+32) = bf16(x^2) (SWIZZLE_128B block pr)
           const int cb = grp * 32;
           uint32_t r[32];
@@ -599,100 +602,130 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
                          tn);
             tma_store_commit();
           }
-        } else {
-          // ---- plain epilogue: bias, activation, per-pixel scale
-          for (int j = pr; j < nblk; j += 2) {
-            const uint32_t sb2 = sbuf + flip * STAGE_BLK_BYTES;
-            flip ^= 1;
-            const int c = j * p.blk_ch;                 // first channel of the block inside the n-tile
-            const uint32_t row = sb2 + t * p.blk_pitch;
-            const bool last_read = last_tile && (j + 2 >= nblk);
-            const int k0 = half * cpg;                  // this group's first 16-channel chunk of the block
-            const bool has0 = k0 < nchunk_blk, has1 = cpg == 2 && k0 + 1 < nchunk_blk;
-            uint32_t r[32];
-            if (has0) tmem_ld16(acc_addr + c + 16 * k0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-            if (has1) tmem_ld16(acc_addr + c + 16 * k0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
-            if (leader) tma_store_wait_read<1>();        // the store issued two blocks ago has left this buffer
-            tmem_ld_wait();
-            if (last_read) release_acc(buf);
-            named_bar_sync(pbar, 256);
+        }
+      }
+      } else {
+        // ---- plain epilogue: bias, activation, per-pixel scale, residual adds.  The item's (tile, block) units are dealt
+        // round-robin to the two group pairs, so two narrow tiles (<= 64 channels) drain concurrently.
+        const int n_units = it.nslots * nblk;
+        if (pr >= n_units) release_acc(buf);         // nothing to do for this group pair
+        int tt = 0, j = pr;
+        while (j >= nblk) { j -= nblk; ++tt; }
+        for (int q = pr; q < n_units; q += 2) {
+          const uint32_t acc_addr = tmem_base + lane_sel + buf * 256 + tt * 128;
+          const bool valid = tt ? it.valid[1] : it.valid[0];
+          const int tn = tt ? it.n[1] : it.n[0], ty0 = tt ? it.y0[1] : it.y0[0], tx0 = tt ? it.x0[1] : it.x0[0];
+          float rs = 1.0f;
+          size_t pix = 0;                           // linear output pixel of this thread's row (residual / rowscale)
+          bool pix_ok = false;
+          if ((p.rowscale || EPI == EPI_RES) && valid) {
+            const int y = ty0 + (t >> 3), x = tx0 + (t & 7);
+            pix_ok = y < p.rs_H && x < p.rs_W;
+            pix = static_cast<size_t>(tn * p.rs_H + y) * p.rs_W + x;
+            if (p.rowscale && pix_ok) rs = __ldg(p.rowscale + pix * p.rs_stride + p.rs_off);
+          }
+          const uint32_t sb2 = sbuf + flip * STAGE_BLK_BYTES;
+          flip ^= 1;
+          const int c = j * p.blk_ch;                 // first channel of the block inside the n-tile
+          const uint32_t row = sb2 + t * p.blk_pitch;
+          const int k0 = half * cpg;                  // this group's first 16-channel chunk of the block
+          const bool has0 = k0 < nchunk_blk, has1 = cpg == 2 && k0 + 1 < nchunk_blk;
+          // residual rows are fetched first: their latency hides behind the TMEM load and the pair barrier
+          const bool do_res = EPI == EPI_RES && pix_ok;
+          uint4 rv[8];
+          if (do_res) {
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
               if (kk == 0 ? has0 : has1) {
-                const int ch = c + 16 * (k0 + kk);       // channel inside the n-tile
-                uint64_t o2[8];                          // 16 channels as packed pairs
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  o2[2 * q] = pk2u(r[16 * kk + 4 * q], r[16 * kk + 4 * q + 1]);
-                  o2[2 * q + 1] = pk2u(r[16 * kk + 4 * q + 2], r[16 * kk + 4 * q + 3]);
-                }
-                if (bias_t) {
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_t + ch) + q);
-                    o2[2 * q] = add2(o2[2 * q], pk2(b4.x, b4.y));
-                    o2[2 * q + 1] = add2(o2[2 * q + 1], pk2(b4.z, b4.w));
-                  }
-                }
-                if (slope != 1.0f) {                     // ReLU / LeakyReLU: max(x, slope * x) for slope in [0, 1)
-                  const uint64_t sl2 = pk2(slope, slope);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    float a0, a1, s0, s1;
-                    upk2(o2[i], a0, a1);
-                    upk2(mul2(o2[i], sl2), s0, s1);
-                    o2[i] = pk2(fmaxf(a0, s0), fmaxf(a1, s1));
-                  }
-                }
-                if (p.rowscale) {
-                  const uint64_t rs2 = pk2(rs, rs);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) o2[i] = mul2(o2[i], rs2);
-                }
-                if (p.res0 && pix_ok) {            // out += residual(s): 16 bf16 = two 16-byte loads each
-                  const int gch = it.nt * p.n_tile + ch;
-#pragma unroll
-                  for (int rr = 0; rr < 2; ++rr) {
-                    const __nv_bfloat16* rp = rr == 0 ? p.res0 + pix * p.res0_pitch + p.res0_coff + gch
-                                                      : (p.res1 ? p.res1 + pix * p.res1_pitch + p.res1_coff + gch : nullptr);
-                    if (!rp) continue;
-                    const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(rp));
-                    const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-                    const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
-                      o2[e] = add2(o2[e], pk2(f.x, f.y));
-                    }
-                  }
-                }
-                if (p.out_fp32) {
-                  const int ch16 = 4 * (k0 + kk);        // 16 fp32 = four 16-B chunks
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    uint32_t w0, w1, w2, w3;
-                    upk2u(o2[2 * q], w0, w1);
-                    upk2u(o2[2 * q + 1], w2, w3);
-                    st_shared_v4(row + (((ch16 + q) ^ sw) << 4), w0, w1, w2, w3);
-                  }
-                } else {
-                  const int ch16 = 2 * (k0 + kk);        // 16 bf16 = two 16-B chunks
-#pragma unroll
-                  for (int q = 0; q < 2; ++q)
-                    st_shared_v4(row + (((ch16 + q) ^ sw) << 4), pack_bf16x2_p(o2[4 * q]), pack_bf16x2_p(o2[4 * q + 1]),
-                                 pack_bf16x2_p(o2[4 * q + 2]), pack_bf16x2_p(o2[4 * q + 3]));
+                const int gch = it.nt * p.n_tile + c + 16 * (k0 + kk);
+                const uint4* r0 = reinterpret_cast<const uint4*>(p.res0 + pix * p.res0_pitch + p.res0_coff + gch);
+                rv[4 * kk] = __ldg(r0); rv[4 * kk + 1] = __ldg(r0 + 1);
+                if (p.res1) {
+                  const uint4* r1 = reinterpret_cast<const uint4*>(p.res1 + pix * p.res1_pitch + p.res1_coff + gch);
+                  rv[4 * kk + 2] = __ldg(r1); rv[4 * kk + 3] = __ldg(r1 + 1);
                 }
               }
             }
-            fence_proxy_async_smem();
-            named_bar_sync(pbar, 256);
-            if (leader && !nostore && valid) {
-              tma_store_5d(&p.tmO, sb2, p.out_coff + v.out_c0 + it.nt * p.n_tile + c, tx0, v.out_p2, ty0,
-                           tn);
-              tma_store_commit();
+          }
+          uint32_t r[32];
+          if (has0) tmem_ld16(acc_addr + c + 16 * k0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+          if (has1) tmem_ld16(acc_addr + c + 16 * k0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+          if (leader) tma_store_wait_read<1>();        // the store issued two blocks ago has left this buffer
+          tmem_ld_wait();
+          if (q + 2 >= n_units) release_acc(buf);      // this thread's last TMEM read of the item
+          named_bar_sync(pbar, 256);
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            if (kk == 0 ? has0 : has1) {
+              const int ch = c + 16 * (k0 + kk);       // channel inside the n-tile
+              uint64_t o2[8];                          // 16 channels as packed pairs
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                o2[2 * e] = pk2u(r[16 * kk + 4 * e], r[16 * kk + 4 * e + 1]);
+                o2[2 * e + 1] = pk2u(r[16 * kk + 4 * e + 2], r[16 * kk + 4 * e + 3]);
+              }
+              if (bias_t) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_t + ch) + e);
+                  o2[2 * e] = add2(o2[2 * e], pk2(b4.x, b4.y));
+                  o2[2 * e + 1] = add2(o2[2 * e + 1], pk2(b4.z, b4.w));
+                }
+              }
+              if (slope != 1.0f) {                     // ReLU / LeakyReLU: max(x, slope * x) for slope in [0, 1)
+                const uint64_t sl2 = pk2(slope, slope);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  float a0, a1, s0, s1;
+                  upk2(o2[i], a0, a1);
+                  upk2(mul2(o2[i], sl2), s0, s1);
+                  o2[i] = pk2(fmaxf(a0, s0), fmaxf(a1, s1));
+                }
+              }
+              if (p.rowscale) {
+                const uint64_t rs2 = pk2(rs, rs);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o2[i] = mul2(o2[i], rs2);
+              }
+              if (do_res) {                            // out += residual(s): 16 bf16 = two 16-byte words each
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                  if (rr == 1 && !p.res1) continue;
+                  const uint4 u0 = rv[4 * kk + 2 * rr], u1 = rv[4 * kk + 2 * rr + 1];
+                  const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+                    o2[e] = add2(o2[e], pk2(f.x, f.y));
+                  }
+                }
+              }
+              if (p.out_fp32) {
+                const int ch16 = 4 * (k0 + kk);        // 16 fp32 = four 16-B chunks
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  uint32_t w0, w1, w2, w3;
+                  upk2u(o2[2 * e], w0, w1);
+                  upk2u(o2[2 * e + 1], w2, w3);
+                  st_shared_v4(row + (((ch16 + e) ^ sw) << 4), w0, w1, w2, w3);
+                }
+              } else {
+                const int ch16 = 2 * (k0 + kk);        // 16 bf16 = two 16-B chunks
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                  st_shared_v4(row + (((ch16 + e) ^ sw) << 4), pack_bf16x2_p(o2[4 * e]), pack_bf16x2_p(o2[4 * e + 1]),
+                               pack_bf16x2_p(o2[4 * e + 2]), pack_bf16x2_p(o2[4 * e + 3]));
+              }
             }
           }
-          if (last_tile && pr >= nblk) release_acc(buf);   // nothing to do for this group pair (single-block tile)
+          fence_proxy_async_smem();
+          named_bar_sync(pbar, 256);
+          if (leader && !nostore && valid) {
+            tma_store_5d(&p.tmO, sb2, p.out_coff + v.out_c0 + it.nt * p.n_tile + c, tx0, v.out_p2, ty0, tn);
+            tma_store_commit();
+          }
+          j += 2;                                      // next unit of this pair: (tt, j) advances by two blocks
+          while (j >= nblk) { j -= nblk; ++tt; }
         }
       }
     }
@@ -1088,9 +1121,11 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
 
   static bool attr_set = false;
   if (!attr_set) {
-    ce = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (ce == cudaSuccess)
-      ce = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    const void* fns[6] = {(const void*)conv_tc_kernel<false, EPI_PLAIN>, (const void*)conv_tc_kernel<false, EPI_GDN>,
+                          (const void*)conv_tc_kernel<false, EPI_RES>, (const void*)conv_tc_kernel<true, EPI_PLAIN>,
+                          (const void*)conv_tc_kernel<true, EPI_GDN>, (const void*)conv_tc_kernel<true, EPI_RES>};
+    for (int i = 0; i < 6 && ce == cudaSuccess; ++i)
+      ce = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (ce != cudaSuccess) { delete pl; return (int)ce; }
     attr_set = true;
   }
@@ -1119,8 +1154,15 @@ extern "C" int masic_conv_plan_launch(const MasicConvPlan* pl, void* stream) {
     ++na;
   }
   cfg.attrs = attr; cfg.numAttrs = na;
-  if (pl->kp.cg2) return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, pl->kp);
-  return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, pl->kp);
+  const int epi = pl->kp.gdn ? EPI_GDN : (pl->kp.res0 ? EPI_RES : EPI_PLAIN);
+  if (pl->kp.cg2) {
+    if (epi == EPI_GDN) return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, EPI_GDN>, pl->kp);
+    if (epi == EPI_RES) return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, EPI_RES>, pl->kp);
+    return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, EPI_PLAIN>, pl->kp);
+  }
+  if (epi == EPI_GDN) return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, EPI_GDN>, pl->kp);
+  if (epi == EPI_RES) return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, EPI_RES>, pl->kp);
+  return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, EPI_PLAIN>, pl->kp);
 }
 
 extern "C" void masic_conv_plan_destroy(MasicConvPlan* pl) {
