@@ -38,7 +38,7 @@ extern "C" {
 #define MASIC_EDRIVER (-3)  /* cuTensorMapEncodeTiled unavailable / failed  */
 
 /* ---------------------------------------------------------------- version */
-int masic_abi_version(void);                 /* bumps on any signature change (2: residual inputs of MasicConvDesc) */
+int masic_abi_version(void);                 /* bumps on any signature change (2: residual inputs, 3: grouped launches of MasicConvDesc) */
 const char* masic_build_info(void);          /* "sm_100a nvcc 12.9 ..." */
 
 /* ------------------------------------------------------------------ convs */
@@ -93,6 +93,12 @@ typedef struct MasicConvDesc {
    * Enhancement_Block, MASIC.py:149-164).  Channel c of the output reads residual[... * cpitch + coff + c]. */
   const void* residual0; int res0_cpitch; int res0_coff;
   const void* residual1; int res1_cpitch; int res1_coff;
+  /* optional GROUPED launch (block-diagonal weights): several layers that share K = c_in and the spatial size run
+   * as one plan, n-tile t of the packed weights reading input channels [in_coff + nt_in_coff[t], +c_in) and writing
+   * its n_tile outputs at channel out_coff + nt_out_coff[t] of output image n + nt_out_img[t] (the out buffer then
+   * holds out_images >= n images).  HOST arrays of c_out_pad / n_tile ints, copied at plan creation; all three NULL =
+   * ordinary convolution.  Used for the three 1x1 entropy-parameter branches (MASIC.py:338-376, :410-444). */
+  const int* nt_in_coff; const int* nt_out_coff; const int* nt_out_img; int out_images;
 } MasicConvDesc;
 
 typedef struct MasicConvPlan MasicConvPlan;   /* opaque: tensor maps + tile program */

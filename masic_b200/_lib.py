@@ -39,6 +39,8 @@ class ConvDesc(C.Structure):
         ("rowscale", C.c_void_p), ("rs_stride", C.c_int), ("rs_off", C.c_int),
         ("residual0", C.c_void_p), ("res0_cpitch", C.c_int), ("res0_coff", C.c_int),
         ("residual1", C.c_void_p), ("res1_cpitch", C.c_int), ("res1_coff", C.c_int),
+        ("nt_in_coff", C.POINTER(C.c_int)), ("nt_out_coff", C.POINTER(C.c_int)), ("nt_out_img", C.POINTER(C.c_int)),
+        ("out_images", C.c_int),
     ]
 
 

@@ -117,7 +117,9 @@ class ConvPlan:
                  gdn_gamma: Optional[torch.Tensor] = None,
                  rowscale: Optional[torch.Tensor] = None, rs_off: int = 0,
                  residual0: Optional[torch.Tensor] = None, res0_coff: int = 0,
-                 residual1: Optional[torch.Tensor] = None, res1_coff: int = 0):
+                 residual1: Optional[torch.Tensor] = None, res1_coff: int = 0,
+                 nt_in_coff: Optional[Sequence[int]] = None, nt_out_coff: Optional[Sequence[int]] = None,
+                 nt_out_img: Optional[Sequence[int]] = None):
         lib = _lib.load()
         assert x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous()
         assert out.is_cuda and out.dim() == 4 and out.is_contiguous()
@@ -160,6 +162,20 @@ class ConvPlan:
                 setattr(d, f"res{i}_cpitch", r.shape[3])
                 setattr(d, f"res{i}_coff", off)
         self.residuals = (residual0, residual1)
+        if nt_in_coff is not None or nt_out_coff is not None or nt_out_img is not None:   # grouped launch
+            tabs = []
+            for name, tab, default in (("nt_in_coff", nt_in_coff, [0] * n_nt),
+                                       ("nt_out_coff", nt_out_coff, [i * packed.n_tile for i in range(n_nt)]),
+                                       ("nt_out_img", nt_out_img, [0] * n_nt)):
+                tab = list(default if tab is None else tab)
+                assert len(tab) == n_nt, (name, len(tab), n_nt)
+                arr = (C.c_int * n_nt)(*tab)
+                tabs.append(arr)
+                setattr(d, name, C.cast(arr, C.POINTER(C.c_int)))
+            self._tabs = tabs
+            d.out_images = out.shape[0]
+        else:
+            assert out.shape[0] == n, (out.shape, n)
         self._desc = d
         handle = C.c_void_p()
         check(lib.masic_conv_plan_create(C.byref(d), C.byref(handle)), "masic_conv_plan_create")

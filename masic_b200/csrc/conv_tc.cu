@@ -99,6 +99,9 @@ struct KParams {
   const __nv_bfloat16* res0;       // optional residuals added after the activation (ResidualBlock / Enhancement_Block):
   const __nv_bfloat16* res1;       // NHWC bf16, same spatial size as the output
   int res0_pitch, res0_coff, res1_pitch, res1_coff;
+  int nt_in_coff[32];              // grouped launches: per n-tile input-channel offset,
+  int nt_out_c[32];                // output channel position (default nt * n_tile)
+  int nt_out_img[32];              // and output image offset
   uint32_t idesc;
   int debug;       // timing experiments only (results are garbage): bit0 skip A loads, bit1 skip B loads, bit2 skip stores,
                    // bit3 skip the GDN norm MMA, bit4 skip the whole epilogue
@@ -318,6 +321,7 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     for (Cursor cur = cursor_init(p, u_begin); cur.u < u_end;) {
       const Item it = next_item<CG2>(p, cur, u_end, rank);
       const int i0 = p.var[it.var].strip_off, i1 = i0 + p.var[it.var].n_strips;
+      const int gc0 = p.nt_in_coff[it.nt];
       for (int i = i0; i < i1; ++i) {
         const Strip sp = p.strips[i];
         const uint32_t full = sMisc + MISC_A_FULL + 8 * st;
@@ -333,10 +337,10 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
             for (int t = 0; t < 2; ++t) {
               if (it.valid[t]) {
                 if (CG2)
-                  tma_load_5d_cg2(sA + st * st_bytes + t * strip_bytes, &p.tmA, fl, sp.c0, it.x0[t] + sp.dx, sp.p2,
+                  tma_load_5d_cg2(sA + st * st_bytes + t * strip_bytes, &p.tmA, fl, sp.c0 + gc0, it.x0[t] + sp.dx, sp.p2,
                                   it.y0[t] + sp.dy, it.n[t]);
                 else
-                  tma_load_5d(sA + st * st_bytes + t * strip_bytes, &p.tmA, fl, sp.c0, it.x0[t] + sp.dx, sp.p2,
+                  tma_load_5d(sA + st * st_bytes + t * strip_bytes, &p.tmA, fl, sp.c0 + gc0, it.x0[t] + sp.dx, sp.p2,
                               it.y0[t] + sp.dy, it.n[t]);
               }
             }
@@ -721,7 +725,8 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
           fence_proxy_async_smem();
           named_bar_sync(pbar, 256);
           if (leader && !nostore && valid) {
-            tma_store_5d(&p.tmO, sb2, p.out_coff + v.out_c0 + it.nt * p.n_tile + c, tx0, v.out_p2, ty0, tn);
+            tma_store_5d(&p.tmO, sb2, p.out_coff + v.out_c0 + p.nt_out_c[it.nt] + c, tx0, v.out_p2, ty0,
+                         tn + p.nt_out_img[it.nt]);
             tma_store_commit();
           }
           j += 2;                                      // next unit of this pair: (tt, j) advances by two blocks
@@ -1065,7 +1070,17 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   const int ktaps = (d.kind == MASIC_DECONV_S2_SUBPIX) ? 9 : (d.kind == MASIC_CONV_XFOLD4 ? 10 : d.ksize * d.ksize);
   const int ncb = (d.kind == MASIC_CONV_XFOLD4) ? 1 : (d.c_in + KBLK - 1) / KBLK;
   if (!rc) rc = encode_rows64(&kp.tmB, d.w_packed, (long)ktaps * ncb * d.c_out_pad, kp.cg2 ? d.n_tile / 2 : d.n_tile);
-  if (!rc) rc = encode_nhwc_view(&kp.tmO, d.out, esz, d.n, out_h, out_w, d.out_cpitch, out_split,
+  const bool grouped = d.nt_in_coff || d.nt_out_coff || d.nt_out_img;
+  if (grouped && (!d.nt_in_coff || !d.nt_out_coff || !d.nt_out_img || d.out_images < d.n || d.gdn || d.residual0 ||
+                  d.rowscale || d.kind == MASIC_CONV_XFOLD4)) { delete pl; return MASIC_EINVAL; }
+  for (int i = 0; i < kp.n_ntiles; ++i) {
+    kp.nt_in_coff[i] = grouped ? d.nt_in_coff[i] : 0;
+    kp.nt_out_c[i] = grouped ? d.nt_out_coff[i] : i * d.n_tile;
+    kp.nt_out_img[i] = grouped ? d.nt_out_img[i] : 0;
+    if (kp.nt_in_coff[i] % 8 || kp.nt_out_c[i] % (d.out_fp32 ? 4 : 8) || kp.nt_out_img[i] < 0 ||
+        (grouped && kp.nt_out_img[i] + d.n > d.out_images)) { delete pl; return MASIC_EINVAL; }
+  }
+  if (!rc) rc = encode_nhwc_view(&kp.tmO, d.out, esz, grouped ? d.out_images : d.n, out_h, out_w, d.out_cpitch, out_split,
                                  kp.blk_ch, TILE_H, kp.blk_pitch == 128);
   if (!rc && d.gdn) rc = encode_gamma(&kp.tmG, d.gamma_packed, kp.cg2 ? 64 : 128);
   if (rc) { delete pl; return rc; }

@@ -214,24 +214,44 @@ class HSICEngine:
         l0 = self._buf(B, h16, w16, 18 * M)
         self._conv(f"{tag}.gmm.l0(3 branches)", p0, gmm_in, l0,
                    act=[ACT_RELU] * 6 + [ACT_LEAKY] * 12)
-        l1 = self._buf(B, h16, w16, 8 * M)
-        l1w = self._buf(B, h16, w16, MK)
-
         def pk(b, i, ci, co):
             pc = PackedConv(ksize=1, c_in=ci, c_out=co, n_tile=192, weight=self._w(f"{net}.{b}.{i}.weight"),
                             transposed=t if i == 2 else False, bias=self._w(f"{net}.{b}.{i}.bias"))
-            self.packs[f"{tag}.gmm.{b[4:]}.l{i // 2}"] = pc
+            self.packs[f"{tag}.gmm.{b[4:]}.l{i // 2}"] = pc          # per-branch packs: the per-pixel decoder's plans
             return pc
-        self._conv(f"{tag}.gmm.sigma.l1", pk("gmm_sigma", 2, 6 * M, 4 * M), l0, l1, in_coff=0, out_coff=0, act=ACT_RELU)
-        self._conv(f"{tag}.gmm.means.l1", pk("gmm_means", 2, 6 * M, 4 * M), l0, l1, in_coff=6 * M, out_coff=4 * M,
-                   act=ACT_LEAKY)
-        self._conv(f"{tag}.gmm.weights.l1", pk("gmm_weights", 2, 6 * M, MK), l0, l1w, in_coff=12 * M, act=ACT_LEAKY)
-        sig = self._buf(B, h16, w16, MK, dtype=torch.float32)
-        mu = self._buf(B, h16, w16, MK, dtype=torch.float32)
-        wl = self._buf(B, h16, w16, MK, dtype=torch.float32)
-        self._conv(f"{tag}.gmm.sigma.l2", pk("gmm_sigma", 4, 4 * M, MK), l1, sig, in_coff=0, act=ACT_RELU)
-        self._conv(f"{tag}.gmm.means.l2", pk("gmm_means", 4, 4 * M, MK), l1, mu, in_coff=4 * M)
-        self._conv(f"{tag}.gmm.weights.l2", pk("gmm_weights", 4, MK, MK), l1w, wl)
+
+        def mat(b, i):                     # 1x1 weight as (c_out, c_in); layer-1 heads of the y1 net are ConvTranspose2d
+            w = self._w(f"{net}.{b}.{i}.weight")[:, :, 0, 0]
+            return w.t() if (t and i == 2) else w
+
+        for b_, i_, ci_, co_ in (("gmm_sigma", 2, 6 * M, 4 * M), ("gmm_means", 2, 6 * M, 4 * M),
+                                 ("gmm_weights", 2, 6 * M, MK), ("gmm_sigma", 4, 4 * M, MK),
+                                 ("gmm_means", 4, 4 * M, MK), ("gmm_weights", 4, MK, MK)):
+            pk(b_, i_, ci_, co_)
+        # layer 1 of the three branches as ONE grouped launch (block-diagonal: each branch reads its own 6M slice of
+        # l0), layer 2 as two (sigma | means share K = 4M; weights has K = 5M): 4 launches per view instead of 7,
+        # 1105 / 850 work items instead of 3 x 340-425 (less wave quantisation on 148 SMs)
+        nt = lambda c: c // 192
+        l1 = self._buf(B, h16, w16, 13 * M)               # sigma 4M | means 4M | weights 5M
+        w1 = torch.cat([mat(b_, 2) for b_ in br], dim=0).reshape(13 * M, 6 * M, 1, 1).contiguous()
+        b1 = torch.cat([self._w(f"{net}.{b_}.2.bias") for b_ in br])
+        p1 = PackedConv(ksize=1, c_in=6 * M, c_out=13 * M, n_tile=192, weight=w1, bias=b1)
+        plan = ConvPlan(packed=p1, x=l0, out=l1, act=[ACT_RELU] * nt(4 * M) + [ACT_LEAKY] * nt(9 * M),
+                        nt_in_coff=[0] * nt(4 * M) + [6 * M] * nt(4 * M) + [12 * M] * nt(5 * M))
+        self.plans[f"{tag}.gmm.l1(3 branches)"] = plan
+        self._add(f"{tag}.gmm.l1(3 branches)", plan.launch)
+        smw = self._buf(3 * B, h16, w16, MK, dtype=torch.float32)     # sigma | mu | weight logits, each dense [B][P][MK]
+        sig, mu, wl = smw[0:B], smw[B:2 * B], smw[2 * B:3 * B]
+        w2 = torch.cat([mat("gmm_sigma", 4), mat("gmm_means", 4)], dim=0).reshape(2 * MK, 4 * M, 1, 1).contiguous()
+        b2 = torch.cat([self._w(f"{net}.gmm_sigma.4.bias"), self._w(f"{net}.gmm_means.4.bias")])
+        p2 = PackedConv(ksize=1, c_in=4 * M, c_out=2 * MK, n_tile=192, weight=w2, bias=b2)
+        tiles = list(range(0, MK, 192))
+        plan = ConvPlan(packed=p2, x=l1, out=smw, act=[ACT_RELU] * nt(MK) + [ACT_NONE] * nt(MK),
+                        nt_in_coff=[0] * nt(MK) + [4 * M] * nt(MK), nt_out_coff=tiles + tiles,
+                        nt_out_img=[0] * nt(MK) + [B] * nt(MK))
+        self.plans[f"{tag}.gmm.l2(sigma|means)"] = plan
+        self._add(f"{tag}.gmm.l2(sigma|means)", plan.launch)
+        self._conv(f"{tag}.gmm.weights.l2", self.packs[f"{tag}.gmm.weights.l2"], l1, wl, in_coff=8 * M)
         self.buf[f"{tag}.sigma"], self.buf[f"{tag}.mu"], self.buf[f"{tag}.wlogit"] = sig, mu, wl
         return sig, mu, wl
 

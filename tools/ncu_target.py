@@ -12,7 +12,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from masic_b200.hsic import HSIC  # noqa: E402
 
 DEFAULT = ["L.g_a.conv1+gdn", "L.g_a.conv2+gdn", "L.g_a.conv4", "L.g_s.deconv3+igdn", "L.g_s.deconv4(subpix)",
-           "L.gmm.l0", "L.gmm.sigma.l2", "L.gmm_likelihood", "R.warp(x1)", "R.pre_conv+pre_gdn", "R.after_conv",
+           "L.gmm.l0", "L.gmm.l2(sigma|means)", "L.gmm_likelihood", "R.warp(x1)", "R.pre_conv+pre_gdn", "R.after_conv",
            "L.x1_hat(unshuffle)", "L.entropy_bottleneck", "x1.pack_nhwc", "L.latent_prep"]
 
 want = sys.argv[1:] or DEFAULT
