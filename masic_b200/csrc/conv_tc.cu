@@ -84,6 +84,7 @@ struct KParams {
   int n_tile;
   int pair;                        // accumulator slots per CTA and work item: 2 (n_tile <= 128) or 1
   int pdl;                         // 1: launched with programmatic stream serialization
+  int b_resident;                  // 1: every weight k-block of the (single) program stays in smem for the whole kernel
   int cg2;                         // 1: launched as CTA pairs (clusters of 2) issuing tcgen05.mma.cta_group::2
   int strip_bytes, b_stage_bytes, a_stages, b_stages;
   int smem_b_off, smem_g_off, smem_stage_off, smem_misc_off;
@@ -368,6 +369,22 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     __syncwarp();
     uint32_t st = 0, ph = 0;
     const uint32_t n_st = p.b_stages, st_bytes = p.b_stage_bytes;
+    if (p.b_resident) {
+      // small layers (sub-pixel deconv4, the CQE's 32/64-channel 3x3 convs): all k-blocks are loaded once, stage i
+      // holds tap i for the whole kernel, and the issuers skip the per-tap full/empty handshake (with N <= 64 a tap's
+      // MMAs take less time than one trip round the ring)
+      if (u_begin < u_end && elect_one()) {
+        const Variant& v0 = p.var[0];
+        if (p.debug & 2) {
+          mbar_arrive(sMisc + MISC_B_FULL);
+        } else {
+          mbar_expect_tx(sMisc + MISC_B_FULL, v0.n_bops * st_bytes);
+          for (int i = 0; i < v0.n_bops; ++i)
+            tma_load_2d(sB + i * st_bytes, &p.tmB, sMisc + MISC_B_FULL, 0, p.bops[v0.bop_off + i]);
+        }
+      }
+      __syncwarp();
+    } else
     for (Cursor cur = cursor_init(p, u_begin); cur.u < u_end;) {
       const Item it = next_item<CG2>(p, cur, u_end, rank);
       // a CTA of a pair stages its half of the n-tile's rows (st_bytes = that half)
@@ -402,6 +419,8 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     const uint64_t descA0 = umma_desc_sw128(sA) + slot * (p.strip_bytes >> 4), descB0 = umma_desc_sw128(sB);
     const uint32_t a_step = (p.pair * p.strip_bytes) >> 4, b_step = p.b_stage_bytes >> 4;
     const uint32_t idesc = p.idesc;
+    const bool b_res = p.b_resident != 0;
+    if (b_res && u_begin < u_end) mbar_wait(sMisc + MISC_B_FULL, 0);     // the whole weight set has landed
     int n_item = 0;
     for (Cursor cur = cursor_init(p, u_begin); cur.u < u_end; ++n_item) {
       const Item it = next_item<CG2>(p, cur, u_end, rank);
@@ -420,7 +439,7 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
         const int64_t a_inc = static_cast<int64_t>(sp.a_step) * 64;
         const int n_taps = sp.n_taps;
         for (int j = 0; j < n_taps; ++j) {
-          if (!free_run) mbar_wait(sMisc + MISC_B_FULL + 8 * sb, pb);
+          if (!free_run && !b_res) mbar_wait(sMisc + MISC_B_FULL + 8 * sb, pb);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t bdesc = descB0 + (sb * b_step + 2u * k0);
@@ -438,7 +457,7 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
                 for (uint32_t k = 0; k < nk; ++k) mma(d0, adesc + 2 * k, bdesc + 2 * k, k ? 1u : acc);
               }
             }
-            if (!free_run) commit(sMisc + MISC_B_EMPTY + 8 * sb);
+            if (!free_run && !b_res) commit(sMisc + MISC_B_EMPTY + 8 * sb);
             if (j + 1 == n_taps) {
               if (!free_run) commit(sMisc + MISC_A_EMPTY + 8 * sa);
               if (i + 1 == i1) commit(sMisc + MISC_ACC_FULL + 8 * buf);
@@ -1042,17 +1061,23 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   const int fixed = gamma_bytes + n_stage_blk * STAGE_BLK_BYTES + MISC_BYTES + 1024 /*align*/;
   const int budget = 227 * 1024 - fixed;                      // ring bytes
   int sa = 2, sb = 2;
+  // resident weights: single program, single n-tile, and the whole k-block list fits next to a double-buffered A ring
+  const int n_bops0 = kp.var[0].n_bops;
+  kp.b_resident = !kp.cg2 && kp.n_var == 1 && kp.n_ntiles == 1 && d.n_tile <= 64 &&
+                  2 * a_stage_bytes + n_bops0 * kp.b_stage_bytes <= budget;
+  { const char* e = getenv("MASIC_CONV_BRES"); if (e && atoi(e) == 0) kp.b_resident = 0; }
+  if (kp.b_resident) sb = n_bops0;
   if (sa * a_stage_bytes + sb * kp.b_stage_bytes > budget) { delete pl; return MASIC_EINVAL; }
   // deepen the rings with what is left (B first: a B stage is consumed by a single tap)
   for (bool grew = true; grew;) {
     grew = false;
-    if (sb < MAX_STAGES && sb < 6 && sa * a_stage_bytes + (sb + 1) * kp.b_stage_bytes <= budget) { ++sb; grew = true; }
+    if (!kp.b_resident && sb < MAX_STAGES && sb < 6 && sa * a_stage_bytes + (sb + 1) * kp.b_stage_bytes <= budget) { ++sb; grew = true; }
     if (sa < 4 && (sa + 1) * a_stage_bytes + sb * kp.b_stage_bytes <= budget) { ++sa; grew = true; }
   }
   {   // experiments: MASIC_CONV_STAGES="sa,sb" caps the ring depths
     const char* e = getenv("MASIC_CONV_STAGES");
     int ea = 0, eb = 0;
-    if (e && sscanf(e, "%d,%d", &ea, &eb) == 2 && ea >= 2 && eb >= 2 && ea <= MAX_STAGES && eb <= MAX_STAGES &&
+    if (!kp.b_resident && e && sscanf(e, "%d,%d", &ea, &eb) == 2 && ea >= 2 && eb >= 2 && ea <= MAX_STAGES && eb <= MAX_STAGES &&
         ea * a_stage_bytes + eb * kp.b_stage_bytes <= budget) { sa = ea; sb = eb; }
   }
   kp.a_stages = sa; kp.b_stages = sb;
