@@ -268,8 +268,13 @@ int masic_nhwc_to_nchw_f32(const float* in_nhwc, int n, int c, int hw, int in_pi
 /* Independent_EN (coremasic/mywork/MASIC.py:1436-1501).  Its 3x3 convs run as MASIC_CONV plans with LeakyReLU and
  * the ResidualBlock / Enhancement_Block adds fused (MasicConvDesc.residual0/1); these are the blends around them.
  * weights_nchw2 = softmax output of mask2weights_EN, (N,2,H,W) fp32: channel 0 weighs the OTHER view's warped map,
- * channel 1 this view's own map.
- * MASIC.py:1470-1471: out[p][0:3] = a[:,p]*w0[p], out[p][3:6] = b[:,p]*w1[p], out[p][6:16] = 0 (NHWC bf16, pitch 16);
+ * channel 1 this view's own map. */
+/* mask2weights_EN.forward (MASIC.py:1411-1434) fused: 4x conv3x3 stride 1 (1->kw->2kw->2kw->kw, ReLU between, each
+ * zero-padding its own input) + softmax over the kw channels; mask (N,1,H,W) fp32 -> weights (N,kw,H,W) fp32.
+ * weights4 / biases4: HOST arrays of 4 DEVICE pointers in torch Conv2d layout.  kw must be 2. */
+int masic_cqe_mask_weights(const float* mask_nchw1, int n, int h, int w, const float* const* weights4,
+                           const float* const* biases4, int kw, float* out_nchw2, void* stream);
+/* MASIC.py:1470-1471: out[p][0:3] = a[:,p]*w0[p], out[p][3:6] = b[:,p]*w1[p], out[p][6:16] = 0 (NHWC bf16, pitch 16);
  * a = the other view warped (NCHW fp32), b = this view's image. */
 int masic_cqe_blend_images(const float* a_nchw, const float* b_nchw, const float* weights_nchw2, int n, int h,
                            int w, void* out_nhwc16_bf16, void* stream);

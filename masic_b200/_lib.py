@@ -147,6 +147,7 @@ def _declare(lib: C.CDLL) -> None:
         "masic_gdn_small_bwd": (i, [vp, vp, i, i, i, vp, vp, f, i, vp, vp, vp, vp]),
         "masic_softmax_channels_bwd": (i, [vp, vp, i, i, i, vp, vp]),
         "masic_colsum_nchw": (i, [vp, i, i, i64, vp, vp]),
+        "masic_cqe_mask_weights": (i, [vp, i, i, i, C.POINTER(vp), C.POINTER(vp), i, vp, vp]),
         "masic_cqe_blend_images": (i, [vp, vp, vp, i, i, i, vp, vp]),
         "masic_cqe_feature_fuse": (i, [vp, i, vp, i, i, vp, vp, i, i, i, vp, i, vp]),
         "masic_cqe_residual_image": (i, [vp, i, vp, i, i, i, vp, vp]),

@@ -13,6 +13,7 @@ The whole sequence replays as one CUDA graph.  No CPU path.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Dict, Tuple
 
 import torch
@@ -182,18 +183,15 @@ class CQEEngine(HSICEngine):
         warp("mask_L=warp(mask_R,Hinv)", mask_r, Tinv, mask_l, 1)
         mk = "mask2weights_unit.maskconv"
         wts = {}
+        mws = [self._w(f"{mk}.{i}.weight") for i in (0, 2, 4, 6)]
+        mbs = [self._w(f"{mk}.{i}.bias") for i in (0, 2, 4, 6)]
+        self._keep += [mws, mbs]
+        pw = (C.c_void_p * 4)(*[t.data_ptr() for t in mws])
+        pb = (C.c_void_p * 4)(*[t.data_ptr() for t in mbs])
         for side, m in (("R", mask_r), ("L", mask_l)):
-            k1 = self._buf(B, 2, H, W, dtype=f32)
-            k2 = self._buf(B, 4, H, W, dtype=f32)
-            k3 = self._buf(B, 4, H, W, dtype=f32)
-            k4 = self._buf(B, 2, H, W, dtype=f32)
-            self._conv_small(f"mask2weights_{side}.conv1", m, None, f"{mk}.0", ksize=3, stride=1, act=ACT_RELU, out=k1)
-            self._conv_small(f"mask2weights_{side}.conv2", k1, None, f"{mk}.2", ksize=3, stride=1, act=ACT_RELU, out=k2)
-            self._conv_small(f"mask2weights_{side}.conv3", k2, None, f"{mk}.4", ksize=3, stride=1, act=ACT_RELU, out=k3)
-            self._conv_small(f"mask2weights_{side}.conv4", k3, None, f"{mk}.6", ksize=3, stride=1, out=k4)
             wt = self._buf(B, 2, H, W, dtype=f32)
-            self._add(f"mask2weights_{side}.softmax", (lambda k4=k4, wt=wt: check(lib.masic_softmax_channels(
-                k4.data_ptr(), B, 2, hw, wt.data_ptr(), None, self._s()), "masic_softmax_channels")))
+            self._add(f"mask2weights_{side}(4 convs+softmax)", (lambda m=m, wt=wt: check(lib.masic_cqe_mask_weights(
+                m.data_ptr(), B, H, W, pw, pb, 2, wt.data_ptr(), self._s()), "masic_cqe_mask_weights")))
             wts[side] = wt
         self.buf["w_R"], self.buf["w_L"] = wts["R"], wts["L"]
 

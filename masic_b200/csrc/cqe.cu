@@ -71,15 +71,18 @@ __global__ void __launch_bounds__(256)
 feature_fuse_kernel(const __nv_bfloat16* __restrict__ self, int self_pitch, const __nv_bfloat16* __restrict__ other,
                     int other_pitch, int C, const float* __restrict__ wgt, const double* __restrict__ T, int n, int h,
                     int w, __nv_bfloat16* __restrict__ out, int out_pitch) {
+  // 2*groups threads per pixel (a power of two <= 32): shifts and 32-bit arithmetic only, batch index on blockIdx.y
   const int groups = C / 8;
-  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  const long total = (long)n * h * w * 2 * groups;
-  if (i >= total) return;
-  const int g = (int)(i % (2 * groups));
-  const long p = i / (2 * groups);
-  const long hw = (long)h * w;
-  const int bi = (int)(p / hw);
-  const long pl = p - bi * hw;
+  const int lg = 31 - __clz(2 * groups);
+  const unsigned li = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned hw32 = (unsigned)h * (unsigned)w;
+  const unsigned plu = li >> lg;
+  if (plu >= hw32) return;                      // whole pixels drop out together
+  const int g = (int)(li & (2 * groups - 1));
+  const int bi = blockIdx.y;
+  const long hw = hw32;
+  const long pl = plu;
+  const long p = (long)bi * hw + pl;
   auto unpack = [](uint4 u, float* f) {
     const uint32_t q[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -90,14 +93,32 @@ feature_fuse_kernel(const __nv_bfloat16* __restrict__ self, int self_pitch, cons
   };
   float acc[8];
   float scale;
+  // the fp64 coordinate chain runs once per pixel (first lane of the warped half) and is handed to the pixel's other
+  // channel groups by shuffles; 2*groups must divide 32 so that a pixel's threads share a warp
+  Bilin b;
+  {
+    const bool owner = (g == groups);
+    if (owner) {
+      const int y = (int)(plu / (unsigned)w), x = (int)(plu - (unsigned)y * (unsigned)w);
+      b = bilin_coords(T + bi * 9, x, y, h, w, h, w);
+    }
+    const int src_lane = (threadIdx.x & 31) - g + groups;      // lane of this pixel's owner
+    uint32_t flags = owner ? ((uint32_t)b.in_x0 | ((uint32_t)b.in_x1 << 1) | ((uint32_t)b.in_y0 << 2) | ((uint32_t)b.in_y1 << 3)) : 0u;
+    b.x0 = __shfl_sync(0xffffffffu, b.x0, src_lane);
+    b.y0 = __shfl_sync(0xffffffffu, b.y0, src_lane);
+    b.w00 = __shfl_sync(0xffffffffu, b.w00, src_lane);
+    b.w01 = __shfl_sync(0xffffffffu, b.w01, src_lane);
+    b.w10 = __shfl_sync(0xffffffffu, b.w10, src_lane);
+    b.w11 = __shfl_sync(0xffffffffu, b.w11, src_lane);
+    flags = __shfl_sync(0xffffffffu, flags, src_lane);
+    b.in_x0 = flags & 1u; b.in_x1 = flags & 2u; b.in_y0 = flags & 4u; b.in_y1 = flags & 8u;
+  }
   if (g < groups) {
     scale = wgt[((long)bi * 2 + 1) * hw + pl];
     unpack(__ldg(reinterpret_cast<const uint4*>(self + p * self_pitch + 8 * g)), acc);
   } else {
     const int gg = g - groups;
     scale = wgt[((long)bi * 2) * hw + pl];
-    const int y = (int)(pl / w), x = (int)(pl - (long)y * w);
-    const Bilin b = bilin_coords(T + bi * 9, x, y, h, w, h, w);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
     const __nv_bfloat16* base = other + (long)bi * hw * other_pitch + 8 * gg;
@@ -139,6 +160,98 @@ residual_image_kernel(const float* __restrict__ conv_out, int pitch, const float
   }
 }
 
+// ------------------------------------------------------------------ mask2weights_EN, fused (MASIC.py:1411-1434)
+// conv3x3(1->2)+ReLU, conv3x3(2->4)+ReLU, conv3x3(4->4)+ReLU, conv3x3(4->2), softmax over the 2 channels, all at full
+// resolution: one block walks a 32x16 output tile through shared memory (9x9 receptive field = halo 4), so the mask
+// is read once and only the two weights are written (12 B / pixel instead of ~100 B / pixel for four launches).
+// Every layer zero-pads ITS OWN input (padding=1), hence intermediate values outside the image are forced to zero.
+constexpr int MW_TW = 32, MW_TH = 16;
+
+template <int CIN, int COUT, bool RELU>
+__device__ __forceinline__ void mw_layer(const float* __restrict__ in, int in_w, int in_h, float* __restrict__ out,
+                                         const float* __restrict__ wt, const float* __restrict__ bias, int gy0, int gx0,
+                                         int H, int W) {
+  // in: [CIN][in_h][in_w] covering image rows gy0-1.. ; out: [COUT][in_h-2][in_w-2] covering rows gy0..
+  const int ow = in_w - 2, oh = in_h - 2;
+  for (int i = threadIdx.x; i < ow * oh; i += blockDim.x) {
+    const int oy = i / ow, ox = i - oy * ow;
+    const int gy = gy0 + oy, gx = gx0 + ox;
+    float acc[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = bias[co];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float v = in[(ci * in_h + oy + ky) * in_w + ox + kx];
+#pragma unroll
+          for (int co = 0; co < COUT; ++co) acc[co] = fmaf(v, wt[((co * CIN + ci) * 3 + ky) * 3 + kx], acc[co]);
+        }
+    const bool inside = gy >= 0 && gy < H && gx >= 0 && gx < W;
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+      float r = RELU ? fmaxf(acc[co], 0.0f) : acc[co];
+      out[(co * oh + oy) * ow + ox] = inside ? r : 0.0f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 2)
+mask_weights_en_kernel(const float* __restrict__ mask, int H, int W, const float* __restrict__ w1,
+                       const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                       const float* __restrict__ w3, const float* __restrict__ b3, const float* __restrict__ w4,
+                       const float* __restrict__ b4, float* __restrict__ out) {
+  constexpr int W0 = MW_TW + 8, H0 = MW_TH + 8, W1 = W0 - 2, H1 = H0 - 2, W2 = W1 - 2, H2 = H1 - 2, W3 = W2 - 2,
+                H3 = H2 - 2;
+  __shared__ float s0[H0 * W0];
+  __shared__ float s1[2 * H1 * W1];
+  __shared__ float s2[4 * H2 * W2];
+  __shared__ float s3[4 * H3 * W3];
+  __shared__ float sw[18 + 72 + 144 + 72], sb[2 + 4 + 4 + 2];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 306; i += 256) sw[i] = i < 18 ? w1[i] : (i < 90 ? w2[i - 18] : (i < 234 ? w3[i - 90] : w4[i - 234]));
+  if (tid < 12) sb[tid] = tid < 2 ? b1[tid] : (tid < 6 ? b2[tid - 2] : (tid < 10 ? b3[tid - 6] : b4[tid - 10]));
+  const int n = blockIdx.z, y0 = blockIdx.y * MW_TH, x0 = blockIdx.x * MW_TW;
+  const float* m = mask + (long)n * H * W;
+  for (int i = tid; i < H0 * W0; i += 256) {
+    const int py = i / W0, px = i - py * W0;
+    const int gy = y0 - 4 + py, gx = x0 - 4 + px;
+    s0[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(m + (long)gy * W + gx) : 0.0f;
+  }
+  __syncthreads();
+  mw_layer<1, 2, true>(s0, W0, H0, s1, sw, sb, y0 - 3, x0 - 3, H, W);
+  __syncthreads();
+  mw_layer<2, 4, true>(s1, W1, H1, s2, sw + 18, sb + 2, y0 - 2, x0 - 2, H, W);
+  __syncthreads();
+  mw_layer<4, 4, true>(s2, W2, H2, s3, sw + 90, sb + 6, y0 - 1, x0 - 1, H, W);
+  __syncthreads();
+  // last layer + softmax over the two channels (MASIC.py:1431), straight to global memory
+  for (int i = tid; i < MW_TW * MW_TH; i += 256) {
+    const int oy = i / MW_TW, ox = i - oy * MW_TW;
+    const int gy = y0 + oy, gx = x0 + ox;
+    if (gy >= H || gx >= W) continue;
+    float a0 = sb[10], a1 = sb[11];
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float v = s3[(ci * H3 + oy + ky) * W3 + ox + kx];
+          a0 = fmaf(v, sw[234 + ((0 * 4 + ci) * 3 + ky) * 3 + kx], a0);
+          a1 = fmaf(v, sw[234 + ((1 * 4 + ci) * 3 + ky) * 3 + kx], a1);
+        }
+    const float mx = fmaxf(a0, a1);
+    const float e0 = expf(a0 - mx), e1 = expf(a1 - mx);
+    const float inv = 1.0f / (e0 + e1);
+    const long o = ((long)n * 2) * H * W + (long)gy * W + gx;
+    out[o] = e0 * inv;
+    out[o + (long)H * W] = e1 * inv;
+  }
+}
+
 }  // namespace
 
 #define S(stream) static_cast<cudaStream_t>(stream)
@@ -155,11 +268,13 @@ extern "C" int masic_cqe_blend_images(const float* a_nchw, const float* b_nchw, 
 extern "C" int masic_cqe_feature_fuse(const void* self_bf16, int self_pitch, const void* other_bf16, int other_pitch,
                                       int c, const float* weights_nchw2, const double* t_prepared, int n, int h, int w,
                                       void* out_bf16, int out_pitch, void* stream) {
-  if (!self_bf16 || !other_bf16 || !weights_nchw2 || !t_prepared || !out_bf16 || c <= 0 || (c % 8) || (self_pitch % 8) ||
+  if (!self_bf16 || !other_bf16 || !weights_nchw2 || !t_prepared || !out_bf16 || c <= 0 || (c % 8) || (32 % (c / 4)) ||
+      (self_pitch % 8) ||
       (other_pitch % 8) || (out_pitch % 8) || out_pitch < 2 * c || h < 2 || w < 2)
     return MASIC_EINVAL;
-  const long total = (long)n * h * w * 2 * (c / 8);
-  feature_fuse_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(
+  if ((long)h * w * 2 * (c / 8) > 0x7fffffffL) return MASIC_EINVAL;
+  const unsigned per_img = (unsigned)h * (unsigned)w * 2u * (unsigned)(c / 8);
+  feature_fuse_kernel<<<dim3((per_img + 255) / 256, n), 256, 0, S(stream)>>>(
       static_cast<const __nv_bfloat16*>(self_bf16), self_pitch, static_cast<const __nv_bfloat16*>(other_bf16), other_pitch,
       c, weights_nchw2, t_prepared, n, h, w, static_cast<__nv_bfloat16*>(out_bf16), out_pitch);
   return (int)cudaGetLastError();
@@ -171,5 +286,17 @@ extern "C" int masic_cqe_residual_image(const float* conv_out_nhwc, int pitch, c
   const long total = (long)n * h * w;
   residual_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(conv_out_nhwc, pitch, identity_nchw, n,
                                                                                 (long)h * w, out_nchw);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int masic_cqe_mask_weights(const float* mask_nchw1, int n, int h, int w, const float* const* weights4,
+                                      const float* const* biases4, int kw, float* out_nchw2, void* stream) {
+  if (!mask_nchw1 || !weights4 || !biases4 || !out_nchw2 || n <= 0 || h <= 0 || w <= 0) return MASIC_EINVAL;
+  if (kw != 2) return MASIC_ENOSUP;           // mask2weights_EN is only instantiated with Kw = 2 (MASIC.py:1449)
+  for (int i = 0; i < 4; ++i)
+    if (!weights4[i] || !biases4[i]) return MASIC_EINVAL;
+  dim3 grid((w + MW_TW - 1) / MW_TW, (h + MW_TH - 1) / MW_TH, n);
+  mask_weights_en_kernel<<<grid, 256, 0, S(stream)>>>(mask_nchw1, h, w, weights4[0], biases4[0], weights4[1], biases4[1],
+                                                      weights4[2], biases4[2], weights4[3], biases4[3], out_nchw2);
   return (int)cudaGetLastError();
 }

@@ -47,6 +47,13 @@ MICRO = {
     "mb_n256": dict(k=1, h=304, w=272, c_in=512, c_out=512, n_tile=256),
     "mb_n16": dict(k=1, h=304, w=272, c_in=512, c_out=16, n_tile=16),
     "mb_n32": dict(k=1, h=304, w=272, c_in=512, c_out=32, n_tile=32),
+    "mb_gl0_n128": dict(k=1, h=H // 16, w=W // 16, c_in=768, c_out=3456, n_tile=128, act=ACT_RELU),
+    "mb_gl0_n192": dict(k=1, h=H // 16, w=W // 16, c_in=768, c_out=3456, n_tile=192, act=ACT_RELU),
+    "mb_ctx_n128": dict(k=5, stride=1, tap_mask=MASK_A_5x5, h=H // 16, w=W // 16, c_in=192, c_out=384, n_tile=128),
+    "mb_hs3_n128": dict(k=3, stride=1, h=H // 16, w=W // 16, c_in=288, in_cp=384, c_out=384, n_tile=128),
+    "mb_ha1_n64": dict(k=5, stride=1, h=H // 16, w=W // 16, c_in=192, c_out=128, n_tile=64, act=ACT_RELU),
+    "mb_ga4_n96": dict(k=5, stride=2, h=H // 8, w=W // 8, c_in=128, c_out=192, n_tile=96, out_fp32=True),
+    "mb_ga4_n64": dict(k=5, stride=2, h=H // 8, w=W // 8, c_in=128, c_out=192, n_tile=64, out_fp32=True),
 }
 
 
