@@ -32,7 +32,7 @@ for r in b["rows"]:
         s, n = int(r[iS] or 0), int(r[iI] or 0)
     except ValueError:
         continue
-    if r[2] == "":      # the cuda-line summary row itself (already the sum of its sass rows) — skip to avoid double count
+    if r[2] in ("", "-"):      # the cuda-line summary row itself (already the sum of its sass rows) — skip to avoid double count
         continue
     a = agg[line]
     a[0] += s; a[1] += n; a[2] = src
