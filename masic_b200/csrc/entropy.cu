@@ -23,11 +23,45 @@ namespace {
 constexpr float kLikBound = 1e-9f;
 constexpr float kInvSqrt2Neg = -0.70710678118654752440f;   // float(-(2**-0.5))
 
-__device__ __forceinline__ float phi(float x) { return 0.5f * erfcf(kInvSqrt2Neg * x); }
+// erfc with fractional error < 1.2e-7 (+ fp32 evaluation error) everywhere, branch-free: the Chebyshev fit of
+// Numerical Recipes' erfcc(), erfc(|x|) = t * exp(-x^2 + P(t)), t = 2 / (2 + |x|).  CUDA's erfcf() costs ~160 issued
+// instructions per call on this data (its argument regimes diverge inside every warp), which made the mixture
+// likelihood kernel ALU-bound at 28 % of HBM peak; this one is ~30.
+__device__ __forceinline__ float erfc_fit(float x) {
+  const float z = fabsf(x);
+  const float t = __fdividef(2.0f, 2.0f + z);      // MUFU.RCP + FMUL; an IEEE division is ~50 issued instructions
+  float p = 0.17087277f;
+  p = fmaf(p, t, -0.82215223f);
+  p = fmaf(p, t, 1.48851587f);
+  p = fmaf(p, t, -1.13520398f);
+  p = fmaf(p, t, 0.27886807f);
+  p = fmaf(p, t, -0.18628806f);
+  p = fmaf(p, t, 0.09678418f);
+  p = fmaf(p, t, 0.37409196f);
+  p = fmaf(p, t, 1.00002368f);
+  p = fmaf(p, t, -1.26551223f);
+  const float r = t * __expf(fmaf(-z, z, p));       // ex2.approx: 2 ulp + |arg| * 2^-23 relative, far inside the tolerance
+  return x >= 0.0f ? r : 2.0f - r;
+}
 
+__device__ __forceinline__ float phi_exact(float x) { return 0.5f * erfcf(kInvSqrt2Neg * x); }
+#ifdef MASIC_EXACT_ERFC
+__device__ __forceinline__ float phi(float x) { return phi_exact(x); }
+#else
+__device__ __forceinline__ float phi(float x) { return 0.5f * erfc_fit(kInvSqrt2Neg * x); }
+#endif
+
+#ifdef MASIC_EXACT_ERFC
 __device__ __forceinline__ float gauss_mass(float v_abs, float s) {
   return phi((0.5f - v_abs) / s) - phi((-0.5f - v_abs) / s);
 }
+#else
+// one approximate reciprocal (<= 1 ulp) instead of two IEEE divisions: the argument of erfc moves by <= 2 ulp
+__device__ __forceinline__ float gauss_mass(float v_abs, float s) {
+  const float inv_s = __fdividef(1.0f, s);
+  return phi((0.5f - v_abs) * inv_s) - phi((-0.5f - v_abs) * inv_s);
+}
+#endif
 
 struct View { long sn, sc, sp; };
 __device__ __forceinline__ long at(const View& v, int n, int c, int p) {
@@ -65,8 +99,9 @@ gmm_fwd_kernel(const float* __restrict__ y, View vy, const float* __restrict__ s
         float sum = 0.0f;
 #pragma unroll
         for (int k = 0; k < K; ++k) { wk[k] = expf(wk[k] - mx); sum += wk[k]; }
+        const float inv_sum = 1.0f / sum;                    // one IEEE division instead of K
 #pragma unroll
-        for (int k = 0; k < K; ++k) wk[k] = wk[k] / sum;
+        for (int k = 0; k < K; ++k) wk[k] *= inv_sum;
       } else {
 #pragma unroll
         for (int k = 0; k < K; ++k) wk[k] = wgt[at(vp, n, k * M + m, p)];
@@ -251,7 +286,30 @@ __global__ void __launch_bounds__(256)
 latent_prep_kernel(const float* __restrict__ y, long total, int C, __nv_bfloat16* __restrict__ y_abs,
                    int abs_pitch, __nv_bfloat16* __restrict__ y_round, int rnd_pitch, int rnd_coff,
                    const float* __restrict__ rowscale, int rs_stride, int rs_off) {
+  // four channels per thread when the layout allows (16-byte loads, 8-byte stores), else one
+  const bool v4 = (C & 3) == 0 && (abs_pitch & 3) == 0 && (rnd_pitch & 3) == 0 && (rnd_coff & 3) == 0;
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (v4) {
+    const unsigned c4 = (unsigned)C >> 2;
+    if (i >= (total >> 2)) return;
+    const unsigned pix = (unsigned)(i / c4);           // total / 4 < 2^32 for every tensor this runs on
+    const int c = (int)((unsigned)i - pix * c4) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(y) + i);
+    if (y_abs) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(fabsf(v.x), fabsf(v.y)), b = __floats2bfloat162_rn(fabsf(v.z), fabsf(v.w));
+      *reinterpret_cast<uint2*>(y_abs + (long)pix * abs_pitch + c) =
+          make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    }
+    if (y_round) {
+      const float s = rowscale ? rowscale[(long)pix * rs_stride + rs_off] : 1.0f;
+      float r0 = rintf(v.x), r1 = rintf(v.y), r2 = rintf(v.z), r3 = rintf(v.w);
+      if (rowscale) { r0 *= s; r1 *= s; r2 *= s; r3 *= s; }
+      __nv_bfloat162 a = __floats2bfloat162_rn(r0, r1), b = __floats2bfloat162_rn(r2, r3);
+      *reinterpret_cast<uint2*>(y_round + (long)pix * rnd_pitch + rnd_coff + c) =
+          make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    }
+    return;
+  }
   if (i >= total) return;
   const long pix = i / C;
   const int c = (int)(i - pix * C);
@@ -308,7 +366,9 @@ gmm_cdf_kernel(const float* __restrict__ sigma, const float* __restrict__ mu, co
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       const float v = fabsf((float)s - m_k[k]);
-      const float d = phi((0.5f - v) / s_k[k]) - phi((-0.5f - v) / s_k[k]);
+      // the coder model keeps erfcf() and IEEE division: the reference evaluates this rule with torch on the GPU
+      // (MASIC.py:738-742, :1013-1016), i.e. with the same CUDA erfcf
+      const float d = phi_exact((0.5f - v) / s_k[k]) - phi_exact((-0.5f - v) / s_k[k]);
       acc = (k == 0) ? d * w_k[0] : acc + d * w_k[k];
     }
     return fminf(fmaxf(acc, 1.0f / 65536.0f), 1.0f);
@@ -428,7 +488,9 @@ extern "C" int masic_latent_prep(const float* y_nhwc, int64_t n_pixels, int c, v
                                  const float* rowscale, int rs_stride, int rs_off, void* stream) {
   if (!y_nhwc || n_pixels <= 0 || c <= 0) return MASIC_EINVAL;
   const long total = n_pixels * c;
-  latent_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  const bool v4 = (c & 3) == 0 && (abs_pitch & 3) == 0 && (rnd_pitch & 3) == 0 && (rnd_coff & 3) == 0;   // as in the kernel
+  const long threads = v4 ? total / 4 : total;
+  latent_prep_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       y_nhwc, total, c, static_cast<__nv_bfloat16*>(y_abs_bf16), abs_pitch,
       static_cast<__nv_bfloat16*>(y_round_bf16), rnd_pitch, rnd_coff, rowscale, rs_stride, rs_off);
   return (int)cudaGetLastError();

@@ -33,6 +33,26 @@ __device__ __forceinline__ void store_pixel_bf16(__nv_bfloat16* o, const float* 
   }
 }
 
+// same for 8 values already zero beyond the real channels, all indices compile-time (the array stays in registers)
+__device__ __forceinline__ void store_pixel8_bf16(__nv_bfloat16* o, const float (&v)[8], int pitch) {
+  if ((pitch & 7) == 0) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 q = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&q);
+    }
+    uint4* o4 = reinterpret_cast<uint4*>(o);
+    o4[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    for (int j = 1; j < pitch / 8; ++j) o4[j] = make_uint4(0u, 0u, 0u, 0u);
+  } else {
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch)
+      if (ch < pitch) o[ch] = __float2bfloat16_rn(v[ch]);
+    for (int ch = 8; ch < pitch; ++ch) o[ch] = __float2bfloat16_rn(0.0f);
+  }
+}
+
 // ------------------------------------------------------------------ homography warp
 // T = inv(N_dst * M * inv(N_src)) with N(h,w) = [[2/(w-1),0,-1],[0,2/(h-1),-1],[0,0,1]]
 // (kornia 0.5.0 normalize_homography); evaluated and stored in fp64.  With invert_m != 0
@@ -109,20 +129,26 @@ warp_kernel(const float* __restrict__ src, int n, int c, int h, int w, int ho, i
   const int x0 = finite ? (int)fxd : -10, y0 = finite ? (int)fyd : -10;
   const bool in_x0 = x0 >= 0 && x0 < w, in_x1 = x0 + 1 >= 0 && x0 + 1 < w;
   const bool in_y0 = y0 >= 0 && y0 < h, in_y1 = y0 + 1 >= 0 && y0 + 1 < h;
+  // out-of-image taps read a clamped address with a zero weight, so the four loads of every channel are independent
+  // and all in flight at once (the kernel was bound by the latency of loads serialised behind their bounds branches)
+  const float k_nw = (in_y0 && in_x0) ? w_nw : 0.0f, k_ne = (in_y0 && in_x1) ? w_ne : 0.0f;
+  const float k_sw = (in_y1 && in_x0) ? w_sw : 0.0f, k_se = (in_y1 && in_x1) ? w_se : 0.0f;
+  const int xc0 = min(max(x0, 0), w - 1), xc1 = min(max(x0 + 1, 0), w - 1);
+  const int yc0 = min(max(y0, 0), h - 1), yc1 = min(max(y0 + 1, 0), h - 1);
+  const long o_nw = (long)yc0 * w + xc0, o_ne = (long)yc0 * w + xc1, o_sw = (long)yc1 * w + xc0, o_se = (long)yc1 * w + xc1;
   float vals[8];
   for (int ch = 0; ch < c && ch < 8; ++ch) {
     float v = 0.0f;
     if (src) {
       const float* s = src + ((long)(b * c + ch) * h) * w;
-      if (in_y0 && in_x0) v += s[(long)y0 * w + x0] * w_nw;
-      if (in_y0 && in_x1) v += s[(long)y0 * w + x0 + 1] * w_ne;
-      if (in_y1 && in_x0) v += s[(long)(y0 + 1) * w + x0] * w_sw;
-      if (in_y1 && in_x1) v += s[(long)(y0 + 1) * w + x0 + 1] * w_se;
+      const float a = __ldg(s + o_nw), bq = __ldg(s + o_ne), cq = __ldg(s + o_sw), d = __ldg(s + o_se);
+      // same accumulation order as before: nw, ne, sw, se (a zero-weight tap adds +0)
+      v = a * k_nw;
+      v += bq * k_ne;
+      v += cq * k_sw;
+      v += d * k_se;
     } else {
-      if (in_y0 && in_x0) v += w_nw;
-      if (in_y0 && in_x1) v += w_ne;
-      if (in_y1 && in_x0) v += w_sw;
-      if (in_y1 && in_x1) v += w_se;
+      v = ((k_nw + k_ne) + k_sw) + k_se;
     }
     vals[ch] = v;
     if (dst) dst[((long)(b * c + ch) * ho + y) * wo + x] = v;
@@ -431,13 +457,14 @@ softmax_channels_kernel(const float* __restrict__ in, int n, int c, int hw, floa
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, int n, int c, int hw, __nv_bfloat16* __restrict__ out,
                          int pitch, int w, int row, int xoff) {
-  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (i >= (long)n * hw) return;
-  const int b = (int)(i / hw), p = (int)(i % hw);
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;      // batch on blockIdx.y: 32-bit index arithmetic only
+  const int b = blockIdx.y;
+  if (p >= hw) return;
   float v[8];
+#pragma unroll
   for (int ch = 0; ch < 8; ++ch) v[ch] = ch < c ? __ldg(in + ((long)(b * c + ch)) * hw + p) : 0.0f;
   const int y = p / w, x = p - y * w;
-  store_pixel_bf16(out + (((long)b * (hw / w) + y) * row + x + xoff) * pitch, v, c, pitch);
+  store_pixel8_bf16(out + (((long)b * (hw / w) + y) * row + x + xoff) * pitch, v, pitch);
 }
 
 // generic tiled transpose between NHWC and NCHW fp32 (c arbitrary)
@@ -540,8 +567,7 @@ extern "C" int masic_nchw_to_nhwc_bf16(const float* in_nchw, int n, int c, int h
   if (row_pixels == 0) { row_pixels = w; xoff = 0; }
   if (row_pixels < w + xoff || xoff < 0) return MASIC_EINVAL;
   const int hw = h * w;
-  const long total = (long)n * hw;
-  nchw_to_nhwc_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  nchw_to_nhwc_bf16_kernel<<<dim3((hw + 255) / 256, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       in_nchw, n, c, hw, static_cast<__nv_bfloat16*>(out), pitch, w, row_pixels, xoff);
   return (int)cudaGetLastError();
 }
