@@ -11,6 +11,15 @@ What the reference does, and what is kept:
     pixel in Python.  The decoder is autoregressive (the mask-A context conv needs the already-decoded
     neighbourhood) and walks the pixels in order, evaluating the SAME conv kernels on a 5x5 crop / a single
     pixel so that it reproduces the encoder's parameters bit for bit.
+  * symbol ORDER inside `<name>.bin`: the reference codes raster order, which forces a decoder to finish row h-1
+    before it can start row h.  The mask-A 5x5 context of position (h, w) only reaches columns w-2..w+2 of the two
+    rows above and w-2, w-1 of its own row, so every position of the anti-diagonal wave t = w + 3h depends on
+    earlier waves only.  By default both sides therefore code the positions in WAVE order
+    (t ascending, h ascending inside a wave; first payload byte = 1): the decoder evaluates the context conv, the
+    parameter nets and the CDF rows of a whole wave (up to ceil(W/48)+1 positions) in one batch and range-decodes
+    their symbols in one host call - (W/16 + 3(H/16-1)) steps instead of H*W/256.  `y_order="raster"` (payload
+    byte 0) keeps the reference's order and the per-position decoder.  The CDFs, hence the code length, are the
+    same either way.
   * the range coder itself: the reference calls the PyPI package `range_coder`, which it neither vendors nor
     pins and which is not installable here; `masic_range_encode` / `masic_range_decode_rows` (csrc/cdf.cu) are a
     plain 32-bit range coder with the same interface.  `<name>.bin` therefore has this library's byte format.
@@ -96,6 +105,78 @@ class _PixelModel:
         return self.sig, self.mu, self.wl
 
 
+ORDER_RASTER, ORDER_WAVE = 0, 1
+
+
+def wave_schedule(h16: int, w16: int):
+    """Positions (raster index h*w16 + w) grouped by wave t = w + 3h, h ascending inside a wave."""
+    waves = []
+    for t in range(w16 + 3 * (h16 - 1)):
+        hs = np.arange(max(0, -(-(t - w16 + 1) // 3)), min(h16 - 1, t // 3) + 1, dtype=np.int64)
+        ws = t - 3 * hs
+        keep = (ws >= 0) & (ws < w16)
+        if keep.any():
+            waves.append((hs[keep], ws[keep]))
+    return waves
+
+
+def wave_permutation(h16: int, w16: int) -> np.ndarray:
+    return np.concatenate([hs * w16 + ws for hs, ws in wave_schedule(h16, w16)])
+
+
+class _WaveModel:
+    """GMM parameters of all positions of one wave through the engine's own conv kernels: the mask-A context conv on
+    a batch of 5x5 crops of the decoded latents, then the 1x1 parameter branches on a (1, 1, n, C) image.  Row results
+    of an MMA do not depend on the other rows, so every position gets bit for bit what the encoder's full-image
+    launches produced."""
+
+    def __init__(self, eng: HSICEngine, tag: str, n_max: int):
+        M, K, dev = eng.M, eng.K, eng.dev
+        self.eng, self.tag, self.M, self.K, self.n_max = eng, tag, M, K, n_max
+        self.right = tag == "R"
+        cin = 5 * M if self.right else 4 * M
+        self.cin = cin
+        MK = M * K
+        bf, f32 = torch.bfloat16, torch.float32
+        z = lambda *s, dtype=bf: torch.zeros(*s, dtype=dtype, device=dev)   # noqa: E731
+        self.crop = z(n_max, 5, 5, M)
+        self.ctx_out = z(n_max, 5, 5, cin)
+        self.rs = z(n_max, 5, 5, 3, dtype=f32) if self.right else None
+        self.px_in = z(1, 1, n_max, cin)
+        self.l0, self.l1, self.l1w = z(1, 1, n_max, 18 * M), z(1, 1, n_max, 8 * M), z(1, 1, n_max, MK)
+        self.sig, self.mu, self.wl = (z(1, 1, n_max, MK, dtype=f32) for _ in range(3))
+        pk = eng.packs
+        self.ctx_plan = ConvPlan(packed=pk[f"{tag}.context"], stride=1, tap_mask=MASK_A_5x5, x=self.crop,
+                                 out=self.ctx_out, out_coff=2 * M, rowscale=self.rs, rs_off=1)
+        self.tail = [
+            ConvPlan(packed=pk[f"{tag}.gmm.l0"], x=self.px_in, out=self.l0, act=[ACT_RELU] * 6 + [ACT_LEAKY] * 12),
+            ConvPlan(packed=pk[f"{tag}.gmm.sigma.l1"], x=self.l0, out=self.l1, in_coff=0, out_coff=0, act=ACT_RELU),
+            ConvPlan(packed=pk[f"{tag}.gmm.means.l1"], x=self.l0, out=self.l1, in_coff=6 * M, out_coff=4 * M, act=ACT_LEAKY),
+            ConvPlan(packed=pk[f"{tag}.gmm.weights.l1"], x=self.l0, out=self.l1w, in_coff=12 * M, act=ACT_LEAKY),
+            ConvPlan(packed=pk[f"{tag}.gmm.sigma.l2"], x=self.l1, out=self.sig, in_coff=0, act=ACT_RELU),
+            ConvPlan(packed=pk[f"{tag}.gmm.means.l2"], x=self.l1, out=self.mu, in_coff=4 * M),
+            ConvPlan(packed=pk[f"{tag}.gmm.weights.l2"], x=self.l1w, out=self.wl),
+        ]
+
+    def params_at(self, ypad_flat: torch.Tensor, gmm_flat: torch.Tensor, crop_idx: torch.Tensor, pos: torch.Tensor):
+        """ypad_flat ((h16+4)*(w16+4), M) bf16, gmm_flat (h16*w16, cin) bf16, crop_idx (n*25,) / pos (n,) int64."""
+        M, n = self.M, pos.numel()
+        self.crop.view(-1, M)[:n * 25].copy_(ypad_flat.index_select(0, crop_idx))
+        if self.right:
+            mw = self.eng.mask_weights.view(-1, 3).index_select(0, pos)
+            self.rs[:n].copy_(mw.view(n, 1, 1, 3).expand(n, 5, 5, 3))
+        self.ctx_plan.launch()
+        g = gmm_flat.index_select(0, pos)
+        px = self.px_in.view(self.n_max, self.cin)
+        px[:n, :2 * M].copy_(g[:, :2 * M])
+        px[:n, 2 * M:4 * M].copy_(self.ctx_out[:n, 2, 2, 2 * M:4 * M])
+        if self.right:
+            px[:n, 4 * M:].copy_(g[:, 4 * M:])
+        for p in self.tail:
+            p.launch()
+        return self.sig, self.mu, self.wl
+
+
 def _symbol_intervals(eng: HSICEngine, tag: str, y_hat_nchw: torch.Tensor, ch: torch.Tensor, minmax: int) -> np.ndarray:
     """(n_pos * n_ch, 3) int32 coding intervals of every listed latent element, raster order, channel-minor."""
     lib = eng.lib
@@ -111,7 +192,7 @@ def _symbol_intervals(eng: HSICEngine, tag: str, y_hat_nchw: torch.Tensor, ch: t
 
 
 def compress(model, x1: torch.Tensor, x2: torch.Tensor, h_matrix: torch.Tensor, output_name, output_path: str = "",
-             device=None) -> Dict:
+             device=None, y_order: str = "wavefront") -> Dict:
     """HSIC.compress (MASIC.py:855-1158).  Batch 1, like the reference's file format."""
     if model.training:
         raise MasicError("HSIC.compress: eval mode only")
@@ -142,11 +223,18 @@ def compress(model, x1: torch.Tensor, x2: torch.Tensor, h_matrix: torch.Tensor, 
             f.write(zs[0])
     # ---- y1, y2: all coding intervals in one kernel each, one range-coded stream
     start = time.time()
+    if y_order not in ("wavefront", "raster"):
+        raise ValueError(f'y_order must be "wavefront" or "raster", got {y_order!r}')
+    order = ORDER_WAVE if y_order == "wavefront" else ORDER_RASTER
+    perm = wave_permutation(H // 16, W // 16) if order == ORDER_WAVE else None
     ivs = []
     for tag in ("L", "R"):
         ch = torch.from_numpy(np.flatnonzero(flags[tag]).astype(np.int32)).to(eng.dev)
         if ch.numel():
-            ivs.append(_symbol_intervals(eng, tag, y_hats[tag], ch, minmaxs[tag]))
+            a = _symbol_intervals(eng, tag, y_hats[tag], ch, minmaxs[tag])
+            if perm is not None:          # positions in wave order, channels stay minor
+                a = a.reshape(perm.size, ch.numel(), 3)[perm].reshape(-1, 3)
+            ivs.append(a)
     iv = np.ascontiguousarray(np.concatenate(ivs, 0)) if ivs else np.zeros((0, 3), np.int32)
     buf = np.empty(iv.shape[0] * 3 + 64, dtype=np.uint8)
     n_out = C.c_int64()
@@ -154,6 +242,7 @@ def compress(model, x1: torch.Tensor, x2: torch.Tensor, h_matrix: torch.Tensor, 
           "masic_range_encode")
     output2 = os.path.join(output_path, str(output_name) + ".bin")
     with open(output2, "wb") as f:
+        f.write(bytes([order]))
         f.write(buf[:n_out.value].tobytes())
     end = time.time()
     num_pixels = H * W * 2
@@ -163,7 +252,7 @@ def compress(model, x1: torch.Tensor, x2: torch.Tensor, h_matrix: torch.Tensor, 
         "bpp_real": (size1 + size2) * 8 / num_pixels, "bpp_side": size1 * 8 / num_pixels, "enctime": end - start,
         "y1_hat": out["y1_hat"].clone(), "y2_hat": out["y2_hat"].clone(),
         "z1_hat": out["z1_hat"].clone(), "z2_hat": out["z2_hat"].clone(),
-        "y_bits_ideal": ideal_bits, "y_bytes": size2, "n_symbols": int(iv.shape[0]),
+        "y_bits_ideal": ideal_bits, "y_bytes": size2 - 1, "n_symbols": int(iv.shape[0]), "y_order": y_order,
     }
 
 
@@ -197,6 +286,56 @@ def _decode_view(eng: HSICEngine, tag: str, dec, flag: np.ndarray, minmax: int) 
                 vals = torch.from_numpy(sym_h.astype(np.float32) - float(minmax)).to(eng.dev)
                 y_nhwc[0, h, w, ch_long] = vals
                 ypad[0, h + 2, w + 2, ch_long] = vals.to(torch.bfloat16)
+    eng.buf[f"{tag}.y_rnd"].copy_(ypad[:, 2:-2, 2:-2, :])
+    return y_nhwc.permute(0, 3, 1, 2).contiguous()
+
+
+def _decode_view_wave(eng: HSICEngine, tag: str, dec, flag: np.ndarray, minmax: int) -> torch.Tensor:
+    """Wavefront decode of one view's latents (positions of wave t = w + 3h in one batch); returns y_hat NCHW fp32 and
+    fills eng.buf[tag.y_rnd]."""
+    lib = eng.lib
+    M, K = eng.M, eng.K
+    h16, w16 = eng.H // 16, eng.W // 16
+    waves = wave_schedule(h16, w16)
+    n_max = max(hs.size for hs, _ in waves)
+    wm = _WaveModel(eng, tag, n_max)
+    gmm_flat = eng.buf[f"{tag}.gmm_in"].view(h16 * w16, -1)
+    ypad = torch.zeros(1, h16 + 4, w16 + 4, M, dtype=torch.bfloat16, device=eng.dev)
+    ypad_flat = ypad.view(-1, M)
+    y_nhwc = torch.zeros(1, h16, w16, M, dtype=torch.float32, device=eng.dev)
+    y_flat = y_nhwc.view(-1, M)
+    ch_np = np.flatnonzero(flag).astype(np.int32)
+    n_ch = int(ch_np.size)
+    if n_ch:
+        ch = torch.from_numpy(ch_np).to(eng.dev)
+        ch_long = ch.long()
+        L1 = 2 * minmax + 2
+        rows = torch.empty(n_max * n_ch, L1, dtype=torch.int32, device=eng.dev)
+        rows_h = torch.empty(n_max * n_ch, L1, dtype=torch.int32).pin_memory()
+        sym_h = torch.empty(n_max * n_ch, dtype=torch.int32).pin_memory()
+        # index tensors of every wave, built once on the host
+        dy, dx = np.meshgrid(np.arange(5), np.arange(5), indexing="ij")
+        sched = []
+        for hs, ws in waves:
+            crop = ((hs[:, None, None] + dy[None]) * (w16 + 4) + ws[:, None, None] + dx[None]).reshape(-1)
+            sched.append((hs.size, crop, hs * w16 + ws, (hs + 2) * (w16 + 4) + ws + 2))
+        cat = lambda i: torch.from_numpy(np.concatenate([s_[i] for s_ in sched])).to(eng.dev)   # noqa: E731
+        crop_all, pos_all, pad_all = cat(1), cat(2), cat(3)
+        c0 = p0 = 0
+        for n, crop_i, _, _ in sched:
+            crop_idx, pos, pad = crop_all[c0:c0 + crop_i.size], pos_all[p0:p0 + n], pad_all[p0:p0 + n]
+            c0 += crop_i.size
+            p0 += n
+            sig, mu, wl = wm.params_at(ypad_flat, gmm_flat, crop_idx, pos)
+            check(lib.masic_gmm_symbol_cdfs(sig.data_ptr(), mu.data_ptr(), wl.data_ptr(), 1, M, K, n, ch.data_ptr(),
+                                            n_ch, minmax, SCALE_BOUND, None, rows.data_ptr(), None, _stream()),
+                  "masic_gmm_symbol_cdfs")
+            rows_h[:n * n_ch].copy_(rows[:n * n_ch])            # synchronises the wave's kernels
+            check(lib.masic_range_decode_rows(dec, rows_h.data_ptr(), n * n_ch, L1, sym_h.data_ptr()),
+                  "masic_range_decode_rows")
+            vals = (sym_h[:n * n_ch].to(eng.dev, non_blocking=True).float() - float(minmax)).view(n, n_ch)
+            y_flat[pos[:, None], ch_long[None, :]] = vals
+            ypad_flat[pad[:, None], ch_long[None, :]] = vals.to(torch.bfloat16)
     eng.buf[f"{tag}.y_rnd"].copy_(ypad[:, 2:-2, 2:-2, :])
     return y_nhwc.permute(0, 3, 1, 2).contiguous()
 
@@ -235,16 +374,20 @@ def decompress(model, x1: Optional[torch.Tensor], x2: Optional[torch.Tensor], h_
             eng.buf[f"{tag}.zq"].copy_(z_hat.permute(0, 2, 3, 1))
             eng.run_steps(lambda n, t=tag: n.startswith(f"{t}.h_s."))
         with open(output2, "rb") as f:
-            data = np.frombuffer(f.read(), dtype=np.uint8).copy()
+            raw = f.read()
+        if not raw or raw[0] not in (ORDER_RASTER, ORDER_WAVE):
+            raise MasicError(f"{output2}: unknown symbol-order tag in the y payload")
+        decode_view = _decode_view_wave if raw[0] == ORDER_WAVE else _decode_view
+        data = np.frombuffer(raw, dtype=np.uint8)[1:].copy()
         dec = C.c_void_p()
         check(lib.masic_range_decoder_create(data.ctypes.data, data.size, C.byref(dec)), "masic_range_decoder_create")
         try:
             start = time.time()
-            o["y1_hat"].copy_(_decode_view(eng, "L", dec, hdr[0][2], hdr[0][1]))
+            o["y1_hat"].copy_(decode_view(eng, "L", dec, hdr[0][2], hdr[0][1]))
             # left reconstruction, its warp, encoder1 on it and the mask-weighted prior term (:1303-1318)
             eng.run_steps(lambda n: n.startswith("L.g_s.") or n.startswith("L.x1_hat") or n == "R.warp(x1_hat)"
                           or n.startswith("R.g_a(enc1 on warped x1_hat)") or n.startswith("R.y1warp"))
-            o["y2_hat"].copy_(_decode_view(eng, "R", dec, hdr[1][2], hdr[1][1]))
+            o["y2_hat"].copy_(decode_view(eng, "R", dec, hdr[1][2], hdr[1][1]))
             eng.run_steps(lambda n: n.startswith("R.g_s.") or n.startswith("R.after_"))
             torch.cuda.synchronize(eng.dev)
             end = time.time()

@@ -84,3 +84,26 @@ def test_reference_error_behaviour():
     assert g.scale_table.numel() == 0 and float(g.scale_bound) == pytest.approx(0.11)
     with pytest.raises(_lib.MasicError):                       # product path never computes on the CPU
         HSIC().eval()(torch.zeros(1, 3, 64, 64), torch.zeros(1, 3, 64, 64), torch.eye(3)[None])
+
+
+def test_wave_schedule_respects_the_mask_a_context():
+    """masic_b200/bitstream.py: every position of wave t = w + 3h only depends (5x5 mask 'A', layers.py:52-78) on
+    positions of earlier waves, and the schedule is a permutation of the raster order."""
+    from masic_b200.bitstream import wave_permutation, wave_schedule
+    for h16, w16 in ((1, 1), (3, 2), (8, 12), (19, 34)):
+        waves = wave_schedule(h16, w16)
+        perm = wave_permutation(h16, w16)
+        assert sorted(perm.tolist()) == list(range(h16 * w16))
+        tmap = np.empty((h16, w16), dtype=np.int64)
+        for t, (hs, ws) in enumerate(waves):
+            tmap[hs, ws] = t
+        for h in range(h16):
+            for w in range(w16):
+                for dh in (-2, -1, 0):
+                    for dw in (-2, -1, 0, 1, 2):
+                        if dh == 0 and dw >= 0:
+                            continue
+                        hh, ww = h + dh, w + dw
+                        if 0 <= hh < h16 and 0 <= ww < w16:
+                            assert tmap[hh, ww] < tmap[h, w]
+    assert len(wave_schedule(76, 136)) == 361 and max(a.size for a, _ in wave_schedule(76, 136)) == 46
