@@ -298,7 +298,10 @@ def _decode_view_wave(eng: HSICEngine, tag: str, dec, flag: np.ndarray, minmax: 
     h16, w16 = eng.H // 16, eng.W // 16
     waves = wave_schedule(h16, w16)
     n_max = max(hs.size for hs, _ in waves)
-    wm = _WaveModel(eng, tag, n_max)
+    cache = eng.__dict__.setdefault("_wave_models", {})          # plans and buffers survive across decompress() calls
+    wm = cache.get(tag)
+    if wm is None:
+        wm = cache[tag] = _WaveModel(eng, tag, n_max)
     gmm_flat = eng.buf[f"{tag}.gmm_in"].view(h16 * w16, -1)
     ypad = torch.zeros(1, h16 + 4, w16 + 4, M, dtype=torch.bfloat16, device=eng.dev)
     ypad_flat = ypad.view(-1, M)
