@@ -307,24 +307,41 @@ conv5x5_6to3_kernel(const float* __restrict__ in0, const float* __restrict__ in1
   const int b = blockIdx.z, y0 = blockIdx.y * F_TH, x0 = blockIdx.x * F_TW;
   // stage the patch with aligned float4 global loads; s_in column c holds image column x0 - 2 + c
   const bool vec_ok = (w & 3) == 0;
-  for (int i = tid; i < 6 * F_PH * (F_PW / 4); i += 128) {
-    const int q = i % (F_PW / 4), py = (i / (F_PW / 4)) % F_PH, ci = i / ((F_PW / 4) * F_PH);
-    const int gy = y0 + py - 2, gx = x0 + 4 * q - 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gy >= 0 && gy < h) {
-      const float* src = (ci < 3 ? in0 + ((long)(b * 3 + ci) * h) * w : in1 + ((long)(b * 3 + ci - 3) * h) * w) + (long)gy * w;
-      if (vec_ok && gx >= 0 && gx + 3 < w) {
-        v = __ldg(reinterpret_cast<const float4*>(src + gx));
-      } else {
-        if (gx >= 0 && gx < w) v.x = __ldg(src + gx);
-        if (gx + 1 >= 0 && gx + 1 < w) v.y = __ldg(src + gx + 1);
-        if (gx + 2 >= 0 && gx + 2 < w) v.z = __ldg(src + gx + 2);
-        if (gx + 3 >= 0 && gx + 3 < w) v.w = __ldg(src + gx + 3);
+  // loads are issued five at a time before any of them is stored: the staging phase used to expose one global-load
+  // latency per iteration (a quarter of the kernel's stall samples)
+  constexpr int N_STAGE = 6 * F_PH * (F_PW / 4), STAGE_BATCH = 5;
+  for (int i0 = tid; i0 < N_STAGE; i0 += 128 * STAGE_BATCH) {
+    float4 v[STAGE_BATCH];
+#pragma unroll
+    for (int u = 0; u < STAGE_BATCH; ++u) {
+      const int i = i0 + u * 128;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < N_STAGE) {
+        const int q = i % (F_PW / 4), py = (i / (F_PW / 4)) % F_PH, ci = i / ((F_PW / 4) * F_PH);
+        const int gy = y0 + py - 2, gx = x0 + 4 * q - 4;
+        if (gy >= 0 && gy < h) {
+          const float* src = (ci < 3 ? in0 + ((long)(b * 3 + ci) * h) * w : in1 + ((long)(b * 3 + ci - 3) * h) * w) + (long)gy * w;
+          if (vec_ok && gx >= 0 && gx + 3 < w) {
+            v[u] = __ldg(reinterpret_cast<const float4*>(src + gx));
+          } else {
+            if (gx >= 0 && gx < w) v[u].x = __ldg(src + gx);
+            if (gx + 1 >= 0 && gx + 1 < w) v[u].y = __ldg(src + gx + 1);
+            if (gx + 2 >= 0 && gx + 2 < w) v[u].z = __ldg(src + gx + 2);
+            if (gx + 3 >= 0 && gx + 3 < w) v[u].w = __ldg(src + gx + 3);
+          }
+        }
       }
     }
-    const int c = 4 * q - 2;
-    if (c >= 0) *reinterpret_cast<float2*>(&s_in[ci][py][c]) = make_float2(v.x, v.y);
-    if (c + 2 < F_PW) *reinterpret_cast<float2*>(&s_in[ci][py][c + 2]) = make_float2(v.z, v.w);
+#pragma unroll
+    for (int u = 0; u < STAGE_BATCH; ++u) {
+      const int i = i0 + u * 128;
+      if (i < N_STAGE) {
+        const int q = i % (F_PW / 4), py = (i / (F_PW / 4)) % F_PH, ci = i / ((F_PW / 4) * F_PH);
+        const int c = 4 * q - 2;
+        if (c >= 0) *reinterpret_cast<float2*>(&s_in[ci][py][c]) = make_float2(v[u].x, v[u].y);
+        if (c + 2 < F_PW) *reinterpret_cast<float2*>(&s_in[ci][py][c + 2]) = make_float2(v[u].z, v[u].w);
+      }
+    }
   }
   __syncthreads();
   // thread (tx, ty): pixels 4tx..4tx+3 (group 0) and 64+4tx..64+4tx+3 (group 1) of row ty: every LDS.128 of a
