@@ -356,6 +356,9 @@ class HSICTrainer:
         dplan4 = ConvPlan(packed=d4, stride=2, x=gimg_bf, out=gprev)
         e3 = prev
         lib = self.lib
+        gimg16 = self._z(B, H, W, 16)                     # dense 16-pitch copy of dL/d(image) for the weight gradient
+        dw16 = self._z(N, 16, 5, 5, dtype=F32)
+        wg4 = WgradPlan(ksize=5, stride=2, lo=e3, c_lo=N, hi=gimg16, c_hi=16, dw=dw16)
 
         def fwd():
             for i in range(3):
@@ -368,7 +371,10 @@ class HSICTrainer:
             check(lib.masic_nchw_to_nhwc_bf16(gimg.data_ptr(), B, 3, H, W, gimg_bf.data_ptr(), IMG_CP, W + XPAD, XOFF,
                                               T._s()), "masic_nchw_to_nhwc_bf16")
             T.colsum_nchw(gimg, db4)
-            T.wgrad_small(e3, N, gimg, dw4)
+            check(lib.masic_nchw_to_nhwc_bf16(gimg.data_ptr(), B, 3, H, W, gimg16.data_ptr(), 16, 0, 0, T._s()),
+                  "masic_nchw_to_nhwc_bf16")
+            wg4.launch()
+            dw4.add_(dw16[:, :3])
             dplan4.launch()
             for i in (2, 1, 0):
                 gdns[i].bwd(layers[i].db)
@@ -832,11 +838,22 @@ class _Conv1:
             B, h, w, _ = out.shape
             self.dimg = torch.zeros(B, h, w, 16, dtype=F32, device=out.device)
             self.dg_plan = ConvPlan(packed=self.dpack, x=gout, out=self.dimg)
+        # weight gradient on the tensor cores: the image as a dense 16-channel-pitch NHWC operand (3 real channels),
+        # dW lands in a (128, 16, 5, 5) scratch whose first 3 input channels are added to the parameter's gradient
+        # (the CUDA-core masic_wgrad_small took ~0.5 ms per launch at 512x896 b2: a fifth of the whole step)
+        Bn, _, Hh, Ww = img_nchw.shape
+        self.img16 = torch.zeros(Bn, Hh, Ww, 16, dtype=torch.bfloat16, device=out.device)
+        self.dw16 = torch.zeros(N, 16, 5, 5, dtype=F32, device=out.device)
+        self.wg_plan = WgradPlan(ksize=5, stride=2, lo=gout, c_lo=N, hi=self.img16, c_hi=16, dw=self.dw16)
 
     def fwd(self):
         self.fwd_plan.launch()
 
     def bwd(self, skip_act: bool = True):
-        T.wgrad_small(self.gout, self.gout.shape[-1], self.img_nchw, self.dw)
+        Bn, _, Hh, Ww = self.img_nchw.shape
+        check(self.tr.lib.masic_nchw_to_nhwc_bf16(self.img_nchw.data_ptr(), Bn, 3, Hh, Ww, self.img16.data_ptr(), 16, 0, 0,
+                                                  T._s()), "masic_nchw_to_nhwc_bf16")
+        self.wg_plan.launch()
+        self.dw.add_(self.dw16[:, :3])
         if self.dg_plan is not None:
             self.dg_plan.launch()

@@ -34,6 +34,9 @@ CASES = [
     ("masked5x5", False, 5, 1, 384, 192, 16, 24, 1, (768, 384), (192, 0), True),
     ("deconv5s2_128", True, 5, 2, 128, 128, 12, 20, 1, (128, 0), (128, 0), False),
     ("deconv5s2_192in", True, 5, 2, 192, 128, 8, 14, 2, (192, 0), (128, 0), False),
+    # the 3-channel side of g_a_conv1 / g_s_conv4: the image travels as a dense 16-channel-pitch NHWC buffer
+    ("conv5s2_img16", False, 5, 2, 128, 16, 24, 40, 2, (128, 0), (16, 0), False),
+    ("conv5s2_img16_big", False, 5, 2, 128, 16, 64, 112, 2, (128, 0), (16, 0), False),
 ]
 
 
