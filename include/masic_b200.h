@@ -38,7 +38,7 @@ extern "C" {
 #define MASIC_EDRIVER (-3)  /* cuTensorMapEncodeTiled unavailable / failed  */
 
 /* ---------------------------------------------------------------- version */
-int masic_abi_version(void);                 /* bumps on any signature change (2: residual inputs, 3: grouped launches of MasicConvDesc) */
+int masic_abi_version(void);                 /* bumps on any signature change (2: residual inputs, 3: grouped launches of MasicConvDesc, 4: pack batches) */
 const char* masic_build_info(void);          /* "sm_100a nvcc 12.9 ..." */
 
 /* ------------------------------------------------------------------ convs */
@@ -124,6 +124,19 @@ int masic_conv_plan_trace(const MasicConvPlan* plan, long long* out_host);
 int64_t masic_packed_weight_bytes(int kind, int ksize, int c_in, int c_out_pad);
 int masic_pack_conv_weights(const float* w, int kind, int transposed, int ksize,
                             int c_in, int c_out, int c_out_pad, void* dst, void* stream);
+/* All weight packs of a training step as ONE launch (after every optimizer.step() the kernels' bf16 copies of every
+ * conv()/deconv() weight and the padded fp32 biases are refreshed: ~110 packs + ~50 bias copies per step).  A job is
+ * one masic_pack_conv_weights() call plus, when bias_src != NULL, bias_dst[i] = bias_src[i % c_out] for
+ * i < c_out (4 * c_out for MASIC_DECONV_S2_SUBPIX).  All pointers are DEVICE pointers that stay valid for the life of
+ * the batch; the job table itself is host memory, copied at creation. */
+typedef struct MasicPackJob {
+  const float* w; void* dst; const float* bias_src; float* bias_dst;
+  int kind, transposed, ksize, c_in, c_out, c_out_pad;
+} MasicPackJob;
+typedef struct MasicPackBatch MasicPackBatch;
+int masic_pack_batch_create(const MasicPackJob* jobs, int n_jobs, MasicPackBatch** batch_out);
+int masic_pack_batch_launch(const MasicPackBatch* batch, void* stream);
+void masic_pack_batch_destroy(MasicPackBatch* batch);
 /* GDN re-parametrisation (parametrizers.py:61-64) + bf16 pack of gamma:
  *   beta'  = max(beta,  sqrt(beta_min + 2^-36))^2 - 2^-36
  *   gamma' = max(gamma, 2^-18)^2 - 2^-36                                        */

@@ -44,6 +44,14 @@ class ConvDesc(C.Structure):
     ]
 
 
+class PackJob(C.Structure):
+    _fields_ = [
+        ("w", C.c_void_p), ("dst", C.c_void_p), ("bias_src", C.c_void_p), ("bias_dst", C.c_void_p),
+        ("kind", C.c_int), ("transposed", C.c_int), ("ksize", C.c_int), ("c_in", C.c_int), ("c_out", C.c_int),
+        ("c_out_pad", C.c_int),
+    ]
+
+
 class WgradDesc(C.Structure):
     _fields_ = [
         ("ksize", C.c_int), ("stride", C.c_int), ("tap_mask", C.c_uint32),
@@ -95,6 +103,9 @@ def _declare(lib: C.CDLL) -> None:
         "masic_conv_plan_trace": (i, [vp, vp]),
         "masic_packed_weight_bytes": (i64, [i, i, i, i]),
         "masic_pack_conv_weights": (i, [vp, i, i, i, i, i, i, vp, vp]),
+        "masic_pack_batch_create": (i, [C.POINTER(PackJob), i, C.POINTER(vp)]),
+        "masic_pack_batch_launch": (i, [vp, vp]),
+        "masic_pack_batch_destroy": (None, [vp]),
         "masic_gdn_prepare": (i, [vp, vp, i, f, vp, vp, vp, vp]),
         "masic_conv_direct_nhwc": (i, [vp, i, i, i, i, i, i, vp, i, i, i, u32, vp, i, vp, i, i, i, vp]),
         "masic_gmm_likelihood_fwd": (i, [vp, vp, vp, vp, i, i, i, i, i, i, f, vp, vp, vp, i, vp, i, i,

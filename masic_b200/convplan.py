@@ -10,7 +10,7 @@ compressai/layers/gdn.py:77-92, compressai/layers/layers.py:75-78 (MaskedConv2d)
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Sequence
+from typing import Optional, Sequence, Tuple
 
 import torch
 
@@ -102,6 +102,39 @@ class PackedConv:
                 self.bias[:4 * self.c_out].copy_(bias.detach().float().repeat(4))
             else:
                 self.bias[:self.c_out].copy_(bias.detach().float())
+
+
+class PackBatch:
+    """Every (PackedConv, weight, bias) re-pack of a training step as one kernel launch (masic_pack_batch_*).  The
+    weights / biases must be fp32 contiguous tensors whose storage stays put (nn.Parameters updated in place)."""
+
+    def __init__(self, jobs: Sequence[Tuple["PackedConv", torch.Tensor, Optional[torch.Tensor]]]):
+        lib = _lib.load()
+        arr = (_lib.PackJob * len(jobs))()
+        self._keep = []
+        for a, (pk, w, b) in zip(arr, jobs):
+            assert w.dtype == torch.float32 and w.is_contiguous() and w.is_cuda, "PackBatch needs fp32 contiguous weights"
+            a.w, a.dst = w.data_ptr(), pk.w_packed.data_ptr()
+            if b is not None and pk.bias is not None:
+                assert b.dtype == torch.float32 and b.is_contiguous()
+                a.bias_src, a.bias_dst = b.data_ptr(), pk.bias.data_ptr()
+            a.kind, a.transposed, a.ksize = pk.kind, int(pk.transposed), pk.ksize
+            a.c_in = w.shape[1] if pk.kind == CONV_XFOLD4 else pk.c_in
+            a.c_out, a.c_out_pad = pk.c_out, pk.c_out_pad
+            self._keep.append((pk, w, b))
+        h = C.c_void_p()
+        check(lib.masic_pack_batch_create(arr, len(jobs), C.byref(h)), "masic_pack_batch_create")
+        self._h, self._lib, self.n_jobs = h, lib, len(jobs)
+
+    def launch(self, stream: Optional[int] = None) -> None:
+        check(self._lib.masic_pack_batch_launch(self._h, _stream() if stream is None else stream),
+              "masic_pack_batch_launch")
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.masic_pack_batch_destroy(h)
+            self._h = None
 
 
 class ConvPlan:

@@ -5,17 +5,16 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "../../include/masic_b200.h"
 
 namespace {
 
 constexpr int KBLK = 64;
 
-__global__ void pack_weights_kernel(const float* __restrict__ w, int kind, int transposed, int k,
-                                    int c_in, int c_out, int c_out_pad, int ncb, long total,
-                                    __nv_bfloat16* __restrict__ dst) {
-  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (i >= total) return;
+__device__ __forceinline__ float pack_weight_value(const float* __restrict__ w, int kind, int transposed, int k,
+                                                   int c_in, int c_out, int c_out_pad, int ncb, long i) {
   const int c = (int)(i % KBLK);
   long r = i / KBLK;
   const int co = (int)(r % c_out_pad);
@@ -53,7 +52,45 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int kind, int t
       }
     }
   }
-  dst[i] = __float2bfloat16_rn(v);
+  return v;
+}
+
+__global__ void pack_weights_kernel(const float* __restrict__ w, int kind, int transposed, int k,
+                                    int c_in, int c_out, int c_out_pad, int ncb, long total,
+                                    __nv_bfloat16* __restrict__ dst) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  dst[i] = __float2bfloat16_rn(pack_weight_value(w, kind, transposed, k, c_in, c_out, c_out_pad, ncb, i));
+}
+
+// Every weight pack (and padded bias copy) of a training step in ONE launch: block b belongs to the job j with
+// first_block[j] <= b < first_block[j+1] (binary search), the tail blocks of a job copy its bias.
+struct PackJobDev {
+  const float* w; __nv_bfloat16* dst; const float* bias_src; float* bias_dst;
+  int kind, transposed, k, c_in, c_out, c_out_pad, ncb, bias_n, bias_rep, pad;
+  long total;           // packed elements
+  int w_blocks;         // blocks of 256 covering `total`; the job's remaining blocks cover the bias
+  int pad2;
+};
+
+__global__ void __launch_bounds__(256)
+pack_batch_kernel(const PackJobDev* __restrict__ jobs, const int* __restrict__ first_block, int n_jobs) {
+  int lo = 0, hi = n_jobs - 1;
+  const int b = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (first_block[mid] <= b) lo = mid; else hi = mid - 1;
+  }
+  const PackJobDev j = jobs[lo];
+  const int lb = b - first_block[lo];
+  if (lb < j.w_blocks) {
+    const long i = (long)lb * 256 + threadIdx.x;
+    if (i < j.total)
+      j.dst[i] = __float2bfloat16_rn(pack_weight_value(j.w, j.kind, j.transposed, j.k, j.c_in, j.c_out, j.c_out_pad, j.ncb, i));
+  } else {
+    const int i = (lb - j.w_blocks) * 256 + threadIdx.x;      // bias_dst[i] = bias_src[i % bias_n], i < bias_n * bias_rep
+    if (i < j.bias_n * j.bias_rep) j.bias_dst[i] = j.bias_src[i % j.bias_n];
+  }
 }
 
 __global__ void gdn_prepare_kernel(const float* __restrict__ beta, const float* __restrict__ gamma,
@@ -169,4 +206,53 @@ extern "C" int masic_conv_direct_nhwc(const void* in, int n, int h_in, int w_in,
       static_cast<const __nv_bfloat16*>(in), n, h_in, w_in, in_cpitch, in_coff, c_in, w, transposed,
       ksize, stride, tap_mask, bias, c_out, h_out, w_out, out_f32, out_cpitch, out_coff, round_w_bf16);
   return (int)cudaGetLastError();
+}
+
+struct MasicPackBatch {
+  PackJobDev* d_jobs = nullptr;
+  int* d_first = nullptr;
+  int n_jobs = 0, n_blocks = 0;
+};
+
+extern "C" int masic_pack_batch_create(const MasicPackJob* jobs, int n_jobs, MasicPackBatch** out) {
+  if (!jobs || !out || n_jobs <= 0) return MASIC_EINVAL;
+  std::vector<PackJobDev> hj(n_jobs);
+  std::vector<int> first(n_jobs + 1, 0);
+  for (int i = 0; i < n_jobs; ++i) {
+    const MasicPackJob& s = jobs[i];
+    if (!s.w || !s.dst || s.c_in <= 0 || s.c_out <= 0) return MASIC_EINVAL;
+    if (s.kind == MASIC_DECONV_S2_SUBPIX ? (s.ksize != 5 || 4 * s.c_out > s.c_out_pad) : (s.c_out > s.c_out_pad)) return MASIC_EINVAL;
+    if (s.kind == MASIC_CONV_XFOLD4 && (s.ksize != 5 || s.c_in > 16 || s.transposed)) return MASIC_EINVAL;
+    if ((s.bias_src == nullptr) != (s.bias_dst == nullptr)) return MASIC_EINVAL;
+    PackJobDev& d = hj[i];
+    d.w = s.w; d.dst = static_cast<__nv_bfloat16*>(s.dst); d.bias_src = s.bias_src; d.bias_dst = s.bias_dst;
+    d.kind = s.kind; d.transposed = s.transposed; d.k = s.ksize; d.c_in = s.c_in; d.c_out = s.c_out; d.c_out_pad = s.c_out_pad;
+    d.ncb = (s.kind == MASIC_CONV_XFOLD4) ? 1 : (s.c_in + KBLK - 1) / KBLK;
+    d.bias_n = s.bias_src ? s.c_out : 0;
+    d.bias_rep = (s.kind == MASIC_DECONV_S2_SUBPIX) ? 4 : 1;
+    d.total = masic_packed_weight_bytes(s.kind, s.ksize, s.c_in, s.c_out_pad) / 2;
+    d.w_blocks = (int)((d.total + 255) / 256);
+    first[i + 1] = first[i] + d.w_blocks + (d.bias_n * d.bias_rep + 255) / 256;
+  }
+  MasicPackBatch* pb = new MasicPackBatch();
+  pb->n_jobs = n_jobs; pb->n_blocks = first[n_jobs];
+  cudaError_t e = cudaMalloc(&pb->d_jobs, sizeof(PackJobDev) * n_jobs);
+  if (e == cudaSuccess) e = cudaMalloc(&pb->d_first, sizeof(int) * (n_jobs + 1));
+  if (e == cudaSuccess) e = cudaMemcpy(pb->d_jobs, hj.data(), sizeof(PackJobDev) * n_jobs, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(pb->d_first, first.data(), sizeof(int) * (n_jobs + 1), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(pb->d_jobs); cudaFree(pb->d_first); delete pb; return (int)e; }
+  *out = pb;
+  return MASIC_OK;
+}
+
+extern "C" int masic_pack_batch_launch(const MasicPackBatch* pb, void* stream) {
+  if (!pb) return MASIC_EINVAL;
+  pack_batch_kernel<<<pb->n_blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(pb->d_jobs, pb->d_first, pb->n_jobs);
+  return (int)cudaGetLastError();
+}
+
+extern "C" void masic_pack_batch_destroy(MasicPackBatch* pb) {
+  if (!pb) return;
+  cudaFree(pb->d_jobs); cudaFree(pb->d_first);
+  delete pb;
 }

@@ -38,7 +38,7 @@ from . import _lib
 from . import train_ops as T
 from ._lib import MasicError, check
 from .convplan import (ACT_LEAKY, ACT_NONE, ACT_RELU, CONV, CONV_XFOLD4, DECONV_S2, DECONV_S2_SUBPIX, GDN_NONE,
-                       MASK_A_5x5, ConvPlan, PackedConv, WgradPlan, gdn_prepare)
+                       MASK_A_5x5, ConvPlan, PackBatch, PackedConv, WgradPlan, gdn_prepare)
 
 NOISE_KEYS = ("z1", "y1_ctx", "y1", "z2", "y2_ctx", "y1w", "y2")
 XOFF, XPAD = _lib.IMG_XOFF, _lib.IMG_XPAD
@@ -256,6 +256,7 @@ class HSICTrainer:
             self._grads[n] = self.flat_grad[off:off + p.numel()].view(p.shape)
             off += p.numel()
         self.repack: List[Tuple[PackedConv, torch.Tensor, Optional[torch.Tensor]]] = []
+        self._pack_batch = None
         self.gdn_prep: List[_GDN] = []
         self.gdn_finish: List[_GDN] = []
         self.zero_each_step: List[torch.Tensor] = []
@@ -727,8 +728,15 @@ class HSICTrainer:
         """Re-pack every weight the kernels read from the model's current fp32 parameters."""
         for f in self.pre_repack:
             f()
-        for pk, w, b in self.repack:
-            pk.repack(w, b)
+        if self._pack_batch is None:
+            ok = all(w.dtype == F32 and w.is_contiguous() and (b is None or (b.dtype == F32 and b.is_contiguous()))
+                     for _, w, b in self.repack)
+            self._pack_batch = PackBatch(self.repack) if ok else False
+        if self._pack_batch:
+            self._pack_batch.launch()                    # ~110 weight packs + ~50 bias copies in one launch
+        else:
+            for pk, w, b in self.repack:
+                pk.repack(w, b)
         for g in self.gdn_prep:
             g.prepare()
         # MaskedConv2d side effect (layers.py:77) is applied through tap_mask; keep the parameter masked too
