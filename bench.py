@@ -177,6 +177,9 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL writes its version banner to stdout at NCCL_DEBUG=VERSION; stdout carries the ONE JSON line only
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     peaks = _peaks()
 
