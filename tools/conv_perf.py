@@ -48,6 +48,7 @@ MICRO = {
     "mb_n16": dict(k=1, h=304, w=272, c_in=512, c_out=16, n_tile=16),
     "mb_n32": dict(k=1, h=304, w=272, c_in=512, c_out=32, n_tile=32),
     "mb_gl0_n128": dict(k=1, h=H // 16, w=W // 16, c_in=768, c_out=3456, n_tile=128, act=ACT_RELU),
+    "mb_gl0_n256": dict(k=1, h=H // 16, w=W // 16, c_in=768, c_out=3456, n_tile=256, act=ACT_RELU),
     "mb_gl0_n192": dict(k=1, h=H // 16, w=W // 16, c_in=768, c_out=3456, n_tile=192, act=ACT_RELU),
     "mb_ctx_n128": dict(k=5, stride=1, tap_mask=MASK_A_5x5, h=H // 16, w=W // 16, c_in=192, c_out=384, n_tile=128),
     "mb_hs3_n128": dict(k=3, stride=1, h=H // 16, w=W // 16, c_in=288, in_cp=384, c_out=384, n_tile=128),
