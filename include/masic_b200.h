@@ -276,6 +276,9 @@ int masic_nchw_to_nhwc_bf16(const float* in_nchw, int n, int c, int h, int w, vo
                             int row_pixels, int xoff, void* stream);
 int masic_nhwc_to_nchw_f32(const float* in_nhwc, int n, int c, int hw, int in_pitch, float* out_nchw,
                            void* stream);
+/* 8-bit image -> float32 in [0,1]: torchvision.transforms.ToTensor as the reference's datasets apply it
+ * (img.float().div(255), IEEE division); lets a caller ship 8-bit images over PCIe (PairStream.submit). */
+int masic_u8_to_unit_f32(const uint8_t* in_u8, int64_t numel, float* out_f32, void* stream);
 
 /* ------------------------------------------------- cross quality enhancement (CQE) glue */
 /* Independent_EN (coremasic/mywork/MASIC.py:1436-1501).  Its 3x3 convs run as MASIC_CONV plans with LeakyReLU and

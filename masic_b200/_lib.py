@@ -130,6 +130,7 @@ def _declare(lib: C.CDLL) -> None:
         "masic_gdn_nchw": (i, [vp, i, i, i, vp, vp, f, i, vp, vp]),
         "masic_softmax_channels": (i, [vp, i, i, i, vp, vp, vp]),
         "masic_nchw_to_nhwc_bf16": (i, [vp, i, i, i, i, vp, i, i, i, vp]),
+        "masic_u8_to_unit_f32": (i, [vp, i64, vp, vp]),
         "masic_nhwc_to_nchw_f32": (i, [vp, i, i, i, i, vp, vp]),
         "masic_wgrad_plan_create": (i, [C.POINTER(WgradDesc), C.POINTER(vp)]),
         "masic_wgrad_plan_workspace_bytes": (i64, [vp]),

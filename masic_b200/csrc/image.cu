@@ -494,6 +494,27 @@ nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, int n, int c, int hw, __n
   store_pixel8_bf16(out + (((long)b * (hw / w) + y) * row + x + xoff) * pitch, v, pitch);
 }
 
+// uint8 image -> float32 in [0, 1]: torchvision's ToTensor (img.float().div(255)), IEEE division, 16 values per thread
+__global__ void __launch_bounds__(256)
+u8_to_unit_f32_kernel(const uint8_t* __restrict__ in, long n, float* __restrict__ out) {
+  const long i = (blockIdx.x * (long)blockDim.x + threadIdx.x) * 16;
+  if (i + 16 <= n && ((reinterpret_cast<uintptr_t>(in + i) & 15) == 0)) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + i));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 o;
+      o.x = __fdiv_rn((float)(w[q] & 255u), 255.0f);
+      o.y = __fdiv_rn((float)((w[q] >> 8) & 255u), 255.0f);
+      o.z = __fdiv_rn((float)((w[q] >> 16) & 255u), 255.0f);
+      o.w = __fdiv_rn((float)(w[q] >> 24), 255.0f);
+      reinterpret_cast<float4*>(out + i)[q] = o;
+    }
+  } else {
+    for (long j = i; j < n && j < i + 16; ++j) out[j] = __fdiv_rn((float)in[j], 255.0f);
+  }
+}
+
 // generic tiled transpose between NHWC and NCHW fp32 (c arbitrary)
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_f32_kernel(const float* __restrict__ in, int c, int hw, int in_pitch, float* __restrict__ out) {
@@ -605,5 +626,14 @@ extern "C" int masic_nhwc_to_nchw_f32(const float* in_nhwc, int n, int c, int hw
   dim3 grid((hw + 31) / 32, (c + 31) / 32, n), block(32, 8);
   nhwc_to_nchw_f32_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(in_nhwc, c, hw, in_pitch,
                                                                                out_nchw);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int masic_u8_to_unit_f32(const uint8_t* in_u8, int64_t numel, float* out_f32, void* stream) {
+  if (!in_u8 || !out_f32 || numel < 0) return MASIC_EINVAL;
+  if (numel == 0) return MASIC_OK;
+  if (reinterpret_cast<uintptr_t>(out_f32) & 15) return MASIC_EINVAL;
+  const long threads = (numel + 15) / 16;
+  u8_to_unit_f32_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in_u8, numel, out_f32);
   return (int)cudaGetLastError();
 }

@@ -168,3 +168,30 @@ def test_pair_stream_matches_forward_and_criterion(dev):
         assert d["loss"] == pytest.approx(0.001 * 255 ** 2 * (d["mse1"] + d["mse2"]) + bpp, rel=1e-6)
     with pytest.raises(ValueError):
         ps.result(tickets[0])                                        # left the two-slot window
+
+
+def test_pair_stream_uint8_inputs_and_depth(dev):
+    """8-bit host images (a quarter of the PCIe bytes) are converted on the device exactly like torchvision's ToTensor
+    (img.float().div(255)): bit-identical reconstructions to forward() on the float32 images, for any pipeline depth,
+    with or without the criterion."""
+    from masic_b200.hsic import HSIC
+    torch.manual_seed(0)
+    net = HSIC().eval().to(dev)
+    h, w = 128, 192
+    g = torch.Generator().manual_seed(3)
+    u1 = torch.randint(0, 256, (4, 3, h, w), generator=g, dtype=torch.uint8)
+    u2 = torch.randint(0, 256, (4, 3, h, w), generator=g, dtype=torch.uint8)
+    _, _, Hm = _inputs(h, w, seed=11, batch=4)
+    f1, f2 = u1.float().div(255), u2.float().div(255)
+    with torch.no_grad():
+        want = [net(f1[i:i + 1].to(dev), f2[i:i + 1].to(dev), Hm[i:i + 1].to(dev)) for i in range(4)]
+    u1p, u2p, Hp = u1.pin_memory(), u2.pin_memory(), Hm.pin_memory()
+    for depth in (1, 3):
+        ps = net.pair_stream(h, w, dev, depth=depth)
+        for i in range(4):
+            t = ps.submit(u1p[i:i + 1], u2p[i:i + 1], Hp[i:i + 1], criterion=(i % 2 == 0))
+            r = ps.result(t)
+            assert (r is None) == (i % 2 == 1)
+            assert torch.equal(ps.outputs()["x1_hat"], want[i]["x1_hat"])
+            assert torch.equal(ps.outputs()["x2_hat"], want[i]["x2_hat"])
+            assert torch.equal(ps.outputs()["lik_y2"], want[i]["likelihoods"]["y2"])
