@@ -83,19 +83,40 @@ gmm_fwd_kernel(const float* __restrict__ y, View vy, const float* __restrict__ s
   __shared__ float s_yh[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
-  // ---- compute phase: pick the mapping that makes the 3K parameter loads coalesced
+  // ---- compute phase: pick the mapping that makes the 3K parameter loads coalesced.  Each thread walks four
+  // (position, channel) elements; the 16 loads of the NEXT element are issued before the current one is evaluated
+  // (the kernel was bound by the latency of loads consumed right where they were issued).
+  struct Elem { float y, s[K], m[K], w[K]; bool ok; int pl, ml; };
+  auto fetch = [&](int j) {
+    Elem e;
+    e.pl = fast_c ? j : threadIdx.x;
+    e.ml = fast_c ? threadIdx.x : j;
+    const int p = p0 + e.pl, m = m0 + e.ml;
+    e.ok = j < 32 && p < P && m < M;
+    e.y = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { e.s[k] = 1.0f; e.m[k] = 0.0f; e.w[k] = 0.0f; }
+    if (e.ok) {
+      e.y = __ldg(y + at(vy, n, m, p));
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const long o = at(vp, n, k * M + m, p);
+        e.s[k] = __ldg(sigma + o); e.m[k] = __ldg(mu + o); e.w[k] = __ldg(wgt + o);
+      }
+    }
+    return e;
+  };
+  Elem cur = fetch(threadIdx.y);
   for (int j = threadIdx.y; j < 32; j += 8) {
-    const int pl = fast_c ? j : threadIdx.x;
-    const int ml = fast_c ? threadIdx.x : j;
-    const int p = p0 + pl, m = m0 + ml;
+    const Elem nxt = fetch(j + 8);
     float l = 0.0f, yh = 0.0f;
-    if (p < P && m < M) {
-      yh = rintf(y[at(vy, n, m, p)]);
+    if (cur.ok) {
+      yh = rintf(cur.y);
       float wk[K];
       if (w_is_logits) {
         float mx = -INFINITY;
 #pragma unroll
-        for (int k = 0; k < K; ++k) { wk[k] = wgt[at(vp, n, k * M + m, p)]; mx = fmaxf(mx, wk[k]); }
+        for (int k = 0; k < K; ++k) { wk[k] = cur.w[k]; mx = fmaxf(mx, wk[k]); }
         float sum = 0.0f;
 #pragma unroll
         for (int k = 0; k < K; ++k) { wk[k] = expf(wk[k] - mx); sum += wk[k]; }
@@ -104,19 +125,19 @@ gmm_fwd_kernel(const float* __restrict__ y, View vy, const float* __restrict__ s
         for (int k = 0; k < K; ++k) wk[k] *= inv_sum;
       } else {
 #pragma unroll
-        for (int k = 0; k < K; ++k) wk[k] = wgt[at(vp, n, k * M + m, p)];
+        for (int k = 0; k < K; ++k) wk[k] = cur.w[k];
       }
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        const long o = at(vp, n, k * M + m, p);
-        const float s = fmaxf(sigma[o], scale_bound);
-        const float v = fabsf(yh - mu[o]);
+        const float s = fmaxf(cur.s[k], scale_bound);
+        const float v = fabsf(yh - cur.m[k]);
         l += gauss_mass(v, s) * wk[k];
       }
       l = fmaxf(l, kLikBound);
     }
-    s_lik[pl][ml] = l;
-    s_yh[pl][ml] = yh;
+    s_lik[cur.pl][cur.ml] = l;
+    s_yh[cur.pl][cur.ml] = yh;
+    cur = nxt;
   }
   __syncthreads();
   // ---- store phase: fastest output dimension on threadIdx.x
