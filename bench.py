@@ -252,14 +252,17 @@ def run_ours(args, rank, world, local_rank):
     # the host; the copy of pair i+1 overlaps the kernels of pairs i and i-1 (three slots = three engines).
 
     def e2e_run(n, a, b):
-        pend, out = None, None
+        # every step submits one pair and reads back the criterion of the pair submitted two steps earlier (three
+        # slots: two pairs stay in flight while the host waits); the last results are drained at the end
+        pend, out = [], None
         for i in range(n):
             j = i % n_rot
-            t = ps.submit(a[j:j + 1], b[j:j + 1], H_h[j:j + 1])
-            if pend is not None:
-                out = ps.result(pend)                      # D2H of the previous step's criterion
-            pend = t
-        return ps.result(pend)
+            pend.append(ps.submit(a[j:j + 1], b[j:j + 1], H_h[j:j + 1]))
+            if len(pend) > 2:
+                out = ps.result(pend.pop(0))               # D2H of an earlier step's criterion
+        for t in pend:
+            out = ps.result(t)
+        return out
 
     def e2e_measure(a, b):
         e2e_run(3, a, b)
@@ -272,11 +275,12 @@ def run_ours(args, rank, world, local_rank):
         ms = max_over_ranks(e0.elapsed_time(e1))
         return r, ms, world * args.steps / (ms / 1e3)
 
-    # the pairs travel as the 8-bit images they are (15.9 MB per pair; float32 conversion = ToTensor's /255, on the
-    # device); the same loop with float32 host tensors (63.5 MB per pair, PCIe-bound) is reported next to it
-    res, e2e_ms, e2e_value = e2e_measure(x1_u8, x2_u8)
-    _, e2e32_ms, e2e32_value = e2e_measure(x1_h, x2_h)
-    h2d = x1_u8[0:1].numel() * 2 + 36
+    # primary figure: float32 host tensors, exactly what the reference's scripts hand to the model (63.5 MB per pair);
+    # next to it the same loop with the 8-bit images the datasets consist of (15.9 MB per pair; ToTensor's /255 then
+    # runs on the device, bit-identical)
+    res, e2e_ms, e2e_value = e2e_measure(x1_h, x2_h)
+    _, e2e8_ms, e2e8_value = e2e_measure(x1_u8, x2_u8)
+    h2d = x1_h[0:1].numel() * 4 * 2 + 36
     d2h = 32
 
     # ---- per-kernel attribution with CUDA events (eager replay of the same step, same stream)
@@ -309,9 +313,9 @@ def run_ours(args, rank, world, local_rank):
                          "of activations",
                    "flop_per_pair": FLOP_PER_PAIR, "compute": "bf16 operands, fp32 accumulation (tcgen05)"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / args.steps, "inputs": "uint8 images (pinned host) + float32 homography",
-                "float32_inputs": {"value": e2e32_value, "ms_per_step": e2e32_ms / args.steps,
-                                   "h2d_bytes_per_step": x1_h[0:1].numel() * 4 * 2 + 36}},
+                "ms_per_step": e2e_ms / args.steps, "inputs": "float32 images + homography, pinned host memory",
+                "uint8_inputs": {"value": e2e8_value, "ms_per_step": e2e8_ms / args.steps,
+                                 "h2d_bytes_per_step": x1_u8[0:1].numel() * 2 + 36}},
         "gpu_launches": (len(eng.steps) + 3) * args.steps,   # engine kernels per step (+ the three input copies)
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops_sustained"],
@@ -328,7 +332,7 @@ def run_ours(args, rank, world, local_rank):
                          "frac": (gmm_bytes / (sum(gmm_ms) / len(gmm_ms) / 1e3) / 1e9 / peaks["hbm_gbs"]) if gmm_ms else None},
         "step_breakdown_ms": {"eager_sum": step_ms_eager, "top": [[n, round(ms, 4)] for n, ms in top]},
         "parity": {"bpp": float(res[0]), "psnr1_db": float(res[1]), "psnr2_db": float(res[2])},
-        "e2e_api": "HSIC.pair_stream(H, W, device, depth=3).submit(x1_host_u8, x2_host_u8, h_host) / .result(ticket)",
+        "e2e_api": "HSIC.pair_stream(H, W, device, depth=3).submit(x1_host, x2_host, h_host) / .result(ticket)",
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
