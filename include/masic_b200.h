@@ -38,7 +38,7 @@ extern "C" {
 #define MASIC_EDRIVER (-3)  /* cuTensorMapEncodeTiled unavailable / failed  */
 
 /* ---------------------------------------------------------------- version */
-int masic_abi_version(void);                 /* bumps on any signature change (2: residual inputs, 3: grouped launches of MasicConvDesc, 4: pack batches) */
+int masic_abi_version(void);                 /* bumps on any signature change (2: residual inputs, 3: grouped launches of MasicConvDesc, 4: pack batches, 5: cta_pairs) */
 const char* masic_build_info(void);          /* "sm_100a nvcc 12.9 ..." */
 
 /* ------------------------------------------------------------------ convs */
@@ -99,6 +99,10 @@ typedef struct MasicConvDesc {
    * holds out_images >= n images).  HOST arrays of c_out_pad / n_tile ints, copied at plan creation; all three NULL =
    * ordinary convolution.  Used for the three 1x1 entropy-parameter branches (MASIC.py:338-376, :410-444). */
   const int* nt_in_coff; const int* nt_out_coff; const int* nt_out_img; int out_images;
+  /* 1: run the plan on CTA PAIRS (clusters of 2, tcgen05.mma.cta_group::2): each CTA stages half of every weight
+   * k-block and the pair issues M = 256 MMAs, which cuts the weight traffic per SM.  Pays off on the 128 -> 128 5x5
+   * stride-2 layers and the wide 1x1 / 3x3 layers (-3..5 %), not on layers with few tiles or tiny K. */
+  int cta_pairs;
 } MasicConvDesc;
 
 typedef struct MasicConvPlan MasicConvPlan;   /* opaque: tensor maps + tile program */

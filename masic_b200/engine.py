@@ -89,9 +89,9 @@ class HSICEngine:
         return torch.cuda.current_stream().cuda_stream
 
     def _conv(self, name: str, packed: PackedConv, x, out, *, stride=1, tap_mask=0, in_coff=0, out_coff=0,
-              act=ACT_NONE, rowscale=None, rs_off=0):
+              act=ACT_NONE, rowscale=None, rs_off=0, cta_pairs=False):
         plan = ConvPlan(packed=packed, stride=stride, tap_mask=tap_mask, x=x, in_coff=in_coff, out=out,
-                        out_coff=out_coff, act=act, rowscale=rowscale, rs_off=rs_off)
+                        out_coff=out_coff, act=act, rowscale=rowscale, rs_off=rs_off, cta_pairs=cta_pairs)
         self.plans[name] = plan
         self._add(name, plan.launch)
         return plan
@@ -127,8 +127,9 @@ class HSICEngine:
         e3 = self._buf(B, H // 8, W // 8, N)
         y = self._buf(B, H // 16, W // 16, M, dtype=torch.float32)
         self._conv(f"{tag}.conv1+gdn", packs[0], img_bf16, e1, stride=2)
-        self._conv(f"{tag}.conv2+gdn", packs[1], e1, e2, stride=2)
-        self._conv(f"{tag}.conv3+gdn", packs[2], e2, e3, stride=2)
+        # CTA pairs (cta_group::2) measured faster on these two, the wide 1x1 / 3x3 layers and the context conv only
+        self._conv(f"{tag}.conv2+gdn", packs[1], e1, e2, stride=2, cta_pairs=True)
+        self._conv(f"{tag}.conv3+gdn", packs[2], e2, e3, stride=2, cta_pairs=True)
         self._conv(f"{tag}.conv4", packs[3], e3, y, stride=2)
         return y
 
@@ -195,7 +196,7 @@ class HSICEngine:
         self._conv(f"{tag}.h_s.deconv2", self._pack(f"{hs}.2", kind=DECONV_S2, c_in=M, c_out=M * 3 // 2, n_tile=192,
                                                       transposed=True), d1, d2, act=ACT_LEAKY)
         self._conv(f"{tag}.h_s.conv3x3", self._pack(f"{hs}.4", ksize=3, c_in=M * 3 // 2, c_out=2 * M, n_tile=192),
-                   d2, gmm_in, stride=1, out_coff=0, rowscale=rowscale, rs_off=0)
+                   d2, gmm_in, stride=1, out_coff=0, rowscale=rowscale, rs_off=0, cta_pairs=True)
         return z_hat, z_lik
 
     def _gmm_net(self, tag: str, net: str, cin: int, first_is_deconv: bool, gmm_in):
@@ -213,7 +214,7 @@ class HSICEngine:
         self.packs[f"{tag}.gmm.l0"] = p0
         l0 = self._buf(B, h16, w16, 18 * M)
         self._conv(f"{tag}.gmm.l0(3 branches)", p0, gmm_in, l0,
-                   act=[ACT_RELU] * 6 + [ACT_LEAKY] * 12)
+                   act=[ACT_RELU] * 6 + [ACT_LEAKY] * 12, cta_pairs=True)
         def pk(b, i, ci, co):
             pc = PackedConv(ksize=1, c_in=ci, c_out=co, n_tile=192, weight=self._w(f"{net}.{b}.{i}.weight"),
                             transposed=t if i == 2 else False, bias=self._w(f"{net}.{b}.{i}.bias"))
@@ -389,7 +390,7 @@ class HSICEngine:
         ctx2 = self._pack("context_prediction2", c_in=M, c_out=2 * M, n_tile=192)
         self.packs["R.context"] = ctx2
         self._conv("R.context(masked5x5)", ctx2, y2_rnd, gmm2_in, stride=1, tap_mask=MASK_A_5x5, out_coff=2 * M,
-                   rowscale=mw, rs_off=1)                                                          # ctx2 * w1
+                   rowscale=mw, rs_off=1, cta_pairs=True)                                                          # ctx2 * w1
         self._record("right")
 
         # ---------------- lane 1: left hyperprior, context, GMM parameters, likelihood (MASIC.py:747-767)
@@ -400,7 +401,8 @@ class HSICEngine:
         o["z1_hat"], o["lik_z1"] = self._hyper("L", 1, y1_abs, gmm1_in)
         ctx1 = self._pack("context_prediction1", c_in=M, c_out=2 * M, n_tile=192)
         self.packs["L.context"] = ctx1
-        self._conv("L.context(masked5x5)", ctx1, y1_rnd, gmm1_in, stride=1, tap_mask=MASK_A_5x5, out_coff=2 * M)
+        self._conv("L.context(masked5x5)", ctx1, y1_rnd, gmm1_in, stride=1, tap_mask=MASK_A_5x5, out_coff=2 * M,
+                   cta_pairs=True)
         s1, m1, w1 = self._gmm_net("L", "_h_s1_same_resolution", 4 * M, True, gmm1_in)
         self._gmm_likelihood("L", y1, s1, m1, w1, o["y1_hat"], o["lik_y1"])
         self._record("left_entropy")
