@@ -66,23 +66,34 @@ blend_images_kernel(const float* __restrict__ a, const float* __restrict__ b, co
 }
 
 // out[p][0:C] = self[p][0:C] * w[1][p];  out[p][C:2C] = bilinear(other, T)[p][0:C] * w[0][p]
-// one thread per (pixel, 8-channel group): 16-byte loads / stores; C multiple of 8
+// A warp owns 32 consecutive pixels.  Phase 1: lane i evaluates the fp64 coordinate chain of pixel i (all 32 lanes busy:
+// with one owner lane per pixel group the fp64 pipe ran at 1/8 utilisation and bounded the kernel).  Phase 2: the warp
+// walks the 32 x 2*groups (pixel, 8-channel group) items, 32 per step, with 16-byte loads / stores; a step's lanes
+// cover whole pixels, so every access is a run of contiguous 16-byte pieces.  C multiple of 8, 2*groups divides 32.
 __global__ void __launch_bounds__(256)
 feature_fuse_kernel(const __nv_bfloat16* __restrict__ self, int self_pitch, const __nv_bfloat16* __restrict__ other,
                     int other_pitch, int C, const float* __restrict__ wgt, const double* __restrict__ T, int n, int h,
                     int w, __nv_bfloat16* __restrict__ out, int out_pitch) {
-  // 2*groups threads per pixel (a power of two <= 32): shifts and 32-bit arithmetic only, batch index on blockIdx.y
-  const int groups = C / 8;
-  const int lg = 31 - __clz(2 * groups);
-  const unsigned li = blockIdx.x * blockDim.x + threadIdx.x;
+  const int groups = C / 8, per_px = 2 * groups;
+  const int lg = 31 - __clz(per_px);
+  const int lane = threadIdx.x & 31;
   const unsigned hw32 = (unsigned)h * (unsigned)w;
-  const unsigned plu = li >> lg;
-  if (plu >= hw32) return;                      // whole pixels drop out together
-  const int g = (int)(li & (2 * groups - 1));
+  const unsigned warp_px0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u;
+  if (warp_px0 >= hw32) return;
   const int bi = blockIdx.y;
   const long hw = hw32;
-  const long pl = plu;
-  const long p = (long)bi * hw + pl;
+  // ---- phase 1: coordinates and the two blend weights of pixel warp_px0 + lane
+  const unsigned my_px = warp_px0 + lane;
+  Bilin b;
+  b.x0 = b.y0 = -10; b.w00 = b.w01 = b.w10 = b.w11 = 0.0f; b.in_x0 = b.in_x1 = b.in_y0 = b.in_y1 = false;
+  float w_self = 0.0f, w_other = 0.0f;
+  if (my_px < hw32) {
+    const int y = (int)(my_px / (unsigned)w), x = (int)(my_px - (unsigned)y * (unsigned)w);
+    b = bilin_coords(T + bi * 9, x, y, h, w, h, w);
+    w_other = __ldg(wgt + ((long)bi * 2) * hw + my_px);
+    w_self = __ldg(wgt + ((long)bi * 2 + 1) * hw + my_px);
+  }
+  const uint32_t my_flags = (uint32_t)b.in_x0 | ((uint32_t)b.in_x1 << 1) | ((uint32_t)b.in_y0 << 2) | ((uint32_t)b.in_y1 << 3);
   auto unpack = [](uint4 u, float* f) {
     const uint32_t q[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -91,56 +102,48 @@ feature_fuse_kernel(const __nv_bfloat16* __restrict__ self, int self_pitch, cons
       f[2 * j] = t.x; f[2 * j + 1] = t.y;
     }
   };
-  float acc[8];
-  float scale;
-  // the fp64 coordinate chain runs once per pixel (first lane of the warped half) and is handed to the pixel's other
-  // channel groups by shuffles; 2*groups must divide 32 so that a pixel's threads share a warp
-  Bilin b;
-  {
-    const bool owner = (g == groups);
-    if (owner) {
-      const int y = (int)(plu / (unsigned)w), x = (int)(plu - (unsigned)y * (unsigned)w);
-      b = bilin_coords(T + bi * 9, x, y, h, w, h, w);
+  // ---- phase 2
+  for (int it = 0; it < per_px; ++it) {
+    const int item = it * 32 + lane;
+    const int src = item >> lg, g = item & (per_px - 1);      // pixel (lane that holds its coordinates), channel group
+    const int x0 = __shfl_sync(0xffffffffu, b.x0, src), y0 = __shfl_sync(0xffffffffu, b.y0, src);
+    const float w00 = __shfl_sync(0xffffffffu, b.w00, src), w01 = __shfl_sync(0xffffffffu, b.w01, src);
+    const float w10 = __shfl_sync(0xffffffffu, b.w10, src), w11 = __shfl_sync(0xffffffffu, b.w11, src);
+    const uint32_t fl = __shfl_sync(0xffffffffu, my_flags, src);
+    const float ws = __shfl_sync(0xffffffffu, w_self, src), wo = __shfl_sync(0xffffffffu, w_other, src);
+    const unsigned px = warp_px0 + src;
+    if (px >= hw32) continue;
+    const long p = (long)bi * hw + px;
+    float acc[8];
+    float scale;
+    if (g < groups) {
+      scale = ws;
+      unpack(__ldg(reinterpret_cast<const uint4*>(self + p * self_pitch + 8 * g)), acc);
+    } else {
+      scale = wo;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+      const __nv_bfloat16* base = other + (long)bi * hw * other_pitch + 8 * (g - groups);
+      auto tap = [&](bool ok, int yy, int xx, float wt) {
+        if (!ok) return;
+        float f[8];
+        unpack(__ldg(reinterpret_cast<const uint4*>(base + ((long)yy * w + xx) * other_pitch)), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j] * wt;
+      };
+      tap((fl & 4u) && (fl & 1u), y0, x0, w00);
+      tap((fl & 4u) && (fl & 2u), y0, x0 + 1, w01);
+      tap((fl & 8u) && (fl & 1u), y0 + 1, x0, w10);
+      tap((fl & 8u) && (fl & 2u), y0 + 1, x0 + 1, w11);
     }
-    const int src_lane = (threadIdx.x & 31) - g + groups;      // lane of this pixel's owner
-    uint32_t flags = owner ? ((uint32_t)b.in_x0 | ((uint32_t)b.in_x1 << 1) | ((uint32_t)b.in_y0 << 2) | ((uint32_t)b.in_y1 << 3)) : 0u;
-    b.x0 = __shfl_sync(0xffffffffu, b.x0, src_lane);
-    b.y0 = __shfl_sync(0xffffffffu, b.y0, src_lane);
-    b.w00 = __shfl_sync(0xffffffffu, b.w00, src_lane);
-    b.w01 = __shfl_sync(0xffffffffu, b.w01, src_lane);
-    b.w10 = __shfl_sync(0xffffffffu, b.w10, src_lane);
-    b.w11 = __shfl_sync(0xffffffffu, b.w11, src_lane);
-    flags = __shfl_sync(0xffffffffu, flags, src_lane);
-    b.in_x0 = flags & 1u; b.in_x1 = flags & 2u; b.in_y0 = flags & 4u; b.in_y1 = flags & 8u;
-  }
-  if (g < groups) {
-    scale = wgt[((long)bi * 2 + 1) * hw + pl];
-    unpack(__ldg(reinterpret_cast<const uint4*>(self + p * self_pitch + 8 * g)), acc);
-  } else {
-    const int gg = g - groups;
-    scale = wgt[((long)bi * 2) * hw + pl];
+    uint32_t q[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
-    const __nv_bfloat16* base = other + (long)bi * hw * other_pitch + 8 * gg;
-    auto tap = [&](bool ok, int yy, int xx, float wt) {
-      if (!ok) return;
-      float f[8];
-      unpack(__ldg(reinterpret_cast<const uint4*>(base + ((long)yy * w + xx) * other_pitch)), f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += f[j] * wt;
-    };
-    tap(b.in_y0 && b.in_x0, b.y0, b.x0, b.w00);
-    tap(b.in_y0 && b.in_x1, b.y0, b.x0 + 1, b.w01);
-    tap(b.in_y1 && b.in_x0, b.y0 + 1, b.x0, b.w10);
-    tap(b.in_y1 && b.in_x1, b.y0 + 1, b.x0 + 1, b.w11);
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[2 * j] * scale, acc[2 * j + 1] * scale);
+      q[j] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    *reinterpret_cast<uint4*>(out + p * out_pitch + 8 * g) = make_uint4(q[0], q[1], q[2], q[3]);
   }
-  uint32_t q[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[2 * j] * scale, acc[2 * j + 1] * scale);
-    q[j] = *reinterpret_cast<uint32_t*>(&h2);
-  }
-  *reinterpret_cast<uint4*>(out + p * out_pitch + 8 * g) = make_uint4(q[0], q[1], q[2], q[3]);
 }
 
 // out_nchw[b][c][p] = conv_out_nhwc[b][p][c] + identity_nchw[b][c][p],  c < 3
@@ -272,9 +275,8 @@ extern "C" int masic_cqe_feature_fuse(const void* self_bf16, int self_pitch, con
       (self_pitch % 8) ||
       (other_pitch % 8) || (out_pitch % 8) || out_pitch < 2 * c || h < 2 || w < 2)
     return MASIC_EINVAL;
-  if ((long)h * w * 2 * (c / 8) > 0x7fffffffL) return MASIC_EINVAL;
-  const unsigned per_img = (unsigned)h * (unsigned)w * 2u * (unsigned)(c / 8);
-  feature_fuse_kernel<<<dim3((per_img + 255) / 256, n), 256, 0, S(stream)>>>(
+  const unsigned px_per_block = 256;                         // 8 warps x 32 pixels
+  feature_fuse_kernel<<<dim3(((unsigned)h * (unsigned)w + px_per_block - 1) / px_per_block, n), 256, 0, S(stream)>>>(
       static_cast<const __nv_bfloat16*>(self_bf16), self_pitch, static_cast<const __nv_bfloat16*>(other_bf16), other_pitch,
       c, weights_nchw2, t_prepared, n, h, w, static_cast<__nv_bfloat16*>(out_bf16), out_pitch);
   return (int)cudaGetLastError();
