@@ -254,10 +254,11 @@ class PairStream:
         # directly in the engine's input buffers (no staging copy), and the kernels of consecutive pairs overlap —
         # the tail of a pair is a chain of launches that leave SMs idle (conv4: 85 tiles, hyper-prior layers: 10-40),
         # which the next pair's kernels fill (+3.6 % pairs/s on a B200 with two engines).
-        first = model.engine_for(1, height, width, self.dev)
-        self.engines = [first] + [HSICEngine(model.state_dict(), 1, height, width, self.dev, model.N, model.M, model.K,
-                                             use_graph=first.use_graph) for _ in range(depth - 1)]
-        self.eng = first
+        # (private engines: model.forward() keeps its own cached one, so the two can be used side by side)
+        first = model.engine_for(1, height, width, self.dev)          # also applies MaskedConv2d's weight masking
+        self.engines = [HSICEngine(model.state_dict(), 1, height, width, self.dev, model.N, model.M, model.K,
+                                   use_graph=first.use_graph) for _ in range(depth)]
+        self.eng = self.engines[0]
         with torch.cuda.device(self.dev):
             self.copy_stream = torch.cuda.Stream(device=self.dev)
             self.slots = []
