@@ -38,7 +38,7 @@ extern "C" {
 #define MASIC_EDRIVER (-3)  /* cuTensorMapEncodeTiled unavailable / failed  */
 
 /* ---------------------------------------------------------------- version */
-int masic_abi_version(void);                 /* bumps on any signature change (2: residual inputs, 3: grouped launches of MasicConvDesc, 4: pack batches, 5: cta_pairs) */
+int masic_abi_version(void);                 /* bumps on any signature change (2: residual inputs, 3: grouped launches of MasicConvDesc, 4: pack batches, 5: cta_pairs, 6: MASIC_CONV_XFOLD8) */
 const char* masic_build_info(void);          /* "sm_100a nvcc 12.9 ..." */
 
 /* ------------------------------------------------------------------ convs */
@@ -53,13 +53,18 @@ enum {
   MASIC_DECONV_S2 = 1,     /* nn.ConvTranspose2d(5, s=2, p=2, op=1) — models/utils.py:138-146 */
   MASIC_DECONV_S2_SUBPIX = 2,/* same op, all 4 output phases stacked on N (for tiny Cout):
                                 out buffer is [N][H][W][4*Cout padded], phase-major   */
-  MASIC_CONV_XFOLD4 = 3      /* nn.Conv2d(c<=16 -> Cout, k=5, s=2, p=2) with four horizontal taps folded into
+  MASIC_CONV_XFOLD4 = 3,     /* nn.Conv2d(c<=16 -> Cout, k=5, s=2, p=2) with four horizontal taps folded into
                                 one K=64 block (g_a_conv1, MASIC.py:513: 10 MMA groups per tile instead
                                 of 25).  The input is a plain 16-channel-pitch image stored with a padded
                                 row: [N][H][W+8][16] bf16, pixel x at column x+2, pad columns zero
                                 (MASIC_IMG_XOFF / MASIC_IMG_XPAD); the TMA tensor map reads OVERLAPPING
                                 4-pixel windows (stride 2 pixels) from it, so nothing is replicated in HBM.
                                 Pass in_cpitch = 16, c_in = 64, w_in = the real width W.               */
+  MASIC_CONV_XFOLD8 = 4      /* the same layer on an 8-channel-pitch image ([N][H][W+8][8] bf16, same padding): the
+                                tensor map reads overlapping 8-PIXEL windows (stride 2 pixels), so all five
+                                horizontal taps of a kernel row sit in one K=64 block (K index = pixel * 8 +
+                                channel, 48 of 64 used): 5 weight k-blocks and 15 K=16 MMAs per tile instead of 10
+                                and 25, half the image bytes.  c <= 8; pass in_cpitch = 8, c_in = 64.       */
 };
 
 typedef struct MasicConvDesc {

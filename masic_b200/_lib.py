@@ -15,7 +15,7 @@ LIB_PATH = _PKG / "libmasic_b200.so"
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 GDN_NONE, GDN_FWD, GDN_INV = 0, 1, 2
 IMG_XOFF, IMG_XPAD = 2, 8       # MASIC_IMG_XOFF / MASIC_IMG_XPAD
-CONV, DECONV_S2, DECONV_S2_SUBPIX, CONV_XFOLD4 = 0, 1, 2, 3
+CONV, DECONV_S2, DECONV_S2_SUBPIX, CONV_XFOLD4, CONV_XFOLD8 = 0, 1, 2, 3, 4
 
 _ERRORS = {-1: "MASIC_EINVAL (bad argument)", -2: "MASIC_ENOSUP (not implemented)",
            -3: "MASIC_EDRIVER (cuTensorMapEncodeTiled unavailable or failed)"}

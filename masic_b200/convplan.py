@@ -15,7 +15,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, CONV, CONV_XFOLD4, DECONV_S2, DECONV_S2_SUBPIX, GDN_FWD,
+from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, CONV, CONV_XFOLD4, CONV_XFOLD8, DECONV_S2, DECONV_S2_SUBPIX, GDN_FWD,
                    GDN_INV, GDN_NONE, ConvDesc, check)
 
 # MaskedConv2d mask 'A' for a 5x5 kernel (layers.py:68-73): rows 0-1 and (2,0),(2,1)
@@ -71,7 +71,7 @@ class PackedConv:
         self.eff_out = 4 * c_out if kind == DECONV_S2_SUBPIX else c_out
         self.c_out_pad = c_out_pad if c_out_pad is not None else -(-self.eff_out // n_tile) * n_tile
         dev = weight.device
-        pack_cin = weight.shape[1] if kind == CONV_XFOLD4 else c_in     # XFOLD4: real channels of w (<= 16)
+        pack_cin = weight.shape[1] if kind in (CONV_XFOLD4, CONV_XFOLD8) else c_in     # XFOLD: real channels of w
         self.w_packed = pack_weights(weight, kind, transposed, ksize, pack_cin, c_out, self.c_out_pad)
         self.bias = None
         if bias is not None:
@@ -92,7 +92,7 @@ class PackedConv:
         w = weight.detach()
         if w.dtype != torch.float32 or not w.is_contiguous():
             w = w.float().contiguous()
-        pack_cin = w.shape[1] if self.kind == CONV_XFOLD4 else self.c_in
+        pack_cin = w.shape[1] if self.kind in (CONV_XFOLD4, CONV_XFOLD8) else self.c_in
         check(lib.masic_pack_conv_weights(w.data_ptr(), self.kind, int(self.transposed), self.ksize, pack_cin,
                                           self.c_out, self.c_out_pad, self.w_packed.data_ptr(), _stream()),
               "masic_pack_conv_weights")
@@ -119,7 +119,7 @@ class PackBatch:
                 assert b.dtype == torch.float32 and b.is_contiguous()
                 a.bias_src, a.bias_dst = b.data_ptr(), pk.bias.data_ptr()
             a.kind, a.transposed, a.ksize = pk.kind, int(pk.transposed), pk.ksize
-            a.c_in = w.shape[1] if pk.kind == CONV_XFOLD4 else pk.c_in
+            a.c_in = w.shape[1] if pk.kind in (CONV_XFOLD4, CONV_XFOLD8) else pk.c_in
             a.c_out, a.c_out_pad = pk.c_out, pk.c_out_pad
             self._keep.append((pk, w, b))
         h = C.c_void_p()
@@ -163,7 +163,7 @@ class ConvPlan:
                                 gdn_beta=gdn_beta, gdn_gamma=gdn_gamma)
         self.packed = packed
         n, h_in, w_in, in_cp = x.shape
-        if packed.kind == CONV_XFOLD4:          # padded image rows: [N][H][W + IMG_XPAD][16]
+        if packed.kind in (CONV_XFOLD4, CONV_XFOLD8):          # padded image rows: [N][H][W + IMG_XPAD][16 or 8]
             w_in -= _lib.IMG_XPAD
         self.rowscale = rowscale
         self.x, self.out = x, out       # keep the bound buffers alive

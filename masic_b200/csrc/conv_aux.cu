@@ -22,7 +22,7 @@ __device__ __forceinline__ float pack_weight_value(const float* __restrict__ w, 
   const int tap = kb / ncb, cb = kb % ncb;
   const int ci = cb * KBLK + c;
   float v = 0.0f;
-  if (ci < c_in || kind == MASIC_CONV_XFOLD4) {
+  if (ci < c_in || kind == MASIC_CONV_XFOLD4 || kind == MASIC_CONV_XFOLD8) {
     if (kind == MASIC_DECONV_S2_SUBPIX) {
       // 3x3 stride-1 taps over the INPUT grid, N = (py, px, co): ky = py + 2*(1 - dy)
       const int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -40,6 +40,12 @@ __device__ __forceinline__ float pack_weight_value(const float* __restrict__ w, 
       const int ky = kb >> 1, grp = kb & 1;
       const int j = c >> 4, ch = c & 15;
       const int kx = grp ? (j == 2 ? 4 : 99) : j;
+      if (co < c_out && ch < c_in && kx < 5)
+        v = w[((static_cast<long>(co) * c_in + ch) * 5 + ky) * 5 + kx];
+    } else if (kind == MASIC_CONV_XFOLD8) {
+      // k-block = ky; column = pixel * 8 + channel of the 8-pixel window that starts at input pixel 2*ox - 2, so
+      // pixel j is tap kx = j (j < 5); `c_in` is the REAL channel count of w (<= 8)
+      const int ky = kb, kx = c >> 3, ch = c & 7;
       if (co < c_out && ch < c_in && kx < 5)
         v = w[((static_cast<long>(co) * c_in + ch) * 5 + ky) * 5 + kx];
     } else if (co < c_out) {
@@ -154,6 +160,7 @@ __global__ void conv_direct_kernel(const __nv_bfloat16* __restrict__ in, int n, 
 
 extern "C" int64_t masic_packed_weight_bytes(int kind, int ksize, int c_in, int c_out_pad) {
   if (kind == MASIC_CONV_XFOLD4) return static_cast<int64_t>(10) * c_out_pad * KBLK * 2;   // (ky, group) blocks
+  if (kind == MASIC_CONV_XFOLD8) return static_cast<int64_t>(5) * c_out_pad * KBLK * 2;    // one block per ky
   const int taps = (kind == MASIC_DECONV_S2_SUBPIX) ? 9 : ksize * ksize;
   const int ncb = (c_in + KBLK - 1) / KBLK;
   return static_cast<int64_t>(taps) * ncb * c_out_pad * KBLK * 2;
@@ -168,7 +175,8 @@ extern "C" int masic_pack_conv_weights(const float* w, int kind, int transposed,
     return MASIC_EINVAL;
   }
   if (kind == MASIC_CONV_XFOLD4 && (ksize != 5 || c_in > 16 || transposed)) return MASIC_EINVAL;
-  const int ncb = (kind == MASIC_CONV_XFOLD4) ? 1 : (c_in + KBLK - 1) / KBLK;
+  if (kind == MASIC_CONV_XFOLD8 && (ksize != 5 || c_in > 8 || transposed)) return MASIC_EINVAL;
+  const int ncb = (kind == MASIC_CONV_XFOLD4 || kind == MASIC_CONV_XFOLD8) ? 1 : (c_in + KBLK - 1) / KBLK;
   const long total = masic_packed_weight_bytes(kind, ksize, c_in, c_out_pad) / 2;
   const int bs = 256;
   pack_weights_kernel<<<(unsigned)((total + bs - 1) / bs), bs, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -223,11 +231,12 @@ extern "C" int masic_pack_batch_create(const MasicPackJob* jobs, int n_jobs, Mas
     if (!s.w || !s.dst || s.c_in <= 0 || s.c_out <= 0) return MASIC_EINVAL;
     if (s.kind == MASIC_DECONV_S2_SUBPIX ? (s.ksize != 5 || 4 * s.c_out > s.c_out_pad) : (s.c_out > s.c_out_pad)) return MASIC_EINVAL;
     if (s.kind == MASIC_CONV_XFOLD4 && (s.ksize != 5 || s.c_in > 16 || s.transposed)) return MASIC_EINVAL;
+    if (s.kind == MASIC_CONV_XFOLD8 && (s.ksize != 5 || s.c_in > 8 || s.transposed)) return MASIC_EINVAL;
     if ((s.bias_src == nullptr) != (s.bias_dst == nullptr)) return MASIC_EINVAL;
     PackJobDev& d = hj[i];
     d.w = s.w; d.dst = static_cast<__nv_bfloat16*>(s.dst); d.bias_src = s.bias_src; d.bias_dst = s.bias_dst;
     d.kind = s.kind; d.transposed = s.transposed; d.k = s.ksize; d.c_in = s.c_in; d.c_out = s.c_out; d.c_out_pad = s.c_out_pad;
-    d.ncb = (s.kind == MASIC_CONV_XFOLD4) ? 1 : (s.c_in + KBLK - 1) / KBLK;
+    d.ncb = (s.kind == MASIC_CONV_XFOLD4 || s.kind == MASIC_CONV_XFOLD8) ? 1 : (s.c_in + KBLK - 1) / KBLK;
     d.bias_n = s.bias_src ? s.c_out : 0;
     d.bias_rep = (s.kind == MASIC_DECONV_S2_SUBPIX) ? 4 : 1;
     d.total = masic_packed_weight_bytes(s.kind, s.ksize, s.c_in, s.c_out_pad) / 2;

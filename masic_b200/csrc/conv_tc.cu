@@ -836,6 +836,23 @@ static int encode_xfold4_view(CUtensorMap* tm, const void* base, int n, int h, i
   return r == CUDA_SUCCESS ? MASIC_OK : MASIC_EDRIVER;
 }
 
+// MASIC_CONV_XFOLD8 input: a [N][H][W + MASIC_IMG_XPAD][8] bf16 image seen as OVERLAPPING 8-pixel windows: dims
+// (64 elements, (W+XPAD)/2 - 3 windows 32 B apart, 2 row phases, H/2, N).  Window hx starts at column 2*hx = pixel 2*hx - 2.
+static int encode_xfold8_view(CUtensorMap* tm, const void* base, int n, int h, int w, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return MASIC_EDRIVER;
+  const cuuint64_t row_bytes = (cuuint64_t)(w + MASIC_IMG_XPAD) * 16;
+  cuuint64_t dims[5] = {64, (cuuint64_t)(w + MASIC_IMG_XPAD) / 2 - 3, 2, (cuuint64_t)h / 2, (cuuint64_t)n};
+  cuuint64_t strides[4] = {32, row_bytes, 2 * row_bytes, (cuuint64_t)h * row_bytes};
+  cuuint32_t box[5] = {64, (cuuint32_t)TILE_W, 1, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (reinterpret_cast<uintptr_t>(base) % 16 || (w % 2) || (h % 2)) return MASIC_EINVAL;
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MASIC_OK : MASIC_EDRIVER;
+}
+
 // gamma [128][128] bf16 row-major, loaded as two (64 x 128-row) K-blocks
 static int encode_gamma(CUtensorMap* tm, const void* base, int box_rows) {
   EncodeTiledFn enc = get_encode_fn();
@@ -963,6 +980,19 @@ int build_programs(const MasicConvDesc& d, std::vector<Strip>& strips_out, std::
       }
     int rc = emit_variant(specs, 1, 0, 0);
     if (rc) return rc;
+  } else if (d.kind == MASIC_CONV_XFOLD8) {
+    // 8-pixel windows of an 8-channel-pitch image (encode_xfold8_view): window ox holds pixels 2*ox-2 .. 2*ox+5, i.e.
+    // taps kx = 0..4 of a kernel row are K columns 0..39 of ONE block: three K=16 MMAs per (ky) and nothing else.
+    if (k != 5 || d.c_in != 64 || d.in_cpitch != 8 || d.in_coff != 0 || d.stride != 2 || d.tap_mask) return MASIC_EINVAL;
+    rows = TILE_H + 2;
+    std::vector<StripSpec> specs;
+    for (int py = 0; py < 2; ++py) {
+      StripSpec s{0, 0, py, -1, {}, 3};
+      for (int ky = py; ky < 5; ky += 2) s.tl.taps.push_back({(ky >> 1), ky});
+      specs.push_back(s);
+    }
+    int rc = emit_variant(specs, 1, 0, 0);
+    if (rc) return rc;
   } else if (d.kind == MASIC_DECONV_S2) {
     if (k != 5) return MASIC_ENOSUP;
     // out[2q+py] gets taps ky = py, py+2, .. from input row q + dy, dy = 1 - (ky-py)/2
@@ -1000,11 +1030,12 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   if (d.c_out_pad % d.n_tile || d.c_out > d.c_out_pad) return MASIC_EINVAL;
   if (d.c_out_pad / d.n_tile > 32) return MASIC_EINVAL;
   if (d.in_cpitch % 8 || d.in_coff % 8 || d.out_coff % 8) return MASIC_EINVAL;
-  if (d.kind == MASIC_CONV_XFOLD4 && d.c_in != 64) return MASIC_EINVAL;
+  if ((d.kind == MASIC_CONV_XFOLD4 || d.kind == MASIC_CONV_XFOLD8) && d.c_in != 64) return MASIC_EINVAL;
   if (d.out_cpitch % (d.out_fp32 ? 4 : 8)) return MASIC_EINVAL;
   if (d.ksize != 1 && d.ksize != 3 && d.ksize != 5) return MASIC_EINVAL;
   if (d.gdn && (d.n_tile != 128 || d.c_out != 128 || !d.gamma_packed || !d.beta || !d.bias)) return MASIC_EINVAL;
-  if ((d.kind == MASIC_CONV || d.kind == MASIC_CONV_XFOLD4) && d.stride == 2 && (d.h_in % 2 || d.w_in % 2))
+  const bool xfold = d.kind == MASIC_CONV_XFOLD4 || d.kind == MASIC_CONV_XFOLD8;
+  if ((d.kind == MASIC_CONV || xfold) && d.stride == 2 && (d.h_in % 2 || d.w_in % 2))
     return MASIC_EINVAL;
 
   MasicConvPlan* pl = new MasicConvPlan();
@@ -1018,7 +1049,7 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
 
   // geometry of the tile grid (output positions for conv, input positions for deconv)
   int gh, gw, out_h, out_w, out_split = 0;
-  if (d.kind == MASIC_CONV || d.kind == MASIC_CONV_XFOLD4) {
+  if (d.kind == MASIC_CONV || xfold) {
     gh = d.stride == 2 ? d.h_in / 2 : d.h_in;
     gw = d.stride == 2 ? d.w_in / 2 : d.w_in;
     out_h = gh; out_w = gw;
@@ -1089,15 +1120,16 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   if (pl->smem_bytes < 120 * 1024) pl->smem_bytes = 120 * 1024;   // keep 1 CTA/SM: 512 TMEM cols each
 
   // tensor maps
-  const int split_in = ((d.kind == MASIC_CONV || d.kind == MASIC_CONV_XFOLD4) && d.stride == 2) ? 1 : 0;
+  const int split_in = ((d.kind == MASIC_CONV || xfold) && d.stride == 2) ? 1 : 0;
   if (d.kind == MASIC_CONV_XFOLD4) rc = encode_xfold4_view(&kp.tmA, d.in, d.n, d.h_in, d.w_in, rows);
+  else if (d.kind == MASIC_CONV_XFOLD8) rc = encode_xfold8_view(&kp.tmA, d.in, d.n, d.h_in, d.w_in, rows);
   else rc = encode_nhwc_view(&kp.tmA, d.in, 2, d.n, d.h_in, d.w_in, d.in_cpitch, split_in, KBLK, rows, true);
-  const int ktaps = (d.kind == MASIC_DECONV_S2_SUBPIX) ? 9 : (d.kind == MASIC_CONV_XFOLD4 ? 10 : d.ksize * d.ksize);
-  const int ncb = (d.kind == MASIC_CONV_XFOLD4) ? 1 : (d.c_in + KBLK - 1) / KBLK;
+  const int ktaps = (d.kind == MASIC_DECONV_S2_SUBPIX) ? 9 : (d.kind == MASIC_CONV_XFOLD4 ? 10 : (d.kind == MASIC_CONV_XFOLD8 ? 5 : d.ksize * d.ksize));
+  const int ncb = xfold ? 1 : (d.c_in + KBLK - 1) / KBLK;
   if (!rc) rc = encode_rows64(&kp.tmB, d.w_packed, (long)ktaps * ncb * d.c_out_pad, kp.cg2 ? d.n_tile / 2 : d.n_tile);
   const bool grouped = d.nt_in_coff || d.nt_out_coff || d.nt_out_img;
   if (grouped && (!d.nt_in_coff || !d.nt_out_coff || !d.nt_out_img || d.out_images < d.n || d.gdn || d.residual0 ||
-                  d.rowscale || d.kind == MASIC_CONV_XFOLD4)) { delete pl; return MASIC_EINVAL; }
+                  d.rowscale || xfold)) { delete pl; return MASIC_EINVAL; }
   for (int i = 0; i < kp.n_ntiles; ++i) {
     kp.nt_in_coff[i] = grouped ? d.nt_in_coff[i] : 0;
     kp.nt_out_c[i] = grouped ? d.nt_out_coff[i] : i * d.n_tile;
@@ -1150,12 +1182,12 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
     const double out_pos = (double)d.n * out_h * out_w;
     double macs;
     const double co_real = (d.kind == MASIC_DECONV_S2_SUBPIX) ? d.c_out / 4 : d.c_out;
-    if (d.kind == MASIC_CONV_XFOLD4) macs = out_pos * 25.0 * 3.0 * d.c_out;       // the real 3-channel 5x5
+    if (xfold) macs = out_pos * 25.0 * 3.0 * d.c_out;       // the real 3-channel 5x5
     else if (d.kind == MASIC_CONV) macs = out_pos * live * d.c_in * d.c_out;
     else macs = (double)d.n * d.h_in * d.w_in * 25.0 * d.c_in * co_real;   // each input feeds 25 taps
     pl->flops = 2.0 * macs + (d.gdn ? 2.0 * out_pos * 128.0 * 128.0 : 0.0);
     const double out_ch = (d.kind == MASIC_DECONV_S2_SUBPIX) ? d.c_out_pad : d.c_out;
-    pl->hbm_bytes = (double)d.n * d.h_in * d.w_in * (d.kind == MASIC_CONV_XFOLD4 ? 16 : d.c_in) * 2.0 + out_pos * out_ch * esz +
+    pl->hbm_bytes = (double)d.n * d.h_in * d.w_in * (d.kind == MASIC_CONV_XFOLD4 ? 16 : (d.kind == MASIC_CONV_XFOLD8 ? 8 : d.c_in)) * 2.0 + out_pos * out_ch * esz +
                     (double)ktaps * ncb * d.c_out_pad * 128.0;
   }
 

@@ -26,12 +26,12 @@ import torch
 
 from . import _lib
 from ._lib import MasicError, check
-from .convplan import (ACT_LEAKY, ACT_NONE, ACT_RELU, CONV, CONV_XFOLD4, DECONV_S2, DECONV_S2_SUBPIX, GDN_FWD, GDN_INV,
+from .convplan import (ACT_LEAKY, ACT_NONE, ACT_RELU, CONV, CONV_XFOLD8, DECONV_S2, DECONV_S2_SUBPIX, GDN_FWD, GDN_INV,
                        GDN_NONE, MASK_A_5x5, ConvPlan, PackedConv)
 
 SCALE_BOUND = 0.11
-IMG_CP = 16          # channel pitch of the bf16 images feeding g_a_conv1 (3 real channels); rows are padded:
-XOFF, XPAD = _lib.IMG_XOFF, _lib.IMG_XPAD   # [N][H][W+XPAD][16], pixel x at column x+XOFF (MASIC_CONV_XFOLD4 input)
+IMG_CP = 8           # channel pitch of the bf16 images feeding g_a_conv1 (3 real channels); rows are padded:
+XOFF, XPAD = _lib.IMG_XOFF, _lib.IMG_XPAD   # [N][H][W+XPAD][8], pixel x at column x+XOFF (MASIC_CONV_XFOLD8 input)
 
 
 class HSICEngine:
@@ -112,7 +112,7 @@ class HSICEngine:
     def _encoder_weights(self, enc: str):
         N, M = self.N, self.M
         return [
-            self._pack(f"{enc}.g_a_conv1", kind=CONV_XFOLD4, c_in=64, c_out=N, n_tile=128, gdn=GDN_FWD,
+            self._pack(f"{enc}.g_a_conv1", kind=CONV_XFOLD8, c_in=64, c_out=N, n_tile=128, gdn=GDN_FWD,
                        gdn_prefix=f"{enc}.g_a_gdn1"),
             self._pack(f"{enc}.g_a_conv2", c_in=N, c_out=N, n_tile=128, gdn=GDN_FWD, gdn_prefix=f"{enc}.g_a_gdn2"),
             self._pack(f"{enc}.g_a_conv3", c_in=N, c_out=N, n_tile=128, gdn=GDN_FWD, gdn_prefix=f"{enc}.g_a_gdn3"),

@@ -48,8 +48,8 @@ def run_case(name, *, kind=CONV, k, stride=1, tap_mask=0, n=1, h, w, c_in, c_out
              in_coff=0, out_cp=None, out_coff=0, out_fp32=False, act=ACT_NONE, gdn=GDN_NONE, bias=True,
              rowscale=False, transposed=None, seed=0):
     torch.manual_seed(seed)
-    if kind == 3:
-        return run_xfold4(name, n=n, h=h, w=w, c_out=c_out, n_tile=n_tile, gdn=gdn)
+    if kind in (3, 4):
+        return run_xfold4(name, n=n, h=h, w=w, c_out=c_out, n_tile=n_tile, gdn=gdn, kind=kind)
     transposed = (kind != CONV) if transposed is None else transposed
     in_cp = in_cp or max(c_in + in_coff, 8)
     x = (torch.randn(n, h, w, in_cp, device=dev) * 1.0).to(torch.bfloat16)
@@ -129,19 +129,21 @@ def run_case(name, *, kind=CONV, k, stride=1, tap_mask=0, n=1, h, w, c_in, c_out
     return ok
 
 
-def run_xfold4(name, *, n, h, w, c_out, n_tile, gdn):
-    """g_a_conv1 path: NCHW fp32 image -> window-4 pack kernel -> XFOLD4 plan (+GDN) vs torch conv2d."""
+def run_xfold4(name, *, n, h, w, c_out, n_tile, gdn, kind=3):
+    """g_a_conv1 path: NCHW fp32 image -> padded NHWC bf16 image (pitch 16 / 8) -> XFOLD4 / XFOLD8 plan (+GDN) vs
+    torch conv2d."""
+    cp = 16 if kind == 3 else 8
     from masic_b200 import _lib as L
     img = torch.rand(n, 3, h, w, device=dev)
     wt = torch.randn(c_out, 3, 5, 5, device=dev) / 75 ** 0.5
     b = torch.randn(c_out, device=dev) * 0.1
-    xw = torch.zeros(n, h, w + L.IMG_XPAD, 16, device=dev, dtype=torch.bfloat16)
-    L.check(L.load().masic_nchw_to_nhwc_bf16(img.data_ptr(), n, 3, h, w, xw.data_ptr(), 16, w + L.IMG_XPAD, L.IMG_XOFF,
+    xw = torch.zeros(n, h, w + L.IMG_XPAD, cp, device=dev, dtype=torch.bfloat16)
+    L.check(L.load().masic_nchw_to_nhwc_bf16(img.data_ptr(), n, 3, h, w, xw.data_ptr(), cp, w + L.IMG_XPAD, L.IMG_XOFF,
                                              torch.cuda.current_stream().cuda_stream), "pack")
     out = torch.zeros(n, h // 2, w // 2, c_out, device=dev, dtype=torch.bfloat16)
     gb = torch.sqrt(torch.rand(c_out, device=dev) * 0.5 + 0.75)
     gg = torch.sqrt(torch.rand(c_out, c_out, device=dev) * 0.02 + 0.1 * torch.eye(c_out, device=dev))
-    plan = ConvPlan(kind=3, ksize=5, stride=2, x=xw, c_in=64, weight=wt, bias=b, c_out=c_out, n_tile=n_tile, out=out,
+    plan = ConvPlan(kind=kind, ksize=5, stride=2, x=xw, c_in=64, weight=wt, bias=b, c_out=c_out, n_tile=n_tile, out=out,
                     gdn=gdn, gdn_beta=gb, gdn_gamma=gg)
     plan.launch()
     torch.cuda.synchronize()
@@ -184,6 +186,8 @@ CASES = {
     "1x1_deconvk1": dict(k=1, h=16, w=8, c_in=128, c_out=256, n_tile=128, transposed=True),
     "1x1_ntile240": dict(k=1, h=16, w=24, c_in=192, c_out=960, n_tile=192, out_fp32=True, in_coff=64, in_cp=320),
     "xfold4_conv1_gdn": dict(kind=3, k=5, stride=2, n=2, h=48, w=40, c_in=3, c_out=128, n_tile=128, gdn=GDN_FWD),
+    "xfold8_conv1_gdn": dict(kind=4, k=5, stride=2, n=2, h=48, w=40, c_in=3, c_out=128, n_tile=128, gdn=GDN_FWD),
+    "xfold8_conv1_odd": dict(kind=4, k=5, stride=2, n=1, h=66, w=150, c_in=3, c_out=128, n_tile=128, gdn=GDN_FWD),
     "batch2_s2": dict(k=5, stride=2, n=2, h=32, w=16, c_in=64, c_out=128, n_tile=128),
 }
 

@@ -26,6 +26,7 @@ LAYERS = {
     # name: kind, k, stride, h_in, w_in, c_in, c_out, n_tile, gdn, out_fp32, extra
     "g_a_conv1(cin16)": dict(k=5, stride=2, h=H, w=W, c_in=16, c_out=128, n_tile=128, gdn=GDN_FWD),
     "g_a_conv1(xfold4)": dict(kind=3, k=5, stride=2, h=H, w=W, c_in=64, c_out=128, n_tile=128, gdn=GDN_FWD),
+    "g_a_conv1(xfold8)": dict(kind=4, k=5, stride=2, h=H, w=W, c_in=64, c_out=128, n_tile=128, gdn=GDN_FWD),
     "g_a_conv2": dict(k=5, stride=2, h=H // 2, w=W // 2, c_in=128, c_out=128, n_tile=128, gdn=GDN_FWD),
     "g_a_conv3": dict(k=5, stride=2, h=H // 4, w=W // 4, c_in=128, c_out=128, n_tile=128, gdn=GDN_FWD),
     "g_a_conv4": dict(k=5, stride=2, h=H // 8, w=W // 8, c_in=128, c_out=192, n_tile=192, out_fp32=True),
@@ -62,13 +63,13 @@ def build(name, kind=CONV, k=1, stride=1, tap_mask=0, h=0, w=0, c_in=0, c_out=0,
           out_fp32=False, act=ACT_NONE, in_cp=None):
     torch.manual_seed(0)
     in_cp = in_cp or c_in
-    if kind == 3:
-        x = torch.randn(1, h, w + 8, 16, device=dev).to(torch.bfloat16)
+    if kind in (3, 4):
+        x = torch.randn(1, h, w + 8, 16 if kind == 3 else 8, device=dev).to(torch.bfloat16)
         wt = torch.randn(c_out, 3, 5, 5, device=dev) / 75 ** 0.5
     else:
         x = torch.randn(1, h, w, in_cp, device=dev).to(torch.bfloat16)
-    transposed = kind not in (CONV, 3)
-    if kind != 3:
+    transposed = kind not in (CONV, 3, 4)
+    if kind not in (3, 4):
         wt = torch.randn(*((c_in, c_out, k, k) if transposed else (c_out, c_in, k, k)), device=dev) / (c_in * k * k) ** 0.5
     b = torch.randn(c_out, device=dev) * 0.1
     ho, wo = (2 * h, 2 * w) if kind == DECONV_S2 else ((h // 2, w // 2) if stride == 2 else (h, w))
