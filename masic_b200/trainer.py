@@ -37,12 +37,12 @@ import torch
 from . import _lib
 from . import train_ops as T
 from ._lib import MasicError, check
-from .convplan import (ACT_LEAKY, ACT_NONE, ACT_RELU, CONV, CONV_XFOLD4, DECONV_S2, DECONV_S2_SUBPIX, GDN_NONE,
+from .convplan import (ACT_LEAKY, ACT_NONE, ACT_RELU, CONV, CONV_XFOLD8, DECONV_S2, DECONV_S2_SUBPIX, GDN_NONE,
                        MASK_A_5x5, ConvPlan, PackBatch, PackedConv, WgradPlan, gdn_prepare)
 
 NOISE_KEYS = ("z1", "y1_ctx", "y1", "z2", "y2_ctx", "y1w", "y2")
 XOFF, XPAD = _lib.IMG_XOFF, _lib.IMG_XPAD
-IMG_CP = 16
+IMG_CP = 8           # MASIC_CONV_XFOLD8 input pitch
 BF = torch.bfloat16
 F32 = torch.float32
 
@@ -357,7 +357,7 @@ class HSICTrainer:
         self.repack.append((p4, w4, b4))
         plan4 = ConvPlan(packed=p4, x=prev, out=sp)
         gimg_bf = self._z(B, H, W + XPAD, IMG_CP)
-        d4 = PackedConv(kind=CONV_XFOLD4, ksize=5, c_in=64, c_out=N, n_tile=128, weight=w4)
+        d4 = PackedConv(kind=CONV_XFOLD8, ksize=5, c_in=64, c_out=N, n_tile=128, weight=w4)
         self.repack.append((d4, w4, None))
         dplan4 = ConvPlan(packed=d4, stride=2, x=gimg_bf, out=gprev)
         e3 = prev
@@ -838,7 +838,7 @@ class _Conv1:
         self.img_nchw, self.gout = img_nchw, gout
         N = out.shape[-1]
         if share is None:
-            self.pack = PackedConv(kind=CONV_XFOLD4, ksize=5, c_in=64, c_out=N, n_tile=128, weight=self.w, bias=self.b)
+            self.pack = PackedConv(kind=CONV_XFOLD8, ksize=5, c_in=64, c_out=N, n_tile=128, weight=self.w, bias=self.b)
             tr.repack.append((self.pack, self.w, self.b))
             self.dpack = PackedConv(kind=DECONV_S2_SUBPIX, ksize=5, c_in=N, c_out=3, n_tile=16, weight=self.w, transposed=True)
             tr.repack.append((self.dpack, self.w, None))
