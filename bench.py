@@ -199,7 +199,20 @@ def run_ours(args, rank, world, local_rank):
         # NCCL writes its version banner to stdout at NCCL_DEBUG=VERSION; stdout carries the ONE JSON line only
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        # ... and the communicator's first use prints it whatever NCCL_DEBUG says: create the communicator now, with
+        # fd 1 pointing at stderr, so that stdout carries the ONE JSON line only
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+            t = torch.zeros(1, device=dev)
+            dist.all_reduce(t)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     peaks = _peaks()
 
     # same seeded random-init weights as the reference/oracle (bit-identical init, tests/test_model_cpu.py)
