@@ -239,6 +239,29 @@ int masic_range_decode_rows(MasicRangeDecoder* dec, const int32_t* rows_host, in
                             int32_t* symbols_host);
 void masic_range_decoder_destroy(MasicRangeDecoder* dec);
 
+/* rANS serialisation of the z side information with the byte format of the reference's `compressai.ans`
+ * extension (compressai/cpp_exts/rans/rans_interface.cpp: BufferedRansEncoder.encode_with_indexes :108-173,
+ * flush :175-200, RansDecoder.set_stream :270-276, decode_stream :278-343; reached from
+ * EntropyModel.compress / decompress, entropy_models.py:165-239).  The reference hands symbols, indexes and the
+ * CDF tables over as Python lists (`.tolist()` of the whole table per call, entropy_models.py:189-194); these
+ * entry points take the int32 buffers themselves: cdfs_host is the (n_tables, row_pitch) `_quantized_cdf` tensor,
+ * cdf_sizes_host / offsets_host the `_cdf_length` / `_offset` tensors.  HOST buffers; byte strings are identical
+ * to the reference extension's for the same inputs (tests/test_rans_cpu.py). */
+typedef struct MasicRansEncoder MasicRansEncoder;
+typedef struct MasicRansDecoder MasicRansDecoder;
+int masic_rans_encoder_create(MasicRansEncoder** enc_out);
+int masic_rans_encoder_push(MasicRansEncoder* enc, const int32_t* symbols_host, const int32_t* indexes_host,
+                            int64_t n, const int32_t* cdfs_host, int n_tables, int row_pitch,
+                            const int32_t* cdf_sizes_host, const int32_t* offsets_host);
+/* *data_out points into the encoder and stays valid until the next call on it */
+int masic_rans_encoder_flush(MasicRansEncoder* enc, const uint8_t** data_out, int64_t* len_out);
+void masic_rans_encoder_destroy(MasicRansEncoder* enc);
+int masic_rans_decoder_create(const uint8_t* data_host, int64_t len, MasicRansDecoder** dec_out);
+int masic_rans_decoder_decode(MasicRansDecoder* dec, const int32_t* indexes_host, int64_t n,
+                              const int32_t* cdfs_host, int n_tables, int row_pitch, const int32_t* cdf_sizes_host,
+                              const int32_t* offsets_host, int32_t* symbols_host);
+void masic_rans_decoder_destroy(MasicRansDecoder* dec);
+
 /* ------------------------------------------------------------ image domain */
 /* kornia.warp_perspective(src, M, (h_out, w_out)) — kornia 0.5.0, call sites MASIC.py:781,821,833.
  * Step 1: T = inv(N_dst M inv(N_src)) per batch element (invert_m=1 first replaces M by

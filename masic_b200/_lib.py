@@ -123,6 +123,13 @@ def _declare(lib: C.CDLL) -> None:
         "masic_range_decoder_create": (i, [vp, i64, C.POINTER(vp)]),
         "masic_range_decode_rows": (i, [vp, vp, i, i, vp]),
         "masic_range_decoder_destroy": (None, [vp]),
+        "masic_rans_encoder_create": (i, [C.POINTER(vp)]),
+        "masic_rans_encoder_push": (i, [vp, vp, vp, i64, vp, i, i, vp, vp]),
+        "masic_rans_encoder_flush": (i, [vp, C.POINTER(vp), C.POINTER(i64)]),
+        "masic_rans_encoder_destroy": (None, [vp]),
+        "masic_rans_decoder_create": (i, [vp, i64, C.POINTER(vp)]),
+        "masic_rans_decoder_decode": (i, [vp, vp, i64, vp, i, i, vp, vp, vp]),
+        "masic_rans_decoder_destroy": (None, [vp]),
         "masic_warp_prepare": (i, [vp, i, i, i, i, i, i, vp, vp]),
         "masic_warp_perspective_fwd": (i, [vp, i, i, i, i, i, i, vp, vp, vp, i, i, i, vp]),
         "masic_conv_small_nchw": (i, [vp, i, vp, i, i, i, i, vp, i, vp, i, i, i, i, i, vp, vp, f, vp, vp, i, i, i, vp]),

@@ -238,7 +238,10 @@ class WgradPlan:
     """Tensor-core weight gradient of one conv / transposed-conv layer (MasicWgradPlan of the C ABI).
     `lo` / `hi` are the bound NHWC bf16 buffers (see include/masic_b200.h), `dw` the fp32 torch-layout gradient."""
 
-    _ws: dict = {}          # one shared workspace per device, grown to the largest plan
+    # Partial-sum workspace: plans of one device share the current buffer while it is large enough; a plan that needs
+    # more allocates a new one for itself and its successors.  Every plan keeps a reference to the buffer it bound,
+    # so a CUDA graph that captured an earlier plan's launch never sees its workspace freed (ADVICE r1).
+    _ws: dict = {}
 
     def __init__(self, *, ksize: int, stride: int, lo: torch.Tensor, c_lo: int, hi: torch.Tensor, c_hi: int,
                  dw: torch.Tensor, lo_coff: int = 0, hi_coff: int = 0, tap_mask: int = 0, accumulate: bool = False):
@@ -266,10 +269,10 @@ class WgradPlan:
         cur = WgradPlan._ws.get(key)
         if cur is None or cur.numel() * 4 < need:
             WgradPlan._ws[key] = torch.empty(need // 4 + 1024, dtype=torch.float32, device=lo.device)
-        self._key = key
+        self._bound_ws = WgradPlan._ws[key]
 
     def launch(self, stream: Optional[int] = None) -> None:
-        ws = WgradPlan._ws[self._key]
+        ws = self._bound_ws
         check(self._lib.masic_wgrad_plan_launch(self._h, ws.data_ptr(), _stream() if stream is None else stream),
               "masic_wgrad_plan_launch")
 

@@ -349,57 +349,95 @@ latent_prep_kernel(const float* __restrict__ y, long total, int C, __nv_bfloat16
 //   pmf[s]  = sum_k w_k [Phi((.5 - |s - (mu_k + minmax)|)/max(sigma_k, bound)) - Phi((-.5 - |..|)/..)],  s = 0..2*minmax
 //   pmf     = round(clip(pmf, 1/65536, 1) / sum(clip) * 65536)          (float32 throughout)
 //   cdf     = [0] + cumsum(pmf)                                         (its total need not be 65536)
-// One warp per (position, listed channel).  mode 0 writes the whole row (L+1 int32, L = 2*minmax+1), which the
-// decoder searches; mode 1 writes only (cdf[sym], cdf[sym+1]-cdf[sym], cdf[L]) for the known symbol
+// One warp per (position, listed channel).  rows != NULL writes the whole row (L+1 int32, L = 2*minmax+1), which
+// the decoder searches; intervals != NULL writes (cdf[sym], cdf[sym+1]-cdf[sym], cdf[L]) for the known symbol
 // sym = y_hat + minmax — all an encoder needs.
+//
+// EXACTNESS.  The reference evaluates the pmf with separate torch ops on cuda:0 (MASIC.py:988-1022: sub, abs, div,
+// mul, erfc, mul, sub, mul, add — each an IEEE fp32 kernel) and the normalisation with NumPy on the host
+// (:1040-1043, float32: np.clip, np.sum, /, *, np.round, np.add.accumulate).  Every operation below is therefore a
+// single correctly rounded fp32 operation in the same order (the _rn intrinsics keep nvcc from contracting them into
+// FMAs), erfc is CUDA's erfcf (what torch calls), and the sum of the clipped pmf follows NumPy's pairwise summation
+// order (blocks of <= 128 with eight interleaved accumulators, halves split at multiples of 8), so that the integer
+// rows are IDENTICAL to the reference's, not just close (tests/test_bitstream_gpu.py).
+
+// np.sum over a contiguous float32 vector (numpy/_core/src/umath/loops_utils.h.src, *_pairwise_sum): all lanes
+// call this with the same arguments and get the same result.
+__device__ float numpy_pairwise_sum(const float* a, int n, int lane) {
+  if (n < 8) {
+    float r = -0.0f;
+    for (int i = 0; i < n; ++i) r = __fadd_rn(r, a[i]);
+    return r;
+  }
+  if (n <= 128) {
+    const int j = lane & 7;                       // lane j (and its copies j+8, j+16, j+24) owns accumulator j
+    float r = a[j];
+    const int body = n - (n & 7);
+    for (int i = 8; i < body; i += 8) r = __fadd_rn(r, a[i + j]);
+    const float r0 = __shfl_sync(0xffffffffu, r, 0), r1 = __shfl_sync(0xffffffffu, r, 1);
+    const float r2 = __shfl_sync(0xffffffffu, r, 2), r3 = __shfl_sync(0xffffffffu, r, 3);
+    const float r4 = __shfl_sync(0xffffffffu, r, 4), r5 = __shfl_sync(0xffffffffu, r, 5);
+    const float r6 = __shfl_sync(0xffffffffu, r, 6), r7 = __shfl_sync(0xffffffffu, r, 7);
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(r0, r1), __fadd_rn(r2, r3)),
+                          __fadd_rn(__fadd_rn(r4, r5), __fadd_rn(r6, r7)));
+    for (int i = body; i < n; ++i) res = __fadd_rn(res, a[i]);
+    return res;
+  }
+  int n2 = n / 2;
+  n2 -= n2 & 7;
+  const float lo = numpy_pairwise_sum(a, n2, lane);
+  const float hi = numpy_pairwise_sum(a + n2, n - n2, lane);
+  return __fadd_rn(lo, hi);
+}
+
 template <int K>
 __global__ void __launch_bounds__(256)
 gmm_cdf_kernel(const float* __restrict__ sigma, const float* __restrict__ mu, const float* __restrict__ wgt,
                int w_is_logits, int M, long n_pos, const int32_t* __restrict__ ch_list, int n_ch, int minmax,
                float scale_bound, const float* __restrict__ y_hat_nhwc, int32_t* __restrict__ rows,
                int32_t* __restrict__ intervals) {
-  const long wid = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+  extern __shared__ float cdf_smem[];             // [warps per block][L]: the clipped pmf of each warp's element
+  const int warp_in_block = threadIdx.x >> 5;
+  const long wid = (long)blockIdx.x * (blockDim.x >> 5) + warp_in_block;
   const int lane = threadIdx.x & 31;
   if (wid >= n_pos * n_ch) return;
   const long pos = wid / n_ch;
   const int ch = ch_list[wid - pos * n_ch];
   const int L = 2 * minmax + 1;
+  float* pmf = cdf_smem + (size_t)warp_in_block * L;
   float s_k[K], m_k[K], w_k[K];
   const long base = pos * (long)(M * K) + ch;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    s_k[k] = fmaxf(sigma[base + (long)k * M], scale_bound);
-    m_k[k] = mu[base + (long)k * M] + (float)minmax;
+    s_k[k] = fmaxf(sigma[base + (long)k * M], scale_bound);             // lower_bound_scale (:1013)
+    m_k[k] = __fadd_rn(mu[base + (long)k * M], (float)minmax);          // means + minmax (:1001)
     w_k[k] = wgt[base + (long)k * M];
   }
-  if (w_is_logits) {
+  if (w_is_logits) {                              // torch.softmax over K (MASIC.py:393): exp(x - max) / sum, fp32
     float mx = -INFINITY;
 #pragma unroll
     for (int k = 0; k < K; ++k) mx = fmaxf(mx, w_k[k]);
     float sum = 0.0f;
 #pragma unroll
-    for (int k = 0; k < K; ++k) { w_k[k] = expf(w_k[k] - mx); sum += w_k[k]; }
+    for (int k = 0; k < K; ++k) { w_k[k] = expf(__fsub_rn(w_k[k], mx)); sum = __fadd_rn(sum, w_k[k]); }
 #pragma unroll
-    for (int k = 0; k < K; ++k) w_k[k] = w_k[k] / sum;
+    for (int k = 0; k < K; ++k) w_k[k] = __fdiv_rn(w_k[k], sum);
   }
-  auto pmf_at = [&](int s) -> float {
+  // pass 1: the clipped pmf (np.clip(pmf, 1/65536, 1)), one sample per lane and step
+  for (int s = lane; s < L; s += 32) {
     float acc = 0.0f;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      const float v = fabsf((float)s - m_k[k]);
-      // the coder model keeps erfcf() and IEEE division: the reference evaluates this rule with torch on the GPU
-      // (MASIC.py:738-742, :1013-1016), i.e. with the same CUDA erfcf
-      const float d = phi_exact((0.5f - v) / s_k[k]) - phi_exact((-0.5f - v) / s_k[k]);
-      acc = (k == 0) ? d * w_k[0] : acc + d * w_k[k];
+      const float v = fabsf(__fsub_rn((float)s, m_k[k]));
+      const float up = __fmul_rn(0.5f, erfcf(__fmul_rn(kInvSqrt2Neg, __fdiv_rn(__fsub_rn(0.5f, v), s_k[k]))));
+      const float lo = __fmul_rn(0.5f, erfcf(__fmul_rn(kInvSqrt2Neg, __fdiv_rn(__fsub_rn(-0.5f, v), s_k[k]))));
+      const float t = __fmul_rn(__fsub_rn(up, lo), w_k[k]);
+      acc = (k == 0) ? t : __fadd_rn(acc, t);
     }
-    return fminf(fmaxf(acc, 1.0f / 65536.0f), 1.0f);
-  };
-  // pass 1: sum of the clipped pmf (lane-strided partial sums, then a shuffle tree; fp32 like np.sum)
-  float part = 0.0f;
-  for (int s = lane; s < L; s += 32) part += pmf_at(s);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-  const float total = part;
+    pmf[s] = fminf(fmaxf(acc, 1.0f / 65536.0f), 1.0f);
+  }
+  __syncwarp();
+  const float total = numpy_pairwise_sum(pmf, L, lane);
   // pass 2: rounded counts and their running sum, 32 samples at a time
   const int sym = y_hat_nhwc ? (int)y_hat_nhwc[pos * (long)M + ch] + minmax : -1;
   int run = 0, lo = 0, fr = 0;
@@ -408,7 +446,7 @@ gmm_cdf_kernel(const float* __restrict__ sigma, const float* __restrict__ mu, co
   for (int s0 = 0; s0 < L; s0 += 32) {
     const int s = s0 + lane;
     int c = 0;
-    if (s < L) c = (int)rintf(pmf_at(s) / total * 65536.0f);
+    if (s < L) c = (int)rintf(__fmul_rn(__fdiv_rn(pmf[s], total), 65536.0f));
     int inc = c;                                  // inclusive scan inside the warp
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -527,8 +565,17 @@ extern "C" int masic_gmm_symbol_cdfs(const float* sigma_nhwc, const float* mu_nh
   if (k != 5) return MASIC_ENOSUP;
   const long warps = n_pos * n_ch;
   if (warps == 0) return MASIC_OK;
-  const long blocks = (warps * 32 + 255) / 256;
-  gmm_cdf_kernel<5><<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  const int L = 2 * minmax + 1;
+  int wpb = 8;                                      // warps per block, limited by L floats of shared memory per warp
+  while (wpb > 1 && (size_t)wpb * L * sizeof(float) > 96 * 1024) wpb >>= 1;
+  const size_t smem = (size_t)wpb * L * sizeof(float);
+  if (smem > 200 * 1024) return MASIC_ENOSUP;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(gmm_cdf_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const long blocks = (warps + wpb - 1) / wpb;
+  gmm_cdf_kernel<5><<<(unsigned)blocks, wpb * 32, smem, static_cast<cudaStream_t>(stream)>>>(
       sigma_nhwc, mu_nhwc, weights_nhwc, weights_are_logits, m, n_pos, ch_list, n_ch, minmax, scale_bound,
       y_hat_nhwc, rows, intervals);
   return (int)cudaGetLastError();

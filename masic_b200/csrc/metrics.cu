@@ -49,7 +49,7 @@ __device__ __forceinline__ double sum_log(const float* __restrict__ p, long n) {
   double acc = 0.0;
   const long tid = (long)blockIdx.x * RD_THREADS + threadIdx.x, nth = (long)RD_BLOCKS * RD_THREADS;
   const long head = min(n, (long)((16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15) / 4);
-  for (long i = tid; i < head; i += nth) acc += (double)__logf(p[i]);
+  for (long i = tid; i < head; i += nth) acc += (double)logf(p[i]);
   const float4* p4 = reinterpret_cast<const float4*>(p + head);
   const long n4 = (n - head) / 4;
   for (long i = tid; i < n4; i += nth) {

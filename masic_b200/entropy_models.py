@@ -5,14 +5,14 @@ Constructor signatures, parameter/buffer names, error messages and call semantic
 compressai/entropy_models/entropy_models.py of the reference (line numbers cited per
 method).  Quantise / likelihood / CDF-index computation run in CUDA (masic_b200/csrc/
 entropy.cu); the integer CDF construction runs in the library's host code (csrc/cdf.cu);
-rANS serialisation stays in the reference's own `compressai.ans` extension, exactly as
-BASELINE.json's north-star prescribes.
+rANS serialisation is host code outside the GPU hot path (BASELINE.json's north-star): the
+library's native coder (csrc/rans.cpp) writes the byte format of the reference's `compressai.ans`
+extension and takes int32 buffers instead of Python lists.
 """
 from __future__ import annotations
 
 import importlib
 import os
-import sys
 from typing import List, Optional
 
 import numpy as np
@@ -36,32 +36,20 @@ def pmf_to_quantized_cdf(pmf: Tensor, precision: int = 16) -> Tensor:
 
 
 def _load_ans():
-    """The reference's rANS coder (compressai/cpp_exts/rans), kept verbatim per the north-star.
-    Resolution order: $MASIC_ANS_MODULE, an installed `compressai.ans`, then the binary that
-    `make -C oracle ref` compiled from the reference's sources (travels to the GPU box)."""
+    """The rANS coder behind EntropyModel.compress / decompress.  Default: the library's own native coder
+    (masic_b200/rans.py over `masic_rans_*`, csrc/rans.cpp), which writes the byte format of the reference's
+    `compressai.ans` extension and takes int32 buffers instead of Python lists.  $MASIC_ANS_MODULE names another
+    module with the `compressai.ans` surface (e.g. the reference's own extension where it is installed); nothing
+    here looks under oracle/."""
     name = os.environ.get("MASIC_ANS_MODULE")
     if name:
         return importlib.import_module(name)
-    mod = sys.modules.get("compressai.ans")
-    if mod is not None and hasattr(mod, "RansEncoder"):
-        return mod
-    import importlib.machinery
-    import importlib.util
-    import sysconfig
-    from pathlib import Path
-    so = Path(__file__).resolve().parents[1] / "oracle" / "_ref" / f"ans{sysconfig.get_config_var('EXT_SUFFIX')}"
-    if so.exists():
-        loader = importlib.machinery.ExtensionFileLoader("ans", str(so))
-        spec = importlib.util.spec_from_file_location("ans", str(so), loader=loader)
-        m = importlib.util.module_from_spec(spec)
-        loader.exec_module(m)
-        return m
-    raise MasicError("no rANS coder: build the reference's compressai.ans extension "
-                     "(`make -C oracle ref`) or set MASIC_ANS_MODULE")
+    from . import rans
+    return rans
 
 
 class _EntropyCoder:
-    """entropy_models.py:13-42 — proxy to the reference's `ans` extension."""
+    """entropy_models.py:13-42 — proxy to the rANS coder."""
 
     def __init__(self, method: str):
         if not isinstance(method, str):
@@ -70,11 +58,13 @@ class _EntropyCoder:
             raise ValueError(f'Unknown entropy coder "{method}" (available: ans)')
         self._encoder = None
         self._decoder = None
+        self.native = False
 
     def _ensure(self):
         if self._encoder is None:
             ans = _load_ans()
             self._encoder, self._decoder = ans.RansEncoder(), ans.RansDecoder()
+            self.native = hasattr(self._decoder, "decode_with_indexes_array")
 
     def encode_with_indexes(self, *a, **k):
         self._ensure()
@@ -144,19 +134,40 @@ class EntropyModel(nn.Module):
         if len(self._cdf_length.size()) != 1:
             raise ValueError(f"Invalid offsets size {self._cdf_length.size()}")
 
-    def _tables_as_lists(self):
-        # the reference converts the tables on every call (entropy_models.py:192-194, SURVEY a12:
-        # 0.32 s per call); they only change in update(), so the lists are cached on their version.
-        key = (self._quantized_cdf._version, self._quantized_cdf.data_ptr(), self._offset.data_ptr())
+    # The coder tables only change in update() / update_scale_table() / load_state_dict(): their host-side copies
+    # (an int32 TableSet for the native coder, Python lists for a `compressai.ans`-style module — the reference
+    # converts them on every call, entropy_models.py:192-194) are cached and dropped EXPLICITLY whenever one of the
+    # three buffers is assigned or loaded; staleness is never inferred from versions or pointers.
+    _TABLE_BUFFERS = ("_quantized_cdf", "_cdf_length", "_offset")
+
+    def __setattr__(self, name, value):
+        if name in EntropyModel._TABLE_BUFFERS:
+            self.__dict__.pop("_tbl_cache", None)
+        super().__setattr__(name, value)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self.__dict__.pop("_tbl_cache", None)
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def invalidate_tables(self):
+        """Call after editing `_quantized_cdf` / `_cdf_length` / `_offset` IN PLACE."""
+        self.__dict__.pop("_tbl_cache", None)
+
+    def _coder_tables(self):
+        self.entropy_coder._ensure()
         cached = self.__dict__.get("_tbl_cache")
-        if cached is None or cached[0] != key:
-            cached = (key, self._quantized_cdf.tolist(), self._cdf_length.reshape(-1).int().tolist(),
-                      self._offset.reshape(-1).int().tolist())
+        if cached is None:
+            if self.entropy_coder.native:
+                from .rans import TableSet
+                cached = (TableSet(self._quantized_cdf, self._cdf_length.reshape(-1), self._offset.reshape(-1)),)
+            else:
+                cached = (self._quantized_cdf.tolist(), self._cdf_length.reshape(-1).int().tolist(),
+                          self._offset.reshape(-1).int().tolist())
             self.__dict__["_tbl_cache"] = cached
-        return cached[1], cached[2], cached[3]
+        return cached
 
     def compress(self, inputs: Tensor, indexes: Tensor, means: Optional[Tensor] = None) -> List[bytes]:
-        """entropy_models.py:165-196: symbols on the GPU, serialisation by the reference's rANS ext."""
+        """entropy_models.py:165-196: symbols on the GPU; serialisation by the rANS coder on int32 buffers."""
         symbols = self._quantize(inputs, "symbols", means)
         if len(inputs.size()) != 4:
             raise ValueError("Invalid `inputs` size. Expected a 4-D tensor.")
@@ -165,13 +176,17 @@ class EntropyModel(nn.Module):
         self._check_cdf_size()
         self._check_cdf_length()
         self._check_offsets_size()
-        cdf, lens, offs = self._tables_as_lists()
-        sym_cpu = symbols.cpu()
-        idx_cpu = indexes.cpu()
+        tables = self._coder_tables()
+        sym_cpu = symbols.to(torch.int32).cpu()
+        idx_cpu = indexes.to(torch.int32).cpu()
         strings = []
         for i in range(sym_cpu.size(0)):
-            strings.append(self.entropy_coder.encode_with_indexes(
-                sym_cpu[i].reshape(-1).int().tolist(), idx_cpu[i].reshape(-1).int().tolist(), cdf, lens, offs))
+            if self.entropy_coder.native:
+                strings.append(self.entropy_coder.encode_with_indexes(
+                    sym_cpu[i].reshape(-1).numpy(), idx_cpu[i].reshape(-1).numpy(), *tables))
+            else:
+                strings.append(self.entropy_coder.encode_with_indexes(
+                    sym_cpu[i].reshape(-1).tolist(), idx_cpu[i].reshape(-1).tolist(), *tables))
         return strings
 
     def decompress(self, strings, indexes: Tensor, means: Optional[Tensor] = None) -> Tensor:
@@ -190,12 +205,17 @@ class EntropyModel(nn.Module):
                 raise ValueError("Invalid means or indexes parameters")
             if means.size() != indexes.size() and (means.size(2) != 1 or means.size(3) != 1):
                 raise ValueError("Invalid means parameters")
-        cdf, lens, offs = self._tables_as_lists()
-        idx_cpu = indexes.cpu()
+        tables = self._coder_tables()
+        idx_cpu = indexes.to(torch.int32).cpu()
         outputs = torch.empty(indexes.size(), dtype=torch.int32)
         for i, s in enumerate(strings):
-            values = self.entropy_coder.decode_with_indexes(s, idx_cpu[i].reshape(-1).int().tolist(), cdf, lens, offs)
-            outputs[i] = torch.tensor(values, dtype=torch.int32).reshape(outputs[i].size())
+            if self.entropy_coder.native:
+                values = torch.from_numpy(self.entropy_coder._decoder.decode_with_indexes_array(
+                    s, idx_cpu[i].reshape(-1).numpy(), *tables))
+            else:
+                values = torch.tensor(self.entropy_coder.decode_with_indexes(
+                    s, idx_cpu[i].reshape(-1).tolist(), *tables), dtype=torch.int32)
+            outputs[i] = values.reshape(outputs[i].size())
         outputs = outputs.to(self._quantized_cdf.device if means is None else means.device)
         return self._dequantize(outputs, means)
 

@@ -202,6 +202,66 @@ class HSIC(nn.Module):
             "likelihoods": {"y1": c(o["lik_y1"]), "y2": c(o["lik_y2"]), "z1": c(o["lik_z1"]), "z2": c(o["lik_z2"])},
         }
 
+    # ---- the same forward, layer by layer (what the unmodified MASIC.py does on masic_b200/compat)
+    @torch.no_grad()
+    def forward_modules(self, x1: torch.Tensor, x2: torch.Tensor, h_matrix: torch.Tensor):
+        """MASIC.py:744-851 (eval) in the reference's own call order, every step one `nn.Module.forward` of
+        masic_b200.layers / entropy_models / kornia_compat on NCHW fp32 tensors — the path the reference's model file
+        takes when its `compressai` / `kornia` imports resolve to masic_b200/compat (path B).  No
+        engine, no fusion, no CUDA graph: each conv packs its input to NHWC bf16, runs the tensor-core kernel and
+        unpacks; GDN, warp, likelihoods are their stand-alone kernels."""
+        from . import kornia_compat as kornia
+        if self.training:
+            raise MasicError("forward_modules implements eval mode (use model.trainer(...) for the training step)")
+
+        def enc(e, x):                                      # Encoder1/2.forward, MASIC.py:521-531 / :570-585
+            x = e.g_a_gdn1(e.g_a_conv1(x))
+            x = e.g_a_gdn2(e.g_a_conv2(x))
+            x = e.g_a_gdn3(e.g_a_conv3(x))
+            return e.g_a_conv4(x)
+
+        def dec(d, y):                                      # Decoder1/2.forward, MASIC.py:544-554 / :602-616
+            y = d.g_s_gdn1(d.g_s_conv1(y))
+            y = d.g_s_gdn2(d.g_s_conv2(y))
+            y = d.g_s_gdn3(d.g_s_conv3(y))
+            return d.g_s_conv4(y)
+
+        def gmm(net, x):                                    # MASIC.py:378-396 / :446-468
+            sigma, mu, lw = net.gmm_sigma(x), net.gmm_means(x), net.gmm_weights(x)
+            t = lw.reshape(-1, self.K, self.M, x.shape[-2], x.shape[-1])
+            return sigma, mu, torch.softmax(t, dim=-4).reshape(-1, self.M * self.K, x.shape[-2], x.shape[-1])
+
+        size = (x1.size()[-2], x1.size()[-1])
+        y1 = enc(self.encoder1, x1)
+        z1 = self._h_a1.encode_hyper(torch.abs(y1))
+        z1_hat, z1_lik = self.entropy_bottleneck1(z1)
+        params1 = self.h_s1_up(z1_hat)
+        y1_hat = self.gaussian1._quantize(y1, "dequantize")
+        ctx1 = self.context_prediction1(y1_hat)
+        y1_hat, y1_lik = self.gaussian1(y1, *gmm(self._h_s1_same_resolution, torch.cat((params1, ctx1), dim=1)))
+        x1_hat = dec(self.decoder1, y1_hat)
+        x1_warp = kornia.warp_perspective(x1, h_matrix, size)
+        e2 = self.encoder2
+        y2 = enc(e2, e2.pre_gdn(e2.pre_conv(torch.cat((x1_warp, x2), dim=-3))))
+        z2 = self._h_a2.encode_hyper(torch.abs(y2))
+        z2_hat, z2_lik = self.entropy_bottleneck2(z2)
+        params2 = self.h_s2_up(z2_hat)
+        y2_hat = self.gaussian2._quantize(y2, "dequantize")
+        ctx2 = self.context_prediction2(y2_hat)
+        ones = torch.ones(x1.shape[0], 1, *size, dtype=x1.dtype, device=x1.device)          # mask(), MASIC.py:627-649
+        mask_r = kornia.warp_perspective(ones, h_matrix, size)
+        mask_l = kornia.warp_perspective(mask_r, torch.inverse(h_matrix), size)
+        o = self.mask2weights_unit.maskconv(mask_r)                                          # MASIC.py:493-506
+        mw = torch.softmax(o.reshape(-1, 3, 1, o.shape[-2], o.shape[-1]), dim=-4).reshape(-1, 3, o.shape[-2], o.shape[-1])
+        x1_hat_warp = kornia.warp_perspective(x1_hat, h_matrix, size)
+        y1w_hat = self.gaussian1._quantize(enc(self.encoder1, x1_hat_warp), "dequantize")
+        fused = torch.cat((params2 * mw[:, 0:1], ctx2 * mw[:, 1:2], y1w_hat * mw[:, 2:3]), dim=1)
+        y2_hat, y2_lik = self.gaussian2(y2, *gmm(self._h_s2_same_resolution, fused))
+        d2 = self.decoder2
+        x2_hat = d2.after_conv(torch.cat((d2.after_gdn(dec(d2, y2_hat)), x1_hat_warp), dim=-3))
+        return {"x1_hat": x1_hat, "x2_hat": x2_hat, "y1_hat": y1_hat, "z1_hat": z1_hat, "x1_mask_R": mask_r,
+                "x1_mask_L": mask_l, "likelihoods": {"y1": y1_lik, "y2": y2_lik, "z1": z1_lik, "z2": z2_lik}}
+
     def pair_stream(self, height: int, width: int, device, depth: int = 2, lmbda: float = 0.0) -> "PairStream":
         """Pipelined host-to-host evaluation of batch-1 stereo pairs (see PairStream)."""
         return PairStream(self, height, width, device, depth=depth, lmbda=lmbda)

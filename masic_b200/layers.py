@@ -96,7 +96,8 @@ class _TCConvMixin:
             if transposed and s != 1:
                 raise MasicError("tiny transposed conv with stride 2 is not on MASIC's path")
             return ops.conv_small(x, None, self.weight, self.bias, ksize=k, stride=s, transposed_s1=transposed)
-        key = (tuple(x.shape), x.device, self.weight._version, self.weight.data_ptr())
+        key = (tuple(x.shape), x.device, self.weight._version, self.weight.data_ptr(),
+               None if self.bias is None else (self.bias._version, self.bias.data_ptr()))
         cache = self.__dict__.setdefault("_plan_cache", {})
         ent = cache.get(key)
         if ent is None:
@@ -159,6 +160,13 @@ class Conv2d(_TCConvMixin, nn.Conv2d):
 
 class ConvTranspose2d(_TCConvMixin, nn.ConvTranspose2d):
     def forward(self, x: Tensor, output_size=None) -> Tensor:
+        if output_size is not None:
+            want = tuple(int(v) for v in output_size)[-2:]
+            s, k, p, op = self.stride[0], self.kernel_size[0], self.padding[0], self.output_padding[0]
+            have = tuple((d - 1) * s - 2 * p + k + op for d in x.shape[-2:])
+            if want != have:
+                raise MasicError(f"ConvTranspose2d: output_size {want} differs from the size the layer's own "
+                                 f"output_padding gives ({have}); only deconv()'s geometry is on the sm_100a path")
         return self._tc_forward(x, transposed=True)
 
 

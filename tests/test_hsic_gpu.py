@@ -15,9 +15,10 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-BPP_RTOL = 1e-3          # 0.1 %
-PSNR_ATOL = 0.01         # dB
-SYMBOL_FLIP_MAX = 0.02
+from parity_common import BPP_RTOL, PSNR_ATOL, record as _record   # tests/parity_common.py
+
+SYMBOL_FLIP_MAX = 0.005     # measured: 0.05-0.12 % at weight scale 1-8 (profiles/r2_parity.json)
+SYMBOL_FLIP_MAX_WIDE = 0.02  # latents spanning +-60 (g_a_conv4 x50): bf16 noise grows with |y|, the .5 boundaries do not
 
 
 def _t(a):
@@ -81,7 +82,7 @@ def test_forward_parity_with_oracle_and_reference_fixture(dev, golden_dir, tag, 
     for k in ("x1_hat", "x2_hat", "y1_hat", "z1_hat", "x1_mask_R", "x1_mask_L"):
         assert out[k].shape == ref[k].shape and bool(torch.isfinite(out[k]).all()), k
     flips = float((out["y1_hat"] != ref["y1_hat"]).float().mean())
-    assert flips <= SYMBOL_FLIP_MAX, flips
+    assert flips <= (SYMBOL_FLIP_MAX if scale <= 8 else SYMBOL_FLIP_MAX_WIDE), flips
     assert float((out["y1_hat"] - ref["y1_hat"]).abs().max()) <= 1.0
     assert (out["x1_mask_R"] - ref["x1_mask_R"]).abs().max() <= 1e-4
     assert (out["x1_mask_L"] - ref["x1_mask_L"]).abs().max() <= 1e-4
@@ -195,3 +196,113 @@ def test_pair_stream_uint8_inputs_and_depth(dev):
             assert torch.equal(ps.outputs()["x1_hat"], want[i]["x1_hat"])
             assert torch.equal(ps.outputs()["x2_hat"], want[i]["x2_hat"])
             assert torch.equal(ps.outputs()["lik_y2"], want[i]["likelihoods"]["y2"])
+
+
+def _compare_with_oracle(name, out, ref, x1, x2, scale, extra=None):
+    """The north-star's tolerances against the oracle, with the measured margins recorded."""
+    n, _, h, w = x1.shape
+    npx = n * h * w
+    b_ref, b_out = _bpp(ref, npx), _bpp(out, npx)
+    tot_ref, tot_out = sum(b_ref.values()), sum(b_out.values())
+    flips1 = float((out["y1_hat"] != ref["y1_hat"]).float().mean())
+    d1 = abs(_psnr(out["x1_hat"], x1) - _psnr(ref["x1_hat"], x1))
+    d2 = abs(_psnr(out["x2_hat"], x2) - _psnr(ref["x2_hat"], x2))
+    rec = dict(scale=scale, shape=[n, h, w], bpp_oracle=tot_ref, bpp_cuda=tot_out, dbpp_rel=abs(tot_out - tot_ref) / tot_ref,
+               psnr1_oracle=_psnr(ref["x1_hat"], x1), psnr2_oracle=_psnr(ref["x2_hat"], x2), dpsnr1_db=d1, dpsnr2_db=d2,
+               y1_symbol_flips=flips1, y1_max_abs_diff=float((out["y1_hat"] - ref["y1_hat"]).abs().max()),
+               z1_symbol_flips=float((out["z1_hat"] != ref["z1_hat"]).float().mean()),
+               tol=dict(dbpp_rel=BPP_RTOL, dpsnr_db=PSNR_ATOL))
+    rec.update(extra or {})
+    _record(name, **rec)
+    print(name, rec)
+    assert abs(tot_out - tot_ref) <= BPP_RTOL * tot_ref, (b_out, b_ref)
+    assert d1 <= PSNR_ATOL and d2 <= PSNR_ATOL, (d1, d2)
+    assert flips1 <= (SYMBOL_FLIP_MAX if scale <= 8 else SYMBOL_FLIP_MAX_WIDE), flips1
+    assert rec["y1_max_abs_diff"] <= 1.0
+    assert (out["x1_mask_R"] - ref["x1_mask_R"]).abs().max() <= 1e-4
+    return rec
+
+
+def _cpu(out):
+    return {k: (v.cpu() if torch.is_tensor(v) else {kk: vv.cpu() for kk, vv in v.items()}) for k, v in out.items()}
+
+
+@pytest.mark.parametrize("h,w", [(512, 512), (1216, 2176)])
+@pytest.mark.parametrize("scale", [1.0, 8.0, 50.0])
+def test_forward_parity_at_baseline_sizes(dev, h, w, scale):
+    """BASELINE.json configs[0] (512x512) and configs[1] (1216x2176), batch 1: the CUDA engine against the oracle on
+    the same seeded weights / inputs, at three latent scales (random init is degenerate: every y symbol is 0)."""
+    from masic_b200.hsic import HSIC
+    torch.set_num_threads(max(1, __import__("os").cpu_count() or 1))
+    oracle = _oracle(scale)
+    x1, x2, Hm = _inputs(h, w, seed=200 + int(scale))
+    ref = oracle(x1, x2, Hm)
+    net = HSIC().eval()
+    net.load_state_dict(oracle.state_dict())
+    net = net.to(dev)
+    with torch.no_grad():
+        out = _cpu(net(x1.to(dev), x2.to(dev), Hm.to(dev)))
+    _compare_with_oracle(f"forward_{h}x{w}_scale{int(scale)}", out, ref, x1, x2, scale)
+
+
+def test_batch64_of_512x512_pairs(dev):
+    """BASELINE.json configs[2]: 64 pairs of 512x512 in ONE engine.  Every item equals its own batch-1 run bit for bit
+    (pairs are independent: that is what makes sharding by pair across GPUs exact), and items 0 / 37 / 63 meet the
+    tolerances against the oracle."""
+    from masic_b200.hsic import HSIC
+    scale, B, h, w = 8.0, 64, 512, 512
+    oracle = _oracle(scale)
+    x1, x2, Hm = _inputs(h, w, seed=64, batch=B)
+    net = HSIC().eval()
+    net.load_state_dict(oracle.state_dict())
+    net = net.to(dev)
+    with torch.no_grad():
+        out = net(x1.to(dev), x2.to(dev), Hm.to(dev))
+        for i in (0, 37, 63):
+            one = net(x1[i:i + 1].to(dev), x2[i:i + 1].to(dev), Hm[i:i + 1].to(dev))
+            for k in ("x1_hat", "x2_hat", "y1_hat", "z1_hat", "x1_mask_R", "x1_mask_L"):
+                assert torch.equal(out[k][i:i + 1], one[k]), (i, k)
+            for k in ("y1", "y2", "z1", "z2"):
+                assert torch.equal(out["likelihoods"][k][i:i + 1], one["likelihoods"][k]), (i, k)
+    out = _cpu(out)
+    for i in (0, 37, 63):
+        ref = oracle(x1[i:i + 1], x2[i:i + 1], Hm[i:i + 1])
+        item = {k: (v[i:i + 1] if torch.is_tensor(v) else {kk: vv[i:i + 1] for kk, vv in v.items()}) for k, v in out.items()}
+        _compare_with_oracle(f"batch64_512x512_item{i}", item, ref, x1[i:i + 1], x2[i:i + 1], scale)
+
+
+def test_module_tree_forward_matches_engine_and_oracle(dev):
+    """INTEGRATION.md path B: the layer-by-layer forward (`HSIC.forward_modules`: masic_b200.layers.Conv2d /
+    ConvTranspose2d / MaskedConv2d / GDN, entropy_models.*, kornia_compat.warp_perspective called one module at a time
+    in the order of MASIC.py:744-851 — what the unmodified model file does on masic_b200/compat) against the fused
+    engine and against the oracle."""
+    import time
+    from masic_b200.hsic import HSIC
+    scale, h, w = 8.0, 256, 384
+    oracle = _oracle(scale)
+    x1, x2, Hm = _inputs(h, w, seed=21)
+    ref = oracle(x1, x2, Hm)
+    net = HSIC().eval()
+    net.load_state_dict(oracle.state_dict())
+    net = net.to(dev)
+    a, b, c = x1.to(dev), x2.to(dev), Hm.to(dev)
+    with torch.no_grad():
+        eng = _cpu(net(a, b, c))
+        mod = net.forward_modules(a, b, c)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            net.forward_modules(a, b, c)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 3
+    mod = _cpu(mod)
+    # MaskedConv2d's side effect (layers.py:77) is visible in the state_dict, as in the reference
+    assert float(net.context_prediction1.weight[:, :, 2, 2:].abs().max()) == 0.0
+    rec = _compare_with_oracle("module_tree_256x384_scale8", mod, ref, x1, x2, scale,
+                               extra={"pairs_per_s_module_tree": 1.0 / dt})
+    # module tree vs the fused engine: same kernels, fp32 instead of bf16 tensors BETWEEN layers
+    flips = float((mod["y1_hat"] != eng["y1_hat"]).float().mean())
+    assert flips <= SYMBOL_FLIP_MAX, flips
+    assert abs(_psnr(mod["x2_hat"], x2) - _psnr(eng["x2_hat"], x2)) <= PSNR_ATOL
+    assert torch.equal(mod["x1_mask_R"], eng["x1_mask_R"]) and torch.equal(mod["x1_mask_L"], eng["x1_mask_L"])
+    assert rec["dbpp_rel"] <= BPP_RTOL
