@@ -334,11 +334,13 @@ class PairStream:
                     lik_n=(C.c_int64 * 4)(*[t.numel() for t in liks])))
         self._n = 0
 
-    def submit(self, x1: torch.Tensor, x2: torch.Tensor, h: torch.Tensor, criterion: bool = True) -> int:
+    def submit(self, x1: torch.Tensor, x2: torch.Tensor, h: torch.Tensor, criterion: bool = True,
+               want_recon: bool = False) -> int:
         """Queue one pair.  x1 / x2: (1,3,H,W) float32 in [0,1] as the reference feeds them, or uint8 images as they
         come out of the dataset's PNG files (converted on the device exactly like torchvision's ToTensor); h: (1,3,3)
         float32.  Pinned host tensors (H2D copy) or device tensors (D2D copy).  criterion=False
-        skips the RateDistortionLoss reduction (forward only; `result` then just waits for the pair)."""
+        skips the RateDistortionLoss reduction (forward only; `result` then just waits for the pair).  want_recon=True
+        also copies the two reconstructions (what a codec is for) to pinned host memory: `reconstructions(ticket)`."""
         from ._lib import check
         s = self.slots[self._n % self.depth]
         if s["busy"]:
@@ -371,8 +373,13 @@ class PairStream:
                                                 self.lmbda, s["scratch"].data_ptr(), s["res_d"].data_ptr(),
                                                 st.cuda_stream), "masic_rd_metrics")
                 s["res_h"].copy_(s["res_d"], non_blocking=True)
+            if want_recon:
+                if "rec_h" not in s:
+                    s["rec_h"] = [torch.empty(1, 3, self.H, self.W).pin_memory() for _ in range(2)]
+                s["rec_h"][0].copy_(o["x1_hat"], non_blocking=True)
+                s["rec_h"][1].copy_(o["x2_hat"], non_blocking=True)
             s["done"].record(st)
-        s["busy"], s["has_result"] = True, criterion
+        s["busy"], s["has_result"], s["has_recon"] = True, criterion, want_recon
         self.eng = eng
         self._n += 1
         return self._n - 1
@@ -389,6 +396,17 @@ class PairStream:
         psnr = [10.0 * math.log10(1.0 / m) if m > 0 else float("inf") for m in r[4:6]]
         return r[6], psnr[0], psnr[1], {"bpp_y1": r[0], "bpp_y2": r[1], "bpp_z1": r[2], "bpp_z2": r[3],
                                         "mse1": r[4], "mse2": r[5], "loss": r[7]}
+
+    def reconstructions(self, ticket: int):
+        """(x1_hat, x2_hat) of a pair submitted with want_recon=True, as pinned HOST tensors (valid until the slot is
+        re-used, i.e. for the next depth-1 submissions); blocks until the D2H copies have landed."""
+        if not (self._n - self.depth <= ticket < self._n):
+            raise ValueError(f"ticket {ticket} is no longer (or not yet) in flight")
+        s = self.slots[ticket % self.depth]
+        s["done"].synchronize()
+        if not s.get("has_recon"):
+            raise ValueError("the pair was submitted without want_recon=True")
+        return s["rec_h"][0], s["rec_h"][1]
 
     def outputs(self) -> Dict[str, torch.Tensor]:
         return self.eng.out

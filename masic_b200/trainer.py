@@ -794,7 +794,8 @@ class HSICTrainer:
             fn()
 
     def train_step(self, x1: torch.Tensor, x2: torch.Tensor, h_matrix: torch.Tensor, optimizer, aux_optimizer,
-                   noise: Optional[Dict[str, torch.Tensor]] = None, group=None) -> Dict[str, float]:
+                   noise: Optional[Dict[str, torch.Tensor]] = None, group=None,
+                   clip_max_norm: Optional[float] = None) -> Dict[str, float]:
         """One iteration of newtrain_codec_real.py:105-146 on this rank's batch: forward + backward, the data-parallel
         gradient all-reduce (mean over ranks: the loss normalises by the LOCAL batch, :76), then both optimisers.
         `optimizer` holds model.parameters() (everything but the bottlenecks), `aux_optimizer` model.aux_parameters()
@@ -807,6 +808,15 @@ class HSICTrainer:
             if world > 1:
                 dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=group)
                 self.flat_grad.mul_(1.0 / world)
+        if clip_max_norm is not None and clip_max_norm > 0:
+            # torch.nn.utils.clip_grad_norm_(model.parameters(), clip_max_norm) of CompressAI's training loops, on the
+            # flat buffer: the main parameters' gradients (everything but the two bottlenecks, MASIC.py:77-94)
+            if getattr(self, "_main_grads", None) is None:
+                aux_ids = {id(p) for p in self.model.aux_parameters()}
+                self._main_grads = [self._grads[n] for n, p in self._params.items() if id(p) not in aux_ids]
+            total = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(g) for g in self._main_grads]))
+            coef = torch.clamp(clip_max_norm / (total + 1e-6), max=1.0)
+            torch._foreach_mul_(self._main_grads, coef)
         optimizer.step()
         aux_optimizer.step()
         return res

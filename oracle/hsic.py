@@ -49,14 +49,14 @@ _PEDESTAL = (2.0 ** -18) ** 2
 
 def nonneg_init(x: torch.Tensor) -> torch.Tensor:
     """ops/parametrizers.py:58-59."""
-    ped = torch.tensor([_PEDESTAL], dtype=x.dtype)
+    ped = torch.tensor([_PEDESTAL], dtype=x.dtype, device=x.device)
     return torch.sqrt(torch.max(x + ped, ped))
 
 
 def nonneg_forward(x: torch.Tensor, minimum: float) -> torch.Tensor:
     """ops/parametrizers.py:61-64: max(x, sqrt(minimum + pedestal))^2 - pedestal (fp32 buffers)."""
-    bound = torch.tensor([(minimum + _PEDESTAL) ** 0.5], dtype=torch.float32)
-    ped = torch.tensor([_PEDESTAL], dtype=torch.float32)
+    bound = torch.tensor([(minimum + _PEDESTAL) ** 0.5], dtype=torch.float32, device=x.device)
+    ped = torch.tensor([_PEDESTAL], dtype=torch.float32, device=x.device)
     return torch.max(x, bound) ** 2 - ped
 
 

@@ -219,7 +219,9 @@ def _compare_with_oracle(name, out, ref, x1, x2, scale, extra=None):
     assert d1 <= PSNR_ATOL and d2 <= PSNR_ATOL, (d1, d2)
     assert flips1 <= (SYMBOL_FLIP_MAX if scale <= 8 else SYMBOL_FLIP_MAX_WIDE), flips1
     assert rec["y1_max_abs_diff"] <= 1.0
-    assert (out["x1_mask_R"] - ref["x1_mask_R"]).abs().max() <= 1e-4
+    # warp: the oracle evaluates kornia's normalised fp32 grid, whose own error against the float64 ground truth grows
+    # with the image width (3e-4 at 2176 px, tests/test_image_gpu.py); the kernel's fp64 coordinates stay within 5e-6
+    assert (out["x1_mask_R"] - ref["x1_mask_R"]).abs().max() <= max(1e-4, 2.5e-7 * max(h, w))
     return rec
 
 

@@ -2,7 +2,7 @@
 the repo's own CUDA training step, on smooth synthetic stereo pairs, so that the parity tolerances (|dPSNR| <= 0.01 dB,
 |dbpp| <= 0.1 %) can be checked where they are not vacuous.
 
-    python tools/train_regime.py [--steps 300] [--lr 1e-3] [--lmbda 0.05] [--size 256 256] [--eval-size 256 384]
+    python tools/train_regime.py [--steps 300] [--lr 3e-4] [--clip 1.0] [--lmbda 0.05] [--size 256 256] [--eval-size 256 384]
 
 `train_to_psnr` is what tests/test_hsic_trained_gpu.py calls; run as a script it prints the trajectory and the
 CUDA-vs-oracle comparison of the trained weights."""
@@ -36,8 +36,8 @@ def smooth_pairs(batch, h, w, gen, shift_px=None):
     return x1, x2, Hm
 
 
-def train_to_psnr(net, dev, *, target_db=25.0, max_steps=600, batch=2, size=(256, 256), lr=1e-3, lmbda=0.05,
-                  seed=0, check_every=50, log=None):
+def train_to_psnr(net, dev, *, target_db=25.0, max_steps=600, batch=2, size=(256, 256), lr=3e-4, lmbda=0.05,
+                  seed=0, check_every=50, clip=1.0, log=None):
     """Adam on net.parameters() (+ the aux optimiser) with HSICTrainer.train_step until the training PSNR (from the
     step's own mse) reaches target_db.  Returns (steps, last psnr)."""
     h, w = size
@@ -49,7 +49,7 @@ def train_to_psnr(net, dev, *, target_db=25.0, max_steps=600, batch=2, size=(256
     psnr, hist = 0.0, []
     for step in range(1, max_steps + 1):
         x1, x2, Hm = smooth_pairs(batch, h, w, gen)
-        res = tr.train_step(x1.to(dev), x2.to(dev), Hm.to(dev), opt, aux)
+        res = tr.train_step(x1.to(dev), x2.to(dev), Hm.to(dev), opt, aux, clip_max_norm=clip)
         if not math.isfinite(res["loss"]):
             raise RuntimeError(f"training diverged at step {step}: {res}")
         hist.append(res["mse"] / 2)
@@ -95,7 +95,8 @@ def compare_with_oracle(net, dev, h, w, seed=9):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--lr", type=float, default=1e-3)
+    ap.add_argument("--lr", type=float, default=3e-4)
+    ap.add_argument("--clip", type=float, default=1.0)
     ap.add_argument("--lmbda", type=float, default=0.05)
     ap.add_argument("--target", type=float, default=99.0)
     ap.add_argument("--size", type=int, nargs=2, default=[256, 256])
@@ -107,7 +108,7 @@ def main():
     net = HSIC().to(dev)
     t0 = time.perf_counter()
     steps, psnr = train_to_psnr(net, dev, target_db=a.target, max_steps=a.steps, size=tuple(a.size), lr=a.lr,
-                                lmbda=a.lmbda, log=print)
+                                lmbda=a.lmbda, clip=a.clip, log=print)
     print(f"trained {steps} steps in {time.perf_counter() - t0:.1f} s, train psnr {psnr:.2f} dB (lr {a.lr}, lambda {a.lmbda})")
     print(compare_with_oracle(net, dev, *a.eval_size))
 
