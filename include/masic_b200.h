@@ -38,7 +38,7 @@ extern "C" {
 #define MASIC_EDRIVER (-3)  /* cuTensorMapEncodeTiled unavailable / failed  */
 
 /* ---------------------------------------------------------------- version */
-int masic_abi_version(void);                 /* bumps on any signature change (2: residual inputs, 3: grouped launches of MasicConvDesc, 4: pack batches, 5: cta_pairs, 6: MASIC_CONV_XFOLD8) */
+int masic_abi_version(void);                 /* bumps on any signature change (2: residual inputs, 3: grouped launches of MasicConvDesc, 4: pack batches, 5: cta_pairs, 6: MASIC_CONV_XFOLD8, 7: masic_rans_*, udh front-end entry points) */
 const char* masic_build_info(void);          /* "sm_100a nvcc 12.9 ..." */
 
 /* ------------------------------------------------------------------ convs */
@@ -261,6 +261,23 @@ int masic_rans_decoder_decode(MasicRansDecoder* dec, const int32_t* indexes_host
                               const int32_t* cdfs_host, int n_tables, int row_pitch, const int32_t* cdf_sizes_host,
                               const int32_t* offsets_host, int32_t* symbols_host);
 void masic_rans_decoder_destroy(MasicRansDecoder* dec);
+
+/* ---------------------------------------------------- udh homography front-end */
+/* nn.MaxPool2d(2, 2) of coremasic/mywork/model.py:66 on an NHWC bf16 activation (c_pitch % 8 == 0). */
+int masic_maxpool2_nhwc_bf16(const void* in, int n, int h, int w, int c_pitch, void* out, void* stream);
+/* nn.Linear weights (rows, c*hw) whose columns follow torch's Flatten of NCHW (model.py:83-87) -> bf16 (rows, hw*c):
+ * the column order of the NHWC activation the FC kernel reads. */
+int masic_fc_pack_weights(const float* weight, int rows, int c, int hw, void* dst_bf16, void* stream);
+/* nn.Linear (+ReLU) for batch <= 8 (model.py:87-90): out[b][r] = act(bias[r] + w[r] . x[b]); x, w bf16, fp32
+ * accumulation; out as fp32 and / or bf16.  HBM-bound on the weight matrix (read once per call). */
+int masic_fc_bf16(const void* x_bf16, int x_batch_stride, const void* w_bf16, const float* bias, int batch, int k,
+                  int rows, int relu, float* out_f32, void* out_bf16, int out_batch_stride, void* stream);
+/* test2_real.py:201-211 / model.py:103-111: corners (batch,4,2) and the net's delta (batch,4,2), fp32 ->
+ * h_matrix (batch,3,3) fp32 = h_adjust(img_h, img_w, pic_h, pic_w, inverse(get_perspective_transform(c', c' + delta)))
+ * with c' = c - c[0] when shift_corners (test2_real.py:203) else c (model.py get_h; img == pic makes h_adjust the
+ * identity).  8x8 solve and 3x3 inverse in fp64. */
+int masic_homography_from_delta(const float* corners, const float* delta, int batch, int shift_corners, int img_h,
+                                int img_w, int pic_h, int pic_w, float* h_out, void* stream);
 
 /* ------------------------------------------------------------ image domain */
 /* kornia.warp_perspective(src, M, (h_out, w_out)) — kornia 0.5.0, call sites MASIC.py:781,821,833.

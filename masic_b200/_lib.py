@@ -130,6 +130,10 @@ def _declare(lib: C.CDLL) -> None:
         "masic_rans_decoder_create": (i, [vp, i64, C.POINTER(vp)]),
         "masic_rans_decoder_decode": (i, [vp, vp, i64, vp, i, i, vp, vp, vp]),
         "masic_rans_decoder_destroy": (None, [vp]),
+        "masic_maxpool2_nhwc_bf16": (i, [vp, i, i, i, i, vp, vp]),
+        "masic_fc_pack_weights": (i, [vp, i, i, i, vp, vp]),
+        "masic_fc_bf16": (i, [vp, i, vp, vp, i, i, i, i, vp, vp, i, vp]),
+        "masic_homography_from_delta": (i, [vp, vp, i, i, i, i, i, i, vp, vp]),
         "masic_warp_prepare": (i, [vp, i, i, i, i, i, i, vp, vp]),
         "masic_warp_perspective_fwd": (i, [vp, i, i, i, i, i, i, vp, vp, vp, i, i, i, vp]),
         "masic_conv_small_nchw": (i, [vp, i, vp, i, i, i, i, vp, i, vp, i, i, i, i, i, vp, vp, f, vp, vp, i, i, i, vp]),

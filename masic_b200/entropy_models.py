@@ -23,6 +23,7 @@ import torch.nn.functional as F
 from torch import Tensor
 
 from . import ops
+from . import torch_ops  # noqa: F401  (registers torch.ops.masic_b200.*)
 from ._lib import MasicError
 from .layers import LowerBound
 
@@ -100,7 +101,9 @@ class EntropyModel(nn.Module):
             raise ValueError(f'Invalid quantization mode: "{mode}"')
         if mode == "noise":
             raise MasicError("quantisation mode 'noise' is training-only; masic_b200 implements inference")
-        return ops.quantize(inputs, means, mode)
+        if means is not None:
+            means = means.expand_as(inputs)
+        return torch.ops.masic_b200.quantize(inputs, means, mode == "symbols")
 
     @staticmethod
     def _dequantize(inputs: Tensor, means: Optional[Tensor] = None) -> Tensor:
@@ -320,8 +323,8 @@ class EntropyBottleneck(EntropyModel):
         """entropy_models.py:384-411 (eval): one fused kernel instead of ~60 ATen launches."""
         if self.training:
             raise MasicError("EntropyBottleneck: training mode (additive noise) is not on the sm_100a path")
-        z_hat, lik, _ = ops.eb_forward(x, list(self._matrices), list(self._biases), list(self._factors), self.quantiles)
-        return z_hat, lik
+        return torch.ops.masic_b200.eb_forward(x, list(self._matrices), list(self._biases), list(self._factors),
+                                               self.quantiles)
 
     @staticmethod
     def _build_indexes(size):
@@ -406,7 +409,7 @@ class _GaussianBase(EntropyModel):
 
     def build_indexes(self, scales: Tensor) -> Tensor:
         """entropy_models.py:556-562 — one kernel (binary search) instead of 63 compare+sub launches."""
-        return ops.gc_build_indexes(scales, self.scale_table, self._bound())
+        return torch.ops.masic_b200.gc_build_indexes(scales, self.scale_table, self._bound())
 
 
 class GaussianConditional(_GaussianBase):
@@ -427,7 +430,8 @@ class GaussianConditional(_GaussianBase):
         """entropy_models.py:546-554 (eval): quantise + likelihood (+floor) fused."""
         if self.training:
             raise MasicError("GaussianConditional: training mode is not on the sm_100a path")
-        y_hat, lik = ops.gc_likelihood(inputs, scales, means, self._bound())
+        y_hat, lik = torch.ops.masic_b200.gc_likelihood(inputs, scales, None if means is None else means.expand_as(inputs),
+                                                        self._bound())
         if not self.use_likelihood_bound:
             lik = self._likelihood(y_hat, scales, means)
         return y_hat, lik
@@ -450,8 +454,7 @@ class GaussianMixtureConditional_gf(_GaussianBase):
             raise MasicError("GaussianMixtureConditional_gf: training mode is not on the sm_100a path")
         if self.K != 5:
             raise MasicError("the fused mixture kernel is specialised for K = 5 (MASIC.py:653)")
-        return ops.gmm_likelihood(inputs, scales, means, weights, K=self.K, weights_are_logits=False,
-                                  scale_bound=self._bound())
+        return torch.ops.masic_b200.gmm_likelihood(inputs, scales, means, weights, self._bound())
 
 
 class GaussianMixtureConditional(GaussianMixtureConditional_gf):

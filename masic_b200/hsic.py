@@ -384,6 +384,42 @@ class PairStream:
         self._n += 1
         return self._n - 1
 
+    # ---- images + grey patches in, criterion out: the homography is estimated on the device
+    def attach_homography_net(self, net) -> None:
+        """`net`: a masic_b200.udh.Net (the udh homography model, test2_real.py:42-47) on this device.  Each slot gets
+        its own UDHEngine (static buffers + CUDA graph) writing h_matrix straight into the slot's codec engine."""
+        from .udh import UDHEngine
+        for s in self.slots:
+            s["udh"] = UDHEngine(net.state_dict(), 1, self.dev, net.patch_size)
+
+    def submit_patches(self, x1: torch.Tensor, x2: torch.Tensor, patch_a: torch.Tensor, patch_b: torch.Tensor,
+                       corners: torch.Tensor, criterion: bool = True, want_recon: bool = False) -> int:
+        """Like `submit`, but instead of h_matrix takes what the dataset hands over (datasets/utils.py:383-395): the two
+        (1,1,128,128) normalised grey patches and their (1,4,2) corner coordinates.  The udh net, the 4-point DLT,
+        the inverse and h_adjust (test2_real.py:201-211) run on the slot's stream ahead of the codec; the host never
+        sees the homography."""
+        s = self.slots[self._n % self.depth]
+        if "udh" not in s:
+            raise MasicError("submit_patches: call attach_homography_net(net) first")
+        if s["busy"]:
+            s["done"].synchronize()
+        u = s["udh"]
+        caller = torch.cuda.current_stream(self.dev)
+        self.copy_stream.wait_stream(caller)
+        with torch.cuda.stream(self.copy_stream):
+            u.ab[:, 0:1].copy_(patch_a.reshape(1, 1, u.P, u.P), non_blocking=True)
+            u.ab[:, 1:2].copy_(patch_b.reshape(1, 1, u.P, u.P), non_blocking=True)
+            u.corners.copy_(corners.reshape(1, 4, 2), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        with torch.cuda.stream(s["stream"]):
+            s["stream"].wait_event(ev)
+            h = u.run(img_hw=(self.H, self.W), corners=u.corners)["h"]
+            ev2 = torch.cuda.Event()
+            ev2.record(s["stream"])
+        self.copy_stream.wait_event(ev2)            # submit() copies h on the copy stream
+        return self.submit(x1, x2, h, criterion=criterion, want_recon=want_recon)
+
     def result(self, ticket: int):
         """(bpp, psnr1_db, psnr2_db, detail) of a submitted pair; blocks until its D2H copy has landed."""
         if not (self._n - self.depth <= ticket < self._n):

@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import torch
 
-from . import ops
+from . import torch_ops  # noqa: F401  (registers torch.ops.masic_b200.*)
 
 __version__ = "0.5.0-masic_b200"
 
@@ -16,9 +16,10 @@ def warp_perspective(src, M, dsize, mode="bilinear", padding_mode="zeros", align
                                   "align_corners=True")
     n, c, h, w = src.shape
     if c <= 8:
-        return ops.warp_perspective(src, M, tuple(dsize))
+        return torch.ops.masic_b200.warp_perspective(src, M, int(dsize[0]), int(dsize[1]))
     # wide feature maps (the CQE net warps 32-channel maps, MASIC.py:1479-1480): 8 channels per launch
-    outs = [ops.warp_perspective(src[:, i:i + 8].contiguous(), M, tuple(dsize)) for i in range(0, c, 8)]
+    outs = [torch.ops.masic_b200.warp_perspective(src[:, i:i + 8].contiguous(), M, int(dsize[0]), int(dsize[1]))
+            for i in range(0, c, 8)]
     return torch.cat(outs, dim=1)
 
 

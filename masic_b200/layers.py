@@ -79,78 +79,89 @@ def _to_nhwc_bf16(x: Tensor, pitch: int) -> Tensor:
     return out
 
 
-class _TCConvMixin:
-    """Module-granularity (unfused) execution of one conv on the tensor-core kernel: used when
-    the reference's own MASIC.py drives the layers one by one.  Plans are cached per input shape
-    and re-packed when the weights change."""
+_PLAN_CACHE: Dict[Any, Any] = {}      # (weight identity / version, input shape) -> bound plan; small LRU
+_PLAN_CACHE_MAX = 96
 
-    _plan_cache: Dict[Any, Any]
+
+def conv_forward(x: Tensor, weight: Tensor, bias: Optional[Tensor], stride: int, transposed: bool,
+                 tap_mask: int = 0) -> Tensor:
+    """One conv()/deconv()/MaskedConv2d on the tensor-core kernel, NCHW fp32 in and out: the implementation of
+    `torch.ops.masic_b200.conv2d`.  Module-granularity (unfused) execution, used when the reference's own MASIC.py
+    drives the layers one by one.  Plans (packed weights + bound staging buffers) are cached per (weight, bias, input
+    shape) and rebuilt when either tensor's version or storage changes."""
+    if not x.is_cuda:
+        raise MasicError("masic_b200 conv: CUDA tensors only (no CPU fallback)")
+    k = weight.shape[-1]
+    s = int(stride)
+    cin, cout = (weight.shape[0], weight.shape[1]) if transposed else (weight.shape[1], weight.shape[0])
+    if max(cin, cout) <= 8:               # tiny-channel layers: CUDA-core direct conv
+        if transposed and s != 1:
+            raise MasicError("tiny transposed conv with stride 2 is not on MASIC's path")
+        return ops.conv_small(x, None, weight, bias, ksize=k, stride=s, transposed_s1=transposed)
+    key = (tuple(x.shape), x.device, weight.data_ptr(), weight._version, s, bool(transposed), int(tap_mask),
+           None if bias is None else (bias.data_ptr(), bias._version))
+    ent = _PLAN_CACHE.get(key)
+    if ent is None:
+        if len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
+            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+        n, _, h, w = x.shape
+        cin_p = max(16, -(-cin // 16) * 16)
+        wt = weight.detach().float()
+        if cin_p != cin:
+            pad_shape = list(wt.shape)
+            pad_shape[0 if transposed else 1] = cin_p
+            wp = torch.zeros(pad_shape, device=wt.device)
+            if transposed:
+                wp[:cin] = wt
+            else:
+                wp[:, :cin] = wt
+            wt = wp
+        xin = torch.empty(n, h, w, cin_p, dtype=torch.bfloat16, device=x.device)
+        if transposed and s == 2:
+            if cout <= 8:
+                kind, n_tile = DECONV_S2_SUBPIX, 16
+            else:
+                kind, n_tile = DECONV_S2, (128 if cout % 128 == 0 else 192 if cout % 192 == 0 else 64)
+        else:
+            kind, n_tile = CONV, (128 if cout % 128 == 0 else 192 if cout % 192 == 0 else 64)
+        packed = PackedConv(kind=kind, ksize=k, c_in=cin_p, c_out=cout, n_tile=n_tile, weight=wt,
+                            transposed=transposed, bias=bias)
+        if kind == DECONV_S2:
+            ho, wo = 2 * h, 2 * w
+        elif kind == CONV and s == 2:
+            ho, wo = h // 2, w // 2
+        else:
+            ho, wo = h, w
+        out = torch.empty(n, ho, wo, packed.c_out_pad, dtype=torch.float32, device=x.device)
+        plan = ConvPlan(packed=packed, stride=s if kind == CONV else 1, tap_mask=tap_mask, x=xin, out=out)
+        ent = _PLAN_CACHE[key] = (plan, xin, out, kind, cin_p)
+    plan, xin, out, kind, cin_p = ent
+    n, c, h, w = x.shape
+    if c <= 8:
+        ops.nchw_to_nhwc_bf16(x, cin_p, out=xin)
+    else:
+        if cin_p != c:
+            xin.zero_()
+        xin[..., :c].copy_(x.permute(0, 2, 3, 1))
+    plan.launch()
+    if kind == DECONV_S2_SUBPIX:
+        from . import _lib
+        res = torch.empty(n, cout, 2 * h, 2 * w, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().masic_subpix_to_nchw(out.data_ptr(), n, h, w, out.shape[3], 0, None, None, 1e-6,
+                                                    res.data_ptr(), None, 0,
+                                                    torch.cuda.current_stream().cuda_stream),
+                   "masic_subpix_to_nchw")
+        return res
+    return ops.nhwc_to_nchw_f32(out, cout)
+
+
+class _TCConvMixin:
+    """nn.Conv2d / nn.ConvTranspose2d parameter containers whose forward is `torch.ops.masic_b200.conv2d`."""
 
     def _tc_forward(self, x: Tensor, *, transposed: bool, tap_mask: int = 0) -> Tensor:
         _require_inference(self, x)
-        k = self.kernel_size[0]
-        s = self.stride[0]
-        cin = self.in_channels
-        cout = self.out_channels
-        if max(cin, cout) <= 8:           # tiny-channel layers: CUDA-core direct conv
-            if transposed and s != 1:
-                raise MasicError("tiny transposed conv with stride 2 is not on MASIC's path")
-            return ops.conv_small(x, None, self.weight, self.bias, ksize=k, stride=s, transposed_s1=transposed)
-        key = (tuple(x.shape), x.device, self.weight._version, self.weight.data_ptr(),
-               None if self.bias is None else (self.bias._version, self.bias.data_ptr()))
-        cache = self.__dict__.setdefault("_plan_cache", {})
-        ent = cache.get(key)
-        if ent is None:
-            cache.clear()
-            n, _, h, w = x.shape
-            cin_p = max(16, -(-cin // 16) * 16)
-            wt = self.weight.detach().float()
-            if cin_p != cin:
-                pad_shape = list(wt.shape)
-                pad_shape[0 if transposed else 1] = cin_p
-                wp = torch.zeros(pad_shape, device=wt.device)
-                if transposed:
-                    wp[:cin] = wt
-                else:
-                    wp[:, :cin] = wt
-                wt = wp
-            xin = torch.empty(n, h, w, cin_p, dtype=torch.bfloat16, device=x.device)
-            if transposed and s == 2:
-                if cout <= 8:
-                    kind, n_tile = DECONV_S2_SUBPIX, 16
-                else:
-                    kind, n_tile = DECONV_S2, (128 if cout % 128 == 0 else 192 if cout % 192 == 0 else 64)
-            else:
-                kind, n_tile = CONV, (128 if cout % 128 == 0 else 192 if cout % 192 == 0 else 64)
-            packed = PackedConv(kind=kind, ksize=k, c_in=cin_p, c_out=cout, n_tile=n_tile, weight=wt,
-                                transposed=transposed, bias=self.bias)
-            if kind == DECONV_S2:
-                ho, wo = 2 * h, 2 * w
-            elif kind == CONV and s == 2:
-                ho, wo = h // 2, w // 2
-            else:
-                ho, wo = h, w
-            out = torch.empty(n, ho, wo, packed.c_out_pad, dtype=torch.float32, device=x.device)
-            plan = ConvPlan(packed=packed, stride=s if kind == CONV else 1, tap_mask=tap_mask, x=xin, out=out)
-            ent = cache[key] = (plan, xin, out, kind, cin_p)
-        plan, xin, out, kind, cin_p = ent
-        n, c, h, w = x.shape
-        if c <= 8:
-            ops.nchw_to_nhwc_bf16(x, cin_p, out=xin)
-        else:
-            if cin_p != c:
-                xin.zero_()
-            xin[..., :c].copy_(x.permute(0, 2, 3, 1))
-        plan.launch()
-        if kind == DECONV_S2_SUBPIX:
-            from . import _lib
-            res = torch.empty(n, cout, 2 * h, 2 * w, dtype=torch.float32, device=x.device)
-            _lib.check(_lib.load().masic_subpix_to_nchw(out.data_ptr(), n, h, w, out.shape[3], 0, None, None, 1e-6,
-                                                        res.data_ptr(), None, 0,
-                                                        torch.cuda.current_stream().cuda_stream),
-                       "masic_subpix_to_nchw")
-            return res
-        return ops.nhwc_to_nchw_f32(out, cout)
+        from . import torch_ops  # noqa: F401  (registers torch.ops.masic_b200.*)
+        return torch.ops.masic_b200.conv2d(x, self.weight, self.bias, self.stride[0], transposed, tap_mask)
 
 
 class Conv2d(_TCConvMixin, nn.Conv2d):
@@ -257,12 +268,5 @@ class GDN(nn.Module):
 
     def forward(self, x: Tensor) -> Tensor:
         _require_inference(self, x)
-        from . import _lib
-        n, c, h, w = x.shape
-        x = x.float().contiguous()
-        out = torch.empty_like(x)
-        _lib.check(_lib.load().masic_gdn_nchw(x.data_ptr(), n, c, h * w, self.beta.data_ptr(),
-                                              self.gamma.detach().contiguous().data_ptr(), float(self.beta_min),
-                                              int(self.inverse), out.data_ptr(),
-                                              torch.cuda.current_stream().cuda_stream), "masic_gdn_nchw")
-        return out
+        from . import torch_ops  # noqa: F401
+        return torch.ops.masic_b200.gdn(x, self.beta, self.gamma, self.inverse, self.beta_min)

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(lib):
     missing = [n for n in names if n not in exported]
     assert not missing, missing
     assert sorted(_lib.declared_symbols()) == names          # the ctypes binding covers the whole header
-    assert lib.masic_abi_version() == 6
+    assert lib.masic_abi_version() == 7
     assert b"sm_100a" in lib.masic_build_info()
 
 
@@ -85,3 +85,24 @@ def test_cuda_ops_refuse_cpu_tensors():
     with pytest.raises(_lib.MasicError):
         ops.gmm_likelihood(torch.zeros(1, 2, 2, 2), torch.zeros(1, 10, 2, 2), torch.zeros(1, 10, 2, 2),
                            torch.zeros(1, 10, 2, 2))
+
+
+def test_torch_library_custom_ops_are_registered_with_fake_impls():
+    """SURVEY §8(b) / north-star: "thin C-ABI torch custom-op extension" — every op is a torch.ops.masic_b200.* custom
+    op with a schema and a fake (meta) implementation; CPU tensors are refused (no fallback)."""
+    import torch
+    from masic_b200 import torch_ops
+    for name in torch_ops.OPS:
+        op = getattr(torch.ops.masic_b200, name)
+        assert op.default._schema.name == f"masic_b200::{name}"
+    m = lambda *s: torch.empty(*s, device="meta")   # noqa: E731
+    assert torch.ops.masic_b200.conv2d(m(2, 128, 64, 96), m(128, 128, 5, 5), m(128), 2, False, 0).shape == (2, 128, 32, 48)
+    assert torch.ops.masic_b200.conv2d(m(2, 128, 64, 96), m(128, 3, 5, 5), None, 2, True, 0).shape == (2, 3, 128, 192)
+    assert torch.ops.masic_b200.gdn(m(1, 128, 8, 8), m(128), m(128, 128), False, 1e-6).shape == (1, 128, 8, 8)
+    assert torch.ops.masic_b200.warp_perspective(m(1, 3, 64, 64), m(1, 3, 3), 32, 48).shape == (1, 3, 32, 48)
+    y_hat, lik = torch.ops.masic_b200.gmm_likelihood(m(1, 192, 4, 4), m(1, 960, 4, 4), m(1, 960, 4, 4), m(1, 960, 4, 4), 0.11)
+    assert y_hat.shape == lik.shape == (1, 192, 4, 4)
+    assert torch.ops.masic_b200.gc_build_indexes(m(1, 8, 4, 4), m(64), 0.11).dtype == torch.int32
+    assert torch.ops.masic_b200.quantize(m(1, 8, 4, 4), None, True).dtype == torch.int32
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.masic_b200.gdn(torch.zeros(1, 3, 4, 4), torch.ones(3), torch.eye(3), False, 1e-6)     # CPU: no kernel

@@ -308,3 +308,31 @@ def test_module_tree_forward_matches_engine_and_oracle(dev):
     assert abs(_psnr(mod["x2_hat"], x2) - _psnr(eng["x2_hat"], x2)) <= PSNR_ATOL
     assert torch.equal(mod["x1_mask_R"], eng["x1_mask_R"]) and torch.equal(mod["x1_mask_L"], eng["x1_mask_L"])
     assert rec["dbpp_rel"] <= BPP_RTOL
+
+
+def test_custom_ops_pass_opcheck_and_trace(dev):
+    """torch.library.opcheck (schema, fake-tensor and dispatch consistency) on the registered ops, and a
+    torch.export-style fake-tensor trace through a module that uses them."""
+    from masic_b200 import torch_ops  # noqa: F401
+    from masic_b200.layers import GDN, conv
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 16, 32, 48, generator=g).to(dev)
+    w = (torch.randn(32, 16, 3, 3, generator=g) * 0.1).to(dev)
+    b = torch.randn(32, generator=g).to(dev)
+    tests = ("test_schema", "test_faketensor")
+    torch.library.opcheck(torch.ops.masic_b200.conv2d.default, (x, w, b, 1, False, 0), test_utils=tests)
+    torch.library.opcheck(torch.ops.masic_b200.gdn.default, (x, torch.ones(16, device=dev), torch.eye(16, device=dev) * 0.3, False, 1e-6),
+                          test_utils=tests)
+    torch.library.opcheck(torch.ops.masic_b200.warp_perspective.default, (x[:, :3].contiguous(), torch.eye(3, device=dev)[None], 32, 48),
+                          test_utils=tests)
+    # the op computes what nn.Conv2d computes (bf16 operands)
+    want = torch.nn.functional.conv2d(x.bfloat16().float(), w.bfloat16().float(), b, padding=1)
+    got = torch.ops.masic_b200.conv2d(x, w, b, 1, False, 0)
+    assert torch.allclose(got, want, rtol=2e-2, atol=2e-2)
+    # fake-tensor tracing through modules built on the ops
+    mod = torch.nn.Sequential(conv(16, 128, kernel_size=5, stride=2), GDN(128)).to(dev).eval()
+    from torch.fx.experimental.proxy_tensor import make_fx
+    with torch.no_grad():
+        gm = make_fx(lambda t: mod(t), tracing_mode="fake")(x)
+    names = [str(n.target) for n in gm.graph.nodes if n.op == "call_function"]
+    assert any("masic_b200.conv2d" in n for n in names) and any("masic_b200.gdn" in n for n in names), names
