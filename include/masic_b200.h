@@ -32,13 +32,17 @@ extern "C" {
 
 #define MASIC_IMG_XOFF 2    /* first real pixel column of a padded image row (MASIC_CONV_XFOLD4 input) */
 #define MASIC_IMG_XPAD 8    /* extra columns per padded image row                                         */
+#define MASIC_FMT_BF16 0    /* 16-bit activation / operand formats: every entry point that reads or writes 16-bit     */
+#define MASIC_FMT_F16 1     /* NHWC buffers takes `int f16` = one of these (see csrc/cvt16.cuh for which and why)     */
+#define MASIC_FMT_SPLIT 2   /* or-ed in (image producers only): pixels of c <= 4 channels are written as [hi(c) | lo(c)], */
+                            /* lo = x - float(hi); MASIC_CONV_XFOLD8 weights repeat for channels c..2c-1 (g_a_conv1)      */
 #define MASIC_OK 0
 #define MASIC_EINVAL (-1)   /* bad argument (shape, alignment, enum)        */
 #define MASIC_ENOSUP (-2)   /* valid request this build does not implement  */
 #define MASIC_EDRIVER (-3)  /* cuTensorMapEncodeTiled unavailable / failed  */
 
 /* ---------------------------------------------------------------- version */
-int masic_abi_version(void);                 /* bumps on any signature change (2: residual inputs, 3: grouped launches of MasicConvDesc, 4: pack batches, 5: cta_pairs, 6: MASIC_CONV_XFOLD8, 7: masic_rans_*, udh front-end entry points) */
+int masic_abi_version(void);                 /* bumps on any signature change (2: residual inputs, 3: grouped launches of MasicConvDesc, 4: pack batches, 5: cta_pairs, 6: MASIC_CONV_XFOLD8, 7: masic_rans_*, udh front-end entry points, 8: `int f16` format selectors / MasicConvDesc.f16) */
 const char* masic_build_info(void);          /* "sm_100a nvcc 12.9 ..." */
 
 /* ------------------------------------------------------------------ convs */
@@ -108,6 +112,10 @@ typedef struct MasicConvDesc {
    * k-block and the pair issues M = 256 MMAs, which cuts the weight traffic per SM.  Pays off on the 128 -> 128 5x5
    * stride-2 layers and the wide 1x1 / 3x3 layers (-3..5 %), not on layers with few tiles or tiny K. */
   int cta_pairs;
+  /* 16-bit format of the input activations, the packed weights, gamma', the residuals and (unless out_fp32) the
+   * output: MASIC_FMT_BF16 (training step: gradients need fp32's exponent range) or MASIC_FMT_F16 (inference engines:
+   * 11 significant bits instead of 8, same tensor-core rate; conversions saturate at +-65504). */
+  int f16;
 } MasicConvDesc;
 
 typedef struct MasicConvPlan MasicConvPlan;   /* opaque: tensor maps + tile program */
@@ -132,7 +140,7 @@ int masic_conv_plan_trace(const MasicConvPlan* plan, long long* out_host);
  * dst must hold masic_packed_weight_bytes() bytes.                             */
 int64_t masic_packed_weight_bytes(int kind, int ksize, int c_in, int c_out_pad);
 int masic_pack_conv_weights(const float* w, int kind, int transposed, int ksize,
-                            int c_in, int c_out, int c_out_pad, void* dst, void* stream);
+                            int c_in, int c_out, int c_out_pad, void* dst, int f16, void* stream);
 /* All weight packs of a training step as ONE launch (after every optimizer.step() the kernels' bf16 copies of every
  * conv()/deconv() weight and the padded fp32 biases are refreshed: ~110 packs + ~50 bias copies per step).  A job is
  * one masic_pack_conv_weights() call plus, when bias_src != NULL, bias_dst[i] = bias_src[i % c_out] for
@@ -151,7 +159,7 @@ void masic_pack_batch_destroy(MasicPackBatch* batch);
  *   gamma' = max(gamma, 2^-18)^2 - 2^-36                                        */
 int masic_gdn_prepare(const float* beta, const float* gamma, int c, float beta_min,
                       float* beta_out, float* gamma_out_f32, void* gamma_out_bf16,
-                      void* stream);
+                      int f16, void* stream);
 
 /* Plain direct convolution on CUDA cores (test oracle on the device + the
  * small-channel layers).  Same NHWC-bf16 activations, fp32 torch-layout weights. */
@@ -159,7 +167,7 @@ int masic_conv_direct_nhwc(const void* in, int n, int h_in, int w_in, int in_cpi
                            int c_in, const float* w, int transposed, int ksize, int stride,
                            uint32_t tap_mask, const float* bias, int c_out,
                            float* out_f32, int out_cpitch, int out_coff, int round_w_bf16,
-                           void* stream);
+                           int f16, void* stream);
 
 
 /* --------------------------------------------------------- entropy models */
@@ -177,7 +185,7 @@ int masic_gmm_likelihood_fwd(const float* y, const float* sigma, const float* mu
                              int weights_are_logits, int in_nhwc, int n, int m, int k, int hw,
                              float scale_bound, float* y_hat, float* lik, int32_t* symbols, int out_nhwc,
                              void* yq_bf16, int bf_pitch, int bf_coff, const float* rowscale,
-                             int rs_stride, int rs_off, void* stream);
+                             int rs_stride, int rs_off, int f16, void* stream);
 
 /* GaussianConditional.forward + _quantize('symbols') (entropy_models.py:528-554, :112-125),
  * elementwise over `numel` contiguous values; means may be NULL. */
@@ -195,7 +203,7 @@ int masic_gc_build_indexes(const float* scales, int64_t numel, const float* scal
 int masic_eb_fwd(const float* z, int in_nhwc, int n, int c, int hw, const float* const* matrices,
                  const float* const* biases, const float* const* factors, const float* quantiles,
                  float* z_hat, float* lik, int32_t* symbols, int out_nhwc, void* zq_bf16, int bf_pitch,
-                 void* stream);
+                 int f16, void* stream);
 
 /* EntropyModel._quantize (entropy_models.py:98-125): dequantized = round(x-means)+means,
  * symbols = int32(round(x-means)); round half to even. */
@@ -206,7 +214,7 @@ int masic_quantize(const float* x, const float* means, int64_t numel, float* deq
  * MASIC.py:184-187, context_prediction :757, the mask-weighted y1_hat_warp term :827). */
 int masic_latent_prep(const float* y_nhwc, int64_t n_pixels, int c, void* y_abs_bf16, int abs_pitch,
                       void* y_round_bf16, int rnd_pitch, int rnd_coff, const float* rowscale,
-                      int rs_stride, int rs_off, void* stream);
+                      int rs_stride, int rs_off, int f16, void* stream);
 
 /* compressai._CXX.pmf_to_quantized_cdf (compressai/cpp_exts/ops/ops.cpp:40-109), HOST buffers.
  * Returns 1 / 2 for the reference's two std::domain_error cases. cdf_host holds n+1 values. */
@@ -264,14 +272,14 @@ void masic_rans_decoder_destroy(MasicRansDecoder* dec);
 
 /* ---------------------------------------------------- udh homography front-end */
 /* nn.MaxPool2d(2, 2) of coremasic/mywork/model.py:66 on an NHWC bf16 activation (c_pitch % 8 == 0). */
-int masic_maxpool2_nhwc_bf16(const void* in, int n, int h, int w, int c_pitch, void* out, void* stream);
+int masic_maxpool2_nhwc_bf16(const void* in, int n, int h, int w, int c_pitch, void* out, int f16, void* stream);
 /* nn.Linear weights (rows, c*hw) whose columns follow torch's Flatten of NCHW (model.py:83-87) -> bf16 (rows, hw*c):
  * the column order of the NHWC activation the FC kernel reads. */
-int masic_fc_pack_weights(const float* weight, int rows, int c, int hw, void* dst_bf16, void* stream);
+int masic_fc_pack_weights(const float* weight, int rows, int c, int hw, void* dst_bf16, int f16, void* stream);
 /* nn.Linear (+ReLU) for batch <= 8 (model.py:87-90): out[b][r] = act(bias[r] + w[r] . x[b]); x, w bf16, fp32
  * accumulation; out as fp32 and / or bf16.  HBM-bound on the weight matrix (read once per call). */
 int masic_fc_bf16(const void* x_bf16, int x_batch_stride, const void* w_bf16, const float* bias, int batch, int k,
-                  int rows, int relu, float* out_f32, void* out_bf16, int out_batch_stride, void* stream);
+                  int rows, int relu, float* out_f32, void* out_bf16, int out_batch_stride, int f16, void* stream);
 /* test2_real.py:201-211 / model.py:103-111: corners (batch,4,2) and the net's delta (batch,4,2), fp32 ->
  * h_matrix (batch,3,3) fp32 = h_adjust(img_h, img_w, pic_h, pic_w, inverse(get_perspective_transform(c', c' + delta)))
  * with c' = c - c[0] when shift_corners (test2_real.py:203) else c (model.py get_h; img == pic makes h_adjust the
@@ -290,7 +298,7 @@ int masic_warp_prepare(const float* m_3x3, int batch, int h, int w, int h_out, i
  * NHWC bf16 zero-padded to bf_pitch channels. */
 int masic_warp_perspective_fwd(const float* src, int n, int c, int h, int w, int h_out, int w_out,
                                const double* t_prepared, float* dst_nchw, void* dst_nhwc_bf16,
-                               int bf_pitch, int bf_row_pixels, int bf_xoff, void* stream);
+                               int bf_pitch, int bf_row_pixels, int bf_xoff, int f16, void* stream);
 
 /* Direct conv for the tiny-channel layers (c_in <= 8, c_out <= 8) on NCHW fp32:
  *   Encoder2.pre_conv+pre_gdn (MASIC.py:573-574): in0=x1_warp, in1=x2, k=5, s=1, gdn=FWD
@@ -301,14 +309,14 @@ int masic_conv_small_nchw(const float* in0, int c0, const float* in1, int c1, in
                           const float* weight, int transposed_s1, const float* bias, int c_out,
                           int ksize, int stride, int act, int gdn, const float* beta,
                           const float* gamma, float beta_min, float* out_nchw, void* out_nhwc_bf16,
-                          int bf_pitch, int bf_row_pixels, int bf_xoff, void* stream);
+                          int bf_pitch, int bf_row_pixels, int bf_xoff, int f16, void* stream);
 
 /* Output of a MASIC_DECONV_S2_SUBPIX plan ([N][H/2][W/2][pitch] fp32, channel = phase*3+co)
  * -> NCHW fp32 image (N,3,H,W), optionally through GDN/IGDN over the 3 channels
  * (Decoder2.after_gdn, MASIC.py:599,615), optionally also NHWC bf16. */
 int masic_subpix_to_nchw(const float* in_nhwc, int n, int h2, int w2, int pitch, int gdn,
                          const float* beta, const float* gamma, float beta_min, float* out_nchw,
-                         void* out_nhwc_bf16, int bf_pitch, void* stream);
+                         void* out_nhwc_bf16, int bf_pitch, int f16, void* stream);
 
 /* Stand-alone GDN.forward (compressai/layers/gdn.py:77-92) on NCHW fp32, c <= 256; beta/gamma are
  * the STORED (re-parametrised) parameters, the kernel applies parametrizers.py:61-64 itself. */
@@ -322,7 +330,7 @@ int masic_softmax_channels(const float* in_nchw, int n, int c, int hw, float* ou
  * masic_conv_small_nchw may have a padded row: pixel (y,x) goes to out[(y*row_pixels + x + xoff)*pitch];
  * row_pixels = 0 means a dense image (row_pixels = w, xoff = 0). */
 int masic_nchw_to_nhwc_bf16(const float* in_nchw, int n, int c, int h, int w, void* out, int pitch,
-                            int row_pixels, int xoff, void* stream);
+                            int row_pixels, int xoff, int f16, void* stream);
 int masic_nhwc_to_nchw_f32(const float* in_nhwc, int n, int c, int hw, int in_pitch, float* out_nchw,
                            void* stream);
 /* 8-bit image -> float32 in [0,1]: torchvision.transforms.ToTensor as the reference's datasets apply it
@@ -342,12 +350,12 @@ int masic_cqe_mask_weights(const float* mask_nchw1, int n, int h, int w, const f
 /* MASIC.py:1470-1471: out[p][0:3] = a[:,p]*w0[p], out[p][3:6] = b[:,p]*w1[p], out[p][6:16] = 0 (NHWC bf16, pitch 16);
  * a = the other view warped (NCHW fp32), b = this view's image. */
 int masic_cqe_blend_images(const float* a_nchw, const float* b_nchw, const float* weights_nchw2, int n, int h,
-                           int w, void* out_nhwc16_bf16, void* stream);
+                           int w, void* out_nhwc16_bf16, int f16, void* stream);
 /* MASIC.py:1479-1482: out[p][0:c] = self[p]*w1[p]; out[p][c:2c] = warp_perspective(other, M)[p]*w0[p] (bilinear,
  * zeros, align_corners=True; t_prepared from masic_warp_prepare with src = dst = (h, w)).  NHWC bf16, c % 8 == 0. */
 int masic_cqe_feature_fuse(const void* self_bf16, int self_pitch, const void* other_bf16, int other_pitch,
                            int c, const float* weights_nchw2, const double* t_prepared, int n, int h, int w,
-                           void* out_bf16, int out_pitch, void* stream);
+                           void* out_bf16, int out_pitch, int f16, void* stream);
 /* MASIC.py:1495-1496: out_nchw[b][c][p] = conv_out_nhwc[b][p][c] + identity_nchw[b][c][p], c < 3 (fp32). */
 int masic_cqe_residual_image(const float* conv_out_nhwc, int pitch, const float* identity_nchw, int n, int h,
                              int w, float* out_nchw, void* stream);

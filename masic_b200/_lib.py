@@ -16,6 +16,15 @@ ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 GDN_NONE, GDN_FWD, GDN_INV = 0, 1, 2
 IMG_XOFF, IMG_XPAD = 2, 8       # MASIC_IMG_XOFF / MASIC_IMG_XPAD
 CONV, DECONV_S2, DECONV_S2_SUBPIX, CONV_XFOLD4, CONV_XFOLD8 = 0, 1, 2, 3, 4
+# 16-bit activation / operand formats (MASIC_FMT_*, csrc/cvt16.cuh): the training step runs in bf16 (gradients need
+# fp32's exponent range), the inference engines in fp16 (8x finer rounding at the same tensor-core rate)
+FMT_BF16, FMT_F16 = 0, 1
+FMT_SPLIT = 2      # or-ed in by image producers: pixels of <= 4 channels as [hi | lo] (see include/masic_b200.h)
+
+
+def act_dtype(f16):
+    import torch
+    return torch.float16 if (f16 & 1) else torch.bfloat16
 
 _ERRORS = {-1: "MASIC_EINVAL (bad argument)", -2: "MASIC_ENOSUP (not implemented)",
            -3: "MASIC_EDRIVER (cuTensorMapEncodeTiled unavailable or failed)"}
@@ -40,7 +49,7 @@ class ConvDesc(C.Structure):
         ("residual0", C.c_void_p), ("res0_cpitch", C.c_int), ("res0_coff", C.c_int),
         ("residual1", C.c_void_p), ("res1_cpitch", C.c_int), ("res1_coff", C.c_int),
         ("nt_in_coff", C.POINTER(C.c_int)), ("nt_out_coff", C.POINTER(C.c_int)), ("nt_out_img", C.POINTER(C.c_int)),
-        ("out_images", C.c_int), ("cta_pairs", C.c_int),
+        ("out_images", C.c_int), ("cta_pairs", C.c_int), ("f16", C.c_int),
     ]
 
 
@@ -102,20 +111,20 @@ def _declare(lib: C.CDLL) -> None:
                                      C.POINTER(i), C.POINTER(i)]),
         "masic_conv_plan_trace": (i, [vp, vp]),
         "masic_packed_weight_bytes": (i64, [i, i, i, i]),
-        "masic_pack_conv_weights": (i, [vp, i, i, i, i, i, i, vp, vp]),
+        "masic_pack_conv_weights": (i, [vp, i, i, i, i, i, i, vp, i, vp]),
         "masic_pack_batch_create": (i, [C.POINTER(PackJob), i, C.POINTER(vp)]),
         "masic_pack_batch_launch": (i, [vp, vp]),
         "masic_pack_batch_destroy": (None, [vp]),
-        "masic_gdn_prepare": (i, [vp, vp, i, f, vp, vp, vp, vp]),
-        "masic_conv_direct_nhwc": (i, [vp, i, i, i, i, i, i, vp, i, i, i, u32, vp, i, vp, i, i, i, vp]),
+        "masic_gdn_prepare": (i, [vp, vp, i, f, vp, vp, vp, i, vp]),
+        "masic_conv_direct_nhwc": (i, [vp, i, i, i, i, i, i, vp, i, i, i, u32, vp, i, vp, i, i, i, i, vp]),
         "masic_gmm_likelihood_fwd": (i, [vp, vp, vp, vp, i, i, i, i, i, i, f, vp, vp, vp, i, vp, i, i,
-                                         vp, i, i, vp]),
+                                         vp, i, i, i, vp]),
         "masic_gc_likelihood_fwd": (i, [vp, vp, vp, i64, f, vp, vp, vp, vp]),
         "masic_gc_build_indexes": (i, [vp, i64, vp, i, f, vp, vp]),
         "masic_eb_fwd": (i, [vp, i, i, i, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp,
-                             i, vp, i, vp]),
+                             i, vp, i, i, vp]),
         "masic_quantize": (i, [vp, vp, i64, vp, vp, vp]),
-        "masic_latent_prep": (i, [vp, i64, i, vp, i, vp, i, i, vp, i, i, vp]),
+        "masic_latent_prep": (i, [vp, i64, i, vp, i, vp, i, i, vp, i, i, i, vp]),
         "masic_pmf_to_quantized_cdf": (i, [vp, i, i, vp]),
         "masic_pmf_table_to_cdf": (i, [vp, i, i, vp, vp, i, i, vp]),
         "masic_gmm_symbol_cdfs": (i, [vp, vp, vp, i, i, i, i64, vp, i, i, f, vp, vp, vp, vp]),
@@ -130,17 +139,17 @@ def _declare(lib: C.CDLL) -> None:
         "masic_rans_decoder_create": (i, [vp, i64, C.POINTER(vp)]),
         "masic_rans_decoder_decode": (i, [vp, vp, i64, vp, i, i, vp, vp, vp]),
         "masic_rans_decoder_destroy": (None, [vp]),
-        "masic_maxpool2_nhwc_bf16": (i, [vp, i, i, i, i, vp, vp]),
-        "masic_fc_pack_weights": (i, [vp, i, i, i, vp, vp]),
-        "masic_fc_bf16": (i, [vp, i, vp, vp, i, i, i, i, vp, vp, i, vp]),
+        "masic_maxpool2_nhwc_bf16": (i, [vp, i, i, i, i, vp, i, vp]),
+        "masic_fc_pack_weights": (i, [vp, i, i, i, vp, i, vp]),
+        "masic_fc_bf16": (i, [vp, i, vp, vp, i, i, i, i, vp, vp, i, i, vp]),
         "masic_homography_from_delta": (i, [vp, vp, i, i, i, i, i, i, vp, vp]),
         "masic_warp_prepare": (i, [vp, i, i, i, i, i, i, vp, vp]),
-        "masic_warp_perspective_fwd": (i, [vp, i, i, i, i, i, i, vp, vp, vp, i, i, i, vp]),
-        "masic_conv_small_nchw": (i, [vp, i, vp, i, i, i, i, vp, i, vp, i, i, i, i, i, vp, vp, f, vp, vp, i, i, i, vp]),
-        "masic_subpix_to_nchw": (i, [vp, i, i, i, i, i, vp, vp, f, vp, vp, i, vp]),
+        "masic_warp_perspective_fwd": (i, [vp, i, i, i, i, i, i, vp, vp, vp, i, i, i, i, vp]),
+        "masic_conv_small_nchw": (i, [vp, i, vp, i, i, i, i, vp, i, vp, i, i, i, i, i, vp, vp, f, vp, vp, i, i, i, i, vp]),
+        "masic_subpix_to_nchw": (i, [vp, i, i, i, i, i, vp, vp, f, vp, vp, i, i, vp]),
         "masic_gdn_nchw": (i, [vp, i, i, i, vp, vp, f, i, vp, vp]),
         "masic_softmax_channels": (i, [vp, i, i, i, vp, vp, vp]),
-        "masic_nchw_to_nhwc_bf16": (i, [vp, i, i, i, i, vp, i, i, i, vp]),
+        "masic_nchw_to_nhwc_bf16": (i, [vp, i, i, i, i, vp, i, i, i, i, vp]),
         "masic_u8_to_unit_f32": (i, [vp, i64, vp, vp]),
         "masic_nhwc_to_nchw_f32": (i, [vp, i, i, i, i, vp, vp]),
         "masic_wgrad_plan_create": (i, [C.POINTER(WgradDesc), C.POINTER(vp)]),
@@ -171,8 +180,8 @@ def _declare(lib: C.CDLL) -> None:
         "masic_softmax_channels_bwd": (i, [vp, vp, i, i, i, vp, vp]),
         "masic_colsum_nchw": (i, [vp, i, i, i64, vp, vp]),
         "masic_cqe_mask_weights": (i, [vp, i, i, i, C.POINTER(vp), C.POINTER(vp), i, vp, vp]),
-        "masic_cqe_blend_images": (i, [vp, vp, vp, i, i, i, vp, vp]),
-        "masic_cqe_feature_fuse": (i, [vp, i, vp, i, i, vp, vp, i, i, i, vp, i, vp]),
+        "masic_cqe_blend_images": (i, [vp, vp, vp, i, i, i, vp, i, vp]),
+        "masic_cqe_feature_fuse": (i, [vp, i, vp, i, i, vp, vp, i, i, i, vp, i, i, vp]),
         "masic_cqe_residual_image": (i, [vp, i, vp, i, i, i, vp, vp]),
         "masic_rd_metrics_scratch_bytes": (i64, []),
         "masic_rd_metrics": (i, [C.POINTER(vp), C.POINTER(i64), vp, vp, vp, vp, i, i, i, i, f, vp, vp, vp]),

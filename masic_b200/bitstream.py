@@ -37,7 +37,7 @@ import torch
 from . import _lib
 from ._lib import MasicError, check
 from .convplan import ACT_LEAKY, ACT_NONE, ACT_RELU, MASK_A_5x5, ConvPlan
-from .engine import SCALE_BOUND, HSICEngine
+from .engine import ACT, SCALE_BOUND, HSICEngine
 
 
 def _stream() -> int:
@@ -67,7 +67,7 @@ class _PixelModel:
         self.right = tag == "R"
         cin = 5 * M if self.right else 4 * M
         MK = M * K
-        bf, f32 = torch.bfloat16, torch.float32
+        bf, f32 = ACT, torch.float32
         z = lambda *s, dtype=bf: torch.zeros(*s, dtype=dtype, device=dev)   # noqa: E731
         self.crop = z(1, 5, 5, M)
         self.ctx_out = z(1, 5, 5, cin)
@@ -137,7 +137,7 @@ class _WaveModel:
         cin = 5 * M if self.right else 4 * M
         self.cin = cin
         MK = M * K
-        bf, f32 = torch.bfloat16, torch.float32
+        bf, f32 = ACT, torch.float32
         z = lambda *s, dtype=bf: torch.zeros(*s, dtype=dtype, device=dev)   # noqa: E731
         self.crop = z(n_max, 5, 5, M)
         self.ctx_out = z(n_max, 5, 5, cin)
@@ -263,7 +263,7 @@ def _decode_view(eng: HSICEngine, tag: str, dec, flag: np.ndarray, minmax: int) 
     h16, w16 = eng.H // 16, eng.W // 16
     pm = _PixelModel(eng, tag)
     gmm_in = eng.buf[f"{tag}.gmm_in"]
-    ypad = torch.zeros(1, h16 + 4, w16 + 4, M, dtype=torch.bfloat16, device=eng.dev)
+    ypad = torch.zeros(1, h16 + 4, w16 + 4, M, dtype=ACT, device=eng.dev)
     y_nhwc = torch.zeros(1, h16, w16, M, dtype=torch.float32, device=eng.dev)
     ch_np = np.flatnonzero(flag).astype(np.int32)
     n_ch = int(ch_np.size)
@@ -285,7 +285,7 @@ def _decode_view(eng: HSICEngine, tag: str, dec, flag: np.ndarray, minmax: int) 
                       "masic_range_decode_rows")
                 vals = torch.from_numpy(sym_h.astype(np.float32) - float(minmax)).to(eng.dev)
                 y_nhwc[0, h, w, ch_long] = vals
-                ypad[0, h + 2, w + 2, ch_long] = vals.to(torch.bfloat16)
+                ypad[0, h + 2, w + 2, ch_long] = vals.to(ACT)
     eng.buf[f"{tag}.y_rnd"].copy_(ypad[:, 2:-2, 2:-2, :])
     return y_nhwc.permute(0, 3, 1, 2).contiguous()
 
@@ -303,7 +303,7 @@ def _decode_view_wave(eng: HSICEngine, tag: str, dec, flag: np.ndarray, minmax: 
     if wm is None:
         wm = cache[tag] = _WaveModel(eng, tag, n_max)
     gmm_flat = eng.buf[f"{tag}.gmm_in"].view(h16 * w16, -1)
-    ypad = torch.zeros(1, h16 + 4, w16 + 4, M, dtype=torch.bfloat16, device=eng.dev)
+    ypad = torch.zeros(1, h16 + 4, w16 + 4, M, dtype=ACT, device=eng.dev)
     ypad_flat = ypad.view(-1, M)
     y_nhwc = torch.zeros(1, h16, w16, M, dtype=torch.float32, device=eng.dev)
     y_flat = y_nhwc.view(-1, M)
@@ -338,7 +338,7 @@ def _decode_view_wave(eng: HSICEngine, tag: str, dec, flag: np.ndarray, minmax: 
                   "masic_range_decode_rows")
             vals = (sym_h[:n * n_ch].to(eng.dev, non_blocking=True).float() - float(minmax)).view(n, n_ch)
             y_flat[pos[:, None], ch_long[None, :]] = vals
-            ypad_flat[pad[:, None], ch_long[None, :]] = vals.to(torch.bfloat16)
+            ypad_flat[pad[:, None], ch_long[None, :]] = vals.to(ACT)
     eng.buf[f"{tag}.y_rnd"].copy_(ypad[:, 2:-2, 2:-2, :])
     return y_nhwc.permute(0, 3, 1, 2).contiguous()
 

@@ -15,8 +15,8 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, CONV, CONV_XFOLD4, CONV_XFOLD8, DECONV_S2, DECONV_S2_SUBPIX, GDN_FWD,
-                   GDN_INV, GDN_NONE, ConvDesc, check)
+from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, CONV, CONV_XFOLD4, CONV_XFOLD8, DECONV_S2, DECONV_S2_SUBPIX, FMT_BF16,
+                   FMT_F16, GDN_FWD, GDN_INV, GDN_NONE, ConvDesc, act_dtype, check)
 
 # MaskedConv2d mask 'A' for a 5x5 kernel (layers.py:68-73): rows 0-1 and (2,0),(2,1)
 MASK_A_5x5 = sum(1 << (ky * 5 + kx) for ky in range(5) for kx in range(5)
@@ -32,28 +32,28 @@ def _stream() -> int:
 
 
 def pack_weights(w: torch.Tensor, kind: int, transposed: bool, ksize: int, c_in: int, c_out: int,
-                 c_out_pad: int) -> torch.Tensor:
-    """fp32 torch-layout weights -> bf16 [k-block][c_out_pad][64] (device)."""
+                 c_out_pad: int, f16: int = FMT_BF16) -> torch.Tensor:
+    """fp32 torch-layout weights -> 16-bit [k-block][c_out_pad][64] (device), bf16 or fp16."""
     lib = _lib.load()
     w = w.detach().to(torch.float32).contiguous()
     nbytes = lib.masic_packed_weight_bytes(kind, ksize, c_in, c_out_pad)
-    dst = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
+    dst = torch.empty(nbytes // 2, dtype=act_dtype(f16), device=w.device)
     check(lib.masic_pack_conv_weights(w.data_ptr(), kind, int(transposed), ksize, c_in, c_out,
-                                      c_out_pad, dst.data_ptr(), _stream()), "masic_pack_conv_weights")
+                                      c_out_pad, dst.data_ptr(), int(f16), _stream()), "masic_pack_conv_weights")
     return dst
 
 
-def gdn_prepare(beta: torch.Tensor, gamma: torch.Tensor, beta_min: float = 1e-6):
-    """Stored (re-parametrised) beta/gamma -> effective beta' (fp32), gamma' (fp32, bf16)."""
+def gdn_prepare(beta: torch.Tensor, gamma: torch.Tensor, beta_min: float = 1e-6, f16: int = FMT_BF16):
+    """Stored (re-parametrised) beta/gamma -> effective beta' (fp32), gamma' (fp32, and 16-bit in the given format)."""
     lib = _lib.load()
     c = beta.numel()
     beta = beta.detach().float().contiguous()
     gamma = gamma.detach().float().contiguous()
     b = torch.empty(c, dtype=torch.float32, device=beta.device)
     g32 = torch.empty(c, c, dtype=torch.float32, device=beta.device)
-    g16 = torch.empty(c, c, dtype=torch.bfloat16, device=beta.device)
+    g16 = torch.empty(c, c, dtype=act_dtype(f16), device=beta.device)
     check(lib.masic_gdn_prepare(beta.data_ptr(), gamma.data_ptr(), c, float(beta_min), b.data_ptr(),
-                                g32.data_ptr(), g16.data_ptr(), _stream()), "masic_gdn_prepare")
+                                g32.data_ptr(), g16.data_ptr(), int(f16), _stream()), "masic_gdn_prepare")
     return b, g32, g16
 
 
@@ -65,14 +65,15 @@ class PackedConv:
     def __init__(self, *, kind: int = CONV, ksize: int, c_in: int, c_out: int, n_tile: int,
                  weight: torch.Tensor, transposed: bool = False, bias: Optional[torch.Tensor] = None,
                  c_out_pad: Optional[int] = None, gdn: int = GDN_NONE,
-                 gdn_beta: Optional[torch.Tensor] = None, gdn_gamma: Optional[torch.Tensor] = None):
+                 gdn_beta: Optional[torch.Tensor] = None, gdn_gamma: Optional[torch.Tensor] = None,
+                 f16: int = FMT_BF16):
         self.kind, self.ksize, self.c_in, self.c_out, self.n_tile = kind, ksize, c_in, c_out, n_tile
-        self.transposed, self.gdn = transposed, gdn
+        self.transposed, self.gdn, self.f16 = transposed, gdn, int(f16)
         self.eff_out = 4 * c_out if kind == DECONV_S2_SUBPIX else c_out
         self.c_out_pad = c_out_pad if c_out_pad is not None else -(-self.eff_out // n_tile) * n_tile
         dev = weight.device
         pack_cin = weight.shape[1] if kind in (CONV_XFOLD4, CONV_XFOLD8) else c_in     # XFOLD: real channels of w
-        self.w_packed = pack_weights(weight, kind, transposed, ksize, pack_cin, c_out, self.c_out_pad)
+        self.w_packed = pack_weights(weight, kind, transposed, ksize, pack_cin, c_out, self.c_out_pad, self.f16)
         self.bias = None
         if bias is not None:
             b = torch.zeros(self.c_out_pad, dtype=torch.float32, device=dev)
@@ -83,7 +84,7 @@ class PackedConv:
             self.bias = b
         self.beta = self.gamma16 = None
         if gdn != GDN_NONE:
-            self.beta, _, self.gamma16 = gdn_prepare(gdn_beta, gdn_gamma)
+            self.beta, _, self.gamma16 = gdn_prepare(gdn_beta, gdn_gamma, f16=self.f16)
 
     def repack(self, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> None:
         """Re-pack changed weights IN PLACE (same device buffers, so bound plans stay valid): the training step
@@ -94,7 +95,7 @@ class PackedConv:
             w = w.float().contiguous()
         pack_cin = w.shape[1] if self.kind in (CONV_XFOLD4, CONV_XFOLD8) else self.c_in
         check(lib.masic_pack_conv_weights(w.data_ptr(), self.kind, int(self.transposed), self.ksize, pack_cin,
-                                          self.c_out, self.c_out_pad, self.w_packed.data_ptr(), _stream()),
+                                          self.c_out, self.c_out_pad, self.w_packed.data_ptr(), self.f16, _stream()),
               "masic_pack_conv_weights")
         self._keep = w
         if bias is not None and self.bias is not None:
@@ -114,6 +115,7 @@ class PackBatch:
         self._keep = []
         for a, (pk, w, b) in zip(arr, jobs):
             assert w.dtype == torch.float32 and w.is_contiguous() and w.is_cuda, "PackBatch needs fp32 contiguous weights"
+            assert pk.f16 == FMT_BF16, "PackBatch re-packs bf16 weights (the training step's format)"
             a.w, a.dst = w.data_ptr(), pk.w_packed.data_ptr()
             if b is not None and pk.bias is not None:
                 assert b.dtype == torch.float32 and b.is_contiguous()
@@ -154,14 +156,17 @@ class ConvPlan:
                  nt_in_coff: Optional[Sequence[int]] = None, nt_out_coff: Optional[Sequence[int]] = None,
                  nt_out_img: Optional[Sequence[int]] = None, cta_pairs: bool = False):
         lib = _lib.load()
-        assert x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous()
+        assert x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and x.dim() == 4 and x.is_contiguous()
         assert out.is_cuda and out.dim() == 4 and out.is_contiguous()
-        assert out.dtype in (torch.bfloat16, torch.float32)
-        if packed is None:
+        if packed is None:      # the format follows the input buffer
             packed = PackedConv(kind=kind, ksize=ksize, c_in=c_in, c_out=c_out, n_tile=n_tile, weight=weight,
                                 transposed=transposed, bias=bias, c_out_pad=c_out_pad, gdn=gdn,
-                                gdn_beta=gdn_beta, gdn_gamma=gdn_gamma)
+                                gdn_beta=gdn_beta, gdn_gamma=gdn_gamma,
+                                f16=FMT_F16 if x.dtype == torch.float16 else FMT_BF16)
         self.packed = packed
+        fmt = act_dtype(packed.f16)
+        assert x.dtype == fmt, f"input buffer is {x.dtype}, the packed weights are {fmt}"
+        assert out.dtype in (fmt, torch.float32), f"output buffer is {out.dtype}, expected {fmt} or float32"
         n, h_in, w_in, in_cp = x.shape
         if packed.kind in (CONV_XFOLD4, CONV_XFOLD8):          # padded image rows: [N][H][W + IMG_XPAD][16 or 8]
             w_in -= _lib.IMG_XPAD
@@ -189,7 +194,7 @@ class ConvPlan:
             d.rowscale, d.rs_stride, d.rs_off = rowscale.data_ptr(), rowscale.shape[3], rs_off
         for i, (r, off) in enumerate(((residual0, res0_coff), (residual1, res1_coff))):
             if r is not None:
-                assert r.is_cuda and r.dtype == torch.bfloat16 and r.dim() == 4 and r.is_contiguous()
+                assert r.is_cuda and r.dtype == fmt and r.dim() == 4 and r.is_contiguous()
                 assert r.shape[:3] == out.shape[:3], (r.shape, out.shape)
                 setattr(d, f"residual{i}", r.data_ptr())
                 setattr(d, f"res{i}_cpitch", r.shape[3])
@@ -210,6 +215,7 @@ class ConvPlan:
         else:
             assert out.shape[0] == n, (out.shape, n)
         d.cta_pairs = int(cta_pairs)
+        d.f16 = packed.f16
         self._desc = d
         handle = C.c_void_p()
         check(lib.masic_conv_plan_create(C.byref(d), C.byref(handle)), "masic_conv_plan_create")
@@ -296,6 +302,6 @@ def conv_direct(x: torch.Tensor, c_in: int, weight: torch.Tensor, *, transposed:
     bt = None if bias is None else bias.detach().float().contiguous()
     check(lib.masic_conv_direct_nhwc(x.data_ptr(), n, h, w, cp, in_coff, c_in, wt.data_ptr(),
                                      int(transposed), ksize, stride, tap_mask, _ptr(bt), c_out,
-                                     out.data_ptr(), c_out, 0, int(round_w_bf16), _stream()),
+                                     out.data_ptr(), c_out, 0, int(round_w_bf16), int(x.dtype == torch.float16), _stream()),
           "masic_conv_direct_nhwc")
     return out

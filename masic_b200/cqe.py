@@ -25,6 +25,9 @@ from .convplan import ACT_LEAKY, ACT_NONE, ACT_RELU, CONV, ConvPlan, PackedConv
 from .engine import HSICEngine
 from .layers import ResidualBlock, conv, conv3x3
 
+F16 = _lib.FMT_F16              # inference runs on fp16 operands / activations (csrc/cvt16.cuh)
+ACT = _lib.act_dtype(F16)
+
 
 class Enhancement_Block(nn.Module):
     """MASIC.py:149-164 — three ResidualBlocks and a skip over all of them."""
@@ -132,7 +135,7 @@ class CQEEngine(HSICEngine):
             wp[:, :real_cin] = w
             w = wp
         return PackedConv(kind=CONV, ksize=3, c_in=c_in, c_out=c_out, n_tile=n_tile, weight=w,
-                          bias=self._w(prefix + ".bias"))
+                          bias=self._w(prefix + ".bias"), f16=F16)
 
     def _c3(self, name, packed, x, out, *, out_coff=0, act=ACT_NONE, res0=None, res1=None, res1_coff=0):
         plan = ConvPlan(packed=packed, stride=1, x=x, out=out, out_coff=out_coff, act=act, residual0=res0,
@@ -174,7 +177,7 @@ class CQEEngine(HSICEngine):
         def warp(tag, src, Tm, dst, channels):
             self._add(tag, lambda: check(lib.masic_warp_perspective_fwd(
                 None if src is None else src.data_ptr(), B, channels, H, W, H, W, Tm.data_ptr(), dst.data_ptr(), None, 0, 0,
-                0, self._s()), "masic_warp_perspective_fwd"))
+                0, F16, self._s()), "masic_warp_perspective_fwd"))
 
         # masks (MASIC.py:1458 -> :627-649) and the per-pixel blend weights (:1459-1460)
         mask_r = self._buf(B, 1, H, W, dtype=f32)
@@ -210,12 +213,12 @@ class CQEEngine(HSICEngine):
         for v, eb, x_self, x_other_w, wt, _, _ in views:
             xbf = self._buf(B, H, W, 16)
             self._add(f"{v}.pack_nhwc", (lambda x_self=x_self, xbf=xbf: check(lib.masic_nchw_to_nhwc_bf16(
-                x_self.data_ptr(), B, 3, H, W, xbf.data_ptr(), 16, 0, 0, self._s()), "masic_nchw_to_nhwc_bf16")))
+                x_self.data_ptr(), B, 3, H, W, xbf.data_ptr(), 16, 0, 0, F16, self._s()), "masic_nchw_to_nhwc_bf16")))
             cat96[v] = self._buf(B, H, W, 96)                 # [EB2 output | conv0(x)]  (:1486-1487)
             self._c3(f"{v}.conv0", p_conv0, xbf, cat96[v], out_coff=64)                      # :1467-1468
             blend = self._buf(B, H, W, 16)
             self._add(f"{v}.blend_images", (lambda a=x_other_w, b=x_self, wt=wt, blend=blend: check(
-                lib.masic_cqe_blend_images(a.data_ptr(), b.data_ptr(), wt.data_ptr(), B, H, W, blend.data_ptr(), self._s()),
+                lib.masic_cqe_blend_images(a.data_ptr(), b.data_ptr(), wt.data_ptr(), B, H, W, blend.data_ptr(), F16, self._s()),
                 "masic_cqe_blend_images")))                                                 # :1470-1471
             f1 = self._buf(B, H, W, 32)
             self._c3(f"{v}.conv1", p_conv1, blend, f1)                                       # :1473-1474
@@ -226,7 +229,7 @@ class CQEEngine(HSICEngine):
             fused = self._buf(B, H, W, 64)
             self._add(f"{v}.feature_fuse", (lambda s=e1[v], ot=e1[other], wt=wt, Tm=Tm, fused=fused: check(
                 lib.masic_cqe_feature_fuse(s.data_ptr(), 32, ot.data_ptr(), 32, 32, wt.data_ptr(), Tm.data_ptr(), B, H, W,
-                                           fused.data_ptr(), 64, self._s()), "masic_cqe_feature_fuse")))   # :1479-1482
+                                           fused.data_ptr(), 64, F16, self._s()), "masic_cqe_feature_fuse")))   # :1479-1482
             self._enh_block(f"{v}.EB2", f"{eb}2", 64, fused, cat96[v], out_coff=0)           # :1483-1484
             e3 = self._buf(B, H, W, 96)
             self._enh_block(f"{v}.EB3", f"{eb}3", 96, cat96[v], e3)                          # :1488-1489

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/masic_b200.h"
+#include "cvt16.cuh"
 
 namespace {
 
@@ -46,8 +47,11 @@ __device__ __forceinline__ float pack_weight_value(const float* __restrict__ w, 
       // k-block = ky; column = pixel * 8 + channel of the 8-pixel window that starts at input pixel 2*ox - 2, so
       // pixel j is tap kx = j (j < 5); `c_in` is the REAL channel count of w (<= 8)
       const int ky = kb, kx = c >> 3, ch = c & 7;
-      if (co < c_out && ch < c_in && kx < 5)
-        v = w[((static_cast<long>(co) * c_in + ch) * 5 + ky) * 5 + kx];
+      // channels c_in .. 2*c_in-1 repeat the weights: a producer may store the pixel as [hi | lo] (MASIC_FMT_SPLIT),
+      // and hi * w + lo * w = x * w; without the split those slots hold zeros
+      const int chr = (ch >= c_in && 2 * c_in <= 8) ? ch - c_in : ch;
+      if (co < c_out && chr < c_in && kx < 5)
+        v = w[((static_cast<long>(co) * c_in + chr) * 5 + ky) * 5 + kx];
     } else if (co < c_out) {
       int ky = tap / k, kx = tap % k;
       if (transposed) {
@@ -63,10 +67,10 @@ __device__ __forceinline__ float pack_weight_value(const float* __restrict__ w, 
 
 __global__ void pack_weights_kernel(const float* __restrict__ w, int kind, int transposed, int k,
                                     int c_in, int c_out, int c_out_pad, int ncb, long total,
-                                    __nv_bfloat16* __restrict__ dst) {
+                                    uint16_t* __restrict__ dst, int f16) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= total) return;
-  dst[i] = __float2bfloat16_rn(pack_weight_value(w, kind, transposed, k, c_in, c_out, c_out_pad, ncb, i));
+  dst[i] = masic::pack16(pack_weight_value(w, kind, transposed, k, c_in, c_out, c_out_pad, ncb, i), f16);
 }
 
 // Every weight pack (and padded bias copy) of a training step in ONE launch: block b belongs to the job j with
@@ -102,7 +106,7 @@ pack_batch_kernel(const PackJobDev* __restrict__ jobs, const int* __restrict__ f
 __global__ void gdn_prepare_kernel(const float* __restrict__ beta, const float* __restrict__ gamma,
                                    int c, float beta_bound, float gamma_bound, float pedestal,
                                    float* __restrict__ beta_out, float* __restrict__ gamma_f32,
-                                   __nv_bfloat16* __restrict__ gamma_bf16) {
+                                   uint16_t* __restrict__ gamma_bf16, int f16) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < c) {
     const float b = fmaxf(beta[i], beta_bound);
@@ -112,11 +116,11 @@ __global__ void gdn_prepare_kernel(const float* __restrict__ beta, const float* 
     const float g = fmaxf(gamma[i], gamma_bound);
     const float gp = g * g - pedestal;
     if (gamma_f32) gamma_f32[i] = gp;
-    if (gamma_bf16) gamma_bf16[i] = __float2bfloat16_rn(gp);
+    if (gamma_bf16) gamma_bf16[i] = masic::pack16(gp, f16);
   }
 }
 
-__global__ void conv_direct_kernel(const __nv_bfloat16* __restrict__ in, int n, int h_in, int w_in,
+__global__ void conv_direct_kernel(const uint16_t* __restrict__ in, int f16, int n, int h_in, int w_in,
                                    int in_cpitch, int in_coff, int c_in,
                                    const float* __restrict__ w, int transposed, int k, int stride,
                                    uint32_t tap_mask, const float* __restrict__ bias, int c_out,
@@ -145,12 +149,12 @@ __global__ void conv_direct_kernel(const __nv_bfloat16* __restrict__ in, int n, 
         iy = ty / stride; ix = tx / stride;
       }
       if (iy < 0 || iy >= h_in || ix < 0 || ix >= w_in) continue;
-      const __nv_bfloat16* ip = in + ((static_cast<long>(ni) * h_in + iy) * w_in + ix) * in_cpitch + in_coff;
+      const uint16_t* ip = in + ((static_cast<long>(ni) * h_in + iy) * w_in + ix) * in_cpitch + in_coff;
       for (int ci = 0; ci < c_in; ++ci) {
         float wv = transposed ? w[((static_cast<long>(ci) * c_out + co) * k + ky) * k + kx]
                               : w[((static_cast<long>(co) * c_in + ci) * k + ky) * k + kx];
-        if (round_w) wv = __bfloat162float(__float2bfloat16_rn(wv));
-        acc = fmaf(__bfloat162float(ip[ci]), wv, acc);
+        if (round_w) wv = masic::unpack16(masic::pack16(wv, f16), f16);
+        acc = fmaf(masic::unpack16(ip[ci], f16), wv, acc);
       }
     }
   out[((static_cast<long>(ni) * h_out + oy) * w_out + ox) * out_cpitch + out_coff + co] = acc;
@@ -167,7 +171,7 @@ extern "C" int64_t masic_packed_weight_bytes(int kind, int ksize, int c_in, int 
 }
 
 extern "C" int masic_pack_conv_weights(const float* w, int kind, int transposed, int ksize, int c_in,
-                                       int c_out, int c_out_pad, void* dst, void* stream) {
+                                       int c_out, int c_out_pad, void* dst, int f16, void* stream) {
   if (!w || !dst || c_in <= 0 || c_out <= 0) return MASIC_EINVAL;
   if (kind == MASIC_DECONV_S2_SUBPIX) {
     if (ksize != 5 || 4 * c_out > c_out_pad) return MASIC_EINVAL;
@@ -180,13 +184,13 @@ extern "C" int masic_pack_conv_weights(const float* w, int kind, int transposed,
   const long total = masic_packed_weight_bytes(kind, ksize, c_in, c_out_pad) / 2;
   const int bs = 256;
   pack_weights_kernel<<<(unsigned)((total + bs - 1) / bs), bs, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, kind, transposed, ksize, c_in, c_out, c_out_pad, ncb, total, static_cast<__nv_bfloat16*>(dst));
+      w, kind, transposed, ksize, c_in, c_out, c_out_pad, ncb, total, static_cast<uint16_t*>(dst), f16);
   return (int)cudaGetLastError();
 }
 
 extern "C" int masic_gdn_prepare(const float* beta, const float* gamma, int c, float beta_min,
                                  float* beta_out, float* gamma_out_f32, void* gamma_out_bf16,
-                                 void* stream) {
+                                 int f16, void* stream) {
   if (!beta || !gamma || !beta_out || c <= 0) return MASIC_EINVAL;
   // compressai/ops/parametrizers.py:49-64 — pedestal = (2^-18)^2, bound = sqrt(minimum + pedestal)
   const float pedestal = 1.4551915228366852e-11f;          // 2^-36
@@ -195,7 +199,7 @@ extern "C" int masic_gdn_prepare(const float* beta, const float* gamma, int c, f
   const int bs = 256, total = c * c;
   gdn_prepare_kernel<<<(total + bs - 1) / bs, bs, 0, static_cast<cudaStream_t>(stream)>>>(
       beta, gamma, c, beta_bound, gamma_bound, pedestal, beta_out, gamma_out_f32,
-      static_cast<__nv_bfloat16*>(gamma_out_bf16));
+      static_cast<uint16_t*>(gamma_out_bf16), f16);
   return (int)cudaGetLastError();
 }
 
@@ -203,7 +207,7 @@ extern "C" int masic_conv_direct_nhwc(const void* in, int n, int h_in, int w_in,
                                       int in_coff, int c_in, const float* w, int transposed, int ksize,
                                       int stride, uint32_t tap_mask, const float* bias, int c_out,
                                       float* out_f32, int out_cpitch, int out_coff, int round_w_bf16,
-                                      void* stream) {
+                                      int f16, void* stream) {
   if (!in || !w || !out_f32 || (stride != 1 && stride != 2)) return MASIC_EINVAL;
   int h_out, w_out;
   if (!transposed) { h_out = (h_in + stride - 1) / stride; w_out = (w_in + stride - 1) / stride; }
@@ -211,7 +215,7 @@ extern "C" int masic_conv_direct_nhwc(const void* in, int n, int h_in, int w_in,
   const long total = (long)n * h_out * w_out * c_out;
   const int bs = 128;
   conv_direct_kernel<<<(unsigned)((total + bs - 1) / bs), bs, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(in), n, h_in, w_in, in_cpitch, in_coff, c_in, w, transposed,
+      static_cast<const uint16_t*>(in), f16, n, h_in, w_in, in_cpitch, in_coff, c_in, w, transposed,
       ksize, stride, tap_mask, bias, c_out, h_out, w_out, out_f32, out_cpitch, out_coff, round_w_bf16);
   return (int)cudaGetLastError();
 }

@@ -39,6 +39,7 @@
 #include <vector>
 
 #include "../../include/masic_b200.h"
+#include "cvt16.cuh"
 #include "ptx.cuh"
 
 namespace masic {
@@ -104,6 +105,7 @@ struct KParams {
   int nt_out_c[32];                // output channel position (default nt * n_tile)
   int nt_out_img[32];              // and output image offset
   uint32_t idesc;
+  int f16;         // 16-bit operand / activation format: 0 = bf16, 1 = fp16 (cvt16.cuh)
   int debug;       // timing experiments only (results are garbage): bit0 skip A loads, bit1 skip B loads, bit2 skip stores,
                    // bit3 skip the GDN norm MMA, bit4 skip the whole epilogue
 };
@@ -167,12 +169,10 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
-__device__ __forceinline__ uint32_t pack_bf16x2_p(uint64_t v) {   // bf16x2 {lo, hi} of a packed fp32 pair
+__device__ __forceinline__ uint32_t pack16x2_p(uint64_t v, int f16) {   // 16-bit pair {lo, hi} of a packed fp32 pair
   float lo, hi;
   upk2(v, lo, hi);
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
+  return pack16x2(lo, hi, f16);
 }
 __device__ __forceinline__ float rsqrt_approx(float x) {           // one MUFU.RSQ (rsqrtf() adds a denormal fix-up path)
   float r;
@@ -262,6 +262,7 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
   // depend on blockIdx and kernel parameters) on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  const int f16 = p.f16;
   // this CTA's (CTA pair's) contiguous, balanced range of tiles
   const int rank = CG2 ? static_cast<int>(cluster_ctarank()) : 0;
   const int unit = CG2 ? blockIdx.x >> 1 : blockIdx.x, n_units = CG2 ? gridDim.x >> 1 : gridDim.x;
@@ -550,9 +551,9 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {
             const uint64_t* xx = &x2[4 * c8];
-            st_shared_v4(arow + (((4 * half + c8) ^ (t & 7)) << 4), pack_bf16x2_p(mul2(xx[0], xx[0])),
-                         pack_bf16x2_p(mul2(xx[1], xx[1])), pack_bf16x2_p(mul2(xx[2], xx[2])),
-                         pack_bf16x2_p(mul2(xx[3], xx[3])));
+            st_shared_v4(arow + (((4 * half + c8) ^ (t & 7)) << 4), pack16x2_p(mul2(xx[0], xx[0]), f16),
+                         pack16x2_p(mul2(xx[1], xx[1]), f16), pack16x2_p(mul2(xx[2], xx[2]), f16),
+                         pack16x2_p(mul2(xx[3], xx[3]), f16));
           }
           fence_proxy_async_smem();
           tc_fence_before();
@@ -615,8 +616,8 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {
             const uint64_t* xx = &x2[4 * c8];
-            st_shared_v4(arow + (((4 * half + c8) ^ (t & 7)) << 4), pack_bf16x2_p(xx[0]), pack_bf16x2_p(xx[1]),
-                         pack_bf16x2_p(xx[2]), pack_bf16x2_p(xx[3]));
+            st_shared_v4(arow + (((4 * half + c8) ^ (t & 7)) << 4), pack16x2_p(xx[0], f16), pack16x2_p(xx[1], f16),
+                         pack16x2_p(xx[2], f16), pack16x2_p(xx[3], f16));
           }
           fence_proxy_async_smem();
           named_bar_sync(pbar, 256);
@@ -718,7 +719,7 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
                   const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
                   for (int e = 0; e < 8; ++e) {
-                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+                    const float2 f = unpack16x2(w[e], f16);
                     o2[e] = add2(o2[e], pk2(f.x, f.y));
                   }
                 }
@@ -736,8 +737,8 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
                 const int ch16 = 2 * (k0 + kk);        // 16 bf16 = two 16-B chunks
 #pragma unroll
                 for (int e = 0; e < 2; ++e)
-                  st_shared_v4(row + (((ch16 + e) ^ sw) << 4), pack_bf16x2_p(o2[4 * e]), pack_bf16x2_p(o2[4 * e + 1]),
-                               pack_bf16x2_p(o2[4 * e + 2]), pack_bf16x2_p(o2[4 * e + 3]));
+                  st_shared_v4(row + (((ch16 + e) ^ sw) << 4), pack16x2_p(o2[4 * e], f16), pack16x2_p(o2[4 * e + 1], f16),
+                               pack16x2_p(o2[4 * e + 2], f16), pack16x2_p(o2[4 * e + 3], f16));
               }
             }
           }
@@ -1067,6 +1068,8 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   { const char* e = getenv("MASIC_CONV_CG2"); kp.cg2 = e ? (atoi(e) != 0) : (d.cta_pairs != 0); }   // env overrides the plan
   { const char* e = getenv("MASIC_CONV_PDL"); kp.pdl = e ? (atoi(e) != 0) : 0; }
   kp.idesc = kp.cg2 ? umma_idesc_bf16_m256(d.n_tile) : umma_idesc_bf16(d.n_tile);
+  kp.f16 = d.f16 != 0;
+  if (kp.f16) kp.idesc &= ~((1u << 7) | (1u << 10));        // a_format / b_format: 1 = bf16, 0 = fp16
 
   // staging block: 128-B swizzled rows when the n-tile is wide enough, else one narrow block
   const int esz = d.out_fp32 ? 4 : 2;

@@ -11,6 +11,7 @@
 #include <stdint.h>
 
 #include "../../include/masic_b200.h"
+#include "cvt16.cuh"
 
 namespace {
 
@@ -40,7 +41,7 @@ __device__ __forceinline__ Bilin bilin_coords(const double* __restrict__ t, int 
 // out[p][0:3] = a[:, p] * w[0][p], out[p][3:6] = b[:, p] * w[1][p], out[p][6:16] = 0      (bf16, pitch 16)
 __global__ void __launch_bounds__(256)
 blend_images_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ wgt, int n,
-                    long hw, __nv_bfloat16* __restrict__ out) {
+                    long hw, __nv_bfloat16* __restrict__ out, int f16) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= (long)n * hw) return;
   const int bi = (int)(i / hw);
@@ -54,10 +55,7 @@ blend_images_kernel(const float* __restrict__ a, const float* __restrict__ b, co
   }
   uint32_t q[8];
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-    q[j] = *reinterpret_cast<uint32_t*>(&h2);
-  }
+  for (int j = 0; j < 3; ++j) q[j] = masic::pack16x2(v[2 * j], v[2 * j + 1], f16);
 #pragma unroll
   for (int j = 3; j < 8; ++j) q[j] = 0u;
   uint4* o = reinterpret_cast<uint4*>(out + i * 16);
@@ -73,7 +71,7 @@ blend_images_kernel(const float* __restrict__ a, const float* __restrict__ b, co
 __global__ void __launch_bounds__(256)
 feature_fuse_kernel(const __nv_bfloat16* __restrict__ self, int self_pitch, const __nv_bfloat16* __restrict__ other,
                     int other_pitch, int C, const float* __restrict__ wgt, const double* __restrict__ T, int n, int h,
-                    int w, __nv_bfloat16* __restrict__ out, int out_pitch) {
+                    int w, __nv_bfloat16* __restrict__ out, int out_pitch, int f16) {
   const int groups = C / 8, per_px = 2 * groups;
   const int lg = 31 - __clz(per_px);
   const int lane = threadIdx.x & 31;
@@ -94,11 +92,11 @@ feature_fuse_kernel(const __nv_bfloat16* __restrict__ self, int self_pitch, cons
     w_self = __ldg(wgt + ((long)bi * 2 + 1) * hw + my_px);
   }
   const uint32_t my_flags = (uint32_t)b.in_x0 | ((uint32_t)b.in_x1 << 1) | ((uint32_t)b.in_y0 << 2) | ((uint32_t)b.in_y1 << 3);
-  auto unpack = [](uint4 u, float* f) {
+  auto unpack = [f16](uint4 u, float* f) {
     const uint32_t q[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[j]));
+      const float2 t = masic::unpack16x2(q[j], f16);
       f[2 * j] = t.x; f[2 * j + 1] = t.y;
     }
   };
@@ -138,10 +136,7 @@ feature_fuse_kernel(const __nv_bfloat16* __restrict__ self, int self_pitch, cons
     }
     uint32_t q[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[2 * j] * scale, acc[2 * j + 1] * scale);
-      q[j] = *reinterpret_cast<uint32_t*>(&h2);
-    }
+    for (int j = 0; j < 4; ++j) q[j] = masic::pack16x2(acc[2 * j] * scale, acc[2 * j + 1] * scale, f16);
     *reinterpret_cast<uint4*>(out + p * out_pitch + 8 * g) = make_uint4(q[0], q[1], q[2], q[3]);
   }
 }
@@ -260,17 +255,17 @@ mask_weights_en_kernel(const float* __restrict__ mask, int H, int W, const float
 #define S(stream) static_cast<cudaStream_t>(stream)
 
 extern "C" int masic_cqe_blend_images(const float* a_nchw, const float* b_nchw, const float* weights_nchw2, int n, int h,
-                                      int w, void* out_nhwc16_bf16, void* stream) {
+                                      int w, void* out_nhwc16_bf16, int f16, void* stream) {
   if (!a_nchw || !b_nchw || !weights_nchw2 || !out_nhwc16_bf16 || n <= 0 || h <= 0 || w <= 0) return MASIC_EINVAL;
   const long total = (long)n * h * w;
   blend_images_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(
-      a_nchw, b_nchw, weights_nchw2, n, (long)h * w, static_cast<__nv_bfloat16*>(out_nhwc16_bf16));
+      a_nchw, b_nchw, weights_nchw2, n, (long)h * w, static_cast<__nv_bfloat16*>(out_nhwc16_bf16), f16);
   return (int)cudaGetLastError();
 }
 
 extern "C" int masic_cqe_feature_fuse(const void* self_bf16, int self_pitch, const void* other_bf16, int other_pitch,
                                       int c, const float* weights_nchw2, const double* t_prepared, int n, int h, int w,
-                                      void* out_bf16, int out_pitch, void* stream) {
+                                      void* out_bf16, int out_pitch, int f16, void* stream) {
   if (!self_bf16 || !other_bf16 || !weights_nchw2 || !t_prepared || !out_bf16 || c <= 0 || (c % 8) || (32 % (c / 4)) ||
       (self_pitch % 8) ||
       (other_pitch % 8) || (out_pitch % 8) || out_pitch < 2 * c || h < 2 || w < 2)
@@ -278,7 +273,7 @@ extern "C" int masic_cqe_feature_fuse(const void* self_bf16, int self_pitch, con
   const unsigned px_per_block = 256;                         // 8 warps x 32 pixels
   feature_fuse_kernel<<<dim3(((unsigned)h * (unsigned)w + px_per_block - 1) / px_per_block, n), 256, 0, S(stream)>>>(
       static_cast<const __nv_bfloat16*>(self_bf16), self_pitch, static_cast<const __nv_bfloat16*>(other_bf16), other_pitch,
-      c, weights_nchw2, t_prepared, n, h, w, static_cast<__nv_bfloat16*>(out_bf16), out_pitch);
+      c, weights_nchw2, t_prepared, n, h, w, static_cast<__nv_bfloat16*>(out_bf16), out_pitch, f16);
   return (int)cudaGetLastError();
 }
 

@@ -17,6 +17,7 @@
 #include <stdint.h>
 
 #include "../../include/masic_b200.h"
+#include "cvt16.cuh"
 
 namespace {
 
@@ -77,7 +78,7 @@ gmm_fwd_kernel(const float* __restrict__ y, View vy, const float* __restrict__ s
                const float* __restrict__ mu, const float* __restrict__ wgt, View vp, int w_is_logits,
                int fast_c, int M, int P, float scale_bound, float* __restrict__ y_hat,
                float* __restrict__ lik, View vo, int32_t* __restrict__ sym,
-               __nv_bfloat16* __restrict__ yq_bf16, int bf_pitch, int bf_coff,
+               __nv_bfloat16* __restrict__ yq_bf16, int bf_pitch, int bf_coff, int f16,
                const float* __restrict__ rowscale, int rs_stride, int rs_off) {
   __shared__ float s_lik[32][33];
   __shared__ float s_yh[32][33];
@@ -159,7 +160,7 @@ gmm_fwd_kernel(const float* __restrict__ y, View vy, const float* __restrict__ s
       if (p < P && m < M) {
         float v = s_yh[j][threadIdx.x];
         if (rowscale) v *= rowscale[((long)n * P + p) * rs_stride + rs_off];
-        yq_bf16[((long)n * P + p) * bf_pitch + bf_coff + m] = __float2bfloat16_rn(v);
+        reinterpret_cast<uint16_t*>(yq_bf16)[((long)n * P + p) * bf_pitch + bf_coff + m] = masic::pack16(v, f16);
       }
     }
   }
@@ -254,7 +255,7 @@ eb_fwd_kernel(const float* __restrict__ z, View vz, int P,
               const float* __restrict__ f2, const float* __restrict__ f3,
               const float* __restrict__ quantiles, float* __restrict__ z_hat,
               float* __restrict__ lik, View vo, int32_t* __restrict__ sym,
-              __nv_bfloat16* __restrict__ zq_bf16, int bf_pitch) {
+              __nv_bfloat16* __restrict__ zq_bf16, int bf_pitch, int f16) {
   __shared__ EBChan sc;
   const int c = blockIdx.y, n = blockIdx.z;
   if (threadIdx.x < 3) {
@@ -279,7 +280,7 @@ eb_fwd_kernel(const float* __restrict__ z, View vz, int P,
   const long o = at(vo, n, c, p);
   if (sym) sym[o] = (int32_t)r;
   if (z_hat) z_hat[o] = q;
-  if (zq_bf16) zq_bf16[((long)n * P + p) * bf_pitch + c] = __float2bfloat16_rn(q);
+  if (zq_bf16) reinterpret_cast<uint16_t*>(zq_bf16)[((long)n * P + p) * bf_pitch + c] = masic::pack16(q, f16);
   if (lik) {
     const float lower = eb_logits(sc, q - 0.5f);
     const float upper = eb_logits(sc, q + 0.5f);
@@ -306,7 +307,7 @@ quantize_kernel(const float* __restrict__ x, const float* __restrict__ means, lo
 __global__ void __launch_bounds__(256)
 latent_prep_kernel(const float* __restrict__ y, long total, int C, __nv_bfloat16* __restrict__ y_abs,
                    int abs_pitch, __nv_bfloat16* __restrict__ y_round, int rnd_pitch, int rnd_coff,
-                   const float* __restrict__ rowscale, int rs_stride, int rs_off) {
+                   const float* __restrict__ rowscale, int rs_stride, int rs_off, int f16) {
   // four channels per thread when the layout allows (16-byte loads, 8-byte stores), else one
   const bool v4 = (C & 3) == 0 && (abs_pitch & 3) == 0 && (rnd_pitch & 3) == 0 && (rnd_coff & 3) == 0;
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -317,17 +318,15 @@ latent_prep_kernel(const float* __restrict__ y, long total, int C, __nv_bfloat16
     const int c = (int)((unsigned)i - pix * c4) * 4;
     const float4 v = __ldg(reinterpret_cast<const float4*>(y) + i);
     if (y_abs) {
-      __nv_bfloat162 a = __floats2bfloat162_rn(fabsf(v.x), fabsf(v.y)), b = __floats2bfloat162_rn(fabsf(v.z), fabsf(v.w));
       *reinterpret_cast<uint2*>(y_abs + (long)pix * abs_pitch + c) =
-          make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+          make_uint2(masic::pack16x2(fabsf(v.x), fabsf(v.y), f16), masic::pack16x2(fabsf(v.z), fabsf(v.w), f16));
     }
     if (y_round) {
       const float s = rowscale ? rowscale[(long)pix * rs_stride + rs_off] : 1.0f;
       float r0 = rintf(v.x), r1 = rintf(v.y), r2 = rintf(v.z), r3 = rintf(v.w);
       if (rowscale) { r0 *= s; r1 *= s; r2 *= s; r3 *= s; }
-      __nv_bfloat162 a = __floats2bfloat162_rn(r0, r1), b = __floats2bfloat162_rn(r2, r3);
       *reinterpret_cast<uint2*>(y_round + (long)pix * rnd_pitch + rnd_coff + c) =
-          make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+          make_uint2(masic::pack16x2(r0, r1, f16), masic::pack16x2(r2, r3, f16));
     }
     return;
   }
@@ -335,11 +334,11 @@ latent_prep_kernel(const float* __restrict__ y, long total, int C, __nv_bfloat16
   const long pix = i / C;
   const int c = (int)(i - pix * C);
   const float v = y[i];
-  if (y_abs) y_abs[pix * abs_pitch + c] = __float2bfloat16_rn(fabsf(v));
+  if (y_abs) reinterpret_cast<uint16_t*>(y_abs)[pix * abs_pitch + c] = masic::pack16(fabsf(v), f16);
   if (y_round) {
     float r = rintf(v);
     if (rowscale) r *= rowscale[pix * rs_stride + rs_off];
-    y_round[pix * rnd_pitch + rnd_coff + c] = __float2bfloat16_rn(r);
+    reinterpret_cast<uint16_t*>(y_round)[pix * rnd_pitch + rnd_coff + c] = masic::pack16(r, f16);
   }
 }
 
@@ -485,14 +484,14 @@ extern "C" int masic_gmm_likelihood_fwd(const float* y, const float* sigma, cons
                                         int n, int m, int k, int hw, float scale_bound,
                                         float* y_hat, float* lik, int32_t* symbols, int out_nhwc,
                                         void* yq_bf16, int bf_pitch, int bf_coff,
-                                        const float* rowscale, int rs_stride, int rs_off, void* stream) {
+                                        const float* rowscale, int rs_stride, int rs_off, int f16, void* stream) {
   if (!y || !sigma || !mu || !weights || n <= 0 || m <= 0 || hw <= 0) return MASIC_EINVAL;
   if (k != 5) return MASIC_ENOSUP;    // HSIC hard-codes K = 5 (MASIC.py:653, test2_real.py:395)
   const View vy = mkview(in_nhwc, m, hw), vp = mkview(in_nhwc, m * k, hw), vo = mkview(out_nhwc, m, hw);
   dim3 grid((hw + 31) / 32, (m + 31) / 32, n), block(32, 8);
   gmm_fwd_kernel<5><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
       y, vy, sigma, mu, weights, vp, weights_are_logits, in_nhwc, m, hw, scale_bound, y_hat, lik, vo,
-      symbols, static_cast<__nv_bfloat16*>(yq_bf16), bf_pitch, bf_coff, rowscale, rs_stride, rs_off);
+      symbols, static_cast<__nv_bfloat16*>(yq_bf16), bf_pitch, bf_coff, f16, rowscale, rs_stride, rs_off);
   return (int)cudaGetLastError();
 }
 
@@ -521,7 +520,7 @@ extern "C" int masic_eb_fwd(const float* z, int in_nhwc, int n, int c, int hw,
                             const float* const* matrices, const float* const* biases,
                             const float* const* factors, const float* quantiles, float* z_hat,
                             float* lik, int32_t* symbols, int out_nhwc, void* zq_bf16, int bf_pitch,
-                            void* stream) {
+                            int f16, void* stream) {
   if (!z || !matrices || !biases || !factors || !quantiles || n <= 0 || c <= 0 || hw <= 0)
     return MASIC_EINVAL;
   const View vz = mkview(in_nhwc, c, hw), vo = mkview(out_nhwc, c, hw);
@@ -529,7 +528,7 @@ extern "C" int masic_eb_fwd(const float* z, int in_nhwc, int n, int c, int hw,
   eb_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       z, vz, hw, matrices[0], matrices[1], matrices[2], matrices[3], matrices[4], biases[0], biases[1],
       biases[2], biases[3], biases[4], factors[0], factors[1], factors[2], factors[3], quantiles, z_hat,
-      lik, vo, symbols, static_cast<__nv_bfloat16*>(zq_bf16), bf_pitch);
+      lik, vo, symbols, static_cast<__nv_bfloat16*>(zq_bf16), bf_pitch, f16);
   return (int)cudaGetLastError();
 }
 
@@ -544,14 +543,14 @@ extern "C" int masic_quantize(const float* x, const float* means, int64_t numel,
 
 extern "C" int masic_latent_prep(const float* y_nhwc, int64_t n_pixels, int c, void* y_abs_bf16,
                                  int abs_pitch, void* y_round_bf16, int rnd_pitch, int rnd_coff,
-                                 const float* rowscale, int rs_stride, int rs_off, void* stream) {
+                                 const float* rowscale, int rs_stride, int rs_off, int f16, void* stream) {
   if (!y_nhwc || n_pixels <= 0 || c <= 0) return MASIC_EINVAL;
   const long total = n_pixels * c;
   const bool v4 = (c & 3) == 0 && (abs_pitch & 3) == 0 && (rnd_pitch & 3) == 0 && (rnd_coff & 3) == 0;   // as in the kernel
   const long threads = v4 ? total / 4 : total;
   latent_prep_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       y_nhwc, total, c, static_cast<__nv_bfloat16*>(y_abs_bf16), abs_pitch,
-      static_cast<__nv_bfloat16*>(y_round_bf16), rnd_pitch, rnd_coff, rowscale, rs_stride, rs_off);
+      static_cast<__nv_bfloat16*>(y_round_bf16), rnd_pitch, rnd_coff, rowscale, rs_stride, rs_off, f16);
   return (int)cudaGetLastError();
 }
 

@@ -13,44 +13,48 @@
 #include <stdint.h>
 
 #include "../../include/masic_b200.h"
+#include "cvt16.cuh"
 
 namespace {
+using masic::pack16;
+using masic::pack16x2;
 
 // write c (<= 8) fp32 values as one zero-padded NHWC bf16 pixel of `pitch` channels with 16-byte stores
-__device__ __forceinline__ void store_pixel_bf16(__nv_bfloat16* o, const float* v, int c, int pitch) {
+__device__ __forceinline__ void store_pixel_bf16(__nv_bfloat16* o, const float* v, int c, int pitch, int f16) {
+  float e[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) e[i] = i < c ? v[i] : 0.0f;
+  if ((f16 & MASIC_FMT_SPLIT) && 2 * c <= 8 && 2 * c <= pitch) {     // [hi(c) | lo(c)]: lo = x - float(hi)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < c) {
+        const float hi = masic::unpack16(pack16(e[i], f16), f16);
+        const float lo = e[i] - hi;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j == c + i) e[j] = lo;       // compile-time indices keep e[] in registers
+      }
+  }
   if ((pitch & 7) == 0) {
     uint32_t w[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      __nv_bfloat162 q = __floats2bfloat162_rn(2 * i < c ? v[2 * i] : 0.0f, 2 * i + 1 < c ? v[2 * i + 1] : 0.0f);
-      w[i] = *reinterpret_cast<uint32_t*>(&q);
-    }
+    for (int i = 0; i < 4; ++i) w[i] = pack16x2(e[2 * i], e[2 * i + 1], f16);
     uint4* o4 = reinterpret_cast<uint4*>(o);
     o4[0] = make_uint4(w[0], w[1], w[2], w[3]);
     for (int j = 1; j < pitch / 8; ++j) o4[j] = make_uint4(0u, 0u, 0u, 0u);
   } else {
-    for (int ch = 0; ch < pitch; ++ch) o[ch] = __float2bfloat16_rn(ch < c ? v[ch] : 0.0f);
+    uint16_t* o16 = reinterpret_cast<uint16_t*>(o);
+    for (int ch = 0; ch < pitch; ++ch) {
+      float x = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (j == ch) x = e[j];
+      o16[ch] = pack16(x, f16);
+    }
   }
 }
 
-// same for 8 values already zero beyond the real channels, all indices compile-time (the array stays in registers)
-__device__ __forceinline__ void store_pixel8_bf16(__nv_bfloat16* o, const float (&v)[8], int pitch) {
-  if ((pitch & 7) == 0) {
-    uint32_t w[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      __nv_bfloat162 q = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-      w[i] = *reinterpret_cast<uint32_t*>(&q);
-    }
-    uint4* o4 = reinterpret_cast<uint4*>(o);
-    o4[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    for (int j = 1; j < pitch / 8; ++j) o4[j] = make_uint4(0u, 0u, 0u, 0u);
-  } else {
-#pragma unroll
-    for (int ch = 0; ch < 8; ++ch)
-      if (ch < pitch) o[ch] = __float2bfloat16_rn(v[ch]);
-    for (int ch = 8; ch < pitch; ++ch) o[ch] = __float2bfloat16_rn(0.0f);
-  }
+// same for 8 values already zero beyond the `c` real channels
+__device__ __forceinline__ void store_pixel8_bf16(__nv_bfloat16* o, const float (&v)[8], int c, int pitch, int f16) {
+  store_pixel_bf16(o, v, c, pitch, f16);
 }
 
 // ------------------------------------------------------------------ homography warp
@@ -104,7 +108,7 @@ __device__ __forceinline__ double fast_rcp(double d) {
 __global__ void __launch_bounds__(256)
 warp_kernel(const float* __restrict__ src, int n, int c, int h, int w, int ho, int wo,
             const double* __restrict__ T, double inv_wo1, double inv_ho1, float* __restrict__ dst,
-            __nv_bfloat16* __restrict__ dst_bf, int bf_pitch, int bf_row, int bf_xoff) {
+            __nv_bfloat16* __restrict__ dst_bf, int bf_pitch, int bf_row, int bf_xoff, int f16) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int b = blockIdx.z;
@@ -165,7 +169,7 @@ warp_kernel(const float* __restrict__ src, int n, int c, int h, int w, int ho, i
   }
   if (dst_bf) {
     for (int ch = c; ch < 8; ++ch) vals[ch] = 0.0f;
-    store_pixel_bf16(dst_bf + ((long)(b * ho + y) * bf_row + x + bf_xoff) * bf_pitch, vals, c, bf_pitch);
+    store_pixel_bf16(dst_bf + ((long)(b * ho + y) * bf_row + x + bf_xoff) * bf_pitch, vals, c, bf_pitch, f16);
   }
 }
 
@@ -180,7 +184,7 @@ conv_small_kernel(const float* __restrict__ in0, int c0, const float* __restrict
                   const float* __restrict__ bias, int c_out, int k, int stride, int act,
                   int gdn, const float* __restrict__ beta, const float* __restrict__ gamma, float beta_bound,
                   int ho, int wo, float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf, int bf_pitch,
-                  int bf_row, int bf_xoff) {
+                  int bf_row, int bf_xoff, int f16) {
   __shared__ float s_w[SC_MAX_CO * SC_MAX_CI * 25];
   __shared__ float s_b[SC_MAX_CO], s_beta[SC_MAX_CO], s_gamma[SC_MAX_CO * SC_MAX_CO];
   const int cin = c0 + c1, kk = k * k;
@@ -267,7 +271,7 @@ conv_small_kernel(const float* __restrict__ in0, int c0, const float* __restrict
   if (out)
     for (int co = 0; co < c_out; ++co) out[((long)(b * c_out + co) * ho + y) * wo + x] = acc[co];
   if (out_bf) {
-    store_pixel_bf16(out_bf + ((long)(b * ho + y) * bf_row + x + bf_xoff) * bf_pitch, acc, c_out, bf_pitch);
+    store_pixel_bf16(out_bf + ((long)(b * ho + y) * bf_row + x + bf_xoff) * bf_pitch, acc, c_out, bf_pitch, f16);
   }
 }
 
@@ -283,7 +287,7 @@ conv5x5_6to3_kernel(const float* __restrict__ in0, const float* __restrict__ in1
                     const float* __restrict__ wt, int transposed_s1, const float* __restrict__ bias,
                     int gdn, const float* __restrict__ beta, const float* __restrict__ gamma, float beta_bound,
                     float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf, int bf_pitch, int bf_row,
-                    int bf_xoff) {
+                    int bf_xoff, int f16) {
   __shared__ __align__(16) float s_in[6][F_PH][F_PW];
   __shared__ __align__(16) float s_w[6 * 5 * 16];      // [ci][ky][kx*3 + co], 15 used of 16
   __shared__ float s_b[3], s_beta[3], s_gamma[9];
@@ -411,7 +415,7 @@ conv5x5_6to3_kernel(const float* __restrict__ in0, const float* __restrict__ in1
       for (int p = 0; p < 4; ++p) {
         if (ox + p >= w) break;
         const float v3[8] = {acc[g][p][0], acc[g][p][1], acc[g][p][2], 0.f, 0.f, 0.f, 0.f, 0.f};
-        store_pixel_bf16(out_bf + ((long)(b * h + oy) * bf_row + ox + p + bf_xoff) * bf_pitch, v3, 3, bf_pitch);
+        store_pixel_bf16(out_bf + ((long)(b * h + oy) * bf_row + ox + p + bf_xoff) * bf_pitch, v3, 3, bf_pitch, f16);
       }
     }
   }
@@ -422,7 +426,7 @@ conv5x5_6to3_kernel(const float* __restrict__ in0, const float* __restrict__ in1
 __global__ void __launch_bounds__(256)
 subpix_to_nchw_kernel(const float* __restrict__ in, int n, int h2, int w2, int pitch, int gdn,
                       const float* __restrict__ beta, const float* __restrict__ gamma, float beta_bound,
-                      float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf, int bf_pitch) {
+                      float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf, int bf_pitch, int f16) {
   __shared__ float s_beta[3], s_gamma[9];
   if (gdn && threadIdx.x < 9) {
     const float ped = 1.4551915228366852e-11f;
@@ -458,7 +462,7 @@ subpix_to_nchw_kernel(const float* __restrict__ in, int n, int h2, int w2, int p
     }
     if (out_bf) {
       const float v3[8] = {x0, x1, x2, 0.f, 0.f, 0.f, 0.f, 0.f};
-      store_pixel_bf16(out_bf + ((long)(b * H + oy) * W + ox) * bf_pitch, v3, 3, bf_pitch);
+      store_pixel_bf16(out_bf + ((long)(b * H + oy) * W + ox) * bf_pitch, v3, 3, bf_pitch, f16);
     }
   }
 }
@@ -482,7 +486,7 @@ softmax_channels_kernel(const float* __restrict__ in, int n, int c, int hw, floa
 
 // NCHW fp32 (c <= 8 real channels) -> NHWC bf16 with `pitch` channels, zero padded
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, int n, int c, int hw, __nv_bfloat16* __restrict__ out,
+nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, int f16, int n, int c, int hw, __nv_bfloat16* __restrict__ out,
                          int pitch, int w, int row, int xoff) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;      // batch on blockIdx.y: 32-bit index arithmetic only
   const int b = blockIdx.y;
@@ -491,7 +495,7 @@ nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, int n, int c, int hw, __n
 #pragma unroll
   for (int ch = 0; ch < 8; ++ch) v[ch] = ch < c ? __ldg(in + ((long)(b * c + ch)) * hw + p) : 0.0f;
   const int y = p / w, x = p - y * w;
-  store_pixel8_bf16(out + (((long)b * (hw / w) + y) * row + x + xoff) * pitch, v, pitch);
+  store_pixel8_bf16(out + (((long)b * (hw / w) + y) * row + x + xoff) * pitch, v, c, pitch, f16);
 }
 
 // uint8 image -> float32 in [0, 1]: torchvision's ToTensor (img.float().div(255)), IEEE division, 16 values per thread
@@ -544,7 +548,7 @@ extern "C" int masic_warp_prepare(const float* m_3x3, int batch, int h, int w, i
 extern "C" int masic_warp_perspective_fwd(const float* src, int n, int c, int h, int w, int h_out,
                                           int w_out, const double* t_prepared, float* dst_nchw,
                                           void* dst_nhwc_bf16, int bf_pitch, int bf_row_pixels, int bf_xoff,
-                                          void* stream) {
+                                          int f16, void* stream) {
   if (!t_prepared || n <= 0 || c <= 0 || c > 8 || (!dst_nchw && !dst_nhwc_bf16)) return MASIC_EINVAL;
   if (bf_row_pixels == 0) { bf_row_pixels = w_out; bf_xoff = 0; }
   if (bf_row_pixels < w_out + bf_xoff || bf_xoff < 0) return MASIC_EINVAL;
@@ -552,7 +556,7 @@ extern "C" int masic_warp_perspective_fwd(const float* src, int n, int c, int h,
   dim3 grid((w_out + 255) / 256, h_out, n);
   warp_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, n, c, h, w, h_out, w_out, t_prepared, 1.0 / (double)(w_out - 1), 1.0 / (double)(h_out - 1), dst_nchw,
-      static_cast<__nv_bfloat16*>(dst_nhwc_bf16), bf_pitch, bf_row_pixels, bf_xoff);
+      static_cast<__nv_bfloat16*>(dst_nhwc_bf16), bf_pitch, bf_row_pixels, bf_xoff, f16);
   return (int)cudaGetLastError();
 }
 
@@ -561,7 +565,7 @@ extern "C" int masic_conv_small_nchw(const float* in0, int c0, const float* in1,
                                      int c_out, int ksize, int stride, int act, int gdn, const float* beta,
                                      const float* gamma, float beta_min, float* out_nchw,
                                      void* out_nhwc_bf16, int bf_pitch, int bf_row_pixels, int bf_xoff,
-                                     void* stream) {
+                                     int f16, void* stream) {
   if (!in0 || !weight || c_out <= 0 || c_out > SC_MAX_CO || c0 + c1 > SC_MAX_CI || c0 <= 0) return MASIC_EINVAL;
   if ((ksize != 3 && ksize != 5 && ksize != 1) || (stride != 1 && stride != 2)) return MASIC_EINVAL;
   if (c1 > 0 && !in1) return MASIC_EINVAL;
@@ -576,7 +580,7 @@ extern "C" int masic_conv_small_nchw(const float* in0, int c0, const float* in1,
     conv5x5_6to3_kernel<<<fgrid, fblock, 0, static_cast<cudaStream_t>(stream)>>>(
         in0, in1, n, h, w, weight, transposed_s1, bias, gdn, beta, gamma,
         sqrtf(beta_min + 1.4551915228366852e-11f), out_nchw, static_cast<__nv_bfloat16*>(out_nhwc_bf16),
-        bf_pitch, bf_row_pixels, bf_xoff);
+        bf_pitch, bf_row_pixels, bf_xoff, f16);
     return (int)cudaGetLastError();
   }
   dim3 grid((wo + 127) / 128, ho, n);
@@ -584,19 +588,19 @@ extern "C" int masic_conv_small_nchw(const float* in0, int c0, const float* in1,
   kern<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       in0, c0, in1, c1, n, h, w, weight, transposed_s1, bias, c_out, ksize, stride, act, gdn, beta, gamma,
       sqrtf(beta_min + 1.4551915228366852e-11f), ho, wo, out_nchw,
-      static_cast<__nv_bfloat16*>(out_nhwc_bf16), bf_pitch, bf_row_pixels, bf_xoff);
+      static_cast<__nv_bfloat16*>(out_nhwc_bf16), bf_pitch, bf_row_pixels, bf_xoff, f16);
   return (int)cudaGetLastError();
 }
 
 extern "C" int masic_subpix_to_nchw(const float* in_nhwc, int n, int h2, int w2, int pitch, int gdn,
                                     const float* beta, const float* gamma, float beta_min, float* out_nchw,
-                                    void* out_nhwc_bf16, int bf_pitch, void* stream) {
+                                    void* out_nhwc_bf16, int bf_pitch, int f16, void* stream) {
   if (!in_nhwc || pitch < 12 || pitch % 4 || n <= 0) return MASIC_EINVAL;
   if (gdn && (!beta || !gamma)) return MASIC_EINVAL;
   dim3 grid((w2 + 255) / 256, h2, n);
   subpix_to_nchw_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       in_nhwc, n, h2, w2, pitch, gdn, beta, gamma, sqrtf(beta_min + 1.4551915228366852e-11f), out_nchw,
-      static_cast<__nv_bfloat16*>(out_nhwc_bf16), bf_pitch);
+      static_cast<__nv_bfloat16*>(out_nhwc_bf16), bf_pitch, f16);
   return (int)cudaGetLastError();
 }
 
@@ -610,13 +614,13 @@ extern "C" int masic_softmax_channels(const float* in_nchw, int n, int c, int hw
 }
 
 extern "C" int masic_nchw_to_nhwc_bf16(const float* in_nchw, int n, int c, int h, int w, void* out, int pitch,
-                                       int row_pixels, int xoff, void* stream) {
+                                       int row_pixels, int xoff, int f16, void* stream) {
   if (!in_nchw || !out || c <= 0 || c > 8 || c > pitch || pitch > 64 || h <= 0 || w <= 0) return MASIC_EINVAL;
   if (row_pixels == 0) { row_pixels = w; xoff = 0; }
   if (row_pixels < w + xoff || xoff < 0) return MASIC_EINVAL;
   const int hw = h * w;
   nchw_to_nhwc_bf16_kernel<<<dim3((hw + 255) / 256, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      in_nchw, n, c, hw, static_cast<__nv_bfloat16*>(out), pitch, w, row_pixels, xoff);
+      in_nchw, f16, n, c, hw, static_cast<__nv_bfloat16*>(out), pitch, w, row_pixels, xoff);
   return (int)cudaGetLastError();
 }
 

@@ -14,12 +14,13 @@
 #include <stdint.h>
 
 #include "../../include/masic_b200.h"
+#include "cvt16.cuh"
 
 namespace {
 
 // 2x2 max-pool over NHWC bf16, 8 channels (16 bytes) per thread.
 __global__ void __launch_bounds__(256)
-maxpool2_kernel(const uint4* __restrict__ in, int n, int h, int w, int c8, uint4* __restrict__ out) {
+maxpool2_kernel(const uint4* __restrict__ in, int n, int h, int w, int c8, uint4* __restrict__ out, int f16) {
   const int ho = h >> 1, wo = w >> 1;
   const long total = (long)n * ho * wo * c8;
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -31,10 +32,7 @@ maxpool2_kernel(const uint4* __restrict__ in, int n, int h, int w, int c8, uint4
   const int img = (int)(r / ho);
   const uint4* p = in + (((long)img * h + 2 * y) * w + 2 * x) * c8 + c;
   const uint4 a = __ldg(p), b = __ldg(p + c8), cc = __ldg(p + (long)w * c8), d = __ldg(p + (long)w * c8 + c8);
-  auto mx = [](uint32_t u, uint32_t v) -> uint32_t {
-    __nv_bfloat162 r2 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&u), *reinterpret_cast<const __nv_bfloat162*>(&v));
-    return *reinterpret_cast<uint32_t*>(&r2);
-  };
+  auto mx = [f16](uint32_t u, uint32_t v) -> uint32_t { return masic::max16x2(u, v, f16); };
   uint4 o;
   o.x = mx(mx(a.x, b.x), mx(cc.x, d.x));
   o.y = mx(mx(a.y, b.y), mx(cc.y, d.y));
@@ -50,7 +48,7 @@ template <int MAXB>
 __global__ void __launch_bounds__(256)
 fc_rows_kernel(const __nv_bfloat16* __restrict__ x, int xb_stride, const __nv_bfloat16* __restrict__ w,
                const float* __restrict__ bias, int batch, int K, int relu, float* __restrict__ out_f32,
-               __nv_bfloat16* __restrict__ out_bf16, int out_stride) {
+               __nv_bfloat16* __restrict__ out_bf16, int out_stride, int f16) {
   const int r = blockIdx.x;
   const uint4* wr = reinterpret_cast<const uint4*>(w + (size_t)r * K);
   float acc[MAXB];
@@ -58,15 +56,15 @@ fc_rows_kernel(const __nv_bfloat16* __restrict__ x, int xb_stride, const __nv_bf
   for (int b = 0; b < MAXB; ++b) acc[b] = 0.0f;
   for (int k8 = threadIdx.x; k8 < K / 8; k8 += blockDim.x) {
     const uint4 wv = __ldg(wr + k8);
-    const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wv);
+    const uint32_t* w2 = reinterpret_cast<const uint32_t*>(&wv);
 #pragma unroll
     for (int b = 0; b < MAXB; ++b) {
       if (b < batch) {
         const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + (size_t)b * xb_stride) + k8);
-        const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(&xv);
+        const uint32_t* x2 = reinterpret_cast<const uint32_t*>(&xv);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float2 a = __bfloat1622float2(w2[e]), c = __bfloat1622float2(x2[e]);
+          const float2 a = masic::unpack16x2(w2[e], f16), c = masic::unpack16x2(x2[e], f16);
           acc[b] = fmaf(a.x, c.x, acc[b]);
           acc[b] = fmaf(a.y, c.y, acc[b]);
         }
@@ -89,13 +87,13 @@ fc_rows_kernel(const __nv_bfloat16* __restrict__ x, int xb_stride, const __nv_bf
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) v += red[b][i];
     if (relu) v = fmaxf(v, 0.0f);
     if (out_f32) out_f32[(size_t)b * out_stride + r] = v;
-    if (out_bf16) out_bf16[(size_t)b * out_stride + r] = __float2bfloat16_rn(v);
+    if (out_bf16) reinterpret_cast<uint16_t*>(out_bf16)[(size_t)b * out_stride + r] = masic::pack16(v, f16);
   }
 }
 
 // [rows][C*H*W] (torch Flatten of NCHW: column = c*HW + p) -> bf16 [rows][HW*C] (column = p*C + c, the order of an NHWC
 // activation), so the FC reads the conv output where it lies.
-__global__ void fc_pack_kernel(const float* __restrict__ w, int rows, int c, int hw, __nv_bfloat16* __restrict__ dst) {
+__global__ void fc_pack_kernel(const float* __restrict__ w, int rows, int c, int hw, uint16_t* __restrict__ dst, int f16) {
   const long total = (long)rows * c * hw;
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -103,7 +101,7 @@ __global__ void fc_pack_kernel(const float* __restrict__ w, int rows, int c, int
   long r = i / c;
   const int p = (int)(r % hw);
   const long row = r / hw;
-  dst[i] = __float2bfloat16_rn(w[(row * c + cc) * hw + p]);
+  dst[i] = masic::pack16(w[(row * c + cc) * hw + p], f16);
 }
 
 // One thread per stereo pair: 8x8 DLT (Gaussian elimination with partial pivoting, fp64), 3x3 inverse, h_adjust.
@@ -158,31 +156,33 @@ __global__ void homography_kernel(const float* __restrict__ corners, const float
 
 }  // namespace
 
-extern "C" int masic_maxpool2_nhwc_bf16(const void* in, int n, int h, int w, int c_pitch, void* out, void* stream) {
+extern "C" int masic_maxpool2_nhwc_bf16(const void* in, int n, int h, int w, int c_pitch, void* out, int f16,
+                                        void* stream) {
   if (!in || !out || n <= 0 || h <= 0 || w <= 0 || (h & 1) || (w & 1) || c_pitch <= 0 || (c_pitch & 7)) return MASIC_EINVAL;
   const long total = (long)n * (h / 2) * (w / 2) * (c_pitch / 8);
   maxpool2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(in), n, h, w, c_pitch / 8, static_cast<uint4*>(out));
+      static_cast<const uint4*>(in), n, h, w, c_pitch / 8, static_cast<uint4*>(out), f16);
   return (int)cudaGetLastError();
 }
 
-extern "C" int masic_fc_pack_weights(const float* weight, int rows, int c, int hw, void* dst_bf16, void* stream) {
+extern "C" int masic_fc_pack_weights(const float* weight, int rows, int c, int hw, void* dst_bf16, int f16,
+                                     void* stream) {
   if (!weight || !dst_bf16 || rows <= 0 || c <= 0 || hw <= 0) return MASIC_EINVAL;
   const long total = (long)rows * c * hw;
   fc_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      weight, rows, c, hw, static_cast<__nv_bfloat16*>(dst_bf16));
+      weight, rows, c, hw, static_cast<uint16_t*>(dst_bf16), f16);
   return (int)cudaGetLastError();
 }
 
 extern "C" int masic_fc_bf16(const void* x_bf16, int x_batch_stride, const void* w_bf16, const float* bias, int batch,
                              int k, int rows, int relu, float* out_f32, void* out_bf16, int out_batch_stride,
-                             void* stream) {
+                             int f16, void* stream) {
   if (!x_bf16 || !w_bf16 || batch <= 0 || batch > 8 || k <= 0 || (k & 7) || (x_batch_stride & 7) || rows <= 0 ||
       (!out_f32 && !out_bf16))
     return MASIC_EINVAL;
   fc_rows_kernel<8><<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x_bf16), x_batch_stride, static_cast<const __nv_bfloat16*>(w_bf16), bias, batch,
-      k, relu, out_f32, static_cast<__nv_bfloat16*>(out_bf16), out_batch_stride);
+      k, relu, out_f32, static_cast<__nv_bfloat16*>(out_bf16), out_batch_stride, f16);
   return (int)cudaGetLastError();
 }
 

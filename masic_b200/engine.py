@@ -29,6 +29,9 @@ from ._lib import MasicError, check
 from .convplan import (ACT_LEAKY, ACT_NONE, ACT_RELU, CONV, CONV_XFOLD8, DECONV_S2, DECONV_S2_SUBPIX, GDN_FWD, GDN_INV,
                        GDN_NONE, MASK_A_5x5, ConvPlan, PackedConv)
 
+F16 = _lib.FMT_F16              # the inference engines run on fp16 operands / activations (csrc/cvt16.cuh)
+ACT = _lib.act_dtype(F16)
+F16_IMG = F16 | _lib.FMT_SPLIT   # images feeding g_a_conv1: pixels stored as [hi(3) | lo(3) | 0 0] (MASIC_FMT_SPLIT)
 SCALE_BOUND = 0.11
 IMG_CP = 8           # channel pitch of the bf16 images feeding g_a_conv1 (3 real channels); rows are padded:
 XOFF, XPAD = _lib.IMG_XOFF, _lib.IMG_XPAD   # [N][H][W+XPAD][8], pixel x at column x+XOFF (MASIC_CONV_XFOLD8 input)
@@ -62,7 +65,7 @@ class HSICEngine:
             self._build()
 
     # ------------------------------------------------------------------ helpers
-    def _buf(self, *shape, dtype=torch.bfloat16):
+    def _buf(self, *shape, dtype=ACT):
         return torch.zeros(*shape, dtype=dtype, device=self.dev)
 
     def _w(self, name):
@@ -106,7 +109,7 @@ class HSICEngine:
         return PackedConv(kind=kind, ksize=ksize, c_in=c_in, c_out=c_out, n_tile=n_tile, weight=w,
                           transposed=transposed, bias=self._w(prefix + ".bias"), c_out_pad=c_out_pad, gdn=gdn,
                           gdn_beta=self._w(gdn_prefix + ".beta") if gdn else None,
-                          gdn_gamma=self._w(gdn_prefix + ".gamma") if gdn else None)
+                          gdn_gamma=self._w(gdn_prefix + ".gamma") if gdn else None, f16=F16)
 
     # ------------------------------------------------------------------ building blocks
     def _encoder_weights(self, enc: str):
@@ -185,7 +188,7 @@ class HSICEngine:
 
         def eb_step():
             check(self.lib.masic_eb_fwd(z.data_ptr(), 1, B, N, hw64, pm, pb, pf, quant.data_ptr(), z_hat.data_ptr(),
-                                        z_lik.data_ptr(), None, 0, zq.data_ptr(), N, self._s()), "masic_eb_fwd")
+                                        z_lik.data_ptr(), None, 0, zq.data_ptr(), N, F16, self._s()), "masic_eb_fwd")
         self._add(f"{tag}.entropy_bottleneck", eb_step)
         # h_s_up: deconv5 s2 -> LeakyReLU -> deconv5 s2 -> LeakyReLU -> conv3 s1 (MASIC.py:678-691)
         hs = f"h_s{idx}_up"
@@ -210,14 +213,14 @@ class HSICEngine:
         br = ("gmm_sigma", "gmm_means", "gmm_weights")
         w0 = torch.cat([self._w(f"{net}.{b}.0.weight") for b in br], dim=cat_dim)
         b0 = torch.cat([self._w(f"{net}.{b}.0.bias") for b in br])
-        p0 = PackedConv(ksize=1, c_in=cin, c_out=18 * M, n_tile=192, weight=w0, transposed=t, bias=b0)
+        p0 = PackedConv(ksize=1, c_in=cin, c_out=18 * M, n_tile=192, weight=w0, transposed=t, bias=b0, f16=F16)
         self.packs[f"{tag}.gmm.l0"] = p0
         l0 = self._buf(B, h16, w16, 18 * M)
         self._conv(f"{tag}.gmm.l0(3 branches)", p0, gmm_in, l0,
                    act=[ACT_RELU] * 6 + [ACT_LEAKY] * 12, cta_pairs=True)
         def pk(b, i, ci, co):
             pc = PackedConv(ksize=1, c_in=ci, c_out=co, n_tile=192, weight=self._w(f"{net}.{b}.{i}.weight"),
-                            transposed=t if i == 2 else False, bias=self._w(f"{net}.{b}.{i}.bias"))
+                            transposed=t if i == 2 else False, bias=self._w(f"{net}.{b}.{i}.bias"), f16=F16)
             self.packs[f"{tag}.gmm.{b[4:]}.l{i // 2}"] = pc          # per-branch packs: the per-pixel decoder's plans
             return pc
 
@@ -236,7 +239,7 @@ class HSICEngine:
         l1 = self._buf(B, h16, w16, 13 * M)               # sigma 4M | means 4M | weights 5M
         w1 = torch.cat([mat(b_, 2) for b_ in br], dim=0).reshape(13 * M, 6 * M, 1, 1).contiguous()
         b1 = torch.cat([self._w(f"{net}.{b_}.2.bias") for b_ in br])
-        p1 = PackedConv(ksize=1, c_in=6 * M, c_out=13 * M, n_tile=192, weight=w1, bias=b1)
+        p1 = PackedConv(ksize=1, c_in=6 * M, c_out=13 * M, n_tile=192, weight=w1, bias=b1, f16=F16)
         plan = ConvPlan(packed=p1, x=l0, out=l1, act=[ACT_RELU] * nt(4 * M) + [ACT_LEAKY] * nt(9 * M),
                         nt_in_coff=[0] * nt(4 * M) + [6 * M] * nt(4 * M) + [12 * M] * nt(5 * M))
         self.plans[f"{tag}.gmm.l1(3 branches)"] = plan
@@ -245,7 +248,7 @@ class HSICEngine:
         sig, mu, wl = smw[0:B], smw[B:2 * B], smw[2 * B:3 * B]
         w2 = torch.cat([mat("gmm_sigma", 4), mat("gmm_means", 4)], dim=0).reshape(2 * MK, 4 * M, 1, 1).contiguous()
         b2 = torch.cat([self._w(f"{net}.gmm_sigma.4.bias"), self._w(f"{net}.gmm_means.4.bias")])
-        p2 = PackedConv(ksize=1, c_in=4 * M, c_out=2 * MK, n_tile=192, weight=w2, bias=b2)
+        p2 = PackedConv(ksize=1, c_in=4 * M, c_out=2 * MK, n_tile=192, weight=w2, bias=b2, f16=F16)
         tiles = list(range(0, MK, 192))
         plan = ConvPlan(packed=p2, x=l1, out=smw, act=[ACT_RELU] * nt(MK) + [ACT_NONE] * nt(MK),
                         nt_in_coff=[0] * nt(MK) + [4 * M] * nt(MK), nt_out_coff=tiles + tiles,
@@ -263,7 +266,7 @@ class HSICEngine:
         def step():
             check(self.lib.masic_gmm_likelihood_fwd(y.data_ptr(), sig.data_ptr(), mu.data_ptr(), wl.data_ptr(), 1, 1,
                                                     B, M, K, hw, SCALE_BOUND, y_hat_nchw.data_ptr(), lik_nchw.data_ptr(),
-                                                    None, 0, None, 0, 0, None, 0, 0, self._s()),
+                                                    None, 0, None, 0, 0, None, 0, 0, F16, self._s()),
                   "masic_gmm_likelihood_fwd")
         self._add(f"{tag}.gmm_likelihood", step)
 
@@ -277,7 +280,7 @@ class HSICEngine:
                                              None if y_rnd is None else y_rnd.data_ptr(),
                                              0 if y_rnd is None else y_rnd.shape[3], rnd_coff,
                                              None if rowscale is None else rowscale.data_ptr(),
-                                             0 if rowscale is None else rowscale.shape[3], rs_off, self._s()),
+                                             0 if rowscale is None else rowscale.shape[3], rs_off, F16, self._s()),
                   "masic_latent_prep")
         self._add(f"{tag}.latent_prep", step)
 
@@ -290,7 +293,7 @@ class HSICEngine:
                                                       None if dst_bf is None else dst_bf.data_ptr(),
                                                       0 if dst_bf is None else dst_bf.shape[3],
                                                       0 if dst_bf is None else dst_bf.shape[2],
-                                                      0 if dst_bf is None else XOFF, self._s()),
+                                                      0 if dst_bf is None else XOFF, F16_IMG, self._s()),
                   "masic_warp_perspective_fwd")
         self._add(tag, step)
 
@@ -314,7 +317,7 @@ class HSICEngine:
                                                  None if out_bf is None else out_bf.data_ptr(),
                                                  0 if out_bf is None else out_bf.shape[3],
                                                  0 if out_bf is None else out_bf.shape[2],
-                                                 0 if out_bf is None else XOFF, self._s()),
+                                                 0 if out_bf is None else XOFF, F16_IMG, self._s()),
                   "masic_conv_small_nchw")
         self._add(tag, step)
 
@@ -339,7 +342,7 @@ class HSICEngine:
         self._on(0)
         x1_bf = self._buf(B, H, W + XPAD, IMG_CP)
         self._add("x1.pack_nhwc", lambda: check(lib.masic_nchw_to_nhwc_bf16(
-            self.x1.data_ptr(), B, 3, H, W, x1_bf.data_ptr(), IMG_CP, W + XPAD, XOFF, self._s()), "masic_nchw_to_nhwc_bf16"))
+            self.x1.data_ptr(), B, 3, H, W, x1_bf.data_ptr(), IMG_CP, W + XPAD, XOFF, F16_IMG, self._s()), "masic_nchw_to_nhwc_bf16"))
         enc1 = self._encoder_weights("encoder1")
         y1 = self._encoder("L.g_a", enc1, x1_bf)
         y1_abs = self._buf(B, h16, w16, M)
@@ -411,7 +414,7 @@ class HSICEngine:
         self._on(0)
         sp1 = self._decoder("L.g_s", "decoder1", y1_rnd)                                           # :777
         self._add("L.x1_hat(unshuffle)", lambda: check(lib.masic_subpix_to_nchw(
-            sp1.data_ptr(), B, H // 2, W // 2, 16, 0, None, None, 1e-6, o["x1_hat"].data_ptr(), None, 0, self._s()),
+            sp1.data_ptr(), B, H // 2, W // 2, 16, 0, None, None, 1e-6, o["x1_hat"].data_ptr(), None, 0, F16, self._s()),
             "masic_subpix_to_nchw"))
         # x1_hat warped once (the reference computes it twice, :821 and :833)
         x1hw = self._buf(B, 3, H, W, dtype=f32)
@@ -431,7 +434,7 @@ class HSICEngine:
         self._keep += [ab, ag]
         self._add("R.after_gdn(unshuffle)", lambda: check(lib.masic_subpix_to_nchw(
             sp2.data_ptr(), B, H // 2, W // 2, 16, GDN_INV, ab.data_ptr(), ag.data_ptr(), 1e-6, after1.data_ptr(), None, 0,
-            self._s()), "masic_subpix_to_nchw"))
+            F16, self._s()), "masic_subpix_to_nchw"))
         self._conv_small("R.after_conv", after1, x1hw, "decoder2.after_conv", ksize=5, stride=1, transposed_s1=True,
                          out=o["x2_hat"])
         self._wait("left_entropy")

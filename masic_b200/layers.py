@@ -15,10 +15,13 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
-from . import ops
+from . import _lib, ops
 from ._lib import MasicError
 from .convplan import (ACT_NONE, CONV, DECONV_S2, DECONV_S2_SUBPIX, GDN_FWD, GDN_INV, GDN_NONE, MASK_A_5x5,
                        ConvPlan, PackedConv)
+
+F16 = _lib.FMT_F16              # inference runs on fp16 operands / activations (csrc/cvt16.cuh)
+ACT = _lib.act_dtype(F16)
 
 __all__ = ["GDN", "MaskedConv2d", "ResidualBlock", "conv3x3", "conv1x1", "LowerBound",
            "NonNegativeParametrizer", "conv", "deconv"]
@@ -73,8 +76,8 @@ def _to_nhwc_bf16(x: Tensor, pitch: int) -> Tensor:
     n, c, h, w = x.shape
     if c <= 8:
         return ops.nchw_to_nhwc_bf16(x, pitch)
-    out = torch.zeros(n, h, w, pitch, dtype=torch.bfloat16, device=x.device) if pitch != c else \
-        torch.empty(n, h, w, pitch, dtype=torch.bfloat16, device=x.device)
+    out = torch.zeros(n, h, w, pitch, dtype=ACT, device=x.device) if pitch != c else \
+        torch.empty(n, h, w, pitch, dtype=ACT, device=x.device)
     out[..., :c].copy_(x.permute(0, 2, 3, 1))
     return out
 
@@ -116,7 +119,7 @@ def conv_forward(x: Tensor, weight: Tensor, bias: Optional[Tensor], stride: int,
             else:
                 wp[:, :cin] = wt
             wt = wp
-        xin = torch.empty(n, h, w, cin_p, dtype=torch.bfloat16, device=x.device)
+        xin = torch.empty(n, h, w, cin_p, dtype=ACT, device=x.device)
         if transposed and s == 2:
             if cout <= 8:
                 kind, n_tile = DECONV_S2_SUBPIX, 16
@@ -125,7 +128,7 @@ def conv_forward(x: Tensor, weight: Tensor, bias: Optional[Tensor], stride: int,
         else:
             kind, n_tile = CONV, (128 if cout % 128 == 0 else 192 if cout % 192 == 0 else 64)
         packed = PackedConv(kind=kind, ksize=k, c_in=cin_p, c_out=cout, n_tile=n_tile, weight=wt,
-                            transposed=transposed, bias=bias)
+                            transposed=transposed, bias=bias, f16=F16)
         if kind == DECONV_S2:
             ho, wo = 2 * h, 2 * w
         elif kind == CONV and s == 2:
@@ -149,7 +152,7 @@ def conv_forward(x: Tensor, weight: Tensor, bias: Optional[Tensor], stride: int,
         res = torch.empty(n, cout, 2 * h, 2 * w, dtype=torch.float32, device=x.device)
         _lib.check(_lib.load().masic_subpix_to_nchw(out.data_ptr(), n, h, w, out.shape[3], 0, None, None, 1e-6,
                                                     res.data_ptr(), None, 0,
-                                                    torch.cuda.current_stream().cuda_stream),
+                                                    F16, torch.cuda.current_stream().cuda_stream),
                    "masic_subpix_to_nchw")
         return res
     return ops.nhwc_to_nchw_f32(out, cout)

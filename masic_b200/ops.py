@@ -15,6 +15,9 @@ import torch
 from . import _lib
 from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU, GDN_FWD, GDN_INV, GDN_NONE, MasicError, check
 
+F16 = _lib.FMT_F16              # inference runs on fp16 operands / activations (csrc/cvt16.cuh)
+ACT16 = _lib.act_dtype(F16)
+
 SCALE_BOUND = 0.11
 
 
@@ -55,7 +58,7 @@ def gmm_likelihood(y: torch.Tensor, sigma: torch.Tensor, mu: torch.Tensor, weigh
     check(_lib.load().masic_gmm_likelihood_fwd(
         y.data_ptr(), sigma.data_ptr(), mu.data_ptr(), weights.data_ptr(), int(weights_are_logits), 0,
         n, m, K, h * w, float(scale_bound), y_hat.data_ptr(), lik.data_ptr(), _p(sym), 0,
-        None, 0, 0, None, 0, 0, _s()), "masic_gmm_likelihood_fwd")
+        None, 0, 0, None, 0, 0, F16, _s()), "masic_gmm_likelihood_fwd")
     return (y_hat, lik, sym) if want_symbols else (y_hat, lik)
 
 
@@ -124,7 +127,7 @@ def eb_forward(z: torch.Tensor, matrices: Sequence[torch.Tensor], biases: Sequen
     lik = torch.empty_like(z) if want_lik else None
     sym = torch.empty(z.shape, dtype=torch.int32, device=z.device) if want_symbols else None
     check(_lib.load().masic_eb_fwd(z.data_ptr(), 0, n, c, h * w, _ptr_array(ms), _ptr_array(bs), _ptr_array(fs),
-                                   q.data_ptr(), z_hat.data_ptr(), _p(lik), _p(sym), 0, None, 0, _s()), "masic_eb_fwd")
+                                   q.data_ptr(), z_hat.data_ptr(), _p(lik), _p(sym), 0, None, 0, F16, _s()), "masic_eb_fwd")
     return z_hat, lik, sym
 
 
@@ -181,9 +184,9 @@ def warp_perspective(src: Optional[torch.Tensor], M: torch.Tensor, dsize: Tuple[
     ho, wo = dsize
     T = warp_prepare(M, (h, w), (ho, wo), invert)
     dst = torch.empty(n, c, ho, wo, dtype=torch.float32, device=M.device)
-    dst_bf = torch.empty(n, ho, wo, bf16_pitch, dtype=torch.bfloat16, device=M.device) if bf16_pitch else None
+    dst_bf = torch.empty(n, ho, wo, bf16_pitch, dtype=ACT16, device=M.device) if bf16_pitch else None
     check(_lib.load().masic_warp_perspective_fwd(_p(src), n, c, h, w, ho, wo, T.data_ptr(), dst.data_ptr(),
-                                                 _p(dst_bf), bf16_pitch, 0, 0, _s()), "masic_warp_perspective_fwd")
+                                                 _p(dst_bf), bf16_pitch, 0, 0, F16, _s()), "masic_warp_perspective_fwd")
     return (dst, dst_bf) if bf16_pitch else dst
 
 
@@ -207,7 +210,7 @@ def conv_small(in0: torch.Tensor, in1: Optional[torch.Tensor], weight: torch.Ten
     check(_lib.load().masic_conv_small_nchw(in0.data_ptr(), c0, _p(in1), c1, n, h, w, weight.data_ptr(),
                                             int(transposed_s1), _p(bias), c_out, ksize, stride, act, gdn, _p(beta),
                                             _p(gamma), float(beta_min), _p(out), _p(out_bf16),
-                                            0 if out_bf16 is None else out_bf16.shape[3], 0, 0, _s()),
+                                            0 if out_bf16 is None else out_bf16.shape[3], 0, 0, F16, _s()),
           "masic_conv_small_nchw")
     return out if out is not None else out_bf16
 
@@ -228,8 +231,8 @@ def nchw_to_nhwc_bf16(x: torch.Tensor, pitch: int, out: Optional[torch.Tensor] =
     x = _f32c(x)
     n, c, h, w = x.shape
     if out is None:
-        out = torch.empty(n, h, w, pitch, dtype=torch.bfloat16, device=x.device)
-    check(_lib.load().masic_nchw_to_nhwc_bf16(x.data_ptr(), n, c, h, w, out.data_ptr(), pitch, 0, 0, _s()),
+        out = torch.empty(n, h, w, pitch, dtype=ACT16, device=x.device)
+    check(_lib.load().masic_nchw_to_nhwc_bf16(x.data_ptr(), n, c, h, w, out.data_ptr(), pitch, 0, 0, F16, _s()),
           "masic_nchw_to_nhwc_bf16")
     return out
 

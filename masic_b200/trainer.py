@@ -190,7 +190,7 @@ class _GDN:
         """beta' / gamma' of this step (parametrizers.py:61-64) -> the two packed 1x1 weights."""
         lib = self.tr.lib
         check(lib.masic_gdn_prepare(self.beta.data_ptr(), self.gamma.data_ptr(), self.c, 1e-6, self.beta_p.data_ptr(),
-                                    self.gamma_p.data_ptr(), None, T._s()), "masic_gdn_prepare")
+                                    self.gamma_p.data_ptr(), None, 0, T._s()), "masic_gdn_prepare")
         self.gamma_pt.copy_(self.gamma_p.t())
         self.pk_n.repack(self.gamma_p.view(self.c, self.c, 1, 1), self.beta_p)
         self.pk_v.repack(self.gamma_pt.view(self.c, self.c, 1, 1))
@@ -375,9 +375,9 @@ class HSICTrainer:
         def bwd(gimg: torch.Tensor):
             """gimg: dL/d(deconv4 output image), NCHW fp32 (B,3,H,W)."""
             check(lib.masic_nchw_to_nhwc_bf16(gimg.data_ptr(), B, 3, H, W, gimg_bf.data_ptr(), IMG_CP, W + XPAD, XOFF,
-                                              T._s()), "masic_nchw_to_nhwc_bf16")
+                                              0, T._s()), "masic_nchw_to_nhwc_bf16")
             T.colsum_nchw(gimg, db4)
-            check(lib.masic_nchw_to_nhwc_bf16(gimg.data_ptr(), B, 3, H, W, gimg16.data_ptr(), 16, 0, 0, T._s()),
+            check(lib.masic_nchw_to_nhwc_bf16(gimg.data_ptr(), B, 3, H, W, gimg16.data_ptr(), 16, 0, 0, 0, T._s()),
                   "masic_nchw_to_nhwc_bf16")
             wg4.launch()
             dw4.add_(dw16[:, :3])
@@ -538,7 +538,7 @@ class HSICTrainer:
         dec1 = self._decoder_pass("L", "decoder1", y1_hat_bf, g_y1hat)
 
         self.F("x1.pack", lambda: check(lib.masic_nchw_to_nhwc_bf16(self.x1.data_ptr(), B, 3, H, W, x1_bf.data_ptr(), IMG_CP,
-                                                                    W + XPAD, XOFF, T._s()), "pack"))
+                                                                    W + XPAD, XOFF, 0, T._s()), "pack"))
         self.F("L.encoder", encA["fwd"])
         self.F("L.latent_prep", lambda: T.latent_prep_train(y1, self.noise["y1_ctx"], y1_abs, y1_ctx))
         self.F("L.hyper", hyp1["fwd"])
@@ -549,7 +549,7 @@ class HSICTrainer:
             y_hat=o["y1_hat"], dy=dy1_lik, dsigma=net1["gsig"], dmu=net1["gmu"], dwl=net1["gwl"]))
         self.F("L.decoder", dec1["fwd"])
         self.F("L.x1_hat", lambda: check(lib.masic_subpix_to_nchw(dec1["sp"].data_ptr(), B, H // 2, W // 2, 16, 0, None, None,
-                                                                  1e-6, o["x1_hat"].data_ptr(), None, 0, T._s()), "subpix"))
+                                                                  1e-6, o["x1_hat"].data_ptr(), None, 0, 0, T._s()), "subpix"))
 
         # ================= right view =================
         Tm = torch.empty(B, 3, 3, device=dev, dtype=torch.float64)
@@ -563,7 +563,7 @@ class HSICTrainer:
                                                  None if dst_bf is None else dst_bf.data_ptr(),
                                                  0 if dst_bf is None else dst_bf.shape[3],
                                                  0 if dst_bf is None else dst_bf.shape[2], 0 if dst_bf is None else XOFF,
-                                                 T._s()), "masic_warp_perspective_fwd")
+                                                 0, T._s()), "masic_warp_perspective_fwd")
         self.F("mask_R", lambda: warp(None, mask_R, ch=1))
         # mask2weights (MASIC.py:472-506)
         mk = "mask2weights_unit.maskconv"
@@ -581,7 +581,7 @@ class HSICTrainer:
             n, c0, h, wd = in0.shape
             check(lib.masic_conv_small_nchw(in0.data_ptr(), c0, None if in1 is None else in1.data_ptr(),
                                             0 if in1 is None else in1.shape[1], n, h, wd, w.data_ptr(), int(tr), b.data_ptr(),
-                                            c_out, k, s, act, 0, None, None, 1e-6, out.data_ptr(), None, 0, 0, 0, T._s()),
+                                            c_out, k, s, act, 0, None, None, 1e-6, out.data_ptr(), None, 0, 0, 0, 0, T._s()),
                   "masic_conv_small_nchw")
 
         def mask_fwd():
@@ -601,7 +601,7 @@ class HSICTrainer:
         self.F("R.pre_conv", lambda: small(x1_warp, self.x2, pre_w, pre_b, 3, 5, 1, ACT_NONE, pc))
         self.F("R.pre_gdn", lambda: pre_gdn.fwd(pc, pg))
         self.F("R.pack", lambda: check(lib.masic_nchw_to_nhwc_bf16(pg.data_ptr(), B, 3, H, W, x2in_bf.data_ptr(), IMG_CP,
-                                                                   W + XPAD, XOFF, T._s()), "pack"))
+                                                                   W + XPAD, XOFF, 0, T._s()), "pack"))
         encB = self._encoder_pass("B", "encoder2", x2in_bf, pg, accumulate=False, share=None, need_dimg=True)
         y2, gy2 = encB["y"], encB["gy"]
         y2_abs, g_y2abs = self._z(B, h16, w16, M), self._z(B, h16, w16, M)
@@ -639,7 +639,7 @@ class HSICTrainer:
         aw, ab = self.param("decoder2.after_conv.weight"), self.param("decoder2.after_conv.bias")
         self.F("R.decoder", dec2["fwd"])
         self.F("R.core", lambda: check(lib.masic_subpix_to_nchw(dec2["sp"].data_ptr(), B, H // 2, W // 2, 16, 0, None, None, 1e-6,
-                                                                core.data_ptr(), None, 0, T._s()), "subpix"))
+                                                                core.data_ptr(), None, 0, 0, T._s()), "subpix"))
         self.F("R.after_gdn", lambda: after_gdn.fwd(core, ag))
         self.F("R.after_conv", lambda: small(ag, x1hw, aw, ab, 3, 5, 1, ACT_NONE, o["x2_hat"], tr=True))
         o["z1_hat"], o["lik_z1"], o["z2_hat"], o["lik_z2"] = hyp1["z_hat"], hyp1["z_lik"], hyp2["z_hat"], hyp2["z_lik"]
@@ -698,7 +698,7 @@ class HSICTrainer:
         self.Bk("R.encoder1(x1_hat_warp)", encC["bwd"])
         d_x1hw_b = self._z(B, 3, H, W, dtype=F32)
         self.Bk("C.dimg", lambda: check(lib.masic_subpix_to_nchw(encC["dimg"].data_ptr(), B, H // 2, W // 2, 16, 0, None, None,
-                                                                 1e-6, d_x1hw_b.data_ptr(), None, 0, T._s()), "subpix"))
+                                                                 1e-6, d_x1hw_b.data_ptr(), None, 0, 0, T._s()), "subpix"))
         d_x1hat_w = self._z(B, 3, H, W, dtype=F32)
         self.zero_each_step += [d_x1hat_w]
         self.Bk("warp_bwd", lambda: T.warp_bwd(d_x1hw_a, d_x1hw_b, Tm, d_x1hat_w))
@@ -710,7 +710,7 @@ class HSICTrainer:
         d_pc = self._z(B, 3, H, W, dtype=F32)
         pdw, pdb = self.grad("encoder2.pre_conv.weight"), self.grad("encoder2.pre_conv.bias")
         self.Bk("B.dimg", lambda: check(lib.masic_subpix_to_nchw(encB["dimg"].data_ptr(), B, H // 2, W // 2, 16, 0, None, None,
-                                                                 1e-6, d_pgt.data_ptr(), None, 0, T._s()), "subpix"))
+                                                                 1e-6, d_pgt.data_ptr(), None, 0, 0, T._s()), "subpix"))
         self.Bk("pre_gdn", lambda: pre_gdn.bwd(pc, d_pgt, d_pc))
         self.Bk("pre_conv", lambda: T.conv_small_bwd(x1_warp, self.x2, pre_w, False, 3, 5, 1, d_pc, dweight=pdw, dbias=pdb))
         # left view
@@ -875,7 +875,7 @@ class _Conv1:
     def bwd(self, skip_act: bool = True):
         Bn, _, Hh, Ww = self.img_nchw.shape
         check(self.tr.lib.masic_nchw_to_nhwc_bf16(self.img_nchw.data_ptr(), Bn, 3, Hh, Ww, self.img16.data_ptr(), 16, 0, 0,
-                                                  T._s()), "masic_nchw_to_nhwc_bf16")
+                                                  0, T._s()), "masic_nchw_to_nhwc_bf16")
         self.wg_plan.launch()
         self.dw.add_(self.dw16[:, :3])
         if self.dg_plan is not None:

@@ -22,6 +22,9 @@ from . import _lib
 from ._lib import MasicError, check
 from .convplan import ACT_RELU, ConvPlan, PackedConv
 
+F16 = _lib.FMT_F16              # inference runs on fp16 operands / activations (csrc/cvt16.cuh)
+ACT = _lib.act_dtype(F16)
+
 PIC_SIZE = 256          # test2_real.py:40 — the views are resized to 256x256 before the 128x128 patches are cut
 
 
@@ -99,7 +102,7 @@ class UDHEngine:
 
     def _build(self, sd):
         B, P, dev = self.B, self.P, self.dev
-        bf = torch.bfloat16
+        bf = ACT
         self.corners = torch.zeros(B, 4, 2, device=dev)
         self.x_in = torch.zeros(B, P, P, 16, dtype=bf, device=dev)         # channels 0/1 = the two patches, rest zero
         self.steps = []
@@ -115,7 +118,7 @@ class UDHEngine:
                     w, ci = wp, 16
                 y = torch.zeros(B, size, size, co, dtype=bf, device=dev)
                 pk = PackedConv(ksize=3, c_in=ci, c_out=co, n_tile=64 if co == 64 else 128, weight=w,
-                                bias=sd[f"cnn.{bi}.layers.{2 * li}.bias"])
+                                bias=sd[f"cnn.{bi}.layers.{2 * li}.bias"], f16=F16)
                 plan = ConvPlan(packed=pk, stride=1, x=x, out=y, act=ACT_RELU)
                 self.plans.append(plan)
                 self.steps.append((f"cnn.{bi}.conv{li}", plan.launch))
@@ -123,7 +126,7 @@ class UDHEngine:
             if bi < 3:                                                        # MaxPool2d(2, 2)
                 y = torch.zeros(B, size // 2, size // 2, cout, dtype=bf, device=dev)
                 self.steps.append((f"cnn.{bi}.maxpool", (lambda xi=x, yo=y, s=size, c=cout: check(
-                    self.lib.masic_maxpool2_nhwc_bf16(xi.data_ptr(), B, s, s, c, yo.data_ptr(), self._s()),
+                    self.lib.masic_maxpool2_nhwc_bf16(xi.data_ptr(), B, s, s, c, yo.data_ptr(), F16, self._s()),
                     "masic_maxpool2_nhwc_bf16"))))
                 x, size = y, size // 2
         self.feat = x                                                         # (B, P/8, P/8, 128) bf16
@@ -132,7 +135,7 @@ class UDHEngine:
         if tuple(w1.shape) != (1024, k1):
             raise MasicError(f"udh Net: fc.2.weight is {tuple(w1.shape)}, expected (1024, {k1})")
         self.w1 = torch.empty(1024, k1, dtype=bf, device=dev)
-        check(self.lib.masic_fc_pack_weights(w1.data_ptr(), 1024, 128, hw, self.w1.data_ptr(), self._s()), "masic_fc_pack_weights")
+        check(self.lib.masic_fc_pack_weights(w1.data_ptr(), 1024, 128, hw, self.w1.data_ptr(), F16, self._s()), "masic_fc_pack_weights")
         self.w2 = w2.to(bf).contiguous()
         self.b1, self.b2 = sd["fc.2.bias"], sd["fc.5.bias"]
         self.h1 = torch.zeros(B, 1024, dtype=bf, device=dev)
@@ -148,15 +151,15 @@ class UDHEngine:
         lib, B, P = self.lib, self.B, self.P
         # cat((a, b), dim=1) (model.py:96): the two patches are the two channels of the static NCHW input pair, packed
         # into the 16-channel-pitch NHWC bf16 buffer the first conv reads (channels 2..15 stay zero)
-        check(lib.masic_nchw_to_nhwc_bf16(self.ab.data_ptr(), B, 2, P, P, self.x_in.data_ptr(), 16, P, 0, self._s()),
+        check(lib.masic_nchw_to_nhwc_bf16(self.ab.data_ptr(), B, 2, P, P, self.x_in.data_ptr(), 16, P, 0, F16, self._s()),
               "masic_nchw_to_nhwc_bf16")
         for _, fn in self.steps:
             fn()
         k1 = self.w1.shape[1]
         check(lib.masic_fc_bf16(self.feat.data_ptr(), k1, self.w1.data_ptr(), self.b1.data_ptr(), B, k1, 1024, 1, None,
-                                self.h1.data_ptr(), 1024, self._s()), "masic_fc_bf16")
+                                self.h1.data_ptr(), 1024, F16, self._s()), "masic_fc_bf16")
         check(lib.masic_fc_bf16(self.h1.data_ptr(), 1024, self.w2.data_ptr(), self.b2.data_ptr(), B, 1024, 8, 0,
-                                self.delta.data_ptr(), None, 8, self._s()), "masic_fc_bf16")
+                                self.delta.data_ptr(), None, 8, F16, self._s()), "masic_fc_bf16")
         if img_hw is not None:
             check(lib.masic_homography_from_delta(self.corners.data_ptr(), self.delta.data_ptr(), B, int(shift_corners),
                                                   img_hw[0], img_hw[1], PIC_SIZE, PIC_SIZE, self.h.data_ptr(), self._s()),

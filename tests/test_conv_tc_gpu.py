@@ -29,9 +29,10 @@ def _names():
     return re.findall(r'^    "([a-z0-9_]+)": dict\(', src, flags=re.M)
 
 
+@pytest.mark.parametrize("fmt", ["bf16", "fp16"])      # the training step's format / the inference engines' format
 @pytest.mark.parametrize("name", _names())
-def test_conv_case(diag, name):
-    assert diag.run_case(name, **diag.CASES[name])
+def test_conv_case(diag, name, fmt):
+    assert diag.run_case(name, dtype=torch.float16 if fmt == "fp16" else torch.bfloat16, **diag.CASES[name])
 
 
 def test_plan_rejects_unsupported(diag):
@@ -48,32 +49,33 @@ def test_plan_rejects_unsupported(diag):
         ConvPlan(ksize=1, x=x, c_in=64, weight=w, c_out=64, n_tile=24, out=out)
 
 
-def _bf(t):
-    return t.to(torch.bfloat16).float()
+def _bf(t, dt=torch.bfloat16):
+    return t.to(dt).float()
 
 
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("c,h,w", [(32, 40, 24), (64, 33, 50), (96, 48, 40)])
-def test_residual_epilogue(diag, c, h, w):
+def test_residual_epilogue(diag, c, h, w, dt):
     """ResidualBlock / Enhancement_Block tail (layers.py:175-190, MASIC.py:156-164) fused into the conv epilogue:
     out = leaky_relu(conv3x3(x) + b) + res0 (+ res1 at a channel offset of a wider buffer)."""
     import torch.nn.functional as F
     from masic_b200.convplan import ACT_LEAKY, ConvPlan
     dev = torch.device("cuda:0")
     torch.manual_seed(c)
-    x = torch.randn(2, h, w, c, device=dev).to(torch.bfloat16)
-    r0 = torch.randn(2, h, w, c, device=dev).to(torch.bfloat16)
-    r1 = torch.randn(2, h, w, c + 32, device=dev).to(torch.bfloat16)
+    x = torch.randn(2, h, w, c, device=dev).to(dt)
+    r0 = torch.randn(2, h, w, c, device=dev).to(dt)
+    r1 = torch.randn(2, h, w, c + 32, device=dev).to(dt)
     wt = torch.randn(c, c, 3, 3, device=dev) / (9 * c) ** 0.5
     b = torch.randn(c, device=dev) * 0.1
-    ref = F.leaky_relu(F.conv2d(x.float().permute(0, 3, 1, 2), _bf(wt), b, padding=1), 0.01).permute(0, 2, 3, 1)
+    ref = F.leaky_relu(F.conv2d(x.float().permute(0, 3, 1, 2), _bf(wt, dt), b, padding=1), 0.01).permute(0, 2, 3, 1)
     for two in (False, True):
-        out = torch.zeros(2, h, w, c + 16, dtype=torch.bfloat16, device=dev)
+        out = torch.zeros(2, h, w, c + 16, dtype=dt, device=dev)
         ConvPlan(ksize=3, x=x, c_in=c, weight=wt, bias=b, c_out=c, n_tile=c, out=out, out_coff=16, act=ACT_LEAKY,
                  residual0=r0, residual1=r1 if two else None, res1_coff=32).launch()
         torch.cuda.synchronize()
         want = ref + r0.float() + (r1[..., 32:32 + c].float() if two else 0.0)
         got = out[..., 16:16 + c].float()
-        tol = 2.0 ** -8 * float(want.abs().max()) + 1e-3
+        tol = 2.0 ** (-8 if dt == torch.bfloat16 else -11) * float(want.abs().max()) + 1e-3
         assert float((got - want).abs().max()) <= tol
         assert float(out[..., :16].abs().max()) == 0.0            # the channel slice before out_coff is untouched
 

@@ -66,7 +66,7 @@ def test_gmm_nhwc_layout_equals_nchw(dev):
     _lib.check(_lib.load().masic_gmm_likelihood_fwd(yn.data_ptr(), sn.data_ptr(), mn.data_ptr(), wn.data_ptr(), 1, 1,
                                                     n, m, k, h * w, 0.11, y2.data_ptr(), l2.data_ptr(), None, 0,
                                                     yq.data_ptr(), 256, 64, None, 0, 0,
-                                                    torch.cuda.current_stream().cuda_stream), "gmm")
+                                                    0, torch.cuda.current_stream().cuda_stream), "gmm")
     assert torch.equal(y2, y_hat) and torch.equal(l2, lik)
     assert torch.equal(yq[..., 64:256].float(), nhwc(y_hat)) and float(yq[..., :64].abs().max()) == 0.0
 

@@ -94,12 +94,12 @@ def test_small_convs_against_torch(dev):
     gamma = OH.nonneg_init(0.1 * torch.eye(3) + torch.rand(3, 3) * 0.02)
     with torch.no_grad():
         ref = OH.gdn(pre(torch.cat((a, b), 1)), beta, gamma, False)
-    out_bf = torch.empty(2, 40, 56, 16, dtype=torch.bfloat16, device=dev)
+    out_bf = torch.empty(2, 40, 56, 16, dtype=ops.ACT16, device=dev)      # the inference engines' 16-bit format (fp16)
     out = torch.empty(2, 3, 40, 56, device=dev)
     ops.conv_small(a.to(dev), b.to(dev), pre.weight.to(dev), pre.bias.to(dev), ksize=5, stride=1, gdn=GDN_FWD,
                    beta=beta.to(dev), gamma=gamma.to(dev), out=out, out_bf16=out_bf)
     assert (out.cpu() - ref).abs().max() <= 2e-5
-    assert (out_bf[..., :3].float().permute(0, 3, 1, 2).cpu() - ref).abs().max() <= 8e-3
+    assert (out_bf[..., :3].float().permute(0, 3, 1, 2).cpu() - ref).abs().max() <= 1e-3
     # ConvTranspose2d(6, 3, 5, stride=1) == after_conv (MASIC.py:600)
     post = torch.nn.ConvTranspose2d(6, 3, 5, 1, 2)
     with torch.no_grad():
@@ -137,7 +137,7 @@ def test_layout_packs_round_trip(dev):
     from masic_b200 import ops
     x = torch.rand(2, 3, 17, 23, device=dev)
     p = ops.nchw_to_nhwc_bf16(x, 16)
-    assert torch.equal(p[..., :3].permute(0, 3, 1, 2).float(), x.to(torch.bfloat16).float())
+    assert p.dtype == ops.ACT16 and torch.equal(p[..., :3].permute(0, 3, 1, 2).float(), x.to(ops.ACT16).float())
     assert float(p[..., 3:].abs().max()) == 0
     y = torch.rand(2, 9, 11, 200, device=dev)
     assert torch.equal(ops.nhwc_to_nchw_f32(y, 192), y[..., :192].permute(0, 3, 1, 2))

@@ -21,11 +21,12 @@ from masic_b200.convplan import (ACT_LEAKY, ACT_NONE, ACT_RELU, CONV, DECONV_S2,
                                  GDN_FWD, GDN_INV, GDN_NONE, MASK_A_5x5, ConvPlan, conv_direct, gdn_prepare)
 
 dev = torch.device("cuda:0")
+DT = torch.bfloat16       # 16-bit format of the case being run (run_case(..., dtype=...) sets it): bf16 or fp16
 
 
 def ref_torch(x_nhwc, c_in, in_coff, w, transposed, k, stride, tap_mask, bias):
     x = x_nhwc[..., in_coff:in_coff + c_in].float().permute(0, 3, 1, 2).contiguous()
-    wq = w.to(torch.bfloat16).float()
+    wq = w.to(DT).float()
     if tap_mask:
         m = torch.tensor([(tap_mask >> i) & 1 for i in range(k * k)], device=w.device, dtype=torch.float32).view(1, 1, k, k)
         wq = wq * m
@@ -46,13 +47,16 @@ def act_ref(y, a):
 
 def run_case(name, *, kind=CONV, k, stride=1, tap_mask=0, n=1, h, w, c_in, c_out, n_tile, in_cp=None,
              in_coff=0, out_cp=None, out_coff=0, out_fp32=False, act=ACT_NONE, gdn=GDN_NONE, bias=True,
-             rowscale=False, transposed=None, seed=0):
+             rowscale=False, transposed=None, seed=0, dtype=torch.bfloat16):
+    global DT
+    DT = dtype
+    name = f"{name}/{'fp16' if dtype == torch.float16 else 'bf16'}"
     torch.manual_seed(seed)
     if kind in (3, 4):
         return run_xfold4(name, n=n, h=h, w=w, c_out=c_out, n_tile=n_tile, gdn=gdn, kind=kind)
     transposed = (kind != CONV) if transposed is None else transposed
     in_cp = in_cp or max(c_in + in_coff, 8)
-    x = (torch.randn(n, h, w, in_cp, device=dev) * 1.0).to(torch.bfloat16)
+    x = (torch.randn(n, h, w, in_cp, device=dev) * 1.0).to(DT)
     wshape = (c_in, c_out, k, k) if transposed else (c_out, c_in, k, k)
     wt = torch.randn(*wshape, device=dev) / (c_in * k * k) ** 0.5
     b = torch.randn(c_out, device=dev) * 0.1 if bias else None
@@ -65,7 +69,7 @@ def run_case(name, *, kind=CONV, k, stride=1, tap_mask=0, n=1, h, w, c_in, c_out
     eff = 4 * c_out if kind == DECONV_S2_SUBPIX else c_out
     c_out_pad = -(-eff // n_tile) * n_tile
     out_cp = out_cp or (c_out_pad + out_coff)
-    out = torch.full((n, ho, wo, out_cp), 777.0, device=dev, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    out = torch.full((n, ho, wo, out_cp), 777.0, device=dev, dtype=torch.float32 if out_fp32 else DT)
     n_nt = c_out_pad // n_tile
     acts = [act] * n_nt if isinstance(act, int) else act
     gb = gg = None
@@ -94,7 +98,7 @@ def run_case(name, *, kind=CONV, k, stride=1, tap_mask=0, n=1, h, w, c_in, c_out
         yd = conv_direct(x, c_in, wt, transposed=transposed, ksize=k, stride=stride if kind == CONV else 2,
                          tap_mask=tap_mask, bias=b, in_coff=in_coff)
     if gdn:
-        beta_p, g32, g16 = gdn_prepare(gb, gg)
+        beta_p, g32, g16 = gdn_prepare(gb, gg, f16=int(DT == torch.float16))
         norm = torch.einsum("nhwj,ij->nhwi", y * y, g32) + beta_p
         y = y * (torch.rsqrt(norm) if gdn == GDN_FWD else torch.sqrt(norm))
     else:
@@ -107,6 +111,8 @@ def run_case(name, *, kind=CONV, k, stride=1, tap_mask=0, n=1, h, w, c_in, c_out
     scale = y.abs().max().item() + 1e-9
     maxerr = err.max().item()
     tol = (3e-2 if gdn else 1.2e-2) * scale if not out_fp32 else (3e-2 if gdn else 2e-3) * scale
+    if DT == torch.float16:         # 11 significant bits instead of 8: the output rounding and the GDN operands are 8x finer
+        tol = ((4e-3 if gdn else 1.5e-3) if not out_fp32 else (4e-3 if gdn else 1e-3)) * scale
     ok = bool(torch.isfinite(got).all()) and maxerr <= tol
     msg = f"[{name}] {'OK ' if ok else 'BAD'} maxerr={maxerr:.4g} scale={scale:.4g} tol={tol:.3g}"
     if yd is not None and not gdn and rs is None:
@@ -137,27 +143,28 @@ def run_xfold4(name, *, n, h, w, c_out, n_tile, gdn, kind=3):
     img = torch.rand(n, 3, h, w, device=dev)
     wt = torch.randn(c_out, 3, 5, 5, device=dev) / 75 ** 0.5
     b = torch.randn(c_out, device=dev) * 0.1
-    xw = torch.zeros(n, h, w + L.IMG_XPAD, cp, device=dev, dtype=torch.bfloat16)
+    xw = torch.zeros(n, h, w + L.IMG_XPAD, cp, device=dev, dtype=DT)
     L.check(L.load().masic_nchw_to_nhwc_bf16(img.data_ptr(), n, 3, h, w, xw.data_ptr(), cp, w + L.IMG_XPAD, L.IMG_XOFF,
-                                             torch.cuda.current_stream().cuda_stream), "pack")
-    out = torch.zeros(n, h // 2, w // 2, c_out, device=dev, dtype=torch.bfloat16)
+                                             int(DT == torch.float16), torch.cuda.current_stream().cuda_stream), "pack")
+    out = torch.zeros(n, h // 2, w // 2, c_out, device=dev, dtype=DT)
     gb = torch.sqrt(torch.rand(c_out, device=dev) * 0.5 + 0.75)
     gg = torch.sqrt(torch.rand(c_out, c_out, device=dev) * 0.02 + 0.1 * torch.eye(c_out, device=dev))
     plan = ConvPlan(kind=kind, ksize=5, stride=2, x=xw, c_in=64, weight=wt, bias=b, c_out=c_out, n_tile=n_tile, out=out,
                     gdn=gdn, gdn_beta=gb, gdn_gamma=gg)
     plan.launch()
     torch.cuda.synchronize()
-    y = F.conv2d(img.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float(), b, stride=2, padding=2).permute(0, 2, 3, 1)
+    y = F.conv2d(img.to(DT).float(), wt.to(DT).float(), b, stride=2, padding=2).permute(0, 2, 3, 1)
     if gdn:
-        beta_p, g32, _ = gdn_prepare(gb, gg)
+        beta_p, g32, _ = gdn_prepare(gb, gg, f16=int(DT == torch.float16))
         norm = torch.einsum("nhwj,ij->nhwi", y * y, g32) + beta_p
         y = y * torch.rsqrt(norm)
     err = (out.float() - y).abs()
     scale = y.abs().max().item()
-    ok = bool(torch.isfinite(out.float()).all()) and err.max().item() <= 3e-2 * scale
+    xtol = (4e-3 if DT == torch.float16 else 3e-2) * scale
+    ok = bool(torch.isfinite(out.float()).all()) and err.max().item() <= xtol
     print(f"[{name}] {'OK ' if ok else 'BAD'} maxerr={err.max().item():.4g} scale={scale:.4g} work={plan.work_items}", flush=True)
     if not ok:
-        bad = (err > 3e-2 * scale).nonzero()
+        bad = (err > xtol).nonzero()
         print("    first bad", bad[:6].tolist(), "count", bad.shape[0], "of", err.numel())
         xs = sorted(set(bad[:, 2].tolist()))
         print("    bad x columns:", xs[:20], " bad y rows:", sorted(set(bad[:, 1].tolist()))[:20])
@@ -202,6 +209,7 @@ if __name__ == "__main__":
         if a.only and a.only != name:
             continue
         res[name] = run_case(name, **kw)
+        res[name + "/fp16"] = run_case(name, dtype=torch.float16, **kw)
     bad = [k for k, v in res.items() if not v]
     print(f"SUMMARY {len(res) - len(bad)}/{len(res)} ok; bad={bad}", flush=True)
     sys.exit(1 if bad else 0)

@@ -64,10 +64,10 @@ def build(name, kind=CONV, k=1, stride=1, tap_mask=0, h=0, w=0, c_in=0, c_out=0,
     torch.manual_seed(0)
     in_cp = in_cp or c_in
     if kind in (3, 4):
-        x = torch.randn(1, h, w + 8, 16 if kind == 3 else 8, device=dev).to(torch.bfloat16)
+        x = torch.randn(1, h, w + 8, 16 if kind == 3 else 8, device=dev).to(torch.float16)
         wt = torch.randn(c_out, 3, 5, 5, device=dev) / 75 ** 0.5
     else:
-        x = torch.randn(1, h, w, in_cp, device=dev).to(torch.bfloat16)
+        x = torch.randn(1, h, w, in_cp, device=dev).to(torch.float16)
     transposed = kind not in (CONV, 3, 4)
     if kind not in (3, 4):
         wt = torch.randn(*((c_in, c_out, k, k) if transposed else (c_out, c_in, k, k)), device=dev) / (c_in * k * k) ** 0.5
@@ -75,7 +75,7 @@ def build(name, kind=CONV, k=1, stride=1, tap_mask=0, h=0, w=0, c_in=0, c_out=0,
     ho, wo = (2 * h, 2 * w) if kind == DECONV_S2 else ((h // 2, w // 2) if stride == 2 else (h, w))
     eff = 4 * c_out if kind == DECONV_S2_SUBPIX else c_out
     c_out_pad = -(-eff // n_tile) * n_tile
-    out = torch.empty(1, ho, wo, c_out_pad, device=dev, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    out = torch.empty(1, ho, wo, c_out_pad, device=dev, dtype=torch.float32 if out_fp32 else torch.float16)
     gb = gg = None
     if gdn:
         gb = torch.ones(c_out, device=dev)

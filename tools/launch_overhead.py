@@ -12,9 +12,9 @@ dev = torch.device("cuda:0")
 
 
 def plan(h, w, cin, cout, n_tile):
-    x = torch.randn(1, h, w, cin, device=dev).to(torch.bfloat16)
+    x = torch.randn(1, h, w, cin, device=dev).to(torch.float16)
     wt = torch.randn(cout, cin, 1, 1, device=dev) * 0.05
-    out = torch.empty(1, h, w, cout, device=dev, dtype=torch.bfloat16)
+    out = torch.empty(1, h, w, cout, device=dev, dtype=torch.float16)
     return ConvPlan(ksize=1, x=x, c_in=cin, weight=wt, bias=torch.zeros(cout, device=dev), c_out=cout, n_tile=n_tile, out=out)
 
 
