@@ -106,6 +106,7 @@ struct KParams {
   int nt_out_img[32];              // and output image offset
   uint32_t idesc;
   int f16;         // 16-bit operand / activation format: 0 = bf16, 1 = fp16 (cvt16.cuh)
+  int gdn2;        // 1: EPI_GDN2 (two epilogue teams, resident weights, one tile per item)
   int debug;       // timing experiments only (results are garbage): bit0 skip A loads, bit1 skip B loads, bit2 skip stores,
                    // bit3 skip the GDN norm MMA, bit4 skip the whole epilogue
 };
@@ -241,7 +242,12 @@ __device__ __forceinline__ Item next_item(const KParams& p, Cursor& c, int u_end
 
 // EPI selects the epilogue at compile time so that each variant gets its own register allocation (the GDN epilogue
 // is issue- and latency-bound: a spill there costs ~40 % on the 608x1088 layers)
-constexpr int EPI_PLAIN = 0, EPI_GDN = 1, EPI_RES = 2;
+constexpr int EPI_PLAIN = 0, EPI_GDN = 1, EPI_RES = 2, EPI_GDN2 = 3;
+// EPI_GDN2 (layers whose whole weight set stays in shared memory, i.e. g_a_conv1): one tile per work item, TWO epilogue
+// teams of 8 warps that alternate over the items, each with its own accumulator, its own norm accumulator (the norm
+// MMA no longer overwrites x, so nothing has to stay in registers across it) and its own A2 / staging blocks.  The
+// per-tile chain TMEM load -> x^2 -> barrier -> norm MMA -> wait -> TMEM load -> rsqrt -> staging -> TMA store is
+// latency-bound (2.7 us per tile with all 16 warps in lock step); two tiles in flight hide half of it.
 
 template <bool CG2, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -283,18 +289,18 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(sMisc + MISC_ACC_FULL + 8 * i, p.pair);
-      mbar_init(sMisc + MISC_ACC_EMPTY + 8 * i, CG2 ? 2 * EPI_THREADS : EPI_THREADS);
+      mbar_init(sMisc + MISC_ACC_EMPTY + 8 * i, EPI == EPI_GDN2 ? 256 : (CG2 ? 2 * EPI_THREADS : EPI_THREADS));
     }
     mbar_init(sMisc + MISC_GDN_BAR, 1);
     mbar_init(sMisc + MISC_G_FULL, 1);
-    mbar_init(sMisc + MISC_A2_READY, 2);
+    mbar_init(sMisc + MISC_A2_READY, EPI == EPI_GDN2 ? 1 : 2);        // EPI_GDN2: the second team's norm-MMA barrier
     fence_mbar_init();
   }
   if (warp == 3) {
     if (CG2) { tmem_alloc_cg2(sMisc + MISC_TMEM_PTR, TMEM_COLS); tmem_relinquish_cg2(); }
     else { tmem_alloc(sMisc + MISC_TMEM_PTR, TMEM_COLS); tmem_relinquish(); }
   }
-  if (EPI == EPI_GDN && threadIdx.x >= 128) {       // the single n-tile's bias / beta' stay in smem for the whole kernel
+  if ((EPI == EPI_GDN || EPI == EPI_GDN2) && threadIdx.x >= 128) {       // the single n-tile's bias / beta' stay in smem for the whole kernel
     float* bs = reinterpret_cast<float*>(smem_gen + p.smem_misc_off + MISC_BIAS);
     float* be = reinterpret_cast<float*>(smem_gen + p.smem_misc_off + MISC_BETA);
     const int i = threadIdx.x - 128;
@@ -354,7 +360,7 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     }
   } else if (warp == 1 && !free_run) {
     // ===================== B producer: weight k-blocks (+ gamma once) =====================
-    if (EPI == EPI_GDN && elect_one()) {
+    if ((EPI == EPI_GDN || EPI == EPI_GDN2) && elect_one()) {
       tma_prefetch_desc(&p.tmG);
       if (CG2) {          // each CTA holds the 64 N-rows of gamma' it feeds to the pair's norm MMA
         if (rank == 0) mbar_expect_tx(sMisc + MISC_G_FULL, 2 * STAGE_BLK_BYTES);
@@ -428,7 +434,7 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
       const int buf = n_item & 1;
       mbar_wait(sMisc + MISC_ACC_EMPTY + 8 * buf, ((n_item >> 1) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t d0 = tmem_base + buf * 256 + slot * 128;
+      const uint32_t d0 = tmem_base + (EPI == EPI_GDN2 ? buf * 128 : buf * 256 + slot * 128);
       const bool active = slot < it.nslots;                // an item may fill only slot 0
       uint32_t acc = 0;                                    // 0 for the first MMA group of the item
       const int i0 = p.var[it.var].strip_off, i1 = i0 + p.var[it.var].n_strips;
@@ -472,6 +478,142 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
         if (++sa == n_sa) { sa = 0; pa ^= 1; }
       }
     }
+  } else if (EPI == EPI_GDN2 && warp >= 4) {
+    // ===================== epilogue, two teams (see EPI_GDN2 above) =====================
+    // TMEM columns: accumulator of team T at 128 T, its norm at 256 + 128 T.  Team T = items with (n_item & 1) == T.
+    // Inside a team: warp quarter ew reads TMEM lanes 32 ew .. 32 ew + 31 (= tile rows), half hf owns channels
+    // 64 hf .. 64 hf + 63 = SWIZZLE_128B block hf of the team's two A2 / staging blocks.
+    const int team = (warp - 4) >> 3;
+    const int hf = ((warp - 4) >> 2) & 1;
+    const int ew = warp & 3;
+    const int t = ew * 32 + lane;
+    const uint32_t lane_sel = static_cast<uint32_t>(ew * 32) << 16;
+    const uint32_t tbar = 1 + team;                               // named barrier of the team (256 threads)
+    const bool leader = (t == 0 && hf == 0);
+    const uint32_t sbuf = sStage + team * 2 * STAGE_BLK_BYTES;    // blocks 2T, 2T+1
+    const uint32_t bias_s = sMisc + MISC_BIAS, beta_s = sMisc + MISC_BETA;
+    const uint32_t gbar = sMisc + (team ? MISC_A2_READY : MISC_GDN_BAR);
+    const bool fwd = (p.gdn == MASIC_GDN_FWD);
+    const bool nostore = (p.debug & 4) != 0;
+    const uint32_t acc_addr = tmem_base + lane_sel + team * 128;
+    const uint32_t nrm_addr = tmem_base + lane_sel + 256 + team * 128;
+    const uint32_t arow = sbuf + hf * STAGE_BLK_BYTES + t * 128;
+    uint32_t gpar = 0;
+    if (hf == 0 && ew == 0) mbar_wait(sMisc + MISC_G_FULL, 0);   // gamma' resident: the warp that issues the team's norm MMAs waits
+    int n_item = 0;
+    for (Cursor cur = cursor_init(p, u_begin); cur.u < u_end; ++n_item) {
+      const Item it = next_item<CG2>(p, cur, u_end, rank);
+      if ((n_item & 1) != team) continue;
+      const Variant& v = p.var[it.var];
+      mbar_wait(sMisc + MISC_ACC_FULL + 8 * team, (n_item >> 1) & 1);
+      tc_fence_after();
+      float rs = 1.0f;
+      if (p.rowscale) {
+        const int y = it.y0[0] + (t >> 3), x = it.x0[0] + (t & 7);
+        if (y < p.rs_H && x < p.rs_W)
+          rs = __ldg(p.rowscale + (static_cast<size_t>(it.n[0] * p.rs_H + y) * p.rs_W + x) * p.rs_stride + p.rs_off);
+      }
+      if (leader) tma_store_wait_read<0>();                       // the team's previous output tile has left its staging blocks
+      named_bar_sync(tbar, 256);
+      // ---- pass 1: A2[:, 64 hf .. +63] = 16-bit((acc + bias)^2)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int cb = hf * 64 + c * 32;
+        uint32_t r[32];
+        tmem_ld16(acc_addr + cb, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+        tmem_ld16(acc_addr + cb + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+        tmem_ld_wait();
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          uint64_t xx[4];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            uint64_t b0, b1;
+            ld_shared_p2(bias_s + (cb + 8 * c8 + 4 * q) * 4, b0, b1);
+            xx[2 * q] = add2(pk2u(r[8 * c8 + 4 * q], r[8 * c8 + 4 * q + 1]), b0);
+            xx[2 * q + 1] = add2(pk2u(r[8 * c8 + 4 * q + 2], r[8 * c8 + 4 * q + 3]), b1);
+          }
+          st_shared_v4(arow + (((4 * c + c8) ^ (t & 7)) << 4), pack16x2_p(mul2(xx[0], xx[0]), f16),
+                       pack16x2_p(mul2(xx[1], xx[1]), f16), pack16x2_p(mul2(xx[2], xx[2]), f16),
+                       pack16x2_p(mul2(xx[3], xx[3]), f16));
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      named_bar_sync(tbar, 256);
+      if (!(p.debug & 8)) {
+        if (hf == 0 && ew == 0) {                                 // one warp of the team; one elected lane issues the 8 MMAs
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t d2 = tmem_base + 256 + team * 128;
+            const uint64_t dh = umma_desc_sw128(0);
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb) {
+              const uint64_t a2 = dh | (((sbuf + kb * STAGE_BLK_BYTES) & 0x3FFFFu) >> 4);
+              const uint64_t g2 = dh | (((sG + kb * STAGE_BLK_BYTES) & 0x3FFFFu) >> 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16(d2, a2 + 2 * k, g2 + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
+            }
+            umma_commit(gbar);
+          }
+          __syncwarp();
+        }
+        mbar_wait(gbar, gpar);
+        gpar ^= 1;
+      }
+      tc_fence_after();
+      // ---- pass 2: out = (acc + bias) * rsqrt(beta' + norm)   (IGDN: * sqrt); the staging rows re-use the A2 rows
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int cb = hf * 64 + c * 32;
+        uint32_t r[32], nn[32];
+        tmem_ld16(acc_addr + cb, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+        tmem_ld16(acc_addr + cb + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+        tmem_ld16(nrm_addr + cb, *reinterpret_cast<uint32_t(*)[16]>(&nn[0]));
+        tmem_ld16(nrm_addr + cb + 16, *reinterpret_cast<uint32_t(*)[16]>(&nn[16]));
+        tmem_ld_wait();
+        if (c == 1) {                                             // last TMEM read of this item: the MMA warp may refill the accumulator
+          tc_fence_before();
+          mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * team);
+        }
+        const uint64_t rs2 = pk2(rs, rs);
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          uint64_t o[4];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            uint64_t b0, b1, e0, e1;
+            ld_shared_p2(bias_s + (cb + 8 * c8 + 4 * q) * 4, b0, b1);
+            ld_shared_p2(beta_s + (cb + 8 * c8 + 4 * q) * 4, e0, e1);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int i0 = 8 * c8 + 4 * q + 2 * e;
+              const uint64_t x = add2(pk2u(r[i0], r[i0 + 1]), e ? b1 : b0);
+              const uint64_t nrm = add2(pk2u(nn[i0], nn[i0 + 1]), e ? e1 : e0);
+              float n0, n1;
+              upk2(nrm, n0, n1);
+              uint64_t f = pk2(rsqrt_approx(n0), rsqrt_approx(n1));
+              if (!fwd) f = mul2(f, nrm);
+              uint64_t y = mul2(x, f);
+              if (p.rowscale) y = mul2(y, rs2);
+              o[2 * q + e] = y;
+            }
+          }
+          st_shared_v4(arow + (((4 * c + c8) ^ (t & 7)) << 4), pack16x2_p(o[0], f16), pack16x2_p(o[1], f16),
+                       pack16x2_p(o[2], f16), pack16x2_p(o[3], f16));
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(tbar, 256);
+      if (leader && !nostore && it.valid[0]) {
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+          tma_store_5d(&p.tmO, sbuf + kb * STAGE_BLK_BYTES, p.out_coff + v.out_c0 + it.nt * p.n_tile + 64 * kb, it.x0[0],
+                       v.out_p2, it.y0[0], it.n[0]);
+        tma_store_commit();
+      }
+    }
+    if (leader) tma_store_wait_all<0>();
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> regs -> smem -> TMA store =====================
     // Four groups of 4 warps (16 warps keep the 4 schedulers busy while tcgen05.ld / MUFU / st.shared latencies
@@ -1081,6 +1223,11 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
 
   // work items: pairs of tiles sharing every weight k-block when two accumulators fit 256 TMEM columns
   kp.pair = (d.n_tile <= 128) ? 2 : 1;
+  // EPI_GDN2: fused GDN on a layer whose whole weight set (<= 6 k-blocks of 16 KB: g_a_conv1's five) stays in shared
+  // memory next to gamma', four staging blocks and a double-buffered strip ring
+  kp.gdn2 = d.gdn && !kp.cg2 && kp.n_var == 1 && kp.var[0].n_bops <= 6;
+  { const char* e = getenv("MASIC_CONV_GDN2"); if (e && atoi(e) == 0) kp.gdn2 = 0; }
+  if (kp.gdn2) kp.pair = 1;
   kp.n_spatial = kp.tiles_x * kp.tiles_y * kp.n_img;
   kp.n_tiles_total = kp.n_spatial * kp.n_var * kp.n_ntiles;
 
@@ -1090,15 +1237,16 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   const int a_stage_bytes = kp.pair * kp.strip_bytes;
   // staging: with GDN two blocks (together the A2 operand of the norm MMA, then the output tile);
   // otherwise two per epilogue group so a block's TMA store drains behind the next block
-  const int n_stage_blk = d.gdn ? 2 : 4;
+  const int n_stage_blk = (d.gdn && !kp.gdn2) ? 2 : 4;
   const int gamma_bytes = d.gdn ? (kp.cg2 ? STAGE_BLK_BYTES : 2 * STAGE_BLK_BYTES) : 0;
   const int fixed = gamma_bytes + n_stage_blk * STAGE_BLK_BYTES + MISC_BYTES + 1024 /*align*/;
   const int budget = 227 * 1024 - fixed;                      // ring bytes
   int sa = 2, sb = 2;
   // resident weights: single program, single n-tile, and the whole k-block list fits next to a double-buffered A ring
   const int n_bops0 = kp.var[0].n_bops;
-  kp.b_resident = !kp.cg2 && kp.n_var == 1 && kp.n_ntiles == 1 && d.n_tile <= 64 &&
+  kp.b_resident = !kp.cg2 && kp.n_var == 1 && kp.n_ntiles == 1 && (d.n_tile <= 64 || kp.gdn2) &&
                   2 * a_stage_bytes + n_bops0 * kp.b_stage_bytes <= budget;
+  if (kp.gdn2 && !kp.b_resident) { delete pl; return MASIC_EINVAL; }
   { const char* e = getenv("MASIC_CONV_BRES"); if (e && atoi(e) == 0) kp.b_resident = 0; }
   if (kp.b_resident) sb = n_bops0;
   if (sa * a_stage_bytes + sb * kp.b_stage_bytes > budget) { delete pl; return MASIC_EINVAL; }
@@ -1196,10 +1344,11 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
 
   static bool attr_set = false;
   if (!attr_set) {
-    const void* fns[6] = {(const void*)conv_tc_kernel<false, EPI_PLAIN>, (const void*)conv_tc_kernel<false, EPI_GDN>,
+    const void* fns[7] = {(const void*)conv_tc_kernel<false, EPI_PLAIN>, (const void*)conv_tc_kernel<false, EPI_GDN>,
                           (const void*)conv_tc_kernel<false, EPI_RES>, (const void*)conv_tc_kernel<true, EPI_PLAIN>,
-                          (const void*)conv_tc_kernel<true, EPI_GDN>, (const void*)conv_tc_kernel<true, EPI_RES>};
-    for (int i = 0; i < 6 && ce == cudaSuccess; ++i)
+                          (const void*)conv_tc_kernel<true, EPI_GDN>, (const void*)conv_tc_kernel<true, EPI_RES>,
+                          (const void*)conv_tc_kernel<false, EPI_GDN2>};
+    for (int i = 0; i < 7 && ce == cudaSuccess; ++i)
       ce = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (ce != cudaSuccess) { delete pl; return (int)ce; }
     attr_set = true;
@@ -1235,6 +1384,7 @@ extern "C" int masic_conv_plan_launch(const MasicConvPlan* pl, void* stream) {
     if (epi == EPI_RES) return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, EPI_RES>, pl->kp);
     return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, EPI_PLAIN>, pl->kp);
   }
+  if (epi == EPI_GDN && pl->kp.gdn2) return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, EPI_GDN2>, pl->kp);
   if (epi == EPI_GDN) return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, EPI_GDN>, pl->kp);
   if (epi == EPI_RES) return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, EPI_RES>, pl->kp);
   return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, EPI_PLAIN>, pl->kp);

@@ -20,11 +20,20 @@ def test_trained_regime_psnr_and_bpp_parity():
     steps, psnr_train = train_to_psnr(net, dev, target_db=27.5, max_steps=1200, size=(256, 256), lr=3e-4, lmbda=0.05,
                                       log=print)
     assert psnr_train >= 25.0, f"training reached only {psnr_train:.2f} dB in {steps} steps"
+    # the training step's atomics make every run a little different: top up (smaller steps) until the EVAL-mode
+    # reconstructions of the comparison pair are in the regime too
+    for extra in range(4):
+        r = compare_with_oracle(net, dev, 256, 384)
+        if min(r["psnr1_oracle"], r["psnr2_oracle"]) >= 25.0:
+            break
+        more, psnr_train = train_to_psnr(net, dev, target_db=99.0, max_steps=150, size=(256, 256), lr=1e-4, lmbda=0.05,
+                                         seed=10 + extra, log=print)
+        steps += more
     for (h, w) in ((256, 384), (512, 512)):
         r = compare_with_oracle(net, dev, h, w)
         r.update(train_steps=steps, train_psnr_db=psnr_train, tol=dict(dbpp_rel=BPP_RTOL, dpsnr_db=PSNR_ATOL))
         _record(f"trained_regime_{h}x{w}", **r)
         print(r)
-        assert max(r["psnr1_oracle"], r["psnr2_oracle"]) >= 25.0 and min(r["psnr1_oracle"], r["psnr2_oracle"]) >= 22.0, r   # not vacuous
+        assert min(r["psnr1_oracle"], r["psnr2_oracle"]) >= 24.0, r     # the comparison is not vacuous
         assert r["dpsnr1_db"] <= PSNR_ATOL and r["dpsnr2_db"] <= PSNR_ATOL, r
         assert r["dbpp_rel"] <= BPP_RTOL, r
