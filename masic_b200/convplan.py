@@ -84,7 +84,8 @@ class PackedConv:
             self.bias = b
         self.beta = self.gamma16 = None
         if gdn != GDN_NONE:
-            self.beta, _, self.gamma16 = gdn_prepare(gdn_beta, gdn_gamma, f16=self.f16)
+            # the norm MMA of the fused GDN runs on bf16 operands in both formats (conv_tc.cu: pack_norm_operand)
+            self.beta, _, self.gamma16 = gdn_prepare(gdn_beta, gdn_gamma, f16=FMT_BF16)
 
     def repack(self, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> None:
         """Re-pack changed weights IN PLACE (same device buffers, so bound plans stay valid): the training step

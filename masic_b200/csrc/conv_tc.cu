@@ -105,8 +105,10 @@ struct KParams {
   int nt_out_c[32];                // output channel position (default nt * n_tile)
   int nt_out_img[32];              // and output image offset
   uint32_t idesc;
+  uint32_t idesc_norm;   // the GDN norm MMA always runs on bf16 operands (x^2 rounded on the ALU pipe, gamma' bf16)
   int f16;         // 16-bit operand / activation format: 0 = bf16, 1 = fp16 (cvt16.cuh)
   int gdn2;        // 1: EPI_GDN2 (two epilogue teams, resident weights, one tile per item)
+  int gdnt;        // 1: EPI_GDNT (one epilogue team per accumulator slot, norm in place)
   int debug;       // timing experiments only (results are garbage): bit0 skip A loads, bit1 skip B loads, bit2 skip stores,
                    // bit3 skip the GDN norm MMA, bit4 skip the whole epilogue
 };
@@ -175,6 +177,23 @@ __device__ __forceinline__ uint32_t pack16x2_p(uint64_t v, int f16) {   // 16-bi
   upk2(v, lo, hi);
   return pack16x2(lo, hi, f16);
 }
+// Operand of the GDN norm MMA: bf16(x^2) of two non-negative fp32 values WITHOUT the XU pipe — round half up in the
+// integer domain and byte-permute the two upper halves together (3 ALU instructions; an F2FP pack costs ~15 cycles of
+// the XU pipe per warp, the pipe the GDN epilogues are bound by).  The norm beta' + gamma' x^2 tolerates bf16 operands:
+// they contribute 3e-5 of the 1e-4 rms deviation of the fp16 engine's latents (tools/noise_analysis.py).
+__device__ __forceinline__ uint32_t pack_bf16x2_alu(uint64_t v) {
+  uint32_t lo, hi, r;
+  upk2u(v, lo, hi);
+  lo += 0x8000u;
+  hi += 0x8000u;
+  asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_norm_operand(uint64_t sq) {     // the A2 operand is bf16 in both formats
+  if (F16) return pack_bf16x2_alu(sq);
+  return pack16x2_p(sq, 0);
+}
 __device__ __forceinline__ float rsqrt_approx(float x) {           // one MUFU.RSQ (rsqrtf() adds a denormal fix-up path)
   float r;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -242,14 +261,20 @@ __device__ __forceinline__ Item next_item(const KParams& p, Cursor& c, int u_end
 
 // EPI selects the epilogue at compile time so that each variant gets its own register allocation (the GDN epilogue
 // is issue- and latency-bound: a spill there costs ~40 % on the 608x1088 layers)
-constexpr int EPI_PLAIN = 0, EPI_GDN = 1, EPI_RES = 2, EPI_GDN2 = 3;
+constexpr int EPI_PLAIN = 0, EPI_GDN = 1, EPI_RES = 2, EPI_GDN2 = 3, EPI_GDNT = 4;
+// EPI_GDNT ("teams"): the fused GDN epilogue of EPI_GDN with the item's two tiles drained CONCURRENTLY, one team of 8
+// warps per accumulator slot (64 channels per thread instead of 32), each team with its own A2 / staging blocks and
+// its own norm-MMA barrier; the norm is still written in place over the accumulator, so a thread keeps 64 fp32 x values
+// in registers across the MMA: the four epilogue warpgroups raise their register budget to 104 with setmaxnreg and the
+// role warpgroup drops to 64 — the CTA pool must balance exactly ((96 - 64) x 128 = (104 - 96) x 512 registers), or the
+// TRY_ALLOC of the last epilogue warpgroup spins forever.  The per-tile chain is latency-bound, so two tiles in flight nearly halve it.
 // EPI_GDN2 (layers whose whole weight set stays in shared memory, i.e. g_a_conv1): one tile per work item, TWO epilogue
 // teams of 8 warps that alternate over the items, each with its own accumulator, its own norm accumulator (the norm
 // MMA no longer overwrites x, so nothing has to stay in registers across it) and its own A2 / staging blocks.  The
 // per-tile chain TMEM load -> x^2 -> barrier -> norm MMA -> wait -> TMEM load -> rsqrt -> staging -> TMA store is
 // latency-bound (2.7 us per tile with all 16 warps in lock step); two tiles in flight hide half of it.
 
-template <bool CG2, int EPI>
+template <bool CG2, int EPI, bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -268,7 +293,10 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
   // depend on blockIdx and kernel parameters) on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int f16 = p.f16;
+  // the 16-bit format is a template parameter: a run-time select costs a second (predicated-off, but issued) F2FP per
+  // conversion, and F2FP shares the XU pipe with MUFU at ~15 cycles per warp instruction — the pipe that bounds the
+  // GDN epilogues (ncu: xu 85 % busy on g_a_conv1)
+  constexpr int f16 = F16 ? 1 : 0;
   // this CTA's (CTA pair's) contiguous, balanced range of tiles
   const int rank = CG2 ? static_cast<int>(cluster_ctarank()) : 0;
   const int unit = CG2 ? blockIdx.x >> 1 : blockIdx.x, n_units = CG2 ? gridDim.x >> 1 : gridDim.x;
@@ -293,14 +321,14 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     }
     mbar_init(sMisc + MISC_GDN_BAR, 1);
     mbar_init(sMisc + MISC_G_FULL, 1);
-    mbar_init(sMisc + MISC_A2_READY, EPI == EPI_GDN2 ? 1 : 2);        // EPI_GDN2: the second team's norm-MMA barrier
+    mbar_init(sMisc + MISC_A2_READY, (EPI == EPI_GDN2 || EPI == EPI_GDNT) ? 1 : 2);   // GDN2 / GDNT: the second team's norm-MMA barrier
     fence_mbar_init();
   }
   if (warp == 3) {
     if (CG2) { tmem_alloc_cg2(sMisc + MISC_TMEM_PTR, TMEM_COLS); tmem_relinquish_cg2(); }
     else { tmem_alloc(sMisc + MISC_TMEM_PTR, TMEM_COLS); tmem_relinquish(); }
   }
-  if ((EPI == EPI_GDN || EPI == EPI_GDN2) && threadIdx.x >= 128) {       // the single n-tile's bias / beta' stay in smem for the whole kernel
+  if ((EPI == EPI_GDN || EPI == EPI_GDN2 || EPI == EPI_GDNT) && threadIdx.x >= 128) {       // the single n-tile's bias / beta' stay in smem for the whole kernel
     float* bs = reinterpret_cast<float*>(smem_gen + p.smem_misc_off + MISC_BIAS);
     float* be = reinterpret_cast<float*>(smem_gen + p.smem_misc_off + MISC_BETA);
     const int i = threadIdx.x - 128;
@@ -322,6 +350,9 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
   // Role loops are WARP-UNIFORM (all 32 lanes walk them, barrier waits included) and only the
   // issue instructions sit under elect_one(): tcgen05.mma / TMA are uniform-datapath instructions.
   const bool free_run = (p.debug & 32) != 0;     // timing experiment: MMA issuers ignore the A/B rings entirely
+  // EPI_GDNT: the role warpgroup (warps 0-3) hands registers to the four epilogue warpgroups
+  if (warp < 4) {
+  if (EPI == EPI_GDNT) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");     // ONE instruction for the whole role warpgroup
   if (warp == 0 && !free_run) {
     // ===================== A producer: activation strips =====================
     uint32_t st = 0, ph = 0;
@@ -360,7 +391,7 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
     }
   } else if (warp == 1 && !free_run) {
     // ===================== B producer: weight k-blocks (+ gamma once) =====================
-    if ((EPI == EPI_GDN || EPI == EPI_GDN2) && elect_one()) {
+    if ((EPI == EPI_GDN || EPI == EPI_GDN2 || EPI == EPI_GDNT) && elect_one()) {
       tma_prefetch_desc(&p.tmG);
       if (CG2) {          // each CTA holds the 64 N-rows of gamma' it feeds to the pair's norm MMA
         if (rank == 0) mbar_expect_tx(sMisc + MISC_G_FULL, 2 * STAGE_BLK_BYTES);
@@ -478,6 +509,144 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
         if (++sa == n_sa) { sa = 0; pa ^= 1; }
       }
     }
+  }
+  } else if (EPI == EPI_GDNT) {
+    // ===================== epilogue, one team per accumulator slot (see EPI_GDNT above) =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int team = (warp - 4) >> 3;                             // = slot of the item this team drains
+    const int hf = ((warp - 4) >> 2) & 1;                         // channels 64 hf .. 64 hf + 63 = A2 / staging block hf of the team
+    const int ew = warp & 3;
+    const int t = ew * 32 + lane;
+    const uint32_t lane_sel = static_cast<uint32_t>(ew * 32) << 16;
+    const uint32_t tbar = 1 + team;
+    const bool leader = (t == 0 && hf == 0);
+    const uint32_t sbuf = sStage + team * 2 * STAGE_BLK_BYTES;
+    const uint32_t bias_s = sMisc + MISC_BIAS, beta_s = sMisc + MISC_BETA;
+    const uint32_t gbar = sMisc + (team ? MISC_A2_READY : MISC_GDN_BAR);
+    const bool fwd = (p.gdn == MASIC_GDN_FWD);
+    const bool nostore = (p.debug & 4) != 0;
+    const uint32_t arow = sbuf + hf * STAGE_BLK_BYTES + t * 128;
+    uint32_t gpar = 0;
+    if (hf == 0 && ew == 0) mbar_wait(sMisc + MISC_G_FULL, 0);   // gamma' resident before this warp issues norm MMAs
+    int n_item = 0;
+    for (Cursor cur = cursor_init(p, u_begin); cur.u < u_end; ++n_item) {
+      const Item it = next_item<CG2>(p, cur, u_end, rank);
+      const Variant& v = p.var[it.var];
+      const int buf = n_item & 1;
+      mbar_wait(sMisc + MISC_ACC_FULL + 8 * buf, (n_item >> 1) & 1);
+      tc_fence_after();
+      if ((p.debug & 16) || team >= it.nslots) {                  // nothing to drain (odd last item) / timing experiment
+        tc_fence_before();
+        mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * buf);
+        continue;
+      }
+      const int tn = team ? it.n[1] : it.n[0], ty0 = team ? it.y0[1] : it.y0[0], tx0 = team ? it.x0[1] : it.x0[0];
+      const uint32_t acc_addr = tmem_base + lane_sel + buf * 256 + team * 128;
+      float rs = 1.0f;
+      if (p.rowscale) {
+        const int y = ty0 + (t >> 3), x = tx0 + (t & 7);
+        if (y < p.rs_H && x < p.rs_W)
+          rs = __ldg(p.rowscale + (static_cast<size_t>(tn * p.rs_H + y) * p.rs_W + x) * p.rs_stride + p.rs_off);
+      }
+      uint64_t x2[32];                                            // x = acc + bias: 64 channels, two per register pair
+      if (leader) tma_store_wait_read<0>();                       // the team's previous output tile has left the staging blocks
+      named_bar_sync(tbar, 256);
+      // ---- pass 1: x stays in registers; A2[:, 64 hf .. +63] = 16-bit(x^2)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int cb = hf * 64 + c * 32;
+        uint32_t r[32];
+        tmem_ld16(acc_addr + cb, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+        tmem_ld16(acc_addr + cb + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint64_t b0, b1;
+          ld_shared_p2(bias_s + (cb + 4 * q) * 4, b0, b1);
+          x2[16 * c + 2 * q] = add2(pk2u(r[4 * q], r[4 * q + 1]), b0);
+          x2[16 * c + 2 * q + 1] = add2(pk2u(r[4 * q + 2], r[4 * q + 3]), b1);
+        }
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          const uint64_t* xx = &x2[16 * c + 4 * c8];
+          st_shared_v4(arow + (((4 * c + c8) ^ (t & 7)) << 4), pack_norm_operand<F16>(mul2(xx[0], xx[0])),
+                       pack_norm_operand<F16>(mul2(xx[1], xx[1])), pack_norm_operand<F16>(mul2(xx[2], xx[2])),
+                       pack_norm_operand<F16>(mul2(xx[3], xx[3])));
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      named_bar_sync(tbar, 256);
+      if (!(p.debug & 8)) {
+        if (hf == 0 && ew == 0) {
+          tc_fence_after();
+          if (elect_one()) {
+            // norm = x^2 * gamma'^T written IN PLACE over the team's accumulator
+            const uint32_t d2 = tmem_base + buf * 256 + team * 128;
+            const uint64_t dh = umma_desc_sw128(0);
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb) {
+              const uint64_t a2 = dh | (((sbuf + kb * STAGE_BLK_BYTES) & 0x3FFFFu) >> 4);
+              const uint64_t g2 = dh | (((sG + kb * STAGE_BLK_BYTES) & 0x3FFFFu) >> 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16(d2, a2 + 2 * k, g2 + 2 * k, p.idesc_norm, (kb | k) ? 1u : 0u);
+            }
+            umma_commit(gbar);
+          }
+          __syncwarp();
+        }
+        mbar_wait(gbar, gpar);
+        gpar ^= 1;
+      }
+      tc_fence_after();
+      // ---- pass 2: out = x * rsqrt(beta' + norm)  (IGDN: x * sqrt(.)); staging rows re-use the A2 rows
+      const uint64_t rs2 = pk2(rs, rs);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int cb = hf * 64 + c * 32;
+        uint32_t r[32];
+        tmem_ld16(acc_addr + cb, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+        tmem_ld16(acc_addr + cb + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+        tmem_ld_wait();
+        if (c == 1) {                                             // last TMEM read of the item by this thread
+          tc_fence_before();
+          mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * buf);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint64_t e0, e1;
+          ld_shared_p2(beta_s + (cb + 4 * q) * 4, e0, e1);
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const uint64_t nrm = add2(pk2u(r[4 * q + 2 * e], r[4 * q + 2 * e + 1]), e ? e1 : e0);
+            float n0, n1;
+            upk2(nrm, n0, n1);
+            uint64_t f = pk2(rsqrt_approx(n0), rsqrt_approx(n1));
+            if (!fwd) f = mul2(f, nrm);
+            uint64_t y = mul2(x2[16 * c + 2 * q + e], f);
+            if (p.rowscale) y = mul2(y, rs2);
+            x2[16 * c + 2 * q + e] = y;
+          }
+        }
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          const uint64_t* xx = &x2[16 * c + 4 * c8];
+          st_shared_v4(arow + (((4 * c + c8) ^ (t & 7)) << 4), pack16x2_p(xx[0], f16), pack16x2_p(xx[1], f16),
+                       pack16x2_p(xx[2], f16), pack16x2_p(xx[3], f16));
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(tbar, 256);
+      const bool valid = team ? it.valid[1] : it.valid[0];
+      if (leader && !nostore && valid) {
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+          tma_store_5d(&p.tmO, sbuf + kb * STAGE_BLK_BYTES, p.out_coff + v.out_c0 + it.nt * p.n_tile + 64 * kb, tx0, v.out_p2,
+                       ty0, tn);
+        tma_store_commit();
+      }
+    }
+    if (leader) tma_store_wait_all<0>();
   } else if (EPI == EPI_GDN2 && warp >= 4) {
     // ===================== epilogue, two teams (see EPI_GDN2 above) =====================
     // TMEM columns: accumulator of team T at 128 T, its norm at 256 + 128 T.  Team T = items with (n_item & 1) == T.
@@ -507,6 +676,11 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
       const Variant& v = p.var[it.var];
       mbar_wait(sMisc + MISC_ACC_FULL + 8 * team, (n_item >> 1) & 1);
       tc_fence_after();
+      if (p.debug & 16) {                         // timing experiment: release the accumulator untouched
+        tc_fence_before();
+        mbar_arrive(sMisc + MISC_ACC_EMPTY + 8 * team);
+        continue;
+      }
       float rs = 1.0f;
       if (p.rowscale) {
         const int y = it.y0[0] + (t >> 3), x = it.x0[0] + (t & 7);
@@ -533,9 +707,9 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
             xx[2 * q] = add2(pk2u(r[8 * c8 + 4 * q], r[8 * c8 + 4 * q + 1]), b0);
             xx[2 * q + 1] = add2(pk2u(r[8 * c8 + 4 * q + 2], r[8 * c8 + 4 * q + 3]), b1);
           }
-          st_shared_v4(arow + (((4 * c + c8) ^ (t & 7)) << 4), pack16x2_p(mul2(xx[0], xx[0]), f16),
-                       pack16x2_p(mul2(xx[1], xx[1]), f16), pack16x2_p(mul2(xx[2], xx[2]), f16),
-                       pack16x2_p(mul2(xx[3], xx[3]), f16));
+          st_shared_v4(arow + (((4 * c + c8) ^ (t & 7)) << 4), pack_norm_operand<F16>(mul2(xx[0], xx[0])),
+                       pack_norm_operand<F16>(mul2(xx[1], xx[1])), pack_norm_operand<F16>(mul2(xx[2], xx[2])),
+                       pack_norm_operand<F16>(mul2(xx[3], xx[3])));
         }
       }
       fence_proxy_async_smem();
@@ -552,7 +726,7 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
               const uint64_t a2 = dh | (((sbuf + kb * STAGE_BLK_BYTES) & 0x3FFFFu) >> 4);
               const uint64_t g2 = dh | (((sG + kb * STAGE_BLK_BYTES) & 0x3FFFFu) >> 4);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(d2, a2 + 2 * k, g2 + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) umma_bf16(d2, a2 + 2 * k, g2 + 2 * k, p.idesc_norm, (kb | k) ? 1u : 0u);
             }
             umma_commit(gbar);
           }
@@ -693,9 +867,9 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {
             const uint64_t* xx = &x2[4 * c8];
-            st_shared_v4(arow + (((4 * half + c8) ^ (t & 7)) << 4), pack16x2_p(mul2(xx[0], xx[0]), f16),
-                         pack16x2_p(mul2(xx[1], xx[1]), f16), pack16x2_p(mul2(xx[2], xx[2]), f16),
-                         pack16x2_p(mul2(xx[3], xx[3]), f16));
+            st_shared_v4(arow + (((4 * half + c8) ^ (t & 7)) << 4), pack_norm_operand<F16>(mul2(xx[0], xx[0])),
+                         pack_norm_operand<F16>(mul2(xx[1], xx[1])), pack_norm_operand<F16>(mul2(xx[2], xx[2])),
+                         pack_norm_operand<F16>(mul2(xx[3], xx[3])));
           }
           fence_proxy_async_smem();
           tc_fence_before();
@@ -718,8 +892,8 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
                 const uint64_t g2 = dh | (((sG + kb * (CG2 ? STAGE_BLK_BYTES / 2 : STAGE_BLK_BYTES)) & 0x3FFFFu) >> 4);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  if (CG2) umma_bf16_cg2(d2, a2 + 2 * k, g2 + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
-                  else umma_bf16(d2, a2 + 2 * k, g2 + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
+                  if (CG2) umma_bf16_cg2(d2, a2 + 2 * k, g2 + 2 * k, p.idesc_norm, (kb | k) ? 1u : 0u);
+                  else umma_bf16(d2, a2 + 2 * k, g2 + 2 * k, p.idesc_norm, (kb | k) ? 1u : 0u);
                 }
               }
               if (CG2) umma_commit_cg2(sMisc + MISC_GDN_BAR); else umma_commit(sMisc + MISC_GDN_BAR);
@@ -1210,6 +1384,7 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   { const char* e = getenv("MASIC_CONV_CG2"); kp.cg2 = e ? (atoi(e) != 0) : (d.cta_pairs != 0); }   // env overrides the plan
   { const char* e = getenv("MASIC_CONV_PDL"); kp.pdl = e ? (atoi(e) != 0) : 0; }
   kp.idesc = kp.cg2 ? umma_idesc_bf16_m256(d.n_tile) : umma_idesc_bf16(d.n_tile);
+  kp.idesc_norm = kp.idesc;
   kp.f16 = d.f16 != 0;
   if (kp.f16) kp.idesc &= ~((1u << 7) | (1u << 10));        // a_format / b_format: 1 = bf16, 0 = fp16
 
@@ -1227,6 +1402,10 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   // memory next to gamma', four staging blocks and a double-buffered strip ring
   kp.gdn2 = d.gdn && !kp.cg2 && kp.n_var == 1 && kp.var[0].n_bops <= 6;
   { const char* e = getenv("MASIC_CONV_GDN2"); if (e && atoi(e) == 0) kp.gdn2 = 0; }
+  // EPI_GDNT is built and tested but measured no faster than EPI_GDN (the two teams start on the same ACC_FULL and run in
+  // lock step, so their stalls coincide): opt-in through MASIC_CONV_GDNT=1
+  { const char* e = getenv("MASIC_CONV_GDNT"); kp.gdnt = d.gdn && !kp.cg2 && (e ? atoi(e) != 0 : 0); }
+  if (kp.gdnt) kp.gdn2 = 0;
   if (kp.gdn2) kp.pair = 1;
   kp.n_spatial = kp.tiles_x * kp.tiles_y * kp.n_img;
   kp.n_tiles_total = kp.n_spatial * kp.n_var * kp.n_ntiles;
@@ -1237,7 +1416,7 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   const int a_stage_bytes = kp.pair * kp.strip_bytes;
   // staging: with GDN two blocks (together the A2 operand of the norm MMA, then the output tile);
   // otherwise two per epilogue group so a block's TMA store drains behind the next block
-  const int n_stage_blk = (d.gdn && !kp.gdn2) ? 2 : 4;
+  const int n_stage_blk = (d.gdn && !kp.gdn2 && !kp.gdnt) ? 2 : 4;
   const int gamma_bytes = d.gdn ? (kp.cg2 ? STAGE_BLK_BYTES : 2 * STAGE_BLK_BYTES) : 0;
   const int fixed = gamma_bytes + n_stage_blk * STAGE_BLK_BYTES + MISC_BYTES + 1024 /*align*/;
   const int budget = 227 * 1024 - fixed;                      // ring bytes
@@ -1344,11 +1523,12 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
 
   static bool attr_set = false;
   if (!attr_set) {
-    const void* fns[7] = {(const void*)conv_tc_kernel<false, EPI_PLAIN>, (const void*)conv_tc_kernel<false, EPI_GDN>,
-                          (const void*)conv_tc_kernel<false, EPI_RES>, (const void*)conv_tc_kernel<true, EPI_PLAIN>,
-                          (const void*)conv_tc_kernel<true, EPI_GDN>, (const void*)conv_tc_kernel<true, EPI_RES>,
-                          (const void*)conv_tc_kernel<false, EPI_GDN2>};
-    for (int i = 0; i < 7 && ce == cudaSuccess; ++i)
+#define MASIC_K2(C, E) (const void*)conv_tc_kernel<C, E, false>, (const void*)conv_tc_kernel<C, E, true>
+    const void* fns[16] = {MASIC_K2(false, EPI_PLAIN), MASIC_K2(false, EPI_GDN), MASIC_K2(false, EPI_RES),
+                           MASIC_K2(true, EPI_PLAIN),  MASIC_K2(true, EPI_GDN),  MASIC_K2(true, EPI_RES),
+                           MASIC_K2(false, EPI_GDN2),  MASIC_K2(false, EPI_GDNT)};
+#undef MASIC_K2
+    for (int i = 0; i < 16 && ce == cudaSuccess; ++i)
       ce = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (ce != cudaSuccess) { delete pl; return (int)ce; }
     attr_set = true;
@@ -1378,16 +1558,22 @@ extern "C" int masic_conv_plan_launch(const MasicConvPlan* pl, void* stream) {
     ++na;
   }
   cfg.attrs = attr; cfg.numAttrs = na;
-  const int epi = pl->kp.gdn ? EPI_GDN : (pl->kp.res0 ? EPI_RES : EPI_PLAIN);
+  const int epi = pl->kp.gdn ? (pl->kp.gdnt ? EPI_GDNT : (pl->kp.gdn2 ? EPI_GDN2 : EPI_GDN)) : (pl->kp.res0 ? EPI_RES : EPI_PLAIN);
+  const bool f16 = pl->kp.f16 != 0;
+#define MASIC_LAUNCH(C, E) \
+  return f16 ? (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<C, E, true>, pl->kp) \
+             : (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<C, E, false>, pl->kp)
   if (pl->kp.cg2) {
-    if (epi == EPI_GDN) return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, EPI_GDN>, pl->kp);
-    if (epi == EPI_RES) return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, EPI_RES>, pl->kp);
-    return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, EPI_PLAIN>, pl->kp);
+    if (epi == EPI_GDN) { MASIC_LAUNCH(true, EPI_GDN); }
+    if (epi == EPI_RES) { MASIC_LAUNCH(true, EPI_RES); }
+    MASIC_LAUNCH(true, EPI_PLAIN);
   }
-  if (epi == EPI_GDN && pl->kp.gdn2) return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, EPI_GDN2>, pl->kp);
-  if (epi == EPI_GDN) return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, EPI_GDN>, pl->kp);
-  if (epi == EPI_RES) return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, EPI_RES>, pl->kp);
-  return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, EPI_PLAIN>, pl->kp);
+  if (epi == EPI_GDNT) { MASIC_LAUNCH(false, EPI_GDNT); }
+  if (epi == EPI_GDN2) { MASIC_LAUNCH(false, EPI_GDN2); }
+  if (epi == EPI_GDN) { MASIC_LAUNCH(false, EPI_GDN); }
+  if (epi == EPI_RES) { MASIC_LAUNCH(false, EPI_RES); }
+  MASIC_LAUNCH(false, EPI_PLAIN);
+#undef MASIC_LAUNCH
 }
 
 extern "C" void masic_conv_plan_destroy(MasicConvPlan* pl) {
