@@ -270,6 +270,20 @@ int masic_rans_decoder_decode(MasicRansDecoder* dec, const int32_t* indexes_host
                               const int32_t* offsets_host, int32_t* symbols_host);
 void masic_rans_decoder_destroy(MasicRansDecoder* dec);
 
+/* ------------------------------------------ g_s_conv4: 128 -> 3 transposed conv at image resolution */
+/* ConvTranspose2d(128, 3, k=5, s=2, p=2, op=1) (models/utils.py:138-146; MASIC.py:542, :596) in col2im form: one
+ * GEMM Z = x W (K = 128, N = 25 taps x 4) on tcgen05 and a shared-memory gather-sum, writing the (n, 3, 2h, 2w) fp32
+ * NCHW image directly; gdn = MASIC_GDN_INV additionally applies after_gdn (IGDN over the 3 channels, MASIC.py:599)
+ * with the STORED beta (3) / gamma (3x3) given as HOST arrays.  in: NHWC 16-bit, channel pitch 128, h_in % 8 == 0. */
+typedef struct MasicDeconvImgPlan MasicDeconvImgPlan;
+int64_t masic_deconv_img_weight_bytes(void);
+int masic_deconv_img_pack_weights(const float* weight_128x3x5x5, void* dst_16, int f16, void* stream);
+int masic_deconv_img_plan_create(const void* in_nhwc16, int n, int h_in, int w_in, int c_pitch, const void* w_packed,
+                                 const float* bias3, int gdn, const float* beta3_host, const float* gamma9_host,
+                                 float* out_nchw, int f16, MasicDeconvImgPlan** plan_out);
+int masic_deconv_img_plan_launch(const MasicDeconvImgPlan* plan, void* stream);
+void masic_deconv_img_plan_destroy(MasicDeconvImgPlan* plan);
+
 /* ---------------------------------------------------- udh homography front-end */
 /* nn.MaxPool2d(2, 2) of coremasic/mywork/model.py:66 on an NHWC bf16 activation (c_pitch % 8 == 0). */
 int masic_maxpool2_nhwc_bf16(const void* in, int n, int h, int w, int c_pitch, void* out, int f16, void* stream);

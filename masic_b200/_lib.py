@@ -139,6 +139,11 @@ def _declare(lib: C.CDLL) -> None:
         "masic_rans_decoder_create": (i, [vp, i64, C.POINTER(vp)]),
         "masic_rans_decoder_decode": (i, [vp, vp, i64, vp, i, i, vp, vp, vp]),
         "masic_rans_decoder_destroy": (None, [vp]),
+        "masic_deconv_img_weight_bytes": (i64, []),
+        "masic_deconv_img_pack_weights": (i, [vp, vp, i, vp]),
+        "masic_deconv_img_plan_create": (i, [vp, i, i, i, i, vp, vp, i, vp, vp, vp, i, C.POINTER(vp)]),
+        "masic_deconv_img_plan_launch": (i, [vp, vp]),
+        "masic_deconv_img_plan_destroy": (None, [vp]),
         "masic_maxpool2_nhwc_bf16": (i, [vp, i, i, i, i, vp, i, vp]),
         "masic_fc_pack_weights": (i, [vp, i, i, i, vp, i, vp]),
         "masic_fc_bf16": (i, [vp, i, vp, vp, i, i, i, i, vp, vp, i, i, vp]),

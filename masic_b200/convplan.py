@@ -241,6 +241,52 @@ class ConvPlan:
             self._h = None
 
 
+class DeconvImgPlan:
+    """g_s_conv4 — ConvTranspose2d(128, 3, k=5, s=2, p=2, op=1) at image resolution (MasicDeconvImgPlan of the C ABI,
+    csrc/deconv_img.cu): NHWC 16-bit (n, h, w, 128) in, NCHW fp32 (n, 3, 2h, 2w) out, optional after_gdn (IGDN over the
+    three channels) fused.  `weight` is the module's (128, 3, 5, 5) tensor."""
+
+    def __init__(self, *, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor,
+                 igdn_beta: Optional[torch.Tensor] = None, igdn_gamma: Optional[torch.Tensor] = None):
+        import numpy as np
+        lib = _lib.load()
+        assert x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and x.dim() == 4 and x.is_contiguous()
+        n, h, w, cp = x.shape
+        assert cp == 128 and tuple(weight.shape) == (128, 3, 5, 5), (x.shape, weight.shape)
+        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (n, 3, 2 * h, 2 * w)
+        f16 = int(x.dtype == torch.float16)
+        self.w_packed = torch.empty(lib.masic_deconv_img_weight_bytes() // 2, dtype=x.dtype, device=x.device)
+        wt = weight.detach().float().contiguous()
+        check(lib.masic_deconv_img_pack_weights(wt.data_ptr(), self.w_packed.data_ptr(), f16, _stream()),
+              "masic_deconv_img_pack_weights")
+        self.bias = None if bias is None else bias.detach().float().contiguous()
+        gdn, pb, pg = GDN_NONE, None, None
+        if igdn_beta is not None:
+            gdn = GDN_INV
+            self._b = np.ascontiguousarray(igdn_beta.detach().float().cpu().numpy())
+            self._g = np.ascontiguousarray(igdn_gamma.detach().float().cpu().numpy())
+            pb, pg = self._b.ctypes.data, self._g.ctypes.data
+        self.x, self.out = x, out
+        hdl = C.c_void_p()
+        check(lib.masic_deconv_img_plan_create(x.data_ptr(), n, h, w, cp, self.w_packed.data_ptr(), _ptr(self.bias), gdn,
+                                               pb, pg, out.data_ptr(), f16, C.byref(hdl)), "masic_deconv_img_plan_create")
+        self._h, self._lib = hdl, lib
+        self.flops = 2.0 * n * h * w * 128 * 75
+        self.work_items = n * (-(-w // 14)) * (h // 8)
+        self.smem_bytes = 0
+        self.hbm_bytes = n * h * w * (256.0 + 48.0)
+
+    def launch(self, stream: Optional[int] = None) -> None:
+        check(self._lib.masic_deconv_img_plan_launch(self._h, _stream() if stream is None else stream),
+              "masic_deconv_img_plan_launch")
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.masic_deconv_img_plan_destroy(h)
+            self._h = None
+
+
 class WgradPlan:
     """Tensor-core weight gradient of one conv / transposed-conv layer (MasicWgradPlan of the C ABI).
     `lo` / `hi` are the bound NHWC bf16 buffers (see include/masic_b200.h), `dw` the fp32 torch-layout gradient."""

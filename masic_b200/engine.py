@@ -27,7 +27,7 @@ import torch
 from . import _lib
 from ._lib import MasicError, check
 from .convplan import (ACT_LEAKY, ACT_NONE, ACT_RELU, CONV, CONV_XFOLD8, DECONV_S2, DECONV_S2_SUBPIX, GDN_FWD, GDN_INV,
-                       GDN_NONE, MASK_A_5x5, ConvPlan, PackedConv)
+                       GDN_NONE, MASK_A_5x5, ConvPlan, DeconvImgPlan, PackedConv)
 
 F16 = _lib.FMT_F16              # the inference engines run on fp16 operands / activations (csrc/cvt16.cuh)
 ACT = _lib.act_dtype(F16)
@@ -136,25 +136,39 @@ class HSICEngine:
         self._conv(f"{tag}.conv4", packs[3], e3, y, stride=2)
         return y
 
-    def _decoder(self, tag: str, dec: str, yq_bf16):
-        """g_s: 3x (deconv5 s2 + IGDN) + deconv5 s2 -> 3 (sub-pixel form) — MASIC.py:544-554."""
+    def _decoder(self, tag: str, dec: str, yq_bf16, out_img, igdn_prefix=None):
+        """g_s: 3x (deconv5 s2 + IGDN) + deconv5 s2 -> 3 — MASIC.py:544-554.  The last layer runs in col2im form
+        (csrc/deconv_img.cu) and writes the NCHW fp32 image `out_img`, with after_gdn fused for the right view."""
+        import os
         B, H, W, N, M = self.B, self.H, self.W, self.N, self.M
         g1 = self._buf(B, H // 8, W // 8, N)
         g2 = self._buf(B, H // 4, W // 4, N)
         g3 = self._buf(B, H // 2, W // 2, N)
-        sp = self._buf(B, H // 2, W // 2, 16, dtype=torch.float32)
         p1 = self._pack(f"{dec}.g_s_conv1", kind=DECONV_S2, c_in=M, c_out=N, n_tile=128, transposed=True,
                         gdn=GDN_INV, gdn_prefix=f"{dec}.g_s_gdn1")
         p2 = self._pack(f"{dec}.g_s_conv2", kind=DECONV_S2, c_in=N, c_out=N, n_tile=128, transposed=True,
                         gdn=GDN_INV, gdn_prefix=f"{dec}.g_s_gdn2")
         p3 = self._pack(f"{dec}.g_s_conv3", kind=DECONV_S2, c_in=N, c_out=N, n_tile=128, transposed=True,
                         gdn=GDN_INV, gdn_prefix=f"{dec}.g_s_gdn3")
-        p4 = self._pack(f"{dec}.g_s_conv4", kind=DECONV_S2_SUBPIX, c_in=N, c_out=3, n_tile=16, transposed=True)
         self._conv(f"{tag}.deconv1+igdn", p1, yq_bf16, g1)
         self._conv(f"{tag}.deconv2+igdn", p2, g1, g2)
         self._conv(f"{tag}.deconv3+igdn", p3, g2, g3)
+        ib = self._w(igdn_prefix + ".beta") if igdn_prefix else None
+        ig = self._w(igdn_prefix + ".gamma") if igdn_prefix else None
+        if os.environ.get("MASIC_DECONV_IMG", "1") != "0":
+            plan = DeconvImgPlan(x=g3, weight=self._w(f"{dec}.g_s_conv4.weight"), bias=self._w(f"{dec}.g_s_conv4.bias"),
+                                 out=out_img, igdn_beta=ib, igdn_gamma=ig)
+            self.plans[f"{tag}.deconv4(col2im)"] = plan
+            self._add(f"{tag}.deconv4(col2im)", plan.launch)
+            return
+        # the earlier form (MASIC_DECONV_IMG=0): sub-pixel conv_tc plan (N = 4 phases x 3 -> 16) + pixel interleave
+        sp = self._buf(B, H // 2, W // 2, 16, dtype=torch.float32)
+        p4 = self._pack(f"{dec}.g_s_conv4", kind=DECONV_S2_SUBPIX, c_in=N, c_out=3, n_tile=16, transposed=True)
         self._conv(f"{tag}.deconv4(subpix)", p4, g3, sp)
-        return sp
+        self._keep += [ib, ig]
+        self._add(f"{tag}.unshuffle", lambda: check(self.lib.masic_subpix_to_nchw(
+            sp.data_ptr(), B, H // 2, W // 2, 16, GDN_INV if igdn_prefix else 0, None if ib is None else ib.data_ptr(),
+            None if ig is None else ig.data_ptr(), 1e-6, out_img.data_ptr(), None, 0, F16, self._s()), "masic_subpix_to_nchw"))
 
     def _hyper(self, tag: str, idx: int, y_abs_bf16, gmm_in, rowscale=None):
         """h_a -> EntropyBottleneck -> h_s_up (MASIC.py:747-754 / :786-793).  Writes params into
@@ -412,10 +426,7 @@ class HSICEngine:
 
         # ---------------- lane 0: left decoder, warp of x1_hat, encoder1 on it, right GMM + decoder
         self._on(0)
-        sp1 = self._decoder("L.g_s", "decoder1", y1_rnd)                                           # :777
-        self._add("L.x1_hat(unshuffle)", lambda: check(lib.masic_subpix_to_nchw(
-            sp1.data_ptr(), B, H // 2, W // 2, 16, 0, None, None, 1e-6, o["x1_hat"].data_ptr(), None, 0, F16, self._s()),
-            "masic_subpix_to_nchw"))
+        self._decoder("L.g_s", "decoder1", y1_rnd, o["x1_hat"])                                    # :777
         # x1_hat warped once (the reference computes it twice, :821 and :833)
         x1hw = self._buf(B, 3, H, W, dtype=f32)
         x1hw_bf = self._buf(B, H, W + XPAD, IMG_CP)
@@ -427,14 +438,8 @@ class HSICEngine:
         self._latent_prep("R.y1warp", y1w, None, gmm2_in, rnd_coff=4 * M, rowscale=mw, rs_off=2)   # round(.) * w2
         s2, m2, w2 = self._gmm_net("R", "_h_s2_same_resolution", 5 * M, False, gmm2_in)            # :827
         self._gmm_likelihood("R", y2, s2, m2, w2, o["y2_hat"], o["lik_y2"])                        # :829
-        sp2 = self._decoder("R.g_s", "decoder2", y2_rnd)                                           # :834
         after1 = self._buf(B, 3, H, W, dtype=f32)
-        ab = self._w("decoder2.after_gdn.beta")
-        ag = self._w("decoder2.after_gdn.gamma")
-        self._keep += [ab, ag]
-        self._add("R.after_gdn(unshuffle)", lambda: check(lib.masic_subpix_to_nchw(
-            sp2.data_ptr(), B, H // 2, W // 2, 16, GDN_INV, ab.data_ptr(), ag.data_ptr(), 1e-6, after1.data_ptr(), None, 0,
-            F16, self._s()), "masic_subpix_to_nchw"))
+        self._decoder("R.g_s", "decoder2", y2_rnd, after1, igdn_prefix="decoder2.after_gdn")        # :834, :615
         self._conv_small("R.after_conv", after1, x1hw, "decoder2.after_conv", ksize=5, stride=1, transposed_s1=True,
                          out=o["x2_hat"])
         self._wait("left_entropy")
