@@ -9,11 +9,11 @@
 //     out[co][2 iy - 2 + ky][2 ix - 2 + kx] += Z[iy][ix][(ky, kx, co)]
 // i.e. 8 MMAs (N = 112) per 128 input pixels, followed by a gather-sum of <= 9 Z entries per output pixel done from
 // shared memory.  A CTA walks DOWN a strip of 16 input columns (14 of them new: the horizontal halo is recomputed),
-// eight input rows per step; Z rows live in a 16-row shared-memory ring, so the vertical halo costs one extra step
+// eight input rows per step; Z rows live in a 12-row shared-memory ring, so the vertical halo costs one extra step
 // only where a CTA's range starts in the middle of a strip.  Out-of-image pixels are TMA zero fill, hence Z = 0.
 //
-// Roles: warp 0 TMA producer (two 16 KB k-blocks per step, 2 stages), warp 1 MMA issuer (8 MMAs per step into one of
-// two TMEM accumulators), warps 2-9 epilogue: TMEM -> Z ring, then 16 output rows x 28 columns x 3 channels per step.
+// Roles: warp 0 TMA producer (two 16 KB k-blocks per step, 3 stages), warp 1 MMA issuer (8 MMAs per step into one of
+// two TMEM accumulators), warps 2-17 epilogue: TMEM -> Z ring, then 16 output rows x 28 columns x 3 channels per step.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,10 +29,11 @@ using namespace masic;
 constexpr int DI_COLS = 16, DI_NEW = 14, DI_ROWS = 8;     // strip width (loaded / new), rows per step
 constexpr int DI_N = 112;                                  // accumulator columns: (ky*5+kx)*4 + co, 100 used
 constexpr int DI_ZP = 116;                                 // floats per pixel in the Z ring (conflict-free float4 rows)
-constexpr int DI_RING = 16;                                // Z ring rows
-constexpr int DI_THREADS = 320, DI_EPI = 256;
+constexpr int DI_RING = 12;                                // Z ring rows: 10 live (R-2 .. R+7) while the next 8 are written
+                                                           // ... after the barrier that ends the step's gather, so 12 suffice
+constexpr int DI_THREADS = 576, DI_EPI = 512;
 constexpr int DI_A_STAGE = 2 * 16384;                      // two k-blocks of [8 rows][16 cols][64 ch]
-constexpr int DI_A_STAGES = 2;
+constexpr int DI_A_STAGES = 3;
 constexpr int DI_B_BYTES = 2 * DI_N * 128;                 // two k-blocks of [112 rows][64 ch]
 constexpr int DI_Z_BYTES = DI_RING * DI_COLS * DI_ZP * 4;
 constexpr int DI_MISC = 256;
@@ -49,13 +50,6 @@ struct DIParams {
   uint32_t idesc;
 };
 
-__device__ __forceinline__ void tmem_ld16x(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  tmem_ld16(taddr, r);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 __global__ void __launch_bounds__(DI_THREADS, 1)
 deconv_img_kernel(const __grid_constant__ DIParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -64,23 +58,25 @@ deconv_img_kernel(const __grid_constant__ DIParams p) {
   const uint32_t sA = base, sB = base + DI_A_STAGES * DI_A_STAGE;
   float* zring = reinterpret_cast<float*>(gen + DI_A_STAGES * DI_A_STAGE + DI_B_BYTES);
   const uint32_t sMisc = base + DI_A_STAGES * DI_A_STAGE + DI_B_BYTES + DI_Z_BYTES;
-  // barriers: A full[2] @0, A empty[2] @16, acc full[2] @32, acc empty[2] @48, B full @64, tmem ptr @72
-  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gen + DI_A_STAGES * DI_A_STAGE + DI_B_BYTES + DI_Z_BYTES + 72);
+  // barriers: A full[3] @0, A empty[3] @24, acc full[2] @48, acc empty[2] @64, B full @80, tmem ptr @88
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(gen + DI_A_STAGES * DI_A_STAGE + DI_B_BYTES + DI_Z_BYTES + 88);
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < DI_A_STAGES; ++i) {
       mbar_init(sMisc + 8 * i, 1);
-      mbar_init(sMisc + 16 + 8 * i, 1);
-      mbar_init(sMisc + 32 + 8 * i, 1);
-      mbar_init(sMisc + 48 + 8 * i, DI_EPI);
+      mbar_init(sMisc + 24 + 8 * i, 1);
     }
-    mbar_init(sMisc + 64, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(sMisc + 48 + 8 * i, 1);
+      mbar_init(sMisc + 64 + 8 * i, DI_EPI);
+    }
+    mbar_init(sMisc + 80, 1);
     fence_mbar_init();
   }
-  if (warp == 1) { tmem_alloc(sMisc + 72, 256); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(sMisc + 88, 256); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -97,15 +93,15 @@ deconv_img_kernel(const __grid_constant__ DIParams p) {
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (u0 < u1 && elect_one()) {
-      mbar_expect_tx(sMisc + 64, DI_B_BYTES);
-      tma_load_2d(sB, &p.tmB, sMisc + 64, 0, 0);
-      tma_load_2d(sB + DI_N * 128, &p.tmB, sMisc + 64, 0, DI_N);
+      mbar_expect_tx(sMisc + 80, DI_B_BYTES);
+      tma_load_2d(sB, &p.tmB, sMisc + 80, 0, 0);
+      tma_load_2d(sB + DI_N * 128, &p.tmB, sMisc + 80, 0, DI_N);
     }
     __syncwarp();
     uint32_t st = 0, ph = 0;
     for (int u = first_iter(); u < u1; ++u) {
       const int s = u % S, strip = (u / S) % p.n_strips, img = u / (S * p.n_strips);
-      mbar_wait(sMisc + 16 + 8 * st, ph ^ 1);
+      mbar_wait(sMisc + 24 + 8 * st, ph ^ 1);
       if (elect_one()) {
         const uint32_t full = sMisc + 8 * st;
         mbar_expect_tx(full, DI_A_STAGE);
@@ -117,13 +113,13 @@ deconv_img_kernel(const __grid_constant__ DIParams p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (u0 < u1) mbar_wait(sMisc + 64, 0);
+    if (u0 < u1) mbar_wait(sMisc + 80, 0);
     uint32_t st = 0, ph = 0;
     int it = 0;
     const uint64_t descA0 = umma_desc_sw128(sA), descB0 = umma_desc_sw128(sB);
     for (int u = first_iter(); u < u1; ++u, ++it) {
       const int buf = it & 1;
-      mbar_wait(sMisc + 48 + 8 * buf, ((it >> 1) & 1) ^ 1);
+      mbar_wait(sMisc + 64 + 8 * buf, ((it >> 1) & 1) ^ 1);
       mbar_wait(sMisc + 8 * st, ph);
       tc_fence_after();
       if (elect_one()) {
@@ -134,8 +130,8 @@ deconv_img_kernel(const __grid_constant__ DIParams p) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(d, a + 2 * k, b + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
         }
-        umma_commit(sMisc + 16 + 8 * st);
-        umma_commit(sMisc + 32 + 8 * buf);
+        umma_commit(sMisc + 24 + 8 * st);
+        umma_commit(sMisc + 48 + 8 * buf);
       }
       __syncwarp();
       if (++st == DI_A_STAGES) { st = 0; ph ^= 1; }
@@ -143,65 +139,70 @@ deconv_img_kernel(const __grid_constant__ DIParams p) {
   } else {
     // ===================== epilogue =====================
     const int q = warp & 3;                 // TMEM lane quarter of this warp
-    const int hcol = (warp - 2) >> 2;       // column half: 0 -> columns 0..63, 1 -> columns 64..111
+    const int cg = (warp - 2) >> 2;         // column group: columns 32 cg .. 32 cg + 31 (the last group holds 16)
     const int m = q * 32 + lane;            // pixel of the step's 8 x 16 block: row m >> 4, column m & 15
-    const int et = (warp - 2) * 32 + lane;  // 0..255
+    const int et = (warp - 2) * 32 + lane;  // 0..511
     const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
     const int H2 = p.h2, W2 = p.w2, HO = 2 * p.h2, WO = 2 * p.w2;
     float bias[3] = {0.f, 0.f, 0.f};
     if (p.bias) { bias[0] = p.bias[0]; bias[1] = p.bias[1]; bias[2] = p.bias[2]; }
+    // gather geometry of this thread, constant over the whole kernel: output (row ro of the step's 18, column oxl of the
+    // strip's 28).  oy = 2R - 2 + ro, ox = 2 X0 + oxl  =>  taps ky = py + 2 jy read input row R - 1 + ((ro + 2 - ky) >> 1),
+    // taps kx = px + 2 jx read strip column ((oxl + 2 - kx) >> 1) + 1; only R changes from step to step.
+    const int ro = et / (2 * DI_NEW), oxl = et - ro * (2 * DI_NEW);
+    const int py = ro & 1, px = oxl & 1;
+    const int nty = py ? 2 : 3, ntx = px ? 2 : 3;
+    int drow[3], coff[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int ky = py + 2 * j;
+      drow[j] = ((ro + 2 - ky) >> 1) - 1;                               // input row relative to R
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int kx = px + 2 * i;
+        coff[j][i] = (((oxl + 2 - kx) >> 1) + 1) * DI_ZP + (ky * 5 + kx) * 4;    // float offset inside a ring row
+      }
+    }
     int it = 0;
     for (int u = first_iter(); u < u1; ++u, ++it) {
       const int s = u % S, strip = (u / S) % p.n_strips, img = u / (S * p.n_strips);
       const int buf = it & 1, R = s * DI_ROWS, X0 = strip * DI_NEW;
-      mbar_wait(sMisc + 32 + 8 * buf, (it >> 1) & 1);
+      mbar_wait(sMisc + 48 + 8 * buf, (it >> 1) & 1);
       tc_fence_after();
       // ---- Z rows R .. R+7 -> ring (pixel m: ring row (R + (m >> 4)) & 15, column m & 15)
       {
-        float* zp = zring + ((((R + (m >> 4)) & (DI_RING - 1)) * DI_COLS + (m & 15)) * DI_ZP);
-        const uint32_t ta = tmem_base + lane_sel + buf * 128 + hcol * 64;
-        const int nchunk = hcol ? 3 : 4;
+        float* zp = zring + ((((R + (m >> 4)) % DI_RING) * DI_COLS + (m & 15)) * DI_ZP) + cg * 32;
+        const uint32_t ta = tmem_base + lane_sel + buf * 128 + cg * 32;
+        uint32_t r[32];
+        tmem_ld16(ta, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));          // both loads in flight before the single wait
+        if (cg < 3) tmem_ld16(ta + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+        tmem_ld_wait();
+        uint4* dst = reinterpret_cast<uint4*>(zp);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c < nchunk) {
-            float v[16];
-            tmem_ld16x(ta + 16 * c, v);
-            tmem_ld_wait();
-            float4* dst = reinterpret_cast<float4*>(zp + hcol * 64 + 16 * c);
-            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-            dst[2] = make_float4(v[8], v[9], v[10], v[11]);
-            dst[3] = make_float4(v[12], v[13], v[14], v[15]);
-          }
-        }
+        for (int c = 0; c < 8; ++c)
+          if (c < 4 || cg < 3) dst[c] = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
       }
       tc_fence_before();
-      mbar_arrive(sMisc + 48 + 8 * buf);            // the accumulator may be refilled
+      mbar_arrive(sMisc + 64 + 8 * buf);            // the accumulator may be refilled
       named_bar_sync(1, DI_EPI);
-      // ---- output rows made complete by this step (none for the halo step of a range)
+      // ---- output rows made complete by this step (none for the halo step of a range): rows 2R-2 .. 2R+13, and the
+      // image's last two rows with the strip's last step
       if (u >= u0) {
-        const int oy0 = max(0, 2 * R - 2), oy1 = (s == S - 1) ? HO : 2 * R + 14;       // [oy0, oy1)
-        const int nrow = oy1 - oy0;
-        for (int idx = et; idx < nrow * 2 * DI_NEW; idx += DI_EPI) {
-          const int ro = idx / (2 * DI_NEW), oxl = idx - ro * (2 * DI_NEW);
-          const int oy = oy0 + ro, ox = 2 * X0 + oxl;
-          if (ox >= WO) continue;
-          const int py = oy & 1, px = ox & 1;
+        const int oy = 2 * R - 2 + ro, ox = 2 * X0 + oxl;
+        if (ro < (s == S - 1 ? 18 : 16) && oy >= 0 && ox < WO) {
           float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
-          for (int jy = 0; jy < 3; ++jy) {
-            const int ky = py + 2 * jy;
-            if (ky > 4) continue;
-            const int iy = (oy + 2 - ky) >> 1;
-            if (iy < 0 || iy >= H2) continue;
-            const float* zr = zring + ((iy & (DI_RING - 1)) * DI_COLS) * DI_ZP;
+          for (int j = 0; j < 3; ++j) {
+            const int iy = R + drow[j];
+            if (j < nty && iy >= 0 && iy < H2) {
+              const float* zr = zring + ((iy % DI_RING) * DI_COLS) * DI_ZP;
 #pragma unroll
-            for (int jx = 0; jx < 3; ++jx) {
-              const int kx = px + 2 * jx;
-              if (kx > 4) continue;
-              const int cx = ((ox + 2 - kx) >> 1) - (X0 - 1);      // 0..15 by construction
-              const float4 z = *reinterpret_cast<const float4*>(zr + cx * DI_ZP + (ky * 5 + kx) * 4);
-              a0 += z.x; a1 += z.y; a2 += z.z;
+              for (int i = 0; i < 3; ++i) {
+                if (i < ntx) {
+                  const float4 z = *reinterpret_cast<const float4*>(zr + coff[j][i]);
+                  a0 += z.x; a1 += z.y; a2 += z.z;
+                }
+              }
             }
           }
           float v0 = a0 + bias[0], v1 = a1 + bias[1], v2 = a2 + bias[2];
