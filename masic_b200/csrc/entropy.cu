@@ -166,6 +166,78 @@ gmm_fwd_kernel(const float* __restrict__ y, View vy, const float* __restrict__ s
   }
 }
 
+// The engine's configuration (parameters NHWC, weight logits, outputs NCHW) with 128-bit loads: a thread owns FOUR
+// consecutive channels of one position, so its 16 parameter loads are LDG.128 (4x fewer load instructions than the
+// generic kernel, all independent and in flight together) and a warp touches 4 positions x 128 contiguous bytes per
+// load.  Results go through a 32 x 32 shared-memory transpose so the NCHW stores are coalesced along positions.
+// Same per-element arithmetic as gmm_fwd_kernel: bit-identical outputs.  block (8, 32): x = channel quad, y = position.
+template <int K>
+__global__ void __launch_bounds__(256)
+gmm_fwd_nhwc_v4_kernel(const float* __restrict__ y, const float* __restrict__ sigma, const float* __restrict__ mu,
+                       const float* __restrict__ wgt, int M, int P, float scale_bound, float* __restrict__ y_hat,
+                       float* __restrict__ lik) {
+  __shared__ float s_lik[32][33];
+  __shared__ float s_yh[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  const int p = p0 + threadIdx.y, m = m0 + 4 * threadIdx.x;
+  if (p < P && m < M) {
+    const size_t row = (static_cast<size_t>(n) * P + p);
+    const float4 yv = __ldg(reinterpret_cast<const float4*>(y + row * M + m));
+    float4 sv[K], mv[K], wv[K];
+    const size_t pb = row * (static_cast<size_t>(K) * M) + m;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      sv[k] = __ldg(reinterpret_cast<const float4*>(sigma + pb + static_cast<size_t>(k) * M));
+      mv[k] = __ldg(reinterpret_cast<const float4*>(mu + pb + static_cast<size_t>(k) * M));
+      wv[k] = __ldg(reinterpret_cast<const float4*>(wgt + pb + static_cast<size_t>(k) * M));
+    }
+    const float ye[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float wk[K], sk[K], mk[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float* sp = reinterpret_cast<const float*>(&sv[k]);
+        const float* mp = reinterpret_cast<const float*>(&mv[k]);
+        const float* wp = reinterpret_cast<const float*>(&wv[k]);
+        sk[k] = sp[e]; mk[k] = mp[e]; wk[k] = wp[e];
+      }
+      const float yh = rintf(ye[e]);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < K; ++k) mx = fmaxf(mx, wk[k]);
+      float sum = 0.0f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) { wk[k] = expf(wk[k] - mx); sum += wk[k]; }
+      const float inv_sum = 1.0f / sum;
+#pragma unroll
+      for (int k = 0; k < K; ++k) wk[k] *= inv_sum;
+      float l = 0.0f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float sd = fmaxf(sk[k], scale_bound);
+        const float v = fabsf(yh - mk[k]);
+        l += gauss_mass(v, sd) * wk[k];
+      }
+      s_lik[threadIdx.y][4 * threadIdx.x + e] = fmaxf(l, kLikBound);
+      s_yh[threadIdx.y][4 * threadIdx.x + e] = yh;
+    }
+  }
+  __syncthreads();
+  // store: thread (tx, ty) -> flat id; position fastest
+  const int tid = threadIdx.y * 8 + threadIdx.x;
+  const int pl = tid & 31;
+  for (int ml = tid >> 5; ml < 32; ml += 8) {
+    const int pp = p0 + pl, mm = m0 + ml;
+    if (pp < P && mm < M) {
+      const size_t o = (static_cast<size_t>(n) * M + mm) * P + pp;
+      lik[o] = s_lik[pl][ml];
+      y_hat[o] = s_yh[pl][ml];
+    }
+  }
+}
+
 // ------------------------------------------------------------------ single Gaussian
 __global__ void __launch_bounds__(256)
 gc_fwd_kernel(const float* __restrict__ y, const float* __restrict__ scales,
@@ -489,6 +561,13 @@ extern "C" int masic_gmm_likelihood_fwd(const float* y, const float* sigma, cons
   if (k != 5) return MASIC_ENOSUP;    // HSIC hard-codes K = 5 (MASIC.py:653, test2_real.py:395)
   const View vy = mkview(in_nhwc, m, hw), vp = mkview(in_nhwc, m * k, hw), vo = mkview(out_nhwc, m, hw);
   dim3 grid((hw + 31) / 32, (m + 31) / 32, n), block(32, 8);
+  if (in_nhwc && weights_are_logits && !out_nhwc && y_hat && lik && !symbols && !yq_bf16 && (m % 4) == 0 &&
+      (reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(sigma) | reinterpret_cast<uintptr_t>(mu) |
+       reinterpret_cast<uintptr_t>(weights)) % 16 == 0) {
+    gmm_fwd_nhwc_v4_kernel<5><<<grid, dim3(8, 32), 0, static_cast<cudaStream_t>(stream)>>>(
+        y, sigma, mu, weights, m, hw, scale_bound, y_hat, lik);
+    return (int)cudaGetLastError();
+  }
   gmm_fwd_kernel<5><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
       y, vy, sigma, mu, weights, vp, weights_are_logits, in_nhwc, m, hw, scale_bound, y_hat, lik, vo,
       symbols, static_cast<__nv_bfloat16*>(yq_bf16), bf_pitch, bf_coff, f16, rowscale, rs_stride, rs_off);

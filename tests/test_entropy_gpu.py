@@ -69,6 +69,12 @@ def test_gmm_nhwc_layout_equals_nchw(dev):
                                                     0, torch.cuda.current_stream().cuda_stream), "gmm")
     assert torch.equal(y2, y_hat) and torch.equal(l2, lik)
     assert torch.equal(yq[..., 64:256].float(), nhwc(y_hat)) and float(yq[..., :64].abs().max()) == 0.0
+    # the engine's configuration (NHWC parameters, logits, NCHW outputs, nothing else): the 128-bit-load kernel
+    y3, l3 = torch.empty_like(y), torch.empty_like(y)
+    _lib.check(_lib.load().masic_gmm_likelihood_fwd(yn.data_ptr(), sn.data_ptr(), mn.data_ptr(), wn.data_ptr(), 1, 1,
+                                                    n, m, k, h * w, 0.11, y3.data_ptr(), l3.data_ptr(), None, 0,
+                                                    None, 0, 0, None, 0, 0, 0, torch.cuda.current_stream().cuda_stream), "gmm")
+    assert torch.equal(y3, y_hat) and torch.equal(l3, lik)
 
 
 def test_gmm_against_oracle_random(dev):
