@@ -247,6 +247,30 @@ int masic_range_decode_rows(MasicRangeDecoder* dec, const int32_t* rows_host, in
                             int32_t* symbols_host);
 void masic_range_decoder_destroy(MasicRangeDecoder* dec);
 
+/* --- the y payload as one range-coded stream per (view, non-zero channel): "format 2" of masic_b200/bitstream.py ---
+ * Same coder arithmetic as masic_range_encode / masic_range_decode_rows, but the symbols of channel c form their own
+ * stream, so a GPU warp per channel can decode a whole wave of positions without leaving the device.
+ * masic_range_encode_channels (HOST): intervals_host (n_pos, n_ch, 3) in coding order -> streams back to back. */
+int masic_range_encode_channels(const int32_t* intervals_host, int64_t n_pos, int n_ch, uint8_t* out_host,
+                                int64_t out_cap, int64_t* lens_host);
+/* DEVICE side of the wavefront decoder (MASIC.py:1227-1301): state is n_streams x 16 bytes of device memory, data the
+ * streams back to back in device memory, offsets (n_streams + 1) int64 byte offsets in device memory. */
+int masic_range_streams_init(const uint8_t* data, const int64_t* offsets, int n_streams, void* state, void* stream);
+/* decode one symbol per (position of the wave, stream): rows (n, n_ch, row_len) int32 from masic_gmm_symbol_cdfs;
+ * symbol - minmax is written to y_nhwc[(h*w16 + w)*m + ch] (fp32) and to the zero-padded 16-bit copy
+ * ypad16[((h+2)*(w16+4) + w+2)*m + ch]; pos_hw: n (h, w) int32 pairs; *error_flag != 0 after a corrupt stream. */
+int masic_range_decode_wave(const int32_t* rows, int n, int n_ch, int row_len, void* state, const uint8_t* data,
+                            const int64_t* offsets, const int32_t* ch_list, int minmax, const int32_t* pos_hw, int w16,
+                            int m, float* y_nhwc, void* ypad16, int f16, int* error_flag, void* stream);
+/* inputs of a wave's context conv and parameter nets in one launch: 5x5 crops of ypad16 around every position, the
+ * position's mask weights replicated over the crop (rs, right view; NULL otherwise), and channels [0, c_lo) and
+ * [c_hi0, cin) of gmm_in16 at the position -> px16 (n, cin). */
+int masic_wave_gather(const void* ypad16, int w16, int m, const void* gmm_in16, int cin, int c_lo, int c_hi0,
+                      const float* mask_weights, const int32_t* pos_hw, int n, void* crop16, float* rs, void* px16,
+                      void* stream);
+/* px16[i][c0 : c0+nc] = ctx_out16[i][2][2][c0 : c0+nc] (the centre pixel of every crop's context output) */
+int masic_wave_center(const void* ctx_out16, int cin, int c0, int nc, int n, void* px16, void* stream);
+
 /* rANS serialisation of the z side information with the byte format of the reference's `compressai.ans`
  * extension (compressai/cpp_exts/rans/rans_interface.cpp: BufferedRansEncoder.encode_with_indexes :108-173,
  * flush :175-200, RansDecoder.set_stream :270-276, decode_stream :278-343; reached from

@@ -132,6 +132,11 @@ def _declare(lib: C.CDLL) -> None:
         "masic_range_decoder_create": (i, [vp, i64, C.POINTER(vp)]),
         "masic_range_decode_rows": (i, [vp, vp, i, i, vp]),
         "masic_range_decoder_destroy": (None, [vp]),
+        "masic_range_encode_channels": (i, [vp, i64, i, vp, i64, vp]),
+        "masic_range_streams_init": (i, [vp, vp, i, vp, vp]),
+        "masic_range_decode_wave": (i, [vp, i, i, i, vp, vp, vp, vp, i, vp, i, i, vp, vp, i, vp, vp]),
+        "masic_wave_gather": (i, [vp, i, i, vp, i, i, i, vp, vp, i, vp, vp, vp, vp]),
+        "masic_wave_center": (i, [vp, i, i, i, i, vp, vp]),
         "masic_rans_encoder_create": (i, [C.POINTER(vp)]),
         "masic_rans_encoder_push": (i, [vp, vp, vp, i64, vp, i, i, vp, vp]),
         "masic_rans_encoder_flush": (i, [vp, C.POINTER(vp), C.POINTER(i64)]),

@@ -105,7 +105,8 @@ class _PixelModel:
         return self.sig, self.mu, self.wl
 
 
-ORDER_RASTER, ORDER_WAVE = 0, 1
+ORDER_RASTER, ORDER_WAVE, ORDER_WAVE_STREAMS = 0, 1, 2
+_ORDERS = {"raster": ORDER_RASTER, "wavefront": ORDER_WAVE, "wavefront_streams": ORDER_WAVE_STREAMS}
 
 
 def wave_schedule(h16: int, w16: int):
@@ -192,7 +193,7 @@ def _symbol_intervals(eng: HSICEngine, tag: str, y_hat_nchw: torch.Tensor, ch: t
 
 
 def compress(model, x1: torch.Tensor, x2: torch.Tensor, h_matrix: torch.Tensor, output_name, output_path: str = "",
-             device=None, y_order: str = "wavefront") -> Dict:
+             device=None, y_order: str = "wavefront_streams") -> Dict:
     """HSIC.compress (MASIC.py:855-1158).  Batch 1, like the reference's file format."""
     if model.training:
         raise MasicError("HSIC.compress: eval mode only")
@@ -223,27 +224,47 @@ def compress(model, x1: torch.Tensor, x2: torch.Tensor, h_matrix: torch.Tensor, 
             f.write(zs[0])
     # ---- y1, y2: all coding intervals in one kernel each, one range-coded stream
     start = time.time()
-    if y_order not in ("wavefront", "raster"):
-        raise ValueError(f'y_order must be "wavefront" or "raster", got {y_order!r}')
-    order = ORDER_WAVE if y_order == "wavefront" else ORDER_RASTER
-    perm = wave_permutation(H // 16, W // 16) if order == ORDER_WAVE else None
-    ivs = []
+    if y_order not in _ORDERS:
+        raise ValueError(f'y_order must be one of {sorted(_ORDERS)}, got {y_order!r}')
+    order = _ORDERS[y_order]
+    perm = wave_permutation(H // 16, W // 16) if order != ORDER_RASTER else None
+    ivs, n_chs = [], []
     for tag in ("L", "R"):
         ch = torch.from_numpy(np.flatnonzero(flags[tag]).astype(np.int32)).to(eng.dev)
+        n_chs.append(int(ch.numel()))
         if ch.numel():
             a = _symbol_intervals(eng, tag, y_hats[tag], ch, minmaxs[tag])
             if perm is not None:          # positions in wave order, channels stay minor
                 a = a.reshape(perm.size, ch.numel(), 3)[perm].reshape(-1, 3)
             ivs.append(a)
-    iv = np.ascontiguousarray(np.concatenate(ivs, 0)) if ivs else np.zeros((0, 3), np.int32)
-    buf = np.empty(iv.shape[0] * 3 + 64, dtype=np.uint8)
-    n_out = C.c_int64()
-    check(lib.masic_range_encode(iv.ctypes.data, iv.shape[0], buf.ctypes.data, buf.size, C.byref(n_out)),
-          "masic_range_encode")
+        else:
+            ivs.append(np.zeros((0, 3), np.int32))
+    iv = np.ascontiguousarray(np.concatenate(ivs, 0))
     output2 = os.path.join(output_path, str(output_name) + ".bin")
-    with open(output2, "wb") as f:
-        f.write(bytes([order]))
-        f.write(buf[:n_out.value].tobytes())
+    if order == ORDER_WAVE_STREAMS:
+        # one range-coded stream per (view, non-zero channel): | 2 | per view: u32 n_ch, u32 len[n_ch], streams |
+        n_pos = (H // 16) * (W // 16)
+        with open(output2, "wb") as f:
+            f.write(bytes([order]))
+            for a, n_ch in zip(ivs, n_chs):
+                f.write(np.array([n_ch], dtype=np.uint32).tobytes())
+                if n_ch == 0:
+                    continue
+                a = np.ascontiguousarray(a)
+                buf = np.empty(a.shape[0] * 3 + 16 * n_ch + 64, dtype=np.uint8)
+                lens = np.zeros(n_ch, dtype=np.int64)
+                check(lib.masic_range_encode_channels(a.ctypes.data, n_pos, n_ch, buf.ctypes.data, buf.size, lens.ctypes.data),
+                      "masic_range_encode_channels")
+                f.write(lens.astype(np.uint32).tobytes())
+                f.write(buf[:int(lens.sum())].tobytes())
+    else:
+        buf = np.empty(iv.shape[0] * 3 + 64, dtype=np.uint8)
+        n_out = C.c_int64()
+        check(lib.masic_range_encode(iv.ctypes.data, iv.shape[0], buf.ctypes.data, buf.size, C.byref(n_out)),
+              "masic_range_encode")
+        with open(output2, "wb") as f:
+            f.write(bytes([order]))
+            f.write(buf[:n_out.value].tobytes())
     end = time.time()
     num_pixels = H * W * 2
     size1, size2 = os.path.getsize(output1), os.path.getsize(output2)
@@ -343,6 +364,76 @@ def _decode_view_wave(eng: HSICEngine, tag: str, dec, flag: np.ndarray, minmax: 
     return y_nhwc.permute(0, 3, 1, 2).contiguous()
 
 
+def _wave_tables(eng: HSICEngine):
+    """(h, w) of every position in wave order as an int32 device tensor, and the waves' sizes (cached on the engine)."""
+    cache = eng.__dict__.setdefault("_wave_tables", None)
+    if cache is None:
+        h16, w16 = eng.H // 16, eng.W // 16
+        waves = wave_schedule(h16, w16)
+        hw = np.concatenate([np.stack([hs, ws], 1) for hs, ws in waves]).astype(np.int32)
+        cache = eng.__dict__["_wave_tables"] = (torch.from_numpy(np.ascontiguousarray(hw)).to(eng.dev),
+                                                 [int(hs.size) for hs, _ in waves])
+    return cache
+
+
+def _decode_view_wave_gpu(eng: HSICEngine, tag: str, streams: bytes, lens: np.ndarray, flag: np.ndarray,
+                          minmax: int) -> torch.Tensor:
+    """Wavefront decode of one view with the range decoder ON THE DEVICE (payload format 2: one stream per non-zero
+    channel): per wave one gather kernel, the context conv, the parameter nets, the CDF-row kernel and the decode kernel
+    (csrc/ydecode.cu) — no host round trip inside the view.  Returns y_hat NCHW fp32 and fills eng.buf[tag.y_rnd]."""
+    lib = eng.lib
+    M, K = eng.M, eng.K
+    h16, w16 = eng.H // 16, eng.W // 16
+    pos_dev, sizes = _wave_tables(eng)
+    n_max = max(sizes)
+    cache = eng.__dict__.setdefault("_wave_models", {})
+    wm = cache.get(tag)
+    if wm is None:
+        wm = cache[tag] = _WaveModel(eng, tag, n_max)
+    gmm_in = eng.buf[f"{tag}.gmm_in"]
+    cin = wm.cin
+    ypad = torch.zeros(1, h16 + 4, w16 + 4, M, dtype=ACT, device=eng.dev)
+    y_nhwc = torch.zeros(1, h16, w16, M, dtype=torch.float32, device=eng.dev)
+    ch_np = np.flatnonzero(flag).astype(np.int32)
+    n_ch = int(ch_np.size)
+    if n_ch:
+        if lens.size != n_ch:
+            raise MasicError("y payload: the stream table does not match the header's non-zero-channel bitmap")
+        ch = torch.from_numpy(ch_np).to(eng.dev)
+        L1 = 2 * minmax + 2
+        rows = torch.empty(n_max * n_ch, L1, dtype=torch.int32, device=eng.dev)
+        data = torch.frombuffer(bytearray(streams), dtype=torch.uint8).to(eng.dev)
+        offs = torch.from_numpy(np.concatenate([[0], np.cumsum(lens.astype(np.int64))])).to(eng.dev)
+        state = torch.zeros(n_ch, 4, dtype=torch.int32, device=eng.dev)
+        err = torch.zeros(1, dtype=torch.int32, device=eng.dev)
+        check(lib.masic_range_streams_init(data.data_ptr(), offs.data_ptr(), n_ch, state.data_ptr(), _stream()),
+              "masic_range_streams_init")
+        mw = eng.mask_weights.data_ptr() if wm.right else None
+        rs = wm.rs.data_ptr() if wm.right else None
+        f16 = int(ACT == torch.float16)
+        off = 0
+        for n in sizes:
+            pp = pos_dev.data_ptr() + off * 8
+            check(lib.masic_wave_gather(ypad.data_ptr(), w16, M, gmm_in.data_ptr(), cin, 2 * M, 4 * M, mw, pp, n,
+                                        wm.crop.data_ptr(), rs, wm.px_in.data_ptr(), _stream()), "masic_wave_gather")
+            wm.ctx_plan.launch()
+            check(lib.masic_wave_center(wm.ctx_out.data_ptr(), cin, 2 * M, 2 * M, n, wm.px_in.data_ptr(), _stream()),
+                  "masic_wave_center")
+            for p in wm.tail:
+                p.launch()
+            check(lib.masic_gmm_symbol_cdfs(wm.sig.data_ptr(), wm.mu.data_ptr(), wm.wl.data_ptr(), 1, M, K, n,
+                                            ch.data_ptr(), n_ch, minmax, SCALE_BOUND, None, rows.data_ptr(), None,
+                                            _stream()), "masic_gmm_symbol_cdfs")
+            check(lib.masic_range_decode_wave(rows.data_ptr(), n, n_ch, L1, state.data_ptr(), data.data_ptr(),
+                                              offs.data_ptr(), ch.data_ptr(), minmax, pp, w16, M, y_nhwc.data_ptr(),
+                                              ypad.data_ptr(), f16, err.data_ptr(), _stream()), "masic_range_decode_wave")
+            off += n
+        if int(err.item()):
+            raise MasicError("y payload: corrupt range-coded stream (an empty or oversized coding interval)")
+    eng.buf[f"{tag}.y_rnd"].copy_(ypad[:, 2:-2, 2:-2, :])
+    return y_nhwc.permute(0, 3, 1, 2).contiguous()
+
+
 def decompress(model, x1: Optional[torch.Tensor], x2: Optional[torch.Tensor], h_matrix: torch.Tensor, output_name,
                output_path: str = "", device=None) -> Dict:
     """HSIC.decompress (MASIC.py:1161-1408).  x1 / x2 are only consulted for the device (the reference uses them
@@ -378,24 +469,47 @@ def decompress(model, x1: Optional[torch.Tensor], x2: Optional[torch.Tensor], h_
             eng.run_steps(lambda n, t=tag: n.startswith(f"{t}.h_s."))
         with open(output2, "rb") as f:
             raw = f.read()
-        if not raw or raw[0] not in (ORDER_RASTER, ORDER_WAVE):
+        if not raw or raw[0] not in (ORDER_RASTER, ORDER_WAVE, ORDER_WAVE_STREAMS):
             raise MasicError(f"{output2}: unknown symbol-order tag in the y payload")
-        decode_view = _decode_view_wave if raw[0] == ORDER_WAVE else _decode_view
-        data = np.frombuffer(raw, dtype=np.uint8)[1:].copy()
-        dec = C.c_void_p()
-        check(lib.masic_range_decoder_create(data.ctypes.data, data.size, C.byref(dec)), "masic_range_decoder_create")
-        try:
-            start = time.time()
-            o["y1_hat"].copy_(decode_view(eng, "L", dec, hdr[0][2], hdr[0][1]))
+
+        def tail_left():
             # left reconstruction, its warp, encoder1 on it and the mask-weighted prior term (:1303-1318)
-            eng.run_steps(lambda n: n.startswith("L.g_s.") or n.startswith("L.x1_hat") or n == "R.warp(x1_hat)"
+            eng.run_steps(lambda n: n.startswith("L.g_s.") or n == "R.warp(x1_hat)"
                           or n.startswith("R.g_a(enc1 on warped x1_hat)") or n.startswith("R.y1warp"))
-            o["y2_hat"].copy_(decode_view(eng, "R", dec, hdr[1][2], hdr[1][1]))
+
+        def tail_right():
             eng.run_steps(lambda n: n.startswith("R.g_s.") or n.startswith("R.after_"))
+
+        if raw[0] == ORDER_WAVE_STREAMS:
+            views, p = [], 1
+            for _ in range(2):
+                n_ch = int(np.frombuffer(raw[p:p + 4], dtype=np.uint32)[0])
+                lens = np.frombuffer(raw[p + 4:p + 4 + 4 * n_ch], dtype=np.uint32).astype(np.int64)
+                p += 4 + 4 * n_ch
+                views.append((raw[p:p + int(lens.sum())], lens))
+                p += int(lens.sum())
+            start = time.time()
+            o["y1_hat"].copy_(_decode_view_wave_gpu(eng, "L", views[0][0], views[0][1], hdr[0][2], hdr[0][1]))
+            tail_left()
+            o["y2_hat"].copy_(_decode_view_wave_gpu(eng, "R", views[1][0], views[1][1], hdr[1][2], hdr[1][1]))
+            tail_right()
             torch.cuda.synchronize(eng.dev)
             end = time.time()
-        finally:
-            lib.masic_range_decoder_destroy(dec)
+        else:
+            decode_view = _decode_view_wave if raw[0] == ORDER_WAVE else _decode_view
+            data = np.frombuffer(raw, dtype=np.uint8)[1:].copy()
+            dec = C.c_void_p()
+            check(lib.masic_range_decoder_create(data.ctypes.data, data.size, C.byref(dec)), "masic_range_decoder_create")
+            try:
+                start = time.time()
+                o["y1_hat"].copy_(decode_view(eng, "L", dec, hdr[0][2], hdr[0][1]))
+                tail_left()
+                o["y2_hat"].copy_(decode_view(eng, "R", dec, hdr[1][2], hdr[1][1]))
+                tail_right()
+                torch.cuda.synchronize(eng.dev)
+                end = time.time()
+            finally:
+                lib.masic_range_decoder_destroy(dec)
     return {"x1_hat": o["x1_hat"].clone(), "x2_hat": o["x2_hat"].clone(), "y1_hat": o["y1_hat"].clone(),
             "y2_hat": o["y2_hat"].clone(), "z1_hat": o["z1_hat"].clone(), "z2_hat": o["z2_hat"].clone(),
             "dectime": end - start}

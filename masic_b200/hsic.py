@@ -274,9 +274,10 @@ class HSIC(nn.Module):
         return HSICTrainer(self, batch, height, width, device, lmbda=lmbda)
 
     # ---- bitstreams (MASIC.py:855-1158, :1161-1408)
-    def compress(self, x1, x2, h_matrix, output_name, output_path="", device="cpu", y_order="wavefront"):
-        """y_order: "wavefront" (default; symbols coded wave by wave so that the decoder runs (W/16 + 3(H/16-1)) batched
-        steps) or "raster" (the reference's order, per-position decoder).  See masic_b200/bitstream.py."""
+    def compress(self, x1, x2, h_matrix, output_name, output_path="", device="cpu", y_order="wavefront_streams"):
+        """y_order: "wavefront_streams" (default: positions coded wave by wave, one range-coded stream per non-zero
+        channel, decoded entirely on the device), "wavefront" (wave order, a single stream, host range decoder) or
+        "raster" (the reference's order, per-position decoder).  See masic_b200/bitstream.py."""
         from .bitstream import compress
         return compress(self, x1, x2, h_matrix, output_name, output_path, device, y_order=y_order)
 

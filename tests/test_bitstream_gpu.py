@@ -102,7 +102,7 @@ def test_symbol_cdf_rows_are_identical_to_the_reference_rule(dev, minmax, P, M):
     print(f"minmax {minmax}: rows identical to the torch-CUDA rule; {differing} counts differ from the CPU oracle (erfc ulp)")
 
 
-@pytest.mark.parametrize("y_order", ["wavefront", "raster"])
+@pytest.mark.parametrize("y_order", ["wavefront_streams", "wavefront", "raster"])
 def test_compress_decompress_round_trip(dev, tmp_path, y_order):
     from masic_b200.hsic import HSIC
     from oracle.hsic import synthetic_homography
@@ -122,8 +122,8 @@ def test_compress_decompress_round_trip(dev, tmp_path, y_order):
         enc = net.compress(x1, x2, Hm, "pair0", str(tmp_path), y_order=y_order)
     assert torch.equal(enc["y1_hat"], fwd["y1_hat"])
     assert enc["n_symbols"] > 0
-    # the range coder lands within a fraction of a percent (+ a few flush bytes) of the ideal code length
-    assert enc["y_bytes"] * 8 <= enc["y_bits_ideal"] * 1.002 + 64
+    # the range coder lands within a fraction of a percent (+ a few flush bytes per stream) of the ideal code length
+    assert enc["y_bytes"] * 8 <= enc["y_bits_ideal"] * 1.002 + 64 + (80 * 384 if y_order == "wavefront_streams" else 0)
     # estimated bits (likelihoods over ALL channels on the unbounded support) bound the coder's ideal length from
     # above: the file skips all-zero channels and renormalises each pmf on [-minmax, minmax] (MASIC.py:925-940,1040)
     est_y = sum(float(torch.log(fwd["likelihoods"][k]).sum()) for k in ("y1", "y2")) / (-math.log(2))
@@ -158,6 +158,11 @@ def test_wave_and_raster_orders_cost_the_same_bits(dev, tmp_path):
     assert a["n_symbols"] == b["n_symbols"]
     assert abs(a["y_bits_ideal"] - b["y_bits_ideal"]) <= 1e-6 * b["y_bits_ideal"]
     assert abs(a["y_bytes"] - b["y_bytes"]) <= 8
+    with torch.no_grad():
+        c = net.compress(x1, x2, Hm, "c", str(tmp_path), y_order="wavefront_streams")
+    assert c["n_symbols"] == a["n_symbols"] and abs(c["y_bits_ideal"] - a["y_bits_ideal"]) <= 1e-6 * a["y_bits_ideal"]
+    n_streams = c["n_symbols"] // ((64 // 16) * (128 // 16))        # symbols per position = non-zero channels of both views
+    assert 0 <= c["y_bytes"] - a["y_bytes"] <= 12 * n_streams + 16   # per stream: 4-byte length + <= 6 flush bytes
 
 
 def test_full_size_round_trip_wavefront(dev, tmp_path):
@@ -181,9 +186,16 @@ def test_full_size_round_trip_wavefront(dev, tmp_path):
         enc = net.compress(x1, x2, Hm, "full", str(tmp_path))
         dec = net.decompress(x1, x2, Hm, "full", str(tmp_path), device=dev)
     assert enc["n_symbols"] > 1_000_000
-    assert enc["y_bytes"] * 8 <= enc["y_bits_ideal"] * 1.001 + 64
+    assert enc["y_bytes"] * 8 <= enc["y_bits_ideal"] * 1.001 + 64 + 80 * 384       # 384 streams: table entry + flush bytes each
     for k in ("y1_hat", "y2_hat", "z1_hat", "z2_hat"):
         assert torch.equal(dec[k], enc[k]), k
     assert torch.equal(dec["y1_hat"], fwd["y1_hat"]) and torch.equal(dec["x1_hat"], fwd["x1_hat"])
     assert torch.equal(dec["x2_hat"], fwd["x2_hat"])
     assert dec["dectime"] < 5.0
+    # the same file through the host decoder path of the single-stream wave format costs the same bits
+    with torch.no_grad():
+        enc1 = net.compress(x1, x2, Hm, "full1", str(tmp_path), y_order="wavefront")
+        dec1 = net.decompress(x1, x2, Hm, "full1", str(tmp_path), device=dev)
+    assert torch.equal(dec1["y2_hat"], dec["y2_hat"]) and torch.equal(dec1["x2_hat"], dec["x2_hat"])
+    print(f"1216x2176: device decoder {dec['dectime'] * 1e3:.1f} ms, host decoder {dec1['dectime'] * 1e3:.1f} ms; "
+          f"payload {enc['y_bytes']} vs {enc1['y_bytes']} bytes")
