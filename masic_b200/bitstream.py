@@ -411,23 +411,28 @@ def _decode_view_wave_gpu(eng: HSICEngine, tag: str, streams: bytes, lens: np.nd
         mw = eng.mask_weights.data_ptr() if wm.right else None
         rs = wm.rs.data_ptr() if wm.right else None
         f16 = int(ACT == torch.float16)
-        off = 0
+        # the loop below issues ~8700 launches at full size: every pointer and the stream are resolved once, and the
+        # status codes are OR-ed and checked after the loop (the host side of the loop is what bounds the decode time)
+        st = _stream()
+        p_ypad, p_gmm, p_crop, p_px, p_ctx = (t.data_ptr() for t in (ypad, gmm_in, wm.crop, wm.px_in, wm.ctx_out))
+        p_sig, p_mu, p_wl, p_ch, p_rows = (t.data_ptr() for t in (wm.sig, wm.mu, wm.wl, ch, rows))
+        p_state, p_data, p_offs, p_y, p_err, p_pos = (t.data_ptr() for t in (state, data, offs, y_nhwc, err, pos_dev))
+        plan_handles = [wm.ctx_plan._h] + [p._h for p in wm.tail]
+        launch = lib.masic_conv_plan_launch
+        gather, center, cdfs, decode = (lib.masic_wave_gather, lib.masic_wave_center, lib.masic_gmm_symbol_cdfs,
+                                        lib.masic_range_decode_wave)
+        off, rc = 0, 0
         for n in sizes:
-            pp = pos_dev.data_ptr() + off * 8
-            check(lib.masic_wave_gather(ypad.data_ptr(), w16, M, gmm_in.data_ptr(), cin, 2 * M, 4 * M, mw, pp, n,
-                                        wm.crop.data_ptr(), rs, wm.px_in.data_ptr(), _stream()), "masic_wave_gather")
-            wm.ctx_plan.launch()
-            check(lib.masic_wave_center(wm.ctx_out.data_ptr(), cin, 2 * M, 2 * M, n, wm.px_in.data_ptr(), _stream()),
-                  "masic_wave_center")
-            for p in wm.tail:
-                p.launch()
-            check(lib.masic_gmm_symbol_cdfs(wm.sig.data_ptr(), wm.mu.data_ptr(), wm.wl.data_ptr(), 1, M, K, n,
-                                            ch.data_ptr(), n_ch, minmax, SCALE_BOUND, None, rows.data_ptr(), None,
-                                            _stream()), "masic_gmm_symbol_cdfs")
-            check(lib.masic_range_decode_wave(rows.data_ptr(), n, n_ch, L1, state.data_ptr(), data.data_ptr(),
-                                              offs.data_ptr(), ch.data_ptr(), minmax, pp, w16, M, y_nhwc.data_ptr(),
-                                              ypad.data_ptr(), f16, err.data_ptr(), _stream()), "masic_range_decode_wave")
+            pp = p_pos + off * 8
+            rc |= gather(p_ypad, w16, M, p_gmm, cin, 2 * M, 4 * M, mw, pp, n, p_crop, rs, p_px, st)
+            rc |= launch(plan_handles[0], st)
+            rc |= center(p_ctx, cin, 2 * M, 2 * M, n, p_px, st)
+            for h in plan_handles[1:]:
+                rc |= launch(h, st)
+            rc |= cdfs(p_sig, p_mu, p_wl, 1, M, K, n, p_ch, n_ch, minmax, SCALE_BOUND, None, p_rows, None, st)
+            rc |= decode(p_rows, n, n_ch, L1, p_state, p_data, p_offs, p_ch, minmax, pp, w16, M, p_y, p_ypad, f16, p_err, st)
             off += n
+        check(rc, "wavefront decode (masic_wave_gather / conv plans / masic_gmm_symbol_cdfs / masic_range_decode_wave)")
         if int(err.item()):
             raise MasicError("y payload: corrupt range-coded stream (an empty or oversized coding interval)")
     eng.buf[f"{tag}.y_rnd"].copy_(ypad[:, 2:-2, 2:-2, :])

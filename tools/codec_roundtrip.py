@@ -13,7 +13,7 @@ from masic_b200.hsic import HSIC  # noqa: E402
 
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
 H, W = (int(args[0]), int(args[1])) if len(args) >= 2 else (1216, 2176)
-orders = ["wavefront"] + (["raster"] if "--raster" in sys.argv else [])
+orders = ["wavefront_streams", "wavefront"] + (["raster"] if "--raster" in sys.argv else [])
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 net = HSIC().eval()
