@@ -116,6 +116,10 @@ typedef struct MasicConvDesc {
    * output: MASIC_FMT_BF16 (training step: gradients need fp32's exponent range) or MASIC_FMT_F16 (inference engines:
    * 11 significant bits instead of 8, same tensor-core rate; conversions saturate at +-65504). */
   int f16;
+  /* 1: launch with programmatic stream serialization (PDL): the kernel's prologue (barrier init, TMEM allocation,
+   * tensor-map prefetch) overlaps the tail of the previous kernel in the stream, and it lets the NEXT kernel's CTAs be
+   * scheduled as soon as SMs free up.  Pays off on chains of tiny launches (the wavefront decoder's per-wave model). */
+  int pdl;
 } MasicConvDesc;
 
 typedef struct MasicConvPlan MasicConvPlan;   /* opaque: tensor maps + tile program */

@@ -49,7 +49,7 @@ class ConvDesc(C.Structure):
         ("residual0", C.c_void_p), ("res0_cpitch", C.c_int), ("res0_coff", C.c_int),
         ("residual1", C.c_void_p), ("res1_cpitch", C.c_int), ("res1_coff", C.c_int),
         ("nt_in_coff", C.POINTER(C.c_int)), ("nt_out_coff", C.POINTER(C.c_int)), ("nt_out_img", C.POINTER(C.c_int)),
-        ("out_images", C.c_int), ("cta_pairs", C.c_int), ("f16", C.c_int),
+        ("out_images", C.c_int), ("cta_pairs", C.c_int), ("f16", C.c_int), ("pdl", C.c_int),
     ]
 
 

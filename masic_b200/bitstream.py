@@ -144,19 +144,25 @@ class _WaveModel:
         self.ctx_out = z(n_max, 5, 5, cin)
         self.rs = z(n_max, 5, 5, 3, dtype=f32) if self.right else None
         self.px_in = z(1, 1, n_max, cin)
-        self.l0, self.l1, self.l1w = z(1, 1, n_max, 18 * M), z(1, 1, n_max, 8 * M), z(1, 1, n_max, MK)
-        self.sig, self.mu, self.wl = (z(1, 1, n_max, MK, dtype=f32) for _ in range(3))
+        # the parameter nets exactly as HSICEngine._gmm_net launches them: layer 0 of the three branches as one wide
+        # GEMM, layer 1 as one grouped launch, layer 2 as sigma|means grouped + weights (4 launches instead of 7)
+        self.l0, self.l1 = z(1, 1, n_max, 18 * M), z(1, 1, n_max, 13 * M)
+        smw = z(3, 1, n_max, MK, dtype=f32)
+        self.sig, self.mu, self.wl = smw[0:1], smw[1:2], smw[2:3]
         pk = eng.packs
+        nt = lambda c: c // 192   # noqa: E731
+        tiles = list(range(0, MK, 192))
         self.ctx_plan = ConvPlan(packed=pk[f"{tag}.context"], stride=1, tap_mask=MASK_A_5x5, x=self.crop,
-                                 out=self.ctx_out, out_coff=2 * M, rowscale=self.rs, rs_off=1)
+                                 out=self.ctx_out, out_coff=2 * M, rowscale=self.rs, rs_off=1, pdl=True)
         self.tail = [
-            ConvPlan(packed=pk[f"{tag}.gmm.l0"], x=self.px_in, out=self.l0, act=[ACT_RELU] * 6 + [ACT_LEAKY] * 12),
-            ConvPlan(packed=pk[f"{tag}.gmm.sigma.l1"], x=self.l0, out=self.l1, in_coff=0, out_coff=0, act=ACT_RELU),
-            ConvPlan(packed=pk[f"{tag}.gmm.means.l1"], x=self.l0, out=self.l1, in_coff=6 * M, out_coff=4 * M, act=ACT_LEAKY),
-            ConvPlan(packed=pk[f"{tag}.gmm.weights.l1"], x=self.l0, out=self.l1w, in_coff=12 * M, act=ACT_LEAKY),
-            ConvPlan(packed=pk[f"{tag}.gmm.sigma.l2"], x=self.l1, out=self.sig, in_coff=0, act=ACT_RELU),
-            ConvPlan(packed=pk[f"{tag}.gmm.means.l2"], x=self.l1, out=self.mu, in_coff=4 * M),
-            ConvPlan(packed=pk[f"{tag}.gmm.weights.l2"], x=self.l1w, out=self.wl),
+            ConvPlan(packed=pk[f"{tag}.gmm.l0"], x=self.px_in, out=self.l0, act=[ACT_RELU] * 6 + [ACT_LEAKY] * 12, pdl=True),
+            ConvPlan(packed=pk[f"{tag}.gmm.l1(3 branches)"], x=self.l0, out=self.l1,
+                     act=[ACT_RELU] * nt(4 * M) + [ACT_LEAKY] * nt(9 * M),
+                     nt_in_coff=[0] * nt(4 * M) + [6 * M] * nt(4 * M) + [12 * M] * nt(5 * M), pdl=True),
+            ConvPlan(packed=pk[f"{tag}.gmm.l2(sigma|means)"], x=self.l1, out=smw, act=[ACT_RELU] * nt(MK) + [ACT_NONE] * nt(MK),
+                     nt_in_coff=[0] * nt(MK) + [4 * M] * nt(MK), nt_out_coff=tiles + tiles,
+                     nt_out_img=[0] * nt(MK) + [1] * nt(MK), pdl=True),
+            ConvPlan(packed=pk[f"{tag}.gmm.weights.l2"], x=self.l1, out=self.wl, in_coff=8 * M, pdl=True),
         ]
 
     def params_at(self, ypad_flat: torch.Tensor, gmm_flat: torch.Tensor, crop_idx: torch.Tensor, pos: torch.Tensor):

@@ -155,7 +155,7 @@ class ConvPlan:
                  residual0: Optional[torch.Tensor] = None, res0_coff: int = 0,
                  residual1: Optional[torch.Tensor] = None, res1_coff: int = 0,
                  nt_in_coff: Optional[Sequence[int]] = None, nt_out_coff: Optional[Sequence[int]] = None,
-                 nt_out_img: Optional[Sequence[int]] = None, cta_pairs: bool = False):
+                 nt_out_img: Optional[Sequence[int]] = None, cta_pairs: bool = False, pdl: bool = False):
         lib = _lib.load()
         assert x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and x.dim() == 4 and x.is_contiguous()
         assert out.is_cuda and out.dim() == 4 and out.is_contiguous()
@@ -217,6 +217,7 @@ class ConvPlan:
             assert out.shape[0] == n, (out.shape, n)
         d.cta_pairs = int(cta_pairs)
         d.f16 = packed.f16
+        d.pdl = int(pdl)
         self._desc = d
         handle = C.c_void_p()
         check(lib.masic_conv_plan_create(C.byref(d), C.byref(handle)), "masic_conv_plan_create")

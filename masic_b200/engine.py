@@ -254,6 +254,7 @@ class HSICEngine:
         w1 = torch.cat([mat(b_, 2) for b_ in br], dim=0).reshape(13 * M, 6 * M, 1, 1).contiguous()
         b1 = torch.cat([self._w(f"{net}.{b_}.2.bias") for b_ in br])
         p1 = PackedConv(ksize=1, c_in=6 * M, c_out=13 * M, n_tile=192, weight=w1, bias=b1, f16=F16)
+        self.packs[f"{tag}.gmm.l1(3 branches)"] = p1            # the wave decoder runs the same grouped launches
         plan = ConvPlan(packed=p1, x=l0, out=l1, act=[ACT_RELU] * nt(4 * M) + [ACT_LEAKY] * nt(9 * M),
                         nt_in_coff=[0] * nt(4 * M) + [6 * M] * nt(4 * M) + [12 * M] * nt(5 * M))
         self.plans[f"{tag}.gmm.l1(3 branches)"] = plan
@@ -263,6 +264,7 @@ class HSICEngine:
         w2 = torch.cat([mat("gmm_sigma", 4), mat("gmm_means", 4)], dim=0).reshape(2 * MK, 4 * M, 1, 1).contiguous()
         b2 = torch.cat([self._w(f"{net}.gmm_sigma.4.bias"), self._w(f"{net}.gmm_means.4.bias")])
         p2 = PackedConv(ksize=1, c_in=4 * M, c_out=2 * MK, n_tile=192, weight=w2, bias=b2, f16=F16)
+        self.packs[f"{tag}.gmm.l2(sigma|means)"] = p2
         tiles = list(range(0, MK, 192))
         plan = ConvPlan(packed=p2, x=l1, out=smw, act=[ACT_RELU] * nt(MK) + [ACT_NONE] * nt(MK),
                         nt_in_coff=[0] * nt(MK) + [4 * M] * nt(MK), nt_out_coff=tiles + tiles,
