@@ -11,9 +11,10 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from masic_b200.hsic import HSIC  # noqa: E402
 
-DEFAULT = ["L.g_a.conv1+gdn", "L.g_a.conv2+gdn", "L.g_a.conv4", "L.g_s.deconv3+igdn", "L.g_s.deconv4(subpix)",
-           "L.gmm.l0", "L.gmm.l2(sigma|means)", "L.gmm_likelihood", "R.warp(x1)", "R.pre_conv+pre_gdn", "R.after_conv",
-           "L.x1_hat(unshuffle)", "L.entropy_bottleneck", "x1.pack_nhwc", "L.latent_prep"]
+DEFAULT = ["L.g_a.conv1+gdn", "L.g_a.conv2+gdn", "L.g_a.conv3+gdn", "L.g_a.conv4", "L.g_s.deconv3+igdn",
+           "L.g_s.deconv4(col2im)", "R.g_s.deconv4(col2im)", "L.gmm.l0", "L.gmm.l1", "L.gmm.l2(sigma|means)",
+           "L.gmm_likelihood", "R.warp(x1)", "R.pre_conv+pre_gdn", "R.after_conv", "L.h_a.conv2", "L.h_s.conv3x3",
+           "L.context", "L.entropy_bottleneck", "x1.pack_nhwc", "L.latent_prep"]
 
 want = sys.argv[1:] or DEFAULT
 if want == ["ALL"]:          # every launch of one step (e.g. `--metrics dram__bytes_read.sum,dram__bytes_write.sum`)

@@ -15,7 +15,7 @@ i_id, i_k, i_m, i_v = hdr.index("ID"), hdr.index("Kernel Name"), hdr.index("Metr
 per = defaultdict(dict)
 for r in rows[1:]:
     per[(r[i_id], r[i_k])][r[i_m]] = float(r[i_v].replace(",", ""))
-conv = [v for (_, k), v in per.items() if "conv_tc_kernel" in k]
+conv = [v for (_, k), v in per.items() if "conv_tc_kernel" in k or "deconv_img_kernel" in k]     # the tcgen05 kernels
 allk = list(per.values())
 b = lambda v: v.get("dram__bytes_read.sum", 0.0) + v.get("dram__bytes_write.sum", 0.0)
 out = {
