@@ -3,15 +3,35 @@ the reference's training step, pinned to the unmodified reference in tests/test_
 seeded weights, inputs and quantisation noise.
 
 Tolerances: the CUDA path feeds the tensor cores bf16 activations / gradients with fp32 accumulation, the oracle is
-fp32 throughout; per parameter tensor the gradient must agree in direction (cosine >= COS_MIN) and magnitude
-(|norm ratio - 1| <= NORM_RTOL); loss / bpp / mse to 0.1 % (the north-star's bpp tolerance)."""
+fp32 throughout; per parameter tensor the gradient must agree in direction and magnitude within the per-module
+tolerances of TOL below; loss / bpp / mse to 0.5 %."""
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
 
-COS_MIN = 0.99
-NORM_RTOL = 0.05
+# per parameter tensor: (cosine >=, |norm ratio - 1| <=), by the module the tensor belongs to.  Measured margins of the
+# round are in profiles/r2_train_gradients.json (median cosine over the 166 tensors: 0.99999).
+#  * main transforms (encoder1/2, decoder1/2 = g_a / g_s stacks, pre/after convs) and the entropy bottlenecks:
+#    measured cos >= 0.99997, norm within 0.7 %;
+#  * hyper-prior / context / entropy-parameter nets: their gradient is the rate term's, d(-log2 lik)/d(sigma, mu, w),
+#    which divides by likelihoods as small as 1e-9: bf16 noise on sigma / mu (3 significant digits) moves c/lik by
+#    percents for the few elements that dominate the sum at these tiny test sizes (4x8 .. 8x12 latents); measured
+#    cos >= 0.994, norm within 2.5 %;
+#  * mask2weights: three 3-channel convs whose gradient arrives through the softmax of a 1/16-resolution map and is
+#    accumulated with atomics; measured cos >= 0.9995, norm within 2.5 %.
+TOL = {"main": (0.9999, 0.01), "rate": (0.99, 0.03), "mask": (0.999, 0.03)}
+
+
+def _tol_class(name):
+    head = name.split(".")[0]
+    if head.startswith(("encoder", "decoder", "entropy_bottleneck")):
+        return "main"
+    if head.startswith("mask2weights"):
+        return "mask"
+    return "rate"
+
+
 LOSS_RTOL = 5e-3      # train mode has no rounding to absorb bf16 activation noise: y + U(-.5,.5) enters the likelihood directly
 
 
@@ -42,6 +62,24 @@ def _setup(batch, h, w, scale, dev):
     return oracle, net, x1, x2, Hm, noise
 
 
+def _record_margins(case, margins, res, want):
+    """Measured per-tensor margins -> gpurun_out/r2_train_gradients.jsonl (copied to profiles/ at the end of a round)."""
+    import json
+    from pathlib import Path
+    out = Path(__file__).resolve().parents[1] / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    worst = sorted(margins, key=lambda t: t[1])[:12]
+    rec = {"case": case, "tensors": len(margins), "cos_min": min(m[1] for m in margins),
+           "cos_median": sorted(m[1] for m in margins)[len(margins) // 2],
+           "norm_ratio_min": min(m[2] for m in margins), "norm_ratio_max": max(m[2] for m in margins),
+           "loss_cuda": res["loss"], "loss_oracle": want[0], "bpp_cuda": res["bpp"], "bpp_oracle": want[1],
+           "mse_cuda": res["mse"], "mse_oracle": want[2],
+           "worst_cos": [[n, round(c, 6), round(r, 5)] for n, c, r in worst],
+           "all": [[n, round(c, 6), round(r, 5)] for n, c, r in margins]}
+    with open(out / "r2_train_gradients.jsonl", "a") as f:
+        f.write(json.dumps(rec) + "\n")
+
+
 @pytest.mark.parametrize("batch,h,w,scale", [(2, 64, 128, 8.0), (1, 128, 192, 1.0)])
 def test_training_step_gradients_match_oracle(dev, batch, h, w, scale):
     from masic_b200.trainer import HSICTrainer
@@ -57,7 +95,7 @@ def test_training_step_gradients_match_oracle(dev, batch, h, w, scale):
     assert res["mse"] == pytest.approx(mse, rel=LOSS_RTOL)
     assert res["loss"] == pytest.approx(loss, rel=LOSS_RTOL)
     assert res["aux"] == pytest.approx(aux, rel=1e-5)
-    bad = []
+    bad, margins = [], []
     for name, p in torch.nn.Module.named_parameters(net):
         want = grads[name].double()
         got = p.grad.detach().cpu().double()
@@ -69,9 +107,12 @@ def test_training_step_gradients_match_oracle(dev, batch, h, w, scale):
             assert ng < 1e-9, name
             continue
         cos = float((want * got).sum() / (nw * ng + 1e-300))
-        if cos < COS_MIN or abs(ng / nw - 1.0) > NORM_RTOL:
+        margins.append((name, cos, ng / nw))
+        cos_min, norm_rtol = TOL[_tol_class(name)]
+        if cos < cos_min or abs(ng / nw - 1.0) > norm_rtol:
             bad.append((name, round(cos, 5), round(ng / nw, 4), nw))
     print("\n".join(str(b) for b in bad))
+    _record_margins(f"b{batch}_{h}x{w}_scale{scale:g}", margins, res, (loss, bpp, mse, aux))
     assert not bad, f"{len(bad)} of {len(grads)} parameter gradients out of tolerance"
     # second step with unchanged weights and inputs reproduces the first (buffers are re-zeroed, weights re-packed)
     g1 = tr.flat_grad.clone()
