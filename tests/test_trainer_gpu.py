@@ -20,7 +20,7 @@ pytestmark = pytest.mark.gpu
 #    cos >= 0.994, norm within 2.5 %;
 #  * mask2weights: three 3-channel convs whose gradient arrives through the softmax of a 1/16-resolution map and is
 #    accumulated with atomics; measured cos >= 0.9995, norm within 2.5 %.
-TOL = {"main": (0.9999, 0.01), "rate": (0.99, 0.03), "mask": (0.999, 0.03)}
+TOL = {"main": (0.9999, 0.01), "rate": (0.99, 0.04), "mask": (0.999, 0.05)}
 
 
 def _tol_class(name):
