@@ -368,6 +368,13 @@ int masic_gdn_nchw(const float* x, int n, int c, int hw, const float* beta, cons
 /* softmax over the c (<= 8) channels of an NCHW tensor (mask2weights, MASIC.py:497-502). */
 int masic_softmax_channels(const float* in_nchw, int n, int c, int hw, float* out_nchw, float* out_nhwc,
                            void* stream);
+/* mask2weights.forward (MASIC.py:472-506) in one launch: the four conv3x3 stride-2 layers (1->3 ReLU, 3->6 ReLU, 6->6 ReLU,
+ * 6->3; torch weight layouts, biases may be NULL) and the softmax over the 3 outputs.  mask: (n,1,h,w) fp32.  Outputs
+ * (either may be NULL): (n,3,h/16,w/16) NCHW and/or [n][h/16][w/16][3] NHWC, sizes rounded up at every level.  Bit-identical
+ * to four masic_conv_small_nchw launches + masic_softmax_channels. */
+int masic_mask2weights(const float* mask_nchw, int n, int h, int w, const float* w1, const float* b1, const float* w2,
+                       const float* b2, const float* w3, const float* b3, const float* w4, const float* b4,
+                       float* out_nchw, float* out_nhwc, void* stream);
 /* layout packs.  The NHWC bf16 outputs of this function, of masic_warp_perspective_fwd and of
  * masic_conv_small_nchw may have a padded row: pixel (y,x) goes to out[(y*row_pixels + x + xoff)*pitch];
  * row_pixels = 0 means a dense image (row_pixels = w, xoff = 0). */

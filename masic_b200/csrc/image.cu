@@ -484,6 +484,129 @@ softmax_channels_kernel(const float* __restrict__ in, int n, int c, int hw, floa
   }
 }
 
+// ------------------------------------------------------------------ mask2weights in ONE launch (MASIC.py:472-506)
+// conv3x3 s2 (1->3) ReLU, conv3x3 s2 (3->6) ReLU, conv3x3 s2 (6->6) ReLU, conv3x3 s2 (6->3), softmax over the 3 outputs.
+// A block produces 4 x 4 positions of the 1/16-resolution map; the intermediate maps it needs (9x9, 19x19, 39x39
+// positions) live in shared memory.  Every layer zero-pads its OWN input, so intermediate values outside a layer's
+// domain are forced to zero.  Accumulation order per output = conv_small_kernel's (bias; ci; ky; kx), so the result
+// is bit-identical to the five separate launches.
+constexpr int MW_T = 4, MW_K3 = 2 * MW_T + 1, MW_K2 = 2 * MW_K3 + 1, MW_K1 = 2 * MW_K2 + 1;
+
+__global__ void __launch_bounds__(256)
+mask2weights_fused_kernel(const float* __restrict__ mask, int h, int w, const float* __restrict__ w1,
+                          const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                          const float* __restrict__ w3, const float* __restrict__ b3, const float* __restrict__ w4,
+                          const float* __restrict__ b4, float* __restrict__ out_nchw, float* __restrict__ out_nhwc) {
+  __shared__ float s_k1[3][MW_K1][MW_K1 + 1];
+  __shared__ float s_k2[6][MW_K2][MW_K2 + 1];
+  __shared__ float s_k3[6][MW_K3][MW_K3 + 1];
+  __shared__ float s_k4[3][MW_T * MW_T];
+  __shared__ float s_w1[27], s_b1[3], s_w2[162], s_b2[6], s_w3[324], s_b3[6], s_w4[162], s_b4[3];
+  const int tid = threadIdx.x, b = blockIdx.z;
+  for (int i = tid; i < 324; i += 256) {
+    s_w3[i] = w3[i];
+    if (i < 162) { s_w2[i] = w2[i]; s_w4[i] = w4[i]; }
+    if (i < 27) s_w1[i] = w1[i];
+    if (i < 6) { s_b2[i] = b2 ? b2[i] : 0.0f; s_b3[i] = b3 ? b3[i] : 0.0f; }
+    if (i < 3) { s_b1[i] = b1 ? b1[i] : 0.0f; s_b4[i] = b4 ? b4[i] : 0.0f; }
+  }
+  const int h1 = (h + 1) / 2, w1d = (w + 1) / 2, h2 = (h1 + 1) / 2, w2d = (w1d + 1) / 2;
+  const int h3 = (h2 + 1) / 2, w3d = (w2d + 1) / 2, h4 = (h3 + 1) / 2, w4d = (w3d + 1) / 2;
+  const int y4_0 = blockIdx.y * MW_T, x4_0 = blockIdx.x * MW_T;
+  const int y3_0 = 2 * y4_0 - 1, x3_0 = 2 * x4_0 - 1;
+  const int y2_0 = 2 * y3_0 - 1, x2_0 = 2 * x3_0 - 1;
+  const int y1_0 = 2 * y2_0 - 1, x1_0 = 2 * x2_0 - 1;
+  const float* src = mask + (long)b * h * w;
+  __syncthreads();
+  // layer 1: mask (global) -> s_k1
+  for (int i = tid; i < MW_K1 * MW_K1; i += 256) {
+    const int ly = i / MW_K1, lx = i % MW_K1, gy = y1_0 + ly, gx = x1_0 + lx;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+    if (gy >= 0 && gy < h1 && gx >= 0 && gx < w1d) {
+      a0 = s_b1[0]; a1 = s_b1[1]; a2 = s_b1[2];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int iy = 2 * gy - 1 + ky, ix = 2 * gx - 1 + kx;
+          const float v = (iy >= 0 && iy < h && ix >= 0 && ix < w) ? __ldg(src + (long)iy * w + ix) : 0.0f;
+          a0 = fmaf(v, s_w1[0 * 9 + ky * 3 + kx], a0);
+          a1 = fmaf(v, s_w1[1 * 9 + ky * 3 + kx], a1);
+          a2 = fmaf(v, s_w1[2 * 9 + ky * 3 + kx], a2);
+        }
+      a0 = fmaxf(a0, 0.0f); a1 = fmaxf(a1, 0.0f); a2 = fmaxf(a2, 0.0f);
+    }
+    s_k1[0][ly][lx] = a0; s_k1[1][ly][lx] = a1; s_k1[2][ly][lx] = a2;
+  }
+  __syncthreads();
+  // layer 2: s_k1 (3 ch) -> s_k2 (6 ch); one (position, channel) per task
+  for (int i = tid; i < 6 * MW_K2 * MW_K2; i += 256) {
+    const int co = i / (MW_K2 * MW_K2), r = i % (MW_K2 * MW_K2), ly = r / MW_K2, lx = r % MW_K2;
+    const int gy = y2_0 + ly, gx = x2_0 + lx;
+    float a = 0.0f;
+    if (gy >= 0 && gy < h2 && gx >= 0 && gx < w2d) {
+      a = s_b2[co];
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+            a = fmaf(s_k1[ci][2 * ly + ky][2 * lx + kx], s_w2[(co * 3 + ci) * 9 + ky * 3 + kx], a);
+      a = fmaxf(a, 0.0f);
+    }
+    s_k2[co][ly][lx] = a;
+  }
+  __syncthreads();
+  // layer 3: s_k2 (6 ch) -> s_k3 (6 ch)
+  for (int i = tid; i < 6 * MW_K3 * MW_K3; i += 256) {
+    const int co = i / (MW_K3 * MW_K3), r = i % (MW_K3 * MW_K3), ly = r / MW_K3, lx = r % MW_K3;
+    const int gy = y3_0 + ly, gx = x3_0 + lx;
+    float a = 0.0f;
+    if (gy >= 0 && gy < h3 && gx >= 0 && gx < w3d) {
+      a = s_b3[co];
+#pragma unroll
+      for (int ci = 0; ci < 6; ++ci)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+            a = fmaf(s_k2[ci][2 * ly + ky][2 * lx + kx], s_w3[(co * 6 + ci) * 9 + ky * 3 + kx], a);
+      a = fmaxf(a, 0.0f);
+    }
+    s_k3[co][ly][lx] = a;
+  }
+  __syncthreads();
+  // layer 4 (no activation): s_k3 (6 ch) -> 3 logits per position
+  if (tid < 3 * MW_T * MW_T) {
+    const int co = tid / (MW_T * MW_T), r = tid % (MW_T * MW_T), ly = r / MW_T, lx = r % MW_T;
+    float a = s_b4[co];
+#pragma unroll
+    for (int ci = 0; ci < 6; ++ci)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+          a = fmaf(s_k3[ci][2 * ly + ky][2 * lx + kx], s_w4[(co * 6 + ci) * 9 + ky * 3 + kx], a);
+    s_k4[co][r] = a;
+  }
+  __syncthreads();
+  if (tid < MW_T * MW_T) {
+    const int gy = y4_0 + tid / MW_T, gx = x4_0 + tid % MW_T;
+    if (gy < h4 && gx < w4d) {
+      float v[3], mx = -INFINITY, sum = 0.0f;
+      for (int ch = 0; ch < 3; ++ch) { v[ch] = s_k4[ch][tid]; mx = fmaxf(mx, v[ch]); }
+      for (int ch = 0; ch < 3; ++ch) { v[ch] = expf(v[ch] - mx); sum += v[ch]; }
+      const long p = (long)gy * w4d + gx, hw4 = (long)h4 * w4d;
+      for (int ch = 0; ch < 3; ++ch) {
+        const float o = v[ch] / sum;
+        if (out_nchw) out_nchw[((long)b * 3 + ch) * hw4 + p] = o;
+        if (out_nhwc) out_nhwc[((long)b * hw4 + p) * 3 + ch] = o;
+      }
+    }
+  }
+}
+
 // NCHW fp32 (c <= 8 real channels) -> NHWC bf16 with `pitch` channels, zero padded
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, int f16, int n, int c, int hw, __nv_bfloat16* __restrict__ out,
@@ -610,6 +733,18 @@ extern "C" int masic_softmax_channels(const float* in_nchw, int n, int c, int hw
   const long total = (long)n * hw;
   softmax_channels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       in_nchw, n, c, hw, out_nchw, out_nhwc);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int masic_mask2weights(const float* mask_nchw, int n, int h, int w, const float* w1, const float* b1,
+                                  const float* w2, const float* b2, const float* w3, const float* b3, const float* w4,
+                                  const float* b4, float* out_nchw, float* out_nhwc, void* stream) {
+  if (!mask_nchw || !w1 || !w2 || !w3 || !w4 || n <= 0 || h <= 0 || w <= 0 || (!out_nchw && !out_nhwc)) return MASIC_EINVAL;
+  int ho = h, wo = w;
+  for (int i = 0; i < 4; ++i) { ho = (ho + 1) / 2; wo = (wo + 1) / 2; }
+  dim3 grid((wo + MW_T - 1) / MW_T, (ho + MW_T - 1) / MW_T, n);
+  mask2weights_fused_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask_nchw, h, w, w1, b1, w2, b2, w3, b3,
+                                                                                 w4, b4, out_nchw, out_nhwc);
   return (int)cudaGetLastError();
 }
 

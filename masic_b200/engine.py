@@ -20,6 +20,7 @@ The engine is built for a fixed (batch, H, W); H and W must be multiples of 64
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -72,6 +73,9 @@ class HSICEngine:
         return self.sd[name].float().contiguous()
 
     def _add(self, name: str, fn: Callable[[], None]):
+        skip = os.environ.get("MASIC_ENGINE_SKIP")     # timing experiments only (results are wrong): drop matching steps
+        if skip and any(t and t in name for t in skip.split(",")):
+            fn = lambda: None
         self.steps.append((name, fn))
         self.sched.append(("run", len(self.steps) - 1, self._lane))
 
@@ -380,18 +384,25 @@ class HSICEngine:
         self._warp("mask_L=warp(mask_R,Hinv)", o["x1_mask_R"], Tinv, o["x1_mask_L"], channels=1)
         # mask2weights: 4x (conv3 s2 [+ReLU]) + softmax over 3 (MASIC.py:472-506)
         mk = "mask2weights_unit.maskconv"
-        k1 = self._buf(B, 3, H // 2, W // 2, dtype=f32)
-        k2 = self._buf(B, 6, H // 4, W // 4, dtype=f32)
-        k3 = self._buf(B, 6, H // 8, W // 8, dtype=f32)
-        k4 = self._buf(B, 3, h16, w16, dtype=f32)
-        self._conv_small("mask2weights.conv1", o["x1_mask_R"], None, f"{mk}.0", ksize=3, stride=2, act=ACT_RELU, out=k1)
-        self._conv_small("mask2weights.conv2", k1, None, f"{mk}.2", ksize=3, stride=2, act=ACT_RELU, out=k2)
-        self._conv_small("mask2weights.conv3", k2, None, f"{mk}.4", ksize=3, stride=2, act=ACT_RELU, out=k3)
-        self._conv_small("mask2weights.conv4", k3, None, f"{mk}.6", ksize=3, stride=2, out=k4)
         mw = self._buf(B, h16, w16, 3, dtype=f32)        # per-pixel fusion weights, NHWC
         self.mask_weights = mw
-        self._add("mask2weights.softmax", lambda: check(lib.masic_softmax_channels(
-            k4.data_ptr(), B, 3, h16 * w16, None, mw.data_ptr(), self._s()), "masic_softmax_channels"))
+        if os.environ.get("MASIC_MASK2W_FUSED", "1") != "0":
+            mp = [self._w(f"{mk}.{i}.{t}") for i in (0, 2, 4, 6) for t in ("weight", "bias")]
+            self._keep += mp
+            self._add("mask2weights(fused)", lambda: check(lib.masic_mask2weights(
+                o["x1_mask_R"].data_ptr(), B, H, W, *[t.data_ptr() for t in mp], None, mw.data_ptr(), self._s()),
+                "masic_mask2weights"))
+        else:
+            k1 = self._buf(B, 3, H // 2, W // 2, dtype=f32)
+            k2 = self._buf(B, 6, H // 4, W // 4, dtype=f32)
+            k3 = self._buf(B, 6, H // 8, W // 8, dtype=f32)
+            k4 = self._buf(B, 3, h16, w16, dtype=f32)
+            self._conv_small("mask2weights.conv1", o["x1_mask_R"], None, f"{mk}.0", ksize=3, stride=2, act=ACT_RELU, out=k1)
+            self._conv_small("mask2weights.conv2", k1, None, f"{mk}.2", ksize=3, stride=2, act=ACT_RELU, out=k2)
+            self._conv_small("mask2weights.conv3", k2, None, f"{mk}.4", ksize=3, stride=2, act=ACT_RELU, out=k3)
+            self._conv_small("mask2weights.conv4", k3, None, f"{mk}.6", ksize=3, stride=2, out=k4)
+            self._add("mask2weights.softmax", lambda: check(lib.masic_softmax_channels(
+                k4.data_ptr(), B, 3, h16 * w16, None, mw.data_ptr(), self._s()), "masic_softmax_channels"))
         self._record("mw")
         x1_warp = self._buf(B, 3, H, W, dtype=f32)
         self._warp("R.warp(x1)", self.x1, T, x1_warp)

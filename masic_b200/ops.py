@@ -215,6 +215,31 @@ def conv_small(in0: torch.Tensor, in1: Optional[torch.Tensor], weight: torch.Ten
     return out if out is not None else out_bf16
 
 
+def mask2weights(mask: torch.Tensor, weights, biases, nhwc_out: bool = False):
+    """mask2weights.forward (MASIC.py:472-506) in one launch.  weights / biases: the four conv3x3 stride-2 layers'
+    parameters (maskconv.0, .2, .4, .6).  Returns the (n,3,h/16,w/16) softmax weights (and the NHWC copy)."""
+    _need_cuda(mask, *weights)
+    mask = _f32c(mask)
+    n, c, h, w = mask.shape
+    if c != 1 or len(weights) != 4 or len(biases) != 4:
+        raise MasicError("mask2weights: mask must be (n,1,h,w) with four layers of parameters")
+    shapes = [(3, 1, 3, 3), (6, 3, 3, 3), (6, 6, 3, 3), (3, 6, 3, 3)]
+    ws = [_f32c(t.detach()) for t in weights]
+    for t, shp in zip(ws, shapes):
+        if tuple(t.shape) != shp:
+            raise MasicError(f"mask2weights: weight shape {tuple(t.shape)} != {shp}")
+    bs = [None if t is None else _f32c(t.detach()) for t in biases]
+    ho, wo = h, w
+    for _ in range(4):
+        ho, wo = (ho + 1) // 2, (wo + 1) // 2
+    out = torch.empty(n, 3, ho, wo, dtype=torch.float32, device=mask.device)
+    out_nhwc = torch.empty(n, ho, wo, 3, dtype=torch.float32, device=mask.device) if nhwc_out else None
+    check(_lib.load().masic_mask2weights(mask.data_ptr(), n, h, w, ws[0].data_ptr(), _p(bs[0]), ws[1].data_ptr(), _p(bs[1]),
+                                         ws[2].data_ptr(), _p(bs[2]), ws[3].data_ptr(), _p(bs[3]), out.data_ptr(),
+                                         _p(out_nhwc), _s()), "masic_mask2weights")
+    return (out, out_nhwc) if nhwc_out else out
+
+
 def softmax_channels(x: torch.Tensor, nhwc_out: bool = False):
     _need_cuda(x)
     x = _f32c(x)

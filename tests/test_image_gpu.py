@@ -119,6 +119,38 @@ def test_small_convs_against_torch(dev):
     assert torch.equal(sm_nhwc.permute(0, 3, 1, 2), sm)
 
 
+@pytest.mark.parametrize("h,w", [(64, 96), (37, 51), (200, 333), (1216, 2176)])
+def test_mask2weights_fused_matches_the_layer_chain(dev, h, w):
+    """masic_mask2weights (one launch) against torch and, bit for bit, against the chain of four small-conv launches +
+    softmax it replaces (MASIC.py:472-506)."""
+    from masic_b200 import ops
+    from masic_b200.ops import ACT_RELU
+    torch.manual_seed(11)
+    n = 2 if h < 1000 else 1
+    m = (torch.rand(n, 1, h, w) > 0.3).float() * torch.rand(n, 1, h, w)
+    layers = [torch.nn.Conv2d(1, 3, 3, 2, 1), torch.nn.Conv2d(3, 6, 3, 2, 1), torch.nn.Conv2d(6, 6, 3, 2, 1),
+              torch.nn.Conv2d(6, 3, 3, 2, 1)]
+    with torch.no_grad():
+        for l in layers:
+            l.weight.mul_(3.0)
+        t = m
+        for i, l in enumerate(layers):
+            t = l(t)
+            if i < 3:
+                t = F.relu(t)
+        ref = torch.softmax(t, 1)
+    ws, bs = [l.weight.to(dev) for l in layers], [l.bias.to(dev) for l in layers]
+    got, got_nhwc = ops.mask2weights(m.to(dev), ws, bs, nhwc_out=True)
+    assert got.shape == ref.shape
+    assert (got.cpu() - ref).abs().max() <= 2e-6
+    assert torch.equal(got_nhwc.permute(0, 3, 1, 2), got)
+    t = m.to(dev)
+    for i in range(4):
+        t = ops.conv_small(t, None, ws[i], bs[i], ksize=3, stride=2, act=ACT_RELU if i < 3 else 0)
+    chain = ops.softmax_channels(t)
+    assert torch.equal(chain, got)
+
+
 def test_standalone_gdn_matches_reference_fixture(dev, golden_dir):
     from masic_b200.layers import GDN
     fx = np.load(golden_dir / "gdn.npz")

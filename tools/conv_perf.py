@@ -51,6 +51,14 @@ MICRO = {
     "mb_gl0_n128": dict(k=1, h=H // 16, w=W // 16, c_in=768, c_out=3456, n_tile=128, act=ACT_RELU),
     "mb_gl0_n256": dict(k=1, h=H // 16, w=W // 16, c_in=768, c_out=3456, n_tile=256, act=ACT_RELU),
     "mb_gl0_n192": dict(k=1, h=H // 16, w=W // 16, c_in=768, c_out=3456, n_tile=192, act=ACT_RELU),
+    "mb_gl0_n128_cg2": dict(k=1, h=H // 16, w=W // 16, c_in=768, c_out=3456, n_tile=128, act=ACT_RELU, cta_pairs=True),
+    "mb_gl0_n192_cg2": dict(k=1, h=H // 16, w=W // 16, c_in=768, c_out=3456, n_tile=192, act=ACT_RELU, cta_pairs=True),
+    "mb_gl0_n256_cg2": dict(k=1, h=H // 16, w=W // 16, c_in=768, c_out=3456, n_tile=256, act=ACT_RELU, cta_pairs=True),
+    "mb_gl1_n192_cg2": dict(k=1, h=H // 16, w=W // 16, c_in=1152, c_out=768, n_tile=192, act=ACT_RELU, cta_pairs=True),
+    "mb_gl1_n256_cg2": dict(k=1, h=H // 16, w=W // 16, c_in=1152, c_out=768, n_tile=256, act=ACT_RELU, cta_pairs=True),
+    "mb_gl2_n192_cg2": dict(k=1, h=H // 16, w=W // 16, c_in=768, c_out=1920, n_tile=192, out_fp32=True, cta_pairs=True),
+    "mb_gl2_n192": dict(k=1, h=H // 16, w=W // 16, c_in=768, c_out=1920, n_tile=192, out_fp32=True),
+    "mb_gl2_n128": dict(k=1, h=H // 16, w=W // 16, c_in=768, c_out=1920, n_tile=128, out_fp32=True),
     "mb_ctx_n128": dict(k=5, stride=1, tap_mask=MASK_A_5x5, h=H // 16, w=W // 16, c_in=192, c_out=384, n_tile=128),
     "mb_hs3_n128": dict(k=3, stride=1, h=H // 16, w=W // 16, c_in=288, in_cp=384, c_out=384, n_tile=128),
     "mb_ha1_n64": dict(k=5, stride=1, h=H // 16, w=W // 16, c_in=192, c_out=128, n_tile=64, act=ACT_RELU),
@@ -60,7 +68,7 @@ MICRO = {
 
 
 def build(name, kind=CONV, k=1, stride=1, tap_mask=0, h=0, w=0, c_in=0, c_out=0, n_tile=128, gdn=GDN_NONE,
-          out_fp32=False, act=ACT_NONE, in_cp=None):
+          out_fp32=False, act=ACT_NONE, in_cp=None, cta_pairs=False):
     torch.manual_seed(0)
     in_cp = in_cp or c_in
     if kind in (3, 4):
@@ -82,7 +90,7 @@ def build(name, kind=CONV, k=1, stride=1, tap_mask=0, h=0, w=0, c_in=0, c_out=0,
         gg = torch.sqrt(0.1 * torch.eye(c_out, device=dev) + 1e-3)
     return ConvPlan(kind=kind, ksize=k, stride=stride, tap_mask=tap_mask, x=x, c_in=c_in, weight=wt,
                     transposed=transposed, bias=b, c_out=c_out, n_tile=n_tile, out=out, act=act, gdn=gdn,
-                    gdn_beta=gb, gdn_gamma=gg)
+                    gdn_beta=gb, gdn_gamma=gg, cta_pairs=cta_pairs)
 
 
 def main():
