@@ -120,6 +120,15 @@ typedef struct MasicConvDesc {
    * tensor-map prefetch) overlaps the tail of the previous kernel in the stream, and it lets the NEXT kernel's CTAs be
    * scheduled as soon as SMs free up.  Pays off on chains of tiny launches (the wavefront decoder's per-wave model). */
   int pdl;
+  /* MASIC_CONV, stride 1: the input buffer's rows hold in_row_pixels >= w_in pixels (0 = w_in); taps that reach past
+   * column w_in read the buffer's own columns instead of zero padding (used with folded-pixel views whose last
+   * window hangs over the image edge). */
+  int in_row_pixels;
+  /* 1: PLANAR output.  The n-tile's 16-channel (fp32) / 32- or 64-channel (16-bit) staging blocks are written to
+   * separate output images: block j of image n goes to image n * nblk + j at channel out_coff, i.e. `out` is
+   * [n * nblk][H][W][out_cpitch] and channels beyond out_cpitch are clipped.  With out_cpitch = 8 and a pixel-folded
+   * input this writes an NCHW fp32 tensor directly (after_conv, MASIC.py:600,616).  Single n-tile plans only. */
+  int out_blk_images;
 } MasicConvDesc;
 
 typedef struct MasicConvPlan MasicConvPlan;   /* opaque: tensor maps + tile program */
@@ -309,6 +318,11 @@ int masic_deconv_img_pack_weights(const float* weight_128x3x5x5, void* dst_16, i
 int masic_deconv_img_plan_create(const void* in_nhwc16, int n, int h_in, int w_in, int c_pitch, const void* w_packed,
                                  const float* bias3, int gdn, const float* beta3_host, const float* gamma9_host,
                                  float* out_nchw, int f16, MasicDeconvImgPlan** plan_out);
+/* Optional second destination of the plan (out_nchw of masic_deconv_img_plan_create may then be NULL): the 3 output
+ * channels as 16-bit NHWC at channel coff (even) of pixel slot (y * row_pixels + x + xoff) * c_pitch.  When coff and
+ * c_pitch are multiples of 4 the pixel is ONE 8-byte store [c0 c1 c2 0] (channel coff + 3 is zeroed). */
+int masic_deconv_img_plan_set_out16(MasicDeconvImgPlan* plan, void* out_nhwc16, int c_pitch, int row_pixels, int xoff,
+                                    int coff, int f16);
 int masic_deconv_img_plan_launch(const MasicDeconvImgPlan* plan, void* stream);
 void masic_deconv_img_plan_destroy(MasicDeconvImgPlan* plan);
 
@@ -341,6 +355,15 @@ int masic_warp_prepare(const float* m_3x3, int batch, int h, int w, int h_out, i
 int masic_warp_perspective_fwd(const float* src, int n, int c, int h, int w, int h_out, int w_out,
                                const double* t_prepared, float* dst_nchw, void* dst_nhwc_bf16,
                                int bf_pitch, int bf_row_pixels, int bf_xoff, int f16, void* stream);
+
+/* Same, with a second 16-bit NHWC destination (plain MASIC_FMT_BF16 / MASIC_FMT_F16): the c warped channels are written at
+ * channel d2_coff of pixel slot (y * d2_row_pixels + x + d2_xoff) * d2_pitch, leaving the slot's other channels
+ * untouched — several producers fill one channels-last image (the input of the tensor-core after_conv).  With c = 3
+ * and d2_coff, d2_pitch multiples of 4 the pixel is ONE 8-byte store [c0 c1 c2 0] (channel d2_coff + 3 is zeroed). */
+int masic_warp_perspective_fwd2(const float* src, int n, int c, int h, int w, int h_out, int w_out,
+                                const double* t_prepared, float* dst_nchw, void* dst_nhwc_bf16, int bf_pitch,
+                                int bf_row_pixels, int bf_xoff, int f16, void* dst2_nhwc16, int d2_pitch,
+                                int d2_row_pixels, int d2_xoff, int d2_coff, int d2_f16, void* stream);
 
 /* Direct conv for the tiny-channel layers (c_in <= 8, c_out <= 8) on NCHW fp32:
  *   Encoder2.pre_conv+pre_gdn (MASIC.py:573-574): in0=x1_warp, in1=x2, k=5, s=1, gdn=FWD

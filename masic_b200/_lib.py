@@ -50,6 +50,7 @@ class ConvDesc(C.Structure):
         ("residual1", C.c_void_p), ("res1_cpitch", C.c_int), ("res1_coff", C.c_int),
         ("nt_in_coff", C.POINTER(C.c_int)), ("nt_out_coff", C.POINTER(C.c_int)), ("nt_out_img", C.POINTER(C.c_int)),
         ("out_images", C.c_int), ("cta_pairs", C.c_int), ("f16", C.c_int), ("pdl", C.c_int),
+        ("in_row_pixels", C.c_int), ("out_blk_images", C.c_int),
     ]
 
 
@@ -148,6 +149,7 @@ def _declare(lib: C.CDLL) -> None:
         "masic_deconv_img_pack_weights": (i, [vp, vp, i, vp]),
         "masic_deconv_img_plan_create": (i, [vp, i, i, i, i, vp, vp, i, vp, vp, vp, i, C.POINTER(vp)]),
         "masic_deconv_img_plan_launch": (i, [vp, vp]),
+        "masic_deconv_img_plan_set_out16": (i, [vp, vp, i, i, i, i, i]),
         "masic_deconv_img_plan_destroy": (None, [vp]),
         "masic_maxpool2_nhwc_bf16": (i, [vp, i, i, i, i, vp, i, vp]),
         "masic_fc_pack_weights": (i, [vp, i, i, i, vp, i, vp]),
@@ -155,6 +157,7 @@ def _declare(lib: C.CDLL) -> None:
         "masic_homography_from_delta": (i, [vp, vp, i, i, i, i, i, i, vp, vp]),
         "masic_warp_prepare": (i, [vp, i, i, i, i, i, i, vp, vp]),
         "masic_warp_perspective_fwd": (i, [vp, i, i, i, i, i, i, vp, vp, vp, i, i, i, i, vp]),
+        "masic_warp_perspective_fwd2": (i, [vp, i, i, i, i, i, i, vp, vp, vp, i, i, i, i, vp, i, i, i, i, i, vp]),
         "masic_conv_small_nchw": (i, [vp, i, vp, i, i, i, i, vp, i, vp, i, i, i, i, i, vp, vp, f, vp, vp, i, i, i, i, vp]),
         "masic_mask2weights": (i, [vp, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "masic_subpix_to_nchw": (i, [vp, i, i, i, i, i, vp, vp, f, vp, vp, i, i, vp]),

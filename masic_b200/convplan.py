@@ -155,7 +155,8 @@ class ConvPlan:
                  residual0: Optional[torch.Tensor] = None, res0_coff: int = 0,
                  residual1: Optional[torch.Tensor] = None, res1_coff: int = 0,
                  nt_in_coff: Optional[Sequence[int]] = None, nt_out_coff: Optional[Sequence[int]] = None,
-                 nt_out_img: Optional[Sequence[int]] = None, cta_pairs: bool = False, pdl: bool = False):
+                 nt_out_img: Optional[Sequence[int]] = None, cta_pairs: bool = False, pdl: bool = False,
+                 w_in: Optional[int] = None, out_blk_images: bool = False):
         lib = _lib.load()
         assert x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and x.dim() == 4 and x.is_contiguous()
         assert out.is_cuda and out.dim() == 4 and out.is_contiguous()
@@ -168,9 +169,15 @@ class ConvPlan:
         fmt = act_dtype(packed.f16)
         assert x.dtype == fmt, f"input buffer is {x.dtype}, the packed weights are {fmt}"
         assert out.dtype in (fmt, torch.float32), f"output buffer is {out.dtype}, expected {fmt} or float32"
+        w_logical = w_in
         n, h_in, w_in, in_cp = x.shape
         if packed.kind in (CONV_XFOLD4, CONV_XFOLD8):          # padded image rows: [N][H][W + IMG_XPAD][16 or 8]
             w_in -= _lib.IMG_XPAD
+        if w_logical is not None:                              # rows wider than the logical image (MasicConvDesc.in_row_pixels)
+            assert w_logical <= w_in
+            row_pixels, w_in = w_in, w_logical
+        else:
+            row_pixels = 0
         self.rowscale = rowscale
         self.x, self.out = x, out       # keep the bound buffers alive
 
@@ -213,11 +220,13 @@ class ConvPlan:
                 setattr(d, name, C.cast(arr, C.POINTER(C.c_int)))
             self._tabs = tabs
             d.out_images = out.shape[0]
-        else:
+        elif not out_blk_images:
             assert out.shape[0] == n, (out.shape, n)
         d.cta_pairs = int(cta_pairs)
         d.f16 = packed.f16
         d.pdl = int(pdl)
+        d.in_row_pixels = int(row_pixels)
+        d.out_blk_images = int(out_blk_images)
         self._desc = d
         handle = C.c_void_p()
         check(lib.masic_conv_plan_create(C.byref(d), C.byref(handle)), "masic_conv_plan_create")
@@ -242,19 +251,61 @@ class ConvPlan:
             self._h = None
 
 
+def fold8_weights_5x5_s1(weight: torch.Tensor, bias: Optional[torch.Tensor], transposed: bool,
+                         slots: Optional[Sequence[int]] = None):
+    """A 5x5 stride-1 pad-2 layer with <= 8 input and 3 output channels (after_conv, MASIC.py:600,616) as a conv over
+    PIXEL-FOLDED data: the NHWC pitch-8 image [H][W + IMG_XPAD][8] (pixel x at column x + IMG_XOFF = 2) is read as
+    [H][(W + 8) / 8][64] — one "pixel" = 8 image pixels x 8 channels — and output block xb (image pixels 8 xb .. 8 xb + 7)
+    needs blocks xb and xb + 1 only, i.e. taps kx' = 2, 3 of a 5-wide kernel.  Returns the (48, 64, 5, 5) weight
+    (row co * 16 + j = output channel co of pixel j, j < 8; column p * 8 + c = channel c of the block's pixel p), the
+    48-entry bias and the tap mask (10 live taps).  With MasicConvDesc.out_blk_images the three 16-column blocks land in
+    the three planes of an NCHW tensor.  slots[ci] = position of input channel ci inside the 8-channel pixel
+    (default 0, 1, 2, ...)."""
+    w = weight.detach().float()
+    wc = w.flip(2, 3).permute(1, 0, 2, 3) if transposed else w           # correlation kernel (c_out, c_in, 5, 5)
+    c_out, c_in = wc.shape[0], wc.shape[1]
+    assert c_out == 3 and c_in <= 8 and tuple(wc.shape[2:]) == (5, 5)
+    big = torch.zeros(48, 64, 5, 5, dtype=torch.float32, device=w.device)
+    slots = list(range(c_in)) if slots is None else list(slots)
+    assert len(slots) == c_in and len(set(slots)) == c_in and all(0 <= t < 8 for t in slots)
+    for kxp, base in ((2, 0), (3, 8)):
+        for pq in range(8):
+            q = base + pq                       # column offset inside the 16-pixel window: image pixel 8 xb - 2 + q
+            for j in range(8):
+                kx = q - j                      # output pixel 8 xb + j reads image pixel 8 xb + j + kx - 2
+                if 0 <= kx < 5:
+                    for co in range(3):
+                        for ci, sl in enumerate(slots):
+                            big[co * 16 + j, pq * 8 + sl, :, kxp] = wc[co, ci, :, kx]
+    b48 = torch.zeros(48, dtype=torch.float32, device=w.device)
+    if bias is not None:
+        for co in range(3):
+            b48[co * 16:co * 16 + 8] = bias.detach().float()[co]
+    mask = 0
+    for ky in range(5):
+        mask |= (1 << (ky * 5 + 2)) | (1 << (ky * 5 + 3))
+    return big, b48, mask
+
+
 class DeconvImgPlan:
     """g_s_conv4 — ConvTranspose2d(128, 3, k=5, s=2, p=2, op=1) at image resolution (MasicDeconvImgPlan of the C ABI,
     csrc/deconv_img.cu): NHWC 16-bit (n, h, w, 128) in, NCHW fp32 (n, 3, 2h, 2w) out, optional after_gdn (IGDN over the
     three channels) fused.  `weight` is the module's (128, 3, 5, 5) tensor."""
 
-    def __init__(self, *, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor,
-                 igdn_beta: Optional[torch.Tensor] = None, igdn_gamma: Optional[torch.Tensor] = None):
+    def __init__(self, *, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
+                 out: Optional[torch.Tensor], igdn_beta: Optional[torch.Tensor] = None,
+                 igdn_gamma: Optional[torch.Tensor] = None, out16: Optional[torch.Tensor] = None, out16_coff: int = 0,
+                 out16_xoff: int = 0):
+        """out16: optional (n, 2h, row_pixels, pitch) 16-bit NHWC image that receives the 3 channels at channel
+        out16_coff of column x + out16_xoff (`out` may then be None)."""
         import numpy as np
         lib = _lib.load()
         assert x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and x.dim() == 4 and x.is_contiguous()
         n, h, w, cp = x.shape
         assert cp == 128 and tuple(weight.shape) == (128, 3, 5, 5), (x.shape, weight.shape)
-        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (n, 3, 2 * h, 2 * w)
+        assert out is not None or out16 is not None
+        if out is not None:
+            assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (n, 3, 2 * h, 2 * w)
         f16 = int(x.dtype == torch.float16)
         self.w_packed = torch.empty(lib.masic_deconv_img_weight_bytes() // 2, dtype=x.dtype, device=x.device)
         wt = weight.detach().float().contiguous()
@@ -270,12 +321,19 @@ class DeconvImgPlan:
         self.x, self.out = x, out
         hdl = C.c_void_p()
         check(lib.masic_deconv_img_plan_create(x.data_ptr(), n, h, w, cp, self.w_packed.data_ptr(), _ptr(self.bias), gdn,
-                                               pb, pg, out.data_ptr(), f16, C.byref(hdl)), "masic_deconv_img_plan_create")
+                                               pb, pg, _ptr(out), f16, C.byref(hdl)), "masic_deconv_img_plan_create")
         self._h, self._lib = hdl, lib
+        self.out16 = out16
+        if out16 is not None:
+            assert out16.is_cuda and out16.dtype in (torch.bfloat16, torch.float16) and out16.is_contiguous()
+            assert out16.dim() == 4 and out16.shape[0] == n and out16.shape[1] == 2 * h
+            check(lib.masic_deconv_img_plan_set_out16(hdl, out16.data_ptr(), out16.shape[3], out16.shape[2], out16_xoff,
+                                                      out16_coff, int(out16.dtype == torch.float16)),
+                  "masic_deconv_img_plan_set_out16")
         self.flops = 2.0 * n * h * w * 128 * 75
         self.work_items = n * (-(-w // 14)) * (h // 8)
         self.smem_bytes = 0
-        self.hbm_bytes = n * h * w * (256.0 + 48.0)
+        self.hbm_bytes = n * h * w * (256.0 + (48.0 if out is not None else 0.0) + (24.0 if out16 is not None else 0.0))
 
     def launch(self, stream: Optional[int] = None) -> None:
         check(self._lib.masic_deconv_img_plan_launch(self._h, _stream() if stream is None else stream),

@@ -104,6 +104,7 @@ struct KParams {
   int nt_in_coff[32];              // grouped launches: per n-tile input-channel offset,
   int nt_out_c[32];                // output channel position (default nt * n_tile)
   int nt_out_img[32];              // and output image offset
+  int blk_img;                     // 1: staging block j of a tile goes to output image tn * nblk + j (planar / NCHW output)
   uint32_t idesc;
   uint32_t idesc_norm;   // the GDN norm MMA always runs on bf16 operands (x^2 rounded on the ALU pipe, gamma' bf16)
   int f16;         // 16-bit operand / activation format: 0 = bf16, 1 = fp16 (cvt16.cuh)
@@ -1061,8 +1062,11 @@ conv_tc_kernel(const __grid_constant__ KParams p) {
           fence_proxy_async_smem();
           named_bar_sync(pbar, 256);
           if (leader && !nostore && valid) {
-            tma_store_5d(&p.tmO, sb2, p.out_coff + v.out_c0 + p.nt_out_c[it.nt] + c, tx0, v.out_p2, ty0,
-                         tn + p.nt_out_img[it.nt]);
+            if (p.blk_img)
+              tma_store_5d(&p.tmO, sb2, p.out_coff + v.out_c0 + p.nt_out_c[it.nt], tx0, v.out_p2, ty0, tn * nblk + j);
+            else
+              tma_store_5d(&p.tmO, sb2, p.out_coff + v.out_c0 + p.nt_out_c[it.nt] + c, tx0, v.out_p2, ty0,
+                           tn + p.nt_out_img[it.nt]);
             tma_store_commit();
           }
           j += 2;                                      // next unit of this pair: (tt, j) advances by two blocks
@@ -1394,6 +1398,7 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   if (d.n_tile % full_blk_ch == 0) { kp.blk_ch = full_blk_ch; kp.blk_pitch = 128; }
   else if (d.n_tile * esz < 128) { kp.blk_ch = d.n_tile; kp.blk_pitch = d.n_tile * esz; }
   else if (!d.out_fp32 && d.n_tile % 32 == 0) { kp.blk_ch = 32; kp.blk_pitch = 64; }    // e.g. 96 channels: 3 narrow blocks
+  else if (d.out_fp32 && d.n_tile % 16 == 0) { kp.blk_ch = 16; kp.blk_pitch = 64; }     // e.g. 48 fp32 channels: 3 narrow blocks
   else { delete pl; return MASIC_EINVAL; }
 
   // work items: pairs of tiles sharing every weight k-block when two accumulators fit 256 TMEM columns
@@ -1453,11 +1458,17 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   const int split_in = ((d.kind == MASIC_CONV || xfold) && d.stride == 2) ? 1 : 0;
   if (d.kind == MASIC_CONV_XFOLD4) rc = encode_xfold4_view(&kp.tmA, d.in, d.n, d.h_in, d.w_in, rows);
   else if (d.kind == MASIC_CONV_XFOLD8) rc = encode_xfold8_view(&kp.tmA, d.in, d.n, d.h_in, d.w_in, rows);
-  else rc = encode_nhwc_view(&kp.tmA, d.in, 2, d.n, d.h_in, d.w_in, d.in_cpitch, split_in, KBLK, rows, true);
+  else rc = encode_nhwc_view(&kp.tmA, d.in, 2, d.n, d.h_in, d.in_row_pixels ? d.in_row_pixels : d.w_in, d.in_cpitch,
+                             split_in, KBLK, rows, true);
   const int ktaps = (d.kind == MASIC_DECONV_S2_SUBPIX) ? 9 : (d.kind == MASIC_CONV_XFOLD4 ? 10 : (d.kind == MASIC_CONV_XFOLD8 ? 5 : d.ksize * d.ksize));
   const int ncb = xfold ? 1 : (d.c_in + KBLK - 1) / KBLK;
   if (!rc) rc = encode_rows64(&kp.tmB, d.w_packed, (long)ktaps * ncb * d.c_out_pad, kp.cg2 ? d.n_tile / 2 : d.n_tile);
   const bool grouped = d.nt_in_coff || d.nt_out_coff || d.nt_out_img;
+  // planar output: the n-tile's staging blocks are separate output images (channel planes of an NCHW tensor seen as
+  // [n * nblk][H][W][out_cpitch]); wider rows than w_in on the input side only make sense for stride-1 convolutions
+  kp.blk_img = d.out_blk_images != 0;
+  if (kp.blk_img && (grouped || d.gdn || d.residual0 || kp.n_ntiles != 1 || d.kind != MASIC_CONV)) { delete pl; return MASIC_EINVAL; }
+  if (d.in_row_pixels && (d.in_row_pixels < d.w_in || d.kind != MASIC_CONV || d.stride != 1)) { delete pl; return MASIC_EINVAL; }
   if (grouped && (!d.nt_in_coff || !d.nt_out_coff || !d.nt_out_img || d.out_images < d.n || d.gdn || d.residual0 ||
                   d.rowscale || xfold)) { delete pl; return MASIC_EINVAL; }
   for (int i = 0; i < kp.n_ntiles; ++i) {
@@ -1467,7 +1478,8 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
     if (kp.nt_in_coff[i] % 8 || kp.nt_out_c[i] % (d.out_fp32 ? 4 : 8) || kp.nt_out_img[i] < 0 ||
         (grouped && kp.nt_out_img[i] + d.n > d.out_images)) { delete pl; return MASIC_EINVAL; }
   }
-  if (!rc) rc = encode_nhwc_view(&kp.tmO, d.out, esz, grouped ? d.out_images : d.n, out_h, out_w, d.out_cpitch, out_split,
+  if (!rc) rc = encode_nhwc_view(&kp.tmO, d.out, esz, grouped ? d.out_images : (kp.blk_img ? d.n * (d.n_tile / kp.blk_ch) : d.n),
+                                 out_h, out_w, d.out_cpitch, out_split,
                                  kp.blk_ch, TILE_H, kp.blk_pitch == 128);
   if (!rc && d.gdn) rc = encode_gamma(&kp.tmG, d.gamma_packed, kp.cg2 ? 64 : 128);
   if (rc) { delete pl; return rc; }

@@ -46,7 +46,9 @@ struct DIParams {
   const float* bias;            // [3] or null
   int gdn;                      // 0 or MASIC_GDN_INV (after_gdn)
   float beta[3], gamma[9];      // effective (re-parametrised) values
-  float* out;                   // (n, 3, 2 h2, 2 w2) fp32
+  float* out;                   // (n, 3, 2 h2, 2 w2) fp32, or null
+  uint16_t* out16;              // optional NHWC 16-bit copy: pixel (y, x) at out16[((img*HO + y)*o16_row + x + o16_xoff)*o16_pitch + o16_coff + c]
+  int o16_pitch, o16_row, o16_xoff, o16_coff, o16_f16;
   uint32_t idesc;
 };
 
@@ -213,10 +215,21 @@ deconv_img_kernel(const __grid_constant__ DIParams p) {
             const float n2 = fmaf(p.gamma[8], s2, fmaf(p.gamma[7], s1, fmaf(p.gamma[6], s0, p.beta[2])));
             v0 *= sqrtf(n0); v1 *= sqrtf(n1); v2 *= sqrtf(n2);
           }
-          float* o = p.out + (static_cast<size_t>(img) * 3 * HO + oy) * WO + ox;
-          o[0] = v0;
-          o[static_cast<size_t>(HO) * WO] = v1;
-          o[2 * static_cast<size_t>(HO) * WO] = v2;
+          if (p.out) {
+            float* o = p.out + (static_cast<size_t>(img) * 3 * HO + oy) * WO + ox;
+            o[0] = v0;
+            o[static_cast<size_t>(HO) * WO] = v1;
+            o[2 * static_cast<size_t>(HO) * WO] = v2;
+          }
+          if (p.out16) {
+            uint16_t* o = p.out16 + ((static_cast<size_t>(img) * HO + oy) * p.o16_row + ox + p.o16_xoff) * p.o16_pitch + p.o16_coff;
+            if (((p.o16_coff | p.o16_pitch) & 3) == 0) {                         // one aligned 8-byte store: [v0 v1 v2 0]
+              *reinterpret_cast<uint2*>(o) = make_uint2(pack16x2(v0, v1, p.o16_f16), pack16x2(v2, 0.0f, p.o16_f16));
+            } else {
+              *reinterpret_cast<uint32_t*>(o) = pack16x2(v0, v1, p.o16_f16);    // o16_coff is even: 4-byte aligned
+              o[2] = pack16(v2, p.o16_f16);
+            }
+          }
         }
       }
       named_bar_sync(1, DI_EPI);                    // the next step's Z rows overwrite ring rows this step still read
@@ -273,7 +286,7 @@ extern "C" int masic_deconv_img_plan_create(const void* in_nhwc16, int n, int h_
                                             const void* w_packed, const float* bias3, int gdn, const float* beta3_host,
                                             const float* gamma9_host, float* out_nchw, int f16,
                                             MasicDeconvImgPlan** plan_out) {
-  if (!in_nhwc16 || !w_packed || !out_nchw || !plan_out || n <= 0 || h_in <= 0 || w_in <= 0 || (h_in % DI_ROWS) ||
+  if (!in_nhwc16 || !w_packed || !plan_out || n <= 0 || h_in <= 0 || w_in <= 0 || (h_in % DI_ROWS) ||
       c_pitch != 128 || (gdn && (!beta3_host || !gamma9_host)) || (gdn && gdn != MASIC_GDN_INV))
     return MASIC_EINVAL;
   EncodeTiledFn enc = encode_fn();
@@ -329,8 +342,19 @@ extern "C" int masic_deconv_img_plan_create(const void* in_nhwc16, int n, int h_
   return MASIC_OK;
 }
 
+extern "C" int masic_deconv_img_plan_set_out16(MasicDeconvImgPlan* pl, void* out_nhwc16, int c_pitch, int row_pixels,
+                                               int xoff, int coff, int f16) {
+  if (!pl || (out_nhwc16 && (c_pitch < coff + 3 || (c_pitch % 2) || (coff % 2) || coff < 0 || xoff < 0 ||
+                             row_pixels < 2 * pl->kp.w2 + xoff || (reinterpret_cast<uintptr_t>(out_nhwc16) & 7))))
+    return MASIC_EINVAL;
+  pl->kp.out16 = static_cast<uint16_t*>(out_nhwc16);
+  pl->kp.o16_pitch = c_pitch; pl->kp.o16_row = row_pixels; pl->kp.o16_xoff = xoff; pl->kp.o16_coff = coff;
+  pl->kp.o16_f16 = f16 & 1;
+  return MASIC_OK;
+}
+
 extern "C" int masic_deconv_img_plan_launch(const MasicDeconvImgPlan* pl, void* stream) {
-  if (!pl) return MASIC_EINVAL;
+  if (!pl || (!pl->kp.out && !pl->kp.out16)) return MASIC_EINVAL;
   deconv_img_kernel<<<pl->grid, DI_THREADS, DI_SMEM, static_cast<cudaStream_t>(stream)>>>(pl->kp);
   return (int)cudaGetLastError();
 }

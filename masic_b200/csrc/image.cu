@@ -108,7 +108,8 @@ __device__ __forceinline__ double fast_rcp(double d) {
 __global__ void __launch_bounds__(256)
 warp_kernel(const float* __restrict__ src, int n, int c, int h, int w, int ho, int wo,
             const double* __restrict__ T, double inv_wo1, double inv_ho1, float* __restrict__ dst,
-            __nv_bfloat16* __restrict__ dst_bf, int bf_pitch, int bf_row, int bf_xoff, int f16) {
+            __nv_bfloat16* __restrict__ dst_bf, int bf_pitch, int bf_row, int bf_xoff, int f16,
+            uint16_t* __restrict__ dst2, int d2_pitch, int d2_row, int d2_xoff, int d2_coff, int d2_f16) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int b = blockIdx.z;
@@ -170,6 +171,14 @@ warp_kernel(const float* __restrict__ src, int n, int c, int h, int w, int ho, i
   if (dst_bf) {
     for (int ch = c; ch < 8; ++ch) vals[ch] = 0.0f;
     store_pixel_bf16(dst_bf + ((long)(b * ho + y) * bf_row + x + bf_xoff) * bf_pitch, vals, c, bf_pitch, f16);
+  }
+  if (dst2) {        // second 16-bit NHWC copy: the c values at channel d2_coff of a shared pixel slot (plain format)
+    uint16_t* o = dst2 + ((long)(b * ho + y) * d2_row + x + d2_xoff) * d2_pitch + d2_coff;
+    if (c == 3 && (d2_coff & 3) == 0 && (d2_pitch & 3) == 0) {     // one aligned 8-byte store: [v0 v1 v2 0]
+      *reinterpret_cast<uint2*>(o) = make_uint2(pack16x2(vals[0], vals[1], d2_f16), pack16x2(vals[2], 0.0f, d2_f16));
+    } else {
+      for (int ch = 0; ch < c && ch < 8; ++ch) o[ch] = pack16(vals[ch], d2_f16);
+    }
   }
 }
 
@@ -672,14 +681,26 @@ extern "C" int masic_warp_perspective_fwd(const float* src, int n, int c, int h,
                                           int w_out, const double* t_prepared, float* dst_nchw,
                                           void* dst_nhwc_bf16, int bf_pitch, int bf_row_pixels, int bf_xoff,
                                           int f16, void* stream) {
-  if (!t_prepared || n <= 0 || c <= 0 || c > 8 || (!dst_nchw && !dst_nhwc_bf16)) return MASIC_EINVAL;
+  return masic_warp_perspective_fwd2(src, n, c, h, w, h_out, w_out, t_prepared, dst_nchw, dst_nhwc_bf16, bf_pitch,
+                                     bf_row_pixels, bf_xoff, f16, nullptr, 0, 0, 0, 0, 0, stream);
+}
+
+extern "C" int masic_warp_perspective_fwd2(const float* src, int n, int c, int h, int w, int h_out, int w_out,
+                                           const double* t_prepared, float* dst_nchw, void* dst_nhwc_bf16,
+                                           int bf_pitch, int bf_row_pixels, int bf_xoff, int f16, void* dst2_nhwc16,
+                                           int d2_pitch, int d2_row_pixels, int d2_xoff, int d2_coff, int d2_f16,
+                                           void* stream) {
+  if (!t_prepared || n <= 0 || c <= 0 || c > 8 || (!dst_nchw && !dst_nhwc_bf16 && !dst2_nhwc16)) return MASIC_EINVAL;
   if (bf_row_pixels == 0) { bf_row_pixels = w_out; bf_xoff = 0; }
   if (bf_row_pixels < w_out + bf_xoff || bf_xoff < 0) return MASIC_EINVAL;
+  if (dst2_nhwc16 && (d2_pitch < d2_coff + c || d2_coff < 0 || d2_xoff < 0 || d2_row_pixels < w_out + d2_xoff))
+    return MASIC_EINVAL;
   if (h_out < 2 || w_out < 2) return MASIC_ENOSUP;
   dim3 grid((w_out + 255) / 256, h_out, n);
   warp_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, n, c, h, w, h_out, w_out, t_prepared, 1.0 / (double)(w_out - 1), 1.0 / (double)(h_out - 1), dst_nchw,
-      static_cast<__nv_bfloat16*>(dst_nhwc_bf16), bf_pitch, bf_row_pixels, bf_xoff, f16);
+      static_cast<__nv_bfloat16*>(dst_nhwc_bf16), bf_pitch, bf_row_pixels, bf_xoff, f16,
+      static_cast<uint16_t*>(dst2_nhwc16), d2_pitch, d2_row_pixels, d2_xoff, d2_coff, d2_f16 & 1);
   return (int)cudaGetLastError();
 }
 

@@ -28,7 +28,7 @@ import torch
 from . import _lib
 from ._lib import MasicError, check
 from .convplan import (ACT_LEAKY, ACT_NONE, ACT_RELU, CONV, CONV_XFOLD8, DECONV_S2, DECONV_S2_SUBPIX, GDN_FWD, GDN_INV,
-                       GDN_NONE, MASK_A_5x5, ConvPlan, DeconvImgPlan, PackedConv)
+                       GDN_NONE, MASK_A_5x5, ConvPlan, DeconvImgPlan, PackedConv, fold8_weights_5x5_s1)
 
 F16 = _lib.FMT_F16              # the inference engines run on fp16 operands / activations (csrc/cvt16.cuh)
 ACT = _lib.act_dtype(F16)
@@ -140,7 +140,7 @@ class HSICEngine:
         self._conv(f"{tag}.conv4", packs[3], e3, y, stride=2)
         return y
 
-    def _decoder(self, tag: str, dec: str, yq_bf16, out_img, igdn_prefix=None):
+    def _decoder(self, tag: str, dec: str, yq_bf16, out_img, igdn_prefix=None, out16=None):
         """g_s: 3x (deconv5 s2 + IGDN) + deconv5 s2 -> 3 — MASIC.py:544-554.  The last layer runs in col2im form
         (csrc/deconv_img.cu) and writes the NCHW fp32 image `out_img`, with after_gdn fused for the right view."""
         import os
@@ -161,10 +161,11 @@ class HSICEngine:
         ig = self._w(igdn_prefix + ".gamma") if igdn_prefix else None
         if os.environ.get("MASIC_DECONV_IMG", "1") != "0":
             plan = DeconvImgPlan(x=g3, weight=self._w(f"{dec}.g_s_conv4.weight"), bias=self._w(f"{dec}.g_s_conv4.bias"),
-                                 out=out_img, igdn_beta=ib, igdn_gamma=ig)
+                                 out=out_img, igdn_beta=ib, igdn_gamma=ig, out16=out16, out16_coff=0, out16_xoff=XOFF)
             self.plans[f"{tag}.deconv4(col2im)"] = plan
             self._add(f"{tag}.deconv4(col2im)", plan.launch)
             return
+        assert out16 is None, "the 16-bit NHWC copy of the decoder output needs the col2im deconv (MASIC_DECONV_IMG=1)"
         # the earlier form (MASIC_DECONV_IMG=0): sub-pixel conv_tc plan (N = 4 phases x 3 -> 16) + pixel interleave
         sp = self._buf(B, H // 2, W // 2, 16, dtype=torch.float32)
         p4 = self._pack(f"{dec}.g_s_conv4", kind=DECONV_S2_SUBPIX, c_in=N, c_out=3, n_tile=16, transposed=True)
@@ -304,17 +305,23 @@ class HSICEngine:
                   "masic_latent_prep")
         self._add(f"{tag}.latent_prep", step)
 
-    def _warp(self, tag, src, T, dst, dst_bf=None, channels=3):
+    def _warp(self, tag, src, T, dst, dst_bf=None, channels=3, dst2=None, dst2_coff=0):
+        """dst: NCHW fp32; dst_bf: hi|lo image for g_a_conv1; dst2: plain 16-bit copy at channel dst2_coff of a shared
+        channels-last image (the tensor-core after_conv's input).  Any of them may be None."""
         B, H, W = self.B, self.H, self.W
 
         def step():
-            check(self.lib.masic_warp_perspective_fwd(None if src is None else src.data_ptr(), B, channels, H, W, H, W,
-                                                      T.data_ptr(), None if dst is None else dst.data_ptr(),
-                                                      None if dst_bf is None else dst_bf.data_ptr(),
-                                                      0 if dst_bf is None else dst_bf.shape[3],
-                                                      0 if dst_bf is None else dst_bf.shape[2],
-                                                      0 if dst_bf is None else XOFF, F16_IMG, self._s()),
-                  "masic_warp_perspective_fwd")
+            check(self.lib.masic_warp_perspective_fwd2(None if src is None else src.data_ptr(), B, channels, H, W, H, W,
+                                                       T.data_ptr(), None if dst is None else dst.data_ptr(),
+                                                       None if dst_bf is None else dst_bf.data_ptr(),
+                                                       0 if dst_bf is None else dst_bf.shape[3],
+                                                       0 if dst_bf is None else dst_bf.shape[2],
+                                                       0 if dst_bf is None else XOFF, F16_IMG,
+                                                       None if dst2 is None else dst2.data_ptr(),
+                                                       0 if dst2 is None else dst2.shape[3],
+                                                       0 if dst2 is None else dst2.shape[2],
+                                                       0 if dst2 is None else XOFF, dst2_coff, F16, self._s()),
+                  "masic_warp_perspective_fwd2")
         self._add(tag, step)
 
     def _conv_small(self, tag, in0, in1, wname, *, ksize, stride, transposed_s1=False, act=ACT_NONE, gdn=GDN_NONE,
@@ -441,20 +448,39 @@ class HSICEngine:
         self._on(0)
         self._decoder("L.g_s", "decoder1", y1_rnd, o["x1_hat"])                                    # :777
         # x1_hat warped once (the reference computes it twice, :821 and :833)
-        x1hw = self._buf(B, 3, H, W, dtype=f32)
         x1hw_bf = self._buf(B, H, W + XPAD, IMG_CP)
+        # after_conv on the tensor cores (MASIC_AFTER_CONV_TC=0: the CUDA-core kernel on fp32 planes): its two inputs
+        # are written straight into ONE channels-last 16-bit image [after_gdn(g_s(y2_hat)) (3) 0 | x1_hat_warp (3) 0],
+        # each producer with one aligned 8-byte store per pixel
+        ac_tc = (os.environ.get("MASIC_AFTER_CONV_TC", "1") != "0" and os.environ.get("MASIC_DECONV_IMG", "1") != "0"
+                 and W % 8 == 0)
+        ac_in = self._buf(B, H, W + XPAD, IMG_CP) if ac_tc else None
+        x1hw = None if ac_tc else self._buf(B, 3, H, W, dtype=f32)
         self._wait("T")
-        self._warp("R.warp(x1_hat)", o["x1_hat"], T, x1hw, x1hw_bf)
+        self._warp("R.warp(x1_hat)", o["x1_hat"], T, x1hw, x1hw_bf, dst2=ac_in, dst2_coff=4)
         y1w = self._encoder("R.g_a(enc1 on warped x1_hat)", enc1, x1hw_bf)                         # :822
         self._wait("mw")
         self._wait("right")
         self._latent_prep("R.y1warp", y1w, None, gmm2_in, rnd_coff=4 * M, rowscale=mw, rs_off=2)   # round(.) * w2
         s2, m2, w2 = self._gmm_net("R", "_h_s2_same_resolution", 5 * M, False, gmm2_in)            # :827
         self._gmm_likelihood("R", y2, s2, m2, w2, o["y2_hat"], o["lik_y2"])                        # :829
-        after1 = self._buf(B, 3, H, W, dtype=f32)
-        self._decoder("R.g_s", "decoder2", y2_rnd, after1, igdn_prefix="decoder2.after_gdn")        # :834, :615
-        self._conv_small("R.after_conv", after1, x1hw, "decoder2.after_conv", ksize=5, stride=1, transposed_s1=True,
-                         out=o["x2_hat"])
+        if ac_tc:
+            self._decoder("R.g_s", "decoder2", y2_rnd, None, igdn_prefix="decoder2.after_gdn", out16=ac_in)   # :834, :615
+            wf, bf_, tmask = fold8_weights_5x5_s1(self._w("decoder2.after_conv.weight"), self._w("decoder2.after_conv.bias"),
+                                                  transposed=True, slots=(0, 1, 2, 4, 5, 6))
+            pk = PackedConv(ksize=5, c_in=64, c_out=48, n_tile=48, weight=wf, bias=bf_, f16=F16)
+            self.packs["R.after_conv"] = pk
+            plan = ConvPlan(packed=pk, x=ac_in.view(B, H, (W + XPAD) // 8, 64), stride=1, tap_mask=tmask, w_in=W // 8,
+                            out=o["x2_hat"].view(B * 3, H, W // 8, 8), out_blk_images=True)
+            plan.flops = 2.0 * B * H * W * 6 * 3 * 25         # useful work (the folded GEMM multiplies mostly zeros)
+            plan.hbm_bytes = B * H * W * (16.0 + 12.0)
+            self.plans["R.after_conv"] = plan
+            self._add("R.after_conv", plan.launch)
+        else:
+            after1 = self._buf(B, 3, H, W, dtype=f32)
+            self._decoder("R.g_s", "decoder2", y2_rnd, after1, igdn_prefix="decoder2.after_gdn")        # :834, :615
+            self._conv_small("R.after_conv", after1, x1hw, "decoder2.after_conv", ksize=5, stride=1, transposed_s1=True,
+                             out=o["x2_hat"])
         self._wait("left_entropy")
         self.flops = sum(p.flops for p in self.plans.values())
 
