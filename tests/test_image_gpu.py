@@ -171,5 +171,17 @@ def test_layout_packs_round_trip(dev):
     p = ops.nchw_to_nhwc_bf16(x, 16)
     assert p.dtype == ops.ACT16 and torch.equal(p[..., :3].permute(0, 3, 1, 2).float(), x.to(ops.ACT16).float())
     assert float(p[..., 3:].abs().max()) == 0
+    # width % 4 == 0, three channels: the four-pixels-per-thread variant, plain and hi|lo (MASIC_FMT_SPLIT) formats
+    from masic_b200 import _lib
+    x4 = torch.rand(2, 3, 18, 24, device=dev)
+    p4 = ops.nchw_to_nhwc_bf16(x4, 8)
+    assert torch.equal(p4[..., :3].permute(0, 3, 1, 2).float(), x4.to(ops.ACT16).float()) and float(p4[..., 3:].abs().max()) == 0
+    sp = torch.full((2, 18, 24 + _lib.IMG_XPAD, 8), 7.0, dtype=ops.ACT16, device=dev)
+    _lib.check(_lib.load().masic_nchw_to_nhwc_bf16(x4.data_ptr(), 2, 3, 18, 24, sp.data_ptr(), 8, 24 + _lib.IMG_XPAD, _lib.IMG_XOFF,
+                                                   _lib.FMT_F16 | _lib.FMT_SPLIT, torch.cuda.current_stream().cuda_stream), "pack")
+    body = sp[:, :, _lib.IMG_XOFF:_lib.IMG_XOFF + 24]
+    hi, lo = body[..., :3].permute(0, 3, 1, 2).float(), body[..., 3:6].permute(0, 3, 1, 2).float()
+    assert torch.equal(hi, x4.half().float()) and float((hi + lo - x4).abs().max()) <= 2e-7
+    assert float(body[..., 6:].abs().max()) == 0 and float((sp[:, :, :_lib.IMG_XOFF] - 7).abs().max()) == 0
     y = torch.rand(2, 9, 11, 200, device=dev)
     assert torch.equal(ops.nhwc_to_nchw_f32(y, 192), y[..., :192].permute(0, 3, 1, 2))
