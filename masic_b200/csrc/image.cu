@@ -105,11 +105,16 @@ __device__ __forceinline__ double fast_rcp(double d) {
 // One thread per destination pixel, all channels.  src == nullptr: source is all ones
 // (mask(), MASIC.py:636-638) so the kernel is write-only.
 // Outputs (either may be null): NCHW fp32, and NHWC bf16 with `bf_pitch` channels (zero padded).
+// CT > 0: channel count known at compile time (the hot calls warp 3-channel images and the 1-channel mask): the
+// per-channel values stay in registers and the guards of the generic CT = 0 form (local-memory arrays, ~300
+// instructions per pixel, issue-bound) disappear.
+template <int CT>
 __global__ void __launch_bounds__(256)
-warp_kernel(const float* __restrict__ src, int n, int c, int h, int w, int ho, int wo,
+warp_kernel(const float* __restrict__ src, int n, int c_rt, int h, int w, int ho, int wo,
             const double* __restrict__ T, double inv_wo1, double inv_ho1, float* __restrict__ dst,
             __nv_bfloat16* __restrict__ dst_bf, int bf_pitch, int bf_row, int bf_xoff, int f16,
             uint16_t* __restrict__ dst2, int d2_pitch, int d2_row, int d2_xoff, int d2_coff, int d2_f16) {
+  const int c = CT ? CT : c_rt;
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int b = blockIdx.z;
@@ -150,9 +155,12 @@ warp_kernel(const float* __restrict__ src, int n, int c, int h, int w, int ho, i
   const float k_sw = (in_y1 && in_x0) ? w_sw : 0.0f, k_se = (in_y1 && in_x1) ? w_se : 0.0f;
   const int xc0 = min(max(x0, 0), w - 1), xc1 = min(max(x0 + 1, 0), w - 1);
   const int yc0 = min(max(y0, 0), h - 1), yc1 = min(max(y0 + 1, 0), h - 1);
-  const long o_nw = (long)yc0 * w + xc0, o_ne = (long)yc0 * w + xc1, o_sw = (long)yc1 * w + xc0, o_se = (long)yc1 * w + xc1;
+  const int o_nw = yc0 * w + xc0, o_ne = yc0 * w + xc1, o_sw = yc1 * w + xc0, o_se = yc1 * w + xc1;   // one plane < 2^31 elements
+  constexpr int NV = CT ? CT : 8;
   float vals[8];
-  for (int ch = 0; ch < c && ch < 8; ++ch) {
+#pragma unroll
+  for (int ch = 0; ch < NV; ++ch) {
+    if (!CT && ch >= c) break;
     float v = 0.0f;
     if (src) {
       const float* s = src + ((long)(b * c + ch) * h) * w;
@@ -169,7 +177,8 @@ warp_kernel(const float* __restrict__ src, int n, int c, int h, int w, int ho, i
     if (dst) dst[((long)(b * c + ch) * ho + y) * wo + x] = v;
   }
   if (dst_bf) {
-    for (int ch = c; ch < 8; ++ch) vals[ch] = 0.0f;
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) if (ch >= c) vals[ch] = 0.0f;
     store_pixel_bf16(dst_bf + ((long)(b * ho + y) * bf_row + x + bf_xoff) * bf_pitch, vals, c, bf_pitch, f16);
   }
   if (dst2) {        // second 16-bit NHWC copy: the c values at channel d2_coff of a shared pixel slot (plain format)
@@ -177,7 +186,8 @@ warp_kernel(const float* __restrict__ src, int n, int c, int h, int w, int ho, i
     if (c == 3 && (d2_coff & 3) == 0 && (d2_pitch & 3) == 0) {     // one aligned 8-byte store: [v0 v1 v2 0]
       *reinterpret_cast<uint2*>(o) = make_uint2(pack16x2(vals[0], vals[1], d2_f16), pack16x2(vals[2], 0.0f, d2_f16));
     } else {
-      for (int ch = 0; ch < c && ch < 8; ++ch) o[ch] = pack16(vals[ch], d2_f16);
+#pragma unroll
+      for (int ch = 0; ch < NV; ++ch) if (ch < c) o[ch] = pack16(vals[ch], d2_f16);
     }
   }
 }
@@ -716,7 +726,9 @@ extern "C" int masic_warp_perspective_fwd2(const float* src, int n, int c, int h
     return MASIC_EINVAL;
   if (h_out < 2 || w_out < 2) return MASIC_ENOSUP;
   dim3 grid((w_out + 255) / 256, h_out, n);
-  warp_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  if ((long)h * w >= (1L << 31)) return MASIC_ENOSUP;
+  auto kern = c == 3 ? warp_kernel<3> : (c == 1 ? warp_kernel<1> : warp_kernel<0>);
+  kern<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, n, c, h, w, h_out, w_out, t_prepared, 1.0 / (double)(w_out - 1), 1.0 / (double)(h_out - 1), dst_nchw,
       static_cast<__nv_bfloat16*>(dst_nhwc_bf16), bf_pitch, bf_row_pixels, bf_xoff, f16,
       static_cast<uint16_t*>(dst2_nhwc16), d2_pitch, d2_row_pixels, d2_xoff, d2_coff, d2_f16 & 1);
