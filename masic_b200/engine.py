@@ -186,9 +186,11 @@ class HSICEngine:
         z = self._buf(B, h16 // 4, w16 // 4, N, dtype=torch.float32)
         self._conv(f"{tag}.h_a.conv1", self._pack(f"{ha}.0", c_in=M, c_out=N, n_tile=128), y_abs_bf16, c1,
                    stride=1, act=ACT_RELU)
-        self._conv(f"{tag}.h_a.conv2", self._pack(f"{ha}.2", c_in=N, c_out=N, n_tile=128), c1, c2, stride=2,
+        # 27 and 10 spatial tiles only: narrow n-tiles spread them over 108 / 40 CTAs (a lone CTA streaming 50 k-blocks is
+        # bound by one SM's L2 bandwidth; tools/conv_perf.py mb_ha2 / mb_ha3: 0.026 -> 0.022, 0.025 -> 0.021 ms)
+        self._conv(f"{tag}.h_a.conv2", self._pack(f"{ha}.2", c_in=N, c_out=N, n_tile=32), c1, c2, stride=2,
                    act=ACT_RELU)
-        self._conv(f"{tag}.h_a.conv3", self._pack(f"{ha}.4", c_in=N, c_out=N, n_tile=128), c2, z, stride=2)
+        self._conv(f"{tag}.h_a.conv3", self._pack(f"{ha}.4", c_in=N, c_out=N, n_tile=32), c2, z, stride=2)
         # EntropyBottleneck (entropy_models.py:384-411)
         eb = f"entropy_bottleneck{idx}."
         mats = [self._w(f"{eb}_matrices.{i}") for i in range(5)]

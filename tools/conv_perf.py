@@ -59,6 +59,33 @@ MICRO = {
     "mb_gl2_n192_cg2": dict(k=1, h=H // 16, w=W // 16, c_in=768, c_out=1920, n_tile=192, out_fp32=True, cta_pairs=True),
     "mb_gl2_n192": dict(k=1, h=H // 16, w=W // 16, c_in=768, c_out=1920, n_tile=192, out_fp32=True),
     "mb_gl2_n128": dict(k=1, h=H // 16, w=W // 16, c_in=768, c_out=1920, n_tile=128, out_fp32=True),
+    "mb_ctx_n192": dict(k=5, stride=1, tap_mask=MASK_A_5x5, h=H // 16, w=W // 16, c_in=192, c_out=384, n_tile=192),
+    "mb_ctx_n192_cg2": dict(k=5, stride=1, tap_mask=MASK_A_5x5, h=H // 16, w=W // 16, c_in=192, c_out=384, n_tile=192, cta_pairs=True),
+    "mb_ctx_n128_cg2": dict(k=5, stride=1, tap_mask=MASK_A_5x5, h=H // 16, w=W // 16, c_in=192, c_out=384, n_tile=128, cta_pairs=True),
+    "mb_ctx_n64": dict(k=5, stride=1, tap_mask=MASK_A_5x5, h=H // 16, w=W // 16, c_in=192, c_out=384, n_tile=64),
+    "mb_ctx_n96": dict(k=5, stride=1, tap_mask=MASK_A_5x5, h=H // 16, w=W // 16, c_in=192, c_out=384, n_tile=96),
+    "mb_hs3_n192": dict(k=3, stride=1, h=H // 16, w=W // 16, c_in=288, in_cp=384, c_out=384, n_tile=192),
+    "mb_hs3_n192_cg2": dict(k=3, stride=1, h=H // 16, w=W // 16, c_in=288, in_cp=384, c_out=384, n_tile=192, cta_pairs=True),
+    "mb_hs3_n128_cg2": dict(k=3, stride=1, h=H // 16, w=W // 16, c_in=288, in_cp=384, c_out=384, n_tile=128, cta_pairs=True),
+    "mb_hs3_n64": dict(k=3, stride=1, h=H // 16, w=W // 16, c_in=288, in_cp=384, c_out=384, n_tile=64),
+    "mb_hs3_n96": dict(k=3, stride=1, h=H // 16, w=W // 16, c_in=288, in_cp=384, c_out=384, n_tile=96),
+    "mb_ga4_n192": dict(k=5, stride=2, h=H // 8, w=W // 8, c_in=128, c_out=192, n_tile=192, out_fp32=True),
+    "mb_ga4_n192_cg2": dict(k=5, stride=2, h=H // 8, w=W // 8, c_in=128, c_out=192, n_tile=192, out_fp32=True, cta_pairs=True),
+    "mb_ga4_n48": dict(k=5, stride=2, h=H // 8, w=W // 8, c_in=128, c_out=192, n_tile=48, out_fp32=True),
+    "mb_ga4_n32": dict(k=5, stride=2, h=H // 8, w=W // 8, c_in=128, c_out=192, n_tile=32, out_fp32=True),
+    "mb_ha1_n128": dict(k=5, stride=1, h=H // 16, w=W // 16, c_in=192, c_out=128, n_tile=128, act=ACT_RELU),
+    "mb_ha1_n32": dict(k=5, stride=1, h=H // 16, w=W // 16, c_in=192, c_out=128, n_tile=32, act=ACT_RELU),
+    "mb_ha2_n128": dict(k=5, stride=2, h=H // 16, w=W // 16, c_in=128, c_out=128, n_tile=128, act=ACT_RELU),
+    "mb_ha2_n32": dict(k=5, stride=2, h=H // 16, w=W // 16, c_in=128, c_out=128, n_tile=32, act=ACT_RELU),
+    "mb_ha2_n16": dict(k=5, stride=2, h=H // 16, w=W // 16, c_in=128, c_out=128, n_tile=16, act=ACT_RELU),
+    "mb_ha3_n128": dict(k=5, stride=2, h=H // 32, w=W // 32, c_in=128, c_out=128, n_tile=128, out_fp32=True),
+    "mb_ha3_n16": dict(k=5, stride=2, h=H // 32, w=W // 32, c_in=128, c_out=128, n_tile=16, out_fp32=True),
+    "mb_ha3_n32": dict(k=5, stride=2, h=H // 32, w=W // 32, c_in=128, c_out=128, n_tile=32, out_fp32=True),
+    "mb_hs1_n128": dict(kind=DECONV_S2, k=5, h=H // 64, w=W // 64, c_in=128, c_out=128, n_tile=128, act=ACT_LEAKY),
+    "mb_hs1_n32": dict(kind=DECONV_S2, k=5, h=H // 64, w=W // 64, c_in=128, c_out=128, n_tile=32, act=ACT_LEAKY),
+    "mb_hs2_n192": dict(kind=DECONV_S2, k=5, h=H // 32, w=W // 32, c_in=128, c_out=192, n_tile=192, act=ACT_LEAKY),
+    "mb_hs2_n96": dict(kind=DECONV_S2, k=5, h=H // 32, w=W // 32, c_in=128, c_out=192, n_tile=96, act=ACT_LEAKY),
+    "mb_hs2_n64": dict(kind=DECONV_S2, k=5, h=H // 32, w=W // 32, c_in=128, c_out=192, n_tile=64, act=ACT_LEAKY),
     "mb_ctx_n128": dict(k=5, stride=1, tap_mask=MASK_A_5x5, h=H // 16, w=W // 16, c_in=192, c_out=384, n_tile=128),
     "mb_hs3_n128": dict(k=3, stride=1, h=H // 16, w=W // 16, c_in=288, in_cp=384, c_out=384, n_tile=128),
     "mb_ha1_n64": dict(k=5, stride=1, h=H // 16, w=W // 16, c_in=192, c_out=128, n_tile=64, act=ACT_RELU),
