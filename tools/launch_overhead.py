@@ -40,3 +40,12 @@ for name, p in (("1 tile K=64 N=16", plan(16, 8, 64, 16, 16)), ("148 tiles K=64 
     b = timeit(lambda: (p.launch(), small.add_(1.0)))
     c = timeit(lambda: small.add_(1.0))
     print(f"{name:40s} back-to-back {a:7.2f} us/launch; alternating with a small kernel {b:7.2f} us/pair (small alone {c:.2f} us)")
+
+# the latency-bound small layers of the step, warm and back to back inside one graph (tools/conv_perf.py shapes)
+import importlib.util
+spec = importlib.util.spec_from_file_location("conv_perf", str(Path(__file__).resolve().parent / "conv_perf.py"))
+cp = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(cp)
+for name in ("mb_ha2_n32", "mb_ha3_n32", "mb_ga4_n192", "mb_ha1_n128", "mb_hs2_n192", "mb_hs1_n128"):
+    p = cp.build(name, **cp.MICRO[name])
+    print(f"{name:40s} back-to-back {timeit(p.launch):7.2f} us/launch  work={p.work_items}")
