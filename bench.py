@@ -283,6 +283,11 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.finish() if sampler else None
     value = world * args.steps / (ms_total / 1e3)
 
+    # ---- per-kernel attribution with CUDA events (eager replay of the same step on the launching stream), taken right
+    # after the headline region: each launch is timed alone and compared with the BURST peak, so it must not inherit
+    # the clocks / temperature of the multi-second blocks further down
+    prof = eng.profile_steps(iters=max(3, min(args.steps, 5)))
+
     # ---- end to end through the public API with host buffers (`e2e`): HSIC.pair_stream() — every step copies
     # its own pair (2 x 31.7 MB + the homography) from pinned host memory and reads its criterion back to
     # the host; the copy of pair i+1 overlaps the kernels of pairs i and i-1 (three slots = three engines).
@@ -334,11 +339,6 @@ def run_ours(args, rank, world, local_rank):
                                  "d2h_bytes_per_step": d2h + x1_h[0:1].numel() * 4 * 2,
                                  "result": "criterion + x1_hat + x2_hat (float32) into pinned host memory every step",
                                  "uint8_inputs": {"value": r8_value, "ms_per_step": r8_ms / args.steps}}
-
-    # ---- per-kernel attribution with CUDA events (eager replay of the same step, same stream); taken BEFORE the
-    # sustained block: each launch is timed alone and compared with the BURST peak, so it must not inherit the power-capped
-    # clocks of a multi-second run
-    prof = eng.profile_steps(iters=max(3, min(args.steps, 5)))
 
     # ---- sustained: >= 3 s of continuous device-resident replay, clocks sampled (the headline region lasts tens of ms)
     sustained = None

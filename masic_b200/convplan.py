@@ -261,11 +261,12 @@ def fold8_weights_5x5_s1(weight: torch.Tensor, bias: Optional[torch.Tensor], tra
     48-entry bias and the tap mask (10 live taps).  With MasicConvDesc.out_blk_images the three 16-column blocks land in
     the three planes of an NCHW tensor.  slots[ci] = position of input channel ci inside the 8-channel pixel
     (default 0, 1, 2, ...)."""
-    w = weight.detach().float()
+    dev = weight.device
+    w = weight.detach().float().cpu()                                     # ~1000 tiny slice copies: on the host
     wc = w.flip(2, 3).permute(1, 0, 2, 3) if transposed else w           # correlation kernel (c_out, c_in, 5, 5)
     c_out, c_in = wc.shape[0], wc.shape[1]
     assert c_out == 3 and c_in <= 8 and tuple(wc.shape[2:]) == (5, 5)
-    big = torch.zeros(48, 64, 5, 5, dtype=torch.float32, device=w.device)
+    big = torch.zeros(48, 64, 5, 5, dtype=torch.float32)
     slots = list(range(c_in)) if slots is None else list(slots)
     assert len(slots) == c_in and len(set(slots)) == c_in and all(0 <= t < 8 for t in slots)
     for kxp, base in ((2, 0), (3, 8)):
@@ -277,14 +278,15 @@ def fold8_weights_5x5_s1(weight: torch.Tensor, bias: Optional[torch.Tensor], tra
                     for co in range(3):
                         for ci, sl in enumerate(slots):
                             big[co * 16 + j, pq * 8 + sl, :, kxp] = wc[co, ci, :, kx]
-    b48 = torch.zeros(48, dtype=torch.float32, device=w.device)
+    b48 = torch.zeros(48, dtype=torch.float32)
     if bias is not None:
+        bh = bias.detach().float().cpu()
         for co in range(3):
-            b48[co * 16:co * 16 + 8] = bias.detach().float()[co]
+            b48[co * 16:co * 16 + 8] = bh[co]
     mask = 0
     for ky in range(5):
         mask |= (1 << (ky * 5 + 2)) | (1 << (ky * 5 + 3))
-    return big, b48, mask
+    return big.to(dev), b48.to(dev), mask
 
 
 class DeconvImgPlan:

@@ -553,13 +553,17 @@ class HSICEngine:
         return done
 
     def profile_steps(self, iters: int = 3) -> List[Tuple[str, float]]:
-        """Eager run with a CUDA-event pair around every step; median ms per step."""
+        """Eager run with a CUDA-event pair around every step; median ms per step.  Every iteration starts with a ~3 ms
+        device-side sleep so that the host has enqueued all launches and events before the first kernel runs: the
+        events then time the kernels back to back, not the host's launch rate (a step of 10-30 us is shorter than
+        one Python launch)."""
         with torch.cuda.device(self.dev):
             self._launch_all(concurrent=False)
             torch.cuda.synchronize()
             acc = [[] for _ in self.steps]
             for _ in range(iters):
                 evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(self.steps) + 1)]
+                torch.cuda._sleep(6_000_000)
                 evs[0].record()
                 for i, (_, fn) in enumerate(self.steps):
                     fn()

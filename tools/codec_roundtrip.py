@@ -28,14 +28,18 @@ Hm = torch.tensor([[[1.0, 0.01, 20.0], [0.0, 1.0, 3.0], [1e-6, 0.0, 1.0]]], devi
 with torch.no_grad(), tempfile.TemporaryDirectory() as tmp:
     fwd = net(x1, x2, Hm)
     for order in orders:
-        for rep in range(2):                         # second repetition: plans and buffers exist
-            t0 = time.time()
+        best_c = best_d = 1e9
+        for rep in range(4):                         # first repetition builds plans and buffers; host-side coding times
+            t0 = time.time()                         # jitter with the box (threads, tmpfs): best of the last three
             enc = net.compress(x1, x2, Hm, "p", tmp, y_order=order)
             torch.cuda.synchronize()
             t1 = time.time()
             dec = net.decompress(x1, x2, Hm, "p", tmp, device=dev)
             torch.cuda.synchronize()
             t2 = time.time()
+            if rep:
+                best_c, best_d = min(best_c, t1 - t0), min(best_d, t2 - t1)
+        t0, t1, t2 = 0.0, best_c, best_c + best_d
         ok = all(torch.equal(dec[k], fwd[k]) for k in ("y1_hat", "x1_hat", "x2_hat")) and torch.equal(dec["y2_hat"], enc["y2_hat"])
         print(f"{order:9s} {H}x{W}: compress {1e3 * (t1 - t0):8.1f} ms (y coding {1e3 * enc['enctime']:.1f}), "
               f"decompress {1e3 * (t2 - t1):8.1f} ms (y decoding {1e3 * dec['dectime']:.1f}); {enc['n_symbols']} symbols, "
