@@ -206,6 +206,86 @@ small_conv_dgrad_kernel(const SCArgs a, float* __restrict__ din0, float* __restr
   }
 }
 
+// Data gradient of the two 6 <-> 3 channel 5x5 stride-1 layers (pre_conv, after_conv) as a shared-memory tiled
+// correlation of the 3-channel output gradient with K[ci][co][ky][kx] (a conv: W[co][ci] flipped; the transposed layer:
+// W[ci][co] as stored): the tiling of conv5x5_6to3_kernel (image.cu) with the channel roles swapped.  A block of 16 x 8
+// threads produces 128 x 8 pixels x 6 channels from a (128+4) x (8+4) x 3 patch; a thread owns 2 x 4 pixels x 6 channels.
+constexpr int DG_TW = 128, DG_TH = 8, DG_PW = DG_TW + 8, DG_PH = DG_TH + 4;
+__global__ void __launch_bounds__(128)
+conv5x5_3to6_dgrad_kernel(const float* __restrict__ g, int h, int w, const float* __restrict__ wt, int transposed,
+                          int c0, float* __restrict__ din0, float* __restrict__ din1) {
+  __shared__ __align__(16) float s_g[3][DG_PH][DG_PW];
+  __shared__ __align__(16) float s_w[3 * 5 * 32];       // [co][ky][kx * 6 + ci], 30 used of 32
+  const int tid = threadIdx.y * 16 + threadIdx.x;
+  for (int i = tid; i < 3 * 5 * 32; i += 128) {
+    const int j = i & 31, ky = (i >> 5) % 5, co = i / 160;
+    float v = 0.0f;
+    if (j < 30) {
+      const int kx = j / 6, ci = j % 6;
+      v = transposed ? wt[((ci * 3 + co) * 5 + ky) * 5 + kx] : wt[((co * 6 + ci) * 5 + (4 - ky)) * 5 + (4 - kx)];
+    }
+    s_w[i] = v;
+  }
+  const int b = blockIdx.z, y0 = blockIdx.y * DG_TH, x0 = blockIdx.x * DG_TW;
+  for (int i = tid; i < 3 * DG_PH * DG_PW; i += 128) {
+    const int c = i % DG_PW, py = (i / DG_PW) % DG_PH, co = i / (DG_PW * DG_PH);
+    const int gy = y0 + py - 2, gx = x0 + c - 2;
+    float v = 0.0f;
+    if (gy >= 0 && gy < h && gx >= 0 && gx < w) v = __ldg(g + ((long)(b * 3 + co) * h + gy) * w + gx);
+    s_g[co][py][c] = v;
+  }
+  __syncthreads();
+  float acc[2][4][6];
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int ci = 0; ci < 6; ++ci) acc[q][p][ci] = 0.0f;
+  const int lx = threadIdx.x * 4, ly = threadIdx.y;
+#pragma unroll 1
+  for (int co = 0; co < 3; ++co) {
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) {
+      const float4* wq = reinterpret_cast<const float4*>(&s_w[(co * 5 + ky) * 32]);
+      float ww[32];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float4 t = wq[i]; ww[4 * i] = t.x; ww[4 * i + 1] = t.y; ww[4 * i + 2] = t.z; ww[4 * i + 3] = t.w; }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&s_g[co][ly + ky][lx + 64 * q]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&s_g[co][ly + ky][lx + 64 * q + 4]);
+        const float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int kx = 0; kx < 5; ++kx)
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float x = v[p + kx];
+#pragma unroll
+            for (int ci = 0; ci < 6; ++ci) acc[q][p][ci] = fmaf(x, ww[kx * 6 + ci], acc[q][p][ci]);
+          }
+      }
+    }
+  }
+  const int oy = y0 + ly;
+  if (oy >= h) return;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int ox = x0 + lx + 64 * q;
+#pragma unroll
+    for (int ci = 0; ci < 6; ++ci) {
+      float* dst = ci < c0 ? (din0 ? din0 + ((long)(b * c0 + ci) * h + oy) * w : nullptr)
+                           : (din1 ? din1 + ((long)(b * (6 - c0) + ci - c0) * h + oy) * w : nullptr);
+      if (!dst) continue;
+      if (ox + 3 < w && (w & 3) == 0) {
+        *reinterpret_cast<float4*>(dst + ox) = make_float4(acc[q][0][ci], acc[q][1][ci], acc[q][2][ci], acc[q][3][ci]);
+      } else {
+        for (int p = 0; p < 4; ++p) if (ox + p < w) dst[ox + p] = acc[q][p][ci];
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- GDN over <= 8 channels, backward (NCHW fp32)
 // dx written; dbeta' [c] and dgamma' [c][c] accumulated (atomics) — chain to the stored parameters with masic_reparam_bwd
 __global__ void __launch_bounds__(256)
@@ -405,8 +485,13 @@ extern "C" int masic_conv_small_bwd(const float* in0, int c0, const float* in1, 
     small_conv_wgrad_kernel<<<blocks, 256, smem, S(stream)>>>(a, dweight_zeroed, dbias_zeroed);
   }
   if (din0 || din1) {
-    dim3 grid((w + 127) / 128, h, n);
-    small_conv_dgrad_kernel<<<grid, 128, 0, S(stream)>>>(a, din0, din1);
+    if (ksize == 5 && stride == 1 && c0 + c1 == 6 && c_out == 3 && !act_out) {
+      dim3 grid((w + DG_TW - 1) / DG_TW, (h + DG_TH - 1) / DG_TH, n), block(16, 8);
+      conv5x5_3to6_dgrad_kernel<<<grid, block, 0, S(stream)>>>(g_out, h, w, weight, transposed_s1, c0, din0, din1);
+    } else {
+      dim3 grid((w + 127) / 128, h, n);
+      small_conv_dgrad_kernel<<<grid, 128, 0, S(stream)>>>(a, din0, din1);
+    }
   }
   return (int)cudaGetLastError();
 }
