@@ -22,16 +22,21 @@ def bf(t):
     return t.to(torch.bfloat16).float()
 
 
+def hf(t):
+    return t.to(torch.float16).float()
+
+
 class Sim:
     """flags: w (weights bf16), a (layer inputs bf16), g (GDN x^2 and gamma' bf16), per-layer overrides in `exact`."""
 
-    def __init__(self, w=True, a=True, g=True, exact=()):
+    def __init__(self, w=True, a=True, g=True, exact=(), fmt=bf, g_x2=True, g_gamma=True, gamma_fmt=bf):
         self.w, self.a, self.g, self.exact = w, a, g, set(exact)
+        self.fmt, self.g_x2, self.g_gamma, self.gamma_fmt = fmt, g_x2, g_gamma, gamma_fmt
 
     def conv(self, name, mod, x, transposed):
         ex = name in self.exact
-        wt = mod.weight if (ex or not self.w) else bf(mod.weight)
-        xi = x if (ex or not self.a) else bf(x)
+        wt = mod.weight if (ex or not self.w) else self.fmt(mod.weight)
+        xi = x if (ex or not self.a) else self.fmt(x)
         if transposed:
             return F.conv_transpose2d(xi, wt, mod.bias, stride=mod.stride, padding=mod.padding, output_padding=mod.output_padding)
         return F.conv2d(xi, wt, mod.bias, stride=mod.stride, padding=mod.padding)
@@ -42,7 +47,10 @@ class Sim:
         g = OH.nonneg_forward(mod.gamma, 0.0).reshape(c, c, 1, 1)
         x2 = x ** 2
         if self.g and name not in self.exact:
-            x2, g = bf(x2), bf(g)
+            if self.g_x2:
+                x2 = bf(x2)
+            if self.g_gamma:
+                g = self.gamma_fmt(g)
         norm = F.conv2d(x2, g, b)
         return x * (torch.sqrt(norm) if mod.inverse else torch.rsqrt(norm))
 
@@ -86,6 +94,18 @@ def main():
         print(f"{name:58s} rms(x_hat dev) {rms:.3e}  dPSNR {10 * math.log10(mse0 / mse):+.5f} dB  flips {flips:.5f}  "
               f"rms(y dev) {float(((y - y0) ** 2).mean().sqrt()):.3e}")
 
+    print("---- the inference engine of round 2: fp16 weights / activations, bf16 x^2 and gamma' in the fused GDN")
+    report("fp16 w, a + bf16 gdn operands", Sim(fmt=hf))
+    report("  ... decoder only (exact symbols fed)", Sim(fmt=hf), same_symbols=True)
+    report("fp16 w, a, exact gdn", Sim(fmt=hf, g=False))
+    report("  ... decoder only", Sim(fmt=hf, g=False), same_symbols=True)
+    report("only gdn operands bf16 (x^2 and gamma')", Sim(w=False, a=False), same_symbols=True)
+    report("only gamma' bf16", Sim(w=False, a=False, g_x2=False), same_symbols=True)
+    report("only x^2 bf16", Sim(w=False, a=False, g_gamma=False), same_symbols=True)
+    report("only gamma' fp16", Sim(w=False, a=False, g_x2=False, gamma_fmt=hf), same_symbols=True)
+    report("fp16 w, a + bf16 x^2 + fp16 gamma'", Sim(fmt=hf, gamma_fmt=hf))
+    report("  ... decoder only", Sim(fmt=hf, gamma_fmt=hf), same_symbols=True)
+    print("---- round 1 numerics (everything bf16)")
     report("engine numerics (w, a, gdn in bf16)", Sim())
     report("  ... decoder only (exact symbols fed)", Sim(), same_symbols=True)
     report("weights bf16 only", Sim(a=False, g=False))
