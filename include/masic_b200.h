@@ -516,6 +516,14 @@ int masic_gdn_bwd_b(void* u_bf16, const void* x_bf16, const float* v, int64_t n_
 /* NonNegativeParametrizer backward with LowerBound's rule (parametrizers.py:61-64, bound_ops.py:40-42). */
 int masic_reparam_bwd(const float* dprime, const float* stored, int n, float minimum, int accumulate,
                       float* dstored, void* stream);
+/* All reparam backwards of a training step as ONE launch (15 GDN layers x {beta, gamma}): HOST arrays of n_jobs device
+ * pointers / sizes / minima / accumulate flags (NULL = 0), copied at creation. */
+typedef struct MasicReparamBatch MasicReparamBatch;
+int masic_reparam_batch_create(const float* const* dprime, const float* const* stored, float* const* dstored,
+                               const int* numel, const float* minimum, const int* accumulate, int n_jobs,
+                               MasicReparamBatch** out);
+int masic_reparam_batch_launch(const MasicReparamBatch* batch, void* stream);
+void masic_reparam_batch_destroy(MasicReparamBatch* batch);
 int masic_latent_prep_train(const float* y_nhwc, const float* noise_nhwc, int64_t n_pixels, int c,
                             void* y_abs_bf16, int abs_pitch, void* y_noisy_bf16, int noisy_pitch, void* stream);
 /* dy = dy_lik + d_dec + d_ctx + sign(y) * d_abs (NULL sources are skipped) -> bf16 */

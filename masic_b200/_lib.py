@@ -182,6 +182,9 @@ def _declare(lib: C.CDLL) -> None:
         "masic_gdn_bwd_a": (i, [vp, vp, vp, i, vp, i64, i, vp, vp]),
         "masic_gdn_bwd_b": (i, [vp, vp, vp, i64, i, vp, vp]),
         "masic_reparam_bwd": (i, [vp, vp, i, f, i, vp, vp]),
+        "masic_reparam_batch_create": (i, [vp, vp, vp, vp, vp, vp, i, C.POINTER(vp)]),
+        "masic_reparam_batch_launch": (i, [vp, vp]),
+        "masic_reparam_batch_destroy": (None, [vp]),
         "masic_latent_prep_train": (i, [vp, vp, i64, i, vp, i, vp, i, vp]),
         "masic_latent_merge_bwd": (i, [vp, vp, vp, vp, vp, i64, vp, vp]),
         "masic_add_f32_bf16": (i, [vp, vp, i64, vp, vp]),

@@ -158,6 +158,18 @@ __global__ void reparam_bwd_kernel(const float* __restrict__ dprime, const float
   dstored[i] = accumulate ? dstored[i] + r : r;
 }
 
+// every reparam_bwd of a training step (15 GDN layers x {beta, gamma}) as ONE launch: blockIdx.y = job
+struct ReparamJob { const float* dprime; const float* stored; float* dstored; int n; float bound; int accumulate; int pad; };
+__global__ void reparam_bwd_batch_kernel(const ReparamJob* __restrict__ jobs) {
+  const ReparamJob j = jobs[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.n; i += gridDim.x * blockDim.x) {
+    const float p = j.stored[i];
+    const float g = j.dprime[i] * 2.0f * fmaxf(p, j.bound);
+    const float r = (p >= j.bound || g < 0.0f) ? g : 0.0f;
+    j.dstored[i] = j.accumulate ? j.dstored[i] + r : r;
+  }
+}
+
 // |y| and y + noise as bf16 NHWC copies of an fp32 NHWC latent [pixels][C]
 __global__ void __launch_bounds__(256)
 latent_prep_train_kernel(const float* __restrict__ y, const float* __restrict__ noise, long total, int C,
@@ -312,6 +324,45 @@ extern "C" int masic_reparam_bwd(const float* dprime, const float* stored, int n
   const float bound = sqrtf(minimum + 1.4551915228366852e-11f);
   reparam_bwd_kernel<<<(n + 255) / 256, 256, 0, S(stream)>>>(dprime, stored, n, bound, accumulate, dstored);
   return (int)cudaGetLastError();
+}
+
+struct MasicReparamBatch { ReparamJob* d_jobs; int n_jobs; int max_n; };
+
+extern "C" int masic_reparam_batch_create(const float* const* dprime, const float* const* stored, float* const* dstored,
+                                          const int* numel, const float* minimum, const int* accumulate, int n_jobs,
+                                          MasicReparamBatch** out) {
+  if (!dprime || !stored || !dstored || !numel || !minimum || !out || n_jobs <= 0 || n_jobs > 4096) return MASIC_EINVAL;
+  ReparamJob* h = new ReparamJob[n_jobs];
+  int max_n = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    if (!dprime[i] || !stored[i] || !dstored[i] || numel[i] <= 0) { delete[] h; return MASIC_EINVAL; }
+    h[i].dprime = dprime[i]; h[i].stored = stored[i]; h[i].dstored = dstored[i]; h[i].n = numel[i];
+    h[i].bound = sqrtf(minimum[i] + 1.4551915228366852e-11f);
+    h[i].accumulate = accumulate ? accumulate[i] : 0; h[i].pad = 0;
+    if (numel[i] > max_n) max_n = numel[i];
+  }
+  MasicReparamBatch* b = new MasicReparamBatch();
+  b->n_jobs = n_jobs; b->max_n = max_n; b->d_jobs = nullptr;
+  cudaError_t e = cudaMalloc(&b->d_jobs, sizeof(ReparamJob) * n_jobs);
+  if (e == cudaSuccess) e = cudaMemcpy(b->d_jobs, h, sizeof(ReparamJob) * n_jobs, cudaMemcpyHostToDevice);
+  delete[] h;
+  if (e != cudaSuccess) { if (b->d_jobs) cudaFree(b->d_jobs); delete b; return (int)e; }
+  *out = b;
+  return MASIC_OK;
+}
+
+extern "C" int masic_reparam_batch_launch(const MasicReparamBatch* b, void* stream) {
+  if (!b) return MASIC_EINVAL;
+  int gx = (b->max_n + 255) / 256;
+  if (gx > 64) gx = 64;
+  reparam_bwd_batch_kernel<<<dim3(gx, b->n_jobs), 256, 0, S(stream)>>>(b->d_jobs);
+  return (int)cudaGetLastError();
+}
+
+extern "C" void masic_reparam_batch_destroy(MasicReparamBatch* b) {
+  if (!b) return;
+  if (b->d_jobs) cudaFree(b->d_jobs);
+  delete b;
 }
 
 extern "C" int masic_latent_prep_train(const float* y_nhwc, const float* noise_nhwc, int64_t n_pixels, int c,

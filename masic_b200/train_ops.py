@@ -79,6 +79,36 @@ def gdn_bwd_b(u, x, v, dbias):
     check(_lib.load().masic_gdn_bwd_b(_p(u), _p(x), _p(v), u.numel() // c, c, _p(dbias), _s()), "masic_gdn_bwd_b")
 
 
+class ReparamBatch:
+    """Every (dprime, stored, minimum, dstored) reparam backward of a training step as one launch
+    (masic_reparam_batch_*); the tensors must stay alive and in place."""
+
+    def __init__(self, jobs):
+        import ctypes as C
+        lib = _lib.load()
+        n = len(jobs)
+        self._keep = list(jobs)
+        dp = (C.c_void_p * n)(*[j[0].data_ptr() for j in jobs])
+        st = (C.c_void_p * n)(*[j[1].data_ptr() for j in jobs])
+        ds = (C.c_void_p * n)(*[j[3].data_ptr() for j in jobs])
+        ne = (C.c_int * n)(*[j[1].numel() for j in jobs])
+        mi = (C.c_float * n)(*[float(j[2]) for j in jobs])
+        for j in jobs:
+            assert j[0].numel() == j[1].numel() == j[3].numel() and all(t.dtype == torch.float32 and t.is_contiguous() for t in (j[0], j[1], j[3]))
+        h = C.c_void_p()
+        check(lib.masic_reparam_batch_create(dp, st, ds, ne, mi, None, n, C.byref(h)), "masic_reparam_batch_create")
+        self._h, self._lib = h, lib
+
+    def launch(self):
+        check(self._lib.masic_reparam_batch_launch(self._h, _s()), "masic_reparam_batch_launch")
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.masic_reparam_batch_destroy(h)
+            self._h = None
+
+
 def reparam_bwd(dprime, stored, minimum, dstored, accumulate=False):
     check(_lib.load().masic_reparam_bwd(_p(dprime), _p(stored), stored.numel(), minimum, int(accumulate), _p(dstored),
                                         _s()), "masic_reparam_bwd")

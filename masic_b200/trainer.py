@@ -722,7 +722,10 @@ class HSICTrainer:
         self.Bk("L.hyper", hyp1["bwd"])
         self.Bk("L.latent_merge", lambda: T.latent_merge_bwd(y1, dy1_lik, g_y1hat, g_y1ctx, g_y1abs, gy1))
         self.Bk("L.encoder", encA["bwd"])
-        self.Bk("gdn.reparam", lambda: [g.finish() for g in self.gdn_finish])
+        # the 2 x 15 reparam backwards of the fused-GDN layers as one launch
+        self._reparam = T.ReparamBatch([j for g in self.gdn_finish
+                                        for j in ((g.dbeta_p, g.beta, 1e-6, g.dbeta), (g.dgamma_p, g.gamma, 0.0, g.dgamma))])
+        self.Bk("gdn.reparam", self._reparam.launch)
         self.Bk("scatter", lambda: [f() for f in self.post_bwd])
         # hyper-synthesis conv3x3 of the LEFT view writes / reads channel slice [0, 2M) of the 4M-wide gmm1_in; its
         # gradient arrives in g_gmm1_in[..., 0:2M] (written by net1's layer-0 dgrad) — same layout, nothing to do.
