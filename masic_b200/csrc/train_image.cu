@@ -168,6 +168,93 @@ small_conv_wgrad_kernel(const SCArgs a, float* __restrict__ dw, float* __restric
   }
 }
 
+// Weight gradient of the two 6 <-> 3 channel 5x5 stride-1 layers (pre_conv, after_conv), register-tiled: a thread owns
+// the 5 x 3 elements (kx, co) of one (ci, ky) row of the kernel and one row of an 8 x 64 pixel tile; walking the row it
+// keeps a sliding window of 5 inputs, so a pixel costs 4 shared-memory loads for 15 FMAs (the generic kernel: 2 per FMA).
+// 30 (ci, ky) groups x 8 rows = 240 threads; threads 240..247 sum the bias gradient.  Persistent blocks keep their
+// accumulators over all their tiles and add them to dW with one atomic per element at the end.
+//   conv:        dW[co][ci][ky][kx]  = sum g[co][y][x] in[ci][y + ky - 2][x + kx - 2]
+//   transposed:  dW[ci][co][ky][kx]  = sum g[co][y][x] in[ci][y + 2 - ky][x + 2 - kx]   (the same sums at flipped taps)
+constexpr int WG_TW = 64, WG_TH = 8, WG_PW = WG_TW + 4, WG_PH = WG_TH + 4;
+__global__ void __launch_bounds__(256)
+conv5x5_6x3_wgrad_kernel(const float* __restrict__ in0, const float* __restrict__ in1, int c0, const float* __restrict__ g,
+                         int n, int h, int w, int transposed, float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float s_in[6][WG_PH][WG_PW];
+  __shared__ float s_g[3][WG_TH][WG_TW];
+  const int tid = threadIdx.x, grp = tid >> 3, row = tid & 7;
+  const int ci = grp / 5, ky = grp % 5;                 // valid for grp < 30
+  float acc[5][3];
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[k][c] = 0.0f;
+  const int tiles_x = (w + WG_TW - 1) / WG_TW, tiles_y = (h + WG_TH - 1) / WG_TH;
+  const int n_tiles = tiles_x * tiles_y * n;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int tx = t % tiles_x, r = t / tiles_x, ty = r % tiles_y, b = r / tiles_y;
+    const int y0 = ty * WG_TH, x0 = tx * WG_TW;
+    __syncthreads();
+    for (int i = tid; i < 6 * WG_PH * WG_PW; i += 256) {
+      const int c = i % WG_PW, py = (i / WG_PW) % WG_PH, ch = i / (WG_PW * WG_PH);
+      const int gy = y0 + py - 2, gx = x0 + c - 2;
+      float v = 0.0f;
+      if (gy >= 0 && gy < h && gx >= 0 && gx < w)
+        v = ch < c0 ? __ldg(in0 + ((long)(b * c0 + ch) * h + gy) * w + gx)
+                    : __ldg(in1 + ((long)(b * (6 - c0) + ch - c0) * h + gy) * w + gx);
+      s_in[ch][py][c] = v;
+    }
+    for (int i = tid; i < 3 * WG_TH * WG_TW; i += 256) {
+      const int c = i % WG_TW, py = (i / WG_TW) % WG_TH, co = i / (WG_TW * WG_TH);
+      const int gy = y0 + py, gx = x0 + c;
+      s_g[co][py][c] = (gy < h && gx < w) ? __ldg(g + ((long)(b * 3 + co) * h + gy) * w + gx) : 0.0f;
+    }
+    __syncthreads();
+    if (grp < 30) {
+      const float* ir = &s_in[ci][row + ky][0];
+      float w0 = ir[0], w1 = ir[1], w2 = ir[2], w3 = ir[3];
+#pragma unroll 4
+      for (int x = 0; x < WG_TW; ++x) {
+        const float w4 = ir[x + 4];
+        const float g0 = s_g[0][row][x], g1 = s_g[1][row][x], g2 = s_g[2][row][x];
+        acc[0][0] = fmaf(g0, w0, acc[0][0]); acc[0][1] = fmaf(g1, w0, acc[0][1]); acc[0][2] = fmaf(g2, w0, acc[0][2]);
+        acc[1][0] = fmaf(g0, w1, acc[1][0]); acc[1][1] = fmaf(g1, w1, acc[1][1]); acc[1][2] = fmaf(g2, w1, acc[1][2]);
+        acc[2][0] = fmaf(g0, w2, acc[2][0]); acc[2][1] = fmaf(g1, w2, acc[2][1]); acc[2][2] = fmaf(g2, w2, acc[2][2]);
+        acc[3][0] = fmaf(g0, w3, acc[3][0]); acc[3][1] = fmaf(g1, w3, acc[3][1]); acc[3][2] = fmaf(g2, w3, acc[3][2]);
+        acc[4][0] = fmaf(g0, w4, acc[4][0]); acc[4][1] = fmaf(g1, w4, acc[4][1]); acc[4][2] = fmaf(g2, w4, acc[4][2]);
+        w0 = w1; w1 = w2; w2 = w3; w3 = w4;
+      }
+    } else if (grp == 30 && db) {
+      for (int x = 0; x < WG_TW; ++x) {
+        acc[0][0] += s_g[0][row][x]; acc[0][1] += s_g[1][row][x]; acc[0][2] += s_g[2][row][x];
+      }
+    }
+  }
+  // sum over the 8 rows (threads of a group are 8 consecutive lanes), then one atomic per element
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = acc[k][c];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      acc[k][c] = v;
+    }
+  if (row == 0) {
+    if (grp < 30) {
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx)
+#pragma unroll
+        for (int co = 0; co < 3; ++co) {
+          const int idx = transposed ? ((ci * 3 + co) * 5 + (4 - ky)) * 5 + (4 - kx) : ((co * 6 + ci) * 5 + ky) * 5 + kx;
+          atomicAdd(dw + idx, acc[kx][co]);
+        }
+    } else if (grp == 30 && db) {
+      for (int co = 0; co < 3; ++co) atomicAdd(db + co, acc[0][co]);
+    }
+  }
+}
+
 // one thread per input pixel: d_in[ci] for every input channel (written to din0 / din1; either may be NULL)
 __global__ void __launch_bounds__(128)
 small_conv_dgrad_kernel(const SCArgs a, float* __restrict__ din0, float* __restrict__ din1) {
@@ -475,7 +562,12 @@ extern "C" int masic_conv_small_bwd(const float* in0, int c0, const float* in1, 
   a.ho = (h + stride - 1) / stride; a.wo = (w + stride - 1) / stride;
   a.c_out = c_out; a.k = ksize; a.stride = stride; a.transposed = transposed_s1;
   a.g = g_out; a.act_out = act_out; a.wt = weight;
-  if (dweight_zeroed) {
+  if (dweight_zeroed && ksize == 5 && stride == 1 && c0 + c1 == 6 && c_out == 3 && !act_out && c1 > 0) {
+    const int n_tiles = ((w + WG_TW - 1) / WG_TW) * ((h + WG_TH - 1) / WG_TH) * n;
+    const int blocks = n_tiles < 592 ? n_tiles : 592;
+    conv5x5_6x3_wgrad_kernel<<<blocks, 256, 0, S(stream)>>>(in0, in1, c0, g_out, n, h, w, transposed_s1, dweight_zeroed,
+                                                            dbias_zeroed);
+  } else if (dweight_zeroed) {
     const int nw = c_out * (c0 + c1) * ksize * ksize;
     if (nw + c_out > SW_MAXW * 256) return MASIC_ENOSUP;
     const int span = transposed_s1 ? SW_T + ksize - 1 : (SW_T - 1) * stride + ksize;
