@@ -659,24 +659,30 @@ nchw3_to_nhwc_x4_kernel(const float* __restrict__ in, int f16, int hw, __nv_bflo
   for (int i = 0; i < 4; ++i) store_pixel8_bf16(o + (long)i * pitch, px[i], 3, pitch, f16);
 }
 
-// uint8 image -> float32 in [0, 1]: torchvision's ToTensor (img.float().div(255)), IEEE division, 16 values per thread
+// uint8 image -> float32 in [0, 1]: torchvision's ToTensor (img.float().div(255)).  The 256 possible results are computed
+// once per block with the IEEE division (bit-identical to the host) and looked up: the kernel is then a pure stream
+// (16 bytes in, 64 bytes out per thread) instead of 16 divisions per thread.
 __global__ void __launch_bounds__(256)
 u8_to_unit_f32_kernel(const uint8_t* __restrict__ in, long n, float* __restrict__ out) {
+  __shared__ float lut[256];
+  lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
+  __syncthreads();
   const long i = (blockIdx.x * (long)blockDim.x + threadIdx.x) * 16;
+  if (i >= n) return;
   if (i + 16 <= n && ((reinterpret_cast<uintptr_t>(in + i) & 15) == 0)) {
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + i));
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float4 o;
-      o.x = __fdiv_rn((float)(w[q] & 255u), 255.0f);
-      o.y = __fdiv_rn((float)((w[q] >> 8) & 255u), 255.0f);
-      o.z = __fdiv_rn((float)((w[q] >> 16) & 255u), 255.0f);
-      o.w = __fdiv_rn((float)(w[q] >> 24), 255.0f);
+      o.x = lut[w[q] & 255u];
+      o.y = lut[(w[q] >> 8) & 255u];
+      o.z = lut[(w[q] >> 16) & 255u];
+      o.w = lut[w[q] >> 24];
       reinterpret_cast<float4*>(out + i)[q] = o;
     }
   } else {
-    for (long j = i; j < n && j < i + 16; ++j) out[j] = __fdiv_rn((float)in[j], 255.0f);
+    for (long j = i; j < n && j < i + 16; ++j) out[j] = lut[in[j]];
   }
 }
 

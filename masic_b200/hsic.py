@@ -337,8 +337,10 @@ class PairStream:
 
     def submit(self, x1: torch.Tensor, x2: torch.Tensor, h: torch.Tensor, criterion: bool = True,
                want_recon: bool = False) -> int:
-        """Queue one pair.  x1 / x2: (1,3,H,W) float32 in [0,1] as the reference feeds them, or uint8 images as they
-        come out of the dataset's PNG files (converted on the device exactly like torchvision's ToTensor); h: (1,3,3)
+        """Queue one pair.  x1 / x2: (1,3,H,W) uint8 images as they come out of the dataset's PNG files (the recommended
+        host format: converted on the device exactly like torchvision's ToTensor, a quarter of the PCIe bytes, which is
+        what keeps eight ranks on one host from becoming host-bound), or float32 in [0,1] as the reference's loaders
+        feed them; h: (1,3,3)
         float32.  Pinned host tensors (H2D copy) or device tensors (D2D copy).  criterion=False
         skips the RateDistortionLoss reduction (forward only; `result` then just waits for the pair).  want_recon=True
         also copies the two reconstructions (what a codec is for) to pinned host memory: `reconstructions(ticket)`."""

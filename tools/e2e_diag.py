@@ -37,10 +37,11 @@ for name, src, h, crit in (("device inputs, no criterion", xd, hd, False), ("dev
                            ("host uint8 inputs, no criterion", xu, hh, False), ("host uint8 inputs, criterion + read-back", xu, hh, True)):
     run(src, h, crit)
     torch.cuda.synchronize()
-    best = 1e9
-    for _ in range(3):
+    reps = []
+    for _ in range(6):
         t0 = time.perf_counter()
         run(src, h, crit)
         torch.cuda.synchronize()
-        best = min(best, (time.perf_counter() - t0) / N)
-    print(f"{name:42s} {best * 1e3:.3f} ms/pair  {1 / best:.1f} pairs/s")
+        reps.append((time.perf_counter() - t0) / N)
+    best = min(reps)
+    print(f"{name:42s} {best * 1e3:.3f} ms/pair  {1 / best:.1f} pairs/s   all: " + " ".join(f"{1 / r:.0f}" for r in reps))
