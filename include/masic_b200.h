@@ -42,7 +42,7 @@ extern "C" {
 #define MASIC_EDRIVER (-3)  /* cuTensorMapEncodeTiled unavailable / failed  */
 
 /* ---------------------------------------------------------------- version */
-int masic_abi_version(void);                 /* bumps on any signature change (2: residual inputs, 3: grouped launches of MasicConvDesc, 4: pack batches, 5: cta_pairs, 6: MASIC_CONV_XFOLD8, 7: masic_rans_*, udh front-end entry points, 8: `int f16` format selectors / MasicConvDesc.f16) */
+int masic_abi_version(void);                 /* bumps on any signature change (2: residual inputs, 3: grouped launches of MasicConvDesc, 4: pack batches, 5: cta_pairs, 6: MASIC_CONV_XFOLD8, 7: masic_rans_*, udh front-end entry points, 8: `int f16` format selectors / MasicConvDesc.f16, 9: in_row_pixels / out_blk_images, 10: masic_warp_perspective_fwd3) */
 const char* masic_build_info(void);          /* "sm_100a nvcc 12.9 ..." */
 
 /* ------------------------------------------------------------------ convs */
@@ -364,6 +364,13 @@ int masic_warp_perspective_fwd2(const float* src, int n, int c, int h, int w, in
                                 const double* t_prepared, float* dst_nchw, void* dst_nhwc_bf16, int bf_pitch,
                                 int bf_row_pixels, int bf_xoff, int f16, void* dst2_nhwc16, int d2_pitch,
                                 int d2_row_pixels, int d2_xoff, int d2_coff, int d2_f16, void* stream);
+/* Same, and the warp of the ALL-ONES image under the same transform (mask(), MASIC.py:636-638: x1_mask_R) written to
+ * dst_ones_nchw (n,1,h_out,w_out) from the same launch — the coordinates are evaluated once for both (NULL = fwd2). */
+int masic_warp_perspective_fwd3(const float* src, int n, int c, int h, int w, int h_out, int w_out,
+                                const double* t_prepared, float* dst_nchw, void* dst_nhwc_bf16, int bf_pitch,
+                                int bf_row_pixels, int bf_xoff, int f16, void* dst2_nhwc16, int d2_pitch,
+                                int d2_row_pixels, int d2_xoff, int d2_coff, int d2_f16, float* dst_ones_nchw,
+                                void* stream);
 
 /* Direct conv for the tiny-channel layers (c_in <= 8, c_out <= 8) on NCHW fp32:
  *   Encoder2.pre_conv+pre_gdn (MASIC.py:573-574): in0=x1_warp, in1=x2, k=5, s=1, gdn=FWD

@@ -158,6 +158,7 @@ def _declare(lib: C.CDLL) -> None:
         "masic_warp_prepare": (i, [vp, i, i, i, i, i, i, vp, vp]),
         "masic_warp_perspective_fwd": (i, [vp, i, i, i, i, i, i, vp, vp, vp, i, i, i, i, vp]),
         "masic_warp_perspective_fwd2": (i, [vp, i, i, i, i, i, i, vp, vp, vp, i, i, i, i, vp, i, i, i, i, i, vp]),
+        "masic_warp_perspective_fwd3": (i, [vp, i, i, i, i, i, i, vp, vp, vp, i, i, i, i, vp, i, i, i, i, i, vp, vp]),
         "masic_conv_small_nchw": (i, [vp, i, vp, i, i, i, i, vp, i, vp, i, i, i, i, i, vp, vp, f, vp, vp, i, i, i, i, vp]),
         "masic_mask2weights": (i, [vp, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "masic_subpix_to_nchw": (i, [vp, i, i, i, i, i, vp, vp, f, vp, vp, i, i, vp]),

@@ -1424,7 +1424,11 @@ extern "C" int masic_conv_plan_create(const MasicConvDesc* dp, MasicConvPlan** p
   const int n_stage_blk = (d.gdn && !kp.gdn2 && !kp.gdnt) ? 2 : 4;
   const int gamma_bytes = d.gdn ? (kp.cg2 ? STAGE_BLK_BYTES : 2 * STAGE_BLK_BYTES) : 0;
   const int fixed = gamma_bytes + n_stage_blk * STAGE_BLK_BYTES + MISC_BYTES + 1024 /*align*/;
-  const int budget = 227 * 1024 - fixed;                      // ring bytes
+  // MASIC_CONV_SMEM_RESERVE=bytes leaves that much shared memory of the SM unused, so that a CTA of a CUDA-core kernel
+  // (warp, likelihood: other stream, other engine) can be resident beside the persistent conv CTA
+  int reserve = 0;
+  { const char* e = getenv("MASIC_CONV_SMEM_RESERVE"); if (e && atoi(e) > 0 && atoi(e) <= 96 * 1024) reserve = atoi(e); }
+  const int budget = 227 * 1024 - fixed - reserve;            // ring bytes
   int sa = 2, sb = 2;
   // resident weights: single program, single n-tile, and the whole k-block list fits next to a double-buffered A ring
   const int n_bops0 = kp.var[0].n_bops;

@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/masic_b200.h"
 #include "cvt16.cuh"
@@ -188,6 +189,117 @@ warp_kernel(const float* __restrict__ src, int n, int c_rt, int h, int w, int ho
     } else {
 #pragma unroll
       for (int ch = 0; ch < NV; ++ch) if (ch < c) o[ch] = pack16(vals[ch], d2_f16);
+    }
+  }
+}
+
+// The engine's hot configurations of the kernel above (C = 3 or 1, fp32 planes and / or the two 16-bit images the
+// right view's encoder and the tensor-core after_conv read), with the same per-pixel arithmetic in the same order
+// (bit-identical outputs) and a fraction of the instructions: the generic form spends ~325 issued instructions per
+// pixel, most of them 64-bit address arithmetic repeated for every tap and plane and the per-thread set-up (nine fp64
+// matrix loads, the row terms).  Here a thread walks WF_PPT pixels of one row (x = x0 + i * WF_BLK, so a warp still
+// touches 32 consecutive pixels), keeps the row terms yn * t[1,4,7] + nothing else hoisted (the fused multiply-adds of
+// the generic form are kept as they are), holds one base pointer per source plane / destination row and reaches every
+// tap with one 32-bit multiply-add.  SPLIT: dst16 pixels are [hi(3) | lo(3) | 0 0] halves (MASIC_FMT_F16 |
+// MASIC_FMT_SPLIT, 8-channel pitch); dst2 is the plain fp16 [v0 v1 v2 0] half of a shared 8-channel pixel.
+constexpr int WF_BLK = 64, WF_PPT = 4;
+template <int CT>
+__global__ void __launch_bounds__(WF_BLK)
+warp_fast_kernel(const float* __restrict__ src, int h, int w, int ho, int wo, const double* __restrict__ T,
+                 double inv_wo1, double inv_ho1, float* __restrict__ dst, uint16_t* __restrict__ dst16, int bf_row,
+                 int bf_xoff, uint16_t* __restrict__ dst2, int d2_row, int d2_xoff, int d2_coff,
+                 float* __restrict__ dst_ones) {
+  const int y = blockIdx.y, b = blockIdx.z;
+  const int xb = blockIdx.x * (WF_BLK * WF_PPT) + threadIdx.x;
+  if (xb >= wo) return;
+  const double* t = T + b * 9;
+  const double t0 = t[0], t1 = t[1], t2 = t[2], t3 = t[3], t4 = t[4], t5 = t[5], t6 = t[6], t7 = t[7], t8 = t[8];
+  const double yn = ((double)y * inv_ho1 - 0.5) * 2.0;
+  const double r0 = yn * t1, r1 = yn * t4, r2 = yn * t7;
+  const double wm1 = (double)(w - 1), hm1 = (double)(h - 1);
+  const size_t hw = (size_t)h * w;
+  const size_t dplane = (size_t)ho * wo;
+  // one pointer per source plane and per destination row, pinned in registers (the opaque asm keeps the compiler from
+  // folding the plane offset back into every tap's 64-bit index arithmetic): a tap is then base + 4 * u32
+  const float* sp[CT];
+  float* dp[CT];
+#pragma unroll
+  for (int ch = 0; ch < CT; ++ch) {
+    sp[ch] = src ? src + ((size_t)b * CT + ch) * hw : nullptr;
+    dp[ch] = dst ? dst + (((size_t)b * CT + ch) * ho + y) * wo : nullptr;
+    asm volatile("" : "+l"(sp[ch]), "+l"(dp[ch]));
+  }
+  uint16_t* o16 = dst16 ? dst16 + ((size_t)(b * ho + y) * bf_row + bf_xoff) * 8 : nullptr;
+  uint16_t* o2 = dst2 ? dst2 + ((size_t)(b * ho + y) * d2_row + d2_xoff) * 8 + d2_coff : nullptr;
+  float* o1 = dst_ones ? dst_ones + ((size_t)b * ho + y) * wo : nullptr;     // warp of the all-ones image, same T
+#pragma unroll
+  for (int i = 0; i < WF_PPT; ++i) {
+    const int x = xb + i * WF_BLK;
+    if (x >= wo) break;
+    const double xn = ((double)x * inv_wo1 - 0.5) * 2.0;
+    const double q0 = fma(xn, t0, r0) + t2;
+    const double q1 = fma(xn, t3, r1) + t5;
+    const double q2 = fma(xn, t6, r2) + t8;
+    const double den = fabs(q2) >= 0.25 ? q2 : q2 + 1e-8;
+    const double aden = fabs(den);
+    const double sc = fabs(q2) > 1e-8 ? ((aden > 1e-30 && aden < 1e30) ? fast_rcp(den) : 1.0 / den) : 1.0;
+    const double gx = q0 * sc, gy = q1 * sc;
+    const double ixd = ((gx + 1.0) / 2.0) * wm1;
+    const double iyd = ((gy + 1.0) / 2.0) * hm1;
+    const double fxd = floor(ixd), fyd = floor(iyd);
+    const float ix = (float)(ixd - fxd), iy = (float)(iyd - fyd);
+    const float wx1 = ix - 0.0f, wx0 = (0.0f + 1.0f) - ix;
+    const float wy1 = iy - 0.0f, wy0 = (0.0f + 1.0f) - iy;
+    const float w_nw = wx0 * wy0, w_ne = wx1 * wy0, w_sw = wx0 * wy1, w_se = wx1 * wy1;
+    const bool finite = fabs(ixd) < 1e9 && fabs(iyd) < 1e9;
+    const int x0 = finite ? (int)fxd : -10, y0 = finite ? (int)fyd : -10;
+    float k_nw = w_nw, k_ne = w_ne, k_sw = w_sw, k_se = w_se;
+    unsigned o_nw, d_e = 1u, d_s = (unsigned)w;                 // ne = nw + d_e, sw = nw + d_s, se = nw + d_s + d_e
+    if (x0 >= 0 && x0 + 1 < w && y0 >= 0 && y0 + 1 < h) {       // all four taps inside the image (nearly every pixel)
+      o_nw = (unsigned)(y0 * w + x0);
+    } else {                                                   // border: zero weight on a clamped address
+      const bool in_x0 = x0 >= 0 && x0 < w, in_x1 = x0 + 1 >= 0 && x0 + 1 < w;
+      const bool in_y0 = y0 >= 0 && y0 < h, in_y1 = y0 + 1 >= 0 && y0 + 1 < h;
+      k_nw = (in_y0 && in_x0) ? w_nw : 0.0f; k_ne = (in_y0 && in_x1) ? w_ne : 0.0f;
+      k_sw = (in_y1 && in_x0) ? w_sw : 0.0f; k_se = (in_y1 && in_x1) ? w_se : 0.0f;
+      const int xc0 = min(max(x0, 0), w - 1), xc1 = min(max(x0 + 1, 0), w - 1);
+      const int yc0 = min(max(y0, 0), h - 1), yc1 = min(max(y0 + 1, 0), h - 1);
+      o_nw = (unsigned)(yc0 * w + xc0);
+      d_e = (unsigned)(xc1 - xc0);
+      d_s = (unsigned)((yc1 - yc0) * w);
+    }
+    if (o1) o1[(unsigned)x] = ((k_nw + k_ne) + k_sw) + k_se;
+    float vals[CT];
+#pragma unroll
+    for (int ch = 0; ch < CT; ++ch) {
+      float v;
+      if (src) {
+        const float* s = sp[ch] + o_nw;
+        const float* s2 = s + d_s;
+        const float a = __ldg(s), bq = __ldg(s + d_e), cq = __ldg(s2), d = __ldg(s2 + d_e);
+        v = a * k_nw;
+        v += bq * k_ne;
+        v += cq * k_sw;
+        v += d * k_se;
+      } else {
+        v = ((k_nw + k_ne) + k_sw) + k_se;
+      }
+      vals[ch] = v;
+      if (dst) dp[ch][(unsigned)x] = v;
+    }
+    if (CT == 3) {
+      if (o16) {          // [hi0 hi1 hi2 lo0 | lo1 lo2 0 0] as one 16-byte store
+        float lo[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+          lo[ch] = vals[ch] - masic::unpack16(pack16(vals[ch], MASIC_FMT_F16), MASIC_FMT_F16);
+        *reinterpret_cast<uint4*>(o16 + (unsigned)x * 8u) =
+            make_uint4(pack16x2(vals[0], vals[1], MASIC_FMT_F16), pack16x2(vals[2], lo[0], MASIC_FMT_F16),
+                       pack16x2(lo[1], lo[2], MASIC_FMT_F16), 0u);
+      }
+      if (o2)
+        *reinterpret_cast<uint2*>(o2 + (unsigned)x * 8u) =
+            make_uint2(pack16x2(vals[0], vals[1], MASIC_FMT_F16), pack16x2(vals[2], 0.0f, MASIC_FMT_F16));
     }
   }
 }
@@ -725,14 +837,45 @@ extern "C" int masic_warp_perspective_fwd2(const float* src, int n, int c, int h
                                            int bf_pitch, int bf_row_pixels, int bf_xoff, int f16, void* dst2_nhwc16,
                                            int d2_pitch, int d2_row_pixels, int d2_xoff, int d2_coff, int d2_f16,
                                            void* stream) {
-  if (!t_prepared || n <= 0 || c <= 0 || c > 8 || (!dst_nchw && !dst_nhwc_bf16 && !dst2_nhwc16)) return MASIC_EINVAL;
+  return masic_warp_perspective_fwd3(src, n, c, h, w, h_out, w_out, t_prepared, dst_nchw, dst_nhwc_bf16, bf_pitch,
+                                     bf_row_pixels, bf_xoff, f16, dst2_nhwc16, d2_pitch, d2_row_pixels, d2_xoff, d2_coff,
+                                     d2_f16, nullptr, stream);
+}
+
+extern "C" int masic_warp_perspective_fwd3(const float* src, int n, int c, int h, int w, int h_out, int w_out,
+                                           const double* t_prepared, float* dst_nchw, void* dst_nhwc_bf16,
+                                           int bf_pitch, int bf_row_pixels, int bf_xoff, int f16, void* dst2_nhwc16,
+                                           int d2_pitch, int d2_row_pixels, int d2_xoff, int d2_coff, int d2_f16,
+                                           float* dst_ones_nchw, void* stream) {
+  if (!t_prepared || n <= 0 || c <= 0 || c > 8 || (!dst_nchw && !dst_nhwc_bf16 && !dst2_nhwc16 && !dst_ones_nchw))
+    return MASIC_EINVAL;
   if (bf_row_pixels == 0) { bf_row_pixels = w_out; bf_xoff = 0; }
   if (bf_row_pixels < w_out + bf_xoff || bf_xoff < 0) return MASIC_EINVAL;
   if (dst2_nhwc16 && (d2_pitch < d2_coff + c || d2_coff < 0 || d2_xoff < 0 || d2_row_pixels < w_out + d2_xoff))
     return MASIC_EINVAL;
   if (h_out < 2 || w_out < 2) return MASIC_ENOSUP;
-  dim3 grid((w_out + 255) / 256, h_out, n);
   if ((long)h * w >= (1L << 31)) return MASIC_ENOSUP;
+  // the engine's configurations: 3- or 1-channel images, 16-bit copies (if any) as fp16 hi|lo pixels of pitch 8 and
+  // as the aligned plain-fp16 half of a shared 8-channel pixel (MASIC_WARP_FAST=0: the generic kernel)
+  static const bool fast_ok = []() { const char* e = getenv("MASIC_WARP_FAST"); return !(e && atoi(e) == 0); }();
+  const bool fmt16_ok = !dst_nhwc_bf16 || (c == 3 && bf_pitch == 8 && f16 == (MASIC_FMT_F16 | MASIC_FMT_SPLIT));
+  const bool fmt2_ok = !dst2_nhwc16 || (c == 3 && d2_pitch == 8 && (d2_coff & 3) == 0 && (d2_f16 & 1) == 1);
+  if (fast_ok && (c == 3 || c == 1) && fmt16_ok && fmt2_ok && (long)n * c * h * w < (1L << 40)) {
+    dim3 fgrid((w_out + WF_BLK * WF_PPT - 1) / (WF_BLK * WF_PPT), h_out, n);
+    auto fk = c == 3 ? warp_fast_kernel<3> : warp_fast_kernel<1>;
+    fk<<<fgrid, WF_BLK, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, h, w, h_out, w_out, t_prepared, 1.0 / (double)(w_out - 1), 1.0 / (double)(h_out - 1), dst_nchw,
+        static_cast<uint16_t*>(dst_nhwc_bf16), bf_row_pixels, bf_xoff, static_cast<uint16_t*>(dst2_nhwc16),
+        d2_row_pixels, d2_xoff, d2_coff, dst_ones_nchw);
+    return (int)cudaGetLastError();
+  }
+  dim3 grid((w_out + 255) / 256, h_out, n);
+  if (dst_ones_nchw) {          // generic path: the mask is a second launch with the all-ones source
+    warp_kernel<1><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        nullptr, n, 1, h, w, h_out, w_out, t_prepared, 1.0 / (double)(w_out - 1), 1.0 / (double)(h_out - 1),
+        dst_ones_nchw, nullptr, 0, w_out, 0, 0, nullptr, 0, 0, 0, 0, 0);
+    if (!dst_nchw && !dst_nhwc_bf16 && !dst2_nhwc16) return (int)cudaGetLastError();
+  }
   auto kern = c == 3 ? warp_kernel<3> : (c == 1 ? warp_kernel<1> : warp_kernel<0>);
   kern<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, n, c, h, w, h_out, w_out, t_prepared, 1.0 / (double)(w_out - 1), 1.0 / (double)(h_out - 1), dst_nchw,

@@ -263,7 +263,8 @@ class HSICEngine:
         p1 = PackedConv(ksize=1, c_in=6 * M, c_out=13 * M, n_tile=192, weight=w1, bias=b1, f16=F16)
         self.packs[f"{tag}.gmm.l1(3 branches)"] = p1            # the wave decoder runs the same grouped launches
         plan = ConvPlan(packed=p1, x=l0, out=l1, act=[ACT_RELU] * nt(4 * M) + [ACT_LEAKY] * nt(9 * M),
-                        nt_in_coff=[0] * nt(4 * M) + [6 * M] * nt(4 * M) + [12 * M] * nt(5 * M))
+                        nt_in_coff=[0] * nt(4 * M) + [6 * M] * nt(4 * M) + [12 * M] * nt(5 * M),
+                        cta_pairs=os.environ.get("MASIC_GMM_L1_CG2", "0") != "0")
         self.plans[f"{tag}.gmm.l1(3 branches)"] = plan
         self._add(f"{tag}.gmm.l1(3 branches)", plan.launch)
         smw = self._buf(3 * B, h16, w16, MK, dtype=torch.float32)     # sigma | mu | weight logits, each dense [B][P][MK]
@@ -275,10 +276,12 @@ class HSICEngine:
         tiles = list(range(0, MK, 192))
         plan = ConvPlan(packed=p2, x=l1, out=smw, act=[ACT_RELU] * nt(MK) + [ACT_NONE] * nt(MK),
                         nt_in_coff=[0] * nt(MK) + [4 * M] * nt(MK), nt_out_coff=tiles + tiles,
-                        nt_out_img=[0] * nt(MK) + [B] * nt(MK))
+                        nt_out_img=[0] * nt(MK) + [B] * nt(MK),
+                        cta_pairs=os.environ.get("MASIC_GMM_L2_CG2", "0") != "0")
         self.plans[f"{tag}.gmm.l2(sigma|means)"] = plan
         self._add(f"{tag}.gmm.l2(sigma|means)", plan.launch)
-        self._conv(f"{tag}.gmm.weights.l2", self.packs[f"{tag}.gmm.weights.l2"], l1, wl, in_coff=8 * M)
+        self._conv(f"{tag}.gmm.weights.l2", self.packs[f"{tag}.gmm.weights.l2"], l1, wl, in_coff=8 * M,
+                   cta_pairs=os.environ.get("MASIC_GMM_L2_CG2", "0") != "0")
         self.buf[f"{tag}.sigma"], self.buf[f"{tag}.mu"], self.buf[f"{tag}.wlogit"] = sig, mu, wl
         return sig, mu, wl
 
@@ -307,13 +310,14 @@ class HSICEngine:
                   "masic_latent_prep")
         self._add(f"{tag}.latent_prep", step)
 
-    def _warp(self, tag, src, T, dst, dst_bf=None, channels=3, dst2=None, dst2_coff=0):
+    def _warp(self, tag, src, T, dst, dst_bf=None, channels=3, dst2=None, dst2_coff=0, ones=None):
         """dst: NCHW fp32; dst_bf: hi|lo image for g_a_conv1; dst2: plain 16-bit copy at channel dst2_coff of a shared
-        channels-last image (the tensor-core after_conv's input).  Any of them may be None."""
+        channels-last image (the tensor-core after_conv's input); ones: the warp of the all-ones image under the same
+        transform (x1_mask_R, MASIC.py:636-638) from the same launch.  Any of them may be None."""
         B, H, W = self.B, self.H, self.W
 
         def step():
-            check(self.lib.masic_warp_perspective_fwd2(None if src is None else src.data_ptr(), B, channels, H, W, H, W,
+            check(self.lib.masic_warp_perspective_fwd3(None if src is None else src.data_ptr(), B, channels, H, W, H, W,
                                                        T.data_ptr(), None if dst is None else dst.data_ptr(),
                                                        None if dst_bf is None else dst_bf.data_ptr(),
                                                        0 if dst_bf is None else dst_bf.shape[3],
@@ -322,8 +326,9 @@ class HSICEngine:
                                                        None if dst2 is None else dst2.data_ptr(),
                                                        0 if dst2 is None else dst2.shape[3],
                                                        0 if dst2 is None else dst2.shape[2],
-                                                       0 if dst2 is None else XOFF, dst2_coff, F16, self._s()),
-                  "masic_warp_perspective_fwd2")
+                                                       0 if dst2 is None else XOFF, dst2_coff, F16,
+                                                       None if ones is None else ones.data_ptr(), self._s()),
+                  "masic_warp_perspective_fwd3")
         self._add(tag, step)
 
     def _conv_small(self, tag, in0, in1, wname, *, ksize, stride, transposed_s1=False, act=ACT_NONE, gdn=GDN_NONE,
@@ -389,7 +394,14 @@ class HSICEngine:
             check(lib.masic_warp_prepare(self.Hm.data_ptr(), B, H, W, H, W, 0, T.data_ptr(), self._s()), "masic_warp_prepare"),
             check(lib.masic_warp_prepare(self.Hm.data_ptr(), B, H, W, H, W, 1, Tinv.data_ptr(), self._s()), "masic_warp_prepare")))
         self._record("T")
-        self._warp("mask_R=warp(ones)", None, T, o["x1_mask_R"], channels=1)
+        # x1 and the all-ones image are warped by ONE launch (same transform: the fp64 coordinates, ~60 % of the kernel's
+        # instructions, are evaluated once); MASIC_WARP_MASK_FUSED=0 keeps the two launches
+        x1_warp = self._buf(B, 3, H, W, dtype=f32)
+        mask_fused = os.environ.get("MASIC_WARP_MASK_FUSED", "1") != "0"
+        if mask_fused:
+            self._warp("R.warp(x1)+mask_R", self.x1, T, x1_warp, ones=o["x1_mask_R"])
+        else:
+            self._warp("mask_R=warp(ones)", None, T, o["x1_mask_R"], channels=1)
         self._warp("mask_L=warp(mask_R,Hinv)", o["x1_mask_R"], Tinv, o["x1_mask_L"], channels=1)
         # mask2weights: 4x (conv3 s2 [+ReLU]) + softmax over 3 (MASIC.py:472-506)
         mk = "mask2weights_unit.maskconv"
@@ -413,8 +425,8 @@ class HSICEngine:
             self._add("mask2weights.softmax", lambda: check(lib.masic_softmax_channels(
                 k4.data_ptr(), B, 3, h16 * w16, None, mw.data_ptr(), self._s()), "masic_softmax_channels"))
         self._record("mw")
-        x1_warp = self._buf(B, 3, H, W, dtype=f32)
-        self._warp("R.warp(x1)", self.x1, T, x1_warp)
+        if not mask_fused:
+            self._warp("R.warp(x1)", self.x1, T, x1_warp)
         x2in_bf = self._buf(B, H, W + XPAD, IMG_CP)
         self._conv_small("R.pre_conv+pre_gdn", x1_warp, self.x2, "encoder2.pre_conv", ksize=5, stride=1, gdn=GDN_FWD,
                          gdn_prefix="encoder2.pre_gdn", out_bf=x2in_bf)

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(lib):
     missing = [n for n in names if n not in exported]
     assert not missing, missing
     assert sorted(_lib.declared_symbols()) == names          # the ctypes binding covers the whole header
-    assert lib.masic_abi_version() == 9
+    assert lib.masic_abi_version() == 10
     assert b"sm_100a" in lib.masic_build_info()
 
 
