@@ -462,8 +462,8 @@ def run_ours(args, rank, world, local_rank):
         torch.manual_seed(0)
         tnet = HSIC().to(dev).train()
         tr = tnet.trainer(2, 512, 896, dev, lmbda=0.01)
-        opt = torch.optim.Adam(tnet.parameters(), lr=1e-4)
-        aux = torch.optim.Adam(tnet.aux_parameters(), lr=1e-3)
+        opt = torch.optim.Adam(tnet.parameters(), lr=1e-4, fused=True)      # one multi-tensor launch per step instead of ~25
+        aux = torch.optim.Adam(tnet.aux_parameters(), lr=1e-3, fused=True)
         g = torch.Generator().manual_seed(100 + rank)
         tx1 = torch.rand(4, 2, 3, 512, 896, generator=g).to(dev)
         tx2 = torch.rand(4, 2, 3, 512, 896, generator=g).to(dev)

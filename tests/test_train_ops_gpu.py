@@ -310,3 +310,41 @@ def test_image_domain_backward(dev):
     T.wgrad_small(lo, 128, hi, dws)
     torch.cuda.synchronize()
     _close(dws, wz.grad, 1e-4, "wgrad small")
+
+
+def test_pack_batch_equals_the_per_layer_pack(dev):
+    """masic_pack_batch_* (every re-pack of a training step in one launch; plain conv / transposed-conv layers through a
+    shared-memory tile, the special kinds element-wise) writes exactly what masic_pack_conv_weights writes — every layer
+    shape class of the trainer: 5x5 / 3x3 / 1x1, Conv2d and ConvTranspose2d layouts, stride-1 transposed (flipped) packs,
+    channel counts that are not multiples of 64 or of the n-tile, the XFOLD8 and sub-pixel kinds, padded biases."""
+    from masic_b200 import _lib
+    from masic_b200.convplan import PackBatch, PackedConv
+    g = torch.Generator().manual_seed(3)
+    CONV, DEC = _lib.CONV, _lib.DECONV_S2
+    cases = [  # kind, k, c_in, c_out, n_tile, transposed
+        (CONV, 5, 128, 128, 128, False), (CONV, 5, 128, 192, 192, False), (CONV, 1, 768, 3456, 192, False),
+        (CONV, 3, 288, 384, 192, False), (CONV, 5, 192, 384, 192, False), (CONV, 1, 1152, 768, 192, True),
+        (CONV, 3, 288, 384, 192, True), (CONV, 5, 128, 128, 128, True), (DEC, 5, 128, 128, 128, True),
+        (DEC, 5, 192, 128, 128, True), (DEC, 5, 128, 128, 128, False), (DEC, 5, 320, 192, 192, False),
+        (CONV, 5, 48, 80, 16, False), (_lib.CONV_XFOLD8, 5, 64, 128, 128, False), (_lib.DECONV_S2_SUBPIX, 5, 128, 3, 16, True),
+    ]
+    jobs, want = [], []
+    for kind, k, ci, co, nt, tr in cases:
+        if kind == _lib.CONV_XFOLD8:
+            w = torch.randn(co, 3, k, k, generator=g).to(dev)
+        elif tr:
+            w = torch.randn(ci, co, k, k, generator=g).to(dev)
+        else:
+            w = torch.randn(co, ci, k, k, generator=g).to(dev)
+        b = torch.randn(co, generator=g).to(dev)
+        ref = PackedConv(kind=kind, ksize=k, c_in=ci, c_out=co, n_tile=nt, weight=w, transposed=tr, bias=b)
+        pk = PackedConv(kind=kind, ksize=k, c_in=ci, c_out=co, n_tile=nt, weight=torch.zeros_like(w), transposed=tr,
+                        bias=torch.zeros_like(b))
+        pk.w_packed.fill_(7.0)                       # stale contents must be overwritten, padding included
+        jobs.append((pk, w, b))
+        want.append(ref)
+    PackBatch(jobs).launch()
+    torch.cuda.synchronize()
+    for (pk, _, _), ref, case in zip(jobs, want, cases):
+        assert torch.equal(pk.w_packed.view(torch.int16), ref.w_packed.view(torch.int16)), case
+        assert torch.equal(pk.bias, ref.bias), case

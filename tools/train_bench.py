@@ -40,8 +40,8 @@ def main():
     torch.manual_seed(0)
     net = HSIC().to(dev).train()
     tr = net.trainer(B, H, W, dev, lmbda=0.01)
-    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
-    aux = torch.optim.Adam(net.aux_parameters(), lr=1e-3)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, fused=True)
+    aux = torch.optim.Adam(net.aux_parameters(), lr=1e-3, fused=True)
     g = torch.Generator().manual_seed(100 + rank)
     x1 = torch.rand(4, B, 3, H, W, generator=g).to(dev)
     x2 = torch.rand(4, B, 3, H, W, generator=g).to(dev)
