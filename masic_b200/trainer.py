@@ -30,6 +30,7 @@ No CPU fallback: everything raises on non-CUDA tensors.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -142,7 +143,7 @@ class _Layer:
                     T.act_bwd_bias(self.gout, self.out_coff + c0, c1 - c0, self.out if acts[i] != ACT_NONE else None,
                                    self.out_coff + c0, acts[i], self.db[c0:c1])
                     i = j
-        self.wg_plan.launch()
+        self.tr.wg_async(self.wg_plan.launch)
         if self.dg_plan is not None:
             self.dg_plan.launch()
 
@@ -206,7 +207,7 @@ class _GDN:
         T.gdn_bwd_a(self.gy, self.x, self.norm, self.inverse, self.t, self.dbeta_p)
         self.p_v.launch()
         T.gdn_bwd_b(self.gy, self.x, self.v, dbias)
-        self.wg.launch()
+        self.tr.wg_async(self.wg.launch)
 
     def finish(self):
         T.reparam_bwd(self.dbeta_p, self.beta, 1e-6, self.dbeta)
@@ -268,7 +269,9 @@ class HSICTrainer:
         self.fwd_ops: List[Tuple[str, Callable[[], None]]] = []
         self.bwd_ops: List[Tuple[str, Callable[[], None]]] = []
         self.flops_fwd = 0.0
+        self.wg_overlap = os.environ.get("MASIC_TRAIN_WG_STREAM", "1") != "0"
         with torch.cuda.device(self.dev):
+            self._wg_stream = torch.cuda.Stream(device=self.dev) if self.wg_overlap else None
             self._build()
 
     # ------------------------------------------------------------------ helpers
@@ -286,6 +289,28 @@ class HSICTrainer:
 
     def Bk(self, name, fn):
         self.bwd_ops.append((name, fn))
+
+    # Weight gradients are leaves of the backward pass: nothing downstream reads dW before the optimizer.  They are
+    # issued on a SECOND stream (forked from the main stream at the point where their operands are final, joined once
+    # before the reparametrisation / scatter ops that read the gradients), so the ~115 wgrad + reduce launches — most
+    # of them at 1/8 and 1/16 resolution with fewer than 148 busy CTAs — overlap the data-gradient chain instead of
+    # extending it.  All of them share ONE side stream: they also share one partial-sum workspace.  Every operand
+    # buffer of the step is allocated once and never reused, so the fork event is the only ordering they need.
+    def wg_async(self, fn):
+        if not self.wg_overlap:
+            fn()
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        self._wg_stream.wait_event(ev)
+        with torch.cuda.stream(self._wg_stream):
+            fn()
+
+    def wg_join(self):
+        if self.wg_overlap:
+            ev = torch.cuda.Event()
+            ev.record(self._wg_stream)
+            torch.cuda.current_stream().wait_event(ev)
 
     # ------------------------------------------------------------------ sub-graphs
     def _encoder_pass(self, tag: str, enc: str, img_bf: torch.Tensor, img_nchw: torch.Tensor, accumulate: bool,
@@ -379,8 +404,7 @@ class HSICTrainer:
             T.colsum_nchw(gimg, db4)
             check(lib.masic_nchw_to_nhwc_bf16(gimg.data_ptr(), B, 3, H, W, gimg16.data_ptr(), 16, 0, 0, 0, T._s()),
                   "masic_nchw_to_nhwc_bf16")
-            wg4.launch()
-            dw4.add_(dw16[:, :3])
+            self.wg_async(lambda: (wg4.launch(), dw4.add_(dw16[:, :3])))
             dplan4.launch()
             for i in (2, 1, 0):
                 gdns[i].bwd(layers[i].db)
@@ -725,6 +749,7 @@ class HSICTrainer:
         # the 2 x 15 reparam backwards of the fused-GDN layers as one launch
         self._reparam = T.ReparamBatch([j for g in self.gdn_finish
                                         for j in ((g.dbeta_p, g.beta, 1e-6, g.dbeta), (g.dgamma_p, g.gamma, 0.0, g.dgamma))])
+        self.Bk("wgrad.join", self.wg_join)
         self.Bk("gdn.reparam", self._reparam.launch)
         self.Bk("scatter", lambda: [f() for f in self.post_bwd])
         # hyper-synthesis conv3x3 of the LEFT view writes / reads channel slice [0, 2M) of the 4M-wide gmm1_in; its
@@ -879,7 +904,6 @@ class _Conv1:
         Bn, _, Hh, Ww = self.img_nchw.shape
         check(self.tr.lib.masic_nchw_to_nhwc_bf16(self.img_nchw.data_ptr(), Bn, 3, Hh, Ww, self.img16.data_ptr(), 16, 0, 0,
                                                   0, T._s()), "masic_nchw_to_nhwc_bf16")
-        self.wg_plan.launch()
-        self.dw.add_(self.dw16[:, :3])
+        self.tr.wg_async(lambda: (self.wg_plan.launch(), self.dw.add_(self.dw16[:, :3])))
         if self.dg_plan is not None:
             self.dg_plan.launch()
