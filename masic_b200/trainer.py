@@ -273,7 +273,7 @@ class HSICTrainer:
         self.lanes = os.environ.get("MASIC_TRAIN_LANES", "1") != "0"
         with torch.cuda.device(self.dev):
             self._wg_stream = torch.cuda.Stream(device=self.dev) if self.wg_overlap else None
-            self._lane_stream = torch.cuda.Stream(device=self.dev) if self.lanes else None
+            self._lane_streams: List[torch.cuda.Stream] = []
             self._build()
 
     # ------------------------------------------------------------------ helpers
@@ -812,54 +812,60 @@ class HSICTrainer:
             r = self.rd_out.tolist()
             return {"loss": r[7], "bpp": r[6], "mse": r[4] + r[5], "aux": float(self.aux_out)}
 
-    # Two lanes, like the inference engine's: the right view's own encoder chain (homography products, mask weights,
+    # Lanes, like the inference engine's: the right view's own encoder chain (homography products, mask weights,
     # pre_conv, encoder2, hyperprior 2, context 2) depends on nothing the left view computes, and its backward
     # (everything below R.mask_fuse that is not the second encoder1 pass) feeds nothing but weight gradients.  These ops
     # are issued on a second stream: forked from the main stream where the lane starts, joined where its results are
     # first read (forward: R.mask_fuse; backward: the final join).  Every buffer is allocated once per trainer and
     # written by one op only, so the two events per phase are the only ordering needed.
-    LANE1_FWD = frozenset(("warp.prepare", "mask_R", "mask2weights", "R.warp(x1)", "R.pre_conv", "R.pre_gdn", "R.pack",
-                           "R.encoder", "R.latent_prep", "R.hyper", "R.context"))
-    LANE1_BWD = frozenset(("mask2weights", "R.context", "R.hyper", "R.latent_merge", "R.encoder", "B.dimg", "pre_gdn",
-                           "pre_conv"))
-    # forward: the lane needs nothing from the main stream (fork at the start of the phase) and the main stream first
-    # reads one of its results (the prepared homography) in R.warp(x1_hat); backward: the lane's inputs are complete once
-    # R.mask_fuse has run, and only the final join reads what it wrote
-    FORK_FWD, JOIN_FWD = None, "R.warp(x1_hat)"
-    FORK_BWD, JOIN_BWD = "R.mask_fuse", "wgrad.join"
+    # (op names of the lane, fork after this main-stream op (None = start of the phase), join before this main-stream op)
+    FWD_LANES = ((frozenset(("warp.prepare", "mask_R", "mask2weights", "R.warp(x1)", "R.pre_conv", "R.pre_gdn", "R.pack",
+                            "R.encoder", "R.latent_prep", "R.hyper", "R.context")),
+                  None, "R.warp(x1_hat)"),)            # the main stream first reads the lane's prepared homography there
+    BWD_LANES = ((frozenset(("mask2weights", "R.context", "R.hyper", "R.latent_merge", "R.encoder", "B.dimg", "pre_gdn",
+                            "pre_conv")),
+                  "R.mask_fuse", "wgrad.join"),)       # inputs complete after R.mask_fuse; only weight gradients come out
+    # (measured and dropped: a third lane for L.gmm_net / L.context / L.hyper from the start of the backward pass,
+    # joined before L.latent_merge: 8.37 vs 8.28 ms — the lanes already keep the SMs busy)
 
-    def _run_lanes(self, ops, lane1, fork_after, join_before):
+    def _run_lanes(self, ops, lanes):
         if not self.lanes:
             for _, fn in ops:
                 fn()
             return
         main = torch.cuda.current_stream()
-        side = self._lane_stream
+        while len(self._lane_streams) < len(lanes):
+            self._lane_streams.append(torch.cuda.Stream(device=self.dev))
+        on_lane = frozenset().union(*[l[0] for l in lanes])
 
-        def fork():                                  # the lane sees everything issued on the main stream so far
+        def fork(i):                                 # the lane sees everything issued on the main stream so far
             ev = torch.cuda.Event()
             ev.record(main)
+            side = self._lane_streams[i]
             side.wait_event(ev)
             with torch.cuda.stream(side):
                 for name, fn in ops:
-                    if name in lane1:
+                    if name in lanes[i][0]:
                         fn()
 
-        joined = False
-        if fork_after is None:
-            fork()
+        joined = set()
+        for i, (_, fork_after, _) in enumerate(lanes):
+            if fork_after is None:
+                fork(i)
         for name, fn in ops:
-            if name in lane1:
+            if name in on_lane:
                 continue
-            if name == join_before:
-                ev = torch.cuda.Event()
-                ev.record(side)
-                main.wait_event(ev)
-                joined = True
+            for i, (_, _, join_before) in enumerate(lanes):
+                if name == join_before:
+                    ev = torch.cuda.Event()
+                    ev.record(self._lane_streams[i])
+                    main.wait_event(ev)
+                    joined.add(i)
             fn()
-            if name == fork_after:
-                fork()
-        assert joined, "lane never joined"
+            for i, (_, fork_after, _) in enumerate(lanes):
+                if name == fork_after:
+                    fork(i)
+        assert len(joined) == len(lanes), "a lane was never joined"
 
     def _issue(self, refresh: bool):
         self.flat_grad.zero_()
@@ -867,8 +873,8 @@ class HSICTrainer:
             t.zero_()
         if refresh:
             self.refresh_weights()
-        self._run_lanes(self.fwd_ops, self.LANE1_FWD, self.FORK_FWD, self.JOIN_FWD)
-        self._run_lanes(self.bwd_ops, self.LANE1_BWD, self.FORK_BWD, self.JOIN_BWD)
+        self._run_lanes(self.fwd_ops, self.FWD_LANES)
+        self._run_lanes(self.bwd_ops, self.BWD_LANES)
 
     def train_step(self, x1: torch.Tensor, x2: torch.Tensor, h_matrix: torch.Tensor, optimizer, aux_optimizer,
                    noise: Optional[Dict[str, torch.Tensor]] = None, group=None,
