@@ -781,7 +781,8 @@ class HSICTrainer:
 
     @torch.no_grad()
     def step_grads(self, x1: torch.Tensor, x2: torch.Tensor, h_matrix: torch.Tensor,
-                   noise: Optional[Dict[str, torch.Tensor]] = None, refresh: bool = True) -> Dict[str, float]:
+                   noise: Optional[Dict[str, torch.Tensor]] = None, refresh: bool = True,
+                   read_back: bool = True) -> Optional[Dict[str, float]]:
         """One forward + backward.  Fills `.grad` of every model parameter (views of `flat_grad`): the main loss's
         gradient everywhere, the aux loss's gradient on the bottleneck quantiles (as the reference's two optimisers
         see them).  noise: NCHW fp32 tensors keyed by NOISE_KEYS, or None to draw U(-.5,.5) on the device."""
@@ -809,8 +810,12 @@ class HSICTrainer:
                 self._warm = True
             for n, p in self._params.items():
                 p.grad = self._grads[n]
-            r = self.rd_out.tolist()
-            return {"loss": r[7], "bpp": r[6], "mse": r[4] + r[5], "aux": float(self.aux_out)}
+            return self.read_losses() if read_back else None
+
+    def read_losses(self) -> Dict[str, float]:
+        """Loss terms of the last step (one device -> host read; synchronises with the step)."""
+        r = torch.cat([self.rd_out, self.aux_out]).tolist()
+        return {"loss": r[7], "bpp": r[6], "mse": r[4] + r[5], "aux": r[8]}
 
     # Lanes, like the inference engine's: the right view's own encoder chain (homography products, mask weights,
     # pre_conv, encoder2, hyperprior 2, context 2) depends on nothing the left view computes, and its backward
@@ -885,12 +890,17 @@ class HSICTrainer:
         (MASIC.py:77-94).  The gradients live in ONE flat fp32 buffer, so the all-reduce is a single NCCL call over
         NVLink/NVSwitch (35 M floats = 140 MB); nothing else is communicated."""
         import torch.distributed as dist
-        res = self.step_grads(x1, x2, h_matrix, noise=noise)
+        # the loss scalars are read back AFTER the optimisers are enqueued: the host does not wait for the step's graph
+        # before it launches the all-reduce and the two Adam steps
+        self.step_grads(x1, x2, h_matrix, noise=noise, read_back=False)
         if dist.is_available() and dist.is_initialized():
             world = dist.get_world_size(group)
             if world > 1:
-                dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=group)
-                self.flat_grad.mul_(1.0 / world)
+                if dist.get_backend(group) == "nccl":                 # the mean is taken inside the collective
+                    dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG, group=group)
+                else:
+                    dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=group)
+                    self.flat_grad.mul_(1.0 / world)
         if clip_max_norm is not None and clip_max_norm > 0:
             # torch.nn.utils.clip_grad_norm_(model.parameters(), clip_max_norm) of CompressAI's training loops, on the
             # flat buffer: the main parameters' gradients (everything but the two bottlenecks, MASIC.py:77-94)
@@ -902,7 +912,7 @@ class HSICTrainer:
             torch._foreach_mul_(self._main_grads, coef)
         optimizer.step()
         aux_optimizer.step()
-        return res
+        return self.read_losses()
 
     def profile(self, iters: int = 3):
         """CUDA-event time of every forward / backward op group (after one warm step)."""
