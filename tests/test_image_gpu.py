@@ -83,6 +83,38 @@ def test_warp_against_oracle(dev, h, w):
     assert (ident.cpu() - img).abs().max() <= 1e-5
 
 
+def test_fast_warp_is_bit_identical_to_the_generic_kernel_and_fused_mask(dev):
+    """warp_fast_kernel (the engine's configurations: 3 / 1 channels) must reproduce warp_kernel bit for bit — a 4-channel
+    image takes the generic kernel, its first three planes are the 3-channel image — and masic_warp_perspective_fwd3
+    writes the warp of the all-ones image (x1_mask_R, MASIC.py:636-638) from the same launch, equal to the separate
+    ones-warp; ragged widths (not a multiple of the 256 pixels a block covers), border pixels included."""
+    from masic_b200 import _lib, ops
+    from oracle import hsic as OH
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(11)
+    for h, w in ((128, 192), (200, 328), (64, 1000)):
+        img = torch.rand(2, 3, h, w, generator=g).to(dev)
+        Hm = OH.synthetic_homography(2, seed=3).to(dev)
+        img4 = torch.cat([img, img[:, :1]], dim=1).contiguous()
+        fast = ops.warp_perspective(img, Hm, (h, w))
+        generic = ops.warp_perspective(img4, Hm, (h, w))
+        assert torch.equal(fast, generic[:, :3]), (h, w)
+        ones_sep = ops.warp_perspective(None, Hm, (h, w), ones_shape=(2, 1, h, w))
+        T = ops.warp_prepare(Hm, (h, w), (h, w), False)
+        out = torch.empty_like(img)
+        ones = torch.empty(2, 1, h, w, device=dev)
+        s = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.masic_warp_perspective_fwd3(img.data_ptr(), 2, 3, h, w, h, w, T.data_ptr(), out.data_ptr(), None, 0, 0, 0,
+                                                   0, None, 0, 0, 0, 0, 0, ones.data_ptr(), s), "masic_warp_perspective_fwd3")
+        assert torch.equal(out, fast) and torch.equal(ones, ones_sep), (h, w)
+        # the generic kernel's form of the same call (4 channels): the mask comes from a second launch
+        out4 = torch.empty_like(img4)
+        ones4 = torch.empty(2, 1, h, w, device=dev)
+        _lib.check(lib.masic_warp_perspective_fwd3(img4.data_ptr(), 2, 4, h, w, h, w, T.data_ptr(), out4.data_ptr(), None, 0, 0,
+                                                   0, 0, None, 0, 0, 0, 0, 0, ones4.data_ptr(), s), "masic_warp_perspective_fwd3")
+        assert torch.equal(out4, generic) and torch.equal(ones4, ones_sep), (h, w)
+
+
 def test_small_convs_against_torch(dev):
     from masic_b200 import ops
     from masic_b200.ops import ACT_RELU, GDN_FWD
