@@ -964,7 +964,7 @@ class HSICTrainer:
         if nccl and self.use_graph and os.environ.get("MASIC_TRAIN_BUCKETS", "0") != "0":
             # opt-in (MASIC_TRAIN_BUCKETS=1): two buckets, the early-final half of the gradients averaged while the rest of
             # the backward pass runs.  Correct (tools/train_bucket_check.py: every rank ends with identical parameters)
-            # but not faster on two GPUs: 8.48 against 8.38 ms per step — splitting the graph joins the weight-gradient
+            # but not faster: 8.48 against 8.38 ms per step on two GPUs, 8.69 against 8.58 on eight — splitting the graph joins the weight-gradient
             # stream and the lane mid-way, and the collective's CTAs compete with persistent kernels for SMs
             h0, h1 = self._step_grads_bucketed(
                 x1, x2, h_matrix, noise,
