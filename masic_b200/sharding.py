@@ -86,6 +86,39 @@ def evaluate_sharded(n_pairs: int, load_pair: Callable[[int], tuple], run_pair: 
     return gather_pair_results(local, n_pairs, width, group=group, device=device)
 
 
+class _MeanWork:
+    """Handle of all_reduce_mean_: wait() blocks (stream-side on NCCL) until the buffer holds the mean."""
+
+    def __init__(self, work, tensor: Optional[torch.Tensor], scale: float):
+        self._work, self._t, self._scale = work, tensor, scale
+
+    def wait(self):
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        if self._t is not None:                      # backends without ReduceOp.AVG: sum, then scale
+            self._t.mul_(self._scale)
+            self._t = None
+
+
+def all_reduce_mean_(t: torch.Tensor, group=None, async_op: bool = False) -> _MeanWork:
+    """In-place mean of `t` over the ranks of `group` — the ONE collective of the data-parallel training step
+    (HSICTrainer.train_step: the flat fp32 gradient buffer, or a contiguous slice of it).  NCCL takes the mean inside the
+    collective (ReduceOp.AVG); other backends sum and scale.  Always returns a handle; with async_op=False it has
+    already completed."""
+    _, world = _world(group)
+    if world == 1:
+        return _MeanWork(None, None, 1.0)
+    if dist.get_backend(group) == "nccl":
+        w = dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
+        return _MeanWork(w if async_op else None, None, 1.0)
+    w = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    h = _MeanWork(w if async_op else None, t, 1.0 / world)
+    if not async_op:
+        h.wait()
+    return h
+
+
 class GradBuckets:
     """Flat fp32 gradient buckets for the data-parallel all-reduce.
 

@@ -959,26 +959,22 @@ class HSICTrainer:
         import torch.distributed as dist
         # the loss scalars are read back AFTER the optimisers are enqueued: the host does not wait for the step's graph
         # before it launches the all-reduce and the two Adam steps
+        from .sharding import all_reduce_mean_
         world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         nccl = world > 1 and dist.get_backend(group) == "nccl"
         if nccl and self.use_graph and os.environ.get("MASIC_TRAIN_BUCKETS", "0") != "0":
             # opt-in (MASIC_TRAIN_BUCKETS=1): two buckets, the early-final half of the gradients averaged while the rest of
             # the backward pass runs.  Correct (tools/train_bucket_check.py: every rank ends with identical parameters)
-            # but not faster: 8.48 against 8.38 ms per step on two GPUs, 8.69 against 8.58 on eight — splitting the graph joins the weight-gradient
-            # stream and the lane mid-way, and the collective's CTAs compete with persistent kernels for SMs
-            h0, h1 = self._step_grads_bucketed(
-                x1, x2, h_matrix, noise,
-                lambda t: dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group, async_op=True))
+            # but not faster: 8.48 against 8.38 ms per step on two GPUs, 8.69 against 8.58 on eight — splitting the graph
+            # joins the weight-gradient stream and the lane mid-way, and the collective's CTAs compete with persistent
+            # kernels for SMs
+            h0, h1 = self._step_grads_bucketed(x1, x2, h_matrix, noise,
+                                               lambda t: all_reduce_mean_(t, group=group, async_op=True))
             h0.wait()                                                 # stream-side waits: the host does not block
             h1.wait()
         else:
             self.step_grads(x1, x2, h_matrix, noise=noise, read_back=False)
-            if world > 1:
-                if nccl:                                              # the mean is taken inside the collective
-                    dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG, group=group)
-                else:
-                    dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=group)
-                    self.flat_grad.mul_(1.0 / world)
+            all_reduce_mean_(self.flat_grad, group=group)             # one collective; no-op on a single rank
         if clip_max_norm is not None and clip_max_norm > 0:
             # torch.nn.utils.clip_grad_norm_(model.parameters(), clip_max_norm) of CompressAI's training loops, on the
             # flat buffer: the main parameters' gradients (everything but the two bottlenecks, MASIC.py:77-94)

@@ -132,3 +132,39 @@ def test_grad_buckets_single_process_is_identity():
     GradBuckets(net.parameters()).allreduce_()
     for a, p in zip(before, net.parameters()):
         assert torch.equal(a, p.grad)
+
+
+def _w_mean(rank, world, tmp):
+    from masic_b200.sharding import all_reduce_mean_
+    g = torch.Generator().manual_seed(40 + rank)
+    flat = torch.rand(1000, generator=g)
+    # the training step's two forms: the whole flat gradient buffer at once, or a prefix started asynchronously
+    # (while the rest of the backward pass would run) and the suffix afterwards
+    whole = flat.clone()
+    assert all_reduce_mean_(whole) is not None
+    split = flat.clone()
+    h0 = all_reduce_mean_(split[:512], async_op=True)
+    h1 = all_reduce_mean_(split[512:], async_op=True)
+    h0.wait(); h1.wait()
+    h0.wait()                                                    # idempotent
+    # (three or more ranks: the backend may add the ranks' values in another order for another buffer size)
+    assert torch.allclose(whole, split, rtol=1e-6, atol=1e-7)
+    if rank == 0:
+        torch.save(whole, tmp)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_all_reduce_mean_whole_and_split_buffer(world, tmp_path):
+    """HSICTrainer.train_step's collective (sharding.all_reduce_mean_): the mean over the ranks, in place, identical
+    whether the flat buffer is reduced at once or as an asynchronous prefix + suffix (MASIC_TRAIN_BUCKETS=1)."""
+    f = str(tmp_path / "m.pt")
+    _spawn(_w_mean, world, f)
+    want = torch.stack([torch.rand(1000, generator=torch.Generator().manual_seed(40 + r)) for r in range(world)]).mean(0)
+    assert torch.allclose(torch.load(f), want, rtol=1e-6, atol=1e-7)
+
+
+def test_all_reduce_mean_single_process_is_identity():
+    from masic_b200.sharding import all_reduce_mean_
+    t = torch.arange(8.0)
+    all_reduce_mean_(t).wait()
+    assert torch.equal(t, torch.arange(8.0))
